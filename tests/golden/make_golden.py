@@ -108,7 +108,6 @@ def build_synth_case(out_dir, seed=11, n_pairs=900, read_len=100, asize=15, erro
         g, J, n_pairs, read_len=read_len, asize=asize, seed=seed + 2, error_rate=error_rate,
         frac_decoy=0.12, frac_nonuniq=0.06, frac_edge=0.04, frac_inner_shift=0.2, frac_read_n=0.03, frac_no_xs=0.1,
     )
-    g.write_fasta(os.path.join(out_dir, "genome.fa"))
     rng = np.random.default_rng(seed + 3)
     lines = []  # list of per-fragment record lists, shuffled at the end (fragments stay contiguous)
 
@@ -122,6 +121,7 @@ def build_synth_case(out_dir, seed=11, n_pairs=900, read_len=100, asize=15, erro
     if paired_extra:
         lines += complex_fragments(g, J, rng, read_len, asize)
 
+    g.write_fasta(os.path.join(out_dir, "genome.fa"))  # after the last planting
     order = rng.permutation(len(lines))
     with open(os.path.join(out_dir, "input.sam"), "w") as fh:
         fh.write(synth.sam_header(g))
@@ -271,9 +271,10 @@ def ambiguous_fragments(g, rng, R):
     for rep in range(4):
         s = 3000 + rep * 2500
         e = s + 800 + rep * 50
-        # donor side: exon ... | GTAGGT ; acceptor side: AGGTAG | exon ...   (0-based: seq[e:e+6], seq[s-6:s])
+        # donor side: exon | GTAGGT ; acceptor side: AG | GTAG exon   (0-based: seq[e:e+6], seq[s-2:s+4]):
+        # the split x (true) and x+4 both show GT/AG and the 4 read bases in between match either flank
         seq[e : e + 6] = np.frombuffer(b"GTAGGT", dtype=np.uint8)
-        seq[s - 6 : s] = np.frombuffer(b"AGGTAG", dtype=np.uint8)
+        seq[s - 2 : s + 4] = np.frombuffer(b"AGGTAG", dtype=np.uint8)
         j = 40 + rep
         read = synth.genome_slice(g, g.names[c], e - j, e) + synth.genome_slice(g, g.names[c], s, s + R - j)
         segs = [synth.Seg(g.names[c], e - j, 0, j), synth.Seg(g.names[c], s, j, R)]
