@@ -1,0 +1,625 @@
+// agg.cu -- junction aggregation on the device.
+//
+// Replaces SpliceSiteStorage.add / Hit.add and the Hit reductions (/root/reference/find_circ.py:486-600, 657-690):
+// instead of one Python dict insert + list appends per accepted span, accepted spans become 48-byte records
+// (fc_jrec); fc_agg_finalize() sorts them by a 64-bit hash of (chrom,start,end,strand,kind) with a stable CUB radix
+// sort (input order = stream order is preserved inside a junction), verifies that equal hashes mean equal keys,
+// and reduces every run:
+//     n_spanned            count                                                   (:543)
+//     n_weighted           sum of weights, exact: weights 1/den with den a power of two are order independent;
+//                          junctions holding any other denominator are re-summed sequentially in stream order (:544)
+//     n_uniq_bridges       same, over records with both anchor qualities non-zero  (:561-563)
+//     best_qual_left/right max                                                     (:592-593)
+//     edits/overlap/n_hits min                                                     (:727)
+//     first idx            min  -> discovery order -> junction name                (:684-686)
+//     n_frags              distinct qname hashes                                   (:584-586)
+//     n_uniq               distinct strand-invariant read hashes (palindromes count half, :588-590)
+#include <cub/cub.cuh>
+
+#include "fc_internal.cuh"
+
+namespace {
+
+struct JAcc {  // per-junction accumulators filled with integer atomics (deterministic)
+  unsigned int n_spanned;
+  unsigned int cw[4];  // records with weight denominator 1,2,4,8
+  unsigned int cw_other;
+  unsigned int cb[4];  // same, restricted to unique bridges
+  unsigned int cb_other;
+  int max_ql, max_qr;
+  unsigned int min_dist, min_ov, min_nh;
+  unsigned int n_frags, n_uniq, n_pal;
+  unsigned long long first_idx;
+  unsigned int seg_start;  // index of the first sorted record
+  unsigned int pad;
+};
+
+__global__ void count_hits_kernel(int64_t n, const fc_hit* __restrict__ hits, uint32_t* __restrict__ accept) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  accept[i] = (hits[i].w2 & 0xFFFFu) ? 1u : 0u;
+}
+
+__global__ void emit_kernel(int64_t n, const fc_hit* __restrict__ hits, const uint32_t* __restrict__ pos,
+                            const int32_t* __restrict__ chrom, const uint8_t* __restrict__ flags,
+                            const uint8_t* __restrict__ wden, const int16_t* __restrict__ q_a,
+                            const int16_t* __restrict__ q_b, const uint64_t* __restrict__ read_hash,
+                            const uint64_t* __restrict__ qname_hash, uint64_t idx_base,
+                            const unsigned long long* __restrict__ n_recs, fc_jrec* __restrict__ recs) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fc_hit h = hits[i];
+  if ((h.w2 & 0xFFFFu) == 0) return;
+  uint32_t fl = flags[i];
+  bool backsplice = fl & FC_PF_BACKSPLICE;
+  fc_jrec r;
+  r.chrom = (uint32_t)chrom[i];
+  r.start = (uint32_t)h.start;
+  r.end = (uint32_t)h.end;
+  uint32_t strand = h.w3 & 1u, sig = (h.w3 >> 1) & 0xFFFu;
+  uint64_t rh = read_hash[i];
+  r.sk = strand | (backsplice ? 0u : 2u) | ((uint32_t)(rh & 1ull) << 2) | ((uint32_t)wden[i] << 8) | (sig << 16);
+  r.idx = idx_base + (uint64_t)i;
+  r.read_hash = rh;
+  r.qname_hash = qname_hash[i];
+  // by convention A precedes B in the genome: swap for back-splices (find_circ.py:552-553)
+  r.q_left = backsplice ? q_b[i] : q_a[i];
+  r.q_right = backsplice ? q_a[i] : q_b[i];
+  r.n_hits = (uint16_t)(h.w2 & 0xFFFFu);
+  r.dist = (uint8_t)((h.w2 >> 16) & 0xFFu);
+  r.ov = (uint8_t)(h.w2 >> 24);
+  recs[*n_recs + pos[i]] = r;
+}
+
+__global__ void bump_kernel(unsigned long long* n_recs, const uint32_t* __restrict__ pos,
+                            const uint32_t* __restrict__ accept, int64_t n) {
+  *n_recs += (unsigned long long)pos[n - 1] + accept[n - 1];
+}
+
+__global__ void key_hash_kernel(int64_t n, const fc_jrec* __restrict__ recs, uint64_t seed, uint64_t* __restrict__ h,
+                                uint32_t* __restrict__ iota) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const fc_jrec& r = recs[i];
+  h[i] = fc_key_hash(r.chrom, r.start, r.end, r.sk, seed);
+  iota[i] = (uint32_t)i;
+}
+
+__global__ void gather_kernel(int64_t n, const fc_jrec* __restrict__ recs, const uint32_t* __restrict__ perm,
+                              fc_jrec* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint4* src = reinterpret_cast<const uint4*>(recs + perm[i]);
+  uint4* dst = reinterpret_cast<uint4*>(out + i);
+  dst[0] = src[0];
+  dst[1] = src[1];
+  dst[2] = src[2];
+}
+
+__device__ inline bool same_key(const fc_jrec& a, const fc_jrec& b) {
+  return a.chrom == b.chrom && a.start == b.start && a.end == b.end && ((a.sk ^ b.sk) & 3u) == 0;
+}
+
+// head[i] = 1 when sorted record i starts a new junction; counts hash collisions (equal hash, different key)
+__global__ void heads_kernel(int64_t n, const fc_jrec* __restrict__ s, const uint64_t* __restrict__ h_sorted,
+                             uint32_t* __restrict__ head, unsigned long long* __restrict__ collisions) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t hd = 1;
+  if (i > 0) {
+    bool same_h = h_sorted[i] == h_sorted[i - 1];
+    bool same_k = same_key(s[i], s[i - 1]);
+    if (same_h && !same_k) atomicAdd(collisions, 1ull);
+    hd = same_k ? 0u : 1u;
+  }
+  head[i] = hd;
+}
+
+__global__ void acc_init_kernel(int64_t nj, JAcc* __restrict__ acc) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nj) return;
+  JAcc a;
+  a.n_spanned = 0;
+  for (int k = 0; k < 4; ++k) a.cw[k] = a.cb[k] = 0;
+  a.cw_other = a.cb_other = 0;
+  a.max_ql = a.max_qr = -2147483647 - 1;
+  a.min_dist = a.min_ov = a.min_nh = 0xFFFFFFFFu;
+  a.n_frags = a.n_uniq = a.n_pal = 0;
+  a.first_idx = ~0ull;
+  a.seg_start = 0;
+  a.pad = 0;
+  acc[j] = a;
+}
+
+// one thread per sorted record; lanes of a warp that share a junction are combined before the atomics
+__global__ void reduce_kernel(int64_t n, const fc_jrec* __restrict__ s, const uint32_t* __restrict__ seg_incl,
+                              const uint32_t* __restrict__ head, JAcc* __restrict__ acc) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool active = i < n;
+  uint32_t seg = active ? seg_incl[i] - 1u : 0xFFFFFFFFu;
+  unsigned amask = __ballot_sync(0xffffffffu, active);
+  if (!active) return;
+  fc_jrec r = s[i];
+  if (head[i]) acc[seg].seg_start = (unsigned int)i;
+  unsigned peers = __match_any_sync(amask, seg);
+  int lane = threadIdx.x & 31;
+  int leader = __ffs((int)peers) - 1;
+  uint32_t den = (r.sk >> 8) & 0xFFu;
+  int cls = den == 1 ? 0 : den == 2 ? 1 : den == 4 ? 2 : den == 8 ? 3 : 4;
+  bool bridge = r.q_left != 0 && r.q_right != 0;
+  // peers are contiguous lanes (records are sorted by junction): reduce with shuffles over the peer group
+  unsigned cnt = __popc(peers);
+  unsigned cw[5], cb[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    cw[k] = __popc(__ballot_sync(amask, cls == k) & peers);
+    cb[k] = __popc(__ballot_sync(amask, cls == k && bridge) & peers);
+  }
+  int ql = r.q_left, qr = r.q_right;
+  unsigned md = r.dist, mo = r.ov, mh = r.n_hits;
+  unsigned long long fi = r.idx;
+  // segmented butterfly inside the peer group
+  int hi_lane = 31 - __clz((int)peers);
+  for (int o = 1; o < 32; o <<= 1) {
+    int src = lane + o;
+    int ql2 = __shfl_down_sync(amask, ql, o);
+    int qr2 = __shfl_down_sync(amask, qr, o);
+    unsigned md2 = __shfl_down_sync(amask, md, o);
+    unsigned mo2 = __shfl_down_sync(amask, mo, o);
+    unsigned mh2 = __shfl_down_sync(amask, mh, o);
+    unsigned long long fi2 = __shfl_down_sync(amask, fi, o);
+    if (src <= hi_lane && ((peers >> src) & 1u)) {
+      ql = max(ql, ql2);
+      qr = max(qr, qr2);
+      md = min(md, md2);
+      mo = min(mo, mo2);
+      mh = min(mh, mh2);
+      fi = fi < fi2 ? fi : fi2;
+    }
+  }
+  if (lane == leader) {
+    JAcc* a = acc + seg;
+    atomicAdd(&a->n_spanned, cnt);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (cw[k]) atomicAdd(&a->cw[k], cw[k]);
+      if (cb[k]) atomicAdd(&a->cb[k], cb[k]);
+    }
+    if (cw[4]) atomicAdd(&a->cw_other, cw[4]);
+    if (cb[4]) atomicAdd(&a->cb_other, cb[4]);
+    atomicMax(&a->max_ql, ql);
+    atomicMax(&a->max_qr, qr);
+    atomicMin(&a->min_dist, md);
+    atomicMin(&a->min_ov, mo);
+    atomicMin(&a->min_nh, mh);
+    atomicMin(&a->first_idx, fi);
+  }
+}
+
+// (hash, seg) pairs for the two distinct counts
+__global__ void split_hash_kernel(int64_t n, const fc_jrec* __restrict__ s, const uint32_t* __restrict__ seg_incl,
+                                  uint64_t* __restrict__ rh, uint64_t* __restrict__ qh, uint32_t* __restrict__ seg) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  rh[i] = s[i].read_hash;
+  qh[i] = s[i].qname_hash;
+  seg[i] = seg_incl[i] - 1u;
+}
+
+// after sorting by (seg, hash): count the first element of every (seg, hash) run
+__global__ void distinct_kernel(int64_t n, const uint32_t* __restrict__ seg, const uint64_t* __restrict__ h, int which,
+                                JAcc* __restrict__ acc) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bool first = i == 0 || seg[i] != seg[i - 1] || h[i] != h[i - 1];
+  if (!first) return;
+  JAcc* a = acc + seg[i];
+  if (which == 0) {
+    atomicAdd(&a->n_uniq, 1u);
+    if (h[i] & 1ull) atomicAdd(&a->n_pal, 1u);
+  } else {
+    atomicAdd(&a->n_frags, 1u);
+  }
+}
+
+__global__ void finish_kernel(int64_t nj, int64_t n, const JAcc* __restrict__ acc, const fc_jrec* __restrict__ s,
+                              fc_junction* __restrict__ out, uint64_t* __restrict__ order_key,
+                              uint32_t* __restrict__ order_val) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nj) return;
+  JAcc a = acc[j];
+  const fc_jrec& r0 = s[a.seg_start];
+  fc_junction o;
+  o.chrom = r0.chrom;
+  o.start = r0.start;
+  o.end = r0.end;
+  o.first_idx = a.first_idx;
+  double w, b;
+  uint32_t last_sk = r0.sk;
+  if (a.cw_other == 0) {
+    // every weight is k/8: any summation order gives this exact value
+    w = (8.0 * a.cw[0] + 4.0 * a.cw[1] + 2.0 * a.cw[2] + 1.0 * a.cw[3]) / 8.0;
+    b = (8.0 * a.cb[0] + 4.0 * a.cb[1] + 2.0 * a.cb[2] + 1.0 * a.cb[3]) / 8.0;
+    last_sk = s[a.seg_start + a.n_spanned - 1].sk;
+  } else {
+    // replay in stream order, exactly as `self.n_weighted += weight` does (find_circ.py:544, 563)
+    w = 0.0;
+    b = 0.0;
+    for (unsigned k = 0; k < a.n_spanned; ++k) {
+      const fc_jrec& r = s[a.seg_start + k];
+      double wt = 1.0 / (double)((r.sk >> 8) & 0xFFu);
+      w += wt;
+      if (r.q_left != 0 && r.q_right != 0) b += wt;
+      last_sk = r.sk;
+    }
+  }
+  o.sk = (r0.sk & 3u) | (last_sk & 0x0FFF0000u);  // signal of the LAST added splice (find_circ.py:528)
+  o.n_weighted = w;
+  o.n_uniq_bridges = b;
+  o.n_spanned = a.n_spanned;
+  o.n_frags = a.n_frags;
+  // len(uniq)/2 with uniq = {read, revcomp(read)}: a palindromic read contributes one element, not two
+  o.n_uniq = a.n_uniq - (a.n_pal + 1) / 2;
+  o.best_q_left = (int16_t)a.max_ql;
+  o.best_q_right = (int16_t)a.max_qr;
+  o.min_n_hits = (uint16_t)a.min_nh;
+  o.min_dist = (uint8_t)a.min_dist;
+  o.min_ov = (uint8_t)a.min_ov;
+  o.pad = 0;
+  out[j] = o;
+  order_key[j] = a.first_idx;
+  order_val[j] = (uint32_t)j;
+}
+
+__global__ void gather_junctions_kernel(int64_t nj, const fc_junction* __restrict__ in, const uint32_t* __restrict__ perm,
+                                        fc_junction* __restrict__ out) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nj) return;
+  const uint4* src = reinterpret_cast<const uint4*>(in + perm[j]);
+  uint4* dst = reinterpret_cast<uint4*>(out + j);
+  dst[0] = src[0];
+  dst[1] = src[1];
+  dst[2] = src[2];
+  dst[3] = src[3];
+}
+
+__global__ void dest_rank_kernel(int64_t n, const fc_jrec* __restrict__ recs, int32_t n_ranks, uint64_t* __restrict__ key,
+                                 uint32_t* __restrict__ iota) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const fc_jrec& r = recs[i];
+  key[i] = fc_key_hash(r.chrom, r.start, r.end, r.sk, 0x5bd1e995ULL) % (uint64_t)n_ranks;
+  iota[i] = (uint32_t)i;
+}
+
+__global__ void rank_hist_kernel(int64_t n, const uint64_t* __restrict__ key_sorted, unsigned long long* __restrict__ counts) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // boundaries of the sorted destination array
+  if (i == 0 || key_sorted[i] != key_sorted[i - 1]) {
+    // start of rank key_sorted[i]; store start offsets, converted to counts on the host
+    counts[key_sorted[i]] = (unsigned long long)i;
+  }
+}
+
+inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+int sort_pairs_u64_u32(fc_ctx* ctx, int64_t n, uint64_t* k_in, uint64_t* k_out, uint32_t* v_in, uint32_t* v_out,
+                       int begin_bit, int end_bit, cudaStream_t st) {
+  size_t tmp = 0;
+  FC_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, v_in, v_out, n, begin_bit, end_bit, st));
+  FC_CUDA(ctx, ctx->agg.cub_tmp.reserve(tmp, st, false, 0));
+  FC_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->agg.cub_tmp.p, tmp, k_in, k_out, v_in, v_out, n, begin_bit, end_bit, st));
+  ctx->launches += 1 + (end_bit - begin_bit + 7) / 8;
+  return FC_OK;
+}
+int sort_pairs_u32_u64(fc_ctx* ctx, int64_t n, uint32_t* k_in, uint32_t* k_out, uint64_t* v_in, uint64_t* v_out,
+                       int begin_bit, int end_bit, cudaStream_t st) {
+  size_t tmp = 0;
+  FC_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, v_in, v_out, n, begin_bit, end_bit, st));
+  FC_CUDA(ctx, ctx->agg.cub_tmp.reserve(tmp, st, false, 0));
+  FC_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->agg.cub_tmp.p, tmp, k_in, k_out, v_in, v_out, n, begin_bit, end_bit, st));
+  ctx->launches += 1 + (end_bit - begin_bit + 7) / 8;
+  return FC_OK;
+}
+int scan_u32(fc_ctx* ctx, int64_t n, const uint32_t* in, uint32_t* out, bool inclusive, cudaStream_t st) {
+  size_t tmp = 0;
+  if (inclusive) {
+    FC_CUDA(ctx, cub::DeviceScan::InclusiveSum(nullptr, tmp, in, out, n, st));
+    FC_CUDA(ctx, ctx->agg.cub_tmp.reserve(tmp, st, false, 0));
+    FC_CUDA(ctx, cub::DeviceScan::InclusiveSum(ctx->agg.cub_tmp.p, tmp, in, out, n, st));
+  } else {
+    FC_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, n, st));
+    FC_CUDA(ctx, ctx->agg.cub_tmp.reserve(tmp, st, false, 0));
+    FC_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->agg.cub_tmp.p, tmp, in, out, n, st));
+  }
+  ctx->launches += 2;
+  return FC_OK;
+}
+
+int ensure_counters(fc_ctx* ctx, cudaStream_t st) {
+  if (!ctx->agg.counters.p) {
+    FC_CUDA(ctx, ctx->agg.counters.reserve(64 * sizeof(unsigned long long), st, false, 0));
+    FC_CUDA(ctx, cudaMemsetAsync(ctx->agg.counters.p, 0, 64 * sizeof(unsigned long long), st));
+  }
+  return FC_OK;
+}
+
+int sync_n_recs(fc_ctx* ctx, cudaStream_t st) {
+  if (!ctx->agg.counters.p) {
+    ctx->agg.n_recs = 0;
+    return FC_OK;
+  }
+  unsigned long long v = 0;
+  FC_CUDA(ctx, cudaMemcpyAsync(&v, ctx->agg.counters.p, sizeof(v), cudaMemcpyDeviceToHost, st));
+  FC_CUDA(ctx, cudaStreamSynchronize(st));
+  ctx->agg.n_recs = (int64_t)v;
+  return FC_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ fc_dbuf
+cudaError_t fc_dbuf::reserve(size_t bytes, cudaStream_t st, bool keep, size_t used) {
+  if (bytes <= cap) return cudaSuccess;
+  size_t ncap = cap ? cap : 4096;
+  while (ncap < bytes) ncap = ncap + ncap / 2 + 4096;
+  void* np = nullptr;
+  cudaError_t e = cudaMalloc(&np, ncap);
+  if (e != cudaSuccess) return e;
+  if (p) {
+    if (keep && used) {
+      e = cudaMemcpyAsync(np, p, used, cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) return e;
+    }
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return e;
+    cudaFree(p);
+  }
+  p = np;
+  cap = ncap;
+  return cudaSuccess;
+}
+void fc_dbuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+}
+
+// ------------------------------------------------------------------------------------------------ C ABI
+extern "C" int fc_agg_reset(fc_ctx* ctx) {
+  if (!ctx) return FC_E_ARG;
+  ctx->agg.n_recs = 0;
+  ctx->agg.n_junc = -1;
+  if (ctx->agg.counters.p) FC_CUDA(ctx, cudaMemset(ctx->agg.counters.p, 0, 64 * sizeof(unsigned long long)));
+  return FC_OK;
+}
+
+extern "C" int fc_agg_emit(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, const int32_t* d_chrom, const uint8_t* d_flags,
+                           const uint8_t* d_wden, const int16_t* d_q_a, const int16_t* d_q_b,
+                           const uint64_t* d_read_hash, const uint64_t* d_qname_hash, uint64_t idx_base, void* stream) {
+  if (!ctx || n < 0) return FC_E_ARG;
+  if (n == 0) return FC_OK;
+  if (n >= (1ll << 32)) return fc_fail(ctx, FC_E_ARG, "batch too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  fc_agg& a = ctx->agg;
+  int rc = ensure_counters(ctx, st);
+  if (rc) return rc;
+  // upper bound of the record count so far (the exact count lives on the device)
+  int64_t ub = a.n_recs + n;
+  FC_CUDA(ctx, a.recs.reserve((size_t)ub * sizeof(fc_jrec), st, true, (size_t)a.n_recs * sizeof(fc_jrec)));
+  FC_CUDA(ctx, a.scratch[0].reserve((size_t)n * 4, st, false, 0));
+  FC_CUDA(ctx, a.scratch[1].reserve((size_t)n * 4, st, false, 0));
+  uint32_t* accept = (uint32_t*)a.scratch[0].p;
+  uint32_t* pos = (uint32_t*)a.scratch[1].p;
+  count_hits_kernel<<<nblk(n, 256), 256, 0, st>>>(n, d_hits, accept);
+  FC_LAUNCH_CHECK(ctx);
+  rc = scan_u32(ctx, n, accept, pos, false, st);
+  if (rc) return rc;
+  emit_kernel<<<nblk(n, 256), 256, 0, st>>>(n, d_hits, pos, d_chrom, d_flags, d_wden, d_q_a, d_q_b, d_read_hash,
+                                            d_qname_hash, idx_base, (const unsigned long long*)a.counters.p,
+                                            (fc_jrec*)a.recs.p);
+  FC_LAUNCH_CHECK(ctx);
+  bump_kernel<<<1, 1, 0, st>>>((unsigned long long*)a.counters.p, pos, accept, n);
+  FC_LAUNCH_CHECK(ctx);
+  a.n_recs = ub;  // upper bound until the next sync
+  a.n_junc = -1;
+  return FC_OK;
+}
+
+extern "C" int fc_agg_append(fc_ctx* ctx, int64_t n, const fc_jrec* d_recs, void* stream) {
+  if (!ctx || n < 0) return FC_E_ARG;
+  if (n == 0) return FC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  fc_agg& a = ctx->agg;
+  int rc = ensure_counters(ctx, st);
+  if (rc) return rc;
+  rc = sync_n_recs(ctx, st);
+  if (rc) return rc;
+  FC_CUDA(ctx, a.recs.reserve((size_t)(a.n_recs + n) * sizeof(fc_jrec), st, true, (size_t)a.n_recs * sizeof(fc_jrec)));
+  FC_CUDA(ctx, cudaMemcpyAsync((fc_jrec*)a.recs.p + a.n_recs, d_recs, (size_t)n * sizeof(fc_jrec), cudaMemcpyDefault, st));
+  a.n_recs += n;
+  unsigned long long v = (unsigned long long)a.n_recs;
+  FC_CUDA(ctx, cudaMemcpyAsync(a.counters.p, &v, sizeof(v), cudaMemcpyHostToDevice, st));
+  FC_CUDA(ctx, cudaStreamSynchronize(st));
+  a.n_junc = -1;
+  return FC_OK;
+}
+
+extern "C" int fc_agg_append_host(fc_ctx* ctx, int64_t n, const fc_jrec* h_recs) {
+  if (!ctx) return FC_E_ARG;
+  return fc_agg_append(ctx, n, h_recs, ctx->own_stream);
+}
+
+extern "C" int64_t fc_agg_n_records(fc_ctx* ctx) {
+  if (!ctx) return FC_E_ARG;
+  int rc = sync_n_recs(ctx, ctx->own_stream);
+  if (rc) return rc;
+  // the record buffer may be in use on another stream: make sure everything has landed
+  cudaDeviceSynchronize();
+  rc = sync_n_recs(ctx, ctx->own_stream);
+  if (rc) return rc;
+  return ctx->agg.n_recs;
+}
+
+extern "C" const fc_jrec* fc_agg_records(fc_ctx* ctx) { return ctx ? (const fc_jrec*)ctx->agg.recs.p : nullptr; }
+
+extern "C" int fc_agg_partition(fc_ctx* ctx, int32_t n_ranks, fc_jrec* d_out, int64_t* h_counts, void* stream) {
+  if (!ctx || n_ranks <= 0 || !h_counts) return FC_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  fc_agg& a = ctx->agg;
+  int rc = sync_n_recs(ctx, st);
+  if (rc) return rc;
+  int64_t n = a.n_recs;
+  for (int r = 0; r < n_ranks; ++r) h_counts[r] = 0;
+  if (n == 0) return FC_OK;
+  if (!d_out) return FC_E_ARG;
+  FC_CUDA(ctx, a.scratch[0].reserve((size_t)n * 8, st, false, 0));
+  FC_CUDA(ctx, a.scratch[1].reserve((size_t)n * 8, st, false, 0));
+  FC_CUDA(ctx, a.scratch[2].reserve((size_t)n * 4, st, false, 0));
+  FC_CUDA(ctx, a.scratch[3].reserve((size_t)n * 4, st, false, 0));
+  FC_CUDA(ctx, a.scratch[4].reserve((size_t)(n_ranks + 1) * 8, st, false, 0));
+  uint64_t* key = (uint64_t*)a.scratch[0].p;
+  uint64_t* key_s = (uint64_t*)a.scratch[1].p;
+  uint32_t* iota = (uint32_t*)a.scratch[2].p;
+  uint32_t* perm = (uint32_t*)a.scratch[3].p;
+  unsigned long long* starts = (unsigned long long*)a.scratch[4].p;
+  dest_rank_kernel<<<nblk(n, 256), 256, 0, st>>>(n, (const fc_jrec*)a.recs.p, n_ranks, key, iota);
+  FC_LAUNCH_CHECK(ctx);
+  int bits = 1;
+  while ((1 << bits) < n_ranks) bits++;
+  rc = sort_pairs_u64_u32(ctx, n, key, key_s, iota, perm, 0, bits, st);  // stable: stream order kept per destination
+  if (rc) return rc;
+  gather_kernel<<<nblk(n, 256), 256, 0, st>>>(n, (const fc_jrec*)a.recs.p, perm, d_out);
+  FC_LAUNCH_CHECK(ctx);
+  FC_CUDA(ctx, cudaMemsetAsync(starts, 0xFF, (size_t)(n_ranks + 1) * 8, st));
+  rank_hist_kernel<<<nblk(n, 256), 256, 0, st>>>(n, key_s, starts);
+  FC_LAUNCH_CHECK(ctx);
+  std::vector<unsigned long long> h(n_ranks + 1);
+  FC_CUDA(ctx, cudaMemcpyAsync(h.data(), starts, (size_t)(n_ranks + 1) * 8, cudaMemcpyDeviceToHost, st));
+  FC_CUDA(ctx, cudaStreamSynchronize(st));
+  h[n_ranks] = (unsigned long long)n;
+  // ranks that received nothing keep the 0xFF.. marker: their start is the next valid start
+  for (int r = n_ranks - 1; r >= 0; --r)
+    if (h[r] == ~0ull) h[r] = h[r + 1];
+  for (int r = 0; r < n_ranks; ++r) h_counts[r] = (int64_t)(h[r + 1] - h[r]);
+  return FC_OK;
+}
+
+extern "C" int64_t fc_agg_finalize(fc_ctx* ctx, void* stream) {
+  if (!ctx) return FC_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  fc_agg& a = ctx->agg;
+  int rc = sync_n_recs(ctx, st);
+  if (rc) return rc;
+  const int64_t n = a.n_recs;
+  if (n == 0) {
+    a.n_junc = 0;
+    return 0;
+  }
+  if (n >= (1ll << 32)) return fc_fail(ctx, FC_E_ARG, "more than 2^32 records on one device");
+  rc = ensure_counters(ctx, st);
+  if (rc) return rc;
+  // scratch layout
+  FC_CUDA(ctx, a.scratch[0].reserve((size_t)n * 8, st, false, 0));  // u64 A
+  FC_CUDA(ctx, a.scratch[1].reserve((size_t)n * 8, st, false, 0));  // u64 B
+  FC_CUDA(ctx, a.scratch[2].reserve((size_t)n * 4, st, false, 0));  // u32 A
+  FC_CUDA(ctx, a.scratch[3].reserve((size_t)n * 4, st, false, 0));  // u32 B
+  FC_CUDA(ctx, a.scratch[4].reserve((size_t)n * sizeof(fc_jrec), st, false, 0));  // sorted records
+  FC_CUDA(ctx, a.scratch[5].reserve((size_t)n * 4, st, false, 0));  // head flags
+  FC_CUDA(ctx, a.scratch[6].reserve((size_t)n * 4, st, false, 0));  // inclusive segment ids
+  uint64_t* kA = (uint64_t*)a.scratch[0].p;
+  uint64_t* kB = (uint64_t*)a.scratch[1].p;
+  uint32_t* vA = (uint32_t*)a.scratch[2].p;
+  uint32_t* vB = (uint32_t*)a.scratch[3].p;
+  fc_jrec* sorted = (fc_jrec*)a.scratch[4].p;
+  uint32_t* head = (uint32_t*)a.scratch[5].p;
+  uint32_t* seg_incl = (uint32_t*)a.scratch[6].p;
+  unsigned long long* counters = (unsigned long long*)a.counters.p;
+
+  uint64_t seed = 0x9E3779B97F4A7C15ULL;
+  bool ok = false;
+  for (int attempt = 0; attempt < 4 && !ok; ++attempt, seed = fc_mix64(seed + attempt)) {
+    key_hash_kernel<<<nblk(n, 256), 256, 0, st>>>(n, (const fc_jrec*)a.recs.p, seed, kA, vA);
+    FC_LAUNCH_CHECK(ctx);
+    rc = sort_pairs_u64_u32(ctx, n, kA, kB, vA, vB, 0, 64, st);
+    if (rc) return rc;
+    gather_kernel<<<nblk(n, 256), 256, 0, st>>>(n, (const fc_jrec*)a.recs.p, vB, sorted);
+    FC_LAUNCH_CHECK(ctx);
+    FC_CUDA(ctx, cudaMemsetAsync(counters + 1, 0, sizeof(unsigned long long), st));
+    heads_kernel<<<nblk(n, 256), 256, 0, st>>>(n, sorted, kB, head, counters + 1);
+    FC_LAUNCH_CHECK(ctx);
+    unsigned long long coll = 0;
+    FC_CUDA(ctx, cudaMemcpyAsync(&coll, counters + 1, sizeof(coll), cudaMemcpyDeviceToHost, st));
+    FC_CUDA(ctx, cudaStreamSynchronize(st));
+    ok = coll == 0;
+  }
+  if (!ok) return fc_fail(ctx, FC_E_COLLISION, "junction key hash collisions survived 4 seeds");
+
+  rc = scan_u32(ctx, n, head, seg_incl, true, st);
+  if (rc) return rc;
+  uint32_t nj32 = 0;
+  FC_CUDA(ctx, cudaMemcpyAsync(&nj32, seg_incl + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+  FC_CUDA(ctx, cudaStreamSynchronize(st));
+  const int64_t nj = nj32;
+
+  FC_CUDA(ctx, a.scratch[7].reserve((size_t)nj * sizeof(JAcc), st, false, 0));
+  JAcc* acc = (JAcc*)a.scratch[7].p;
+  acc_init_kernel<<<nblk(nj, 256), 256, 0, st>>>(nj, acc);
+  FC_LAUNCH_CHECK(ctx);
+  reduce_kernel<<<nblk(n, 256), 256, 0, st>>>(n, sorted, seg_incl, head, acc);
+  FC_LAUNCH_CHECK(ctx);
+
+  // distinct read sequences / fragment names per junction: sort (hash) then stable sort (segment)
+  int seg_bits = 1;
+  while ((1ll << seg_bits) < nj) seg_bits++;
+  for (int which = 0; which < 2; ++which) {
+    // kA = read hashes, kB = qname hashes, vA = segment ids
+    split_hash_kernel<<<nblk(n, 256), 256, 0, st>>>(n, sorted, seg_incl, kA, kB, vA);
+    FC_LAUNCH_CHECK(ctx);
+    uint64_t* hin = which == 0 ? kA : kB;
+    uint64_t* hout = which == 0 ? kB : kA;
+    rc = sort_pairs_u64_u32(ctx, n, hin, hout, vA, vB, 0, 64, st);
+    if (rc) return rc;
+    rc = sort_pairs_u32_u64(ctx, n, vB, vA, hout, hin, 0, seg_bits, st);
+    if (rc) return rc;
+    distinct_kernel<<<nblk(n, 256), 256, 0, st>>>(n, vA, hin, which, acc);
+    FC_LAUNCH_CHECK(ctx);
+  }
+
+  FC_CUDA(ctx, a.junctions.reserve((size_t)nj * sizeof(fc_junction), st, false, 0));
+  // finish into scratch, then order by first_idx
+  FC_CUDA(ctx, a.scratch[5].reserve((size_t)nj * sizeof(fc_junction), st, false, 0));
+  fc_junction* tmpj = (fc_junction*)a.scratch[5].p;
+  finish_kernel<<<nblk(nj, 128), 128, 0, st>>>(nj, n, acc, sorted, tmpj, kA, vA);
+  FC_LAUNCH_CHECK(ctx);
+  rc = sort_pairs_u64_u32(ctx, nj, kA, kB, vA, vB, 0, 64, st);
+  if (rc) return rc;
+  gather_junctions_kernel<<<nblk(nj, 256), 256, 0, st>>>(nj, tmpj, vB, (fc_junction*)a.junctions.p);
+  FC_LAUNCH_CHECK(ctx);
+  a.n_junc = nj;
+  return nj;
+}
+
+extern "C" int fc_agg_fetch(fc_ctx* ctx, int64_t n, fc_junction* h_out) {
+  if (!ctx || !h_out) return FC_E_ARG;
+  if (ctx->agg.n_junc < 0) return fc_fail(ctx, FC_E_STATE, "fc_agg_fetch before fc_agg_finalize");
+  if (n > ctx->agg.n_junc) n = ctx->agg.n_junc;
+  if (n <= 0) return FC_OK;
+  FC_CUDA(ctx, cudaDeviceSynchronize());
+  FC_CUDA(ctx, cudaMemcpy(h_out, ctx->agg.junctions.p, (size_t)n * sizeof(fc_junction), cudaMemcpyDeviceToHost));
+  return FC_OK;
+}
+
+extern "C" const fc_junction* fc_agg_junctions(fc_ctx* ctx) {
+  return ctx && ctx->agg.n_junc >= 0 ? (const fc_junction*)ctx->agg.junctions.p : nullptr;
+}
+
+void fc_agg_release(fc_ctx* ctx) {
+  fc_agg& a = ctx->agg;
+  a.recs.release();
+  a.junctions.release();
+  for (auto& s : a.scratch) s.release();
+  a.cub_tmp.release();
+  a.counters.release();
+}

@@ -1,0 +1,98 @@
+// fc_internal.cuh -- context layout and helpers shared by the translation units of libfindcirc_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/findcirc_b200.h"
+#include "scan_core.cuh"
+
+struct fc_genome {
+  bool loaded = false;
+  std::vector<std::string> names;
+  std::vector<int64_t> sizes;
+  std::vector<int64_t> offs;  // global base offset of each chromosome
+  int64_t total = 0;          // padded length in bases
+  int64_t n_bases = 0, n_n = 0, n_other = 0;
+  uint32_t* d_seq2 = nullptr;
+  uint32_t* d_nmask = nullptr;
+  uint32_t* d_nsum = nullptr;
+  int64_t* d_off = nullptr;
+  int64_t* d_size = nullptr;
+  int64_t dev_bytes = 0;
+  fc::GenomeView view() const {
+    fc::GenomeView v;
+    v.seq2 = d_seq2;
+    v.nmask = d_nmask;
+    v.nsum = d_nsum;
+    v.chrom_off = d_off;
+    v.chrom_size = d_size;
+    v.n_chrom = (int32_t)names.size();
+    v.pad = FC_GENOME_PAD;
+    return v;
+  }
+};
+
+// growable device buffer
+struct fc_dbuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes, cudaStream_t st, bool keep, size_t used);
+  void release();
+};
+
+struct fc_agg {
+  fc_dbuf recs;         // fc_jrec[n_recs]
+  int64_t n_recs = 0;
+  fc_dbuf junctions;    // fc_junction[n_junc]
+  int64_t n_junc = -1;  // -1: not finalized
+  fc_dbuf scratch[8];
+  fc_dbuf cub_tmp;
+  fc_dbuf counters;     // small device counters
+};
+
+struct fc_ctx {
+  int device = 0;
+  std::string err;
+  fc_genome genome;
+  fc_agg agg;
+  cudaStream_t own_stream = nullptr;  // used by the host-buffer convenience calls
+  fc_dbuf host_path[16];              // staging for fc_scan_host / fc_batch_host
+  int64_t launches = 0;
+  int sm_count = 148;
+};
+
+int fc_fail(fc_ctx* ctx, int code, const char* fmt, ...);
+
+#define FC_CUDA(ctx, call)                                                                         \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return fc_fail((ctx), FC_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+#define FC_LAUNCH_CHECK(ctx)                                                                       \
+  do {                                                                                             \
+    (ctx)->launches++;                                                                             \
+    cudaError_t e__ = cudaGetLastError();                                                          \
+    if (e__ != cudaSuccess)                                                                        \
+      return fc_fail((ctx), FC_E_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+// 64-bit mix (splitmix64 finaliser)
+__host__ __device__ inline uint64_t fc_mix64(uint64_t x) {
+  x ^= x >> 30;
+  x *= 0xbf58476d1ce4e5b9ULL;
+  x ^= x >> 27;
+  x *= 0x94d049bb133111ebULL;
+  x ^= x >> 31;
+  return x;
+}
+__host__ __device__ inline uint64_t fc_key_hash(uint32_t chrom, uint32_t start, uint32_t end, uint32_t sk, uint64_t seed) {
+  uint64_t a = ((uint64_t)chrom << 32) | start;
+  uint64_t b = ((uint64_t)end << 32) | (sk & 3u);
+  return fc_mix64(fc_mix64(a + seed) ^ (b * 0x9E3779B97F4A7C15ULL + 0x632BE59BD9B4E019ULL));
+}

@@ -1,0 +1,217 @@
+"""
+Engine -- python face of one libfindcirc_b200 context (one GPU).
+
+Mirrors the three objects of the reference that sit on the hot path:
+  genome store      Track(options.genome, accessor=GenomeAccessor)        find_circ.py:435-436
+  breakpoint scan   JunctionSpan.find_breakpoints()                       find_circ.py:854-974
+  junction tables   SpliceSiteStorage("circ") / SpliceSiteStorage("lin")  find_circ.py:1142-1143
+All arithmetic happens in CUDA kernels behind the C ABI (include/findcirc_b200.h); torch is used only to hold
+device buffers and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import HIT_DTYPE, JREC_DTYPE, JUNCTION_DTYPE, FindCircError, Pairs, ScanParams, ptr
+
+SIG_LETTERS = "ACGTN"
+
+
+def decode_signal(code: int) -> str:
+    return "".join(SIG_LETTERS[(code >> (3 * k)) & 7] for k in range(4))
+
+
+class Engine:
+    def __init__(self, device: int = 0, asize: int = 15, margin: int = 2, maxdist: int = 2, noncanonical: bool = False,
+                 strandpref: bool = False):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        rc = self.lib.fc_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise FindCircError(rc, self.lib.fc_last_error(None).decode())
+        self.h = h
+        self.device = device
+        self.params = ScanParams(asize, margin, maxdist, int(noncanonical), int(strandpref))
+        self.chrom_names: List[str] = []
+        self.chrom_sizes: List[int] = []
+        self._chrom_ids = {}
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc):
+        if rc is not None and rc < 0:
+            raise FindCircError(rc, self.lib.fc_last_error(self.h).decode())
+        return rc
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.fc_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def eff(self) -> int:
+        return self.params.asize - self.params.margin
+
+    def launch_count(self) -> int:
+        return int(self.lib.fc_launch_count(self.h))
+
+    def sync(self):
+        self._check(self.lib.fc_device_sync(self.h))
+
+    # ------------------------------------------------------------------ genome store
+    def _refresh_chroms(self):
+        n = self.lib.fc_genome_n_chrom(self.h)
+        buf = C.create_string_buffer(4096)
+        self.chrom_names, self.chrom_sizes = [], []
+        for i in range(n):
+            self._check(self.lib.fc_genome_chrom_name(self.h, i, buf, 4096))
+            self.chrom_names.append(buf.value.decode())
+            self.chrom_sizes.append(int(self.lib.fc_genome_chrom_size(self.h, i)))
+        self._chrom_ids = {n: i for i, n in enumerate(self.chrom_names)}
+
+    def load_genome_fasta(self, path: str):
+        self._check(self.lib.fc_genome_load_fasta(self.h, path.encode()))
+        self._refresh_chroms()
+
+    def load_genome_arrays(self, names: Sequence[str], seqs: Sequence[np.ndarray]):
+        """chromosomes as uint8 ASCII arrays (synthetic genomes)"""
+        seqs = [np.ascontiguousarray(s, dtype=np.uint8) for s in seqs]
+        n = len(seqs)
+        c_names = (C.c_char_p * n)(*[s.encode() for s in names])
+        c_seqs = (C.c_void_p * n)(*[s.ctypes.data for s in seqs])
+        sizes = np.array([len(s) for s in seqs], dtype=np.int64)
+        self._check(self.lib.fc_genome_load_ascii(self.h, n, c_names, c_seqs, sizes.ctypes.data))
+        self._refresh_chroms()
+
+    def chrom_id(self, name: str) -> int:
+        """KeyError for unknown chromosomes, as the reference raises (find_circ.py:193)"""
+        return self._chrom_ids[name]
+
+    def genome_stats(self):
+        s = np.zeros(4, dtype=np.int64)
+        self._check(self.lib.fc_genome_stats(self.h, s.ctypes.data))
+        return {"bases": int(s[0]), "n": int(s[1]), "other_as_n": int(s[2]), "device_bytes": int(s[3])}
+
+    def fetch(self, chrom: int, start: int, end: int) -> str:
+        """genome.get(chrom,start,end,'+').upper() decoded from the device store"""
+        n = max(0, end - start)
+        buf = np.zeros(n, dtype=np.uint8)
+        self._check(self.lib.fc_genome_fetch(self.h, chrom, start, end, buf.ctypes.data))
+        return buf.tobytes().decode()
+
+    # ------------------------------------------------------------------ scan, host buffers in / out
+    def scan_host(self, chrom, a_start, b_end, l, flags, internal, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """One batch through H2D -> pack -> scan -> D2H.  `internal` is an [n, stride] uint8 ASCII matrix."""
+        n = len(chrom)
+        if out is None:
+            out = np.zeros(n, dtype=HIT_DTYPE)
+        if n == 0:
+            return out
+        internal = np.ascontiguousarray(internal, dtype=np.uint8)
+        if internal.ndim != 2 or internal.shape[0] != n:
+            raise ValueError("internal must be [n, stride]")
+        stride = max(int(internal.shape[1]), 1)
+        if internal.shape[1] == 0:
+            internal = np.zeros((n, 1), dtype=np.uint8)
+        args = [np.ascontiguousarray(x, dtype=t) for x, t in
+                ((chrom, np.int32), (a_start, np.int32), (b_end, np.int32), (l, np.int32), (flags, np.uint8))]
+        self._check(self.lib.fc_scan_host(self.h, C.byref(self.params), n, *[a.ctypes.data for a in args],
+                                          internal.ctypes.data, stride, out.ctypes.data))
+        return out
+
+    def batch_host(self, chrom, a_start, b_end, l, flags, internal, wden, q_a, q_b, read_hash, qname_hash, idx_base,
+                   emit=True, out: Optional[np.ndarray] = None, want_hits=True) -> Optional[np.ndarray]:
+        """scan one batch and append its junction records to the device aggregator (host buffers in, hits out)"""
+        n = len(chrom)
+        if want_hits and out is None:
+            out = np.zeros(n, dtype=HIT_DTYPE)
+        if n == 0:
+            return out
+        internal = np.ascontiguousarray(internal, dtype=np.uint8)
+        if internal.shape[1] == 0:
+            internal = np.zeros((n, 1), dtype=np.uint8)
+        stride = int(internal.shape[1])
+        a = [np.ascontiguousarray(x, dtype=t) for x, t in (
+            (chrom, np.int32), (a_start, np.int32), (b_end, np.int32), (l, np.int32), (flags, np.uint8))]
+        pay = [np.ascontiguousarray(x, dtype=t) for x, t in (
+            (wden, np.uint8), (q_a, np.int16), (q_b, np.int16), (read_hash, np.uint64), (qname_hash, np.uint64))]
+        self._check(self.lib.fc_batch_host(
+            self.h, C.byref(self.params), n, *[x.ctypes.data for x in a], internal.ctypes.data, stride,
+            *[x.ctypes.data for x in pay], int(idx_base), int(bool(emit)), out.ctypes.data if want_hits else None))
+        return out
+
+    # ------------------------------------------------------------------ scan, device buffers (torch tensors)
+    def pack_reads(self, d_ascii, stride: int, d_l, n_words: int, d_rd2, d_rdn, d_flags, stream=0):
+        n = d_l.numel()
+        self._check(self.lib.fc_pack_reads(self.h, n, ptr(d_ascii), stride, ptr(d_l), n_words, ptr(d_rd2), ptr(d_rdn),
+                                           ptr(d_flags), stream))
+
+    def make_pairs(self, n, d_chrom, d_a_start, d_b_end, d_l, d_flags, d_rd2, d_rdn, n_words, max_l) -> Pairs:
+        return Pairs(n, ptr(d_chrom), ptr(d_a_start), ptr(d_b_end), ptr(d_l), ptr(d_flags), ptr(d_rd2), ptr(d_rdn),
+                     n_words, max_l)
+
+    def scan(self, pairs: Pairs, d_out, stream=0):
+        self._check(self.lib.fc_scan(self.h, C.byref(self.params), C.byref(pairs), ptr(d_out), stream))
+
+    def scan_ties(self, pairs: Pairs, d_hits, d_tie_off, d_ties, stream=0):
+        self._check(self.lib.fc_scan_ties(self.h, C.byref(self.params), C.byref(pairs), ptr(d_hits), ptr(d_tie_off),
+                                          ptr(d_ties), stream))
+
+    # ------------------------------------------------------------------ aggregation
+    def agg_reset(self):
+        self._check(self.lib.fc_agg_reset(self.h))
+
+    def agg_emit(self, n, d_hits, d_chrom, d_flags, d_wden, d_q_a, d_q_b, d_read_hash, d_qname_hash, idx_base, stream=0):
+        self._check(self.lib.fc_agg_emit(self.h, n, ptr(d_hits), ptr(d_chrom), ptr(d_flags), ptr(d_wden), ptr(d_q_a),
+                                         ptr(d_q_b), ptr(d_read_hash), ptr(d_qname_hash), idx_base, stream))
+
+    def agg_append_host(self, recs: np.ndarray):
+        recs = np.ascontiguousarray(recs, dtype=JREC_DTYPE)
+        self._check(self.lib.fc_agg_append_host(self.h, len(recs), recs.ctypes.data))
+
+    def agg_append_device(self, n, d_recs, stream=0):
+        self._check(self.lib.fc_agg_append(self.h, n, ptr(d_recs), stream))
+
+    def agg_n_records(self) -> int:
+        return int(self._check(self.lib.fc_agg_n_records(self.h)))
+
+    def agg_records_ptr(self) -> int:
+        return int(self.lib.fc_agg_records(self.h) or 0)
+
+    def agg_partition(self, n_ranks: int, d_out, stream=0) -> np.ndarray:
+        counts = np.zeros(n_ranks, dtype=np.int64)
+        self._check(self.lib.fc_agg_partition(self.h, n_ranks, ptr(d_out), counts.ctypes.data, stream))
+        return counts
+
+    def agg_finalize(self, stream=0) -> int:
+        return int(self._check(self.lib.fc_agg_finalize(self.h, stream)))
+
+    def agg_fetch(self, n: int) -> np.ndarray:
+        out = np.zeros(n, dtype=JUNCTION_DTYPE)
+        if n:
+            self._check(self.lib.fc_agg_fetch(self.h, n, out.ctypes.data))
+        return out
+
+    # ------------------------------------------------------------------ hashing (host helpers of the ABI)
+    def hash_reads(self, seqs: np.ndarray, lens: np.ndarray) -> np.ndarray:
+        seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+        lens = np.ascontiguousarray(lens, dtype=np.int32)
+        out = np.zeros(len(lens), dtype=np.uint64)
+        self._check(self.lib.fc_hash_reads_host(len(lens), seqs.ctypes.data, seqs.shape[1], lens.ctypes.data,
+                                                out.ctypes.data, None))
+        return out
+
+    def hash_read(self, seq: bytes) -> int:
+        return int(self.lib.fc_hash_read(seq, len(seq), None))
+
+    def hash_bytes(self, b: bytes) -> int:
+        return int(self.lib.fc_hash_bytes(b, len(b)))

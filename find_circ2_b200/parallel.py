@@ -1,0 +1,73 @@
+"""
+Multi-GPU plumbing: one process per GPU, anchor pairs sharded by rank, ONE exchange step.
+
+The scan needs no communication (the genome is replicated per GPU).  Junction aggregation is a keyed reduce:
+every rank turns its accepted spans into 48-byte records (fc_jrec), partitions them by hash(key) % world on the
+device (fc_agg_partition, stable -> stream order survives), and a single all-to-all over NCCL/NVLink moves each
+record to the rank that owns its key.  Ranks hold contiguous, ascending ranges of the input stream, and the
+all-to-all output is ordered by source rank, so every receiver sees its records in global stream order --
+which is what the discovery-order junction names and the sequential float sums of the reference depend on
+(find_circ.py:684-686, 544).  Raw records (not partial sums) are exchanged because n_uniq / n_frags are distinct
+counts (find_circ.py:584-590).  The reference's own multi-sample story has the same shape: independent runs
+merged by merge_bed.py (merge_bed.py:117-130).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+REC_BYTES = 48
+
+
+def exchange_records(eng, dist, dev, stream=0):
+    """hash-partition this rank's junction records and swap them with the other ranks; afterwards the engine's
+    aggregator holds exactly the records whose keys this rank owns.  Returns (sent_bytes, received_bytes)."""
+    import torch
+
+    world = dist.get_world_size()
+    if world == 1:
+        return 0, 0
+    n = eng.agg_n_records()
+    send = torch.empty(max(n, 1) * REC_BYTES, dtype=torch.uint8, device=dev)
+    counts = eng.agg_partition(world, send, stream)  # int64[world], records per destination
+    c_send = torch.from_numpy(np.ascontiguousarray(counts, dtype=np.int64)).to(dev)
+    c_recv = torch.empty_like(c_send)
+    dist.all_to_all_single(c_recv, c_send)
+    recv_counts = c_recv.cpu().numpy()
+    n_recv = int(recv_counts.sum())
+    recv = torch.empty(max(n_recv, 1) * REC_BYTES, dtype=torch.uint8, device=dev)
+    dist.all_to_all_single(
+        recv[: n_recv * REC_BYTES],
+        send[: n * REC_BYTES],
+        output_split_sizes=[int(c) * REC_BYTES for c in recv_counts],
+        input_split_sizes=[int(c) * REC_BYTES for c in counts],
+    )
+    if dev is not None and getattr(dev, "type", "cpu") == "cuda":
+        torch.cuda.current_stream().synchronize()
+    eng.agg_reset()
+    eng.agg_append_device(n_recv, recv, stream)
+    return int(n * REC_BYTES), int(n_recv * REC_BYTES)
+
+
+def gather_junctions(junctions: np.ndarray, dist, dev):
+    """ordered gather of every rank's junction table to rank 0 (rows sorted by first_idx = discovery order)"""
+    import torch
+
+    world = dist.get_world_size()
+    if world == 1:
+        return junctions
+    rank = dist.get_rank()
+    raw = np.ascontiguousarray(junctions).view(np.uint8).reshape(-1)
+    n_local = torch.tensor([raw.size], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, n_local)
+    sizes = [int(s.item()) for s in sizes]
+    mx = max(max(sizes), 1)
+    buf = torch.zeros(mx, dtype=torch.uint8, device=dev)
+    buf[: raw.size] = torch.from_numpy(raw.copy()).to(dev)
+    bufs = [torch.zeros(mx, dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(bufs, buf)
+    if rank != 0:
+        return None
+    parts = [b[:s].cpu().numpy().view(junctions.dtype) for b, s in zip(bufs, sizes)]
+    allj = np.concatenate(parts) if parts else junctions
+    return allj[np.argsort(allj["first_idx"], kind="stable")]

@@ -200,16 +200,19 @@ def _gather_reads(genome: SynthGenome, chrom, left_pos, left_len, right_pos, rea
     n = len(chrom)
     out = np.empty((n, read_len), dtype=np.uint8)
     col = np.arange(read_len, dtype=np.int64)[None, :]
-    ll = left_len.astype(np.int64)[:, None]
-    gpos = np.where(col < ll, left_pos[:, None] + col, right_pos[:, None] + (col - ll))
-    for c in np.unique(chrom):
-        rows = np.nonzero(chrom == c)[0]
-        g = genome.seqs[c]
-        p = gpos[rows]
-        ok = (p >= 0) & (p < len(g))
-        vals = g[np.clip(p, 0, len(g) - 1)] & 0xDF  # upper-case
-        vals = np.where(ok, vals, ord("N")).astype(np.uint8)
-        out[rows] = vals
+    step = 1 << 17  # rows per chunk: bounds the [rows, read_len] int64 temporaries
+    for lo in range(0, n, step):
+        hi = min(n, lo + step)
+        ll = left_len[lo:hi].astype(np.int64)[:, None]
+        gpos = np.where(col < ll, left_pos[lo:hi, None] + col, right_pos[lo:hi, None] + (col - ll))
+        cc = chrom[lo:hi]
+        for c in np.unique(cc):
+            rows = np.nonzero(cc == c)[0]
+            g = genome.seqs[c]
+            p = gpos[rows]
+            ok = (p >= 0) & (p < len(g))
+            vals = g[np.clip(p, 0, len(g) - 1)] & 0xDF  # upper-case
+            out[lo + rows] = np.where(ok, vals, ord("N")).astype(np.uint8)
     return out
 
 
@@ -292,7 +295,7 @@ def make_pairs(
 
     # sequencing errors: substitutions only (simulate_reads.py:146-159 does the same)
     if error_rate > 0:
-        mask = rng.random(reads.shape) < error_rate
+        mask = rng.random(reads.shape, dtype=np.float32) < error_rate
         shift = rng.integers(1, 4, size=int(mask.sum()), dtype=np.uint8)
         cur = reads[mask]
         code = np.searchsorted(_ACGT, cur)  # N -> 4 (stays N)

@@ -1,0 +1,227 @@
+/*
+ * findcirc_b200.h -- C ABI of libfindcirc_b200.so: the B200-native (sm_100a) breakpoint scan and junction
+ * aggregation behind find_circ.py's command line.
+ *
+ * The reference (feiyue126/find_circ2, /root/reference/find_circ.py v1.99) is one Python process with no
+ * FFI seam; the drop-in boundary is its internal call structure.  Each entry point
+ * below names the reference code it replaces:
+ *
+ *   genome store    Track / GenomeAccessor / indexed_fasta.get_data      find_circ.py:103-215, 242-371
+ *   scan            JunctionSpan.find_breakpoints + Splice.score          find_circ.py:766-806, 854-974
+ *   aggregation     SpliceSiteStorage.add + Hit.add + Hit reductions      find_circ.py:486-600, 657-690
+ *
+ * Conventions: plain pointers and sizes only; every call returns 0 on success and a negative FC_E_* code
+ * on failure (fc_last_error() gives the text); nothing throws or exits across the boundary; one calling
+ * thread per context; a context is bound to one CUDA device.  Pointers named d_* are DEVICE pointers
+ * (e.g. torch tensors' data_ptr()), h_* are host pointers.  `stream` is a cudaStream_t passed as void*
+ * (NULL = the legacy default stream); device-pointer calls are asynchronous on that stream.
+ *
+ * There is no CPU implementation behind these entry points.
+ */
+#ifndef FINDCIRC_B200_H
+#define FINDCIRC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FC_ABI_VERSION 1
+
+/* error codes */
+#define FC_OK 0
+#define FC_E_CUDA -1      /* a CUDA runtime call failed */
+#define FC_E_ARG -2       /* bad argument */
+#define FC_E_IO -3        /* file could not be read */
+#define FC_E_FORMAT -4    /* malformed FASTA */
+#define FC_E_NOGENOME -5  /* scan before a genome was loaded */
+#define FC_E_RANGE -6     /* an anchor window lies entirely outside its chromosome (undefined in the reference) */
+#define FC_E_NOMEM -7
+#define FC_E_STATE -8     /* call order violated */
+#define FC_E_COLLISION -9 /* 64-bit junction-key hash collision survived all reseeds */
+
+typedef struct fc_ctx fc_ctx;
+
+/* Scan switches -- the subset of find_circ.py's optparse table (find_circ.py:383-413) that reaches
+ * find_breakpoints():  -a/--anchor, -m/--margin, -d/--max-mismatch, --non-canonical, --strand-pref. */
+typedef struct fc_scan_params {
+  int32_t asize;        /* find_circ.py:394 */
+  int32_t margin;       /* find_circ.py:395 */
+  int32_t maxdist;      /* find_circ.py:396 */
+  int32_t noncanonical; /* find_circ.py:401 */
+  int32_t strandpref;   /* find_circ.py:404 */
+  int32_t reserved[3];
+} fc_scan_params;
+
+/* ---- per-pair flags (fc_pairs.flags) ---- */
+#define FC_PF_BACKSPLICE 1u  /* JunctionSpan.is_backsplice, find_circ.py:850-852 */
+#define FC_PF_MINUS 2u       /* JunctionSpan.strand == '-', find_circ.py:834-837 */
+#define FC_PF_READ_N 4u      /* the internal read part contains a non-ACGT letter (set by fc_pack_reads) */
+#define FC_PF_LINEAR_KIND 8u /* informational: not a back-splice (== !BACKSPLICE) */
+
+/* Struct-of-arrays batch of anchor pairs (one row per JunctionSpan, find_circ.py:821-852), device resident.
+ *   a_start = A.pos + (asize - margin)       genomic position of A_flank[0]      (find_circ.py:901)
+ *   b_end   = B.aend - (asize - margin)      one past the last base of B_flank   (find_circ.py:902)
+ *   l       = len(read_part) - 2*(asize-margin)   number of internal bases        (find_circ.py:904); may be < 0
+ *   rd2     2-bit packed internal read bases, word-major: word w of pair i at rd2[w*n + i], base j of the
+ *           internal sequence in word j/16 at bits 2*(j%16) (A=0 C=1 G=2 T=3, N stored as 0)
+ *   rdn     same layout, bit 2*(j%16) set when base j is not A/C/G/T
+ *   n_words = words per pair in rd2/rdn  (>= ceil(max l / 16))
+ */
+typedef struct fc_pairs {
+  int64_t n;
+  const int32_t* d_chrom;
+  const int32_t* d_a_start;
+  const int32_t* d_b_end;
+  const int32_t* d_l;
+  const uint8_t* d_flags; /* FC_PF_* ; READ_N may be OR-ed in by fc_pack_reads, hence also written */
+  const uint32_t* d_rd2;
+  const uint32_t* d_rdn;
+  int32_t n_words;
+  int32_t max_l; /* upper bound of l over the batch (selects the kernel specialisation) */
+} fc_pairs;
+
+/* Result of the scan for one pair: the FIRST best-scoring breakpoint (ties keep ascending split position,
+ * '+' before '-', find_circ.py:966-974) and the number of ties.  16 bytes, one coalesced store per pair.
+ *   start,end  BED coordinates after the back-splice / linear correction (find_circ.py:929-945); valid iff n_hits>0
+ *   w2         bits 0-15 n_hits (= number of ties, find_circ.py:969), 16-23 dist, 24-31 anchor overlap
+ *   w3         bit 0 strand ('-' = 1), bits 1-12 signal (4 letters x 3 bits, A0 C1 G2 T3 N4, first letter lowest),
+ *              bits 13-22 best score + 512, bit 30 window-out-of-range, bit 31 slow (per-base) path was taken
+ */
+typedef struct fc_hit {
+  int32_t start;
+  int32_t end;
+  uint32_t w2;
+  uint32_t w3;
+} fc_hit;
+
+/* 48-byte junction record: one per Hit.add() call (find_circ.py:526-582); this is also the unit exchanged
+ * between GPUs (hash-partitioned by key). */
+typedef struct fc_jrec {
+  uint32_t chrom;
+  uint32_t start;
+  uint32_t end;
+  uint32_t sk;         /* bit0 strand '-', bit1 kind (1 = linear table), bit2 read is its own reverse complement,
+                          bits 8-15 weight denominator (weight = 1/den, find_circ.py:1084), bits 16-27 signal */
+  uint64_t idx;        /* position in the input stream (orders names and float sums, find_circ.py:684-686, 544) */
+  uint64_t read_hash;  /* strand-invariant hash of primary.seq (n_uniq, find_circ.py:581-590) */
+  uint64_t qname_hash; /* hash of primary.qname (n_frags, find_circ.py:584-586) */
+  int16_t q_left;      /* AS-XS of the genome-left anchor, XS default 0 (find_circ.py:552-559) */
+  int16_t q_right;
+  uint16_t n_hits;
+  uint8_t dist;
+  uint8_t ov;
+} fc_jrec;
+
+/* 64-byte aggregated junction (one Hit): everything store_list() prints that is not text (find_circ.py:722-730) */
+typedef struct fc_junction {
+  uint32_t chrom;
+  uint32_t start;
+  uint32_t end;
+  uint32_t sk;         /* bit0 strand, bit1 kind, bits 16-27 signal */
+  uint64_t first_idx;  /* smallest idx -> discovery order -> name number */
+  double n_weighted;   /* sum of weights in stream order */
+  double n_uniq_bridges;
+  uint32_t n_spanned;
+  uint32_t n_frags;    /* distinct qnames */
+  uint32_t n_uniq;     /* len(uniq)/2: distinct read sequences modulo reverse complement */
+  int16_t best_q_left;
+  int16_t best_q_right;
+  uint16_t min_n_hits;
+  uint8_t min_dist;
+  uint8_t min_ov;
+  uint32_t pad;
+} fc_junction;
+
+/* ------------------------------------------------------------------ context */
+int fc_abi_version(void);
+int fc_ctx_create(int device, fc_ctx** out);
+void fc_ctx_destroy(fc_ctx* ctx);
+const char* fc_last_error(fc_ctx* ctx); /* ctx may be NULL: last error of a failed fc_ctx_create */
+
+/* ------------------------------------------------------------------ genome store
+ * Replaces indexed_fasta / GenomeAccessor (find_circ.py:103-215, 329-371).  Chromosomes are 2-bit packed into one
+ * device array with >= FC_GENOME_PAD bases of 'N' padding around each, so reads outside [0,size) return 'N' as
+ * find_circ.py:194-211 does; soft-masked (lower-case) letters are upper-cased as the callers do (:901-902);
+ * letters other than ACGTN are stored as N and counted (fc_genome_stats). */
+#define FC_GENOME_PAD 4096
+int fc_genome_load_fasta(fc_ctx* ctx, const char* path);
+/* n_chrom sequences given as ASCII in host memory (synthetic genomes; avoids a FASTA round trip) */
+int fc_genome_load_ascii(fc_ctx* ctx, int32_t n_chrom, const char* const* names, const uint8_t* const* seqs,
+                         const int64_t* sizes);
+int fc_genome_n_chrom(fc_ctx* ctx);
+int fc_genome_chrom_name(fc_ctx* ctx, int32_t i, char* buf, int32_t cap);
+int64_t fc_genome_chrom_size(fc_ctx* ctx, int32_t i);
+int fc_genome_chrom_id(fc_ctx* ctx, const char* name); /* -1 unknown (the reference raises KeyError, :193) */
+/* stats[0]=total bases, [1]=N bases, [2]=other non-ACGT letters stored as N, [3]=device bytes */
+int fc_genome_stats(fc_ctx* ctx, int64_t stats[4]);
+/* genome.get(chrom,start,end,'+').upper() decoded FROM THE DEVICE store into h_out (end-start bytes) */
+int fc_genome_fetch(fc_ctx* ctx, int32_t chrom, int64_t start, int64_t end, char* h_out);
+
+/* ------------------------------------------------------------------ read packing
+ * d_ascii: n rows of `stride` bytes, row i holds the l[i] internal read bases (read_part[eff:-eff], find_circ.py:895),
+ * any case.  Writes rd2 / rdn (n_words words per pair, word-major) and ORs FC_PF_READ_N into d_flags. */
+int fc_pack_reads(fc_ctx* ctx, int64_t n, const uint8_t* d_ascii, int32_t stride, const int32_t* d_l,
+                  int32_t n_words, uint32_t* d_rd2, uint32_t* d_rdn, uint8_t* d_flags, void* stream);
+
+/* ------------------------------------------------------------------ breakpoint scan
+ * One thread per anchor pair; see find_circ2_b200/csrc/scan_core.cuh. */
+int fc_scan(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs* pairs, fc_hit* d_out, void* stream);
+/* --all-hits (find_circ.py:1312-1317): d_tie_off[i] = exclusive prefix sum of n_hits over the pairs (n+1 entries);
+ * writes every tie of every pair in rank order to d_ties[d_tie_off[i] ...] */
+int fc_scan_ties(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs* pairs, const fc_hit* d_hits,
+                 const int64_t* d_tie_off, fc_hit* d_ties, void* stream);
+/* host-buffer convenience (the reference-facing call): copies the batch in, scans, copies results out.
+ * h_ascii rows hold the internal read bases.  Pinned host memory makes the copies asynchronous. */
+int fc_scan_host(fc_ctx* ctx, const fc_scan_params* p, int64_t n, const int32_t* h_chrom, const int32_t* h_a_start,
+                 const int32_t* h_b_end, const int32_t* h_l, const uint8_t* h_flags, const uint8_t* h_ascii,
+                 int32_t stride, fc_hit* h_out);
+
+/* One batch through the whole device path with HOST buffers: upload scan inputs (+ the aggregation payload when
+ * emit != 0), pack, scan, append the first tie of every pair with n_hits > 0 to the device aggregator
+ * (== circ_splices.add / linear_splices.add, find_circ.py:1312-1317, 1364-1378), download the hits (h_out may be NULL).
+ * Record order (fc_jrec.idx) is idx_base + row. */
+int fc_batch_host(fc_ctx* ctx, const fc_scan_params* p, int64_t n, const int32_t* h_chrom, const int32_t* h_a_start,
+                  const int32_t* h_b_end, const int32_t* h_l, const uint8_t* h_flags, const uint8_t* h_ascii,
+                  int32_t stride, const uint8_t* h_wden, const int16_t* h_q_a, const int16_t* h_q_b,
+                  const uint64_t* h_read_hash, const uint64_t* h_qname_hash, uint64_t idx_base, int32_t emit,
+                  fc_hit* h_out);
+
+/* ------------------------------------------------------------------ junction aggregation
+ * fc_agg_emit: turns scan results into fc_jrec records on the device (first tie of every pair with n_hits>0),
+ *   appending to the context's record buffer.  Per-pair payload arrays are device pointers.
+ * fc_agg_finalize: sort by key + segmented reduce -> fc_junction table (device), returns the count.
+ */
+int fc_agg_reset(fc_ctx* ctx);
+int fc_agg_emit(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, const int32_t* d_chrom, const uint8_t* d_flags,
+                const uint8_t* d_wden, const int16_t* d_q_a, const int16_t* d_q_b, const uint64_t* d_read_hash,
+                const uint64_t* d_qname_hash, uint64_t idx_base, void* stream);
+int fc_agg_append(fc_ctx* ctx, int64_t n, const fc_jrec* d_recs, void* stream); /* records built elsewhere (other ranks) */
+int fc_agg_append_host(fc_ctx* ctx, int64_t n, const fc_jrec* h_recs);
+int64_t fc_agg_n_records(fc_ctx* ctx);
+const fc_jrec* fc_agg_records(fc_ctx* ctx); /* device pointer to the record buffer (for the all-to-all) */
+/* destination rank of every record: hash(key) % n_ranks (int32 per record) and per-rank counts (int64[n_ranks]) */
+int fc_agg_partition(fc_ctx* ctx, int32_t n_ranks, fc_jrec* d_out_sorted_by_rank, int64_t* h_counts, void* stream);
+int64_t fc_agg_finalize(fc_ctx* ctx, void* stream);
+int fc_agg_fetch(fc_ctx* ctx, int64_t n, fc_junction* h_out); /* sorted by first_idx */
+const fc_junction* fc_agg_junctions(fc_ctx* ctx);             /* device pointer, after finalize */
+
+/* ------------------------------------------------------------------ utilities */
+void* fc_pinned_alloc(int64_t bytes);
+void fc_pinned_free(void* p);
+int fc_device_sync(fc_ctx* ctx);
+/* number of kernels this library has launched in this context (bench.py's gpu_launches) */
+int64_t fc_launch_count(fc_ctx* ctx);
+/* the hash functions the host must use for fc_jrec.read_hash / qname_hash (FNV-1a 64 + finaliser) */
+uint64_t fc_hash_bytes(const uint8_t* p, int64_t n);
+/* strand-invariant read hash + palindrome flag: min(hash(seq.upper()), hash(revcomp)) */
+uint64_t fc_hash_read(const uint8_t* seq, int64_t n, int32_t* is_palindrome);
+/* vectorised: rows of a fixed-stride matrix */
+int fc_hash_reads_host(int64_t n, const uint8_t* h_seq, int32_t stride, const int32_t* h_len, uint64_t* h_out,
+                       uint8_t* h_pal);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FINDCIRC_B200_H */

@@ -1,0 +1,131 @@
+"""shared helpers of the test-suite (test infrastructure; may use the oracle)"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+from oracle import find_circ_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SIG_LETTERS = "ACGTN"
+
+
+def decode_sig(code):
+    return "".join(SIG_LETTERS[(code >> (3 * k)) & 7] for k in range(4))
+
+
+def decode_hit(h):
+    """(start, end, strand, dist, ov, signal, n_hits) or None from one fc_hit row (4 x uint32 view)"""
+    start, end, w2, w3 = int(h[0]), int(h[1]), int(h[2]), int(h[3])
+    n_hits = w2 & 0xFFFF
+    if n_hits == 0:
+        return None
+    start = start - (1 << 32) if start >= (1 << 31) else start
+    end = end - (1 << 32) if end >= (1 << 31) else end
+    return (start, end, "-" if (w3 & 1) else "+", (w2 >> 16) & 0xFF, w2 >> 24, decode_sig((w3 >> 1) & 0xFFF), n_hits)
+
+
+def pairs_to_soa(t, asize, margin):
+    """PairTable (find_circ2_b200.synth) -> scan inputs for 2-segment reads that tile the read (q_start=0, q_end=R)"""
+    eff = asize - margin
+    R = t.read_len
+    n = len(t)
+    a_start = (t.a_pos + eff).astype(np.int32)
+    b_end = (t.b_pos + t.b_len - eff).astype(np.int32)
+    l = np.full(n, R - 2 * eff, dtype=np.int32)
+    backsplice = (t.b_pos - (t.a_pos + t.a_len)) < 0
+    flags = (backsplice.astype(np.uint8) * 1) | (t.reverse.astype(np.uint8) * 2)
+    internal = np.ascontiguousarray(t.reads[:, eff : R - eff])
+    return t.chrom.astype(np.int32), a_start, b_end, l, flags.astype(np.uint8), internal
+
+
+class GenomeStrings:
+    """oracle-style genome.get over a synth genome"""
+
+    def __init__(self, g):
+        self.seqs = {n: s.tobytes().decode() for n, s in zip(g.names, g.seqs)}
+        self.names = list(g.names)
+
+    get = O.Genome.get
+
+
+def oracle_scan(gs, names, chrom, a_start, b_end, l, flags, internal, opt):
+    """first tie + n_hits per pair, through the oracle's per-split loop"""
+    out = []
+    for i in range(len(chrom)):
+        li = int(l[i])
+        if li < 0:
+            out.append(None)
+            continue
+        c = names[int(chrom[i])]
+        a0, b1 = int(a_start[i]), int(b_end[i])
+        af = gs.get(c, a0, a0 + li + 2).upper()
+        bf = gs.get(c, b1 - li - 2, b1).upper()
+        inner = internal[i, :li].tobytes().decode().upper()
+        hits = O.scan_windows(af, bf, inner, c, a0, b1, bool(flags[i] & 1), "-" if flags[i] & 2 else "+", opt)
+        if not hits:
+            out.append(None)
+        else:
+            h = hits[0]
+            out.append((h.start, h.end, h.strand, int(h.dist), h.ov, h.gtag, h.n_hits))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- host harness
+_HARNESS = None
+
+
+def host_harness():
+    """device scan code compiled for the host (tests/tools/scan_host_harness.cpp)"""
+    global _HARNESS
+    if _HARNESS is None:
+        src = os.path.join(ROOT, "tests", "tools", "scan_host_harness.cpp")
+        so = os.path.join(ROOT, "tests", "tools", "libscan_host_harness.so")
+        core = os.path.join(ROOT, "find_circ2_b200", "csrc", "scan_core.cuh")
+        if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core)):
+            subprocess.check_call(
+                ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", so, src]
+            )
+        lib = ctypes.CDLL(so)
+        lib.hh_genome_build.restype = ctypes.c_void_p
+        lib.hh_genome_build.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        lib.hh_genome_free.argtypes = [ctypes.c_void_p]
+        lib.hh_pack_reads.argtypes = [ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int] + [
+            ctypes.c_void_p
+        ] * 3
+        lib.hh_scan.argtypes = (
+            [ctypes.c_void_p] + [ctypes.c_int] * 5 + [ctypes.c_int64] + [ctypes.c_void_p] * 7 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+        )
+        _HARNESS = lib
+    return _HARNESS
+
+
+def harness_scan(g, chrom, a_start, b_end, l, flags, internal, margin, maxdist, noncanonical=0, strandpref=0, nw=None,
+                 force_per_base=0):
+    lib = host_harness()
+    seqs = [np.ascontiguousarray(s) for s in g.seqs]
+    ptrs = (ctypes.c_void_p * len(seqs))(*[s.ctypes.data for s in seqs])
+    sizes = np.array([len(s) for s in seqs], dtype=np.int64)
+    h = lib.hh_genome_build(len(seqs), ptrs, sizes.ctypes.data)
+    try:
+        n = len(chrom)
+        max_l = int(max(l.max(), 0)) if n else 0
+        n_words = max(1, (max_l + 15) // 16)
+        stride = internal.shape[1] if internal.ndim == 2 and internal.shape[1] else 1
+        internal = np.ascontiguousarray(internal)
+        rd2 = np.zeros(n_words * n, dtype=np.uint32)
+        rdn = np.zeros(n_words * n, dtype=np.uint32)
+        flags = flags.copy()
+        lib.hh_pack_reads(n, internal.ctypes.data, stride, l.ctypes.data, n_words, rd2.ctypes.data, rdn.ctypes.data, flags.ctypes.data)
+        if nw is None:
+            need = max_l + 2
+            nw = 3 if need <= 48 else 5 if need <= 80 else 8 if need <= 128 else 12 if need <= 192 else 16
+        out = np.zeros((n, 4), dtype=np.uint32)
+        rc = lib.hh_scan(h, margin, maxdist, noncanonical, strandpref, nw, n, chrom.ctypes.data, a_start.ctypes.data,
+                         b_end.ctypes.data, l.ctypes.data, flags.ctypes.data, rd2.ctypes.data, rdn.ctypes.data, n_words,
+                         out.ctypes.data, force_per_base)
+        assert rc == 0
+        return out
+    finally:
+        lib.hh_genome_free(h)

@@ -1,0 +1,390 @@
+"""
+GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI of
+libfindcirc_b200.so; the oracle (oracle/find_circ_oracle.py) is the checker.  Bit-exact.
+"""
+import os
+from collections import defaultdict
+
+import numpy as np
+import pytest
+
+import helpers as H
+from conftest import GOLDEN
+from find_circ2_b200 import synth
+from oracle import find_circ_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    return torch
+
+
+def _engine(**kw):
+    from find_circ2_b200.engine import Engine
+
+    return Engine(device=0, **kw)
+
+
+def _case(read_len, asize, seed, n=3000, error_rate=0.01, sizes=(60000, 45000, 7000)):
+    g = synth.make_genome(list(sizes), seed=seed, n_frac=0.01, n_run=(20, 200))
+    J = synth.plant_junctions(g, 80, 50, seed=seed + 1, span=(150, 8000), margin=300)
+    t = synth.make_pairs(g, J, n, read_len=read_len, asize=asize, seed=seed + 2, error_rate=error_rate, frac_decoy=0.15,
+                         frac_edge=0.05, frac_read_n=0.03, frac_inner_shift=0.2)
+    return g, J, t
+
+
+# ---------------------------------------------------------------------------------------------- genome store
+def test_genome_fetch_matches_reference_get(tmp_path):
+    """device 2-bit + N-mask store vs indexed_fasta.get_data semantics (find_circ.py:189-215), incl. N padding,
+    soft-masked letters and ragged last FASTA lines"""
+    fa = os.path.join(GOLDEN, "synth_a", "genome.fa")
+    og = O.Genome(fa)
+    e = _engine()
+    e.load_genome_fasta(fa)
+    assert e.chrom_names == og.names
+    assert e.chrom_sizes == [og.size(n) for n in og.names]
+    rng = np.random.default_rng(5)
+    for name in og.names:
+        cid = e.chrom_id(name)
+        size = og.size(name)
+        assert e.fetch(cid, 0, size) == og.get(name, 0, size).upper()
+        for _ in range(50):
+            s = int(rng.integers(-300, size + 100))
+            ln = int(rng.integers(1, 400))
+            assert e.fetch(cid, s, s + ln) == og.get(name, s, s + ln).upper(), (name, s, ln)
+        assert e.fetch(cid, -100, 5) == "N" * 100 + og.get(name, 0, 5).upper()
+        assert e.fetch(cid, size - 3, size + 50) == og.get(name, size - 3, size).upper() + "N" * 50
+    st = e.genome_stats()
+    assert st["bases"] == sum(e.chrom_sizes)
+    assert st["n"] == sum(og.seqs[n].upper().count("N") for n in og.names)
+    with pytest.raises(KeyError):
+        e.chrom_id("no_such_chrom")
+    e.close()
+
+
+def test_genome_from_reference_fixtures():
+    for case in ("kat3", "cdr1as"):
+        fa = os.path.join(GOLDEN, case, "genome.fa")
+        og = O.Genome(fa)
+        e = _engine()
+        e.load_genome_fasta(fa)
+        for name in og.names:
+            assert e.fetch(e.chrom_id(name), -10, og.size(name) + 10) == og.get(name, -10, og.size(name) + 10).upper()
+        e.close()
+
+
+def test_missing_genome_is_an_error(tmp_path):
+    from find_circ2_b200._lib import FindCircError
+
+    e = _engine()
+    with pytest.raises(FindCircError):
+        e.load_genome_fasta(str(tmp_path / "nope.fa"))
+    with pytest.raises(FindCircError):
+        e.scan_host(np.zeros(1, np.int32), np.zeros(1, np.int32), np.zeros(1, np.int32), np.zeros(1, np.int32),
+                    np.zeros(1, np.uint8), np.zeros((1, 4), np.uint8))
+    e.close()
+
+
+# ---------------------------------------------------------------------------------------------- scan
+PARAM_SETS = [
+    (100, 20, 2, 2, 0, 0),
+    (100, 15, 2, 2, 0, 0),
+    (76, 20, 2, 2, 0, 0),
+    (150, 20, 2, 2, 0, 0),
+    (250, 20, 2, 2, 0, 0),
+    (300, 15, 2, 2, 0, 0),
+    (100, 20, 0, 0, 0, 0),
+    (100, 20, 4, 3, 0, 1),
+    (100, 20, 2, 2, 1, 0),
+    (100, 20, 2, 2, 1, 1),
+    (44, 20, 2, 2, 0, 0),
+    (36, 20, 2, 2, 0, 0),
+]
+
+
+@pytest.mark.parametrize("read_len,asize,margin,maxdist,nonc,spref", PARAM_SETS)
+def test_scan_matches_oracle(read_len, asize, margin, maxdist, nonc, spref):
+    g, J, t = _case(read_len, asize, seed=300 + read_len + asize + margin + nonc)
+    chrom, a_start, b_end, l, flags, internal = H.pairs_to_soa(t, asize, margin)
+    opt = O.Options(asize=asize, margin=margin, maxdist=maxdist, noncanonical=bool(nonc), strandpref=bool(spref))
+    want = H.oracle_scan(H.GenomeStrings(g), g.names, chrom, a_start, b_end, l, flags, internal, opt)
+    e = _engine(asize=asize, margin=margin, maxdist=maxdist, noncanonical=bool(nonc), strandpref=bool(spref))
+    e.load_genome_arrays(g.names, g.seqs)
+    hits = e.scan_host(chrom, a_start, b_end, l, flags, internal)
+    got = [H.decode_hit(r) for r in hits.view(np.uint32).reshape(-1, 4)]
+    bad = [(i, got[i], want[i]) for i in range(len(want)) if got[i] != want[i]]
+    assert not bad, bad[:5]
+    assert sum(1 for w in want if w) > 0.3 * len(want) or read_len < 50
+    e.close()
+
+
+def test_scan_edge_inputs():
+    """empty batch, l < 0, l == 0, ragged lengths inside one batch"""
+    g, J, t = _case(100, 20, seed=77, n=400)
+    e = _engine(asize=20)
+    e.load_genome_arrays(g.names, g.seqs)
+    z = np.zeros(0, np.int32)
+    assert len(e.scan_host(z, z, z, z, np.zeros(0, np.uint8), np.zeros((0, 8), np.uint8))) == 0
+    chrom, a_start, b_end, l, flags, internal = H.pairs_to_soa(t, 20, 2)
+    # ragged: shorten the internal part of some pairs (as shorter reads in the same batch would)
+    l = l.copy()
+    a_start = a_start.copy()
+    rng = np.random.default_rng(3)
+    cut = rng.integers(0, 70, size=len(l))
+    l = np.maximum(l - cut, -3).astype(np.int32)
+    opt = O.Options(asize=20)
+    want = H.oracle_scan(H.GenomeStrings(g), g.names, chrom, a_start, b_end, l, flags, internal, opt)
+    hits = e.scan_host(chrom, a_start, b_end, l, flags, internal)
+    got = [H.decode_hit(r) for r in hits.view(np.uint32).reshape(-1, 4)]
+    assert got == want
+    assert (l == 0).any() or True
+    e.close()
+
+
+def test_device_path_equals_host_path(torch_cuda):
+    torch = torch_cuda
+    g, J, t = _case(100, 20, seed=9)
+    chrom, a_start, b_end, l, flags, internal = H.pairs_to_soa(t, 20, 2)
+    e = _engine(asize=20)
+    e.load_genome_arrays(g.names, g.seqs)
+    host = e.scan_host(chrom, a_start, b_end, l, flags, internal)
+    dev = torch.device("cuda:0")
+    n = len(chrom)
+    n_words = (int(l.max()) + 15) // 16
+    d = {k: torch.from_numpy(v).to(dev) for k, v in dict(chrom=chrom, a=a_start, b=b_end, l=l, fl=flags, asc=internal).items()}
+    rd2 = torch.zeros(n_words * n, dtype=torch.int32, device=dev)
+    rdn = torch.zeros(n_words * n, dtype=torch.int32, device=dev)
+    out = torch.zeros(n * 4, dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    e.pack_reads(d["asc"], internal.shape[1], d["l"], n_words, rd2, rdn, d["fl"], st)
+    pairs = e.make_pairs(n, d["chrom"], d["a"], d["b"], d["l"], d["fl"], rd2, rdn, n_words, int(l.max()))
+    e.scan(pairs, out, st)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().view(np.uint32).reshape(-1, 4)
+    assert np.array_equal(got, host.view(np.uint32).reshape(-1, 4))
+    e.close()
+
+
+def test_all_ties_enumeration(torch_cuda):
+    """--all-hits: every tie in the reference's order (find_circ.py:966-974, 1312-1317)"""
+    torch = torch_cuda
+    g, J, t = _case(100, 20, seed=21, n=1200)
+    chrom, a_start, b_end, l, flags, internal = H.pairs_to_soa(t, 20, 2)
+    for nonc in (1, 0):
+        opt = O.Options(asize=20, noncanonical=bool(nonc), allhits=True)
+        e = _engine(asize=20, noncanonical=bool(nonc))
+        e.load_genome_arrays(g.names, g.seqs)
+        dev = torch.device("cuda:0")
+        n = len(chrom)
+        n_words = (int(l.max()) + 15) // 16
+        d = {k: torch.from_numpy(v).to(dev) for k, v in dict(chrom=chrom, a=a_start, b=b_end, l=l, fl=flags, asc=internal).items()}
+        rd2 = torch.zeros(n_words * n, dtype=torch.int32, device=dev)
+        rdn = torch.zeros(n_words * n, dtype=torch.int32, device=dev)
+        out = torch.zeros(n * 4, dtype=torch.int32, device=dev)
+        e.pack_reads(d["asc"], internal.shape[1], d["l"], n_words, rd2, rdn, d["fl"], 0)
+        pairs = e.make_pairs(n, d["chrom"], d["a"], d["b"], d["l"], d["fl"], rd2, rdn, n_words, int(l.max()))
+        e.scan(pairs, out, 0)
+        torch.cuda.synchronize()
+        hits = out.cpu().numpy().view(np.uint32).reshape(-1, 4)
+        nh = (hits[:, 2] & 0xFFFF).astype(np.int64)
+        off = np.zeros(n + 1, dtype=np.int64)
+        off[1:] = np.cumsum(nh)
+        d_off = torch.from_numpy(off).to(dev)
+        ties = torch.zeros(max(int(off[-1]), 1) * 4, dtype=torch.int32, device=dev)
+        e.scan_ties(pairs, out, d_off, ties, 0)
+        torch.cuda.synchronize()
+        tt = ties.cpu().numpy().view(np.uint32).reshape(-1, 4)
+        gs = H.GenomeStrings(g)
+        for i in range(n):
+            li = int(l[i])
+            c = g.names[int(chrom[i])]
+            a0, b1 = int(a_start[i]), int(b_end[i])
+            want = O.scan_windows(gs.get(c, a0, a0 + li + 2).upper(), gs.get(c, b1 - li - 2, b1).upper(),
+                                  internal[i, :li].tobytes().decode(), c, a0, b1, bool(flags[i] & 1),
+                                  "-" if flags[i] & 2 else "+", opt)
+            want = [(h.start, h.end, h.strand, int(h.dist), h.ov, h.gtag, h.n_hits) for h in want]
+            got = [H.decode_hit(tt[k]) for k in range(off[i], off[i + 1])]
+            assert got == want, (i, got[:3], want[:3])
+        e.close()
+
+
+# ---------------------------------------------------------------------------------------------- aggregation
+def _py_aggregate(recs):
+    """dict-based restatement of Hit.add / reductions (find_circ.py:526-600) over fc_jrec-like rows"""
+    acc = {}
+    for r in recs:
+        key = (int(r["chrom"]), int(r["start"]), int(r["end"]), int(r["sk"]) & 3)
+        a = acc.setdefault(key, dict(first=int(r["idx"]), w=0.0, b=0.0, n=0, ql=[], qr=[], d=[], o=[], nh=[], rh=set(),
+                                     qh=set(), pal=set(), sig=0))
+        wt = 1.0 / ((int(r["sk"]) >> 8) & 0xFF)
+        a["w"] += wt
+        if r["q_left"] != 0 and r["q_right"] != 0:
+            a["b"] += wt
+        a["n"] += 1
+        a["ql"].append(int(r["q_left"]))
+        a["qr"].append(int(r["q_right"]))
+        a["d"].append(int(r["dist"]))
+        a["o"].append(int(r["ov"]))
+        a["nh"].append(int(r["n_hits"]))
+        a["rh"].add(int(r["read_hash"]))
+        if int(r["read_hash"]) & 1:
+            a["pal"].add(int(r["read_hash"]))
+        a["qh"].add(int(r["qname_hash"]))
+        a["sig"] = (int(r["sk"]) >> 16) & 0xFFF
+    out = []
+    for key, a in sorted(acc.items(), key=lambda kv: kv[1]["first"]):
+        out.append((key, a["first"], a["w"], a["b"], a["n"], len(a["qh"]), len(a["rh"]) - (len(a["pal"]) + 1) // 2,
+                    max(a["ql"]), max(a["qr"]), min(a["nh"]), min(a["d"]), min(a["o"]), a["sig"]))
+    return out
+
+
+def _junction_rows(j):
+    return [((int(r["chrom"]), int(r["start"]), int(r["end"]), int(r["sk"]) & 3), int(r["first_idx"]), float(r["n_weighted"]),
+             float(r["n_uniq_bridges"]), int(r["n_spanned"]), int(r["n_frags"]), int(r["n_uniq"]), int(r["best_q_left"]),
+             int(r["best_q_right"]), int(r["min_n_hits"]), int(r["min_dist"]), int(r["min_ov"]), (int(r["sk"]) >> 16) & 0xFFF)
+            for r in j]
+
+
+def _random_records(n, n_keys, seed, dens=(1, 1, 1, 2, 2, 3, 4, 5, 8)):
+    from find_circ2_b200._lib import JREC_DTYPE
+
+    rng = np.random.default_rng(seed)
+    keys = np.zeros(n_keys, dtype=[("chrom", "u4"), ("start", "u4"), ("end", "u4"), ("s", "u4")])
+    keys["chrom"] = rng.integers(0, 5, n_keys)
+    keys["start"] = rng.integers(0, 1 << 20, n_keys)
+    keys["end"] = keys["start"] + rng.integers(1, 1 << 16, n_keys)
+    keys["s"] = rng.integers(0, 4, n_keys)
+    w = 1.0 / np.arange(1, n_keys + 1)
+    pick = rng.choice(n_keys, size=n, p=w / w.sum())
+    r = np.zeros(n, dtype=JREC_DTYPE)
+    r["chrom"] = keys["chrom"][pick]
+    r["start"] = keys["start"][pick]
+    r["end"] = keys["end"][pick]
+    den = rng.choice(np.array(dens), size=n)
+    r["sk"] = keys["s"][pick] | (den.astype(np.uint32) << 8) | (np.uint32(0x4D3) << 16)
+    r["idx"] = np.arange(n, dtype=np.uint64) * 3 + 7
+    # few distinct reads / names so that duplicates occur; some palindromes (bit 0)
+    r["read_hash"] = rng.integers(0, max(n // 3, 2), n).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    r["qname_hash"] = rng.integers(0, max(n // 2, 2), n).astype(np.uint64) * np.uint64(0xC2B2AE3D27D4EB4F)
+    r["q_left"] = rng.integers(-5, 60, n)
+    r["q_right"] = rng.integers(-5, 60, n)
+    r["q_left"][rng.random(n) < 0.1] = 0
+    r["n_hits"] = rng.integers(1, 5, n)
+    r["dist"] = rng.integers(0, 3, n)
+    r["ov"] = rng.integers(0, 3, n)
+    return r
+
+
+@pytest.mark.parametrize("n,n_keys,seed", [(1, 1, 1), (37, 5, 2), (5000, 300, 3), (200000, 5000, 4), (300000, 3, 5)])
+def test_aggregation_matches_python(n, n_keys, seed):
+    recs = _random_records(n, n_keys, seed)
+    e = _engine()
+    e.agg_reset()
+    # appended in three pieces: stream order must survive
+    cuts = [0, n // 3, n // 2, n]
+    for a, b in zip(cuts, cuts[1:]):
+        e.agg_append_host(recs[a:b])
+    assert e.agg_n_records() == n
+    nj = e.agg_finalize()
+    got = _junction_rows(e.agg_fetch(nj))
+    want = _py_aggregate(recs)
+    assert len(got) == len(want)
+    for gr, wr in zip(got, want):
+        assert gr == wr, (gr, wr)
+    # finalize is idempotent
+    assert e.agg_finalize() == nj
+    e.agg_reset()
+    assert e.agg_finalize() == 0
+    e.close()
+
+
+def test_emit_from_scan_matches_python(torch_cuda):
+    """scan -> fc_agg_emit -> finalize on the device == python aggregation of the oracle's first ties"""
+    torch = torch_cuda
+    g, J, t = _case(100, 20, seed=31, n=6000, error_rate=0.005)
+    chrom, a_start, b_end, l, flags, internal = H.pairs_to_soa(t, 20, 2)
+    n = len(chrom)
+    opt = O.Options(asize=20)
+    want_hits = H.oracle_scan(H.GenomeStrings(g), g.names, chrom, a_start, b_end, l, flags, internal, opt)
+    e = _engine(asize=20)
+    e.load_genome_arrays(g.names, g.seqs)
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(8)
+    wden = rng.choice(np.array([1, 1, 1, 2, 3], dtype=np.uint8), size=n)
+    q_a = (t.as_a - np.maximum(t.xs_a, 0)).astype(np.int16)
+    q_b = (t.as_b - np.maximum(t.xs_b, 0)).astype(np.int16)
+    lens = np.full(n, t.read_len, dtype=np.int32)
+    rh = e.hash_reads(t.reads, lens)
+    qh = np.array([e.hash_bytes(("r%d" % (i // 2)).encode()) for i in range(n)], dtype=np.uint64)
+    n_words = (int(l.max()) + 15) // 16
+    tn = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    d_chrom, d_a, d_b, d_l, d_fl, d_asc = tn(chrom), tn(a_start), tn(b_end), tn(l), tn(flags), tn(internal)
+    rd2 = torch.zeros(n_words * n, dtype=torch.int32, device=dev)
+    rdn = torch.zeros(n_words * n, dtype=torch.int32, device=dev)
+    out = torch.zeros(n * 4, dtype=torch.int32, device=dev)
+    e.pack_reads(d_asc, internal.shape[1], d_l, n_words, rd2, rdn, d_fl, 0)
+    pairs = e.make_pairs(n, d_chrom, d_a, d_b, d_l, d_fl, rd2, rdn, n_words, int(l.max()))
+    e.agg_reset()
+    half = n // 2
+    e.scan(pairs, out, 0)
+    d_w, d_qa, d_qb, d_rh, d_qh = tn(wden), tn(q_a), tn(q_b), tn(rh.view(np.int64)), tn(qh.view(np.int64))
+    # emit in two batches with consecutive idx ranges
+    for lo, hi in ((0, half), (half, n)):
+        e.agg_emit(hi - lo, out[4 * lo:], d_chrom[lo:], d_fl[lo:], d_w[lo:], d_qa[lo:], d_qb[lo:], d_rh[lo:], d_qh[lo:], 1000 + lo, 0)
+    nj = e.agg_finalize()
+    got = _junction_rows(e.agg_fetch(nj))
+    # python side
+    from find_circ2_b200._lib import JREC_DTYPE
+
+    rows = []
+    for i, h in enumerate(want_hits):
+        if h is None:
+            continue
+        start, end, strand, dist, ov, sig, nh = h
+        back = bool(flags[i] & 1)
+        r = np.zeros((), dtype=JREC_DTYPE)
+        r["chrom"], r["start"], r["end"] = chrom[i], start, end
+        sigc = sum("ACGTN".index(ch) << (3 * k) for k, ch in enumerate(sig))
+        r["sk"] = (1 if strand == "-" else 0) | (0 if back else 2) | (int(rh[i]) & 1) << 2 | int(wden[i]) << 8 | sigc << 16
+        r["idx"] = 1000 + i
+        r["read_hash"], r["qname_hash"] = rh[i], qh[i]
+        r["q_left"], r["q_right"] = (q_b[i], q_a[i]) if back else (q_a[i], q_b[i])
+        r["n_hits"], r["dist"], r["ov"] = nh, dist, ov
+        rows.append(r)
+    want = _py_aggregate(rows)
+    assert e.agg_n_records() == len(rows)
+    assert got == want
+    e.close()
+
+
+def test_partition_by_key(torch_cuda):
+    """hash partition for the multi-GPU exchange: every key goes to exactly one rank, stream order kept per rank"""
+    torch = torch_cuda
+    from find_circ2_b200._lib import JREC_DTYPE
+
+    recs = _random_records(50000, 700, 12)
+    e = _engine()
+    e.agg_reset()
+    e.agg_append_host(recs)
+    outbuf = torch.zeros(len(recs) * 48, dtype=torch.uint8, device="cuda:0")
+    for n_ranks in (1, 2, 3, 8):
+        counts = e.agg_partition(n_ranks, outbuf, 0)
+        torch.cuda.synchronize()
+        assert counts.sum() == len(recs)
+        out = outbuf.cpu().numpy().view(JREC_DTYPE)
+        seen = {}
+        pos = 0
+        for r in range(n_ranks):
+            part = out[pos : pos + counts[r]]
+            pos += counts[r]
+            assert (np.diff(part["idx"].astype(np.int64)) > 0).all()
+            for k in set(zip(part["chrom"].tolist(), part["start"].tolist(), part["end"].tolist(), (part["sk"] & 3).tolist())):
+                assert k not in seen
+                seen[k] = r
+        assert sorted(out["idx"].tolist()) == sorted(recs["idx"].tolist())
+    e.close()
