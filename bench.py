@@ -224,18 +224,17 @@ def run_gpu(args):
     soa, idx = soa_from_table(t, eng)
     n = len(idx)
     max_l = int(soa["l"].max())
-    n_words = (max_l + 15) // 16
+    n_words = max(1, (max_l + 31) // 32)
     stride = soa["internal"].shape[1]
 
     # ---- device-resident copy of the batch (for `value`)
     tn = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
     d = {k: tn(v if v.dtype != np.uint64 else v.view(np.int64)) for k, v in soa.items()}
-    rd2 = torch.zeros(n_words * n, dtype=torch.int32, device=dev)
-    rdn = torch.zeros(n_words * n, dtype=torch.int32, device=dev)
+    planes = torch.zeros(3 * n_words * n, dtype=torch.int32, device=dev)
     hits = torch.zeros(n * 4, dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
-    eng.pack_reads(d["internal"], stride, d["l"], n_words, rd2, rdn, d["flags"], stream)
-    pairs = eng.make_pairs(n, d["chrom"], d["a_start"], d["b_end"], d["l"], d["flags"], rd2, rdn, n_words, max_l)
+    eng.pack_reads(d["internal"], stride, d["l"], n_words, planes, d["flags"], stream)
+    pairs = eng.make_pairs(n, d["chrom"], d["a_start"], d["b_end"], d["l"], d["flags"], planes, n_words, max_l)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     idx_base = rank * (1 << 40)
 

@@ -42,7 +42,7 @@ class ScanParams(C.Structure):
 class Pairs(C.Structure):
     _fields_ = [
         ("n", C.c_int64), ("d_chrom", C.c_void_p), ("d_a_start", C.c_void_p), ("d_b_end", C.c_void_p),
-        ("d_l", C.c_void_p), ("d_flags", C.c_void_p), ("d_rd2", C.c_void_p), ("d_rdn", C.c_void_p),
+        ("d_l", C.c_void_p), ("d_flags", C.c_void_p), ("d_rlo", C.c_void_p), ("d_rhi", C.c_void_p), ("d_rn", C.c_void_p),
         ("n_words", C.c_int32), ("max_l", C.c_int32),
     ]
 
@@ -79,7 +79,7 @@ SYMBOLS = [
     ("fc_genome_chrom_id", C.c_int, [_P, C.c_char_p]),
     ("fc_genome_stats", C.c_int, [_P, _P]),
     ("fc_genome_fetch", C.c_int, [_P, C.c_int32, C.c_int64, C.c_int64, _P]),
-    ("fc_pack_reads", C.c_int, [_P, C.c_int64, _P, C.c_int32, _P, C.c_int32, _P, _P, _P, _P]),
+    ("fc_pack_reads", C.c_int, [_P, C.c_int64, _P, C.c_int32, _P, C.c_int32, _P, _P, _P, _P, _P]),
     ("fc_scan", C.c_int, [_P, C.POINTER(ScanParams), C.POINTER(Pairs), _P, _P]),
     ("fc_scan_ties", C.c_int, [_P, C.POINTER(ScanParams), C.POINTER(Pairs), _P, _P, _P, _P]),
     ("fc_scan_host", C.c_int, [_P, C.POINTER(ScanParams), C.c_int64, _P, _P, _P, _P, _P, _P, C.c_int32, _P]),

@@ -17,21 +17,31 @@ struct fc_genome {
   std::vector<int64_t> offs;  // global base offset of each chromosome
   int64_t total = 0;          // padded length in bases
   int64_t n_bases = 0, n_n = 0, n_other = 0;
-  uint32_t* d_seq2 = nullptr;
-  uint32_t* d_nmask = nullptr;
-  uint32_t* d_nsum = nullptr;
+  uint32_t* d_plo = nullptr;
+  uint32_t* d_phi = nullptr;
+  uint32_t* d_pn = nullptr;
+  uint32_t* d_tiles = nullptr;
+  int tile_T = 0, tile_S = 0, tile_W = 0;
+  uint64_t tile_magic = 0;
+  int64_t tile_bytes = 0;
   int64_t* d_off = nullptr;
   int64_t* d_size = nullptr;
   int64_t dev_bytes = 0;
   fc::GenomeView view() const {
     fc::GenomeView v;
-    v.seq2 = d_seq2;
-    v.nmask = d_nmask;
-    v.nsum = d_nsum;
+    v.plo = d_plo;
+    v.phi = d_phi;
+    v.pn = d_pn;
     v.chrom_off = d_off;
     v.chrom_size = d_size;
     v.n_chrom = (int32_t)names.size();
     v.pad = FC_GENOME_PAD;
+    v.tiles = d_tiles;
+    v.tile_magic = tile_magic;
+    v.tile_T = d_tiles ? tile_T : 0;
+    v.tile_S = tile_S;
+    v.tile_W = d_tiles ? tile_W : 0;
+    v.reserved = 0;
     return v;
   }
 };
@@ -66,6 +76,7 @@ struct fc_ctx {
 };
 
 int fc_fail(fc_ctx* ctx, int code, const char* fmt, ...);
+int fc_genome_ensure_tiles(fc_ctx* ctx, int w, cudaStream_t st);
 
 #define FC_CUDA(ctx, call)                                                                         \
   do {                                                                                             \

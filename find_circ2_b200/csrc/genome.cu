@@ -1,12 +1,14 @@
 // genome.cu -- device-resident genome store.
 //
 // Replaces Track / GenomeAccessor / indexed_fasta (/root/reference/find_circ.py:103-215, 242-371): instead of an
-// mmap'ed FASTA sliced per request, every chromosome is packed once (on the GPU) into
-//   seq2   2 bits / base            (A0 C1 G2 T3)
-//   nmask  1 bit  / base            (not ACGT -> reads as 'N')
-//   nsum   1 bit  / 64-base block   (block contains an N: lets the scan skip the mask in the common case)
+// mmap'ed FASTA sliced per request, every chromosome is packed once (on the GPU) into three bit planes
+//   plo / phi   low / high bit of the 2-bit base code (A0 C1 G2 T3)
+//   pn          1 = not ACGT -> reads as 'N'
 // laid out in ONE global coordinate space with FC_GENOME_PAD bases of N between chromosomes, so that windows
 // hanging over a chromosome end read 'N' exactly as find_circ.py:194-211 pads them.
+// For the scan the planes are additionally re-cut into overlapping sector-sized tiles (see scan_core.cuh):
+// 180 GB of HBM make the 2-4x replication of a mammalian genome a non-issue, and it turns every window fetch
+// into a single 256-bit load per 32-byte sector with the N summary in-band.
 #include <stdarg.h>
 #include <string.h>
 
@@ -16,52 +18,61 @@
 
 namespace {
 
-constexpr int64_t ALIGN = 2048;          // chromosome offsets: one nsum word
+constexpr int64_t ALIGN = 2048;          // chromosome offsets
 constexpr int64_t CHUNK = 32ll << 20;    // ASCII staging chunk (bases), multiple of ALIGN
+constexpr int64_t SLACK_BASES = 4096;    // readable bases past `total` (tile building and unaligned window loads)
 
-// one thread per 64-base block of the chunk; a warp therefore owns one nsum word
+// one thread per 32-base word of the chunk: 32 ASCII bytes in, one word per plane out
 __global__ void pack_chunk_kernel(const uint8_t* __restrict__ ascii, int64_t chunk_bases /*valid bytes in ascii*/,
-                                  int64_t gbase /*global base index of ascii[0], multiple of 2048*/,
-                                  int64_t n_blocks, uint32_t* __restrict__ seq2, uint32_t* __restrict__ nmask,
-                                  uint32_t* __restrict__ nsum, unsigned long long* __restrict__ counters) {
-  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool active = b < n_blocks;
-  uint32_t anyn = 0;
+                                  int64_t gbase /*global base index of ascii[0], multiple of 32*/, int64_t n_words,
+                                  uint32_t* __restrict__ plo, uint32_t* __restrict__ phi, uint32_t* __restrict__ pn,
+                                  unsigned long long* __restrict__ counters) {
+  int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned n_n = 0, n_other = 0;
-  if (active) {
-    int64_t s = b * 64;
-    uint32_t w2[4] = {0, 0, 0, 0}, wn[2] = {0, 0};
-    for (int j = 0; j < 64; ++j) {
-      int64_t p = s + j;
-      uint32_t code = 0, isn = 1;
-      if (p < chunk_bases) {
-        uint32_t c = ascii[p] & 0xDFu;
+  if (w < n_words) {
+    int64_t s = w * 32;
+    uint32_t lo = 0, hi = 0, nn = 0;
+    if (s + 32 <= chunk_bases) {
+      const uint4* src = reinterpret_cast<const uint4*>(ascii + s);
+      uint4 v[2] = {src[0], src[1]};
+      const uint8_t* b = reinterpret_cast<const uint8_t*>(v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        uint32_t c = b[j] & 0xDFu;
+        uint32_t code = 0, isn = 1;
         if (c == 'A') { code = 0; isn = 0; }
         else if (c == 'C') { code = 1; isn = 0; }
         else if (c == 'G') { code = 2; isn = 0; }
         else if (c == 'T') { code = 3; isn = 0; }
         else if (c == 'N') { n_n++; }
         else { n_other++; }
+        lo |= (code & 1u) << j;
+        hi |= (code >> 1) << j;
+        nn |= isn << j;
       }
-      w2[j >> 4] |= code << (2 * (j & 15));
-      wn[j >> 5] |= isn << (j & 31);
+    } else {
+      for (int j = 0; j < 32; ++j) {
+        int64_t p = s + j;
+        uint32_t code = 0, isn = 1;
+        if (p < chunk_bases) {
+          uint32_t c = ascii[p] & 0xDFu;
+          if (c == 'A') { code = 0; isn = 0; }
+          else if (c == 'C') { code = 1; isn = 0; }
+          else if (c == 'G') { code = 2; isn = 0; }
+          else if (c == 'T') { code = 3; isn = 0; }
+          else if (c == 'N') { n_n++; }
+          else { n_other++; }
+        }
+        lo |= (code & 1u) << j;
+        hi |= (code >> 1) << j;
+        nn |= isn << j;
+      }
     }
-    int64_t g = gbase + s;
-    uint4* dst = reinterpret_cast<uint4*>(seq2 + (g >> 4));
-    *dst = make_uint4(w2[0], w2[1], w2[2], w2[3]);
-    uint2* dn = reinterpret_cast<uint2*>(nmask + (g >> 5));
-    *dn = make_uint2(wn[0], wn[1]);
-    anyn = (wn[0] | wn[1]) != 0u;
+    int64_t gw = (gbase >> 5) + w;
+    plo[gw] = lo;
+    phi[gw] = hi;
+    pn[gw] = nn;
   }
-  uint32_t ball = __ballot_sync(0xffffffffu, anyn);
-  if ((threadIdx.x & 31) == 0 && b < n_blocks + 31) {
-    int64_t g = gbase + (b & ~31ll) * 64;
-    // lanes beyond n_blocks belong to padding (already N); keep their bits set
-    int64_t remaining = n_blocks - (b & ~31ll);
-    uint32_t keep = remaining >= 32 ? 0u : (remaining <= 0 ? ~0u : (~0u << remaining));
-    if (remaining > 0) nsum[g >> 11] = ball | keep;
-  }
-  // counters
   for (int o = 16; o; o >>= 1) {
     n_n += __shfl_down_sync(0xffffffffu, n_n, o);
     n_other += __shfl_down_sync(0xffffffffu, n_other, o);
@@ -69,6 +80,43 @@ __global__ void pack_chunk_kernel(const uint8_t* __restrict__ ascii, int64_t chu
   if ((threadIdx.x & 31) == 0) {
     if (n_n) atomicAdd(&counters[0], (unsigned long long)n_n);
     if (n_other) atomicAdd(&counters[1], (unsigned long long)n_other);
+  }
+}
+
+__device__ inline uint32_t extract32(const uint32_t* __restrict__ plane, int64_t bit) {
+  const uint32_t* p = plane + (bit >> 5);
+  return __funnelshift_r(p[0], p[1], (uint32_t)(bit & 31));
+}
+
+// one thread per tile: cut 4T words per plane out of the master planes at base t*S, put the N summary in the
+// 4 spare bits of the lo plane's last word
+__global__ void build_tiles_kernel(const uint32_t* __restrict__ plo, const uint32_t* __restrict__ phi,
+                                   const uint32_t* __restrict__ pn, int64_t n_tiles, int T, int S,
+                                   uint32_t* __restrict__ tiles) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  const int PW = 4 * T;
+  const int64_t g0 = t * (int64_t)S;
+  uint32_t* dst = tiles + t * (int64_t)(8 * T);
+  uint32_t anyn = 0;
+  for (int j = 0; j < PW; ++j) {
+    uint32_t lo = extract32(plo, g0 + 32 * j);
+    uint32_t hi = extract32(phi, g0 + 32 * j);
+    uint32_t nn = extract32(pn, g0 + 32 * j);
+    if (j == PW - 1) {
+      lo &= 0x0FFFFFFFu;
+      hi &= 0x0FFFFFFFu;
+      nn &= 0x0FFFFFFFu;
+    }
+    anyn |= nn;
+    if (j == PW - 1 && anyn) lo |= fc::TILE_FLAG_N;
+    if (j < PW - 1) {
+      dst[j] = lo;
+    } else {
+      // the flag depends on all words: written last
+      dst[j] = lo;
+    }
+    dst[PW + j] = hi;
   }
 }
 
@@ -80,9 +128,10 @@ __global__ void fetch_kernel(fc::GenomeView g, int64_t gp, int64_t n, char* __re
 }
 
 void genome_free(fc_genome& g) {
-  cudaFree(g.d_seq2);
-  cudaFree(g.d_nmask);
-  cudaFree(g.d_nsum);
+  cudaFree(g.d_plo);
+  cudaFree(g.d_phi);
+  cudaFree(g.d_pn);
+  cudaFree(g.d_tiles);
   cudaFree(g.d_off);
   cudaFree(g.d_size);
   g = fc_genome();
@@ -98,19 +147,19 @@ int genome_layout(fc_ctx* ctx) {
     off += g.sizes[i] + FC_GENOME_PAD;
   }
   g.total = (off + ALIGN - 1) / ALIGN * ALIGN + ALIGN;
-  int64_t b2 = g.total / 4 + 256, bn = g.total / 8 + 256, bs = g.total / 64 / 8 + 256;
-  FC_CUDA(ctx, cudaMalloc(&g.d_seq2, b2));
-  FC_CUDA(ctx, cudaMalloc(&g.d_nmask, bn));
-  FC_CUDA(ctx, cudaMalloc(&g.d_nsum, bs));
-  FC_CUDA(ctx, cudaMemset(g.d_seq2, 0, b2));
-  FC_CUDA(ctx, cudaMemset(g.d_nmask, 0xFF, bn));
-  FC_CUDA(ctx, cudaMemset(g.d_nsum, 0xFF, bs));
+  int64_t bp = (g.total + SLACK_BASES) / 8 + 256;  // bytes per plane
+  FC_CUDA(ctx, cudaMalloc(&g.d_plo, bp));
+  FC_CUDA(ctx, cudaMalloc(&g.d_phi, bp));
+  FC_CUDA(ctx, cudaMalloc(&g.d_pn, bp));
+  FC_CUDA(ctx, cudaMemset(g.d_plo, 0, bp));
+  FC_CUDA(ctx, cudaMemset(g.d_phi, 0, bp));
+  FC_CUDA(ctx, cudaMemset(g.d_pn, 0xFF, bp));
   size_t nc = g.sizes.size();
   FC_CUDA(ctx, cudaMalloc(&g.d_off, sizeof(int64_t) * std::max<size_t>(nc, 1)));
   FC_CUDA(ctx, cudaMalloc(&g.d_size, sizeof(int64_t) * std::max<size_t>(nc, 1)));
   FC_CUDA(ctx, cudaMemcpy(g.d_off, g.offs.data(), sizeof(int64_t) * nc, cudaMemcpyHostToDevice));
   FC_CUDA(ctx, cudaMemcpy(g.d_size, g.sizes.data(), sizeof(int64_t) * nc, cudaMemcpyHostToDevice));
-  g.dev_bytes = b2 + bn + bs + 2 * sizeof(int64_t) * nc;
+  g.dev_bytes = 3 * bp + 2 * sizeof(int64_t) * nc;
   return FC_OK;
 }
 
@@ -149,16 +198,15 @@ struct Packer {
     if (chrom < 0) return FC_OK;
     if (fill == 0 && !last_of_chrom) return FC_OK;
     int64_t gbase = g.offs[chrom] + chrom_pos;
-    // a partial trailing block is completed with N by the kernel; only the last chunk of a chromosome may be partial
-    int64_t n_blocks = (fill + 63) / 64;
-    if (n_blocks > 0) {
+    // a partial trailing word is completed with N by the kernel; only the last chunk of a chromosome may be partial
+    int64_t n_words = (fill + 31) / 32;
+    if (n_words > 0) {
       cudaStream_t st = ctx->own_stream;
       FC_CUDA(ctx, cudaMemcpyAsync(d_stage[cur], h_stage[cur], fill, cudaMemcpyHostToDevice, st));
       int threads = 256;
-      int64_t nthreads = (n_blocks + 31) / 32 * 32;
+      int64_t nthreads = (n_words + 31) / 32 * 32;
       int blocks = (int)((nthreads + threads - 1) / threads);
-      pack_chunk_kernel<<<blocks, threads, 0, st>>>(d_stage[cur], fill, gbase, n_blocks, g.d_seq2, g.d_nmask, g.d_nsum,
-                                                    d_cnt);
+      pack_chunk_kernel<<<blocks, threads, 0, st>>>(d_stage[cur], fill, gbase, n_words, g.d_plo, g.d_phi, g.d_pn, d_cnt);
       FC_LAUNCH_CHECK(ctx);
       FC_CUDA(ctx, cudaEventRecord(done[cur], st));
     }
@@ -376,6 +424,40 @@ extern "C" int fc_genome_fetch(fc_ctx* ctx, int32_t chrom, int64_t start, int64_
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->own_stream);
   cudaFree(d);
   if (e != cudaSuccess) return fc_fail(ctx, FC_E_CUDA, "fetch copy failed: %s", cudaGetErrorString(e));
+  return FC_OK;
+}
+
+// (re)build the tile store so that windows of up to `w` bases fit inside one tile
+int fc_genome_ensure_tiles(fc_ctx* ctx, int w, cudaStream_t st) {
+  fc_genome& g = ctx->genome;
+  if (!g.loaded) return fc_fail(ctx, FC_E_NOGENOME, "no genome loaded");
+  if (w < 8) w = 8;
+  if (w > 256) w = 256;
+  if (g.d_tiles && w <= g.tile_W) return FC_OK;
+  w = (w + 3) / 4 * 4;  // a little head-room so that slightly longer reads do not trigger a rebuild
+  int T, P, S;
+  fc::tile_geometry(w, T, P, S);
+  if (S < 2) return fc_fail(ctx, FC_E_ARG, "tile stride too small for window %d", w);
+  int64_t n_tiles = g.total / S + 2;
+  size_t bytes = (size_t)n_tiles * 32 * T + 256;
+  if (g.d_tiles) {
+    FC_CUDA(ctx, cudaStreamSynchronize(st));
+    FC_CUDA(ctx, cudaDeviceSynchronize());
+    cudaFree(g.d_tiles);
+    g.d_tiles = nullptr;
+    g.dev_bytes -= g.tile_bytes;
+  }
+  FC_CUDA(ctx, cudaMalloc(&g.d_tiles, bytes));
+  int threads = 128;
+  build_tiles_kernel<<<(unsigned)((n_tiles + threads - 1) / threads), threads, 0, st>>>(g.d_plo, g.d_phi, g.d_pn, n_tiles, T,
+                                                                                       S, g.d_tiles);
+  FC_LAUNCH_CHECK(ctx);
+  g.tile_T = T;
+  g.tile_S = S;
+  g.tile_W = w;
+  g.tile_magic = (~0ull) / (uint64_t)S + 1ull;
+  g.tile_bytes = (int64_t)bytes;
+  g.dev_bytes += g.tile_bytes;
   return FC_OK;
 }
 

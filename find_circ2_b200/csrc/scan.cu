@@ -6,46 +6,47 @@
 
 namespace {
 
-// ---------------------------------------------------------------- ASCII -> 2-bit internal read words
+// ---------------------------------------------------------------- ASCII -> bit planes of the internal read part
 // one thread per pair; rows are read 16 bytes at a time when the matrix is 16-byte aligned
 __global__ void pack_reads_kernel(int64_t n, const uint8_t* __restrict__ ascii, int32_t stride,
-                                  const int32_t* __restrict__ l, int32_t n_words, uint32_t* __restrict__ rd2,
-                                  uint32_t* __restrict__ rdn, uint8_t* __restrict__ flags, int aligned16) {
+                                  const int32_t* __restrict__ l, int32_t n_words, uint32_t* __restrict__ rlo,
+                                  uint32_t* __restrict__ rhi, uint32_t* __restrict__ rn, uint8_t* __restrict__ flags,
+                                  int aligned16) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int li = l[i];
   const uint8_t* row = ascii + i * (int64_t)stride;
   uint32_t any = 0;
   for (int w = 0; w < n_words; ++w) {
-    int count = li - 16 * w;
-    count = count < 0 ? 0 : (count > 16 ? 16 : count);
-    uint32_t w2 = 0, wn = 0;
+    int count = li - 32 * w;
+    count = count < 0 ? 0 : (count > 32 ? 32 : count);
+    uint32_t lo = 0, hi = 0, nn = 0;
     if (count > 0) {
       if (aligned16) {
-        uint4 v = __ldg(reinterpret_cast<const uint4*>(row + 16 * w));
-        uint8_t tmp[16];
-        *reinterpret_cast<uint4*>(tmp) = v;
-        fc::pack16(tmp, count, w2, wn);
+        uint4 v[2];
+        v[0] = __ldg(reinterpret_cast<const uint4*>(row + 32 * w));
+        v[1] = count > 16 ? __ldg(reinterpret_cast<const uint4*>(row + 32 * w + 16)) : make_uint4(0, 0, 0, 0);
+        fc::pack32(reinterpret_cast<const uint8_t*>(v), count, lo, hi, nn);
       } else {
-        fc::pack16(row + 16 * w, count, w2, wn);
+        fc::pack32(row + 32 * w, count, lo, hi, nn);
       }
     }
-    rd2[(int64_t)w * n + i] = w2;
-    rdn[(int64_t)w * n + i] = wn;
-    any |= wn;
+    rlo[(int64_t)w * n + i] = lo;
+    rhi[(int64_t)w * n + i] = hi;
+    rn[(int64_t)w * n + i] = nn;
+    any |= nn;
   }
   if (any) flags[i] |= (uint8_t)FC_PF_READ_N;
 }
 
 // ---------------------------------------------------------------- the scan
-template <int NW>
-__global__ void __launch_bounds__(256) scan_kernel(fc::GenomeView g, fc::ScanCfg cfg, int64_t n,
+template <int NP, int T>
+__global__ void __launch_bounds__(256) scan_kernel(fc::GenomeView g, fc::ScanCfg cfg, fc::ReadView rv,
                                                    const int32_t* __restrict__ chrom,
                                                    const int32_t* __restrict__ a_start,
                                                    const int32_t* __restrict__ b_end, const int32_t* __restrict__ l,
-                                                   const uint8_t* __restrict__ flags,
-                                                   const uint32_t* __restrict__ rd2, const uint32_t* __restrict__ rdn,
-                                                   int n_words, fc_hit* __restrict__ out) {
+                                                   const uint8_t* __restrict__ flags, fc_hit* __restrict__ out) {
+  const int64_t n = rv.n;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     fc::PairArgs p;
     p.chrom = chrom[i];
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(256) scan_kernel(fc::GenomeView g, fc::ScanCfg
     p.flags = flags[i];
     fc::HitOut h;
     fc::NoEmit ne;
-    fc::scan_pair<NW>(g, cfg, p, rd2, rdn, n, i, n_words, h, ne, false);
+    fc::scan_pair<NP, T>(g, cfg, p, rv, i, h, ne, false);
     reinterpret_cast<uint4*>(out)[i] = make_uint4((uint32_t)h.start, (uint32_t)h.end, h.w2, h.w3);
   }
 }
@@ -73,7 +74,6 @@ struct TieEmit {
     fc::Best b;
     b.score = s;
     b.n_ties = n_ties;
-    b.n_total = 0;
     b.x = x;
     b.info = strand | (sig << 1) | ((uint32_t)dist << 16) | ((uint32_t)ov << 24);
     fc::HitOut h;
@@ -82,14 +82,13 @@ struct TieEmit {
   }
 };
 
-__global__ void ties_kernel(fc::GenomeView g, fc::ScanCfg cfg, int64_t n, const int32_t* __restrict__ chrom,
+__global__ void ties_kernel(fc::GenomeView g, fc::ScanCfg cfg, fc::ReadView rv, const int32_t* __restrict__ chrom,
                             const int32_t* __restrict__ a_start, const int32_t* __restrict__ b_end,
                             const int32_t* __restrict__ l, const uint8_t* __restrict__ flags,
-                            const uint32_t* __restrict__ rd2, const uint32_t* __restrict__ rdn,
                             const fc_hit* __restrict__ hits, const int64_t* __restrict__ tie_off,
                             fc_hit* __restrict__ ties) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= rv.n) return;
   int nh = (int)(hits[i].w2 & 0xFFFFu);
   if (nh == 0) return;
   if (hits[i].w3 & fc::W3_RANGE) return;
@@ -100,7 +99,7 @@ __global__ void ties_kernel(fc::GenomeView g, fc::ScanCfg cfg, int64_t n, const 
   fc::Best best;
   best.init();
   fc::NoEmit ne;
-  fc::scan_per_base(g, cfg, ga, gb, li, (fl & 2u) != 0, rd2, rdn, n, i, (fl & 4u) != 0, best, ne);
+  fc::scan_per_base(g, cfg, ga, gb, li, (fl & 2u) != 0, rv, i, (fl & 4u) != 0, best, ne);
   TieEmit te;
   te.best = best.score;
   te.dst = ties + tie_off[i];
@@ -112,7 +111,7 @@ __global__ void ties_kernel(fc::GenomeView g, fc::ScanCfg cfg, int64_t n, const 
   te.k = 0;
   fc::Best dummy;
   dummy.init();
-  fc::scan_per_base(g, cfg, ga, gb, li, (fl & 2u) != 0, rd2, rdn, n, i, (fl & 4u) != 0, dummy, te);
+  fc::scan_per_base(g, cfg, ga, gb, li, (fl & 2u) != 0, rv, i, (fl & 4u) != 0, dummy, te);
 }
 
 int check_pairs(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs* pr) {
@@ -123,7 +122,7 @@ int check_pairs(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs* pr) {
   if (pr->n < 0) return fc_fail(ctx, FC_E_ARG, "negative pair count");
   if (pr->max_l + 2 > FC_GENOME_PAD)
     return fc_fail(ctx, FC_E_ARG, "internal read length %d exceeds the genome padding (%d)", pr->max_l, FC_GENOME_PAD);
-  if (pr->n > 0 && pr->n_words * 16 < pr->max_l)
+  if (pr->n > 0 && pr->n_words * 32 < pr->max_l)
     return fc_fail(ctx, FC_E_ARG, "n_words=%d too small for max_l=%d", pr->n_words, pr->max_l);
   return FC_OK;
 }
@@ -131,13 +130,14 @@ int check_pairs(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs* pr) {
 }  // namespace
 
 extern "C" int fc_pack_reads(fc_ctx* ctx, int64_t n, const uint8_t* d_ascii, int32_t stride, const int32_t* d_l,
-                             int32_t n_words, uint32_t* d_rd2, uint32_t* d_rdn, uint8_t* d_flags, void* stream) {
+                             int32_t n_words, uint32_t* d_rlo, uint32_t* d_rhi, uint32_t* d_rn, uint8_t* d_flags,
+                             void* stream) {
   if (!ctx || n < 0 || n_words < 0) return FC_E_ARG;
   if (n == 0 || n_words == 0) return FC_OK;
   int threads = 128;
-  int aligned16 = ((reinterpret_cast<uintptr_t>(d_ascii) | (uintptr_t)stride) & 15u) == 0 && n_words * 16 <= stride;
+  int aligned16 = ((reinterpret_cast<uintptr_t>(d_ascii) | (uintptr_t)stride) & 15u) == 0 && n_words * 32 <= stride;
   pack_reads_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
-      n, d_ascii, stride, d_l, n_words, d_rd2, d_rdn, d_flags, aligned16);
+      n, d_ascii, stride, d_l, n_words, d_rlo, d_rhi, d_rn, d_flags, aligned16);
   FC_LAUNCH_CHECK(ctx);
   return FC_OK;
 }
@@ -146,24 +146,34 @@ extern "C" int fc_scan(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs* pr,
   int rc = check_pairs(ctx, p, pr);
   if (rc) return rc;
   if (pr->n == 0) return FC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int need = pr->max_l + 2;
+  if (!p->noncanonical) {
+    rc = fc_genome_ensure_tiles(ctx, need, st);  // no-op when the tile store already covers this window size
+    if (rc) return rc;
+  }
   fc::ScanCfg cfg{p->margin, p->maxdist, p->noncanonical, p->strandpref};
   fc::GenomeView g = ctx->genome.view();
-  cudaStream_t st = (cudaStream_t)stream;
+  fc::ReadView rv{pr->d_rlo, pr->d_rhi, pr->d_rn, pr->n, pr->n_words};
   const int threads = 256;
   // grid: whole waves of resident CTAs (148 SMs x 8 CTAs of 256 threads), grid-stride beyond that
   int64_t want = (pr->n + threads - 1) / threads;
   int64_t wave = (int64_t)ctx->sm_count * 8;
   int64_t blocks = want <= wave ? want : ((want + wave - 1) / wave) * wave;
   if (blocks > wave * 64) blocks = wave * 64;
-  int need = pr->max_l + 2;
-#define FC_SCAN_LAUNCH(NW)                                                                                          \
-  scan_kernel<NW><<<(unsigned)blocks, threads, 0, st>>>(g, cfg, pr->n, pr->d_chrom, pr->d_a_start, pr->d_b_end, pr->d_l, \
-                                                        pr->d_flags, pr->d_rd2, pr->d_rdn, pr->n_words, d_out)
-  if (need <= 48) FC_SCAN_LAUNCH(3);
-  else if (need <= 80) FC_SCAN_LAUNCH(5);
-  else if (need <= 128) FC_SCAN_LAUNCH(8);
-  else if (need <= 192) FC_SCAN_LAUNCH(12);
-  else FC_SCAN_LAUNCH(16);  // longer pairs take the per-base path inside the kernel
+#define FC_SCAN_LAUNCH(NP, T)                                                                                          \
+  scan_kernel<NP, T><<<(unsigned)blocks, threads, 0, st>>>(g, cfg, rv, pr->d_chrom, pr->d_a_start, pr->d_b_end, pr->d_l, \
+                                                           pr->d_flags, d_out)
+  // the kernel specialisation follows the tile geometry of the store (scan_core.cuh: tile_geometry)
+  switch (g.tile_T) {
+    case 1:
+      if (need <= 64) FC_SCAN_LAUNCH(2, 1);
+      else FC_SCAN_LAUNCH(3, 1);
+      break;
+    case 2: FC_SCAN_LAUNCH(4, 2); break;
+    case 4: FC_SCAN_LAUNCH(8, 4); break;
+    default: FC_SCAN_LAUNCH(8, 0); break;  // no tile store (--non-canonical): master planes / per-base path
+  }
 #undef FC_SCAN_LAUNCH
   FC_LAUNCH_CHECK(ctx);
   return FC_OK;
@@ -176,9 +186,10 @@ extern "C" int fc_scan_ties(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs
   if (pr->n == 0) return FC_OK;
   fc::ScanCfg cfg{p->margin, p->maxdist, p->noncanonical, p->strandpref};
   int threads = 128;
+  fc::ReadView rv{pr->d_rlo, pr->d_rhi, pr->d_rn, pr->n, pr->n_words};
   ties_kernel<<<(unsigned)((pr->n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
-      ctx->genome.view(), cfg, pr->n, pr->d_chrom, pr->d_a_start, pr->d_b_end, pr->d_l, pr->d_flags, pr->d_rd2,
-      pr->d_rdn, d_hits, d_tie_off, d_ties);
+      ctx->genome.view(), cfg, rv, pr->d_chrom, pr->d_a_start, pr->d_b_end, pr->d_l, pr->d_flags, d_hits, d_tie_off,
+      d_ties);
   FC_LAUNCH_CHECK(ctx);
   return FC_OK;
 }
@@ -194,21 +205,23 @@ extern "C" int fc_scan_host(fc_ctx* ctx, const fc_scan_params* p, int64_t n, con
   int32_t max_l = 0;
   for (int64_t i = 0; i < n; ++i) max_l = h_l[i] > max_l ? h_l[i] : max_l;
   if (max_l > stride) return fc_fail(ctx, FC_E_ARG, "stride %d smaller than the longest internal read %d", stride, max_l);
-  int32_t n_words = (max_l + 15) / 16;
+  int32_t n_words = (max_l + 31) / 32;
   if (n_words < 1) n_words = 1;
   size_t sizes[9] = {sizeof(int32_t) * (size_t)n, sizeof(int32_t) * (size_t)n, sizeof(int32_t) * (size_t)n,
                      sizeof(int32_t) * (size_t)n, (size_t)n + 4,           (size_t)n * (size_t)stride,
                      sizeof(uint32_t) * (size_t)n * n_words, sizeof(uint32_t) * (size_t)n * n_words,
                      sizeof(fc_hit) * (size_t)n};
   for (int k = 0; k < 9; ++k) FC_CUDA(ctx, ctx->host_path[k].reserve(sizes[k], st, false, 0));
+  FC_CUDA(ctx, ctx->host_path[14].reserve(sizes[6], st, false, 0));
   int32_t* d_chrom = (int32_t*)ctx->host_path[0].p;
   int32_t* d_a = (int32_t*)ctx->host_path[1].p;
   int32_t* d_b = (int32_t*)ctx->host_path[2].p;
   int32_t* d_l = (int32_t*)ctx->host_path[3].p;
   uint8_t* d_fl = (uint8_t*)ctx->host_path[4].p;
   uint8_t* d_asc = (uint8_t*)ctx->host_path[5].p;
-  uint32_t* d_rd2 = (uint32_t*)ctx->host_path[6].p;
-  uint32_t* d_rdn = (uint32_t*)ctx->host_path[7].p;
+  uint32_t* d_rlo = (uint32_t*)ctx->host_path[6].p;
+  uint32_t* d_rhi = (uint32_t*)ctx->host_path[7].p;
+  uint32_t* d_rn = (uint32_t*)ctx->host_path[14].p;
   fc_hit* d_out = (fc_hit*)ctx->host_path[8].p;
   FC_CUDA(ctx, cudaMemcpyAsync(d_chrom, h_chrom, sizes[0], cudaMemcpyHostToDevice, st));
   FC_CUDA(ctx, cudaMemcpyAsync(d_a, h_a_start, sizes[1], cudaMemcpyHostToDevice, st));
@@ -216,7 +229,7 @@ extern "C" int fc_scan_host(fc_ctx* ctx, const fc_scan_params* p, int64_t n, con
   FC_CUDA(ctx, cudaMemcpyAsync(d_l, h_l, sizes[3], cudaMemcpyHostToDevice, st));
   FC_CUDA(ctx, cudaMemcpyAsync(d_fl, h_flags, (size_t)n, cudaMemcpyHostToDevice, st));
   FC_CUDA(ctx, cudaMemcpyAsync(d_asc, h_ascii, sizes[5], cudaMemcpyHostToDevice, st));
-  int rc = fc_pack_reads(ctx, n, d_asc, stride, d_l, n_words, d_rd2, d_rdn, d_fl, st);
+  int rc = fc_pack_reads(ctx, n, d_asc, stride, d_l, n_words, d_rlo, d_rhi, d_rn, d_fl, st);
   if (rc) return rc;
   fc_pairs pr;
   pr.n = n;
@@ -225,8 +238,9 @@ extern "C" int fc_scan_host(fc_ctx* ctx, const fc_scan_params* p, int64_t n, con
   pr.d_b_end = d_b;
   pr.d_l = d_l;
   pr.d_flags = d_fl;
-  pr.d_rd2 = d_rd2;
-  pr.d_rdn = d_rdn;
+  pr.d_rlo = d_rlo;
+  pr.d_rhi = d_rhi;
+  pr.d_rn = d_rn;
   pr.n_words = n_words;
   pr.max_l = max_l;
   rc = fc_scan(ctx, p, &pr, d_out, st);
@@ -251,12 +265,13 @@ extern "C" int fc_batch_host(fc_ctx* ctx, const fc_scan_params* p, int64_t n, co
   int32_t max_l = 0;
   for (int64_t i = 0; i < n; ++i) max_l = h_l[i] > max_l ? h_l[i] : max_l;
   if (max_l > stride) return fc_fail(ctx, FC_E_ARG, "stride %d smaller than the longest internal read %d", stride, max_l);
-  int32_t n_words = (max_l + 15) / 16;
+  int32_t n_words = (max_l + 31) / 32;
   if (n_words < 1) n_words = 1;
   const size_t N = (size_t)n;
   size_t sizes[14] = {4 * N, 4 * N, 4 * N, 4 * N, N + 4, N * (size_t)stride, 4 * N * n_words, 4 * N * n_words,
                       sizeof(fc_hit) * N, N, 2 * N, 2 * N, 8 * N, 8 * N};
   for (int k = 0; k < 14; ++k) FC_CUDA(ctx, ctx->host_path[k].reserve(sizes[k], st, false, 0));
+  FC_CUDA(ctx, ctx->host_path[14].reserve(sizes[6], st, false, 0));
   void** d = nullptr;
   void* dp[14];
   for (int k = 0; k < 14; ++k) dp[k] = ctx->host_path[k].p;
@@ -270,7 +285,7 @@ extern "C" int fc_batch_host(fc_ctx* ctx, const fc_scan_params* p, int64_t n, co
     FC_CUDA(ctx, cudaMemcpyAsync(dp[k], src[k], bytes, cudaMemcpyHostToDevice, st));
   }
   int rc = fc_pack_reads(ctx, n, (const uint8_t*)dp[5], stride, (const int32_t*)dp[3], n_words, (uint32_t*)dp[6],
-                         (uint32_t*)dp[7], (uint8_t*)dp[4], st);
+                         (uint32_t*)dp[7], (uint32_t*)ctx->host_path[14].p, (uint8_t*)dp[4], st);
   if (rc) return rc;
   fc_pairs pr;
   pr.n = n;
@@ -279,8 +294,9 @@ extern "C" int fc_batch_host(fc_ctx* ctx, const fc_scan_params* p, int64_t n, co
   pr.d_b_end = (const int32_t*)dp[2];
   pr.d_l = (const int32_t*)dp[3];
   pr.d_flags = (const uint8_t*)dp[4];
-  pr.d_rd2 = (const uint32_t*)dp[6];
-  pr.d_rdn = (const uint32_t*)dp[7];
+  pr.d_rlo = (const uint32_t*)dp[6];
+  pr.d_rhi = (const uint32_t*)dp[7];
+  pr.d_rn = (const uint32_t*)ctx->host_path[14].p;
   pr.n_words = n_words;
   pr.max_l = max_l;
   rc = fc_scan(ctx, p, &pr, (fc_hit*)dp[8], st);

@@ -10,13 +10,18 @@
 //                     keep if dist<=maxdist and (A[x],A[x+1],B[x],B[x+1]) is GT/AG ('+') or CT/AC ('-')   (:915-954)
 //     rank by 20*canonical - 10*dist - ov (+100*strand match), stable, ties counted         (:792-799, 961-974)
 //
-// B200 formulation (one thread per pair, everything in registers):
-//   * windows are funnel-shifted out of two/three 128-bit loads of the 2-bit genome;
-//   * mismatch flags mA/mB are one XOR + fold per 16 bases; dist(x) = popc(mA below x) + popc(mB at/above x) -> O(l/16);
-//   * GT/AG and CT/AC positions are found for all x at once with bit logic on the 2-bit planes, so only the
-//     (on average ~1.5) signal-bearing split positions are ever scored;
-//   * pairs whose windows touch an N (coarse 64-base summary bit), whose read contains N, that are longer than the
-//     compiled register budget, or that run with --non-canonical take an exact per-base path.
+// B200 formulation -- one thread per pair, everything in registers, 1 bit per base and plane:
+//   * the genome is held as bit planes (lo / hi bit of the 2-bit code, plus an N plane).  For the scan the planes
+//     are re-cut into overlapping 32*T-byte TILES (stride chosen so that every window lies inside one tile), the
+//     lo and hi plane of a tile sit in the same sector(s) and 4 spare bits flag "tile contains N": one 256-bit
+//     load per sector fetches a whole window including its N summary -- two gathers per pair when T = 1;
+//   * mismatch flags of 32 bases cost two XORs and an OR; dist(x) = popc(mA below x) + popc(mB at/above x);
+//   * GT/AG and CT/AC positions are found for all split positions at once with plane logic, and a word is only
+//     searched when the mismatches before it (donor side) and after it (acceptor side) both stay <= maxdist,
+//     so chance signals far from the true breakpoint are never scored;
+//   * windows or reads containing N take the same bit-parallel code with the N planes loaded from the master store
+//     (bytes are compared as the reference does: N equals N and differs from every base);
+//   * --non-canonical and windows longer than 256 bases take an exact per-base loop.
 #pragma once
 #include <stdint.h>
 
@@ -29,13 +34,21 @@
 namespace fc {
 
 struct GenomeView {
-  const uint32_t* seq2;   // 16 bases / word, A0 C1 G2 T3 (N stored as 0)
-  const uint32_t* nmask;  // 32 bases / word, 1 = not ACGT
-  const uint32_t* nsum;   // one bit per 64-base block: block contains a non-ACGT base
-  const int64_t* chrom_off;   // global index of base 0 of each chromosome (multiple of 128, >= PAD)
+  // master store: 1 bit per base and plane, base g at word g>>5, bit g&31
+  const uint32_t* plo;
+  const uint32_t* phi;
+  const uint32_t* pn;  // 1 = not ACGT (reads as 'N'); the padding between chromosomes is N
+  const int64_t* chrom_off;  // global index of base 0 of each chromosome
   const int64_t* chrom_size;
   int32_t n_chrom;
   int32_t pad;  // bases of N padding on both sides of every chromosome
+  // tile store (may be absent: tile_T == 0)
+  const uint32_t* tiles;   // tile t: 4T words lo plane (top 4 bits of the last word = flags), then 4T words hi plane
+  uint64_t tile_magic;     // ceil(2^64 / tile_S)
+  int32_t tile_T;          // sectors per tile (1, 2 or 4)
+  int32_t tile_S;          // stride in bases between tile starts
+  int32_t tile_W;          // largest window (bases) guaranteed to fit in one tile
+  int32_t reserved;
 };
 
 struct ScanCfg {
@@ -47,10 +60,10 @@ struct HitOut {
   uint32_t w2, w3;
 };
 
-constexpr uint32_t M55 = 0x55555555u;
 constexpr uint32_t SIG_GTAG = 2u | (3u << 3) | (0u << 6) | (2u << 9);
 constexpr uint32_t W3_RANGE = 1u << 30;
 constexpr uint32_t W3_SLOW = 1u << 31;
+constexpr uint32_t TILE_FLAG_N = 1u << 31;
 
 FC_HD int popc32(uint32_t x) {
 #if defined(__CUDA_ARCH__)
@@ -73,6 +86,15 @@ FC_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {  // (hi:lo >> s)
   return s ? (lo >> s) | (hi << (32 - s)) : lo;
 #endif
 }
+FC_HD int imin(int a, int b) { return a < b ? a : b; }
+FC_HD int imax(int a, int b) { return a > b ? a : b; }
+FC_HD uint32_t low_mask(int k) {  // k in [0,32]: the k lowest bits
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_rc(0xFFFFFFFFu, 0u, 32 - k);
+#else
+  return k >= 32 ? 0xFFFFFFFFu : ((1u << k) - 1u);
+#endif
+}
 FC_HD uint32_t ldg32(const uint32_t* p) {
 #if defined(__CUDA_ARCH__)
   return __ldg(p);
@@ -80,15 +102,21 @@ FC_HD uint32_t ldg32(const uint32_t* p) {
   return *p;
 #endif
 }
-struct U4 {
-  uint32_t x, y, z, w;
-};
-FC_HD U4 ldg128(const uint32_t* p) {  // p 16-byte aligned
+FC_HD uint64_t umul64hi(uint64_t a, uint64_t b) {
 #if defined(__CUDA_ARCH__)
-  uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
-  return U4{v.x, v.y, v.z, v.w};
+  return __umul64hi(a, b);
 #else
-  return U4{p[0], p[1], p[2], p[3]};
+  return (uint64_t)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+// one 32-byte sector (8 words), p 32-byte aligned
+FC_HD void ldg256(const uint32_t* p, uint32_t (&v)[8]) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p));
+#else
+  for (int k = 0; k < 8; ++k) v[k] = p[k];
 #endif
 }
 
@@ -96,19 +124,16 @@ FC_HD U4 ldg128(const uint32_t* p) {  // p 16-byte aligned
 struct Best {
   int score;     // best score so far
   int n_ties;    // hits with that score
-  int n_total;   // all hits
   int x;         // split position of the first best hit
   uint32_t info; // strand | sig<<1 | dist<<16 | ov<<24 of the first best hit
   FC_HD void init() {
     score = -100000;
     n_ties = 0;
-    n_total = 0;
     x = -1;
     info = 0;
   }
   // hits must be offered in the reference's list order (ascending x, '+' before '-')
   FC_HD void offer(int s, int xx, uint32_t strand, uint32_t sig, int dist, int ov) {
-    n_total++;
     if (s > score) {
       score = s;
       n_ties = 1;
@@ -153,14 +178,25 @@ FC_HD void finish(const Best& b, int a_start, int b_end, int l, bool backsplice,
 
 // ---------------------------------------------------------------- exact per-base path
 FC_HD int gcode(const GenomeView& g, int64_t gp) {  // 0..3, 4 = N
-  uint32_t nm = ldg32(g.nmask + (gp >> 5));
-  if ((nm >> (gp & 31)) & 1u) return 4;
-  return (int)((ldg32(g.seq2 + (gp >> 4)) >> (2 * (gp & 15))) & 3u);
+  const int64_t w = gp >> 5;
+  const uint32_t sh = (uint32_t)(gp & 31);
+  if ((ldg32(g.pn + w) >> sh) & 1u) return 4;
+  return (int)(((ldg32(g.plo + w) >> sh) & 1u) | (((ldg32(g.phi + w) >> sh) & 1u) << 1));
 }
-FC_HD int rcode(const uint32_t* rd2, const uint32_t* rdn, int64_t n, int64_t i, int j, bool has_n) {
-  int w = j >> 4, sh = 2 * (j & 15);
-  if (has_n && ((ldg32(rdn + (int64_t)w * n + i) >> sh) & 1u)) return 4;
-  return (int)((ldg32(rd2 + (int64_t)w * n + i) >> sh) & 3u);
+
+struct ReadView {
+  const uint32_t* rlo;  // word-major: word w of pair i at [w*n + i], base j in word j>>5, bit j&31
+  const uint32_t* rhi;
+  const uint32_t* rn;
+  int64_t n;
+  int32_t n_words;
+};
+
+FC_HD int rcode(const ReadView& rv, int64_t i, int j, bool has_n) {
+  const int64_t a = (int64_t)(j >> 5) * rv.n + i;
+  const uint32_t sh = (uint32_t)(j & 31);
+  if (has_n && ((ldg32(rv.rn + a) >> sh) & 1u)) return 4;
+  return (int)(((ldg32(rv.rlo + a) >> sh) & 1u) | (((ldg32(rv.rhi + a) >> sh) & 1u) << 1));
 }
 FC_HD uint32_t comp_code(uint32_t c) { return c == 4 ? 4u : 3u - c; }
 
@@ -171,11 +207,10 @@ struct NoEmit {
 
 template <class Emit>
 FC_HD void scan_per_base(const GenomeView& g, const ScanCfg& cfg, int64_t ga, int64_t gb, int l, bool minus_span,
-                         const uint32_t* rd2, const uint32_t* rdn, int64_t n, int64_t i, bool has_n, Best& best,
-                         Emit& emit) {
+                         const ReadView& rv, int64_t i, bool has_n, Best& best, Emit& emit) {
   // dist(0): everything explained by the acceptor side
   int dist = 0;
-  for (int j = 0; j < l; ++j) dist += gcode(g, gb + j + 2) != rcode(rd2, rdn, n, i, j, has_n);
+  for (int j = 0; j < l; ++j) dist += gcode(g, gb + j + 2) != rcode(rv, i, j, has_n);
   for (int x = 0; x <= l; ++x) {
     if (dist <= cfg.maxdist) {
       uint32_t a0 = gcode(g, ga + x), a1 = gcode(g, ga + x + 1), b0 = gcode(g, gb + x), b1 = gcode(g, gb + x + 1);
@@ -202,93 +237,111 @@ FC_HD void scan_per_base(const GenomeView& g, const ScanCfg& cfg, int64_t ga, in
       }
     }
     if (x < l) {
-      int r = rcode(rd2, rdn, n, i, x, has_n);
+      int r = rcode(rv, i, x, has_n);
       dist += (gcode(g, ga + x) != r) - (gcode(g, gb + x + 2) != r);
     }
   }
 }
 
-// ---------------------------------------------------------------- bit-parallel path
-// Extract NW 32-bit words (16 bases each) starting at global base index gp.
-template <int NW>
-FC_HD void load_window(const GenomeView& g, int64_t gp, int nbases, uint32_t (&W)[NW + 1]) {
-  constexpr int NQ = (NW + 4 + 3) / 4;  // 128-bit loads that can be touched: NW words + up to 3 words of misalignment + 1
-  constexpr int NS = NQ * 4;
-  uint32_t s[NS + 2];
-  const int64_t q0 = gp >> 6;        // 64 bases per 16 bytes
-  const int o = (int)(gp & 63);      // base offset inside the first 16-byte chunk
-  const uint32_t* base = g.seq2 + q0 * 4;
-  const int last_q = (o + nbases - 1) >> 6;  // index of the last chunk actually needed
+// ---------------------------------------------------------------- window loaders
+// A window is NP words per plane (32 bases per word) + one zero guard word.
+template <int NP>
+struct Window {
+  uint32_t lo[NP + 1], hi[NP + 1];
+};
+
+// from the master planes: any alignment, NP+1 scalar loads per plane (rare path)
+template <int NP>
+FC_HD void load_plane(const uint32_t* plane, int64_t gp, uint32_t (&W)[NP + 1]) {
+  const uint32_t* base = plane + (gp >> 5);
+  const uint32_t bo = (uint32_t)(gp & 31);
+  uint32_t prev = ldg32(base);
 #pragma unroll
-  for (int q = 0; q < NQ; ++q) {
-    if (q <= last_q) {
-      U4 v = ldg128(base + q * 4);
-      s[q * 4 + 0] = v.x;
-      s[q * 4 + 1] = v.y;
-      s[q * 4 + 2] = v.z;
-      s[q * 4 + 3] = v.w;
-    } else {
-      s[q * 4 + 0] = s[q * 4 + 1] = s[q * 4 + 2] = s[q * 4 + 3] = 0;
+  for (int j = 0; j < NP; ++j) {
+    uint32_t next = ldg32(base + j + 1);
+    W[j] = funnel_r(prev, next, bo);
+    prev = next;
+  }
+  W[NP] = 0;
+}
+
+// from the tile store: one 256-bit load per sector.  Returns the tile flags (TILE_FLAG_N).
+template <int NP, int T>
+FC_HD uint32_t load_tile_window(const GenomeView& g, int64_t gp, Window<NP>& w) {
+  constexpr int PW = 4 * T;  // words per plane in a tile
+  const uint64_t t = umul64hi((uint64_t)gp, g.tile_magic);
+  const int o = (int)((uint64_t)gp - t * (uint64_t)g.tile_S);  // offset of the window inside the tile
+  const uint32_t* base = g.tiles + t * (uint64_t)(8 * T);
+  uint32_t s_lo[PW + 1], s_hi[PW + 1];
+  if (T == 1) {
+    uint32_t v[8];
+    ldg256(base, v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      s_lo[k] = v[k];
+      s_hi[k] = v[4 + k];
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < T / 2; ++q) {
+      uint32_t v[8];
+      ldg256(base + 8 * q, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s_lo[8 * q + k] = v[k];
+      ldg256(base + PW + 8 * q, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s_hi[8 * q + k] = v[k];
     }
   }
-  s[NS] = 0;
-  s[NS + 1] = 0;
-  const int wo = o >> 4;                  // whole-word offset 0..3
-  const uint32_t bo = (uint32_t)(o & 15) * 2;  // bit offset 0..30
-  if (wo & 2) {
+  const uint32_t flags = s_lo[PW - 1] & 0xF0000000u;
+  s_lo[PW - 1] &= 0x0FFFFFFFu;
+  s_lo[PW] = 0;
+  s_hi[PW] = 0;
+  // the window starts at word (o>>5), bit (o&31) of the tile planes
+  const int wo = o >> 5;
+  const uint32_t bo = (uint32_t)(o & 31);
+  constexpr int MAXWO = PW - NP + 1;  // largest word offset that can occur (window must fit)
 #pragma unroll
-    for (int k = 0; k < NS; ++k) s[k] = s[k + 2];
+  for (int step = 1; step <= MAXWO; step <<= 1) {
+    if (wo & step) {
+#pragma unroll
+      for (int k = 0; k <= PW; ++k) {
+        s_lo[k] = (k + step <= PW) ? s_lo[k + step] : 0u;
+        s_hi[k] = (k + step <= PW) ? s_hi[k + step] : 0u;
+      }
+    }
   }
-  if (wo & 1) {
 #pragma unroll
-    for (int k = 0; k < NS; ++k) s[k] = s[k + 1];
+  for (int j = 0; j < NP; ++j) {
+    w.lo[j] = funnel_r(s_lo[j], s_lo[j + 1], bo);
+    w.hi[j] = funnel_r(s_hi[j], s_hi[j + 1], bo);
   }
-#pragma unroll
-  for (int k = 0; k < NW; ++k) W[k] = funnel_r(s[k], s[k + 1], bo);
-  W[NW] = 0;
+  w.lo[NP] = 0;
+  w.hi[NP] = 0;
+  return flags;
 }
 
-// true when any 64-base block overlapping [gp, gp+nbases) contains a non-ACGT base
-FC_HD bool window_has_n(const GenomeView& g, int64_t gp, int nbases) {
-  int64_t b0 = gp >> 6, b1 = (gp + nbases - 1) >> 6;
-  int64_t w0 = b0 >> 5, w1 = b1 >> 5;
-  uint32_t lo = ldg32(g.nsum + w0);
-  uint32_t hi = (w1 != w0) ? ldg32(g.nsum + w0 + 1) : 0u;
-  uint64_t bits = (((uint64_t)hi << 32) | lo) >> (b0 & 31);
-  int nb = (int)(b1 - b0 + 1);  // <= 32 for windows up to ~2000 bases
-  uint64_t mask = nb >= 64 ? ~0ull : ((1ull << nb) - 1ull);
-  return (bits & mask) != 0ull;
-}
-
-FC_HD uint32_t valid_mask(int nbases, int word) {  // even bits of the bases < nbases that live in `word`
-  int k = nbases - 16 * word;
-  if (k <= 0) return 0u;
-  if (k >= 16) return M55;
-  return ((1u << (2 * k)) - 1u) & M55;
-}
-
-// canonical-signal scan with NW window words in registers (covers l + 2 <= 16*NW)
-template <int NW>
-FC_HD void scan_bits(const GenomeView& g, const ScanCfg& cfg, int64_t ga, int64_t gb, int l, bool minus_span,
-                     const uint32_t* rd2, int64_t n, int64_t i, int n_words, Best& best) {
-  uint32_t A[NW + 1], B[NW + 1];
-  load_window<NW>(g, ga, l + 2, A);
-  load_window<NW>(g, gb, l + 2, B);
-
-  // splice signal at every split position x (bit 2*(x%16) of word x/16):
+// ---------------------------------------------------------------- bit-parallel scan on loaded windows
+// NP words of 32 split positions; covers l + 2 <= 32*NP.  WITH_N: nA/nB are the N planes of the windows,
+// the read's N plane is consulted when read_n.
+template <int NP, bool WITH_N>
+FC_HD void scan_planes(const ScanCfg& cfg, const Window<NP>& A, const Window<NP>& B, const uint32_t (&nA)[NP + 1],
+                       const uint32_t (&nB)[NP + 1], int l, bool minus_span, const ReadView& rv, int64_t i,
+                       bool read_n, Best& best) {
+  // splice signal at split position x (bit x&31 of word x>>5):
   //   GT..AG: A[x]=G A[x+1]=T B[x]=A B[x+1]=G ;  CT..AC: A[x]=C A[x+1]=T B[x]=A B[x+1]=C     (find_circ.py:924-954)
-  uint32_t sigP[NW], sigM[NW];
+  //   codes A=00 C=01 G=10 T=11 (hi,lo)
+  uint32_t sigP[NP], sigM[NP];
   uint32_t any = 0;
 #pragma unroll
-  for (int k = 0; k < NW; ++k) {
-    uint32_t a = A[k], a1 = (A[k] >> 2) | (A[k + 1] << 30);
-    uint32_t b = B[k], b1 = (B[k] >> 2) | (B[k + 1] << 30);
-    uint32_t a_lo = a, a_hi = a >> 1, a1_lo = a1, a1_hi = a1 >> 1;
-    uint32_t b_lo = b, b_hi = b >> 1, b1_lo = b1, b1_hi = b1 >> 1;
-    uint32_t common = (a1_hi & a1_lo) & ~(b_hi | b_lo);          // A[x+1]==T and B[x]==A
-    uint32_t gg = (a_hi & ~a_lo) & (b1_hi & ~b1_lo);             // A[x]==G and B[x+1]==G
-    uint32_t cc = (~a_hi & a_lo) & (~b1_hi & b1_lo);             // A[x]==C and B[x+1]==C
-    uint32_t vm = valid_mask(l + 1, k);
+  for (int k = 0; k < NP; ++k) {
+    uint32_t a1lo = funnel_r(A.lo[k], A.lo[k + 1], 1), a1hi = funnel_r(A.hi[k], A.hi[k + 1], 1);
+    uint32_t b1lo = funnel_r(B.lo[k], B.lo[k + 1], 1), b1hi = funnel_r(B.hi[k], B.hi[k + 1], 1);
+    uint32_t common = (a1hi & a1lo) & ~(B.hi[k] | B.lo[k]);                 // A[x+1]==T and B[x]==A
+    uint32_t gg = (A.hi[k] & ~A.lo[k]) & (b1hi & ~b1lo);                    // A[x]==G and B[x+1]==G
+    uint32_t cc = (~A.hi[k] & A.lo[k]) & (~b1hi & b1lo);                    // A[x]==C and B[x+1]==C
+    uint32_t vm = low_mask(imin(imax(l + 1 - 32 * k, 0), 32));
+    if (WITH_N) vm &= ~(nA[k] | funnel_r(nA[k], nA[k + 1], 1) | nB[k] | funnel_r(nB[k], nB[k + 1], 1));
     sigP[k] = common & gg & vm;
     sigM[k] = common & cc & vm;
     any |= sigP[k] | sigM[k];
@@ -296,30 +349,44 @@ FC_HD void scan_bits(const GenomeView& g, const ScanCfg& cfg, int64_t ga, int64_
   if (!any) return;  // no split position carries a canonical signal (most decoy pairs end here)
 
   // mismatch flags of the read against the donor window (A[i] vs R[i]) and the acceptor window (B[i+2] vs R[i])
-  uint32_t mA[NW], mB[NW];
-  int totalB = 0;
+  uint32_t mA[NP], mB[NP];
+  int cumA[NP + 1], cumB[NP + 1];
+  cumA[0] = 0;
+  cumB[0] = 0;
 #pragma unroll
-  for (int k = 0; k < NW; ++k) {
-    uint32_t r = (k < n_words) ? ldg32(rd2 + (int64_t)k * n + i) : 0u;
-    uint32_t b2 = (B[k] >> 4) | (B[k + 1] << 28);
-    uint32_t xa = A[k] ^ r, xb = b2 ^ r;
-    uint32_t vm = valid_mask(l, k);
-    mA[k] = (xa | (xa >> 1)) & vm;
-    mB[k] = (xb | (xb >> 1)) & vm;
-    totalB += popc32(mB[k]);
+  for (int k = 0; k < NP; ++k) {
+    const bool have = k < rv.n_words;
+    uint32_t rlo = have ? ldg32(rv.rlo + (int64_t)k * rv.n + i) : 0u;
+    uint32_t rhi = have ? ldg32(rv.rhi + (int64_t)k * rv.n + i) : 0u;
+    uint32_t b2lo = funnel_r(B.lo[k], B.lo[k + 1], 2), b2hi = funnel_r(B.hi[k], B.hi[k + 1], 2);
+    uint32_t fa = (A.lo[k] ^ rlo) | (A.hi[k] ^ rhi);
+    uint32_t fb = (b2lo ^ rlo) | (b2hi ^ rhi);
+    if (WITH_N) {
+      // N is stored as code 0 on both sides: the base difference is 0 where both are N, the flag XOR decides the rest
+      uint32_t rn = (read_n && have) ? ldg32(rv.rn + (int64_t)k * rv.n + i) : 0u;
+      fa |= nA[k] ^ rn;
+      fb |= funnel_r(nB[k], nB[k + 1], 2) ^ rn;
+    }
+    uint32_t vm = low_mask(imin(imax(l - 32 * k, 0), 32));
+    mA[k] = fa & vm;
+    mB[k] = fb & vm;
+    cumA[k + 1] = cumA[k] + popc32(mA[k]);
+    cumB[k + 1] = cumB[k] + popc32(mB[k]);
   }
+  const int totalB = cumB[NP];
 
-  int accA = 0, accB = 0;
 #pragma unroll
-  for (int k = 0; k < NW; ++k) {
+  for (int k = 0; k < NP; ++k) {
+    // a split inside word k has at least cumA[k] donor-side and totalB - cumB[k+1] acceptor-side mismatches
+    if (cumA[k] > cfg.maxdist || totalB - cumB[k + 1] > cfg.maxdist) continue;
     uint32_t c = sigP[k] | sigM[k];
     while (c) {
       int bit = ffs32(c);
       c &= c - 1;
       uint32_t below = (1u << bit) - 1u;
-      int dist = accA + popc32(mA[k] & below) + (totalB - accB - popc32(mB[k] & below));
+      int dist = cumA[k] + popc32(mA[k] & below) + (totalB - cumB[k] - popc32(mB[k] & below));
       if (dist <= cfg.maxdist) {
-        int x = 16 * k + (bit >> 1);
+        int x = 32 * k + bit;
         uint32_t strand = (sigM[k] >> bit) & 1u;
         int ov = anchor_overlap(x, l, cfg.margin);
         int s = 20 - 10 * dist - ov;
@@ -327,8 +394,6 @@ FC_HD void scan_bits(const GenomeView& g, const ScanCfg& cfg, int64_t ga, int64_
         best.offer(s, x, strand, SIG_GTAG, dist, ov);
       }
     }
-    accA += popc32(mA[k]);
-    accB += popc32(mB[k]);
   }
 }
 
@@ -338,10 +403,10 @@ struct PairArgs {
   uint32_t flags;  // FC_PF_*
 };
 
-template <int NW, class Emit>
-FC_HD void scan_pair(const GenomeView& g, const ScanCfg& cfg, const PairArgs& p, const uint32_t* rd2,
-                     const uint32_t* rdn, int64_t n, int64_t i, int n_words, HitOut& out, Emit& emit,
-                     bool force_per_base) {
+// NP: 32-base words per window held in registers; T: sectors per tile of the tile store (0: no tile store)
+template <int NP, int T, class Emit>
+FC_HD void scan_pair(const GenomeView& g, const ScanCfg& cfg, const PairArgs& p, const ReadView& rv, int64_t i,
+                     HitOut& out, Emit& emit, bool force_per_base) {
   Best best;
   best.init();
   const bool backsplice = p.flags & 1u, minus_span = p.flags & 2u, read_n = p.flags & 4u;
@@ -351,21 +416,38 @@ FC_HD void scan_pair(const GenomeView& g, const ScanCfg& cfg, const PairArgs& p,
     const int64_t size = g.chrom_size[p.chrom];
     const int64_t wa0 = p.a_start, wa1 = (int64_t)p.a_start + l + 2;
     const int64_t wb1 = p.b_end, wb0 = (int64_t)p.b_end - (l + 2);
-    // windows must overlap the chromosome (find_circ.py:194-211 pads the overhang with N; a window entirely outside
+    // windows must touch the chromosome (find_circ.py:194-211 pads the overhang with N; a window entirely outside
     // is undefined there) and the overhang must fit in the padding
-    // (a window that merely touches the boundary still has the right length there and reads all-N)
     const bool ok = wa0 <= size && wa1 >= 0 && wb0 <= size && wb1 >= 0 && wa0 >= -(int64_t)g.pad &&
                     wa1 <= size + g.pad && wb0 >= -(int64_t)g.pad && wb1 <= size + g.pad;
     if (ok) {
       const int64_t off = g.chrom_off[p.chrom];
       const int64_t ga = off + wa0, gb = off + wb0;
-      bool slow = force_per_base || cfg.noncanonical || read_n || (l + 2 > 16 * NW);
-      if (!slow) slow = window_has_n(g, ga, l + 2) || window_has_n(g, gb, l + 2);
-      if (slow) {
+      if (force_per_base || cfg.noncanonical || (l + 2 > 32 * NP)) {
         extra |= W3_SLOW;
-        scan_per_base(g, cfg, ga, gb, l, minus_span, rd2, rdn, n, i, read_n, best, emit);
+        scan_per_base(g, cfg, ga, gb, l, minus_span, rv, i, read_n, best, emit);
       } else {
-        scan_bits<NW>(g, cfg, ga, gb, l, minus_span, rd2, n, i, n_words, best);
+        Window<NP> A, B;
+        uint32_t nA[NP + 1], nB[NP + 1];
+        bool with_n = read_n;
+        if (T > 0 && l + 2 <= g.tile_W) {
+          constexpr int TT = T > 0 ? T : 1;
+          uint32_t fl = load_tile_window<NP, TT>(g, ga, A) | load_tile_window<NP, TT>(g, gb, B);
+          with_n = with_n || (fl & TILE_FLAG_N);
+        } else {
+          load_plane<NP>(g.plo, ga, A.lo);
+          load_plane<NP>(g.phi, ga, A.hi);
+          load_plane<NP>(g.plo, gb, B.lo);
+          load_plane<NP>(g.phi, gb, B.hi);
+          with_n = true;  // no summary without tiles: always consult the N plane
+        }
+        if (with_n) {
+          load_plane<NP>(g.pn, ga, nA);
+          load_plane<NP>(g.pn, gb, nB);
+          scan_planes<NP, true>(cfg, A, B, nA, nB, l, minus_span, rv, i, read_n, best);
+        } else {
+          scan_planes<NP, false>(cfg, A, B, nA, nB, l, minus_span, rv, i, false, best);
+        }
       }
     } else {
       extra |= W3_RANGE;
@@ -376,22 +458,31 @@ FC_HD void scan_pair(const GenomeView& g, const ScanCfg& cfg, const PairArgs& p,
   finish(best, p.a_start, p.b_end, l, backsplice, extra, out);
 }
 
-// ---------------------------------------------------------------- ASCII -> 2-bit
-FC_HD void pack16(const uint8_t* src, int count, uint32_t& w2, uint32_t& wn) {
-  uint32_t a = 0, nn = 0;
+// ---------------------------------------------------------------- ASCII -> planes (32 bases per word)
+FC_HD void pack32(const uint8_t* src, int count, uint32_t& lo, uint32_t& hi, uint32_t& nn) {
+  uint32_t a = 0, b = 0, c = 0;
   for (int j = 0; j < count; ++j) {
-    uint32_t c = src[j] & 0xDFu;  // upper-case
-    uint32_t code, isn = 0;
-    if (c == 'A') code = 0;
-    else if (c == 'C') code = 1;
-    else if (c == 'G') code = 2;
-    else if (c == 'T') code = 3;
-    else { code = 0; isn = 1; }
-    a |= code << (2 * j);
-    nn |= isn << (2 * j);
+    uint32_t ch = src[j] & 0xDFu;  // upper-case
+    uint32_t code = 0, isn = 0;
+    if (ch == 'A') code = 0;
+    else if (ch == 'C') code = 1;
+    else if (ch == 'G') code = 2;
+    else if (ch == 'T') code = 3;
+    else isn = 1;
+    a |= (code & 1u) << j;
+    b |= (code >> 1) << j;
+    c |= isn << j;
   }
-  w2 = a;
-  wn = nn;
+  lo = a;
+  hi = b;
+  nn = c;
+}
+
+// tile geometry for windows of up to `w` bases: T sectors per tile, P payload bases, S stride
+FC_HD void tile_geometry(int w, int& T, int& P, int& S) {
+  T = w <= 96 ? 1 : (w <= 128 ? 2 : 4);
+  P = 128 * T - 4;
+  S = P - w + 1;
 }
 
 }  // namespace fc

@@ -150,14 +150,26 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ scan, device buffers (torch tensors)
-    def pack_reads(self, d_ascii, stride: int, d_l, n_words: int, d_rd2, d_rdn, d_flags, stream=0):
+    def pack_reads(self, d_ascii, stride: int, d_l, n_words: int, d_planes, d_flags, stream=0):
+        """d_planes: int32 device tensor of 3*n_words*n words (lo plane, hi plane, N plane)"""
         n = d_l.numel()
-        self._check(self.lib.fc_pack_reads(self.h, n, ptr(d_ascii), stride, ptr(d_l), n_words, ptr(d_rd2), ptr(d_rdn),
+        lo, hi, nn = self.plane_ptrs(d_planes, n, n_words)
+        self._check(self.lib.fc_pack_reads(self.h, n, ptr(d_ascii), stride, ptr(d_l), n_words, lo, hi, nn,
                                            ptr(d_flags), stream))
 
-    def make_pairs(self, n, d_chrom, d_a_start, d_b_end, d_l, d_flags, d_rd2, d_rdn, n_words, max_l) -> Pairs:
-        return Pairs(n, ptr(d_chrom), ptr(d_a_start), ptr(d_b_end), ptr(d_l), ptr(d_flags), ptr(d_rd2), ptr(d_rdn),
-                     n_words, max_l)
+    @staticmethod
+    def n_words_for(max_l: int) -> int:
+        return max(1, (max_l + 31) // 32)
+
+    @staticmethod
+    def plane_ptrs(d_planes, n, n_words):
+        base = ptr(d_planes)
+        step = 4 * n * n_words
+        return base, base + step, base + 2 * step
+
+    def make_pairs(self, n, d_chrom, d_a_start, d_b_end, d_l, d_flags, d_planes, n_words, max_l) -> Pairs:
+        lo, hi, nn = self.plane_ptrs(d_planes, n, n_words)
+        return Pairs(n, ptr(d_chrom), ptr(d_a_start), ptr(d_b_end), ptr(d_l), ptr(d_flags), lo, hi, nn, n_words, max_l)
 
     def scan(self, pairs: Pairs, d_out, stream=0):
         self._check(self.lib.fc_scan(self.h, C.byref(self.params), C.byref(pairs), ptr(d_out), stream))

@@ -64,10 +64,10 @@ typedef struct fc_scan_params {
  *   a_start = A.pos + (asize - margin)       genomic position of A_flank[0]      (find_circ.py:901)
  *   b_end   = B.aend - (asize - margin)      one past the last base of B_flank   (find_circ.py:902)
  *   l       = len(read_part) - 2*(asize-margin)   number of internal bases        (find_circ.py:904); may be < 0
- *   rd2     2-bit packed internal read bases, word-major: word w of pair i at rd2[w*n + i], base j of the
- *           internal sequence in word j/16 at bits 2*(j%16) (A=0 C=1 G=2 T=3, N stored as 0)
- *   rdn     same layout, bit 2*(j%16) set when base j is not A/C/G/T
- *   n_words = words per pair in rd2/rdn  (>= ceil(max l / 16))
+ *   rlo,rhi low / high bit plane of the 2-bit codes (A0 C1 G2 T3, N stored as 0) of the internal read bases,
+ *           word-major: word w of pair i at rlo[w*n + i], base j in word j/32 at bit j%32
+ *   rn      same layout, bit set when base j is not A/C/G/T
+ *   n_words = words per pair and plane  (>= ceil(max l / 32))
  */
 typedef struct fc_pairs {
   int64_t n;
@@ -76,8 +76,9 @@ typedef struct fc_pairs {
   const int32_t* d_b_end;
   const int32_t* d_l;
   const uint8_t* d_flags; /* FC_PF_* ; READ_N may be OR-ed in by fc_pack_reads, hence also written */
-  const uint32_t* d_rd2;
-  const uint32_t* d_rdn;
+  const uint32_t* d_rlo;
+  const uint32_t* d_rhi;
+  const uint32_t* d_rn;
   int32_t n_words;
   int32_t max_l; /* upper bound of l over the batch (selects the kernel specialisation) */
 } fc_pairs;
@@ -141,8 +142,8 @@ void fc_ctx_destroy(fc_ctx* ctx);
 const char* fc_last_error(fc_ctx* ctx); /* ctx may be NULL: last error of a failed fc_ctx_create */
 
 /* ------------------------------------------------------------------ genome store
- * Replaces indexed_fasta / GenomeAccessor (find_circ.py:103-215, 329-371).  Chromosomes are 2-bit packed into one
- * device array with >= FC_GENOME_PAD bases of 'N' padding around each, so reads outside [0,size) return 'N' as
+ * Replaces indexed_fasta / GenomeAccessor (find_circ.py:103-215, 329-371).  Chromosomes are packed into device bit
+ * planes (2 bits + an N bit per base) in one coordinate space with >= FC_GENOME_PAD bases of 'N' padding around each, so reads outside [0,size) return 'N' as
  * find_circ.py:194-211 does; soft-masked (lower-case) letters are upper-cased as the callers do (:901-902);
  * letters other than ACGTN are stored as N and counted (fc_genome_stats). */
 #define FC_GENOME_PAD 4096
@@ -161,9 +162,9 @@ int fc_genome_fetch(fc_ctx* ctx, int32_t chrom, int64_t start, int64_t end, char
 
 /* ------------------------------------------------------------------ read packing
  * d_ascii: n rows of `stride` bytes, row i holds the l[i] internal read bases (read_part[eff:-eff], find_circ.py:895),
- * any case.  Writes rd2 / rdn (n_words words per pair, word-major) and ORs FC_PF_READ_N into d_flags. */
+ * any case.  Writes rlo / rhi / rn (n_words words per pair and plane, word-major) and ORs FC_PF_READ_N into d_flags. */
 int fc_pack_reads(fc_ctx* ctx, int64_t n, const uint8_t* d_ascii, int32_t stride, const int32_t* d_l,
-                  int32_t n_words, uint32_t* d_rd2, uint32_t* d_rdn, uint8_t* d_flags, void* stream);
+                  int32_t n_words, uint32_t* d_rlo, uint32_t* d_rhi, uint32_t* d_rn, uint8_t* d_flags, void* stream);
 
 /* ------------------------------------------------------------------ breakpoint scan
  * One thread per anchor pair; see find_circ2_b200/csrc/scan_core.cuh. */

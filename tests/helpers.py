@@ -91,18 +91,20 @@ def host_harness():
         lib.hh_genome_build.restype = ctypes.c_void_p
         lib.hh_genome_build.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         lib.hh_genome_free.argtypes = [ctypes.c_void_p]
+        lib.hh_build_tiles.argtypes = [ctypes.c_void_p, ctypes.c_int]
         lib.hh_pack_reads.argtypes = [ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int] + [
             ctypes.c_void_p
-        ] * 3
+        ] * 4
         lib.hh_scan.argtypes = (
-            [ctypes.c_void_p] + [ctypes.c_int] * 5 + [ctypes.c_int64] + [ctypes.c_void_p] * 7 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+            [ctypes.c_void_p] + [ctypes.c_int] * 6 + [ctypes.c_int64] + [ctypes.c_void_p] * 8 + [ctypes.c_int, ctypes.c_void_p]
         )
         _HARNESS = lib
     return _HARNESS
 
 
-def harness_scan(g, chrom, a_start, b_end, l, flags, internal, margin, maxdist, noncanonical=0, strandpref=0, nw=None,
-                 force_per_base=0):
+def harness_scan(g, chrom, a_start, b_end, l, flags, internal, margin, maxdist, noncanonical=0, strandpref=0, mode=0,
+                 tile_window=None):
+    """mode 0: tile store + kernel choice as fc_scan; 1: master planes only; 2: per-base path"""
     lib = host_harness()
     seqs = [np.ascontiguousarray(s) for s in g.seqs]
     ptrs = (ctypes.c_void_p * len(seqs))(*[s.ctypes.data for s in seqs])
@@ -111,20 +113,18 @@ def harness_scan(g, chrom, a_start, b_end, l, flags, internal, margin, maxdist, 
     try:
         n = len(chrom)
         max_l = int(max(l.max(), 0)) if n else 0
-        n_words = max(1, (max_l + 15) // 16)
+        lib.hh_build_tiles(h, tile_window if tile_window is not None else max_l + 2)
+        n_words = max(1, (max_l + 31) // 32)
         stride = internal.shape[1] if internal.ndim == 2 and internal.shape[1] else 1
         internal = np.ascontiguousarray(internal)
-        rd2 = np.zeros(n_words * n, dtype=np.uint32)
-        rdn = np.zeros(n_words * n, dtype=np.uint32)
+        planes = np.zeros((3, n_words * n), dtype=np.uint32)
         flags = flags.copy()
-        lib.hh_pack_reads(n, internal.ctypes.data, stride, l.ctypes.data, n_words, rd2.ctypes.data, rdn.ctypes.data, flags.ctypes.data)
-        if nw is None:
-            need = max_l + 2
-            nw = 3 if need <= 48 else 5 if need <= 80 else 8 if need <= 128 else 12 if need <= 192 else 16
+        lib.hh_pack_reads(n, internal.ctypes.data, stride, l.ctypes.data, n_words, planes[0].ctypes.data, planes[1].ctypes.data,
+                          planes[2].ctypes.data, flags.ctypes.data)
         out = np.zeros((n, 4), dtype=np.uint32)
-        rc = lib.hh_scan(h, margin, maxdist, noncanonical, strandpref, nw, n, chrom.ctypes.data, a_start.ctypes.data,
-                         b_end.ctypes.data, l.ctypes.data, flags.ctypes.data, rd2.ctypes.data, rdn.ctypes.data, n_words,
-                         out.ctypes.data, force_per_base)
+        rc = lib.hh_scan(h, margin, maxdist, noncanonical, strandpref, mode, max_l, n, chrom.ctypes.data, a_start.ctypes.data,
+                         b_end.ctypes.data, l.ctypes.data, flags.ctypes.data, planes[0].ctypes.data, planes[1].ctypes.data,
+                         planes[2].ctypes.data, n_words, out.ctypes.data)
         assert rc == 0
         return out
     finally:

@@ -155,14 +155,13 @@ def test_device_path_equals_host_path(torch_cuda):
     host = e.scan_host(chrom, a_start, b_end, l, flags, internal)
     dev = torch.device("cuda:0")
     n = len(chrom)
-    n_words = (int(l.max()) + 15) // 16
+    n_words = max(1, (int(l.max()) + 31) // 32)
     d = {k: torch.from_numpy(v).to(dev) for k, v in dict(chrom=chrom, a=a_start, b=b_end, l=l, fl=flags, asc=internal).items()}
-    rd2 = torch.zeros(n_words * n, dtype=torch.int32, device=dev)
-    rdn = torch.zeros(n_words * n, dtype=torch.int32, device=dev)
+    planes = torch.zeros(3 * n_words * n, dtype=torch.int32, device=dev)
     out = torch.zeros(n * 4, dtype=torch.int32, device=dev)
     st = torch.cuda.current_stream().cuda_stream
-    e.pack_reads(d["asc"], internal.shape[1], d["l"], n_words, rd2, rdn, d["fl"], st)
-    pairs = e.make_pairs(n, d["chrom"], d["a"], d["b"], d["l"], d["fl"], rd2, rdn, n_words, int(l.max()))
+    e.pack_reads(d["asc"], internal.shape[1], d["l"], n_words, planes, d["fl"], st)
+    pairs = e.make_pairs(n, d["chrom"], d["a"], d["b"], d["l"], d["fl"], planes, n_words, int(l.max()))
     e.scan(pairs, out, st)
     torch.cuda.synchronize()
     got = out.cpu().numpy().view(np.uint32).reshape(-1, 4)
@@ -181,13 +180,12 @@ def test_all_ties_enumeration(torch_cuda):
         e.load_genome_arrays(g.names, g.seqs)
         dev = torch.device("cuda:0")
         n = len(chrom)
-        n_words = (int(l.max()) + 15) // 16
+        n_words = max(1, (int(l.max()) + 31) // 32)
         d = {k: torch.from_numpy(v).to(dev) for k, v in dict(chrom=chrom, a=a_start, b=b_end, l=l, fl=flags, asc=internal).items()}
-        rd2 = torch.zeros(n_words * n, dtype=torch.int32, device=dev)
-        rdn = torch.zeros(n_words * n, dtype=torch.int32, device=dev)
+        planes = torch.zeros(3 * n_words * n, dtype=torch.int32, device=dev)
         out = torch.zeros(n * 4, dtype=torch.int32, device=dev)
-        e.pack_reads(d["asc"], internal.shape[1], d["l"], n_words, rd2, rdn, d["fl"], 0)
-        pairs = e.make_pairs(n, d["chrom"], d["a"], d["b"], d["l"], d["fl"], rd2, rdn, n_words, int(l.max()))
+        e.pack_reads(d["asc"], internal.shape[1], d["l"], n_words, planes, d["fl"], 0)
+        pairs = e.make_pairs(n, d["chrom"], d["a"], d["b"], d["l"], d["fl"], planes, n_words, int(l.max()))
         e.scan(pairs, out, 0)
         torch.cuda.synchronize()
         hits = out.cpu().numpy().view(np.uint32).reshape(-1, 4)
@@ -321,14 +319,13 @@ def test_emit_from_scan_matches_python(torch_cuda):
     lens = np.full(n, t.read_len, dtype=np.int32)
     rh = e.hash_reads(t.reads, lens)
     qh = np.array([e.hash_bytes(("r%d" % (i // 2)).encode()) for i in range(n)], dtype=np.uint64)
-    n_words = (int(l.max()) + 15) // 16
+    n_words = max(1, (int(l.max()) + 31) // 32)
     tn = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
     d_chrom, d_a, d_b, d_l, d_fl, d_asc = tn(chrom), tn(a_start), tn(b_end), tn(l), tn(flags), tn(internal)
-    rd2 = torch.zeros(n_words * n, dtype=torch.int32, device=dev)
-    rdn = torch.zeros(n_words * n, dtype=torch.int32, device=dev)
+    planes = torch.zeros(3 * n_words * n, dtype=torch.int32, device=dev)
     out = torch.zeros(n * 4, dtype=torch.int32, device=dev)
-    e.pack_reads(d_asc, internal.shape[1], d_l, n_words, rd2, rdn, d_fl, 0)
-    pairs = e.make_pairs(n, d_chrom, d_a, d_b, d_l, d_fl, rd2, rdn, n_words, int(l.max()))
+    e.pack_reads(d_asc, internal.shape[1], d_l, n_words, planes, d_fl, 0)
+    pairs = e.make_pairs(n, d_chrom, d_a, d_b, d_l, d_fl, planes, n_words, int(l.max()))
     e.agg_reset()
     half = n // 2
     e.scan(pairs, out, 0)
@@ -387,4 +384,24 @@ def test_partition_by_key(torch_cuda):
                 assert k not in seen
                 seen[k] = r
         assert sorted(out["idx"].tolist()) == sorted(recs["idx"].tolist())
+    e.close()
+
+
+def test_tile_store_rebuild_across_read_lengths():
+    """one engine, batches of different read lengths: the tile store is rebuilt for longer windows and keeps
+    answering shorter ones (T = 1 -> 2 -> 4 sectors per tile)"""
+    g = synth.make_genome([60000, 45000, 7000], seed=401, n_frac=0.01, n_run=(20, 200))
+    J = synth.plant_junctions(g, 80, 50, seed=402, span=(150, 8000), margin=300)
+    e = _engine(asize=20)
+    e.load_genome_arrays(g.names, g.seqs)
+    gs = H.GenomeStrings(g)
+    opt = O.Options(asize=20)
+    for read_len in (76, 100, 150, 100, 250, 60, 300):
+        t = synth.make_pairs(g, J, 1500, read_len=read_len, asize=20, seed=400 + read_len, error_rate=0.01,
+                             frac_edge=0.05, frac_read_n=0.03)
+        chrom, a_start, b_end, l, flags, internal = H.pairs_to_soa(t, 20, 2)
+        want = H.oracle_scan(gs, g.names, chrom, a_start, b_end, l, flags, internal, opt)
+        hits = e.scan_host(chrom, a_start, b_end, l, flags, internal)
+        got = [H.decode_hit(r) for r in hits.view(np.uint32).reshape(-1, 4)]
+        assert got == want, read_len
     e.close()

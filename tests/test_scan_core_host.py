@@ -41,23 +41,23 @@ def test_host_compiled_scan_matches_oracle(read_len, asize, margin, maxdist, non
     chrom, a_start, b_end, l, flags, internal = H.pairs_to_soa(t, asize, margin)
     opt = O.Options(asize=asize, margin=margin, maxdist=maxdist, noncanonical=bool(nonc), strandpref=bool(spref))
     want = H.oracle_scan(H.GenomeStrings(g), g.names, chrom, a_start, b_end, l, flags, internal, opt)
-    for force in (0, 1):
-        got = H.harness_scan(g, chrom, a_start, b_end, l, flags, internal, margin, maxdist, nonc, spref, force_per_base=force)
+    for mode in (0, 1, 2):
+        got = H.harness_scan(g, chrom, a_start, b_end, l, flags, internal, margin, maxdist, nonc, spref, mode=mode)
         dec = [H.decode_hit(r) for r in got]
         bad = [(i, dec[i], want[i]) for i in range(len(want)) if dec[i] != want[i]]
-        assert not bad, bad[:5]
+        assert not bad, (mode, bad[:5])
     n_hit = sum(1 for w in want if w)
     assert n_hit > 0.3 * len(want) or read_len < 50
 
 
-def test_wide_template_on_short_reads():
-    """a kernel specialisation wider than needed must give the same answers"""
+def test_tile_store_built_for_longer_windows():
+    """a tile store built for longer reads (other T / stride) must give the same answers on short reads"""
     g, t = _case(100, 20, seed=7)
     chrom, a_start, b_end, l, flags, internal = H.pairs_to_soa(t, 20, 2)
-    base = H.harness_scan(g, chrom, a_start, b_end, l, flags, internal, 2, 2, nw=5)
-    for nw in (8, 12, 16):
-        other = H.harness_scan(g, chrom, a_start, b_end, l, flags, internal, 2, 2, nw=nw)
-        assert np.array_equal(base[:, :3], other[:, :3])
-    # too narrow -> per-base path, same answers
-    narrow = H.harness_scan(g, chrom, a_start, b_end, l, flags, internal, 2, 2, nw=3)
+    base = H.harness_scan(g, chrom, a_start, b_end, l, flags, internal, 2, 2)
+    for w in (80, 96, 118, 128, 200, 256):
+        other = H.harness_scan(g, chrom, a_start, b_end, l, flags, internal, 2, 2, tile_window=w)
+        assert np.array_equal(base[:, :3], other[:, :3]), w
+    # tile store too small for the batch -> master planes, same answers
+    narrow = H.harness_scan(g, chrom, a_start, b_end, l, flags, internal, 2, 2, tile_window=40)
     assert np.array_equal(base[:, :3], narrow[:, :3])
