@@ -51,13 +51,13 @@ class Pairs(C.Structure):
 HIT_DTYPE = np.dtype([("start", "<i4"), ("end", "<i4"), ("w2", "<u4"), ("w3", "<u4")])
 JREC_DTYPE = np.dtype(
     [
-        ("chrom", "<u4"), ("start", "<u4"), ("end", "<u4"), ("sk", "<u4"), ("idx", "<u8"), ("read_hash", "<u8"),
+        ("chrom", "<u4"), ("start", "<i4"), ("end", "<i4"), ("sk", "<u4"), ("idx", "<u8"), ("read_hash", "<u8"),
         ("qname_hash", "<u8"), ("q_left", "<i2"), ("q_right", "<i2"), ("n_hits", "<u2"), ("dist", "u1"), ("ov", "u1"),
     ]
 )
 JUNCTION_DTYPE = np.dtype(
     [
-        ("chrom", "<u4"), ("start", "<u4"), ("end", "<u4"), ("sk", "<u4"), ("first_idx", "<u8"), ("n_weighted", "<f8"),
+        ("chrom", "<u4"), ("start", "<i4"), ("end", "<i4"), ("sk", "<u4"), ("first_idx", "<u8"), ("n_weighted", "<f8"),
         ("n_uniq_bridges", "<f8"), ("n_spanned", "<u4"), ("n_frags", "<u4"), ("n_uniq", "<u4"), ("best_q_left", "<i2"),
         ("best_q_right", "<i2"), ("min_n_hits", "<u2"), ("min_dist", "u1"), ("min_ov", "u1"), ("pad", "<u4"),
     ]
@@ -86,7 +86,9 @@ SYMBOLS = [
     ("fc_batch_host", C.c_int, [_P, C.POINTER(ScanParams), C.c_int64, _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P,
                                 C.c_uint64, C.c_int32, _P]),
     ("fc_agg_reset", C.c_int, [_P]),
-    ("fc_agg_emit", C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, C.c_uint64, _P]),
+    ("fc_agg_emit", C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_uint64, _P]),
+    ("fc_batch_emit_host", C.c_int, [_P, _P, C.c_uint64]),
+    ("fc_batch_ties_host", C.c_int, [_P, C.POINTER(ScanParams), _P, _P]),
     ("fc_agg_append", C.c_int, [_P, C.c_int64, _P, _P]),
     ("fc_agg_append_host", C.c_int, [_P, C.c_int64, _P]),
     ("fc_agg_n_records", C.c_int64, [_P]),

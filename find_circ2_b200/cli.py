@@ -1,0 +1,182 @@
+"""
+Command line of the drop-in: the option table of the shipped find_circ.py (find_circ.py:383-413), plus the
+README (v1.2) spellings of the same switches (README.md:283-337), the same output directory layout
+(find_circ.py:420-458) and the same run.log counter dump (find_circ.py:1605-1607).
+
+    bwa mem ... | find_circ.py --genome genome.fa -n sample -o out_dir
+    find_circ.py --genome genome.fa -o out_dir alignments.bam
+"""
+from __future__ import annotations
+
+import gzip
+import logging
+import optparse
+import os
+import sys
+import time
+import traceback
+
+from . import samio
+from .pipeline import VERSION, Options, Run
+
+USAGE = """
+   bwa mem -t<threads> [-p] -A2 -B10 -k 15 -T 1 $GENOME_INDEX reads.fastq.gz | %prog [options]
+
+   OR:
+
+   %prog [options] <bwa_mem_genome_alignments.bam>
+"""
+
+
+def build_parser() -> optparse.OptionParser:
+    p = optparse.OptionParser(usage=USAGE)
+    a = p.add_option
+    a("-v", "--version", dest="version", action="store_true", default=False, help="get version information")
+    a("-S", "--system", dest="system", type=str, default="", help="model system database (not supported: needs the byo library)")
+    a("-G", "--genome", dest="genome", type=str, default="", help="path to genome (one multichromosome FASTA file)")
+    a("", "--known-circ", dest="known_circ", type=str, default="", help="file with known circRNA junctions (BED6) [not supported yet]")
+    a("", "--known-lin", dest="known_lin", type=str, default="", help="file with known linear splice junctions (BED6) [not supported yet]")
+    a("-o", "--output", dest="output", default="find_circ_run", help="where to store output")
+    a("-q", "--silent", dest="silent", default=False, action="store_true", help="suppress any normal output to stdout")
+    a("", "--stdout", dest="stdout", default=None, choices=["circs", "lins", "reads", "multi", "test"],
+      help="use to direct chosen type of output (circs, lins, reads, multi) to stdout instead of file")
+    a("-n", "--name", dest="name", default="unknown", help="tissue/sample name to use (default='unknown')")
+    a("", "--min-uniq-qual", "--min_uniq_qual", dest="min_uniq_qual", type=int, default=2,
+      help="minimal uniqness for anchor alignments to consider (default=2)")
+    a("-a", "--anchor", dest="asize", type=int, default=15, help="anchor size (default=15)")
+    a("-m", "--margin", dest="margin", type=int, default=2, help="maximum nts the BP is allowed to reside within a segment (default=2)")
+    a("-d", "--max-mismatch", "--maxdist", dest="maxdist", type=int, default=2,
+      help="maximum mismatches (no indels) allowed in segment extensions (default=2)")
+    a("", "--short-threshold", dest="short_threshold", type=int, default=100, help="minimal genomic span [nt] of a circRNA before it is labeled SHORT (default=100)")
+    a("", "--huge-threshold", dest="huge_threshold", type=int, default=100000, help="maximal genomic span [nt] of a circRNA before it is labeled HUGE (default=100000)")
+    a("", "--debug", dest="debug", default=False, action="store_true", help="(accepted, no effect)")
+    a("", "--profile", dest="profile", default=False, action="store_true", help="(accepted, no effect)")
+    a("", "--non-canonical", "--noncanonical", dest="noncanonical", default=False, action="store_true",
+      help="relax the GU/AG constraint (will produce many more ambiguous counts)")
+    a("", "--all-hits", "--allhits", dest="allhits", default=False, action="store_true", help="in case of ambiguities, report each hit")
+    a("", "--stranded", dest="stranded", default=False, action="store_true", help="not supported (crashes in the reference: find_circ.py:533)")
+    a("", "--strand-pref", "--strandpref", dest="strandpref", default=False, action="store_true",
+      help="prefer splice sites that match annotated direction of transcription")
+    a("", "--half-unique", "--halfunique", "--halfuniq", dest="halfunique", default=False, action="store_true",
+      help="also report junctions where only one anchor aligns uniquely (less likely to be true)")
+    a("", "--report-nobridges", "--report_nobridges", "--report_nobridge", dest="report_nobridges", default=False, action="store_true",
+      help="also report junctions lacking at least a single read where both anchors, jointly align uniquely")
+    a("-B", "--bam", dest="bam", default=False, action="store_true", help="not supported")
+    a("-t", "--throughput", dest="throughput", default=False, action="store_true", help="print information on throughput to stderr")
+    a("", "--chunk-size", "--chunksize", dest="chunksize", type=int, default=100000, help="number of reads to be processed in one chunk (default=100000)")
+    a("", "--noop", dest="noop", default=False, action="store_true", help="Do not search for any junctions. Only process the alignment stream")
+    a("", "--test", dest="test", default=False, action="store_true", help="not supported")
+    a("", "--no-linear", dest="nolinear", default=False, action="store_true", help="Do not investigate linear junctions, unless associated with another backsplice event")
+    a("", "--no-multi", dest="multi_events", default=True, action="store_false", help="Do not record multi-events")
+    a("", "--batch-pairs", dest="batch_pairs", type=int, default=1 << 18, help="anchor pairs per GPU batch (default 262144)")
+    a("", "--device", dest="device", type=int, default=0, help="CUDA device (default 0)")
+    return p
+
+
+def parse_args(argv):
+    o, args = build_parser().parse_args(list(argv))
+    for bad in ("stranded", "bam", "test"):
+        if getattr(o, bad):
+            raise SystemExit("option --%s is not supported by this build" % bad)
+    if o.system or o.known_circ or o.known_lin:
+        raise SystemExit("-S/--system and --known-circ/--known-lin are not supported by this build")
+    opt = Options(
+        genome=o.genome, output=o.output, name=o.name, min_uniq_qual=o.min_uniq_qual, asize=o.asize, margin=o.margin,
+        maxdist=o.maxdist, short_threshold=o.short_threshold, huge_threshold=o.huge_threshold, noncanonical=o.noncanonical,
+        allhits=o.allhits, strandpref=o.strandpref, halfunique=o.halfunique, report_nobridges=o.report_nobridges,
+        nolinear=o.nolinear, multi_events=o.multi_events, throughput=o.throughput, chunksize=o.chunksize, noop=o.noop,
+        silent=o.silent, stdout=o.stdout, batch_pairs=o.batch_pairs, device=o.device,
+    )
+    return opt, args, o
+
+
+def run_to_strings(opt: Options, path=None, engine=None):
+    """the whole run, outputs as strings (tests and the single-process CLI share this)"""
+    names, lengths, records = samio.open_alignments(path)
+    run = Run(opt, names, engine)
+    try:
+        t0 = time.perf_counter()
+        run.process(records)
+        t1 = time.perf_counter()
+        run.finalize()
+        out = {
+            "circ": run.bed_text(0),
+            "lin": run.bed_text(1),
+            "reads": run.reads_text(),
+            "multi": run.multi_text(),
+            "counters": run.counters_text(),
+            "n_fragments": run.n_fragments,
+            "n_pairs_scanned": run.n_pairs_scanned,
+            "seconds_ingest_and_scan": t1 - t0,
+            "seconds_gpu_calls": run.t_scan,
+            "seconds_total": time.perf_counter() - t0,
+        }
+    finally:
+        run.close()
+    return out
+
+
+def main(argv=None) -> int:
+    argv = sys.argv[1:] if argv is None else argv
+    opt, args, raw = parse_args(argv)
+    if raw.version:
+        print("find_circ.py version %s (B200-native breakpoint scan + junction merge)" % VERSION)
+        return 0
+    if not opt.genome:
+        print("need to specify either model system database (-S) or genome FASTA file (-G).")
+        return 1
+    if not os.path.isdir(opt.output):
+        os.makedirs(opt.output)
+    fmt = "%(asctime)-20s\t%(levelname)s\t%(name)s\t%(message)s"
+    logging.basicConfig(level=logging.INFO, format=fmt, filename=os.path.join(opt.output, "run.log"), filemode="w")
+    log = logging.getLogger("find_circ")
+    log.info("find_circ %s invoked as '%s'" % (VERSION, " ".join(sys.argv)))
+    files = {
+        "circs": open(os.path.join(opt.output, "circ_splice_sites.bed"), "w"),
+        "lins": open(os.path.join(opt.output, "lin_splice_sites.bed"), "w"),
+        "reads": gzip.open(os.path.join(opt.output, "spliced_reads.fastq.gz"), "wt"),
+        "multi": open(os.path.join(opt.output, "multi_events.tsv"), "w"),
+    }
+    if opt.stdout and opt.stdout in files:
+        files[opt.stdout].write("# redirected to stdout\n")
+        files[opt.stdout].close()
+        files[opt.stdout] = sys.stdout
+        log.info("redirected %s to stdout" % opt.stdout)
+    path = args[0] if args else None
+    log.info("reading from %s" % (path or "stdin"))
+    t0 = time.time()
+    try:
+        out = run_to_strings(opt, path)
+    except KeyboardInterrupt:
+        logging.warning("KeyboardInterrupt by user")
+        return 1
+    except Exception:
+        exc = traceback.format_exc()
+        logging.error("Unhandled exception raised while processing input")
+        logging.error(exc)
+        sys.stderr.write(exc)
+        return 1
+    t1 = time.time()
+    n = out["n_fragments"]
+    txt = "processed %.2fM (paired or single end) reads in %.1f minutes (overall %.2fk reads/second on average)" % (
+        n / 1e6, (t1 - t0) / 60.0, n / max(t1 - t0, 1e-9) / 1000.0)
+    log.info(txt)
+    log.info("anchor pairs scanned on the GPU: %d, seconds inside GPU calls: %.3f" % (out["n_pairs_scanned"], out["seconds_gpu_calls"]))
+    if not opt.silent and not opt.stdout:
+        print("#", txt)
+        print("# results stored in '%s'" % opt.output)
+    log.info("run finished")
+    for line in out["counters"].splitlines():
+        log.info(line)
+    files["circs"].write(out["circ"])
+    files["lins"].write(out["lin"])
+    files["reads"].write(out["reads"])
+    files["multi"].write(out["multi"])
+    for f in files.values():
+        if f is not sys.stdout:
+            f.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

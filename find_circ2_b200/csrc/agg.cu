@@ -34,13 +34,15 @@ struct JAcc {  // per-junction accumulators filled with integer atomics (determi
   unsigned int pad;
 };
 
-__global__ void count_hits_kernel(int64_t n, const fc_hit* __restrict__ hits, uint32_t* __restrict__ accept) {
+__global__ void count_hits_kernel(int64_t n, const fc_hit* __restrict__ hits, const uint8_t* __restrict__ mask,
+                                  uint32_t* __restrict__ accept) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  accept[i] = (hits[i].w2 & 0xFFFFu) ? 1u : 0u;
+  accept[i] = ((hits[i].w2 & 0xFFFFu) && (!mask || mask[i])) ? 1u : 0u;
 }
 
-__global__ void emit_kernel(int64_t n, const fc_hit* __restrict__ hits, const uint32_t* __restrict__ pos,
+__global__ void emit_kernel(int64_t n, const fc_hit* __restrict__ hits, const uint8_t* __restrict__ mask,
+                            const uint32_t* __restrict__ pos,
                             const int32_t* __restrict__ chrom, const uint8_t* __restrict__ flags,
                             const uint8_t* __restrict__ wden, const int16_t* __restrict__ q_a,
                             const int16_t* __restrict__ q_b, const uint64_t* __restrict__ read_hash,
@@ -50,6 +52,7 @@ __global__ void emit_kernel(int64_t n, const fc_hit* __restrict__ hits, const ui
   if (i >= n) return;
   fc_hit h = hits[i];
   if ((h.w2 & 0xFFFFu) == 0) return;
+  if (mask && !mask[i]) return;
   uint32_t fl = flags[i];
   bool backsplice = fl & FC_PF_BACKSPLICE;
   fc_jrec r;
@@ -397,7 +400,8 @@ extern "C" int fc_agg_reset(fc_ctx* ctx) {
 
 extern "C" int fc_agg_emit(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, const int32_t* d_chrom, const uint8_t* d_flags,
                            const uint8_t* d_wden, const int16_t* d_q_a, const int16_t* d_q_b,
-                           const uint64_t* d_read_hash, const uint64_t* d_qname_hash, uint64_t idx_base, void* stream) {
+                           const uint64_t* d_read_hash, const uint64_t* d_qname_hash, const uint8_t* d_mask,
+                           uint64_t idx_base, void* stream) {
   if (!ctx || n < 0) return FC_E_ARG;
   if (n == 0) return FC_OK;
   if (n >= (1ll << 32)) return fc_fail(ctx, FC_E_ARG, "batch too large");
@@ -412,11 +416,11 @@ extern "C" int fc_agg_emit(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, const i
   FC_CUDA(ctx, a.scratch[1].reserve((size_t)n * 4, st, false, 0));
   uint32_t* accept = (uint32_t*)a.scratch[0].p;
   uint32_t* pos = (uint32_t*)a.scratch[1].p;
-  count_hits_kernel<<<nblk(n, 256), 256, 0, st>>>(n, d_hits, accept);
+  count_hits_kernel<<<nblk(n, 256), 256, 0, st>>>(n, d_hits, d_mask, accept);
   FC_LAUNCH_CHECK(ctx);
   rc = scan_u32(ctx, n, accept, pos, false, st);
   if (rc) return rc;
-  emit_kernel<<<nblk(n, 256), 256, 0, st>>>(n, d_hits, pos, d_chrom, d_flags, d_wden, d_q_a, d_q_b, d_read_hash,
+  emit_kernel<<<nblk(n, 256), 256, 0, st>>>(n, d_hits, d_mask, pos, d_chrom, d_flags, d_wden, d_q_a, d_q_b, d_read_hash,
                                             d_qname_hash, idx_base, (const unsigned long long*)a.counters.p,
                                             (fc_jrec*)a.recs.p);
   FC_LAUNCH_CHECK(ctx);

@@ -73,6 +73,10 @@ struct fc_ctx {
   fc_dbuf host_path[16];              // staging for fc_scan_host / fc_batch_host
   int64_t launches = 0;
   int sm_count = 148;
+  // device state of the last fc_batch_host call (two-step batches)
+  int64_t last_n = 0;
+  fc_pairs last_pairs = {};
+  bool last_has_payload = false;
 };
 
 int fc_fail(fc_ctx* ctx, int code, const char* fmt, ...);

@@ -280,7 +280,7 @@ extern "C" int fc_batch_host(fc_ctx* ctx, const fc_scan_params* p, int64_t n, co
                          h_wden, h_q_a, h_q_b, h_read_hash, h_qname_hash};
   for (int k = 0; k < 14; ++k) {
     if (!src[k]) continue;
-    if (k >= 9 && !emit) continue;
+    if (k >= 9 && !src[k]) continue;
     size_t bytes = k == 4 ? N : sizes[k];
     FC_CUDA(ctx, cudaMemcpyAsync(dp[k], src[k], bytes, cudaMemcpyHostToDevice, st));
   }
@@ -304,10 +304,59 @@ extern "C" int fc_batch_host(fc_ctx* ctx, const fc_scan_params* p, int64_t n, co
   if (emit) {
     if (!h_wden || !h_q_a || !h_q_b || !h_read_hash || !h_qname_hash) return fc_fail(ctx, FC_E_ARG, "emit needs the payload arrays");
     rc = fc_agg_emit(ctx, n, (const fc_hit*)dp[8], pr.d_chrom, pr.d_flags, (const uint8_t*)dp[9], (const int16_t*)dp[10],
-                     (const int16_t*)dp[11], (const uint64_t*)dp[12], (const uint64_t*)dp[13], idx_base, st);
+                     (const int16_t*)dp[11], (const uint64_t*)dp[12], (const uint64_t*)dp[13], nullptr, idx_base, st);
     if (rc) return rc;
   }
   if (h_out) FC_CUDA(ctx, cudaMemcpyAsync(h_out, dp[8], sizes[8], cudaMemcpyDeviceToHost, st));
+  FC_CUDA(ctx, cudaStreamSynchronize(st));
+  ctx->last_n = n;
+  ctx->last_pairs = pr;
+  ctx->last_has_payload = h_wden && h_q_a && h_q_b && h_read_hash && h_qname_hash;
+  return FC_OK;
+}
+
+// second half of a two-step batch: the host has looked at the hits of the last fc_batch_host(emit=0) call and decided
+// per pair whether its first tie is recorded (the linear spans of a fragment are only recorded when its back-splices
+// resolved to at most one junction, find_circ.py:1319-1329; --no-linear, :1328-1329)
+extern "C" int fc_batch_emit_host(fc_ctx* ctx, const uint8_t* h_mask, uint64_t idx_base) {
+  if (!ctx) return FC_E_ARG;
+  if (ctx->last_n <= 0) return FC_OK;
+  if (!ctx->last_has_payload) return fc_fail(ctx, FC_E_STATE, "the last batch was uploaded without aggregation payload");
+  cudaStream_t st = ctx->own_stream;
+  const int64_t n = ctx->last_n;
+  uint8_t* d_mask = nullptr;
+  if (h_mask) {
+    FC_CUDA(ctx, ctx->host_path[15].reserve((size_t)n, st, false, 0));
+    d_mask = (uint8_t*)ctx->host_path[15].p;
+    FC_CUDA(ctx, cudaMemcpyAsync(d_mask, h_mask, (size_t)n, cudaMemcpyHostToDevice, st));
+  }
+  void** dp = nullptr;
+  (void)dp;
+  int rc = fc_agg_emit(ctx, n, (const fc_hit*)ctx->host_path[8].p, ctx->last_pairs.d_chrom, ctx->last_pairs.d_flags,
+                       (const uint8_t*)ctx->host_path[9].p, (const int16_t*)ctx->host_path[10].p,
+                       (const int16_t*)ctx->host_path[11].p, (const uint64_t*)ctx->host_path[12].p,
+                       (const uint64_t*)ctx->host_path[13].p, d_mask, idx_base, st);
+  if (rc) return rc;
+  FC_CUDA(ctx, cudaStreamSynchronize(st));
+  return FC_OK;
+}
+
+// --all-hits on the last fc_batch_host batch: h_tie_off = exclusive prefix sum of n_hits (n+1 entries)
+extern "C" int fc_batch_ties_host(fc_ctx* ctx, const fc_scan_params* p, const int64_t* h_tie_off, fc_hit* h_ties) {
+  if (!ctx || !p || !h_tie_off || !h_ties) return FC_E_ARG;
+  if (ctx->last_n <= 0) return FC_OK;
+  cudaStream_t st = ctx->own_stream;
+  const int64_t n = ctx->last_n;
+  const int64_t total = h_tie_off[n];
+  if (total <= 0) return FC_OK;
+  FC_CUDA(ctx, ctx->host_path[15].reserve((size_t)(n + 1) * 8, st, false, 0));
+  fc_dbuf& tb = ctx->agg.scratch[0];
+  FC_CUDA(ctx, tb.reserve((size_t)total * sizeof(fc_hit), st, false, 0));
+  FC_CUDA(ctx, cudaMemcpyAsync(ctx->host_path[15].p, h_tie_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+  int rc = fc_scan_ties(ctx, p, &ctx->last_pairs, (const fc_hit*)ctx->host_path[8].p, (const int64_t*)ctx->host_path[15].p,
+                        (fc_hit*)tb.p, st);
+  if (rc) return rc;
+  FC_CUDA(ctx, cudaMemcpyAsync(h_ties, tb.p, (size_t)total * sizeof(fc_hit), cudaMemcpyDeviceToHost, st));
   FC_CUDA(ctx, cudaStreamSynchronize(st));
   return FC_OK;
 }

@@ -300,7 +300,10 @@ FC_HD uint32_t load_tile_window(const GenomeView& g, int64_t gp, Window<NP>& w) 
   // the window starts at word (o>>5), bit (o&31) of the tile planes
   const int wo = o >> 5;
   const uint32_t bo = (uint32_t)(o & 31);
-  constexpr int MAXWO = PW - NP + 1;  // largest word offset that can occur (window must fit)
+  // largest word offset that can occur: the offset is below the tile stride S = P - tile_W + 1 and tile_W is at
+  // least the smallest window this NP is launched for (32*(NP-1)+1; the NP=2 kernel also serves tiny windows)
+  constexpr int P_BASES = 128 * T - 4;
+  constexpr int MAXWO = (NP <= 2) ? (PW - 1) : (P_BASES - (32 * (NP - 1) + 1)) / 32;
 #pragma unroll
   for (int step = 1; step <= MAXWO; step <<= 1) {
     if (wo & step) {
@@ -322,15 +325,26 @@ FC_HD uint32_t load_tile_window(const GenomeView& g, int64_t gp, Window<NP>& w) 
 }
 
 // ---------------------------------------------------------------- bit-parallel scan on loaded windows
-// NP words of 32 split positions; covers l + 2 <= 32*NP.  WITH_N: nA/nB are the N planes of the windows,
-// the read's N plane is consulted when read_n.
-template <int NP, bool WITH_N>
+// NP words of 32 split positions; covers l + 2 <= 32*NP.  nA/nB are the N planes of the windows (all zero for the
+// common N-free pair: ONE code path for every lane of the warp -- a separate N variant would be executed in full by
+// every warp that holds a single N-touching pair); the read's N plane is consulted when read_n.
+template <int NP>
 FC_HD void scan_planes(const ScanCfg& cfg, const Window<NP>& A, const Window<NP>& B, const uint32_t (&nA)[NP + 1],
                        const uint32_t (&nB)[NP + 1], int l, bool minus_span, const ReadView& rv, int64_t i,
                        bool read_n, Best& best) {
   // splice signal at split position x (bit x&31 of word x>>5):
   //   GT..AG: A[x]=G A[x+1]=T B[x]=A B[x+1]=G ;  CT..AC: A[x]=C A[x+1]=T B[x]=A B[x+1]=C     (find_circ.py:924-954)
-  //   codes A=00 C=01 G=10 T=11 (hi,lo)
+  //   codes A=00 C=01 G=10 T=11 (hi,lo); a signal never contains N
+  // the read planes are needed by almost every pair: issue the loads before the signal logic so that their latency
+  // overlaps it
+  uint32_t rlo[NP], rhi[NP], rnn[NP];
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    const bool have = k < rv.n_words;
+    rlo[k] = have ? ldg32(rv.rlo + (int64_t)k * rv.n + i) : 0u;
+    rhi[k] = have ? ldg32(rv.rhi + (int64_t)k * rv.n + i) : 0u;
+    rnn[k] = (read_n && have) ? ldg32(rv.rn + (int64_t)k * rv.n + i) : 0u;
+  }
   uint32_t sigP[NP], sigM[NP];
   uint32_t any = 0;
 #pragma unroll
@@ -340,33 +354,26 @@ FC_HD void scan_planes(const ScanCfg& cfg, const Window<NP>& A, const Window<NP>
     uint32_t common = (a1hi & a1lo) & ~(B.hi[k] | B.lo[k]);                 // A[x+1]==T and B[x]==A
     uint32_t gg = (A.hi[k] & ~A.lo[k]) & (b1hi & ~b1lo);                    // A[x]==G and B[x+1]==G
     uint32_t cc = (~A.hi[k] & A.lo[k]) & (~b1hi & b1lo);                    // A[x]==C and B[x+1]==C
-    uint32_t vm = low_mask(imin(imax(l + 1 - 32 * k, 0), 32));
-    if (WITH_N) vm &= ~(nA[k] | funnel_r(nA[k], nA[k + 1], 1) | nB[k] | funnel_r(nB[k], nB[k + 1], 1));
+    uint32_t nn = nA[k] | funnel_r(nA[k], nA[k + 1], 1) | nB[k] | funnel_r(nB[k], nB[k + 1], 1);
+    uint32_t vm = low_mask(imin(imax(l + 1 - 32 * k, 0), 32)) & ~nn;
     sigP[k] = common & gg & vm;
     sigM[k] = common & cc & vm;
     any |= sigP[k] | sigM[k];
   }
   if (!any) return;  // no split position carries a canonical signal (most decoy pairs end here)
 
-  // mismatch flags of the read against the donor window (A[i] vs R[i]) and the acceptor window (B[i+2] vs R[i])
+  // mismatch flags of the read against the donor window (A[i] vs R[i]) and the acceptor window (B[i+2] vs R[i]).
+  // N is stored as code 0 on both sides: the base difference is 0 where both are N, the XOR of the N flags decides
+  // the rest (N equals N, N differs from every base -- the reference compares bytes, find_circ.py:861-863)
   uint32_t mA[NP], mB[NP];
   int cumA[NP + 1], cumB[NP + 1];
   cumA[0] = 0;
   cumB[0] = 0;
 #pragma unroll
   for (int k = 0; k < NP; ++k) {
-    const bool have = k < rv.n_words;
-    uint32_t rlo = have ? ldg32(rv.rlo + (int64_t)k * rv.n + i) : 0u;
-    uint32_t rhi = have ? ldg32(rv.rhi + (int64_t)k * rv.n + i) : 0u;
     uint32_t b2lo = funnel_r(B.lo[k], B.lo[k + 1], 2), b2hi = funnel_r(B.hi[k], B.hi[k + 1], 2);
-    uint32_t fa = (A.lo[k] ^ rlo) | (A.hi[k] ^ rhi);
-    uint32_t fb = (b2lo ^ rlo) | (b2hi ^ rhi);
-    if (WITH_N) {
-      // N is stored as code 0 on both sides: the base difference is 0 where both are N, the flag XOR decides the rest
-      uint32_t rn = (read_n && have) ? ldg32(rv.rn + (int64_t)k * rv.n + i) : 0u;
-      fa |= nA[k] ^ rn;
-      fb |= funnel_r(nB[k], nB[k + 1], 2) ^ rn;
-    }
+    uint32_t fa = (A.lo[k] ^ rlo[k]) | (A.hi[k] ^ rhi[k]) | (nA[k] ^ rnn[k]);
+    uint32_t fb = (b2lo ^ rlo[k]) | (b2hi ^ rhi[k]) | (funnel_r(nB[k], nB[k + 1], 2) ^ rnn[k]);
     uint32_t vm = low_mask(imin(imax(l - 32 * k, 0), 32));
     mA[k] = fa & vm;
     mB[k] = fb & vm;
@@ -375,24 +382,50 @@ FC_HD void scan_planes(const ScanCfg& cfg, const Window<NP>& A, const Window<NP>
   }
   const int totalB = cumB[NP];
 
+  // candidates: signal positions of the words that can still reach dist <= maxdist (a split inside word k has at
+  // least cumA[k] donor-side and totalB - cumB[k+1] acceptor-side mismatches)
+  uint32_t c[NP];
+  any = 0;
 #pragma unroll
   for (int k = 0; k < NP; ++k) {
-    // a split inside word k has at least cumA[k] donor-side and totalB - cumB[k+1] acceptor-side mismatches
-    if (cumA[k] > cfg.maxdist || totalB - cumB[k + 1] > cfg.maxdist) continue;
-    uint32_t c = sigP[k] | sigM[k];
-    while (c) {
-      int bit = ffs32(c);
-      c &= c - 1;
-      uint32_t below = (1u << bit) - 1u;
-      int dist = cumA[k] + popc32(mA[k] & below) + (totalB - cumB[k] - popc32(mB[k] & below));
-      if (dist <= cfg.maxdist) {
-        int x = 32 * k + bit;
-        uint32_t strand = (sigM[k] >> bit) & 1u;
-        int ov = anchor_overlap(x, l, cfg.margin);
-        int s = 20 - 10 * dist - ov;
-        if (cfg.strandpref && ((strand != 0u) == minus_span)) s += 100;
-        best.offer(s, x, strand, SIG_GTAG, dist, ov);
+    const bool feasible = cumA[k] <= cfg.maxdist && totalB - cumB[k + 1] <= cfg.maxdist;
+    c[k] = feasible ? (sigP[k] | sigM[k]) : 0u;
+    any |= c[k];
+  }
+  // ONE loop over all words (ascending x), so that the lanes of a warp walk their candidates together
+  while (any) {
+    int k = 0;
+    uint32_t cw = 0, ma = 0, mb = 0, sm = 0;
+    int ca = 0, cb = 0;
+#pragma unroll
+    for (int q = NP - 1; q >= 0; --q) {
+      if (c[q]) {
+        k = q;
+        cw = c[q];
+        ma = mA[q];
+        mb = mB[q];
+        sm = sigM[q];
+        ca = cumA[q];
+        cb = cumB[q];
       }
+    }
+    const int bit = ffs32(cw);
+    const uint32_t rest = cw & (cw - 1u);
+    any = 0;
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      if (q == k) c[q] = rest;
+      any |= c[q];
+    }
+    const uint32_t below = (1u << bit) - 1u;
+    const int dist = ca + popc32(ma & below) + (totalB - cb - popc32(mb & below));
+    if (dist <= cfg.maxdist) {
+      const int x = 32 * k + bit;
+      const uint32_t strand = (sm >> bit) & 1u;
+      const int ov = anchor_overlap(x, l, cfg.margin);
+      int s = 20 - 10 * dist - ov;
+      if (cfg.strandpref && ((strand != 0u) == minus_span)) s += 100;
+      best.offer(s, x, strand, SIG_GTAG, dist, ov);
     }
   }
 }
@@ -444,10 +477,11 @@ FC_HD void scan_pair(const GenomeView& g, const ScanCfg& cfg, const PairArgs& p,
         if (with_n) {
           load_plane<NP>(g.pn, ga, nA);
           load_plane<NP>(g.pn, gb, nB);
-          scan_planes<NP, true>(cfg, A, B, nA, nB, l, minus_span, rv, i, read_n, best);
         } else {
-          scan_planes<NP, false>(cfg, A, B, nA, nB, l, minus_span, rv, i, false, best);
+#pragma unroll
+          for (int k = 0; k <= NP; ++k) nA[k] = nB[k] = 0u;
         }
+        scan_planes<NP>(cfg, A, B, nA, nB, l, minus_span, rv, i, read_n, best);
       }
     } else {
       extra |= W3_RANGE;

@@ -182,9 +182,24 @@ class Engine:
     def agg_reset(self):
         self._check(self.lib.fc_agg_reset(self.h))
 
-    def agg_emit(self, n, d_hits, d_chrom, d_flags, d_wden, d_q_a, d_q_b, d_read_hash, d_qname_hash, idx_base, stream=0):
+    def agg_emit(self, n, d_hits, d_chrom, d_flags, d_wden, d_q_a, d_q_b, d_read_hash, d_qname_hash, idx_base, stream=0,
+                 d_mask=None):
         self._check(self.lib.fc_agg_emit(self.h, n, ptr(d_hits), ptr(d_chrom), ptr(d_flags), ptr(d_wden), ptr(d_q_a),
-                                         ptr(d_q_b), ptr(d_read_hash), ptr(d_qname_hash), idx_base, stream))
+                                         ptr(d_q_b), ptr(d_read_hash), ptr(d_qname_hash), ptr(d_mask), idx_base, stream))
+
+    def batch_emit(self, mask, idx_base):
+        """record the pairs of the last batch_host(emit=False) call whose mask byte is non-zero (None = all)"""
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        self._check(self.lib.fc_batch_emit_host(self.h, None if m is None else m.ctypes.data, int(idx_base)))
+
+    def batch_ties(self, n_hits: np.ndarray) -> (np.ndarray, np.ndarray):
+        """every tie of every pair of the last batch (--all-hits); returns (offsets[n+1], ties)"""
+        off = np.zeros(len(n_hits) + 1, dtype=np.int64)
+        off[1:] = np.cumsum(n_hits.astype(np.int64))
+        ties = np.zeros(int(off[-1]), dtype=HIT_DTYPE)
+        if len(ties):
+            self._check(self.lib.fc_batch_ties_host(self.h, C.byref(self.params), off.ctypes.data, ties.ctypes.data))
+        return off, ties
 
     def agg_append_host(self, recs: np.ndarray):
         recs = np.ascontiguousarray(recs, dtype=JREC_DTYPE)

@@ -1,0 +1,616 @@
+"""
+Host side of the drop-in: the reference's main loop (find_circ.py:1490-1610) re-organised around batched GPU calls.
+
+  alignments -> fragments (find_circ.py:1450-1486) -> mates / adjacent segment pairs (:976-1140)
+             -> batches of anchor pairs (struct of arrays) -> Engine.batch_host(): breakpoint scan on the GPU
+             -> per-fragment evidence logic on the returned hits (record_hits, :1276-1439; control flow only)
+             -> junction records appended to the GPU aggregator -> sort/reduce on the GPU
+             -> BED / reads / multi-event / counter writers (:695-730, 733-763, 1442-1447, 1605-1607)
+
+Nothing here computes a breakpoint or a junction count: with no CUDA device the Engine constructor raises.
+Output row order: the reference iterates a python2 dict (hash order); here rows come in discovery order, which is the
+order python3 would give -- comparisons are made after a canonical sort (BASELINE.json north_star).
+"""
+from __future__ import annotations
+
+import dataclasses
+import gzip
+import logging
+import os
+import sys
+import time
+from collections import defaultdict
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from ._lib import HIT_DTYPE, JREC_DTYPE
+from .engine import Engine, decode_signal
+from .samio import Alignment
+
+VERSION = "1.99-b200"
+
+
+@dataclasses.dataclass
+class Options:
+    """find_circ.py:383-413"""
+
+    genome: str = ""
+    output: str = "find_circ_run"
+    name: str = "unknown"
+    min_uniq_qual: int = 2
+    asize: int = 15
+    margin: int = 2
+    maxdist: int = 2
+    short_threshold: int = 100
+    huge_threshold: int = 100000
+    noncanonical: bool = False
+    allhits: bool = False
+    strandpref: bool = False
+    halfunique: bool = False
+    report_nobridges: bool = False
+    nolinear: bool = False
+    multi_events: bool = True
+    throughput: bool = False
+    chunksize: int = 100000
+    noop: bool = False
+    silent: bool = False
+    stdout: Optional[str] = None
+    batch_pairs: int = 1 << 18  # anchor pairs per GPU batch (ours)
+    device: int = 0
+
+
+def py2_str(x) -> str:
+    """python2 str(): 12 significant digits for floats"""
+    if isinstance(x, (bool, np.bool_)):
+        return "True" if x else "False"
+    if isinstance(x, (float, np.floating)):
+        s = "%.12g" % float(x)
+        if s in ("inf", "-inf", "nan"):
+            return s
+        if "." not in s and "e" not in s:
+            s += ".0"
+        return s
+    return str(x)
+
+
+class Mate(object):
+    """MateSegments (find_circ.py:976-1056)"""
+
+    __slots__ = ("primary", "proper", "other_chrom", "other_strand")
+
+    def __init__(self, primary: Alignment):
+        self.primary = primary
+        self.proper = [primary]
+        self.other_chrom: List[Alignment] = []
+        self.other_strand: List[Alignment] = []
+
+    def add(self, rec: Alignment):
+        if rec.tid != self.primary.tid:
+            self.other_chrom.append(rec)
+        elif rec.is_reverse != self.primary.is_reverse:
+            self.other_strand.append(rec)
+        else:
+            self.proper.append(rec)
+
+
+class Span(object):
+    """one anchor pair = JunctionSpan (find_circ.py:821-852); `row` is its index in the current GPU batch"""
+
+    __slots__ = ("A", "B", "primary", "q_start", "q_end", "den", "uniq", "backsplice", "row")
+
+    def __init__(self, A, B, primary, q_start, q_end, den):
+        self.A = A
+        self.B = B
+        self.primary = primary
+        self.q_start = q_start
+        self.q_end = q_end
+        self.den = den
+        self.uniq = min(A.uniqueness(), B.uniqueness())
+        self.backsplice = (B.pos - A.aend) < 0
+        self.row = -1
+
+
+class Fragment(object):
+    __slots__ = ("name", "mates", "circ", "lin", "unspliced", "broken", "conditional")
+
+    def __init__(self, name):
+        self.name = name
+        self.mates: List[Mate] = []
+        self.circ: List[Span] = []
+        self.lin: List[Span] = []
+        self.unspliced: List[Alignment] = []
+        self.broken: List[Alignment] = []
+        self.conditional = False
+
+
+def iter_fragments(records: Iterable[Alignment], N) -> Iterable[Tuple[Optional[Mate], Mate]]:
+    """find_circ.py:1450-1486"""
+    it = iter(records)
+    try:
+        first = next(it)
+    except StopIteration:
+        return
+    N["total_mates"] += 1
+    cur, other = Mate(first), None
+    for rec in it:
+        if rec.flag & 0x4:
+            N["unmapped_reads"] += 1
+            continue
+        p = cur.primary
+        if rec.qname == p.qname:
+            if (rec.flag & 0x40) == (p.flag & 0x40):
+                cur.add(rec)
+            else:
+                N["total_mates"] += 1
+                other, cur = cur, Mate(rec)
+        else:
+            yield other, cur
+            N["total_mates"] += 1
+            other, cur = None, Mate(rec)
+    yield other, cur
+
+
+def mate_spans(mate: Mate, asize: int, N) -> List[Span]:
+    """adjacent_segment_pairs (find_circ.py:1058-1140)"""
+    segs = mate.proper
+    den = len(segs) - 1
+    starts = [s.clip_start() for s in segs]
+    ends = [st + s.query_length() for st, s in zip(starts, segs)]
+    order = sorted(range(len(segs)), key=lambda k: starts[k])
+    out = []
+    for ia, ib in zip(order, order[1:]):
+        if ends[ia] - starts[ia] < asize or ends[ib] - starts[ib] < asize:
+            N["seg_too_short_skip"] += 1
+            continue
+        out.append(Span(segs[ia], segs[ib], mate.primary, min(starts[ia], starts[ib]), max(ends[ia], ends[ib]), den))
+    return out
+
+
+class JunctionInfo(object):
+    """host-side companions of a junction that never reach the GPU: per-fragment flags (find_circ.py:513-524, 632-652)"""
+
+    __slots__ = ("flags", "read_flags")
+
+    def __init__(self):
+        self.flags: Dict[str, int] = defaultdict(int)
+        self.read_flags: Dict[str, set] = defaultdict(set)
+
+
+BED_HEADER = [
+    "chrom", "start", "end", "name", "n_frags", "strand", "n_weight", "n_spanned", "n_uniq", "uniq_bridges",
+    "best_qual_left", "best_qual_right", "tissues", "tiss_counts", "edits", "anchor_overlap", "breakpoints",
+    "signal", "strandmatch", "category", "flags", "flag_counts",
+]
+MULTI_HEADER = ["chrom", "start", "end", "name", "score", "strand", "fragment_name", "lin_cons", "lin_incons",
+                "unspliced_cons", "unspliced_incons"]
+
+
+class Run(object):
+    def __init__(self, opt: Options, chrom_names: Sequence[str], engine: Optional[Engine] = None):
+        self.opt = opt
+        self.N: Dict[str, float] = defaultdict(float)
+        self.eng = engine or Engine(opt.device, opt.asize, opt.margin, opt.maxdist, opt.noncanonical, opt.strandpref)
+        self.own_engine = engine is None
+        if not self.eng.chrom_names:
+            self.eng.load_genome_fasta(opt.genome)
+        self.sam_chroms = list(chrom_names)
+        # SAM tid -> genome chromosome id; unknown names raise KeyError when first used, like find_circ.py:193
+        self._tid2gid: Dict[int, int] = {}
+        self.eff = opt.asize - opt.margin
+        self.frags: List[Fragment] = []
+        self._reset_batch()
+        self.idx_base = 0
+        self.n_fragments = 0
+        self.n_pairs_scanned = 0
+        self.info: Dict[tuple, JunctionInfo] = {}
+        self.reads_out: List[tuple] = []   # (qname, seq, qual, [keys], flags)
+        self.multi_out: List[tuple] = []
+        self.t_scan = 0.0
+        self.eng.agg_reset()
+
+    # ------------------------------------------------------------------ batch assembly
+    def _reset_batch(self):
+        self.b_chrom, self.b_a, self.b_b, self.b_l, self.b_fl = [], [], [], [], []
+        self.b_int, self.b_den, self.b_qa, self.b_qb, self.b_rh, self.b_qh = [], [], [], [], [], []
+        self.frags = []
+        self.b_conditional = False
+
+    def gid(self, tid: int) -> int:
+        g = self._tid2gid.get(tid)
+        if g is None:
+            g = self.eng.chrom_id(self.sam_chroms[tid])
+            self._tid2gid[tid] = g
+        return g
+
+    def _queue(self, sp: Span):
+        eff = self.eff
+        A, B = sp.A, sp.B
+        part = sp.primary.seq[sp.q_start:sp.q_end]
+        L = len(part)
+        sp.row = len(self.b_chrom)
+        self.b_chrom.append(self.gid(A.tid))
+        self.b_a.append(A.pos + eff)
+        self.b_b.append(B.aend - eff)
+        self.b_l.append(L - 2 * eff)
+        self.b_fl.append((1 if sp.backsplice else 0) | (2 if sp.primary.is_reverse else 0))
+        self.b_int.append(part[eff:max(L - eff, 0)].encode("latin-1"))
+        if sp.den > 255:
+            raise ValueError("read %s has more than 256 segments" % sp.primary.qname)
+        self.b_den.append(sp.den)
+        # Hit.add: AS - XS with XS defaulting to 0 (find_circ.py:556-559)
+        self.b_qa.append(A.AS - (A.XS or 0))
+        self.b_qb.append(B.AS - (B.XS or 0))
+        self.b_rh.append(self.eng.hash_read(sp.primary.seq.encode("latin-1")))
+        self.b_qh.append(self.eng.hash_bytes(sp.primary.qname.encode("latin-1")))
+
+    def add_fragment(self, mate1: Optional[Mate], mate2: Mate):
+        """process_mate x2 + the head of record_hits (find_circ.py:1492-1526, 1560-1574)"""
+        opt, N = self.opt, self.N
+        self.n_fragments += 1
+        fr = Fragment(mate2.primary.qname)
+        for mate in (mate1, mate2):
+            if mate is None:
+                continue
+            fr.mates.append(mate)
+            if len(mate.proper) < 2:
+                N["unspliced_mates"] += 1
+                fr.unspliced.append(mate.primary)
+                continue
+            L = len(mate.primary.seq)
+            lo, hi = L, 0
+            for sp in mate_spans(mate, opt.asize, N):
+                (fr.circ if sp.backsplice else fr.lin).append(sp)
+                lo, hi = min(lo, sp.q_start), max(hi, sp.q_end)
+            if hi < L - opt.asize or lo > opt.asize:
+                fr.broken.extend(mate.other_chrom)
+                fr.broken.extend(mate.other_strand)
+        if not fr.circ and opt.nolinear:
+            return
+        if not (fr.circ or fr.lin):
+            return
+        for sp in fr.circ + fr.lin:
+            if sp.uniq >= opt.min_uniq_qual:
+                self._queue(sp)
+        # the linear spans only count when the back-splices resolve to <= 1 junction (find_circ.py:1319-1329)
+        n_circ_q = sum(1 for sp in fr.circ if sp.row >= 0)
+        fr.conditional = bool(fr.lin) and (n_circ_q >= 2 or opt.nolinear or (opt.allhits and n_circ_q >= 1))
+        self.b_conditional = self.b_conditional or fr.conditional
+        self.frags.append(fr)
+        if len(self.b_chrom) >= opt.batch_pairs:
+            self.flush()
+
+    # ------------------------------------------------------------------ GPU batch + evidence logic
+    def flush(self):
+        n = len(self.b_chrom)
+        if not self.frags:
+            return
+        opt = self.opt
+        two_step = self.b_conditional or opt.allhits
+        hits = np.zeros(n, dtype=HIT_DTYPE)
+        if n:
+            width = max(1, max(len(b) for b in self.b_int))
+            width = (width + 15) // 16 * 16
+            internal = np.zeros((n, width), dtype=np.uint8)
+            for i, b in enumerate(self.b_int):
+                if b:
+                    internal[i, :len(b)] = np.frombuffer(b, dtype=np.uint8)
+            t0 = time.perf_counter()
+            self.eng.batch_host(
+                np.array(self.b_chrom, np.int32), np.array(self.b_a, np.int32), np.array(self.b_b, np.int32),
+                np.array(self.b_l, np.int32), np.array(self.b_fl, np.uint8), internal,
+                np.array(self.b_den, np.uint8), np.clip(np.array(self.b_qa, np.int64), -32768, 32767).astype(np.int16),
+                np.clip(np.array(self.b_qb, np.int64), -32768, 32767).astype(np.int16),
+                np.array(self.b_rh, np.uint64), np.array(self.b_qh, np.uint64), self.idx_base,
+                emit=not two_step, out=hits)
+            self.t_scan += time.perf_counter() - t0
+            self.n_pairs_scanned += n
+        ties_off = ties = None
+        if opt.allhits and n:
+            ties_off, ties = self.eng.batch_ties((hits["w2"] & 0xFFFF).astype(np.int64))
+        mask = np.ones(n, dtype=np.uint8) if two_step else None
+        host_recs: List[tuple] = []
+        for fr in self.frags:
+            self._record_hits(fr, hits, mask, ties_off, ties, host_recs)
+        if two_step and n:
+            if opt.allhits:
+                self._append_host_records(host_recs)
+            else:
+                self.eng.batch_emit(mask, self.idx_base)
+        self.idx_base += max(n, 1) * (64 if opt.allhits else 1)
+        self._reset_batch()
+
+    def _append_host_records(self, recs: List[tuple]):
+        """--all-hits: the records (one per tie) are assembled on the host from the GPU's tie list"""
+        if not recs:
+            return
+        arr = np.zeros(len(recs), dtype=JREC_DTYPE)
+        for k, (key, row, sub, dist, ov, nh, sig) in enumerate(recs):
+            gid, start, end, strand, kind = key
+            rh = self.b_rh[row]
+            back = self.b_fl[row] & 1
+            qa, qb = self.b_qa[row], self.b_qb[row]
+            arr[k] = (gid, start, end, (1 if strand == "-" else 0) | (kind << 1) | ((rh & 1) << 2) | (self.b_den[row] << 8) | (sig << 16),
+                      self.idx_base + row * 64 + min(sub, 63), rh, self.b_qh[row],
+                      max(-32768, min(32767, qb if back else qa)), max(-32768, min(32767, qa if back else qb)), nh, dist, ov)
+        self.eng.agg_append_host(arr)
+
+    @staticmethod
+    def _hit_fields(h):
+        w2, w3 = int(h["w2"]), int(h["w3"])
+        return (int(h["start"]), int(h["end"]), "-" if (w3 & 1) else "+", (w2 >> 16) & 0xFF, w2 >> 24, w2 & 0xFFFF, (w3 >> 1) & 0xFFF)
+
+    def _splices(self, sp: Span, hits, ties_off, ties):
+        """the list find_breakpoints() returns, truncated to the first tie unless --all-hits (find_circ.py:1312-1317)"""
+        h = hits[sp.row]
+        nh = int(h["w2"]) & 0xFFFF
+        if nh == 0:
+            return []
+        if self.opt.allhits and nh > 1:
+            return [self._hit_fields(ties[k]) for k in range(int(ties_off[sp.row]), int(ties_off[sp.row + 1]))]
+        return [self._hit_fields(h)]
+
+    def _info(self, key) -> JunctionInfo:
+        inf = self.info.get(key)
+        if inf is None:
+            inf = self.info[key] = JunctionInfo()
+        return inf
+
+    def _record_hits(self, fr: Fragment, hits, mask, ties_off, ties, host_recs):
+        """record_hits (find_circ.py:1276-1439) on the GPU's answers; junction identity = (chrom id, start, end, strand, kind)"""
+        opt, N = self.opt, self.N
+        warns = set()
+        junctions: List[tuple] = []
+
+        def note(key):
+            if key not in junctions:
+                junctions.append(key)
+
+        circ_coords = set()
+        circ_key = None
+        for sp in fr.circ:
+            if sp.row < 0:
+                N["circ_junc_not_unique"] += 1
+                continue
+            spl = self._splices(sp, hits, ties_off, ties)
+            if not spl:
+                N["circ_no_bp"] += 1
+                warns.add("WARN_UNRESOLVED_EXTRA_BACKSPLICE")
+                continue
+            N["circ_spliced"] += 1
+            gid = self.b_chrom[sp.row]
+            for sub, (start, end, strand, dist, ov, nh, sig) in enumerate(spl):
+                circ_key = (gid, start, end, strand, 0)
+                if opt.allhits:
+                    host_recs.append((circ_key, sp.row, sub, dist, ov, nh, sig))
+                circ_coords.add(circ_key)
+                note(circ_key)
+                if not opt.allhits:
+                    break
+
+        def skip_linear():
+            if mask is not None:
+                for sp in fr.lin:
+                    if sp.row >= 0:
+                        mask[sp.row] = 0
+
+        if len(circ_coords) > 1:
+            for key in circ_coords:
+                warns.add("WARN_MULTI_BACKSPLICE")
+                self._info(key).flags["WARN_MULTI_BACKSPLICE"] += 1
+                self._info(key).read_flags[fr.name].add("WARN_MULTI_BACKSPLICE")
+                note(key)
+            skip_linear()
+            return self._finish_fragment(fr, junctions, warns)
+        if not circ_coords and opt.nolinear:
+            skip_linear()
+            return self._finish_fragment(fr, junctions, warns)
+
+        if circ_coords:
+            _, circ_start, circ_end, _, _ = circ_key
+            first_tid = fr.circ[0].primary.tid
+            if len(fr.circ) > 1:
+                warns.add("SUPPORT_CLOSURE")
+
+        lin_cons, lin_incons = set(), set()
+        for sp in fr.lin:
+            if sp.row < 0:
+                N["lin_junc_not_unique"] += 1
+                continue
+            spl = self._splices(sp, hits, ties_off, ties)
+            if not spl:
+                N["lin_no_bp"] += 1
+                warns.add("WARN_UNRESOLVED_LINSPLICE")
+                continue
+            N["lin_spliced"] += 1
+            gid = self.b_chrom[sp.row]
+            cname = self.eng.chrom_names[gid]
+            for sub, (start, end, strand, dist, ov, nh, sig) in enumerate(spl):
+                key = (gid, start, end, strand, 1)
+                if opt.allhits:
+                    host_recs.append((key, sp.row, sub, dist, ov, nh, sig))
+                note(key)
+                if circ_coords:
+                    coord = (cname, start, end, strand)
+                    if start <= circ_start or end >= circ_end:
+                        warns.add("WARN_OUTSIDE_SPLICE_JUNCTION")
+                        lin_incons.add(coord)
+                    else:
+                        lin_cons.add(coord)
+                        warns.add("SUPPORT_INSIDE_SPLICE_JUNCTION")
+                if not opt.allhits:
+                    break
+
+        if circ_coords:
+            un_cons, un_incons = set(), set()
+            for rec in fr.unspliced:
+                coord = (self.sam_chroms[rec.tid], rec.pos, rec.aend, "*")
+                if first_tid != rec.tid:
+                    warns.add("WARN_OTHER_CHROM_MATE")
+                    un_incons.add(coord)
+                elif rec.pos + opt.asize <= circ_start or rec.aend - opt.asize >= circ_end:
+                    warns.add("WARN_OUTSIDE_MATE")
+                    un_incons.add(coord)
+                else:
+                    warns.add("SUPPORT_INSIDE_MATE")
+                    un_cons.add(coord)
+            if fr.broken:
+                warns.add("BROKEN_SEGMENTS")
+            if (un_cons or un_incons or lin_cons or lin_incons) and opt.multi_events:
+                self.multi_out.append((fr.name, circ_key, lin_cons, lin_incons, un_cons, un_incons))
+            inf = self._info(circ_key)
+            for w in warns:
+                inf.flags[w] += 1
+                inf.read_flags[fr.name].add(w)
+        return self._finish_fragment(fr, junctions, warns)
+
+    def _finish_fragment(self, fr: Fragment, junctions, warns):
+        if junctions:
+            fl = tuple(sorted(warns))
+            for mate in fr.mates:
+                p = mate.primary
+                self.reads_out.append((p.qname, p.seq, p.qual, tuple(junctions), fl))
+
+    # ------------------------------------------------------------------ driver
+    def process(self, records: Iterable[Alignment]):
+        for mate1, mate2 in iter_fragments(records, self.N):
+            if self.opt.noop:
+                self.n_fragments += 1
+                continue
+            self.add_fragment(mate1, mate2)
+        self.flush()
+
+    # ------------------------------------------------------------------ outputs
+    def finalize(self, dist=None, torch_dev=None):
+        """aggregate on the GPU and build the text outputs"""
+        if dist is not None and dist.get_world_size() > 1:
+            from . import parallel
+
+            parallel.exchange_records(self.eng, dist, torch_dev, 0)
+        nj = self.eng.agg_finalize(0)
+        junc = self.eng.agg_fetch(nj)
+        if dist is not None and dist.get_world_size() > 1:
+            from . import parallel
+
+            junc = parallel.gather_junctions(junc, dist, torch_dev)
+        self.junctions = junc
+        return junc
+
+    def _names(self, junc) -> Dict[tuple, str]:
+        """discovery-order names, counting junctions that are filtered from the output too (find_circ.py:683-686)"""
+        names = {}
+        counts = [0, 0]
+        prefix = ("circ", "lin")
+        cn = self.eng.chrom_names
+        for r in junc:
+            kind = (int(r["sk"]) >> 1) & 1
+            counts[kind] += 1
+            key = (int(r["chrom"]), int(r["start"]), int(r["end"]), "-" if int(r["sk"]) & 1 else "+", kind)
+            names[key] = "%s_%s_%06d" % (self.opt.name, prefix[kind], counts[kind])
+        return names
+
+    def categories(self, r, inf: Optional[JunctionInfo], min_dist) -> List[str]:
+        """Hit.categories (find_circ.py:601-654)"""
+        opt = self.opt
+        cats = []
+        if decode_signal((int(r["sk"]) >> 16) & 0xFFF) != "GTAG":
+            cats.append("NON_CANONICAL")
+        if int(r["best_q_left"]) == 0 or int(r["best_q_right"]) == 0:
+            cats.append("WARN_NON_UNIQUE_ANCHOR")
+        if float(r["n_uniq_bridges"]) == 0:
+            cats.append("WARN_NO_UNIQ_BRIDGES")
+        if int(r["min_n_hits"]) > 1:
+            cats.append("WARN_AMBIGUOUS_BP")
+        ov, ed = int(r["min_ov"]), int(min_dist)
+        if ov == 0 and ed == 0:
+            pass
+        elif ov < 2 and ed < 2:
+            cats.append("WARN_EXT_1MM")
+        elif ov >= 2 or ed >= 2:
+            cats.append("WARN_EXT_2MM+")
+        span = int(r["end"]) - int(r["start"])
+        if span < opt.short_threshold:
+            cats.append("SHORT")
+        elif span > opt.huge_threshold:
+            cats.append("HUGE")
+        if inf is not None and inf.read_flags:
+            unbroken = sum(1 for fl in inf.read_flags.values() if "BROKEN_SEGMENTS" not in fl)
+            unwarned = sum(1 for fl in inf.read_flags.values() for w in fl if not w.startswith("WARN"))
+            if not unbroken:
+                cats.append("WARN_ALWAYS_BROKEN")
+            if not unwarned:
+                cats.append("WARN_ALWAYS_WARN")
+        return cats
+
+    def bed_text(self, kind: int) -> str:
+        """store_list (find_circ.py:695-730)"""
+        opt = self.opt
+        names = self._names(self.junctions)
+        cn = self.eng.chrom_names
+        lines = ["#" + "\t".join(BED_HEADER) + "\n"]
+        for r in self.junctions:
+            sk = int(r["sk"])
+            if ((sk >> 1) & 1) != kind:
+                continue
+            ql, qr = int(r["best_q_left"]), int(r["best_q_right"])
+            if opt.halfunique:
+                if ql < opt.min_uniq_qual and qr < opt.min_uniq_qual:
+                    continue
+            elif ql < opt.min_uniq_qual or qr < opt.min_uniq_qual:
+                continue
+            bridges = float(r["n_uniq_bridges"])
+            if bridges == 0 and not opt.report_nobridges:
+                continue
+            start, end = int(r["start"]), int(r["end"])
+            strand = "-" if sk & 1 else "+"
+            key = (int(r["chrom"]), start, end, strand, kind)
+            inf = self.info.get(key)
+            if inf is not None and inf.flags:
+                flags = sorted(inf.flags)
+                fcounts = [inf.flags[f] for f in flags]
+            else:
+                flags, fcounts = ["N/A"], [0]
+            w = float(r["n_weighted"])
+            # with --max-mismatch 0 the reference's edit distance is a python bool (find_circ.py:868-870)
+            edits = bool(int(r["min_dist"])) if opt.maxdist == 0 else int(r["min_dist"])
+            cols = [
+                cn[int(r["chrom"])], start, end, names[key], int(r["n_frags"]), strand, w, int(r["n_spanned"]), int(r["n_uniq"]),
+                bridges, ql, qr, opt.name, py2_str(w), edits, int(r["min_ov"]), int(r["min_n_hits"]),
+                decode_signal((sk >> 16) & 0xFFF), "N/A", ",".join(sorted(self.categories(r, inf, int(r["min_dist"])))),
+                ",".join(flags), ",".join(str(c) for c in fcounts),
+            ]
+            lines.append("\t".join(py2_str(c) for c in cols) + "\n")
+        return "".join(lines)
+
+    def reads_text(self) -> str:
+        """write_read (find_circ.py:1442-1447)"""
+        names = self._names(self.junctions)
+        out = []
+        for qname, seq, qual, keys, flags in self.reads_out:
+            head = "%s %s %s" % (qname, ",".join(sorted(names[k] for k in keys)), ",".join(flags))
+            out.append("@%s\n%s\n+%s\n%s\n" % (head, seq, head, qual))
+        return "".join(out)
+
+    def multi_text(self) -> str:
+        """MultiEventRecorder (find_circ.py:733-763)"""
+        names = self._names(self.junctions)
+        cn = self.eng.chrom_names
+        lines = ["#" + "\t".join(MULTI_HEADER) + "\n"]
+        for frag, ck, lin_cons, lin_incons, un_cons, un_incons in self.multi_out:
+            score = len(lin_cons) - 10 * len(lin_incons) + len(un_cons) - 10 * len(un_incons)
+            gid, start, end, strand, _ = ck
+            cols = [cn[gid], str(start), str(end), "ME:" + names[ck], str(score), strand, frag]
+            cols.append(",".join("%d-%d" % (s, e) for c, s, e, _ in sorted(lin_cons)) if lin_cons else "NO_LIN_CONS")
+            cols.append(",".join("[%s:%d-%d]" % (c, s, e) for c, s, e, _ in sorted(lin_incons)) if lin_incons else "NO_LIN_INCONS")
+            cols.append(",".join("%d-%d" % (s, e) for c, s, e, _ in sorted(un_cons)) if un_cons else "NO_UNSPLICED_CONS")
+            cols.append(",".join("[%s:%d-%d]" % (c, s, e) for c, s, e, _ in sorted(un_incons)) if un_incons else "NO_UNSPLICED_INCONS")
+            lines.append("\t".join(cols) + "\n")
+        return "".join(lines)
+
+    def counters_text(self) -> str:
+        """the N dump of find_circ.py:1605-1607"""
+        return "".join("%s=%s\n" % (k, py2_str(float(self.N[k]))) for k in sorted(self.N))
+
+    def close(self):
+        if self.own_engine:
+            self.eng.close()

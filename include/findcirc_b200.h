@@ -189,6 +189,13 @@ int fc_batch_host(fc_ctx* ctx, const fc_scan_params* p, int64_t n, const int32_t
                   const uint64_t* h_read_hash, const uint64_t* h_qname_hash, uint64_t idx_base, int32_t emit,
                   fc_hit* h_out);
 
+/* Two-step batches: after fc_batch_host(..., emit = 0) the host inspects the hits and decides which pairs are
+ * recorded (find_circ.py:1319-1329: the linear spans of a fragment count only when its back-splices resolved to at most
+ * one junction); fc_batch_emit_host records the pairs with h_mask[i] != 0 (NULL = all) from the retained device copy. */
+int fc_batch_emit_host(fc_ctx* ctx, const uint8_t* h_mask, uint64_t idx_base);
+/* --all-hits (find_circ.py:1312-1317) for the retained batch: h_tie_off = exclusive prefix sum of n_hits (n+1 entries) */
+int fc_batch_ties_host(fc_ctx* ctx, const fc_scan_params* p, const int64_t* h_tie_off, fc_hit* h_ties);
+
 /* ------------------------------------------------------------------ junction aggregation
  * fc_agg_emit: turns scan results into fc_jrec records on the device (first tie of every pair with n_hits>0),
  *   appending to the context's record buffer.  Per-pair payload arrays are device pointers.
@@ -197,7 +204,8 @@ int fc_batch_host(fc_ctx* ctx, const fc_scan_params* p, int64_t n, const int32_t
 int fc_agg_reset(fc_ctx* ctx);
 int fc_agg_emit(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, const int32_t* d_chrom, const uint8_t* d_flags,
                 const uint8_t* d_wden, const int16_t* d_q_a, const int16_t* d_q_b, const uint64_t* d_read_hash,
-                const uint64_t* d_qname_hash, uint64_t idx_base, void* stream);
+                const uint64_t* d_qname_hash, const uint8_t* d_mask /* NULL or per-pair 0/1: record this pair */,
+                uint64_t idx_base, void* stream);
 int fc_agg_append(fc_ctx* ctx, int64_t n, const fc_jrec* d_recs, void* stream); /* records built elsewhere (other ranks) */
 int fc_agg_append_host(fc_ctx* ctx, int64_t n, const fc_jrec* h_recs);
 int64_t fc_agg_n_records(fc_ctx* ctx);

@@ -1,0 +1,29 @@
+"""
+CPU coverage of the product's HOST logic (find_circ2_b200/pipeline.py, cli.py, samio.py): with the GPU engine replaced
+by tests/fake_engine.py the pipeline must reproduce the reference goldens.  The real engine is covered by
+tests/test_gpu_pipeline.py (-m gpu).
+"""
+import os
+
+import pytest
+
+from conftest import golden_cases, golden_ids
+from fake_engine import FakeEngine
+from oracle import find_circ_oracle as O
+
+
+@pytest.mark.parametrize("case_dir,ref_dir,argv", golden_cases(), ids=golden_ids())
+def test_host_logic_matches_reference(case_dir, ref_dir, argv):
+    from find_circ2_b200 import cli
+
+    opt = cli.parse_args(["-G", os.path.join(case_dir, "genome.fa")] + argv)[0]
+    opt.batch_pairs = 211
+    eng = FakeEngine(0, opt.asize, opt.margin, opt.maxdist, opt.noncanonical, opt.strandpref)
+    eng.load_genome_fasta(opt.genome)
+    out = cli.run_to_strings(opt, os.path.join(case_dir, "input.sam"), engine=eng)
+    rd = lambda n: open(os.path.join(ref_dir, n)).read()  # noqa: E731
+    assert O.canonical_bed(out["circ"]) == O.canonical_bed(rd("circ_splice_sites.bed"))
+    assert O.canonical_bed(out["lin"]) == O.canonical_bed(rd("lin_splice_sites.bed"))
+    assert out["reads"] == rd("spliced_reads.fastq")
+    assert O.canonical_multi(out["multi"]) == O.canonical_multi(rd("multi_events.tsv"))
+    assert out["counters"] == rd("counters.txt")
