@@ -105,12 +105,12 @@ __device__ inline bool same_key(const fc_jrec& a, const fc_jrec& b) {
 
 // head[i] = 1 when sorted record i starts a new junction; counts hash collisions (equal hash, different key)
 __global__ void heads_kernel(int64_t n, const fc_jrec* __restrict__ s, const uint64_t* __restrict__ h_sorted,
-                             uint32_t* __restrict__ head, unsigned long long* __restrict__ collisions) {
+                             uint64_t hmask, uint32_t* __restrict__ head, unsigned long long* __restrict__ collisions) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t hd = 1;
   if (i > 0) {
-    bool same_h = h_sorted[i] == h_sorted[i - 1];
+    bool same_h = ((h_sorted[i] ^ h_sorted[i - 1]) & hmask) == 0;  // only the sorted bits order the records
     bool same_k = same_key(s[i], s[i - 1]);
     if (same_h && !same_k) atomicAdd(collisions, 1ull);
     hd = same_k ? 0u : 1u;
@@ -209,19 +209,65 @@ __global__ void split_hash_kernel(int64_t n, const fc_jrec* __restrict__ s, cons
   seg[i] = seg_incl[i] - 1u;
 }
 
-// after sorting by (seg, hash): count the first element of every (seg, hash) run
-__global__ void distinct_kernel(int64_t n, const uint32_t* __restrict__ seg, const uint64_t* __restrict__ h, int which,
-                                JAcc* __restrict__ acc) {
+// ---- distinct counts with exact hash sets (128-bit entries, 128-bit CAS) ----------------------------------------
+struct alignas(16) U128 {
+  unsigned long long lo, hi;
+};
+__device__ __forceinline__ U128 cas128(U128* addr, U128 cmp, U128 val) {
+  U128 old;
+  asm volatile(
+      "{\n\t"
+      ".reg .b128 c, v, o;\n\t"
+      "mov.b128 c, {%2, %3};\n\t"
+      "mov.b128 v, {%4, %5};\n\t"
+      "atom.global.relaxed.gpu.cas.b128 o, [%6], c, v;\n\t"
+      "mov.b128 {%0, %1}, o;\n\t"
+      "}\n"
+      : "=l"(old.lo), "=l"(old.hi)
+      : "l"(cmp.lo), "l"(cmp.hi), "l"(val.lo), "l"(val.hi), "l"(addr)
+      : "memory");
+  return old;
+}
+// insert (value, seg) into an open-addressing set; returns true when it was not present.  The whole element is the
+// 128-bit entry, so membership is exact (no fingerprint collisions).
+__device__ __forceinline__ bool set_insert(U128* table, unsigned long long mask, unsigned long long value, uint32_t seg) {
+  const U128 mine{value, (unsigned long long)seg + 1ull};
+  unsigned long long slot = fc_mix64(value ^ ((unsigned long long)seg * 0x9E3779B97F4A7C15ULL)) & mask;
+  for (;;) {
+    const ulonglong2 cur = __ldcg(reinterpret_cast<const ulonglong2*>(table + slot));
+    if (cur.x == mine.lo && cur.y == mine.hi) return false;
+    if (cur.x == 0ull && cur.y == 0ull) {
+      const U128 old = cas128(table + slot, U128{0ull, 0ull}, mine);
+      if (old.lo == 0ull && old.hi == 0ull) return true;
+      if (old.lo == mine.lo && old.hi == mine.hi) return false;
+    }
+    slot = (slot + 1ull) & mask;
+  }
+}
+
+// one thread per sorted record: is this the first time its read sequence / its fragment name is seen in its junction?
+// Records are sorted by junction, so the lanes of a warp mostly share one junction: the per-junction counters are
+// bumped once per (warp, junction) group.
+__global__ void distinct_hash_kernel(int64_t n, const fc_jrec* __restrict__ s, const uint32_t* __restrict__ seg_incl,
+                                     U128* __restrict__ tab_reads, U128* __restrict__ tab_names, unsigned long long mask,
+                                     JAcc* __restrict__ acc) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  bool first = i == 0 || seg[i] != seg[i - 1] || h[i] != h[i - 1];
-  if (!first) return;
-  JAcc* a = acc + seg[i];
-  if (which == 0) {
-    atomicAdd(&a->n_uniq, 1u);
-    if (h[i] & 1ull) atomicAdd(&a->n_pal, 1u);
-  } else {
-    atomicAdd(&a->n_frags, 1u);
+  const bool active = i < n;
+  const unsigned amask = __ballot_sync(0xffffffffu, active);
+  if (!active) return;
+  const uint32_t seg = seg_incl[i] - 1u;
+  const unsigned long long rh = s[i].read_hash, qh = s[i].qname_hash;
+  const bool new_read = set_insert(tab_reads, mask, rh, seg);
+  const bool new_name = set_insert(tab_names, mask, qh, seg);
+  const unsigned peers = __match_any_sync(amask, seg);
+  const unsigned b_read = __ballot_sync(amask, new_read) & peers;
+  const unsigned b_pal = __ballot_sync(amask, new_read && (rh & 1ull)) & peers;
+  const unsigned b_name = __ballot_sync(amask, new_name) & peers;
+  if ((int)(threadIdx.x & 31) == __ffs((int)peers) - 1) {
+    JAcc* a = acc + seg;
+    if (b_read) atomicAdd(&a->n_uniq, (unsigned)__popc(b_read));
+    if (b_pal) atomicAdd(&a->n_pal, (unsigned)__popc(b_pal));
+    if (b_name) atomicAdd(&a->n_frags, (unsigned)__popc(b_name));
   }
 }
 
@@ -543,15 +589,22 @@ extern "C" int64_t fc_agg_finalize(fc_ctx* ctx, void* stream) {
 
   uint64_t seed = 0x9E3779B97F4A7C15ULL;
   bool ok = false;
-  for (int attempt = 0; attempt < 4 && !ok; ++attempt, seed = fc_mix64(seed + attempt)) {
+  // sort only as many hash bits as make a collision between two different keys unlikely (~2^-7); the run check
+  // below detects one, and the retries use all 64 bits
+  int lg = 1;
+  while ((1ll << lg) < n) lg++;
+  int bits = 2 * lg + 6;
+  if (bits > 64) bits = 64;
+  for (int attempt = 0; attempt < 4 && !ok; ++attempt, seed = fc_mix64(seed + attempt), bits = 64) {
+    const uint64_t hmask = bits >= 64 ? ~0ull : ((1ull << bits) - 1ull);
     key_hash_kernel<<<nblk(n, 256), 256, 0, st>>>(n, (const fc_jrec*)a.recs.p, seed, kA, vA);
     FC_LAUNCH_CHECK(ctx);
-    rc = sort_pairs_u64_u32(ctx, n, kA, kB, vA, vB, 0, 64, st);
+    rc = sort_pairs_u64_u32(ctx, n, kA, kB, vA, vB, 0, bits, st);
     if (rc) return rc;
     gather_kernel<<<nblk(n, 256), 256, 0, st>>>(n, (const fc_jrec*)a.recs.p, vB, sorted);
     FC_LAUNCH_CHECK(ctx);
     FC_CUDA(ctx, cudaMemsetAsync(counters + 1, 0, sizeof(unsigned long long), st));
-    heads_kernel<<<nblk(n, 256), 256, 0, st>>>(n, sorted, kB, head, counters + 1);
+    heads_kernel<<<nblk(n, 256), 256, 0, st>>>(n, sorted, kB, hmask, head, counters + 1);
     FC_LAUNCH_CHECK(ctx);
     unsigned long long coll = 0;
     FC_CUDA(ctx, cudaMemcpyAsync(&coll, counters + 1, sizeof(coll), cudaMemcpyDeviceToHost, st));
@@ -574,20 +627,15 @@ extern "C" int64_t fc_agg_finalize(fc_ctx* ctx, void* stream) {
   reduce_kernel<<<nblk(n, 256), 256, 0, st>>>(n, sorted, seg_incl, head, acc);
   FC_LAUNCH_CHECK(ctx);
 
-  // distinct read sequences / fragment names per junction: sort (hash) then stable sort (segment)
-  int seg_bits = 1;
-  while ((1ll << seg_bits) < nj) seg_bits++;
-  for (int which = 0; which < 2; ++which) {
-    // kA = read hashes, kB = qname hashes, vA = segment ids
-    split_hash_kernel<<<nblk(n, 256), 256, 0, st>>>(n, sorted, seg_incl, kA, kB, vA);
-    FC_LAUNCH_CHECK(ctx);
-    uint64_t* hin = which == 0 ? kA : kB;
-    uint64_t* hout = which == 0 ? kB : kA;
-    rc = sort_pairs_u64_u32(ctx, n, hin, hout, vA, vB, 0, 64, st);
-    if (rc) return rc;
-    rc = sort_pairs_u32_u64(ctx, n, vB, vA, hout, hin, 0, seg_bits, st);
-    if (rc) return rc;
-    distinct_kernel<<<nblk(n, 256), 256, 0, st>>>(n, vA, hin, which, acc);
+  // distinct read sequences / fragment names per junction: two exact hash sets of (value, junction) pairs
+  {
+    unsigned long long cap = 1024;
+    while (cap < 2ull * (unsigned long long)n) cap <<= 1;
+    for (int k = 0; k < 2; ++k) {
+      FC_CUDA(ctx, a.htab[k].reserve((size_t)cap * 16, st, false, 0));
+      FC_CUDA(ctx, cudaMemsetAsync(a.htab[k].p, 0, (size_t)cap * 16, st));
+    }
+    distinct_hash_kernel<<<nblk(n, 256), 256, 0, st>>>(n, sorted, seg_incl, (U128*)a.htab[0].p, (U128*)a.htab[1].p, cap - 1, acc);
     FC_LAUNCH_CHECK(ctx);
   }
 
@@ -626,4 +674,5 @@ void fc_agg_release(fc_ctx* ctx) {
   for (auto& s : a.scratch) s.release();
   a.cub_tmp.release();
   a.counters.release();
+  for (auto& h : a.htab) h.release();
 }

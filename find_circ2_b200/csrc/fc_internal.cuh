@@ -62,6 +62,7 @@ struct fc_agg {
   fc_dbuf scratch[8];
   fc_dbuf cub_tmp;
   fc_dbuf counters;     // small device counters
+  fc_dbuf htab[2];      // hash sets for the distinct counts (reads, fragment names)
 };
 
 struct fc_ctx {
