@@ -440,6 +440,7 @@ extern "C" int fc_agg_reset(fc_ctx* ctx) {
   if (!ctx) return FC_E_ARG;
   ctx->agg.n_recs = 0;
   ctx->agg.n_junc = -1;
+  ctx->agg.max_idx = 0;
   if (ctx->agg.counters.p) FC_CUDA(ctx, cudaMemset(ctx->agg.counters.p, 0, 64 * sizeof(unsigned long long)));
   return FC_OK;
 }
@@ -474,6 +475,7 @@ extern "C" int fc_agg_emit(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, const i
   FC_LAUNCH_CHECK(ctx);
   a.n_recs = ub;  // upper bound until the next sync
   a.n_junc = -1;
+  if (a.max_idx != ~0ull && idx_base + (uint64_t)n > a.max_idx) a.max_idx = idx_base + (uint64_t)n;
   return FC_OK;
 }
 
@@ -489,6 +491,7 @@ extern "C" int fc_agg_append(fc_ctx* ctx, int64_t n, const fc_jrec* d_recs, void
   FC_CUDA(ctx, a.recs.reserve((size_t)(a.n_recs + n) * sizeof(fc_jrec), st, true, (size_t)a.n_recs * sizeof(fc_jrec)));
   FC_CUDA(ctx, cudaMemcpyAsync((fc_jrec*)a.recs.p + a.n_recs, d_recs, (size_t)n * sizeof(fc_jrec), cudaMemcpyDefault, st));
   a.n_recs += n;
+  a.max_idx = ~0ull;  // records built elsewhere: their idx range is unknown
   unsigned long long v = (unsigned long long)a.n_recs;
   FC_CUDA(ctx, cudaMemcpyAsync(a.counters.p, &v, sizeof(v), cudaMemcpyHostToDevice, st));
   FC_CUDA(ctx, cudaStreamSynchronize(st));
@@ -589,6 +592,7 @@ extern "C" int64_t fc_agg_finalize(fc_ctx* ctx, void* stream) {
 
   uint64_t seed = 0x9E3779B97F4A7C15ULL;
   bool ok = false;
+  uint32_t nj32 = 0;
   // sort only as many hash bits as make a collision between two different keys unlikely (~2^-7); the run check
   // below detects one, and the retries use all 64 bits
   int lg = 1;
@@ -606,18 +610,16 @@ extern "C" int64_t fc_agg_finalize(fc_ctx* ctx, void* stream) {
     FC_CUDA(ctx, cudaMemsetAsync(counters + 1, 0, sizeof(unsigned long long), st));
     heads_kernel<<<nblk(n, 256), 256, 0, st>>>(n, sorted, kB, hmask, head, counters + 1);
     FC_LAUNCH_CHECK(ctx);
+    // segment ids; the collision count and the number of junctions come back with ONE synchronisation
+    rc = scan_u32(ctx, n, head, seg_incl, true, st);
+    if (rc) return rc;
     unsigned long long coll = 0;
     FC_CUDA(ctx, cudaMemcpyAsync(&coll, counters + 1, sizeof(coll), cudaMemcpyDeviceToHost, st));
+    FC_CUDA(ctx, cudaMemcpyAsync(&nj32, seg_incl + (n - 1), 4, cudaMemcpyDeviceToHost, st));
     FC_CUDA(ctx, cudaStreamSynchronize(st));
     ok = coll == 0;
   }
   if (!ok) return fc_fail(ctx, FC_E_COLLISION, "junction key hash collisions survived 4 seeds");
-
-  rc = scan_u32(ctx, n, head, seg_incl, true, st);
-  if (rc) return rc;
-  uint32_t nj32 = 0;
-  FC_CUDA(ctx, cudaMemcpyAsync(&nj32, seg_incl + (n - 1), 4, cudaMemcpyDeviceToHost, st));
-  FC_CUDA(ctx, cudaStreamSynchronize(st));
   const int64_t nj = nj32;
 
   FC_CUDA(ctx, a.scratch[7].reserve((size_t)nj * sizeof(JAcc), st, false, 0));
@@ -645,7 +647,12 @@ extern "C" int64_t fc_agg_finalize(fc_ctx* ctx, void* stream) {
   fc_junction* tmpj = (fc_junction*)a.scratch[5].p;
   finish_kernel<<<nblk(nj, 128), 128, 0, st>>>(nj, n, acc, sorted, tmpj, kA, vA);
   FC_LAUNCH_CHECK(ctx);
-  rc = sort_pairs_u64_u32(ctx, nj, kA, kB, vA, vB, 0, 64, st);
+  int order_bits = 64;
+  if (a.max_idx != ~0ull) {
+    order_bits = 1;
+    while (order_bits < 64 && (a.max_idx >> order_bits)) order_bits++;
+  }
+  rc = sort_pairs_u64_u32(ctx, nj, kA, kB, vA, vB, 0, order_bits, st);
   if (rc) return rc;
   gather_junctions_kernel<<<nblk(nj, 256), 256, 0, st>>>(nj, tmpj, vB, (fc_junction*)a.junctions.p);
   FC_LAUNCH_CHECK(ctx);

@@ -37,11 +37,8 @@ struct fc_genome {
     v.n_chrom = (int32_t)names.size();
     v.pad = FC_GENOME_PAD;
     v.tiles = d_tiles;
-    v.tile_magic = tile_magic;
     v.tile_T = d_tiles ? tile_T : 0;
-    v.tile_S = tile_S;
     v.tile_W = d_tiles ? tile_W : 0;
-    v.reserved = 0;
     return v;
   }
 };
@@ -59,6 +56,7 @@ struct fc_agg {
   int64_t n_recs = 0;
   fc_dbuf junctions;    // fc_junction[n_junc]
   int64_t n_junc = -1;  // -1: not finalized
+  uint64_t max_idx = 0; // upper bound of fc_jrec.idx seen so far (~0: unknown)
   fc_dbuf scratch[8];
   fc_dbuf cub_tmp;
   fc_dbuf counters;     // small device counters

@@ -434,10 +434,9 @@ int fc_genome_ensure_tiles(fc_ctx* ctx, int w, cudaStream_t st) {
   if (w < 8) w = 8;
   if (w > 256) w = 256;
   if (g.d_tiles && w <= g.tile_W) return FC_OK;
-  w = (w + 3) / 4 * 4;  // a little head-room so that slightly longer reads do not trigger a rebuild
-  int T, P, S;
-  fc::tile_geometry(w, T, P, S);
-  if (S < 2) return fc_fail(ctx, FC_E_ARG, "tile stride too small for window %d", w);
+  int T, P, cap;
+  fc::tile_geometry(w, T, P, cap);
+  const int S = fc::TILE_STRIDE;
   int64_t n_tiles = g.total / S + 2;
   size_t bytes = (size_t)n_tiles * 32 * T + 256;
   if (g.d_tiles) {
@@ -454,8 +453,7 @@ int fc_genome_ensure_tiles(fc_ctx* ctx, int w, cudaStream_t st) {
   FC_LAUNCH_CHECK(ctx);
   g.tile_T = T;
   g.tile_S = S;
-  g.tile_W = w;
-  g.tile_magic = (~0ull) / (uint64_t)S + 1ull;
+  g.tile_W = cap;
   g.tile_bytes = (int64_t)bytes;
   g.dev_bytes += g.tile_bytes;
   return FC_OK;

@@ -2,6 +2,8 @@
 // host-buffer convenience entry (H2D + pack + scan + D2H).
 //
 // Replaces JunctionSpan.find_breakpoints (/root/reference/find_circ.py:854-974); see scan_core.cuh.
+#include <stdlib.h>
+
 #include "fc_internal.cuh"
 
 namespace {
@@ -40,8 +42,8 @@ __global__ void pack_reads_kernel(int64_t n, const uint8_t* __restrict__ ascii, 
 }
 
 // ---------------------------------------------------------------- the scan
-template <int NP, int T>
-__global__ void __launch_bounds__(256) scan_kernel(fc::GenomeView g, fc::ScanCfg cfg, fc::ReadView rv,
+template <int NP, int T, int BS, int MB>
+__global__ void __launch_bounds__(BS, MB) scan_kernel(fc::GenomeView g, fc::ScanCfg cfg, fc::ReadView rv,
                                                    const int32_t* __restrict__ chrom,
                                                    const int32_t* __restrict__ a_start,
                                                    const int32_t* __restrict__ b_end, const int32_t* __restrict__ l,
@@ -155,25 +157,27 @@ extern "C" int fc_scan(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs* pr,
   fc::ScanCfg cfg{p->margin, p->maxdist, p->noncanonical, p->strandpref};
   fc::GenomeView g = ctx->genome.view();
   fc::ReadView rv{pr->d_rlo, pr->d_rhi, pr->d_rn, pr->n, pr->n_words};
-  const int threads = 256;
-  // grid: whole waves of resident CTAs (148 SMs x 8 CTAs of 256 threads), grid-stride beyond that
-  int64_t want = (pr->n + threads - 1) / threads;
-  int64_t wave = (int64_t)ctx->sm_count * 8;
-  int64_t blocks = want <= wave ? want : ((want + wave - 1) / wave) * wave;
-  if (blocks > wave * 64) blocks = wave * 64;
-#define FC_SCAN_LAUNCH(NP, T)                                                                                          \
-  scan_kernel<NP, T><<<(unsigned)blocks, threads, 0, st>>>(g, cfg, rv, pr->d_chrom, pr->d_a_start, pr->d_b_end, pr->d_l, \
-                                                           pr->d_flags, d_out)
+#define FC_SCAN_LAUNCH_BS(NP, T, BS, MB)                                                                               \
+  scan_kernel<NP, T, BS, MB><<<(unsigned)((pr->n + BS - 1) / BS), BS, 0, st>>>(g, cfg, rv, pr->d_chrom, pr->d_a_start,   \
+                                                                               pr->d_b_end, pr->d_l, pr->d_flags, d_out)
+  // 256-thread CTAs, 48 registers -> 5 CTAs (40 warps) per SM.  Measured alternatives on B200 (round 1): 128- and
+  // 192-thread CTAs, register caps 32/40/58, and a persistent software-pipelined variant with L2 prefetch of the next
+  // pair's tiles were all equal or slower.
+#define FC_SCAN_LAUNCH(NP, T) FC_SCAN_LAUNCH_BS(NP, T, 256, 5);
   // the kernel specialisation follows the tile geometry of the store (scan_core.cuh: tile_geometry)
   switch (g.tile_T) {
     case 1:
-      if (need <= 64) FC_SCAN_LAUNCH(2, 1);
-      else FC_SCAN_LAUNCH(3, 1);
+      if (need <= 64) FC_SCAN_LAUNCH(2, 1)
+      else FC_SCAN_LAUNCH(3, 1)
       break;
-    case 2: FC_SCAN_LAUNCH(4, 2); break;
-    case 4: FC_SCAN_LAUNCH(8, 4); break;
-    default: FC_SCAN_LAUNCH(8, 0); break;  // no tile store (--non-canonical): master planes / per-base path
+    case 2:
+      if (need <= 128) FC_SCAN_LAUNCH(4, 2)
+      else FC_SCAN_LAUNCH(8, 2)
+      break;
+    case 4: FC_SCAN_LAUNCH(8, 4) break;
+    default: FC_SCAN_LAUNCH(8, 0) break;  // no tile store (--non-canonical): master planes / per-base path
   }
+#undef FC_SCAN_LAUNCH_BS
 #undef FC_SCAN_LAUNCH
   FC_LAUNCH_CHECK(ctx);
   return FC_OK;

@@ -12,7 +12,7 @@
 //
 // B200 formulation -- one thread per pair, everything in registers, 1 bit per base and plane:
 //   * the genome is held as bit planes (lo / hi bit of the 2-bit code, plus an N plane).  For the scan the planes
-//     are re-cut into overlapping 32*T-byte TILES (stride chosen so that every window lies inside one tile), the
+//     are re-cut into overlapping 32*T-byte TILES starting every 32 bases (every window lies inside one tile), the
 //     lo and hi plane of a tile sit in the same sector(s) and 4 spare bits flag "tile contains N": one 256-bit
 //     load per sector fetches a whole window including its N summary -- two gathers per pair when T = 1;
 //   * mismatch flags of 32 bases cost two XORs and an OR; dist(x) = popc(mA below x) + popc(mB at/above x);
@@ -44,11 +44,8 @@ struct GenomeView {
   int32_t pad;  // bases of N padding on both sides of every chromosome
   // tile store (may be absent: tile_T == 0)
   const uint32_t* tiles;   // tile t: 4T words lo plane (top 4 bits of the last word = flags), then 4T words hi plane
-  uint64_t tile_magic;     // ceil(2^64 / tile_S)
   int32_t tile_T;          // sectors per tile (1, 2 or 4)
-  int32_t tile_S;          // stride in bases between tile starts
   int32_t tile_W;          // largest window (bases) guaranteed to fit in one tile
-  int32_t reserved;
 };
 
 struct ScanCfg {
@@ -265,13 +262,15 @@ FC_HD void load_plane(const uint32_t* plane, int64_t gp, uint32_t (&W)[NP + 1]) 
   W[NP] = 0;
 }
 
-// from the tile store: one 256-bit load per sector.  Returns the tile flags (TILE_FLAG_N).
+// from the tile store: one 256-bit load per sector.  Tiles start every 32 bases (tile t covers bases [32t, 32t+P)),
+// so the tile index is a shift and the window starts inside the tile's first word: no division, no word select.
+// Returns the tile flags (TILE_FLAG_N).
 template <int NP, int T>
 FC_HD uint32_t load_tile_window(const GenomeView& g, int64_t gp, Window<NP>& w) {
   constexpr int PW = 4 * T;  // words per plane in a tile
-  const uint64_t t = umul64hi((uint64_t)gp, g.tile_magic);
-  const int o = (int)((uint64_t)gp - t * (uint64_t)g.tile_S);  // offset of the window inside the tile
-  const uint32_t* base = g.tiles + t * (uint64_t)(8 * T);
+  static_assert(NP <= PW, "window does not fit the tile");
+  const uint32_t bo = (uint32_t)(gp & 31);
+  const uint32_t* base = g.tiles + (gp >> 5) * (int64_t)(8 * T);
   uint32_t s_lo[PW + 1], s_hi[PW + 1];
   if (T == 1) {
     uint32_t v[8];
@@ -297,23 +296,6 @@ FC_HD uint32_t load_tile_window(const GenomeView& g, int64_t gp, Window<NP>& w) 
   s_lo[PW - 1] &= 0x0FFFFFFFu;
   s_lo[PW] = 0;
   s_hi[PW] = 0;
-  // the window starts at word (o>>5), bit (o&31) of the tile planes
-  const int wo = o >> 5;
-  const uint32_t bo = (uint32_t)(o & 31);
-  // largest word offset that can occur: the offset is below the tile stride S = P - tile_W + 1 and tile_W is at
-  // least the smallest window this NP is launched for (32*(NP-1)+1; the NP=2 kernel also serves tiny windows)
-  constexpr int P_BASES = 128 * T - 4;
-  constexpr int MAXWO = (NP <= 2) ? (PW - 1) : (P_BASES - (32 * (NP - 1) + 1)) / 32;
-#pragma unroll
-  for (int step = 1; step <= MAXWO; step <<= 1) {
-    if (wo & step) {
-#pragma unroll
-      for (int k = 0; k <= PW; ++k) {
-        s_lo[k] = (k + step <= PW) ? s_lo[k + step] : 0u;
-        s_hi[k] = (k + step <= PW) ? s_hi[k + step] : 0u;
-      }
-    }
-  }
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
     w.lo[j] = funnel_r(s_lo[j], s_lo[j + 1], bo);
@@ -325,40 +307,37 @@ FC_HD uint32_t load_tile_window(const GenomeView& g, int64_t gp, Window<NP>& w) 
 }
 
 // ---------------------------------------------------------------- bit-parallel scan on loaded windows
-// NP words of 32 split positions; covers l + 2 <= 32*NP.  nA/nB are the N planes of the windows (all zero for the
-// common N-free pair: ONE code path for every lane of the warp -- a separate N variant would be executed in full by
-// every warp that holds a single N-touching pair); the read's N plane is consulted when read_n.
-template <int NP>
+// NP words of 32 split positions; covers l + 2 <= 32*NP.  WITH_N is chosen per WARP (any lane touching an N), so an
+// N-free warp runs the short variant and a warp with N runs the full one for all its lanes -- never both.  In the
+// full variant nA/nB are the N planes of the windows (all zero for the lanes without N).
+template <int NP, bool WITH_N>
 FC_HD void scan_planes(const ScanCfg& cfg, const Window<NP>& A, const Window<NP>& B, const uint32_t (&nA)[NP + 1],
                        const uint32_t (&nB)[NP + 1], int l, bool minus_span, const ReadView& rv, int64_t i,
                        bool read_n, Best& best) {
-  // splice signal at split position x (bit x&31 of word x>>5):
-  //   GT..AG: A[x]=G A[x+1]=T B[x]=A B[x+1]=G ;  CT..AC: A[x]=C A[x+1]=T B[x]=A B[x+1]=C     (find_circ.py:924-954)
-  //   codes A=00 C=01 G=10 T=11 (hi,lo); a signal never contains N
-  // the read planes are needed by almost every pair: issue the loads before the signal logic so that their latency
-  // overlaps it
+  // the read planes are needed by almost every pair: issue the loads before the signal logic
   uint32_t rlo[NP], rhi[NP], rnn[NP];
 #pragma unroll
   for (int k = 0; k < NP; ++k) {
     const bool have = k < rv.n_words;
     rlo[k] = have ? ldg32(rv.rlo + (int64_t)k * rv.n + i) : 0u;
     rhi[k] = have ? ldg32(rv.rhi + (int64_t)k * rv.n + i) : 0u;
-    rnn[k] = (read_n && have) ? ldg32(rv.rn + (int64_t)k * rv.n + i) : 0u;
+    rnn[k] = (WITH_N && read_n && have) ? ldg32(rv.rn + (int64_t)k * rv.n + i) : 0u;
   }
-  uint32_t sigP[NP], sigM[NP];
+  // splice signal at split position x (bit x&31 of word x>>5), codes A=00 C=01 G=10 T=11 (hi,lo):
+  //   GT..AG: A[x]=G A[x+1]=T B[x]=A B[x+1]=G ;  CT..AC: A[x]=C A[x+1]=T B[x]=A B[x+1]=C     (find_circ.py:924-954)
+  //   <=> A[x+1]==T, B[x]==A, A[x]==B[x+1], A[x] in {C,G};  '-' strand iff A[x]==C (lo bit set); never contains N
+  uint32_t sig[NP];
   uint32_t any = 0;
 #pragma unroll
   for (int k = 0; k < NP; ++k) {
-    uint32_t a1lo = funnel_r(A.lo[k], A.lo[k + 1], 1), a1hi = funnel_r(A.hi[k], A.hi[k + 1], 1);
-    uint32_t b1lo = funnel_r(B.lo[k], B.lo[k + 1], 1), b1hi = funnel_r(B.hi[k], B.hi[k + 1], 1);
-    uint32_t common = (a1hi & a1lo) & ~(B.hi[k] | B.lo[k]);                 // A[x+1]==T and B[x]==A
-    uint32_t gg = (A.hi[k] & ~A.lo[k]) & (b1hi & ~b1lo);                    // A[x]==G and B[x+1]==G
-    uint32_t cc = (~A.hi[k] & A.lo[k]) & (~b1hi & b1lo);                    // A[x]==C and B[x+1]==C
-    uint32_t nn = nA[k] | funnel_r(nA[k], nA[k + 1], 1) | nB[k] | funnel_r(nB[k], nB[k + 1], 1);
-    uint32_t vm = low_mask(imin(imax(l + 1 - 32 * k, 0), 32)) & ~nn;
-    sigP[k] = common & gg & vm;
-    sigM[k] = common & cc & vm;
-    any |= sigP[k] | sigM[k];
+    const uint32_t a1lo = funnel_r(A.lo[k], A.lo[k + 1], 1), a1hi = funnel_r(A.hi[k], A.hi[k + 1], 1);
+    const uint32_t b1lo = funnel_r(B.lo[k], B.lo[k + 1], 1), b1hi = funnel_r(B.hi[k], B.hi[k + 1], 1);
+    uint32_t v = (a1hi & a1lo) & ~(B.hi[k] | B.lo[k]);
+    v &= (A.hi[k] ^ A.lo[k]) & ~(A.hi[k] ^ b1hi) & ~(A.lo[k] ^ b1lo);
+    v &= low_mask(imin(imax(l + 1 - 32 * k, 0), 32));
+    if (WITH_N) v &= ~(nA[k] | funnel_r(nA[k], nA[k + 1], 1) | nB[k] | funnel_r(nB[k], nB[k + 1], 1));
+    sig[k] = v;
+    any |= v;
   }
   if (!any) return;  // no split position carries a canonical signal (most decoy pairs end here)
 
@@ -371,10 +350,14 @@ FC_HD void scan_planes(const ScanCfg& cfg, const Window<NP>& A, const Window<NP>
   cumB[0] = 0;
 #pragma unroll
   for (int k = 0; k < NP; ++k) {
-    uint32_t b2lo = funnel_r(B.lo[k], B.lo[k + 1], 2), b2hi = funnel_r(B.hi[k], B.hi[k + 1], 2);
-    uint32_t fa = (A.lo[k] ^ rlo[k]) | (A.hi[k] ^ rhi[k]) | (nA[k] ^ rnn[k]);
-    uint32_t fb = (b2lo ^ rlo[k]) | (b2hi ^ rhi[k]) | (funnel_r(nB[k], nB[k + 1], 2) ^ rnn[k]);
-    uint32_t vm = low_mask(imin(imax(l - 32 * k, 0), 32));
+    const uint32_t b2lo = funnel_r(B.lo[k], B.lo[k + 1], 2), b2hi = funnel_r(B.hi[k], B.hi[k + 1], 2);
+    uint32_t fa = (A.lo[k] ^ rlo[k]) | (A.hi[k] ^ rhi[k]);
+    uint32_t fb = (b2lo ^ rlo[k]) | (b2hi ^ rhi[k]);
+    if (WITH_N) {
+      fa |= nA[k] ^ rnn[k];
+      fb |= funnel_r(nB[k], nB[k + 1], 2) ^ rnn[k];
+    }
+    const uint32_t vm = low_mask(imin(imax(l - 32 * k, 0), 32));
     mA[k] = fa & vm;
     mB[k] = fb & vm;
     cumA[k + 1] = cumA[k] + popc32(mA[k]);
@@ -384,27 +367,26 @@ FC_HD void scan_planes(const ScanCfg& cfg, const Window<NP>& A, const Window<NP>
 
   // candidates: signal positions of the words that can still reach dist <= maxdist (a split inside word k has at
   // least cumA[k] donor-side and totalB - cumB[k+1] acceptor-side mismatches)
-  uint32_t c[NP];
   any = 0;
 #pragma unroll
   for (int k = 0; k < NP; ++k) {
     const bool feasible = cumA[k] <= cfg.maxdist && totalB - cumB[k + 1] <= cfg.maxdist;
-    c[k] = feasible ? (sigP[k] | sigM[k]) : 0u;
-    any |= c[k];
+    sig[k] = feasible ? sig[k] : 0u;
+    any |= sig[k];
   }
   // ONE loop over all words (ascending x), so that the lanes of a warp walk their candidates together
   while (any) {
     int k = 0;
-    uint32_t cw = 0, ma = 0, mb = 0, sm = 0;
+    uint32_t cw = 0, ma = 0, mb = 0, alo = 0;
     int ca = 0, cb = 0;
 #pragma unroll
     for (int q = NP - 1; q >= 0; --q) {
-      if (c[q]) {
+      if (sig[q]) {
         k = q;
-        cw = c[q];
+        cw = sig[q];
         ma = mA[q];
         mb = mB[q];
-        sm = sigM[q];
+        alo = A.lo[q];
         ca = cumA[q];
         cb = cumB[q];
       }
@@ -414,14 +396,14 @@ FC_HD void scan_planes(const ScanCfg& cfg, const Window<NP>& A, const Window<NP>
     any = 0;
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
-      if (q == k) c[q] = rest;
-      any |= c[q];
+      if (q == k) sig[q] = rest;
+      any |= sig[q];
     }
     const uint32_t below = (1u << bit) - 1u;
     const int dist = ca + popc32(ma & below) + (totalB - cb - popc32(mb & below));
     if (dist <= cfg.maxdist) {
       const int x = 32 * k + bit;
-      const uint32_t strand = (sm >> bit) & 1u;
+      const uint32_t strand = (alo >> bit) & 1u;  // A[x]==C -> CT..AC -> '-'
       const int ov = anchor_overlap(x, l, cfg.margin);
       int s = 20 - 10 * dist - ov;
       if (cfg.strandpref && ((strand != 0u) == minus_span)) s += 100;
@@ -436,6 +418,14 @@ struct PairArgs {
   uint32_t flags;  // FC_PF_*
 };
 
+FC_HD bool warp_any(bool p) {
+#if defined(__CUDA_ARCH__)
+  return __any_sync(__activemask(), p);
+#else
+  return p;
+#endif
+}
+
 // NP: 32-base words per window held in registers; T: sectors per tile of the tile store (0: no tile store)
 template <int NP, int T, class Emit>
 FC_HD void scan_pair(const GenomeView& g, const ScanCfg& cfg, const PairArgs& p, const ReadView& rv, int64_t i,
@@ -445,49 +435,63 @@ FC_HD void scan_pair(const GenomeView& g, const ScanCfg& cfg, const PairArgs& p,
   const bool backsplice = p.flags & 1u, minus_span = p.flags & 2u, read_n = p.flags & 4u;
   const int l = p.l;
   uint32_t extra = 0;
-  if (l >= 0 && p.chrom >= 0 && p.chrom < g.n_chrom) {
+  bool fast = false;
+  int64_t ga = 0, gb = 0;
+  if (l >= 0 && p.chrom >= 0 && p.chrom < g.n_chrom && l + 2 <= g.pad) {
     const int64_t size = g.chrom_size[p.chrom];
-    const int64_t wa0 = p.a_start, wa1 = (int64_t)p.a_start + l + 2;
-    const int64_t wb1 = p.b_end, wb0 = (int64_t)p.b_end - (l + 2);
-    // windows must touch the chromosome (find_circ.py:194-211 pads the overhang with N; a window entirely outside
-    // is undefined there) and the overhang must fit in the padding
-    const bool ok = wa0 <= size && wa1 >= 0 && wb0 <= size && wb1 >= 0 && wa0 >= -(int64_t)g.pad &&
-                    wa1 <= size + g.pad && wb0 >= -(int64_t)g.pad && wb1 <= size + g.pad;
+    const int w = l + 2;
+    // both windows must touch the chromosome (find_circ.py:194-211 pads the overhang with N; a window entirely
+    // outside is undefined there): -w <= a_start <= size  and  0 <= b_end <= size + w   (w <= pad keeps the overhang
+    // inside the N padding)
+    const bool ok = (uint64_t)((int64_t)p.a_start + w) <= (uint64_t)(size + w) && (uint64_t)(int64_t)p.b_end <= (uint64_t)(size + w);
     if (ok) {
       const int64_t off = g.chrom_off[p.chrom];
-      const int64_t ga = off + wa0, gb = off + wb0;
-      if (force_per_base || cfg.noncanonical || (l + 2 > 32 * NP)) {
+      ga = off + p.a_start;
+      gb = off + (int64_t)p.b_end - w;
+      if (force_per_base || cfg.noncanonical || (w > 32 * NP)) {
         extra |= W3_SLOW;
         scan_per_base(g, cfg, ga, gb, l, minus_span, rv, i, read_n, best, emit);
       } else {
-        Window<NP> A, B;
-        uint32_t nA[NP + 1], nB[NP + 1];
-        bool with_n = read_n;
-        if (T > 0 && l + 2 <= g.tile_W) {
-          constexpr int TT = T > 0 ? T : 1;
-          uint32_t fl = load_tile_window<NP, TT>(g, ga, A) | load_tile_window<NP, TT>(g, gb, B);
-          with_n = with_n || (fl & TILE_FLAG_N);
-        } else {
-          load_plane<NP>(g.plo, ga, A.lo);
-          load_plane<NP>(g.phi, ga, A.hi);
-          load_plane<NP>(g.plo, gb, B.lo);
-          load_plane<NP>(g.phi, gb, B.hi);
-          with_n = true;  // no summary without tiles: always consult the N plane
-        }
-        if (with_n) {
-          load_plane<NP>(g.pn, ga, nA);
-          load_plane<NP>(g.pn, gb, nB);
-        } else {
-#pragma unroll
-          for (int k = 0; k <= NP; ++k) nA[k] = nB[k] = 0u;
-        }
-        scan_planes<NP>(cfg, A, B, nA, nB, l, minus_span, rv, i, read_n, best);
+        fast = true;
       }
     } else {
       extra |= W3_RANGE;
     }
   } else if (l >= 0) {
     extra |= W3_RANGE;
+  }
+  if (fast) {
+    Window<NP> A, B;
+    uint32_t nA[NP + 1], nB[NP + 1];
+    bool with_n = read_n;
+    bool tiled = false;
+    if constexpr (T > 0) {
+      if (l + 2 <= g.tile_W) {
+        const uint32_t fl = load_tile_window<NP, T>(g, ga, A) | load_tile_window<NP, T>(g, gb, B);
+        with_n = with_n || (fl & TILE_FLAG_N);
+        tiled = true;
+      }
+    }
+    if (!tiled) {
+      load_plane<NP>(g.plo, ga, A.lo);
+      load_plane<NP>(g.phi, ga, A.hi);
+      load_plane<NP>(g.plo, gb, B.lo);
+      load_plane<NP>(g.phi, gb, B.hi);
+      with_n = true;  // no summary without tiles: always consult the N plane
+    }
+    // one variant per warp (the lanes that reached this point): the N-aware one only if some lane needs it
+    if (warp_any(with_n)) {
+      if (with_n) {
+        load_plane<NP>(g.pn, ga, nA);
+        load_plane<NP>(g.pn, gb, nB);
+      } else {
+#pragma unroll
+        for (int k = 0; k <= NP; ++k) nA[k] = nB[k] = 0u;
+      }
+      scan_planes<NP, true>(cfg, A, B, nA, nB, l, minus_span, rv, i, read_n, best);
+    } else {
+      scan_planes<NP, false>(cfg, A, B, nA, nB, l, minus_span, rv, i, false, best);
+    }
   }
   finish(best, p.a_start, p.b_end, l, backsplice, extra, out);
 }
@@ -512,11 +516,14 @@ FC_HD void pack32(const uint8_t* src, int count, uint32_t& lo, uint32_t& hi, uin
   nn = c;
 }
 
-// tile geometry for windows of up to `w` bases: T sectors per tile, P payload bases, S stride
-FC_HD void tile_geometry(int w, int& T, int& P, int& S) {
-  T = w <= 96 ? 1 : (w <= 128 ? 2 : 4);
+// tile geometry for windows of up to `w` bases: T sectors per tile, P payload bases; tiles start every TILE_STRIDE
+// bases, so a window starting anywhere fits when w <= P - (TILE_STRIDE - 1)
+constexpr int TILE_STRIDE = 32;
+FC_HD void tile_geometry(int w, int& T, int& P, int& cap) {
+  T = w <= 93 ? 1 : (w <= 221 ? 2 : 4);
   P = 128 * T - 4;
-  S = P - w + 1;
+  cap = P - (TILE_STRIDE - 1);
+  if (cap > 256) cap = 256;
 }
 
 }  // namespace fc

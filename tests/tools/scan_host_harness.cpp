@@ -75,9 +75,9 @@ void hh_build_tiles(void* h, int w) {
   HostGenome* g = static_cast<HostGenome*>(h);
   if (w < 8) w = 8;
   if (w > 256) w = 256;
-  w = (w + 3) / 4 * 4;
-  int T, P, S;
-  fc::tile_geometry(w, T, P, S);
+  int T, P, cap;
+  fc::tile_geometry(w, T, P, cap);
+  const int S = fc::TILE_STRIDE;
   int64_t n_tiles = g->total / S + 2;
   g->tiles.assign((size_t)n_tiles * 8 * T + 64, 0u);
   const int PW = 4 * T;
@@ -100,8 +100,7 @@ void hh_build_tiles(void* h, int w) {
   }
   g->T = T;
   g->S = S;
-  g->W = w;
-  g->magic = (~0ull) / (uint64_t)S + 1ull;
+  g->W = cap;
 }
 
 void hh_genome_free(void* h) { delete static_cast<HostGenome*>(h); }
@@ -140,11 +139,8 @@ int hh_scan(void* h, int margin, int maxdist, int noncanonical, int strandpref, 
   gv.pad = (int32_t)PAD;
   const bool use_tiles = mode == 0 && !noncanonical && !g->tiles.empty();
   gv.tiles = use_tiles ? g->tiles.data() : nullptr;
-  gv.tile_magic = g->magic;
   gv.tile_T = use_tiles ? g->T : 0;
-  gv.tile_S = g->S;
   gv.tile_W = use_tiles ? g->W : 0;
-  gv.reserved = 0;
   fc::ScanCfg cfg{margin, maxdist, noncanonical, strandpref};
   fc::ReadView rv{rlo, rhi, rn, n, n_words};
   const int need = max_l + 2;
@@ -154,7 +150,10 @@ int hh_scan(void* h, int margin, int maxdist, int noncanonical, int strandpref, 
       if (need <= 64) run<2, 1>(gv, cfg, rv, chrom, a_start, b_end, l, flags, out, force);
       else run<3, 1>(gv, cfg, rv, chrom, a_start, b_end, l, flags, out, force);
       break;
-    case 2: run<4, 2>(gv, cfg, rv, chrom, a_start, b_end, l, flags, out, force); break;
+    case 2:
+      if (need <= 128) run<4, 2>(gv, cfg, rv, chrom, a_start, b_end, l, flags, out, force);
+      else run<8, 2>(gv, cfg, rv, chrom, a_start, b_end, l, flags, out, force);
+      break;
     case 4: run<8, 4>(gv, cfg, rv, chrom, a_start, b_end, l, flags, out, force); break;
     default: run<8, 0>(gv, cfg, rv, chrom, a_start, b_end, l, flags, out, force); break;
   }
