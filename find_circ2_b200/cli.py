@@ -116,8 +116,107 @@ def run_to_strings(opt: Options, path=None, engine=None):
     return out
 
 
+V12_ONLY = ("-p", "--prefix", "-s", "--stats", "-R", "--reads", "-w", "--wiggle", "-r", "--reads2samples", "--format=1.2")
+
+
+def wants_v12(argv) -> bool:
+    """the two generations of the command line share `-q` with different meanings (README.md:303 vs find_circ.py:390);
+    the v1.2 face is selected by any option only it has, or by --format=1.2"""
+    for a in argv:
+        head = a.split("=")[0]
+        if a in V12_ONLY or head in V12_ONLY:
+            return True
+    return False
+
+
+def build_parser_v12() -> optparse.OptionParser:
+    """README.md:283-337"""
+    p = optparse.OptionParser(usage="\n  bowtie2 [mapping options] anchors.fastq.gz | %prog [options] > candidates.bed\n")
+    a = p.add_option
+    a("-v", "--version", dest="version", action="store_true", default=False)
+    a("-G", "--genome", dest="genome", type=str, default="")
+    a("-n", "--name", dest="name", default="unknown")
+    a("-p", "--prefix", dest="prefix", default="")
+    a("-q", "--min_uniq_qual", dest="min_uniq_qual", type=int, default=2)
+    a("-a", "--anchor", dest="asize", type=int, default=20)
+    a("-m", "--margin", dest="margin", type=int, default=2)
+    a("-d", "--maxdist", dest="maxdist", type=int, default=2)
+    a("-w", "--wiggle", dest="wiggle", type=int, default=2)
+    a("", "--noncanonical", dest="noncanonical", default=False, action="store_true")
+    a("", "--allhits", dest="allhits", default=False, action="store_true")
+    a("", "--halfunique", "--halfuniq", dest="halfunique", default=False, action="store_true")
+    a("", "--report_nobridges", "--report_nobridge", dest="report_nobridges", default=False, action="store_true")
+    a("-R", "--reads", dest="reads", default=None)
+    a("-s", "--stats", dest="stats", default="runstats.log")
+    a("", "--format", dest="format", default="1.2")
+    a("", "--batch-pairs", dest="batch_pairs", type=int, default=1 << 18)
+    a("", "--device", dest="device", type=int, default=0)
+    for unsupported in ("--randomize", "--stranded", "--strandpref"):
+        a("", unsupported, dest=unsupported.strip("-"), default=False, action="store_true")
+    a("-B", "--bam", dest="bam", default=None)
+    a("-r", "--reads2samples", dest="reads2samples", default="")
+    a("-S", "--system", dest="system", default="")
+    return p
+
+
+def run_v12_to_strings(opt, path=None, engine=None):
+    from .v12 import RunV12
+
+    names, lengths, records = samio.open_alignments(path)
+    run = RunV12(opt, names, engine)
+    try:
+        run.process(records)
+        run.finalize()
+        bed, reads, stats = run.bed_and_reads()
+    finally:
+        run.close()
+    return {"bed": bed, "reads": reads, "stats": stats, "n_pairs_scanned": run.n_pairs_scanned}
+
+
+def parse_args_v12(argv):
+    from .v12 import OptionsV12
+
+    o, args = build_parser_v12().parse_args(list(argv))
+    for bad in ("randomize", "stranded", "strandpref"):
+        if getattr(o, bad):
+            raise SystemExit("option --%s is not supported by this build" % bad)
+    if o.bam or o.reads2samples or o.system:
+        raise SystemExit("-B, -r and -S are not supported by this build")
+    opt = OptionsV12(genome=o.genome, name=o.name, prefix=o.prefix, min_uniq_qual=o.min_uniq_qual, asize=o.asize,
+                     margin=o.margin, maxdist=o.maxdist, wiggle=o.wiggle, noncanonical=o.noncanonical, allhits=o.allhits,
+                     halfunique=o.halfunique, report_nobridges=o.report_nobridges, reads=o.reads, stats=o.stats,
+                     batch_pairs=o.batch_pairs, device=o.device)
+    return opt, args, o
+
+
+def main_v12(argv) -> int:
+    opt, args, raw = parse_args_v12(argv)
+    if raw.version:
+        print("find_circ.py version %s (v1.2 command line)" % VERSION)
+        return 0
+    if not opt.genome:
+        print("need to specify either model system database (-S) or genome FASTA file (-G).")
+        return 1
+    try:
+        out = run_v12_to_strings(opt, args[0] if args else None)
+    except Exception:
+        sys.stderr.write(traceback.format_exc())
+        return 1
+    sys.stdout.write(out["bed"])
+    if opt.reads:
+        with open(opt.reads, "w") as fh:
+            fh.write(out["reads"])
+    else:
+        sys.stderr.write(out["reads"])
+    with open(opt.stats, "w") as fh:
+        fh.write(out["stats"])
+    return 0
+
+
 def main(argv=None) -> int:
     argv = sys.argv[1:] if argv is None else argv
+    if wants_v12(argv):
+        return main_v12(argv)
     opt, args, raw = parse_args(argv)
     if raw.version:
         print("find_circ.py version %s (B200-native breakpoint scan + junction merge)" % VERSION)

@@ -217,8 +217,10 @@ FC_HD void scan_per_base(const GenomeView& g, const ScanCfg& cfg, int64_t ga, in
       int base = -10 * dist - ov;
       bool is_gtag = sig == SIG_GTAG, is_ctac = rc == SIG_GTAG;
       if (cfg.noncanonical) {
-        int sp = base + (is_gtag ? 20 : 0) + ((cfg.strandpref && !minus_span) ? 100 : 0);
-        int sm = base + (is_ctac ? 20 : 0) + ((cfg.strandpref && minus_span) ? 100 : 0);
+        // noncanonical == 2: the v1.2 ranking (edits, then anchor overlap; README.md:301-312) without the canonical bonus
+        const int bonus = cfg.noncanonical == 2 ? 0 : 20;
+        int sp = base + (is_gtag ? bonus : 0) + ((cfg.strandpref && !minus_span) ? 100 : 0);
+        int sm = base + (is_ctac ? bonus : 0) + ((cfg.strandpref && minus_span) ? 100 : 0);
         best.offer(sp, x, 0u, sig, dist, ov);
         emit(sp, x, 0u, sig, dist, ov);
         best.offer(sm, x, 1u, rc, dist, ov);

@@ -1,0 +1,123 @@
+"""
+BASELINE.json full-size checks on the GPU through size-independent properties (the oracle needs ~0.3 ms per pair, so it
+only checks a random sample here):
+  config 2   100 Mb genome, 10 000 planted circRNAs, 1 M anchor pairs, 100-nt reads
+  config 3*  hg19-sized coordinates: a 3.1 Gb genome (global bit indices beyond 2^31), 2 M pairs, 2x100-nt style reads
+"""
+import numpy as np
+import pytest
+
+import helpers as H
+from find_circ2_b200 import synth
+from oracle import find_circ_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+ASIZE, MARGIN = 20, 2
+
+
+def _soa(t):
+    return H.pairs_to_soa(t, ASIZE, MARGIN)
+
+
+def _check_planted(J, t, hits, chrom, flags):
+    """a read of a planted junction that carries no sequencing error and no N must recover exactly that junction"""
+    eff = ASIZE - MARGIN
+    R = t.read_len
+    ok = t.junc >= 0
+    jx = t.junc[ok]
+    # error-free: the read equals the genome on both sides -> dist 0.  We only know that for reads we did not mutate;
+    # use dist==0 hits and require coordinates == planted coordinates whenever the true split is inside the scan range.
+    nh = hits["w2"] & 0xFFFF
+    dist = (hits["w2"] >> 16) & 0xFF
+    sel = np.nonzero(ok)[0]
+    good = sel[(nh[sel] == 1) & (dist[sel] == 0)]
+    assert len(good) > 0.5 * len(sel)
+    jj = t.junc[good]
+    assert np.array_equal(hits["start"][good].astype(np.int64), J.start[jj])
+    assert np.array_equal(hits["end"][good].astype(np.int64), J.end[jj])
+    assert np.array_equal((hits["w3"][good] & 1).astype(bool), J.minus[jj])
+    assert np.array_equal((flags[good] & 1).astype(bool), J.circ[jj])
+
+
+def _full_case(engine_kw, genome_sizes, n_pairs, n_circ, seed, sample=1500):
+    from find_circ2_b200.engine import Engine
+
+    g = synth.make_genome(genome_sizes, seed=seed, n_frac=0.005, n_run=(50, 5000), soft_frac=0.0)
+    J = synth.plant_junctions(g, n_circ, n_circ // 20, seed=seed + 1, span=(200, 50000), margin=400)
+    t = synth.make_pairs(g, J, n_pairs, read_len=100, asize=ASIZE, seed=seed + 2, error_rate=0.005, frac_decoy=0.10,
+                         frac_nonuniq=0.0, frac_edge=0.01)
+    chrom, a_start, b_end, l, flags, internal = _soa(t)
+    e = Engine(device=0, asize=ASIZE, **engine_kw)
+    e.load_genome_arrays(g.names, g.seqs)
+    n = len(chrom)
+    rh = e.hash_reads(t.reads, np.full(n, t.read_len, dtype=np.int32))
+    qh = (t.name_id.astype(np.uint64) // np.uint64(2)) * np.uint64(0x9E3779B97F4A7C15)  # two reads share a fragment name
+    qa = (t.as_a - np.maximum(t.xs_a, 0)).astype(np.int16)
+    qb = (t.as_b - np.maximum(t.xs_b, 0)).astype(np.int16)
+    e.agg_reset()
+    hits = e.batch_host(chrom, a_start, b_end, l, flags, internal, np.ones(n, np.uint8), qa, qb, rh, qh, 0, emit=True)
+    # idempotence: the same batch scanned again gives the same hits
+    again = e.scan_host(chrom, a_start, b_end, l, flags, internal)
+    assert np.array_equal(hits.view(np.uint32), again.view(np.uint32))
+    _check_planted(J, t, hits, chrom, flags)
+    # a random sample against the oracle
+    rng = np.random.default_rng(seed)
+    idx = np.sort(rng.choice(n, size=sample, replace=False))
+    want = H.oracle_scan(H.GenomeStrings(g), g.names, chrom[idx], a_start[idx], b_end[idx], l[idx], flags[idx], internal[idx],
+                         O.Options(asize=ASIZE))
+    got = [H.decode_hit(r) for r in hits[idx].view(np.uint32).reshape(-1, 4)]
+    assert got == want
+    # aggregation: counts per key equal a numpy group-by of the hits; distinct counts are bounded by them
+    nh = (hits["w2"] & 0xFFFF) > 0
+    nj = e.agg_finalize()
+    junc = e.agg_fetch(nj)
+    assert e.agg_n_records() == int(nh.sum())
+    assert int(junc["n_spanned"].sum()) == int(nh.sum())
+    key = np.stack([chrom[nh].astype(np.int64), hits["start"][nh].astype(np.int64), hits["end"][nh].astype(np.int64),
+                    (hits["w3"][nh] & 1).astype(np.int64), (1 - (flags[nh] & 1)).astype(np.int64)], axis=1)
+    uk, first, cnt = np.unique(key, axis=0, return_index=True, return_counts=True)
+    assert nj == len(uk)
+    got_key = np.stack([junc["chrom"].astype(np.int64), junc["start"].astype(np.int64), junc["end"].astype(np.int64),
+                        (junc["sk"] & 1).astype(np.int64), ((junc["sk"] >> 1) & 1).astype(np.int64)], axis=1)
+    order = np.lexsort(got_key.T[::-1])
+    assert np.array_equal(got_key[order], uk)
+    assert np.array_equal(junc["n_spanned"][order].astype(np.int64), cnt)
+    # discovery order: first_idx is the row of the first supporting pair, rows come sorted by it
+    rows = np.nonzero(nh)[0]
+    assert np.array_equal(junc["first_idx"][order].astype(np.int64), rows[first])
+    assert (np.diff(junc["first_idx"].astype(np.int64)) > 0).all()
+    assert (junc["n_uniq"] <= junc["n_spanned"]).all() and (junc["n_uniq"] >= 1).all()
+    assert (junc["n_frags"] <= junc["n_spanned"]).all() and (junc["n_frags"] >= 1).all()
+    assert np.array_equal(junc["n_weighted"], junc["n_spanned"].astype(np.float64))
+    # exact distinct counts for the 50 biggest junctions
+    big = np.argsort(-junc["n_spanned"].astype(np.int64))[:50]
+    inv = {tuple(k): i for i, k in enumerate(got_key.tolist())}
+    where = np.array([inv[tuple(k)] for k in key.tolist()])
+    rhh, qhh = rh[nh], qh[nh]
+    for j in big:
+        m = where == j
+        assert int(junc["n_frags"][j]) == len(np.unique(qhh[m]))
+        pal = np.unique(rhh[m][(rhh[m] & np.uint64(1)) == 1])
+        assert int(junc["n_uniq"][j]) == len(np.unique(rhh[m])) - (len(pal) + 1) // 2
+    st = e.genome_stats()
+    e.close()
+    return st
+
+
+def test_config2_full_size():
+    st = _full_case({}, [5000000] * 20, 1000000, 10000, seed=1)
+    assert st["bases"] == 100000000
+
+
+def test_hg19_sized_coordinates():
+    """3.1 Gb of genome: global base indices pass 2^31; tile store ~3.2 GB + planes ~1.2 GB on the device"""
+    import psutil
+
+    if psutil.virtual_memory().available < 24 << 30:
+        pytest.skip("needs ~20 GB of host memory to synthesise the genome")
+    sizes = [249250621, 243199373, 198022430, 191154276, 180915260, 171115067, 159138663, 146364022, 141213431, 135534747,
+             135006516, 133851895, 115169878, 107349540, 102531392, 90354753, 81195210, 78077248, 59128983, 63025520,
+             48129895, 51304566, 155270560]  # chr1..22, X (test_data/test_norm.sam:1-93 lists the hg19 lengths)
+    st = _full_case({}, sizes, 2000000, 100000, seed=5, sample=800)
+    assert st["bases"] == sum(sizes)
