@@ -14,6 +14,8 @@
 //     first idx            min  -> discovery order -> junction name                (:684-686)
 //     n_frags              distinct qname hashes                                   (:584-586)
 //     n_uniq               distinct strand-invariant read hashes (palindromes count half, :588-590)
+#include <stdlib.h>
+
 #include <cub/cub.cuh>
 
 #include "fc_internal.cuh"
@@ -33,6 +35,26 @@ struct JAcc {  // per-junction accumulators filled with integer atomics (determi
   unsigned int seg_start;  // index of the first sorted record
   unsigned int pad;
 };
+
+// ---- 128-bit table entries and compare-and-swap (ATOMG.E.CAS.128) ------------------------------------------------
+struct alignas(16) U128 {
+  unsigned long long lo, hi;
+};
+__device__ __forceinline__ U128 cas128(U128* addr, U128 cmp, U128 val) {
+  U128 old;
+  asm volatile(
+      "{\n\t"
+      ".reg .b128 c, v, o;\n\t"
+      "mov.b128 c, {%2, %3};\n\t"
+      "mov.b128 v, {%4, %5};\n\t"
+      "atom.global.relaxed.gpu.cas.b128 o, [%6], c, v;\n\t"
+      "mov.b128 {%0, %1}, o;\n\t"
+      "}\n"
+      : "=l"(old.lo), "=l"(old.hi)
+      : "l"(cmp.lo), "l"(cmp.hi), "l"(val.lo), "l"(val.hi), "l"(addr)
+      : "memory");
+  return old;
+}
 
 __global__ void count_hits_kernel(int64_t n, const fc_hit* __restrict__ hits, const uint8_t* __restrict__ mask,
                                   uint32_t* __restrict__ accept) {
@@ -210,24 +232,6 @@ __global__ void split_hash_kernel(int64_t n, const fc_jrec* __restrict__ s, cons
 }
 
 // ---- distinct counts with exact hash sets (128-bit entries, 128-bit CAS) ----------------------------------------
-struct alignas(16) U128 {
-  unsigned long long lo, hi;
-};
-__device__ __forceinline__ U128 cas128(U128* addr, U128 cmp, U128 val) {
-  U128 old;
-  asm volatile(
-      "{\n\t"
-      ".reg .b128 c, v, o;\n\t"
-      "mov.b128 c, {%2, %3};\n\t"
-      "mov.b128 v, {%4, %5};\n\t"
-      "atom.global.relaxed.gpu.cas.b128 o, [%6], c, v;\n\t"
-      "mov.b128 {%0, %1}, o;\n\t"
-      "}\n"
-      : "=l"(old.lo), "=l"(old.hi)
-      : "l"(cmp.lo), "l"(cmp.hi), "l"(val.lo), "l"(val.hi), "l"(addr)
-      : "memory");
-  return old;
-}
 // insert (value, seg) into an open-addressing set; returns true when it was not present.  The whole element is the
 // 128-bit entry, so membership is exact (no fingerprint collisions).
 __device__ __forceinline__ bool set_insert(U128* table, unsigned long long mask, unsigned long long value, uint32_t seg) {
@@ -269,6 +273,163 @@ __global__ void distinct_hash_kernel(int64_t n, const fc_jrec* __restrict__ s, c
     if (b_pal) atomicAdd(&a->n_pal, (unsigned)__popc(b_pal));
     if (b_name) atomicAdd(&a->n_frags, (unsigned)__popc(b_name));
   }
+}
+
+// ======================================================================================================================
+// Sort-free aggregation (default).  Junction ids come from an exact 128-bit hash table, the per-junction statistics
+// are pre-aggregated per CTA in shared memory (a junction supported by 10 % of all reads would otherwise serialise
+// ~10^5 atomics on one L2 line) and flushed with integer atomics, the distinct counts use the exact hash sets above.
+// Float sums need stream order only when a weight denominator is not a power of two; such inputs fall back to the
+// sort-based path below.
+// ======================================================================================================================
+__device__ __forceinline__ U128 rec_key(const fc_jrec& r) {
+  return U128{((unsigned long long)r.chrom << 32) | (unsigned long long)r.start,
+              ((unsigned long long)r.end << 32) | 0x80000000ull | (unsigned long long)(((r.sk >> 16) & 0xFFFu) << 2) |
+                  (unsigned long long)(r.sk & 3u)};
+}
+
+__global__ void assign_kernel(int64_t n, const fc_jrec* __restrict__ recs, U128* __restrict__ table, unsigned long long mask,
+                              uint32_t* __restrict__ slot_jid, U128* __restrict__ jkeys, unsigned int* __restrict__ n_junc,
+                              unsigned int* __restrict__ n_other, uint32_t* __restrict__ rec_slot) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const fc_jrec r = recs[i];
+  const U128 key = rec_key(r);
+  unsigned long long slot = fc_mix64(key.lo ^ fc_mix64(key.hi)) & mask;
+  for (;;) {
+    const ulonglong2 cur = __ldcg(reinterpret_cast<const ulonglong2*>(table + slot));
+    if (cur.x == key.lo && cur.y == key.hi) break;
+    if (cur.x == 0ull && cur.y == 0ull) {
+      const U128 old = cas128(table + slot, U128{0ull, 0ull}, key);
+      if (old.lo == 0ull && old.hi == 0ull) {  // this thread created the junction
+        const unsigned int jid = atomicAdd(n_junc, 1u);
+        slot_jid[slot] = jid;
+        jkeys[jid] = key;
+        break;
+      }
+      if (old.lo == key.lo && old.hi == key.hi) break;
+    }
+    slot = (slot + 1ull) & mask;
+  }
+  rec_slot[i] = (uint32_t)slot;
+  const uint32_t den = (r.sk >> 8) & 0xFFu;
+  if (!(den == 1 || den == 2 || den == 4 || den == 8)) atomicAdd(n_other, 1u);
+}
+
+constexpr int ACC_ENTRIES = 1024;  // shared-memory table entries per CTA
+constexpr int ACC_WORDS = 16;      // words per entry
+constexpr int ACC_RECS_PER_THREAD = 2;
+
+__global__ void __launch_bounds__(256) accumulate_kernel(int64_t n, const fc_jrec* __restrict__ recs,
+                                                         const uint32_t* __restrict__ rec_slot,
+                                                         const uint32_t* __restrict__ slot_jid, U128* __restrict__ tab_reads,
+                                                         U128* __restrict__ tab_names, unsigned long long mask,
+                                                         JAcc* __restrict__ acc) {
+  extern __shared__ uint32_t sm[];  // ACC_ENTRIES x ACC_WORDS
+  for (int e = threadIdx.x; e < ACC_ENTRIES; e += blockDim.x) {
+    uint32_t* w = sm + e * ACC_WORDS;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) w[k] = 0u;
+    w[9] = 0x80000000u;  // max_ql as int: INT_MIN
+    w[10] = 0x80000000u;
+    w[11] = w[12] = w[13] = 0xFFFFFFFFu;
+    w[14] = w[15] = 0xFFFFFFFFu;
+  }
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * (blockDim.x * ACC_RECS_PER_THREAD);
+#pragma unroll
+  for (int q = 0; q < ACC_RECS_PER_THREAD; ++q) {
+    const int64_t i = base + q * blockDim.x + threadIdx.x;
+    if (i < n) {
+      const fc_jrec r = recs[i];
+      const uint32_t jid = slot_jid[rec_slot[i]];
+      const bool new_read = set_insert(tab_reads, mask, r.read_hash, jid);
+      const bool new_name = set_insert(tab_names, mask, r.qname_hash, jid);
+      // find / create the CTA-local entry of this junction
+      uint32_t e = (jid * 2654435761u) >> 22;  // 10 bits
+      for (;;) {
+        const uint32_t old = atomicCAS(&sm[e * ACC_WORDS], 0u, jid + 1u);
+        if (old == 0u || old == jid + 1u) break;
+        e = (e + 1u) & (ACC_ENTRIES - 1);
+      }
+      uint32_t* w = sm + e * ACC_WORDS;
+      const uint32_t den = (r.sk >> 8) & 0xFFu;
+      const int cls = den == 1 ? 0 : den == 2 ? 1 : den == 4 ? 2 : den == 8 ? 3 : 4;
+      const bool bridge = r.q_left != 0 && r.q_right != 0;
+      atomicAdd(&w[1], 1u);
+      if (cls < 4) {
+        atomicAdd(&w[2 + (cls >> 1)], 1u << (16 * (cls & 1)));
+        if (bridge) atomicAdd(&w[5 + (cls >> 1)], 1u << (16 * (cls & 1)));
+      } else {
+        atomicAdd(&w[4], bridge ? 0x00010001u : 1u);
+      }
+      if (new_read) atomicAdd(&w[7], (r.read_hash & 1ull) ? 0x00010001u : 1u);
+      if (new_name) atomicAdd(&w[8], 1u);
+      atomicMax(reinterpret_cast<int*>(&w[9]), (int)r.q_left);
+      atomicMax(reinterpret_cast<int*>(&w[10]), (int)r.q_right);
+      atomicMin(&w[11], (uint32_t)r.dist);
+      atomicMin(&w[12], (uint32_t)r.ov);
+      atomicMin(&w[13], (uint32_t)r.n_hits);
+      atomicMin(reinterpret_cast<unsigned long long*>(&w[14]), (unsigned long long)r.idx);
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < ACC_ENTRIES; e += blockDim.x) {
+    const uint32_t* w = sm + e * ACC_WORDS;
+    if (w[0] == 0u) continue;
+    JAcc* a = acc + (w[0] - 1u);
+    atomicAdd(&a->n_spanned, w[1]);
+    if (w[2] & 0xFFFFu) atomicAdd(&a->cw[0], w[2] & 0xFFFFu);
+    if (w[2] >> 16) atomicAdd(&a->cw[1], w[2] >> 16);
+    if (w[3] & 0xFFFFu) atomicAdd(&a->cw[2], w[3] & 0xFFFFu);
+    if (w[3] >> 16) atomicAdd(&a->cw[3], w[3] >> 16);
+    if (w[4] & 0xFFFFu) atomicAdd(&a->cw_other, w[4] & 0xFFFFu);
+    if (w[4] >> 16) atomicAdd(&a->cb_other, w[4] >> 16);
+    if (w[5] & 0xFFFFu) atomicAdd(&a->cb[0], w[5] & 0xFFFFu);
+    if (w[5] >> 16) atomicAdd(&a->cb[1], w[5] >> 16);
+    if (w[6] & 0xFFFFu) atomicAdd(&a->cb[2], w[6] & 0xFFFFu);
+    if (w[6] >> 16) atomicAdd(&a->cb[3], w[6] >> 16);
+    if (w[7] & 0xFFFFu) atomicAdd(&a->n_uniq, w[7] & 0xFFFFu);
+    if (w[7] >> 16) atomicAdd(&a->n_pal, w[7] >> 16);
+    if (w[8]) atomicAdd(&a->n_frags, w[8]);
+    atomicMax(&a->max_ql, (int)w[9]);
+    atomicMax(&a->max_qr, (int)w[10]);
+    atomicMin(&a->min_dist, w[11]);
+    atomicMin(&a->min_ov, w[12]);
+    atomicMin(&a->min_nh, w[13]);
+    atomicMin(&a->first_idx, *reinterpret_cast<const unsigned long long*>(&w[14]));
+  }
+}
+
+__global__ void finish_hash_kernel(int64_t nj, const JAcc* __restrict__ acc, const U128* __restrict__ jkeys,
+                                   fc_junction* __restrict__ out, uint64_t* __restrict__ order_key,
+                                   uint32_t* __restrict__ order_val) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nj) return;
+  const JAcc a = acc[j];
+  const U128 k = jkeys[j];
+  fc_junction o;
+  o.chrom = (uint32_t)(k.lo >> 32);
+  o.start = (uint32_t)k.lo;
+  o.end = (uint32_t)(k.hi >> 32);
+  const uint32_t low = (uint32_t)k.hi;
+  o.sk = (low & 3u) | (((low >> 2) & 0xFFFu) << 16);
+  o.first_idx = a.first_idx;
+  // all weights are k/8 here (checked on the host before this path is taken): any summation order is exact
+  o.n_weighted = (8.0 * a.cw[0] + 4.0 * a.cw[1] + 2.0 * a.cw[2] + 1.0 * a.cw[3]) / 8.0;
+  o.n_uniq_bridges = (8.0 * a.cb[0] + 4.0 * a.cb[1] + 2.0 * a.cb[2] + 1.0 * a.cb[3]) / 8.0;
+  o.n_spanned = a.n_spanned;
+  o.n_frags = a.n_frags;
+  o.n_uniq = a.n_uniq - (a.n_pal + 1) / 2;
+  o.best_q_left = (int16_t)a.max_ql;
+  o.best_q_right = (int16_t)a.max_qr;
+  o.min_n_hits = (uint16_t)a.min_nh;
+  o.min_dist = (uint8_t)a.min_dist;
+  o.min_ov = (uint8_t)a.min_ov;
+  o.pad = 0;
+  out[j] = o;
+  order_key[j] = a.first_idx;
+  order_val[j] = (uint32_t)j;
 }
 
 __global__ void finish_kernel(int64_t nj, int64_t n, const JAcc* __restrict__ acc, const fc_jrec* __restrict__ s,
@@ -559,6 +720,73 @@ extern "C" int fc_agg_partition(fc_ctx* ctx, int32_t n_ranks, fc_jrec* d_out, in
   return FC_OK;
 }
 
+// sort-free path; returns -100 when the input needs the sort-based path (non power-of-two weight denominators)
+static int64_t finalize_hash(fc_ctx* ctx, int64_t n, cudaStream_t st) {
+  fc_agg& a = ctx->agg;
+  unsigned long long cap = 1024;
+  while (cap < 2ull * (unsigned long long)n) cap <<= 1;
+  FC_CUDA(ctx, a.htab[2].reserve((size_t)cap * 16, st, false, 0));  // junction keys
+  for (int k = 0; k < 3; ++k) {
+    if (k < 2) FC_CUDA(ctx, a.htab[k].reserve((size_t)cap * 16, st, false, 0));
+    FC_CUDA(ctx, cudaMemsetAsync(a.htab[k].p, 0, (size_t)cap * 16, st));
+  }
+  FC_CUDA(ctx, a.scratch[0].reserve((size_t)cap * 4, st, false, 0));   // slot -> junction id
+  FC_CUDA(ctx, a.scratch[1].reserve((size_t)n * 16, st, false, 0));    // junction id -> key
+  FC_CUDA(ctx, a.scratch[2].reserve((size_t)n * 4, st, false, 0));     // record -> slot
+  uint32_t* slot_jid = (uint32_t*)a.scratch[0].p;
+  U128* jkeys = (U128*)a.scratch[1].p;
+  uint32_t* rec_slot = (uint32_t*)a.scratch[2].p;
+  unsigned long long* counters = (unsigned long long*)a.counters.p;
+  unsigned int* n_junc = (unsigned int*)(counters + 2);
+  unsigned int* n_other = (unsigned int*)(counters + 3);
+  FC_CUDA(ctx, cudaMemsetAsync(counters + 2, 0, 2 * sizeof(unsigned long long), st));
+  assign_kernel<<<nblk(n, 256), 256, 0, st>>>(n, (const fc_jrec*)a.recs.p, (U128*)a.htab[2].p, cap - 1, slot_jid, jkeys, n_junc,
+                                              n_other, rec_slot);
+  FC_LAUNCH_CHECK(ctx);
+  unsigned long long h[2] = {0, 0};
+  FC_CUDA(ctx, cudaMemcpyAsync(h, counters + 2, sizeof(h), cudaMemcpyDeviceToHost, st));
+  FC_CUDA(ctx, cudaStreamSynchronize(st));
+  if ((unsigned int)h[1] != 0) return -100;
+  const int64_t nj = (unsigned int)h[0];
+  FC_CUDA(ctx, a.scratch[7].reserve((size_t)nj * sizeof(JAcc), st, false, 0));
+  JAcc* acc = (JAcc*)a.scratch[7].p;
+  acc_init_kernel<<<nblk(nj, 256), 256, 0, st>>>(nj, acc);
+  FC_LAUNCH_CHECK(ctx);
+  const size_t smem = (size_t)ACC_ENTRIES * ACC_WORDS * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FC_CUDA(ctx, cudaFuncSetAttribute(accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int per_block = 256 * ACC_RECS_PER_THREAD;
+  accumulate_kernel<<<(unsigned)((n + per_block - 1) / per_block), 256, smem, st>>>(
+      n, (const fc_jrec*)a.recs.p, rec_slot, slot_jid, (U128*)a.htab[0].p, (U128*)a.htab[1].p, cap - 1, acc);
+  FC_LAUNCH_CHECK(ctx);
+  FC_CUDA(ctx, a.junctions.reserve((size_t)nj * sizeof(fc_junction), st, false, 0));
+  FC_CUDA(ctx, a.scratch[5].reserve((size_t)nj * sizeof(fc_junction), st, false, 0));
+  FC_CUDA(ctx, a.scratch[3].reserve((size_t)nj * 8, st, false, 0));
+  FC_CUDA(ctx, a.scratch[4].reserve((size_t)nj * 8, st, false, 0));
+  FC_CUDA(ctx, a.scratch[6].reserve((size_t)nj * 8, st, false, 0));
+  fc_junction* tmpj = (fc_junction*)a.scratch[5].p;
+  uint64_t* kA = (uint64_t*)a.scratch[3].p;
+  uint64_t* kB = (uint64_t*)a.scratch[4].p;
+  uint32_t* vA = (uint32_t*)a.scratch[6].p;
+  uint32_t* vB = vA + nj;
+  finish_hash_kernel<<<nblk(nj, 128), 128, 0, st>>>(nj, acc, jkeys, tmpj, kA, vA);
+  FC_LAUNCH_CHECK(ctx);
+  int order_bits = 64;
+  if (a.max_idx != ~0ull) {
+    order_bits = 1;
+    while (order_bits < 64 && (a.max_idx >> order_bits)) order_bits++;
+  }
+  int rc = sort_pairs_u64_u32(ctx, nj, kA, kB, vA, vB, 0, order_bits, st);
+  if (rc) return rc;
+  gather_junctions_kernel<<<nblk(nj, 256), 256, 0, st>>>(nj, tmpj, vB, (fc_junction*)a.junctions.p);
+  FC_LAUNCH_CHECK(ctx);
+  a.n_junc = nj;
+  return nj;
+}
+
 extern "C" int64_t fc_agg_finalize(fc_ctx* ctx, void* stream) {
   if (!ctx) return FC_E_ARG;
   cudaStream_t st = (cudaStream_t)stream;
@@ -573,6 +801,16 @@ extern "C" int64_t fc_agg_finalize(fc_ctx* ctx, void* stream) {
   if (n >= (1ll << 32)) return fc_fail(ctx, FC_E_ARG, "more than 2^32 records on one device");
   rc = ensure_counters(ctx, st);
   if (rc) return rc;
+  // FC_AGG_MODE=sort forces the sort-based path (tests compare the two)
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("FC_AGG_MODE");
+    mode = (e && e[0] == 's') ? 1 : 0;
+  }
+  if (mode == 0) {
+    const int64_t r = finalize_hash(ctx, n, st);
+    if (r != -100) return r;
+  }
   // scratch layout
   FC_CUDA(ctx, a.scratch[0].reserve((size_t)n * 8, st, false, 0));  // u64 A
   FC_CUDA(ctx, a.scratch[1].reserve((size_t)n * 8, st, false, 0));  // u64 B

@@ -60,7 +60,7 @@ struct fc_agg {
   fc_dbuf scratch[8];
   fc_dbuf cub_tmp;
   fc_dbuf counters;     // small device counters
-  fc_dbuf htab[2];      // hash sets for the distinct counts (reads, fragment names)
+  fc_dbuf htab[3];      // hash sets for the distinct counts (reads, fragment names) and the junction-key table
 };
 
 struct fc_ctx {

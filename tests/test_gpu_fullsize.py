@@ -20,12 +20,27 @@ def _soa(t):
     return H.pairs_to_soa(t, ASIZE, MARGIN)
 
 
-def _check_planted(J, t, hits, chrom, flags):
+def _intact(g, J):
+    """junctions whose planted dinucleotides survived later plantings (two junctions a base apart overwrite each other)"""
+    ok = np.zeros(len(J), dtype=bool)
+    for i in range(len(J)):
+        seq = g.seqs[int(J.chrom[i])]
+        s, e = int(J.start[i]), int(J.end[i])
+        if J.circ[i]:
+            left, right = (b"AC", b"CT") if J.minus[i] else (b"AG", b"GT")
+            ok[i] = seq[s - 2 : s].tobytes() == left and seq[e : e + 2].tobytes() == right
+        else:
+            left, right = (b"CT", b"AC") if J.minus[i] else (b"GT", b"AG")
+            ok[i] = seq[s : s + 2].tobytes() == left and seq[e - 2 : e].tobytes() == right
+    return ok
+
+
+def _check_planted(g, J, t, hits, chrom, flags):
     """a read of a planted junction that carries no sequencing error and no N must recover exactly that junction"""
     eff = ASIZE - MARGIN
     R = t.read_len
-    ok = t.junc >= 0
-    jx = t.junc[ok]
+    intact = _intact(g, J)
+    ok = (t.junc >= 0) & intact[np.maximum(t.junc, 0)]
     # error-free: the read equals the genome on both sides -> dist 0.  We only know that for reads we did not mutate;
     # use dist==0 hits and require coordinates == planted coordinates whenever the true split is inside the scan range.
     nh = hits["w2"] & 0xFFFF
@@ -34,10 +49,13 @@ def _check_planted(J, t, hits, chrom, flags):
     good = sel[(nh[sel] == 1) & (dist[sel] == 0)]
     assert len(good) > 0.5 * len(sel)
     jj = t.junc[good]
-    assert np.array_equal(hits["start"][good].astype(np.int64), J.start[jj])
-    assert np.array_equal(hits["end"][good].astype(np.int64), J.end[jj])
-    assert np.array_equal((hits["w3"][good] & 1).astype(bool), J.minus[jj])
-    assert np.array_equal((flags[good] & 1).astype(bool), J.circ[jj])
+    same = ((hits["start"][good].astype(np.int64) == J.start[jj]) & (hits["end"][good].astype(np.int64) == J.end[jj])
+            & ((hits["w3"][good] & 1).astype(bool) == J.minus[jj]) & ((flags[good] & 1).astype(bool) == J.circ[jj]))
+    # the rare exceptions (a second planted junction inside the read, chance homology next to a damaged signal) must be
+    # exceptions for the oracle too
+    odd = good[~same]
+    assert len(odd) < 2e-3 * len(good), (len(odd), len(good))
+    return odd[:300]
 
 
 def _full_case(engine_kw, genome_sizes, n_pairs, n_circ, seed, sample=1500):
@@ -60,10 +78,10 @@ def _full_case(engine_kw, genome_sizes, n_pairs, n_circ, seed, sample=1500):
     # idempotence: the same batch scanned again gives the same hits
     again = e.scan_host(chrom, a_start, b_end, l, flags, internal)
     assert np.array_equal(hits.view(np.uint32), again.view(np.uint32))
-    _check_planted(J, t, hits, chrom, flags)
-    # a random sample against the oracle
+    odd = _check_planted(g, J, t, hits, chrom, flags)
+    # a random sample (plus every pair that did not recover its planted junction) against the oracle
     rng = np.random.default_rng(seed)
-    idx = np.sort(rng.choice(n, size=sample, replace=False))
+    idx = np.unique(np.concatenate([rng.choice(n, size=sample, replace=False), odd]))
     want = H.oracle_scan(H.GenomeStrings(g), g.names, chrom[idx], a_start[idx], b_end[idx], l[idx], flags[idx], internal[idx],
                          O.Options(asize=ASIZE))
     got = [H.decode_hit(r) for r in hits[idx].view(np.uint32).reshape(-1, 4)]
@@ -87,7 +105,9 @@ def _full_case(engine_kw, genome_sizes, n_pairs, n_circ, seed, sample=1500):
     rows = np.nonzero(nh)[0]
     assert np.array_equal(junc["first_idx"][order].astype(np.int64), rows[first])
     assert (np.diff(junc["first_idx"].astype(np.int64)) > 0).all()
-    assert (junc["n_uniq"] <= junc["n_spanned"]).all() and (junc["n_uniq"] >= 1).all()
+    # n_uniq may legitimately be 0: junctions planted inside an N run are supported by all-N reads, which equal their
+    # own reverse complement -- {read, rev_comp(read)} has ONE element and the reference prints len/2 = 0 (find_circ.py:588-590)
+    assert (junc["n_uniq"] <= junc["n_spanned"]).all()
     assert (junc["n_frags"] <= junc["n_spanned"]).all() and (junc["n_frags"] >= 1).all()
     assert np.array_equal(junc["n_weighted"], junc["n_spanned"].astype(np.float64))
     # exact distinct counts for the 50 biggest junctions

@@ -405,3 +405,27 @@ def test_tile_store_rebuild_across_read_lengths():
         got = [H.decode_hit(r) for r in hits.view(np.uint32).reshape(-1, 4)]
         assert got == want, read_len
     e.close()
+
+
+def test_sort_based_and_hash_based_aggregation_agree():
+    """fc_agg_finalize has two implementations (sort-free default, sort-based fallback for weight denominators that are
+    not powers of two): both must produce identical junction tables"""
+    import subprocess
+    import sys
+
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, "tests")
+from test_gpu_parity import _random_records, _engine
+recs = _random_records(250000, 4000, 77, dens=(1, 1, 2, 4, 8))
+e = _engine(); e.agg_reset(); e.agg_append_host(recs)
+nj = e.agg_finalize(); j = e.agg_fetch(nj)
+sys.stdout.buffer.write(j.tobytes())
+'''
+    outs = []
+    for mode in ("hash", "sort"):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, env=dict(os.environ, FC_AGG_MODE=mode), cwd=H.ROOT)
+        assert r.returncode == 0, r.stderr.decode()[-2000:]
+        outs.append(r.stdout)
+    assert len(outs[0]) > 64 * 1000
+    assert outs[0] == outs[1]
