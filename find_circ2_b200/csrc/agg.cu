@@ -316,7 +316,7 @@ __global__ void assign_kernel(int64_t n, const fc_jrec* __restrict__ recs, U128*
   if (!(den == 1 || den == 2 || den == 4 || den == 8)) atomicAdd(n_other, 1u);
 }
 
-constexpr int ACC_ENTRIES = 1024;  // shared-memory table entries per CTA
+constexpr int ACC_ENTRIES = 1024;  // shared-memory table entries per CTA (2 x the records of a CTA)
 constexpr int ACC_WORDS = 16;      // words per entry
 constexpr int ACC_RECS_PER_THREAD = 2;
 
@@ -340,13 +340,15 @@ __global__ void __launch_bounds__(256) accumulate_kernel(int64_t n, const fc_jre
 #pragma unroll
   for (int q = 0; q < ACC_RECS_PER_THREAD; ++q) {
     const int64_t i = base + q * blockDim.x + threadIdx.x;
-    if (i < n) {
+    const bool active = i < n;
+    const unsigned amask = __ballot_sync(0xffffffffu, active);
+    if (active) {
       const fc_jrec r = recs[i];
       const uint32_t jid = slot_jid[rec_slot[i]];
       const bool new_read = set_insert(tab_reads, mask, r.read_hash, jid);
       const bool new_name = set_insert(tab_names, mask, r.qname_hash, jid);
       // find / create the CTA-local entry of this junction
-      uint32_t e = (jid * 2654435761u) >> 22;  // 10 bits
+      uint32_t e = (jid * 2654435761u) >> 22;  // 10 bits = log2(ACC_ENTRIES)
       for (;;) {
         const uint32_t old = atomicCAS(&sm[e * ACC_WORDS], 0u, jid + 1u);
         if (old == 0u || old == jid + 1u) break;
@@ -356,21 +358,35 @@ __global__ void __launch_bounds__(256) accumulate_kernel(int64_t n, const fc_jre
       const uint32_t den = (r.sk >> 8) & 0xFFu;
       const int cls = den == 1 ? 0 : den == 2 ? 1 : den == 4 ? 2 : den == 8 ? 3 : 4;
       const bool bridge = r.q_left != 0 && r.q_right != 0;
-      atomicAdd(&w[1], 1u);
-      if (cls < 4) {
-        atomicAdd(&w[2 + (cls >> 1)], 1u << (16 * (cls & 1)));
-        if (bridge) atomicAdd(&w[5 + (cls >> 1)], 1u << (16 * (cls & 1)));
-      } else {
-        atomicAdd(&w[4], bridge ? 0x00010001u : 1u);
+      // counters: the lanes of the warp that share the junction add once, through their first lane (a junction
+      // that collects a large share of the reads would otherwise serialise on its shared-memory words)
+      const unsigned peers = __match_any_sync(amask, jid);
+      const bool lead = (int)(threadIdx.x & 31) == __ffs((int)peers) - 1;
+      unsigned add[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // words 1..8
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const unsigned cwk = __popc(__ballot_sync(amask, cls == k) & peers);
+        const unsigned cbk = __popc(__ballot_sync(amask, cls == k && bridge) & peers);
+        add[1 + (k >> 1)] += cwk << (16 * (k & 1));
+        add[4 + (k >> 1)] += cbk << (16 * (k & 1));
       }
-      if (new_read) atomicAdd(&w[7], (r.read_hash & 1ull) ? 0x00010001u : 1u);
-      if (new_name) atomicAdd(&w[8], 1u);
-      atomicMax(reinterpret_cast<int*>(&w[9]), (int)r.q_left);
-      atomicMax(reinterpret_cast<int*>(&w[10]), (int)r.q_right);
-      atomicMin(&w[11], (uint32_t)r.dist);
-      atomicMin(&w[12], (uint32_t)r.ov);
-      atomicMin(&w[13], (uint32_t)r.n_hits);
-      atomicMin(reinterpret_cast<unsigned long long*>(&w[14]), (unsigned long long)r.idx);
+      add[3] = __popc(__ballot_sync(amask, cls == 4) & peers) | (__popc(__ballot_sync(amask, cls == 4 && bridge) & peers) << 16);
+      add[6] = __popc(__ballot_sync(amask, new_read) & peers) | (__popc(__ballot_sync(amask, new_read && (r.read_hash & 1ull)) & peers) << 16);
+      add[7] = __popc(__ballot_sync(amask, new_name) & peers);
+      add[0] = __popc(peers);
+      if (lead) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (add[k]) atomicAdd(&w[1 + k], add[k]);
+      }
+      // extrema: only touch the word when this record improves it (reads of shared memory broadcast, atomics serialise)
+      if ((int)r.q_left > *reinterpret_cast<volatile int*>(&w[9])) atomicMax(reinterpret_cast<int*>(&w[9]), (int)r.q_left);
+      if ((int)r.q_right > *reinterpret_cast<volatile int*>(&w[10])) atomicMax(reinterpret_cast<int*>(&w[10]), (int)r.q_right);
+      if ((uint32_t)r.dist < *reinterpret_cast<volatile uint32_t*>(&w[11])) atomicMin(&w[11], (uint32_t)r.dist);
+      if ((uint32_t)r.ov < *reinterpret_cast<volatile uint32_t*>(&w[12])) atomicMin(&w[12], (uint32_t)r.ov);
+      if ((uint32_t)r.n_hits < *reinterpret_cast<volatile uint32_t*>(&w[13])) atomicMin(&w[13], (uint32_t)r.n_hits);
+      if ((unsigned long long)r.idx < *reinterpret_cast<volatile unsigned long long*>(&w[14]))
+        atomicMin(reinterpret_cast<unsigned long long*>(&w[14]), (unsigned long long)r.idx);
     }
   }
   __syncthreads();
