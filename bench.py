@@ -247,7 +247,7 @@ def run_gpu(args):
             ev_scan[1].record()
         eng.agg_emit(n, hits, d["chrom"], d["flags"], d["wden"], d["q_a"], d["q_b"], d["read_hash"], d["qname_hash"], idx_base, stream)
         if world > 1:
-            parallel.exchange_records(eng, dist, dev, stream)
+            parallel.exchange_records(eng, dist, dev, stream, upper_bound=n)
         return eng.agg_finalize(stream)
 
     # ---- pinned host copy of the batch (for `e2e`)
@@ -265,7 +265,7 @@ def run_gpu(args):
         eng.batch_host(p["chrom"], p["a_start"], p["b_end"], p["l"], p["flags"], p["internal"], p["wden"], p["q_a"], p["q_b"],
                        p["read_hash"], p["qname_hash"], idx_base, emit=True, out=h_hits)
         if world > 1:
-            parallel.exchange_records(eng, dist, dev, 0)
+            parallel.exchange_records(eng, dist, dev, 0, upper_bound=n)
         nj = eng.agg_finalize(0)
         junc = eng.agg_fetch(nj)
         return nj, junc
@@ -343,7 +343,7 @@ def run_gpu(args):
                 "scan_ms": scan_step, "merge_ms": ms_step - scan_step, "seeds": {"genome": 1, "junctions": 2, "pairs": "3+1000*rank"},
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "scan_kernel<5>", "bytes_per_pair": BYTES_PER_PAIR, "peak_source": peak_src},
+                         "traffic": None, "kernel": "scan_kernel<NP=3,T=1> (csrc/scan.cu)", "bytes_per_pair": BYTES_PER_PAIR, "peak_source": peak_src},
             "e2e": {"value": total_pairs / e2e_step, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_step * 1e3},
             "gpu_launches": int(launches),

@@ -91,6 +91,7 @@ SYMBOLS = [
     ("fc_batch_ties_host", C.c_int, [_P, C.POINTER(ScanParams), _P, _P]),
     ("fc_agg_append", C.c_int, [_P, C.c_int64, _P, _P]),
     ("fc_agg_append_host", C.c_int, [_P, C.c_int64, _P]),
+    ("fc_agg_replace", C.c_int, [_P, C.c_int64, _P, _P]),
     ("fc_agg_n_records", C.c_int64, [_P]),
     ("fc_agg_records", _P, [_P]),
     ("fc_agg_partition", C.c_int, [_P, C.c_int32, _P, _P, _P]),

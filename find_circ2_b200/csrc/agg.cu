@@ -576,10 +576,12 @@ int sync_n_recs(fc_ctx* ctx, cudaStream_t st) {
     ctx->agg.n_recs = 0;
     return FC_OK;
   }
+  if (ctx->agg.n_exact) return FC_OK;  // the host already knows the exact count
   unsigned long long v = 0;
   FC_CUDA(ctx, cudaMemcpyAsync(&v, ctx->agg.counters.p, sizeof(v), cudaMemcpyDeviceToHost, st));
   FC_CUDA(ctx, cudaStreamSynchronize(st));
   ctx->agg.n_recs = (int64_t)v;
+  ctx->agg.n_exact = true;
   return FC_OK;
 }
 
@@ -616,6 +618,7 @@ void fc_dbuf::release() {
 extern "C" int fc_agg_reset(fc_ctx* ctx) {
   if (!ctx) return FC_E_ARG;
   ctx->agg.n_recs = 0;
+  ctx->agg.n_exact = true;
   ctx->agg.n_junc = -1;
   ctx->agg.max_idx = 0;
   if (ctx->agg.counters.p) FC_CUDA(ctx, cudaMemset(ctx->agg.counters.p, 0, 64 * sizeof(unsigned long long)));
@@ -651,6 +654,7 @@ extern "C" int fc_agg_emit(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, const i
   bump_kernel<<<1, 1, 0, st>>>((unsigned long long*)a.counters.p, pos, accept, n);
   FC_LAUNCH_CHECK(ctx);
   a.n_recs = ub;  // upper bound until the next sync
+  a.n_exact = false;
   a.n_junc = -1;
   if (a.max_idx != ~0ull && idx_base + (uint64_t)n > a.max_idx) a.max_idx = idx_base + (uint64_t)n;
   return FC_OK;
@@ -672,6 +676,27 @@ extern "C" int fc_agg_append(fc_ctx* ctx, int64_t n, const fc_jrec* d_recs, void
   unsigned long long v = (unsigned long long)a.n_recs;
   FC_CUDA(ctx, cudaMemcpyAsync(a.counters.p, &v, sizeof(v), cudaMemcpyHostToDevice, st));
   FC_CUDA(ctx, cudaStreamSynchronize(st));
+  a.n_junc = -1;
+  return FC_OK;
+}
+
+__global__ void set_count_kernel(unsigned long long* c, unsigned long long v) { *c = v; }
+
+// replace the record buffer by n records given on the device (the receive side of the multi-GPU exchange);
+// asynchronous on `stream`, no host synchronisation
+extern "C" int fc_agg_replace(fc_ctx* ctx, int64_t n, const fc_jrec* d_recs, void* stream) {
+  if (!ctx || n < 0) return FC_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  fc_agg& a = ctx->agg;
+  int rc = ensure_counters(ctx, st);
+  if (rc) return rc;
+  FC_CUDA(ctx, a.recs.reserve((size_t)(n > 0 ? n : 1) * sizeof(fc_jrec), st, false, 0));
+  if (n > 0) FC_CUDA(ctx, cudaMemcpyAsync(a.recs.p, d_recs, (size_t)n * sizeof(fc_jrec), cudaMemcpyDeviceToDevice, st));
+  set_count_kernel<<<1, 1, 0, st>>>((unsigned long long*)a.counters.p, (unsigned long long)n);
+  FC_LAUNCH_CHECK(ctx);
+  a.n_recs = n;
+  a.n_exact = true;
+  a.max_idx = ~0ull;
   a.n_junc = -1;
   return FC_OK;
 }

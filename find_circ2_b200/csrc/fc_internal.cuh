@@ -54,6 +54,7 @@ struct fc_dbuf {
 struct fc_agg {
   fc_dbuf recs;         // fc_jrec[n_recs]
   int64_t n_recs = 0;
+  bool n_exact = true;  // n_recs is the exact count (false: upper bound, the exact value is in the device counter)
   fc_dbuf junctions;    // fc_junction[n_junc]
   int64_t n_junc = -1;  // -1: not finalized
   uint64_t max_idx = 0; // upper bound of fc_jrec.idx seen so far (~0: unknown)

@@ -208,6 +208,9 @@ class Engine:
     def agg_append_device(self, n, d_recs, stream=0):
         self._check(self.lib.fc_agg_append(self.h, n, ptr(d_recs), stream))
 
+    def agg_replace_device(self, n, d_recs, stream=0):
+        self._check(self.lib.fc_agg_replace(self.h, n, ptr(d_recs), stream))
+
     def agg_n_records(self) -> int:
         return int(self._check(self.lib.fc_agg_n_records(self.h)))
 

@@ -18,33 +18,52 @@ import numpy as np
 REC_BYTES = 48
 
 
-def exchange_records(eng, dist, dev, stream=0):
+_BUF = {}
+
+
+def _buffer(tag, nbytes, dev):
+    """persistent, growing byte buffers (no allocation inside the exchange once warmed up)"""
+    import torch
+
+    key = (tag, str(dev))
+    t = _BUF.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8, device=dev)
+        _BUF[key] = t
+    return t
+
+
+def exchange_records(eng, dist, dev, stream=0, upper_bound=None):
     """hash-partition this rank's junction records and swap them with the other ranks; afterwards the engine's
-    aggregator holds exactly the records whose keys this rank owns.  Returns (sent_bytes, received_bytes)."""
+    aggregator holds exactly the records whose keys this rank owns.  Returns (sent_bytes, received_bytes).
+    Host synchronisations: two inside the partition (record count, per-destination counts) and one for the counts
+    received from the peers."""
     import torch
 
     world = dist.get_world_size()
     if world == 1:
         return 0, 0
-    n = eng.agg_n_records()
-    send = torch.empty(max(n, 1) * REC_BYTES, dtype=torch.uint8, device=dev)
+    ub = upper_bound if upper_bound is not None else eng.agg_n_records()
+    send = _buffer("send", max(ub, 1) * REC_BYTES, dev)
     counts = eng.agg_partition(world, send, stream)  # int64[world], records per destination
-    c_send = torch.from_numpy(np.ascontiguousarray(counts, dtype=np.int64)).to(dev)
+    n = int(counts.sum())
+    c_send = torch.from_numpy(np.ascontiguousarray(counts, dtype=np.int64)).to(dev, non_blocking=True)
     c_recv = torch.empty_like(c_send)
     dist.all_to_all_single(c_recv, c_send)
     recv_counts = c_recv.cpu().numpy()
     n_recv = int(recv_counts.sum())
-    recv = torch.empty(max(n_recv, 1) * REC_BYTES, dtype=torch.uint8, device=dev)
+    recv = _buffer("recv", max(n_recv, 1) * REC_BYTES, dev)
     dist.all_to_all_single(
         recv[: n_recv * REC_BYTES],
         send[: n * REC_BYTES],
         output_split_sizes=[int(c) * REC_BYTES for c in recv_counts],
         input_split_sizes=[int(c) * REC_BYTES for c in counts],
     )
-    if dev is not None and getattr(dev, "type", "cpu") == "cuda":
-        torch.cuda.current_stream().synchronize()
-    eng.agg_reset()
-    eng.agg_append_device(n_recv, recv, stream)
+    if hasattr(eng, "agg_replace_device"):
+        eng.agg_replace_device(n_recv, recv, stream)
+    else:
+        eng.agg_reset()
+        eng.agg_append_device(n_recv, recv, stream)
     return int(n * REC_BYTES), int(n_recv * REC_BYTES)
 
 

@@ -208,6 +208,8 @@ int fc_agg_emit(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, const int32_t* d_c
                 uint64_t idx_base, void* stream);
 int fc_agg_append(fc_ctx* ctx, int64_t n, const fc_jrec* d_recs, void* stream); /* records built elsewhere (other ranks) */
 int fc_agg_append_host(fc_ctx* ctx, int64_t n, const fc_jrec* h_recs);
+/* replace the record buffer by n device records (receive side of the exchange); asynchronous, no host synchronisation */
+int fc_agg_replace(fc_ctx* ctx, int64_t n, const fc_jrec* d_recs, void* stream);
 int64_t fc_agg_n_records(fc_ctx* ctx);
 const fc_jrec* fc_agg_records(fc_ctx* ctx); /* device pointer to the record buffer (for the all-to-all) */
 /* destination rank of every record: hash(key) % n_ranks (int32 per record) and per-rank counts (int64[n_ranks]) */
