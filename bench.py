@@ -173,6 +173,28 @@ def cpu_baseline(g, t, n_sample, procs=1):
     return len(idx) / dt, dt
 
 
+def host_ingest(g, t, n_sample, eng):
+    """host ingest reported separately (north_star): SAM text -> fragments -> struct-of-arrays batches in the python host of
+    the drop-in (find_circ2_b200/pipeline.py), measured on a sample by running the whole CLI path and subtracting the time
+    spent inside GPU calls"""
+    import tempfile
+
+    from find_circ2_b200 import cli, synth
+
+    idx = np.arange(min(n_sample, len(t)))
+    with tempfile.TemporaryDirectory() as tmp:
+        sam = os.path.join(tmp, "sample.sam")
+        with open(sam, "w") as fh:
+            fh.write(synth.sam_header(g))
+            for i in idx:
+                fh.writelines(synth.bwa_records_for_pair(g, t, int(i), "r%d" % int(t.name_id[i])))
+        opt = cli.parse_args(["-G", "unused", "-a", str(ASIZE), "-n", "bench"])[0]
+        out = cli.run_to_strings(opt, sam, engine=eng)
+    host_s = out["seconds_total"] - out["seconds_gpu_calls"]
+    return {"value": len(idx) / host_s, "unit": "pairs/s", "kind": "python host (SAM text -> fragments -> SoA batches -> writers), GPU calls excluded",
+            "sample": "%d reads" % len(idx), "seconds_host": host_s, "seconds_gpu_calls": out["seconds_gpu_calls"]}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -238,16 +260,28 @@ def run_gpu(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     idx_base = rank * (1 << 40)
 
+    # multi-GPU: records travel to the rank that owns their key.  Preferred: the emit kernel writes them straight into
+    # the owner's buffer over NVLink (CUDA IPC peer memory); fallback: partition + NCCL all-to-all.
+    use_p2p = world > 1 and not args.no_p2p and parallel.p2p_setup(eng, dist, dev, int(2.5 * n) + (1 << 16))
+
     def step_device(ev_scan=None):
-        eng.agg_reset()
+        if use_p2p:
+            eng.agg_reset_async(stream)
+            parallel.stream_barrier(dist, dev)  # every rank's counter is zero before anybody writes
+        else:
+            eng.agg_reset()
         if ev_scan:
             ev_scan[0].record()
         eng.scan(pairs, hits, stream)
         if ev_scan:
             ev_scan[1].record()
-        eng.agg_emit(n, hits, d["chrom"], d["flags"], d["wden"], d["q_a"], d["q_b"], d["read_hash"], d["qname_hash"], idx_base, stream)
-        if world > 1:
-            parallel.exchange_records(eng, dist, dev, stream, upper_bound=n)
+        if use_p2p:
+            eng.agg_emit_p2p(n, hits, d["chrom"], d["flags"], d["wden"], d["q_a"], d["q_b"], d["read_hash"], d["qname_hash"], idx_base, stream)
+            parallel.stream_barrier(dist, dev)  # every rank's records have landed
+        else:
+            eng.agg_emit(n, hits, d["chrom"], d["flags"], d["wden"], d["q_a"], d["q_b"], d["read_hash"], d["qname_hash"], idx_base, stream)
+            if world > 1:
+                parallel.exchange_records(eng, dist, dev, stream, upper_bound=n)
         return eng.agg_finalize(stream)
 
     # ---- pinned host copy of the batch (for `e2e`)
@@ -340,6 +374,7 @@ def run_gpu(args):
                             % (args.genome_mb, args.n_circ, args.pairs),
                 "pairs_scanned_per_gpu": n, "junctions_rank0": int(nj), "l2": "flushed (256 MiB memset) before every timed step",
                 "timing": "per-step CUDA events summed over the steps; max over ranks",
+                "exchange": ("none" if world == 1 else ("fused emit+exchange over peer memory (CUDA IPC, NVLink)" if use_p2p else "partition + NCCL all-to-all")),
                 "scan_ms": scan_step, "merge_ms": ms_step - scan_step, "seeds": {"genome": 1, "junctions": 2, "pairs": "3+1000*rank"},
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -350,6 +385,7 @@ def run_gpu(args):
             "clocks": sampler.summary(),
         }
         if world == 1:
+            line["ingest"] = host_ingest(g, t, min(args.cpu_sample, 20000), eng)
             v, dt = cpu_baseline(g, t, args.cpu_sample, 1)
             line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": 1, "kind": "port",
                                     "sample": "first %d pairs of the same workload, oracle scan+aggregation single process (%.1f s); SAM decode untimed" % (args.cpu_sample, dt)}
@@ -369,6 +405,7 @@ def main():
     ap.add_argument("--genome-mb", type=int, default=100)
     ap.add_argument("--n-circ", type=int, default=10000)
     ap.add_argument("--cpu-sample", type=int, default=20000)
+    ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: use partition + NCCL all-to-all instead of peer-memory emit")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

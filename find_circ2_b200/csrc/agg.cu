@@ -15,6 +15,7 @@
 //     n_frags              distinct qname hashes                                   (:584-586)
 //     n_uniq               distinct strand-invariant read hashes (palindromes count half, :588-590)
 #include <stdlib.h>
+#include <string.h>
 
 #include <cub/cub.cuh>
 
@@ -107,6 +108,13 @@ __global__ void key_hash_kernel(int64_t n, const fc_jrec* __restrict__ recs, uin
   if (i >= n) return;
   const fc_jrec& r = recs[i];
   h[i] = fc_key_hash(r.chrom, r.start, r.end, r.sk, seed);
+  iota[i] = (uint32_t)i;
+}
+
+__global__ void idx_key_kernel(int64_t n, const fc_jrec* __restrict__ recs, uint64_t* __restrict__ k, uint32_t* __restrict__ iota) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  k[i] = recs[i].idx;
   iota[i] = (uint32_t)i;
 }
 
@@ -619,9 +627,24 @@ extern "C" int fc_agg_reset(fc_ctx* ctx) {
   if (!ctx) return FC_E_ARG;
   ctx->agg.n_recs = 0;
   ctx->agg.n_exact = true;
+  ctx->agg.unordered = false;
   ctx->agg.n_junc = -1;
   ctx->agg.max_idx = 0;
   if (ctx->agg.counters.p) FC_CUDA(ctx, cudaMemset(ctx->agg.counters.p, 0, 64 * sizeof(unsigned long long)));
+  return FC_OK;
+}
+
+extern "C" int fc_agg_reset_async(fc_ctx* ctx, void* stream) {
+  if (!ctx) return FC_E_ARG;
+  fc_agg& a = ctx->agg;
+  int rc = ensure_counters(ctx, (cudaStream_t)stream);
+  if (rc) return rc;
+  a.n_recs = 0;
+  a.n_exact = true;
+  a.unordered = false;
+  a.n_junc = -1;
+  a.max_idx = 0;
+  FC_CUDA(ctx, cudaMemsetAsync(a.counters.p, 0, 64 * sizeof(unsigned long long), (cudaStream_t)stream));
   return FC_OK;
 }
 
@@ -842,6 +865,12 @@ extern "C" int64_t fc_agg_finalize(fc_ctx* ctx, void* stream) {
   if (n >= (1ll << 32)) return fc_fail(ctx, FC_E_ARG, "more than 2^32 records on one device");
   rc = ensure_counters(ctx, st);
   if (rc) return rc;
+  if (a.p2p_enabled) {
+    unsigned long long ovf = 0;
+    FC_CUDA(ctx, cudaMemcpyAsync(&ovf, (unsigned long long*)a.counters.p + 4, sizeof(ovf), cudaMemcpyDeviceToHost, st));
+    FC_CUDA(ctx, cudaStreamSynchronize(st));
+    if (ovf) return fc_fail(ctx, FC_E_NOMEM, "peer-to-peer record buffer overflow (%llu records dropped): raise the capacity", ovf);
+  }
   // FC_AGG_MODE=sort forces the sort-based path (tests compare the two)
   static int mode = -1;
   if (mode < 0) {
@@ -869,6 +898,18 @@ extern "C" int64_t fc_agg_finalize(fc_ctx* ctx, void* stream) {
   uint32_t* seg_incl = (uint32_t*)a.scratch[6].p;
   unsigned long long* counters = (unsigned long long*)a.counters.p;
 
+  if (a.unordered) {
+    // records arrived in arbitrary order (peer-to-peer emit): restore stream order first, the stable sort below and the
+    // sequential float sums rely on it
+    idx_key_kernel<<<nblk(n, 256), 256, 0, st>>>(n, (const fc_jrec*)a.recs.p, kA, vA);
+    FC_LAUNCH_CHECK(ctx);
+    rc = sort_pairs_u64_u32(ctx, n, kA, kB, vA, vB, 0, 64, st);
+    if (rc) return rc;
+    gather_kernel<<<nblk(n, 256), 256, 0, st>>>(n, (const fc_jrec*)a.recs.p, vB, sorted);
+    FC_LAUNCH_CHECK(ctx);
+    FC_CUDA(ctx, cudaMemcpyAsync(a.recs.p, sorted, (size_t)n * sizeof(fc_jrec), cudaMemcpyDeviceToDevice, st));
+    a.unordered = false;
+  }
   uint64_t seed = 0x9E3779B97F4A7C15ULL;
   bool ok = false;
   uint32_t nj32 = 0;
@@ -951,6 +992,149 @@ extern "C" int fc_agg_fetch(fc_ctx* ctx, int64_t n, fc_junction* h_out) {
 
 extern "C" const fc_junction* fc_agg_junctions(fc_ctx* ctx) {
   return ctx && ctx->agg.n_junc >= 0 ? (const fc_junction*)ctx->agg.junctions.p : nullptr;
+}
+
+// ======================================================================================================================
+// Fused emit + exchange over peer memory (multi-GPU, one node).  Every rank exports its record buffer and its record
+// counter with CUDA IPC; the emit kernel of every rank hashes the junction key of each accepted pair to its owner rank,
+// claims slots in the OWNER's buffer with a warp-aggregated system-scope atomicAdd on the owner's counter and stores
+// the 48-byte record straight into the owner's memory over NVLink.  No partition pass, no all-to-all, no host
+// synchronisation: two stream-ordered barriers (tiny NCCL all-reduces issued by the host) bracket the kernel.
+// Arrival order is arbitrary; the sort-free aggregation does not depend on it and the sort-based fallback re-orders by idx.
+// ======================================================================================================================
+struct P2PView {
+  fc_jrec* recs[8];
+  unsigned long long* cnt[8];
+  unsigned long long capacity;
+  int world;
+};
+
+__global__ void emit_p2p_kernel(int64_t n, const fc_hit* __restrict__ hits, const uint8_t* __restrict__ mask,
+                                const int32_t* __restrict__ chrom, const uint8_t* __restrict__ flags,
+                                const uint8_t* __restrict__ wden, const int16_t* __restrict__ q_a,
+                                const int16_t* __restrict__ q_b, const uint64_t* __restrict__ read_hash,
+                                const uint64_t* __restrict__ qname_hash, uint64_t idx_base, P2PView pv,
+                                unsigned long long* __restrict__ overflow) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in = i < n;
+  fc_jrec r;
+  bool accept = false;
+  int dest = 0;
+  if (in) {
+    const fc_hit h = hits[i];
+    accept = (h.w2 & 0xFFFFu) != 0 && (!mask || mask[i]);
+    if (accept) {
+      const uint32_t fl = flags[i];
+      const bool backsplice = fl & FC_PF_BACKSPLICE;
+      r.chrom = (uint32_t)chrom[i];
+      r.start = (uint32_t)h.start;
+      r.end = (uint32_t)h.end;
+      const uint32_t strand = h.w3 & 1u, sig = (h.w3 >> 1) & 0xFFFu;
+      const uint64_t rh = read_hash[i];
+      r.sk = strand | (backsplice ? 0u : 2u) | ((uint32_t)(rh & 1ull) << 2) | ((uint32_t)wden[i] << 8) | (sig << 16);
+      r.idx = idx_base + (uint64_t)i;
+      r.read_hash = rh;
+      r.qname_hash = qname_hash[i];
+      r.q_left = backsplice ? q_b[i] : q_a[i];
+      r.q_right = backsplice ? q_a[i] : q_b[i];
+      r.n_hits = (uint16_t)(h.w2 & 0xFFFFu);
+      r.dist = (uint8_t)((h.w2 >> 16) & 0xFFu);
+      r.ov = (uint8_t)(h.w2 >> 24);
+      dest = (int)(fc_key_hash(r.chrom, r.start, r.end, r.sk, 0x5bd1e995ULL) % (uint64_t)pv.world);
+    }
+  }
+  const unsigned lane = threadIdx.x & 31;
+  for (int d = 0; d < pv.world; ++d) {
+    const unsigned m = __ballot_sync(0xffffffffu, accept && dest == d);
+    if (!m) continue;
+    const int leader = __ffs((int)m) - 1;
+    unsigned long long base = 0;
+    if ((int)lane == leader) base = atomicAdd_system(pv.cnt[d], (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (accept && dest == d) {
+      const unsigned long long pos = base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
+      if (pos < pv.capacity) {
+        uint4* dst = reinterpret_cast<uint4*>(pv.recs[d] + pos);
+        const uint4* src = reinterpret_cast<const uint4*>(&r);
+        dst[0] = src[0];
+        dst[1] = src[1];
+        dst[2] = src[2];
+      } else {
+        atomicAdd(overflow, 1ull);
+      }
+    }
+  }
+}
+
+extern "C" int fc_p2p_export(fc_ctx* ctx, int64_t capacity_records, uint8_t* h_handles /* 128 bytes */) {
+  if (!ctx || capacity_records <= 0 || !h_handles) return FC_E_ARG;
+  fc_agg& a = ctx->agg;
+  cudaStream_t st = ctx->own_stream;
+  int rc = ensure_counters(ctx, st);
+  if (rc) return rc;
+  FC_CUDA(ctx, a.recs.reserve((size_t)capacity_records * sizeof(fc_jrec), st, false, 0));
+  FC_CUDA(ctx, cudaStreamSynchronize(st));
+  a.p2p_capacity = (int64_t)(a.recs.cap / sizeof(fc_jrec));
+  cudaIpcMemHandle_t h0, h1;
+  FC_CUDA(ctx, cudaIpcGetMemHandle(&h0, a.recs.p));
+  FC_CUDA(ctx, cudaIpcGetMemHandle(&h1, a.counters.p));
+  memcpy(h_handles, &h0, 64);
+  memcpy(h_handles + 64, &h1, 64);
+  memcpy(h_handles + 56, &a.p2p_capacity, 0);  // (capacity travels separately)
+  return FC_OK;
+}
+
+extern "C" int fc_p2p_connect(fc_ctx* ctx, int32_t world, int32_t rank, const uint8_t* h_all_handles /* world x 128 */,
+                              const int64_t* h_capacities /* world */) {
+  if (!ctx || world < 1 || world > 8 || rank < 0 || rank >= world || !h_all_handles || !h_capacities) return FC_E_ARG;
+  fc_agg& a = ctx->agg;
+  a.p2p_world = world;
+  a.p2p_rank = rank;
+  int64_t cap = a.p2p_capacity;
+  for (int r = 0; r < world; ++r) {
+    if (h_capacities[r] < cap) cap = h_capacities[r];
+    if (r == rank) {
+      a.p2p_recs[r] = a.recs.p;
+      a.p2p_cnt[r] = a.counters.p;
+      continue;
+    }
+    cudaIpcMemHandle_t h0, h1;
+    memcpy(&h0, h_all_handles + (size_t)r * 128, 64);
+    memcpy(&h1, h_all_handles + (size_t)r * 128 + 64, 64);
+    FC_CUDA(ctx, cudaIpcOpenMemHandle(&a.p2p_recs[r], h0, cudaIpcMemLazyEnablePeerAccess));
+    FC_CUDA(ctx, cudaIpcOpenMemHandle(&a.p2p_cnt[r], h1, cudaIpcMemLazyEnablePeerAccess));
+  }
+  a.p2p_min_capacity = cap;
+  a.p2p_enabled = true;
+  return FC_OK;
+}
+
+extern "C" int fc_agg_emit_p2p(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, const int32_t* d_chrom, const uint8_t* d_flags,
+                               const uint8_t* d_wden, const int16_t* d_q_a, const int16_t* d_q_b,
+                               const uint64_t* d_read_hash, const uint64_t* d_qname_hash, const uint8_t* d_mask,
+                               uint64_t idx_base, void* stream) {
+  if (!ctx || n < 0) return FC_E_ARG;
+  fc_agg& a = ctx->agg;
+  if (!a.p2p_enabled) return fc_fail(ctx, FC_E_STATE, "fc_agg_emit_p2p before fc_p2p_connect");
+  if (n == 0) return FC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  P2PView pv;
+  for (int r = 0; r < 8; ++r) {
+    pv.recs[r] = r < a.p2p_world ? (fc_jrec*)a.p2p_recs[r] : nullptr;
+    pv.cnt[r] = r < a.p2p_world ? (unsigned long long*)a.p2p_cnt[r] : nullptr;
+  }
+  pv.capacity = (unsigned long long)a.p2p_min_capacity;
+  pv.world = a.p2p_world;
+  unsigned long long* counters = (unsigned long long*)a.counters.p;
+  emit_p2p_kernel<<<nblk(n, 256), 256, 0, st>>>(n, d_hits, d_mask, d_chrom, d_flags, d_wden, d_q_a, d_q_b, d_read_hash,
+                                                d_qname_hash, idx_base, pv, counters + 4);
+  FC_LAUNCH_CHECK(ctx);
+  a.n_recs = a.p2p_capacity;  // upper bound; the exact count is the (shared) device counter
+  a.n_exact = false;
+  a.unordered = true;
+  a.max_idx = ~0ull;
+  a.n_junc = -1;
+  return FC_OK;
 }
 
 void fc_agg_release(fc_ctx* ctx) {

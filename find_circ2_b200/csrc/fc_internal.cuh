@@ -58,6 +58,13 @@ struct fc_agg {
   fc_dbuf junctions;    // fc_junction[n_junc]
   int64_t n_junc = -1;  // -1: not finalized
   uint64_t max_idx = 0; // upper bound of fc_jrec.idx seen so far (~0: unknown)
+  bool unordered = false;  // records are not in idx order (peer-to-peer emit)
+  // fused emit + exchange over peer memory
+  bool p2p_enabled = false;
+  int p2p_world = 1, p2p_rank = 0;
+  int64_t p2p_capacity = 0, p2p_min_capacity = 0;
+  void* p2p_recs[8] = {};
+  void* p2p_cnt[8] = {};
   fc_dbuf scratch[8];
   fc_dbuf cub_tmp;
   fc_dbuf counters;     // small device counters

@@ -208,6 +208,25 @@ class Engine:
     def agg_append_device(self, n, d_recs, stream=0):
         self._check(self.lib.fc_agg_append(self.h, n, ptr(d_recs), stream))
 
+    # ---- fused emit + exchange over peer memory (multi-GPU) ----
+    def p2p_export(self, capacity_records: int) -> np.ndarray:
+        h = np.zeros(128, dtype=np.uint8)
+        self._check(self.lib.fc_p2p_export(self.h, int(capacity_records), h.ctypes.data))
+        return h
+
+    def p2p_connect(self, world: int, rank: int, handles: np.ndarray, capacities: np.ndarray):
+        handles = np.ascontiguousarray(handles, dtype=np.uint8)
+        capacities = np.ascontiguousarray(capacities, dtype=np.int64)
+        self._check(self.lib.fc_p2p_connect(self.h, world, rank, handles.ctypes.data, capacities.ctypes.data))
+
+    def agg_emit_p2p(self, n, d_hits, d_chrom, d_flags, d_wden, d_q_a, d_q_b, d_read_hash, d_qname_hash, idx_base, stream=0,
+                     d_mask=None):
+        self._check(self.lib.fc_agg_emit_p2p(self.h, n, ptr(d_hits), ptr(d_chrom), ptr(d_flags), ptr(d_wden), ptr(d_q_a),
+                                             ptr(d_q_b), ptr(d_read_hash), ptr(d_qname_hash), ptr(d_mask), idx_base, stream))
+
+    def agg_reset_async(self, stream=0):
+        self._check(self.lib.fc_agg_reset_async(self.h, stream))
+
     def agg_replace_device(self, n, d_recs, stream=0):
         self._check(self.lib.fc_agg_replace(self.h, n, ptr(d_recs), stream))
 

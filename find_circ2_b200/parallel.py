@@ -67,6 +67,46 @@ def exchange_records(eng, dist, dev, stream=0, upper_bound=None):
     return int(n * REC_BYTES), int(n_recv * REC_BYTES)
 
 
+def p2p_setup(eng, dist, dev, capacity_records: int) -> bool:
+    """export this rank's record buffer / counter with CUDA IPC, collect everybody's handles, open the peers'.
+    Returns False (and leaves the engine on the NCCL all-to-all path) when IPC is not available."""
+    import torch
+
+    world, rank = dist.get_world_size(), dist.get_rank()
+    ok = 1
+    try:
+        handle = eng.p2p_export(capacity_records)
+    except Exception:
+        handle = np.zeros(128, dtype=np.uint8)
+        ok = 0
+    mine = torch.from_numpy(np.concatenate([handle, np.frombuffer(np.int64(capacity_records).tobytes(), dtype=np.uint8),
+                                            np.array([ok], dtype=np.uint8)])).to(dev)
+    allh = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allh, mine)
+    allh = np.stack([t.cpu().numpy() for t in allh])
+    if not allh[:, 136].all():
+        return False
+    caps = np.array([np.frombuffer(allh[r, 128:136].tobytes(), dtype=np.int64)[0] for r in range(world)], dtype=np.int64)
+    try:
+        eng.p2p_connect(world, rank, allh[:, :128].copy(), caps)
+        good = 1
+    except Exception:
+        good = 0
+    flag = torch.tensor([good], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return bool(flag.item())
+
+
+def stream_barrier(dist, dev, _cache={}):
+    """a barrier that orders the STREAMS of all ranks without blocking the host: a one-element all-reduce"""
+    import torch
+
+    t = _cache.get(str(dev))
+    if t is None:
+        t = _cache[str(dev)] = torch.zeros(1, dtype=torch.int32, device=dev)
+    dist.all_reduce(t)
+
+
 def gather_junctions(junctions: np.ndarray, dist, dev):
     """ordered gather of every rank's junction table to rank 0 (rows sorted by first_idx = discovery order)"""
     import torch

@@ -218,6 +218,19 @@ int64_t fc_agg_finalize(fc_ctx* ctx, void* stream);
 int fc_agg_fetch(fc_ctx* ctx, int64_t n, fc_junction* h_out); /* sorted by first_idx */
 const fc_junction* fc_agg_junctions(fc_ctx* ctx);             /* device pointer, after finalize */
 
+/* ------------------------------------------------------------------ fused emit + exchange over peer memory (one node)
+ * Every rank exports its record buffer and counter (fc_p2p_export -> 128 handle bytes, exchanged by the host with any
+ * collective), opens its peers' (fc_p2p_connect) and from then on fc_agg_emit_p2p writes each record directly into the
+ * buffer of the rank that owns its junction key (hash(key) % world) over NVLink.  Per step the host issues
+ * fc_agg_reset_async, a stream-ordered barrier, the scan, fc_agg_emit_p2p, a second barrier and fc_agg_finalize. */
+int fc_p2p_export(fc_ctx* ctx, int64_t capacity_records, uint8_t* h_handles /* 128 bytes */);
+int fc_p2p_connect(fc_ctx* ctx, int32_t world, int32_t rank, const uint8_t* h_all_handles /* world x 128 */,
+                   const int64_t* h_capacities /* world */);
+int fc_agg_emit_p2p(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, const int32_t* d_chrom, const uint8_t* d_flags,
+                    const uint8_t* d_wden, const int16_t* d_q_a, const int16_t* d_q_b, const uint64_t* d_read_hash,
+                    const uint64_t* d_qname_hash, const uint8_t* d_mask, uint64_t idx_base, void* stream);
+int fc_agg_reset_async(fc_ctx* ctx, void* stream);
+
 /* ------------------------------------------------------------------ utilities */
 void* fc_pinned_alloc(int64_t bytes);
 void fc_pinned_free(void* p);
