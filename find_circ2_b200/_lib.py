@@ -43,7 +43,7 @@ class Pairs(C.Structure):
     _fields_ = [
         ("n", C.c_int64), ("d_chrom", C.c_void_p), ("d_a_start", C.c_void_p), ("d_b_end", C.c_void_p),
         ("d_l", C.c_void_p), ("d_flags", C.c_void_p), ("d_rlo", C.c_void_p), ("d_rhi", C.c_void_p), ("d_rn", C.c_void_p),
-        ("n_words", C.c_int32), ("max_l", C.c_int32),
+        ("n_words", C.c_int32), ("max_l", C.c_int32), ("plane_stride", C.c_int64),
     ]
 
 
@@ -85,6 +85,14 @@ SYMBOLS = [
     ("fc_scan_host", C.c_int, [_P, C.POINTER(ScanParams), C.c_int64, _P, _P, _P, _P, _P, _P, C.c_int32, _P]),
     ("fc_batch_host", C.c_int, [_P, C.POINTER(ScanParams), C.c_int64, _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P,
                                 C.c_uint64, C.c_int32, _P]),
+    ("fc_batch_host_idx", C.c_int, [_P, C.POINTER(ScanParams), C.c_int64, _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P, _P,
+                                    C.c_uint64, C.c_int32, _P]),
+    ("fc_batch_host_planes", C.c_int, [_P, C.POINTER(ScanParams), C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int64,
+                                       C.c_int32, _P, _P, _P, _P, _P, _P, C.c_uint64, C.c_int32, _P]),
+    ("fc_agg_emit_idx", C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    ("fc_ingest_create", _P, [_P, C.c_int32, _P, _P]),
+    ("fc_ingest_destroy", None, [_P]),
+    ("fc_ingest_parse", C.c_int64, [_P, _P, C.c_int64, C.c_int32, _P]),
     ("fc_agg_reset", C.c_int, [_P]),
     ("fc_agg_emit", C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_uint64, _P]),
     ("fc_batch_emit_host", C.c_int, [_P, _P, C.c_uint64]),

@@ -70,6 +70,8 @@ def build_parser() -> optparse.OptionParser:
     a("", "--no-multi", dest="multi_events", default=True, action="store_false", help="Do not record multi-events")
     a("", "--batch-pairs", dest="batch_pairs", type=int, default=1 << 18, help="anchor pairs per GPU batch (default 262144)")
     a("", "--device", dest="device", type=int, default=0, help="CUDA device (default 0)")
+    a("", "--python-ingest", dest="native", default=True, action="store_false",
+      help="decode SAM text in python instead of the native (C++) ingest")
     return p
 
 
@@ -85,18 +87,32 @@ def parse_args(argv):
         maxdist=o.maxdist, short_threshold=o.short_threshold, huge_threshold=o.huge_threshold, noncanonical=o.noncanonical,
         allhits=o.allhits, strandpref=o.strandpref, halfunique=o.halfunique, report_nobridges=o.report_nobridges,
         nolinear=o.nolinear, multi_events=o.multi_events, throughput=o.throughput, chunksize=o.chunksize, noop=o.noop,
-        silent=o.silent, stdout=o.stdout, batch_pairs=o.batch_pairs, device=o.device,
+        silent=o.silent, stdout=o.stdout, batch_pairs=o.batch_pairs, device=o.device, native=o.native,
     )
     return opt, args, o
 
 
-def run_to_strings(opt: Options, path=None, engine=None):
+def native_ok(opt: Options, path) -> bool:
+    """the native ingest covers SAM text files; BAM, stdin and --all-hits / --noop use the python reader"""
+    return bool(path) and path != "-" and path.endswith("sam") and not opt.allhits and not opt.noop and opt.native
+
+
+def run_to_strings(opt: Options, path=None, engine=None, native=None):
     """the whole run, outputs as strings (tests and the single-process CLI share this)"""
-    names, lengths, records = samio.open_alignments(path)
+    native = native_ok(opt, path) if native is None else native
+    if native:
+        names = samio.sam_header_names(path)
+        records = None
+    else:
+        names, lengths, records = samio.open_alignments(path)
     run = Run(opt, names, engine)
     try:
         t0 = time.perf_counter()
-        run.process(records)
+        if native:
+            with open(path, "rb") as fh:
+                run.process_native(fh)
+        else:
+            run.process(records)
         t1 = time.perf_counter()
         run.finalize()
         out = {

@@ -69,7 +69,7 @@ __global__ void emit_kernel(int64_t n, const fc_hit* __restrict__ hits, const ui
                             const int32_t* __restrict__ chrom, const uint8_t* __restrict__ flags,
                             const uint8_t* __restrict__ wden, const int16_t* __restrict__ q_a,
                             const int16_t* __restrict__ q_b, const uint64_t* __restrict__ read_hash,
-                            const uint64_t* __restrict__ qname_hash, uint64_t idx_base,
+                            const uint64_t* __restrict__ qname_hash, uint64_t idx_base, const uint64_t* __restrict__ idx,
                             const unsigned long long* __restrict__ n_recs, fc_jrec* __restrict__ recs) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -85,7 +85,7 @@ __global__ void emit_kernel(int64_t n, const fc_hit* __restrict__ hits, const ui
   uint32_t strand = h.w3 & 1u, sig = (h.w3 >> 1) & 0xFFFu;
   uint64_t rh = read_hash[i];
   r.sk = strand | (backsplice ? 0u : 2u) | ((uint32_t)(rh & 1ull) << 2) | ((uint32_t)wden[i] << 8) | (sig << 16);
-  r.idx = idx_base + (uint64_t)i;
+  r.idx = idx ? idx[i] : idx_base + (uint64_t)i;
   r.read_hash = rh;
   r.qname_hash = qname_hash[i];
   // by convention A precedes B in the genome: swap for back-splices (find_circ.py:552-553)
@@ -648,10 +648,10 @@ extern "C" int fc_agg_reset_async(fc_ctx* ctx, void* stream) {
   return FC_OK;
 }
 
-extern "C" int fc_agg_emit(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, const int32_t* d_chrom, const uint8_t* d_flags,
+static int agg_emit_impl(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, const int32_t* d_chrom, const uint8_t* d_flags,
                            const uint8_t* d_wden, const int16_t* d_q_a, const int16_t* d_q_b,
                            const uint64_t* d_read_hash, const uint64_t* d_qname_hash, const uint8_t* d_mask,
-                           uint64_t idx_base, void* stream) {
+                           uint64_t idx_base, const uint64_t* d_idx, void* stream) {
   if (!ctx || n < 0) return FC_E_ARG;
   if (n == 0) return FC_OK;
   if (n >= (1ll << 32)) return fc_fail(ctx, FC_E_ARG, "batch too large");
@@ -671,7 +671,7 @@ extern "C" int fc_agg_emit(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, const i
   rc = scan_u32(ctx, n, accept, pos, false, st);
   if (rc) return rc;
   emit_kernel<<<nblk(n, 256), 256, 0, st>>>(n, d_hits, d_mask, pos, d_chrom, d_flags, d_wden, d_q_a, d_q_b, d_read_hash,
-                                            d_qname_hash, idx_base, (const unsigned long long*)a.counters.p,
+                                            d_qname_hash, idx_base, d_idx, (const unsigned long long*)a.counters.p,
                                             (fc_jrec*)a.recs.p);
   FC_LAUNCH_CHECK(ctx);
   bump_kernel<<<1, 1, 0, st>>>((unsigned long long*)a.counters.p, pos, accept, n);
@@ -679,8 +679,30 @@ extern "C" int fc_agg_emit(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, const i
   a.n_recs = ub;  // upper bound until the next sync
   a.n_exact = false;
   a.n_junc = -1;
-  if (a.max_idx != ~0ull && idx_base + (uint64_t)n > a.max_idx) a.max_idx = idx_base + (uint64_t)n;
+  if (d_idx) {
+    a.max_idx = ~0ull;
+    a.unordered = true;  // rows are not in stream order: the sort-based path restores it from idx
+  } else if (a.max_idx != ~0ull && idx_base + (uint64_t)n > a.max_idx) {
+    a.max_idx = idx_base + (uint64_t)n;
+  }
   return FC_OK;
+}
+
+extern "C" int fc_agg_emit(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, const int32_t* d_chrom, const uint8_t* d_flags,
+                           const uint8_t* d_wden, const int16_t* d_q_a, const int16_t* d_q_b,
+                           const uint64_t* d_read_hash, const uint64_t* d_qname_hash, const uint8_t* d_mask,
+                           uint64_t idx_base, void* stream) {
+  return agg_emit_impl(ctx, n, d_hits, d_chrom, d_flags, d_wden, d_q_a, d_q_b, d_read_hash, d_qname_hash, d_mask, idx_base,
+                       nullptr, stream);
+}
+
+extern "C" int fc_agg_emit_idx(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, const int32_t* d_chrom, const uint8_t* d_flags,
+                               const uint8_t* d_wden, const int16_t* d_q_a, const int16_t* d_q_b,
+                               const uint64_t* d_read_hash, const uint64_t* d_qname_hash, const uint8_t* d_mask,
+                               const uint64_t* d_idx, void* stream) {
+  if (!d_idx) return FC_E_ARG;
+  return agg_emit_impl(ctx, n, d_hits, d_chrom, d_flags, d_wden, d_q_a, d_q_b, d_read_hash, d_qname_hash, d_mask, 0, d_idx,
+                       stream);
 }
 
 extern "C" int fc_agg_append(fc_ctx* ctx, int64_t n, const fc_jrec* d_recs, void* stream) {

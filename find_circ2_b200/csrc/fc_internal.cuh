@@ -84,6 +84,7 @@ struct fc_ctx {
   int64_t last_n = 0;
   fc_pairs last_pairs = {};
   bool last_has_payload = false;
+  bool last_has_idx = false;  // host_path[15] holds explicit stream positions of the last batch
 };
 
 int fc_fail(fc_ctx* ctx, int code, const char* fmt, ...);

@@ -1,0 +1,393 @@
+// ingest.cu -- native SAM-text ingest for the common fragment shapes (host code; no device work).
+//
+// The reference decodes every record through pysam and builds Python objects per read
+// (/root/reference/find_circ.py:461-469, 1450-1486, 976-1140, 821-852); a python host that does the same is three orders
+// of magnitude slower than the scan kernel.  This file parses SAM text in C++ and emits, for every fragment that consists
+// of ONE mate with at most one supplementary record (single-end two-segment reads: the bulk of real input), the
+// struct-of-arrays row the GPU needs: window coordinates, flags, the internal read part already as bit planes,
+// anchor qualities and the read / name hashes -- ready to be copied to the device as they are.
+// Everything else (paired mates, three or more segments, records it cannot interpret) is handed back as a byte range
+// and goes through the python implementation of the same logic (find_circ2_b200/pipeline.py), so the two paths together
+// cover exactly what the reference covers.  Counters are accumulated here only for the fragments handled here.
+#include <string.h>
+
+#include <string>
+#include <string_view>
+#include <unordered_map>
+#include <vector>
+
+#include "fc_internal.cuh"
+
+extern "C" uint64_t fc_hash_bytes(const uint8_t* p, int64_t n);
+extern "C" uint64_t fc_hash_read(const uint8_t* seq, int64_t n, int32_t* is_palindrome);
+
+namespace {
+
+using sv = std::string_view;
+
+struct Rec {
+  int64_t off = 0, len = 0;  // line in the chunk
+  sv qname, seq, qual;
+  int flag = 0, tid = -1, pos = 0, aend = 0, clip_start = 0, qlen = 0, AS = 0, XS = 0;
+  bool has_cigar = false, has_AS = false, has_XS = false, has_seq = false, has_qual = false, ok = true;
+};
+
+inline bool parse_int(sv s, int& out) {
+  if (s.empty()) return false;
+  size_t i = 0;
+  bool neg = false;
+  if (s[0] == '-') { neg = true; i = 1; }
+  else if (s[0] == '+') i = 1;
+  if (i >= s.size()) return false;
+  long v = 0;
+  for (; i < s.size(); ++i) {
+    char c = s[i];
+    if (c < '0' || c > '9') return false;
+    v = v * 10 + (c - '0');
+    if (v > 2147483647L) return false;
+  }
+  out = (int)(neg ? -v : v);
+  return true;
+}
+
+struct Ingest {
+  fc_ingest_params p;
+  std::unordered_map<std::string, int> name2tid;
+  std::vector<int32_t> tid2gid;
+  std::string last_name;
+  int last_tid = -1;
+  int64_t frag_seq = 0;
+  bool first_record = true;
+
+  int lookup(sv name) {
+    if (name.size() == last_name.size() && memcmp(name.data(), last_name.data(), name.size()) == 0) return last_tid;
+    auto it = name2tid.find(std::string(name));
+    last_name.assign(name.data(), name.size());
+    last_tid = it == name2tid.end() ? -1 : it->second;
+    return last_tid;
+  }
+
+  // pysam field semantics (find_circ2_b200/samio.py is the python twin of this function)
+  void parse_line(const char* base, int64_t off, int64_t len, Rec& r) {
+    r = Rec();
+    r.off = off;
+    r.len = len;
+    sv line(base + off, (size_t)len);
+    while (!line.empty() && (line.back() == '\n' || line.back() == '\r')) line.remove_suffix(1);
+    sv f[11];
+    size_t start = 0;
+    int k = 0;
+    for (; k < 11; ++k) {
+      size_t t = line.find('\t', start);
+      if (t == sv::npos) {
+        f[k] = line.substr(start);
+        start = line.size();
+        ++k;
+        break;
+      }
+      f[k] = line.substr(start, t - start);
+      start = t + 1;
+    }
+    if (k < 11) { r.ok = false; return; }
+    r.qname = f[0];
+    if (!parse_int(f[1], r.flag)) { r.ok = false; return; }
+    r.tid = f[2] == "*" ? -1 : lookup(f[2]);
+    int pos1;
+    if (!parse_int(f[3], pos1)) { r.ok = false; return; }
+    r.pos = pos1 - 1;
+    // CIGAR
+    if (f[5] != "*") {
+      r.has_cigar = true;
+      int aend = r.pos, clip = 0, lead_soft = 0, trail_soft = 0;
+      bool in_lead = true, clip_done = false, any = false;
+      long num = 0;
+      bool have_num = false;
+      int last_soft = 0;  // trailing soft clip candidate
+      for (char c : f[5]) {
+        if (c >= '0' && c <= '9') { num = num * 10 + (c - '0'); have_num = true; continue; }
+        if (!have_num) { r.ok = false; return; }
+        int n = (int)num;
+        num = 0;
+        have_num = false;
+        any = true;
+        switch (c) {
+          case 'M': case '=': case 'X': aend += n; break;
+          case 'D': case 'N': aend += n; break;
+          case 'I': case 'P': break;
+          case 'S': case 'H': break;
+          default: r.ok = false; return;
+        }
+        // offset of the aligned part: S/H lengths are summed until the first M; other operations do not stop the walk
+        // (find_circ.py:1086-1097)
+        if (!clip_done) {
+          if (c == 'S' || c == 'H') clip += n;
+          else if (c == 'M') clip_done = true;
+        }
+        // soft clips at the two ends of the stored sequence (hard clips may sit outside them)
+        if (in_lead) {
+          if (c == 'H') { /* skip */ }
+          else if (c == 'S') lead_soft += n;
+          else in_lead = false;
+        }
+        if (c == 'S') last_soft += n;
+        else if (c != 'H') last_soft = 0;
+      }
+      if (have_num || !any) { r.ok = false; return; }
+      trail_soft = in_lead ? 0 : last_soft;  // an all-clip CIGAR has no trailing part of its own
+      r.aend = aend;
+      r.clip_start = clip;
+      r.qlen = -(lead_soft + trail_soft);  // completed below with the sequence length
+    }
+    if (f[9] != "*") { r.has_seq = true; r.seq = f[9]; }
+    if (f[10] != "*") { r.has_qual = true; r.qual = f[10]; }
+    r.qlen += (int)r.seq.size();
+    // tags
+    while (start < line.size()) {
+      size_t t = line.find('\t', start);
+      sv tag = line.substr(start, t == sv::npos ? sv::npos : t - start);
+      if (tag.size() > 5 && tag[2] == ':' && tag[3] == 'i' && tag[4] == ':') {
+        if (tag[0] == 'A' && tag[1] == 'S') r.has_AS = parse_int(tag.substr(5), r.AS);
+        else if (tag[0] == 'X' && tag[1] == 'S') r.has_XS = parse_int(tag.substr(5), r.XS);
+      }
+      if (t == sv::npos) break;
+      start = t + 1;
+    }
+  }
+};
+
+inline void pack_planes(sv s, int n_words, int64_t stride, int64_t row, uint32_t* rlo, uint32_t* rhi, uint32_t* rn, bool& any_n) {
+  for (int w = 0; w < n_words; ++w) {
+    uint32_t lo = 0, hi = 0, nn = 0;
+    int count = (int)s.size() - 32 * w;
+    if (count > 32) count = 32;
+    if (count > 0) fc::pack32(reinterpret_cast<const uint8_t*>(s.data()) + 32 * w, count, lo, hi, nn);
+    rlo[(int64_t)w * stride + row] = lo;
+    rhi[(int64_t)w * stride + row] = hi;
+    rn[(int64_t)w * stride + row] = nn;
+    if (nn) any_n = true;
+  }
+}
+
+}  // namespace
+
+struct fc_ingest {
+  Ingest g;
+};
+
+extern "C" fc_ingest* fc_ingest_create(const fc_ingest_params* p, int32_t n_names, const char* const* names,
+                                       const int32_t* tid2gid) {
+  if (!p || n_names < 0) return nullptr;
+  fc_ingest* h = new fc_ingest();
+  h->g.p = *p;
+  for (int32_t i = 0; i < n_names; ++i) {
+    h->g.name2tid.emplace(names[i], i);
+    h->g.tid2gid.push_back(tid2gid ? tid2gid[i] : i);
+  }
+  return h;
+}
+
+extern "C" void fc_ingest_destroy(fc_ingest* h) { delete h; }
+
+extern "C" int64_t fc_ingest_parse(fc_ingest* h, const char* text, int64_t nbytes, int32_t final, fc_ingest_out* o) {
+  if (!h || !text || !o || nbytes < 0) return FC_E_ARG;
+  Ingest& g = h->g;
+  const fc_ingest_params& P = g.p;
+  const int eff = P.asize - P.margin;
+  o->n_rows = 0;
+  o->n_complex = 0;
+  o->n_fragments = 0;
+  o->max_l = 0;
+  for (int k = 0; k < 8; ++k) o->counters[k] = 0;
+  enum { C_TOTAL_MATES, C_UNMAPPED, C_UNSPLICED, C_TOO_SHORT, C_CIRC_NOT_UNIQ, C_LIN_NOT_UNIQ };
+
+  std::vector<Rec> frag;       // mapped records of the current fragment (first record regardless of its flag)
+  frag.reserve(8);
+  int64_t frag_start = 0;      // byte offset of the first line of the current fragment
+  int64_t frag_unmapped = 0;   // unmapped records skipped inside the current fragment's byte range
+  bool frag_switch = false;    // a mate switch happened
+  bool have_frag = false;
+  int64_t consumed = 0;
+
+  auto finish = [&](int64_t frag_end) -> bool {
+    // returns false when the output arrays are full (the fragment is then NOT consumed)
+    const size_t nrec = frag.size();
+    bool complex = frag_switch || nrec > 2;
+    for (const Rec& r : frag) complex = complex || !r.ok;
+    const Rec& p = frag[0];
+    double add[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool row = false;
+    const Rec *A = nullptr, *B = nullptr;
+    int q_start = 0, q_end = 0;
+    bool backsplice = false;
+    if (!complex) {
+      add[C_TOTAL_MATES] += 1;
+      add[C_UNMAPPED] += (double)frag_unmapped;
+      bool proper2 = false;
+      if (nrec == 2) {
+        const Rec& s = frag[1];
+        proper2 = s.tid == p.tid && ((s.flag ^ p.flag) & 0x10) == 0;
+      }
+      if (!proper2) {
+        add[C_UNSPLICED] += 1;
+      } else {
+        const Rec& s = frag[1];
+        if (!p.has_seq || !s.has_seq || !p.has_cigar || !s.has_cigar || (p.flag & 0x4)) {
+          complex = true;  // python raises on these, keep its behaviour
+        } else {
+          const Rec* a = &p;
+          const Rec* b = &s;
+          if (s.clip_start < p.clip_start) { a = &s; b = &p; }
+          const int la = a->qlen, lb = b->qlen;
+          if (la < P.asize || lb < P.asize) {
+            add[C_TOO_SHORT] += 1;
+          } else {
+            A = a;
+            B = b;
+            q_start = a->clip_start < b->clip_start ? a->clip_start : b->clip_start;
+            const int ea = a->clip_start + la, eb = b->clip_start + lb;
+            q_end = ea > eb ? ea : eb;
+            backsplice = (B->pos - A->aend) < 0;
+            if (P.nolinear && !backsplice) {
+              // fragment without back-splice candidates is dropped before record_hits (find_circ.py:1568-1569)
+            } else if (!A->has_AS || !B->has_AS) {
+              complex = true;
+            } else {
+              const int ua = A->has_XS ? A->AS - A->XS : A->AS, ub = B->has_XS ? B->AS - B->XS : B->AS;
+              const int uniq = ua < ub ? ua : ub;
+              if (uniq < P.min_uniq_qual) add[backsplice ? C_CIRC_NOT_UNIQ : C_LIN_NOT_UNIQ] += 1;
+              else row = true;
+            }
+          }
+        }
+      }
+    }
+    int gid = -1;
+    if (row) {
+      gid = (A->tid >= 0 && A->tid < (int)g.tid2gid.size()) ? g.tid2gid[A->tid] : -1;
+      if (gid < 0) { complex = true; row = false; }
+    }
+    if (complex) {
+      if (o->n_complex >= o->cap_complex) return false;
+      o->cx_start[o->n_complex] = frag_start;
+      o->cx_end[o->n_complex] = frag_end;
+      o->cx_seq[o->n_complex] = g.frag_seq;
+      o->n_complex++;
+    } else {
+      if (row) {
+        if (o->n_rows >= o->cap) return false;
+        const int64_t i = o->n_rows;
+        const int plen = (int)p.seq.size();
+        int qs = q_start < plen ? q_start : plen, qe = q_end < plen ? q_end : plen;
+        if (qe < qs) qe = qs;
+        const int L = qe - qs;
+        const int l = L - 2 * eff;
+        sv internal;
+        if (eff > 0 && L - eff > eff) internal = p.seq.substr((size_t)(qs + eff), (size_t)(L - 2 * eff));
+        if ((int)((internal.size() + 31) / 32) > o->n_words) {
+          // read longer than the caller's plane buffer: let the python path deal with it
+          if (o->n_complex >= o->cap_complex) return false;
+          o->cx_start[o->n_complex] = frag_start;
+          o->cx_end[o->n_complex] = frag_end;
+          o->cx_seq[o->n_complex] = g.frag_seq;
+          o->n_complex++;
+          for (int k = 0; k < 8; ++k) add[k] = 0;
+          row = false;
+        } else {
+          o->chrom[i] = gid;
+          o->a_start[i] = A->pos + eff;
+          o->b_end[i] = B->aend - eff;
+          o->l[i] = l;
+          bool any_n = false;
+          pack_planes(internal, o->n_words, o->cap, i, o->rlo, o->rhi, o->rn, any_n);
+          o->flags[i] = (uint8_t)((backsplice ? 1 : 0) | ((p.flag & 0x10) ? 2 : 0) | (any_n ? 4 : 0));
+          o->wden[i] = 1;
+          const int qa = A->AS - (A->has_XS ? A->XS : 0), qb = B->AS - (B->has_XS ? B->XS : 0);
+          o->q_a[i] = (int16_t)(qa < -32768 ? -32768 : (qa > 32767 ? 32767 : qa));
+          o->q_b[i] = (int16_t)(qb < -32768 ? -32768 : (qb > 32767 ? 32767 : qb));
+          o->read_hash[i] = fc_hash_read(reinterpret_cast<const uint8_t*>(p.seq.data()), (int64_t)p.seq.size(), nullptr);
+          o->qname_hash[i] = fc_hash_bytes(reinterpret_cast<const uint8_t*>(p.qname.data()), (int64_t)p.qname.size());
+          o->frag_seq[i] = g.frag_seq;
+          o->qname_off[i] = p.qname.data() - text;
+          o->qname_len[i] = (int32_t)p.qname.size();
+          o->seq_off[i] = p.seq.data() - text;
+          o->seq_len[i] = (int32_t)p.seq.size();
+          o->qual_off[i] = p.has_qual ? p.qual.data() - text : 0;
+          o->qual_len[i] = p.has_qual ? (int32_t)p.qual.size() : -1;
+          if (l > o->max_l) o->max_l = l;
+          o->n_rows++;
+        }
+      }
+      for (int k = 0; k < 8; ++k) o->counters[k] += add[k];
+    }
+    o->n_fragments++;
+    g.frag_seq++;
+    return true;
+  };
+
+  int64_t pos = 0;
+  Rec r;
+  while (pos < nbytes) {
+    const char* nl = (const char*)memchr(text + pos, '\n', (size_t)(nbytes - pos));
+    int64_t line_end;
+    if (!nl) {
+      if (!final) break;  // incomplete last line: wait for more text
+      line_end = nbytes;
+    } else {
+      line_end = (nl - text) + 1;
+    }
+    const int64_t line_off = pos;
+    const int64_t line_len = line_end - pos;
+    pos = line_end;
+    // skip header and blank lines
+    if (text[line_off] == '@' || line_len <= 1 || (line_len == 2 && text[line_off] == '\r')) {
+      if (!have_frag) consumed = pos;
+      continue;
+    }
+    g.parse_line(text, line_off, line_len, r);
+    if (!have_frag) {
+      frag.clear();
+      frag.push_back(r);
+      frag_start = line_off;
+      frag_unmapped = 0;
+      frag_switch = false;
+      have_frag = true;
+      g.first_record = false;
+      continue;
+    }
+    if (r.ok && (r.flag & 0x4)) {  // unmapped records after the first are counted and skipped (find_circ.py:1466-1467)
+      frag_unmapped++;
+      continue;
+    }
+    const Rec& p = frag[0];
+    if (r.ok && p.ok && r.qname == p.qname) {
+      if (((r.flag ^ frag.back().flag) & 0x40) != 0 || ((r.flag ^ p.flag) & 0x40) != 0) frag_switch = true;
+      frag.push_back(r);
+      continue;
+    }
+    if (!r.ok || !p.ok) {
+      // unparsable line: make the whole neighbourhood complex and let python report it
+      frag_switch = true;
+      if (!r.ok && p.ok) {
+        frag.push_back(r);
+        continue;
+      }
+    }
+    // a new fragment starts at this line: the previous one is complete
+    if (!finish(line_off)) {
+      // output full: stop before the fragment that did not fit
+      return frag_start;
+    }
+    consumed = line_off;
+    frag.clear();
+    frag.push_back(r);
+    frag_start = line_off;
+    frag_unmapped = 0;
+    frag_switch = false;
+  }
+  if (final && have_frag && pos >= nbytes) {
+    if (!finish(nbytes)) return frag_start;
+    consumed = nbytes;
+    have_frag = false;
+  }
+  return consumed;
+}

@@ -156,7 +156,7 @@ extern "C" int fc_scan(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs* pr,
   }
   fc::ScanCfg cfg{p->margin, p->maxdist, p->noncanonical, p->strandpref};
   fc::GenomeView g = ctx->genome.view();
-  fc::ReadView rv{pr->d_rlo, pr->d_rhi, pr->d_rn, pr->n, pr->n_words};
+  fc::ReadView rv{pr->d_rlo, pr->d_rhi, pr->d_rn, pr->n, pr->n_words, pr->plane_stride > 0 ? pr->plane_stride : pr->n};
 #define FC_SCAN_LAUNCH_BS(NP, T, BS, MB)                                                                               \
   scan_kernel<NP, T, BS, MB><<<(unsigned)((pr->n + BS - 1) / BS), BS, 0, st>>>(g, cfg, rv, pr->d_chrom, pr->d_a_start,   \
                                                                                pr->d_b_end, pr->d_l, pr->d_flags, d_out)
@@ -190,7 +190,7 @@ extern "C" int fc_scan_ties(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs
   if (pr->n == 0) return FC_OK;
   fc::ScanCfg cfg{p->margin, p->maxdist, p->noncanonical, p->strandpref};
   int threads = 128;
-  fc::ReadView rv{pr->d_rlo, pr->d_rhi, pr->d_rn, pr->n, pr->n_words};
+  fc::ReadView rv{pr->d_rlo, pr->d_rhi, pr->d_rn, pr->n, pr->n_words, pr->plane_stride > 0 ? pr->plane_stride : pr->n};
   ties_kernel<<<(unsigned)((pr->n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
       ctx->genome.view(), cfg, rv, pr->d_chrom, pr->d_a_start, pr->d_b_end, pr->d_l, pr->d_flags, d_hits, d_tie_off,
       d_ties);
@@ -247,6 +247,7 @@ extern "C" int fc_scan_host(fc_ctx* ctx, const fc_scan_params* p, int64_t n, con
   pr.d_rn = d_rn;
   pr.n_words = n_words;
   pr.max_l = max_l;
+  pr.plane_stride = 0;
   rc = fc_scan(ctx, p, &pr, d_out, st);
   if (rc) return rc;
   FC_CUDA(ctx, cudaMemcpyAsync(h_out, d_out, sizes[8], cudaMemcpyDeviceToHost, st));
@@ -262,6 +263,16 @@ extern "C" int fc_batch_host(fc_ctx* ctx, const fc_scan_params* p, int64_t n, co
                              const uint8_t* h_ascii, int32_t stride, const uint8_t* h_wden, const int16_t* h_q_a,
                              const int16_t* h_q_b, const uint64_t* h_read_hash, const uint64_t* h_qname_hash,
                              uint64_t idx_base, int32_t emit, fc_hit* h_out) {
+  return fc_batch_host_idx(ctx, p, n, h_chrom, h_a_start, h_b_end, h_l, h_flags, h_ascii, stride, h_wden, h_q_a, h_q_b,
+                           h_read_hash, h_qname_hash, nullptr, idx_base, emit, h_out);
+}
+
+extern "C" int fc_batch_host_idx(fc_ctx* ctx, const fc_scan_params* p, int64_t n, const int32_t* h_chrom,
+                                 const int32_t* h_a_start, const int32_t* h_b_end, const int32_t* h_l,
+                                 const uint8_t* h_flags, const uint8_t* h_ascii, int32_t stride, const uint8_t* h_wden,
+                                 const int16_t* h_q_a, const int16_t* h_q_b, const uint64_t* h_read_hash,
+                                 const uint64_t* h_qname_hash, const uint64_t* h_idx, uint64_t idx_base, int32_t emit,
+                                 fc_hit* h_out) {
   if (!ctx || !p || n < 0) return FC_E_ARG;
   if (n == 0) return FC_OK;
   FC_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -303,12 +314,24 @@ extern "C" int fc_batch_host(fc_ctx* ctx, const fc_scan_params* p, int64_t n, co
   pr.d_rn = (const uint32_t*)ctx->host_path[14].p;
   pr.n_words = n_words;
   pr.max_l = max_l;
+  pr.plane_stride = 0;
   rc = fc_scan(ctx, p, &pr, (fc_hit*)dp[8], st);
   if (rc) return rc;
+  ctx->last_has_idx = false;
+  if (h_idx) {
+    FC_CUDA(ctx, ctx->host_path[15].reserve(8 * N + (size_t)n + 64, st, false, 0));
+    FC_CUDA(ctx, cudaMemcpyAsync(ctx->host_path[15].p, h_idx, 8 * N, cudaMemcpyHostToDevice, st));
+    ctx->last_has_idx = true;
+  }
   if (emit) {
     if (!h_wden || !h_q_a || !h_q_b || !h_read_hash || !h_qname_hash) return fc_fail(ctx, FC_E_ARG, "emit needs the payload arrays");
-    rc = fc_agg_emit(ctx, n, (const fc_hit*)dp[8], pr.d_chrom, pr.d_flags, (const uint8_t*)dp[9], (const int16_t*)dp[10],
-                     (const int16_t*)dp[11], (const uint64_t*)dp[12], (const uint64_t*)dp[13], nullptr, idx_base, st);
+    if (h_idx)
+      rc = fc_agg_emit_idx(ctx, n, (const fc_hit*)dp[8], pr.d_chrom, pr.d_flags, (const uint8_t*)dp[9], (const int16_t*)dp[10],
+                           (const int16_t*)dp[11], (const uint64_t*)dp[12], (const uint64_t*)dp[13], nullptr,
+                           (const uint64_t*)ctx->host_path[15].p, st);
+    else
+      rc = fc_agg_emit(ctx, n, (const fc_hit*)dp[8], pr.d_chrom, pr.d_flags, (const uint8_t*)dp[9], (const int16_t*)dp[10],
+                       (const int16_t*)dp[11], (const uint64_t*)dp[12], (const uint64_t*)dp[13], nullptr, idx_base, st);
     if (rc) return rc;
   }
   if (h_out) FC_CUDA(ctx, cudaMemcpyAsync(h_out, dp[8], sizes[8], cudaMemcpyDeviceToHost, st));
@@ -329,17 +352,27 @@ extern "C" int fc_batch_emit_host(fc_ctx* ctx, const uint8_t* h_mask, uint64_t i
   cudaStream_t st = ctx->own_stream;
   const int64_t n = ctx->last_n;
   uint8_t* d_mask = nullptr;
+  const uint64_t* d_idx = ctx->last_has_idx ? (const uint64_t*)ctx->host_path[15].p : nullptr;
   if (h_mask) {
-    FC_CUDA(ctx, ctx->host_path[15].reserve((size_t)n, st, false, 0));
-    d_mask = (uint8_t*)ctx->host_path[15].p;
+    // host_path[15] = [idx (8n bytes, optional) | mask (n bytes)]
+    FC_CUDA(ctx, ctx->host_path[15].reserve(8 * (size_t)n + (size_t)n + 64, st, true, ctx->last_has_idx ? 8 * (size_t)n : 0));
+    d_idx = ctx->last_has_idx ? (const uint64_t*)ctx->host_path[15].p : nullptr;
+    d_mask = (uint8_t*)ctx->host_path[15].p + 8 * (size_t)n;
     FC_CUDA(ctx, cudaMemcpyAsync(d_mask, h_mask, (size_t)n, cudaMemcpyHostToDevice, st));
   }
   void** dp = nullptr;
   (void)dp;
-  int rc = fc_agg_emit(ctx, n, (const fc_hit*)ctx->host_path[8].p, ctx->last_pairs.d_chrom, ctx->last_pairs.d_flags,
-                       (const uint8_t*)ctx->host_path[9].p, (const int16_t*)ctx->host_path[10].p,
-                       (const int16_t*)ctx->host_path[11].p, (const uint64_t*)ctx->host_path[12].p,
-                       (const uint64_t*)ctx->host_path[13].p, d_mask, idx_base, st);
+  int rc;
+  if (d_idx)
+    rc = fc_agg_emit_idx(ctx, n, (const fc_hit*)ctx->host_path[8].p, ctx->last_pairs.d_chrom, ctx->last_pairs.d_flags,
+                         (const uint8_t*)ctx->host_path[9].p, (const int16_t*)ctx->host_path[10].p,
+                         (const int16_t*)ctx->host_path[11].p, (const uint64_t*)ctx->host_path[12].p,
+                         (const uint64_t*)ctx->host_path[13].p, d_mask, d_idx, st);
+  else
+    rc = fc_agg_emit(ctx, n, (const fc_hit*)ctx->host_path[8].p, ctx->last_pairs.d_chrom, ctx->last_pairs.d_flags,
+                     (const uint8_t*)ctx->host_path[9].p, (const int16_t*)ctx->host_path[10].p,
+                     (const int16_t*)ctx->host_path[11].p, (const uint64_t*)ctx->host_path[12].p,
+                     (const uint64_t*)ctx->host_path[13].p, d_mask, idx_base, st);
   if (rc) return rc;
   FC_CUDA(ctx, cudaStreamSynchronize(st));
   return FC_OK;
@@ -362,5 +395,76 @@ extern "C" int fc_batch_ties_host(fc_ctx* ctx, const fc_scan_params* p, const in
   if (rc) return rc;
   FC_CUDA(ctx, cudaMemcpyAsync(h_ties, tb.p, (size_t)total * sizeof(fc_hit), cudaMemcpyDeviceToHost, st));
   FC_CUDA(ctx, cudaStreamSynchronize(st));
+  return FC_OK;
+}
+
+// rows that arrive with their internal read part already packed (native ingest): no ASCII upload, no pack kernel
+extern "C" int fc_batch_host_planes(fc_ctx* ctx, const fc_scan_params* p, int64_t n, const int32_t* h_chrom,
+                                    const int32_t* h_a_start, const int32_t* h_b_end, const int32_t* h_l,
+                                    const uint8_t* h_flags, const uint32_t* h_rlo, const uint32_t* h_rhi,
+                                    const uint32_t* h_rn, int32_t n_words, int64_t plane_stride, int32_t max_l,
+                                    const uint8_t* h_wden, const int16_t* h_q_a, const int16_t* h_q_b,
+                                    const uint64_t* h_read_hash, const uint64_t* h_qname_hash, const uint64_t* h_idx,
+                                    uint64_t idx_base, int32_t emit, fc_hit* h_out) {
+  if (!ctx || !p || n < 0 || n_words < 1 || plane_stride < n) return FC_E_ARG;
+  if (n == 0) return FC_OK;
+  FC_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->own_stream;
+  const size_t N = (size_t)n;
+  size_t sizes[14] = {4 * N, 4 * N, 4 * N, 4 * N, N + 4, 16, 4 * N * n_words, 4 * N * n_words,
+                      sizeof(fc_hit) * N, N, 2 * N, 2 * N, 8 * N, 8 * N};
+  for (int k = 0; k < 14; ++k) FC_CUDA(ctx, ctx->host_path[k].reserve(sizes[k], st, false, 0));
+  FC_CUDA(ctx, ctx->host_path[14].reserve(sizes[6], st, false, 0));
+  void* dp[15];
+  for (int k = 0; k < 15; ++k) dp[k] = ctx->host_path[k].p;
+  const bool payload = h_wden && h_q_a && h_q_b && h_read_hash && h_qname_hash;
+  const void* src[14] = {h_chrom, h_a_start, h_b_end, h_l, h_flags, nullptr, nullptr, nullptr, nullptr,
+                         h_wden, h_q_a, h_q_b, h_read_hash, h_qname_hash};
+  for (int k = 0; k < 14; ++k) {
+    if (!src[k]) continue;
+    FC_CUDA(ctx, cudaMemcpyAsync(dp[k], src[k], k == 4 ? N : sizes[k], cudaMemcpyHostToDevice, st));
+  }
+  // planes: word rows of n entries each (the host arrays may be strided wider)
+  const uint32_t* hp[3] = {h_rlo, h_rhi, h_rn};
+  void* dpl[3] = {dp[6], dp[7], dp[14]};
+  for (int k = 0; k < 3; ++k)
+    FC_CUDA(ctx, cudaMemcpy2DAsync(dpl[k], 4 * N, hp[k], 4 * (size_t)plane_stride, 4 * N, (size_t)n_words, cudaMemcpyHostToDevice, st));
+  fc_pairs pr;
+  pr.n = n;
+  pr.d_chrom = (const int32_t*)dp[0];
+  pr.d_a_start = (const int32_t*)dp[1];
+  pr.d_b_end = (const int32_t*)dp[2];
+  pr.d_l = (const int32_t*)dp[3];
+  pr.d_flags = (const uint8_t*)dp[4];
+  pr.d_rlo = (const uint32_t*)dp[6];
+  pr.d_rhi = (const uint32_t*)dp[7];
+  pr.d_rn = (const uint32_t*)dp[14];
+  pr.n_words = n_words;
+  pr.max_l = max_l;
+  pr.plane_stride = 0;
+  int rc = fc_scan(ctx, p, &pr, (fc_hit*)dp[8], st);
+  if (rc) return rc;
+  uint64_t* d_idx = nullptr;
+  if (h_idx) {
+    FC_CUDA(ctx, ctx->host_path[15].reserve(8 * N, st, false, 0));
+    d_idx = (uint64_t*)ctx->host_path[15].p;
+    FC_CUDA(ctx, cudaMemcpyAsync(d_idx, h_idx, 8 * N, cudaMemcpyHostToDevice, st));
+  }
+  if (emit) {
+    if (!payload) return fc_fail(ctx, FC_E_ARG, "emit needs the payload arrays");
+    if (d_idx)
+      rc = fc_agg_emit_idx(ctx, n, (const fc_hit*)dp[8], pr.d_chrom, pr.d_flags, (const uint8_t*)dp[9], (const int16_t*)dp[10],
+                           (const int16_t*)dp[11], (const uint64_t*)dp[12], (const uint64_t*)dp[13], nullptr, d_idx, st);
+    else
+      rc = fc_agg_emit(ctx, n, (const fc_hit*)dp[8], pr.d_chrom, pr.d_flags, (const uint8_t*)dp[9], (const int16_t*)dp[10],
+                       (const int16_t*)dp[11], (const uint64_t*)dp[12], (const uint64_t*)dp[13], nullptr, idx_base, st);
+    if (rc) return rc;
+  }
+  if (h_out) FC_CUDA(ctx, cudaMemcpyAsync(h_out, dp[8], sizes[8], cudaMemcpyDeviceToHost, st));
+  FC_CUDA(ctx, cudaStreamSynchronize(st));
+  ctx->last_n = n;
+  ctx->last_pairs = pr;
+  ctx->last_has_payload = payload;
+  ctx->last_has_idx = h_idx != nullptr;
   return FC_OK;
 }

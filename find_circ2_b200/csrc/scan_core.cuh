@@ -185,12 +185,13 @@ struct ReadView {
   const uint32_t* rlo;  // word-major: word w of pair i at [w*n + i], base j in word j>>5, bit j&31
   const uint32_t* rhi;
   const uint32_t* rn;
-  int64_t n;
-  int32_t n_words;
+  int64_t n;       // pairs
+  int32_t n_words; // words per pair and plane
+  int64_t stride;  // distance (in words) between word w and word w+1 of one pair (>= n)
 };
 
 FC_HD int rcode(const ReadView& rv, int64_t i, int j, bool has_n) {
-  const int64_t a = (int64_t)(j >> 5) * rv.n + i;
+  const int64_t a = (int64_t)(j >> 5) * rv.stride + i;
   const uint32_t sh = (uint32_t)(j & 31);
   if (has_n && ((ldg32(rv.rn + a) >> sh) & 1u)) return 4;
   return (int)(((ldg32(rv.rlo + a) >> sh) & 1u) | (((ldg32(rv.rhi + a) >> sh) & 1u) << 1));
@@ -321,9 +322,9 @@ FC_HD void scan_planes(const ScanCfg& cfg, const Window<NP>& A, const Window<NP>
 #pragma unroll
   for (int k = 0; k < NP; ++k) {
     const bool have = k < rv.n_words;
-    rlo[k] = have ? ldg32(rv.rlo + (int64_t)k * rv.n + i) : 0u;
-    rhi[k] = have ? ldg32(rv.rhi + (int64_t)k * rv.n + i) : 0u;
-    rnn[k] = (WITH_N && read_n && have) ? ldg32(rv.rn + (int64_t)k * rv.n + i) : 0u;
+    rlo[k] = have ? ldg32(rv.rlo + (int64_t)k * rv.stride + i) : 0u;
+    rhi[k] = have ? ldg32(rv.rhi + (int64_t)k * rv.stride + i) : 0u;
+    rnn[k] = (WITH_N && read_n && have) ? ldg32(rv.rn + (int64_t)k * rv.stride + i) : 0u;
   }
   // splice signal at split position x (bit x&31 of word x>>5), codes A=00 C=01 G=10 T=11 (hi,lo):
   //   GT..AG: A[x]=G A[x+1]=T B[x]=A B[x+1]=G ;  CT..AC: A[x]=C A[x+1]=T B[x]=A B[x+1]=C     (find_circ.py:924-954)

@@ -129,7 +129,7 @@ class Engine:
         return out
 
     def batch_host(self, chrom, a_start, b_end, l, flags, internal, wden, q_a, q_b, read_hash, qname_hash, idx_base,
-                   emit=True, out: Optional[np.ndarray] = None, want_hits=True) -> Optional[np.ndarray]:
+                   emit=True, out: Optional[np.ndarray] = None, want_hits=True, idx=None) -> Optional[np.ndarray]:
         """scan one batch and append its junction records to the device aggregator (host buffers in, hits out)"""
         n = len(chrom)
         if want_hits and out is None:
@@ -144,9 +144,25 @@ class Engine:
             (chrom, np.int32), (a_start, np.int32), (b_end, np.int32), (l, np.int32), (flags, np.uint8))]
         pay = [np.ascontiguousarray(x, dtype=t) for x, t in (
             (wden, np.uint8), (q_a, np.int16), (q_b, np.int16), (read_hash, np.uint64), (qname_hash, np.uint64))]
-        self._check(self.lib.fc_batch_host(
+        h_idx = None if idx is None else np.ascontiguousarray(idx, dtype=np.uint64)
+        self._check(self.lib.fc_batch_host_idx(
             self.h, C.byref(self.params), n, *[x.ctypes.data for x in a], internal.ctypes.data, stride,
-            *[x.ctypes.data for x in pay], int(idx_base), int(bool(emit)), out.ctypes.data if want_hits else None))
+            *[x.ctypes.data for x in pay], None if h_idx is None else h_idx.ctypes.data, int(idx_base), int(bool(emit)),
+            out.ctypes.data if want_hits else None))
+        return out
+
+    def batch_host_planes(self, n, chrom, a_start, b_end, l, flags, rlo, rhi, rn, n_words, plane_stride, max_l, wden, q_a, q_b,
+                          read_hash, qname_hash, idx=None, idx_base=0, emit=True, out: Optional[np.ndarray] = None):
+        """rows whose internal read part is already packed as bit planes (native ingest); arrays may be longer than n"""
+        if out is None:
+            out = np.zeros(n, dtype=HIT_DTYPE)
+        if n == 0:
+            return out
+        self._check(self.lib.fc_batch_host_planes(
+            self.h, C.byref(self.params), n, chrom.ctypes.data, a_start.ctypes.data, b_end.ctypes.data, l.ctypes.data,
+            flags.ctypes.data, rlo.ctypes.data, rhi.ctypes.data, rn.ctypes.data, int(n_words), int(plane_stride), int(max_l),
+            wden.ctypes.data, q_a.ctypes.data, q_b.ctypes.data, read_hash.ctypes.data, qname_hash.ctypes.data,
+            None if idx is None else idx.ctypes.data, int(idx_base), int(bool(emit)), out.ctypes.data))
         return out
 
     # ------------------------------------------------------------------ scan, device buffers (torch tensors)
@@ -169,7 +185,7 @@ class Engine:
 
     def make_pairs(self, n, d_chrom, d_a_start, d_b_end, d_l, d_flags, d_planes, n_words, max_l) -> Pairs:
         lo, hi, nn = self.plane_ptrs(d_planes, n, n_words)
-        return Pairs(n, ptr(d_chrom), ptr(d_a_start), ptr(d_b_end), ptr(d_l), ptr(d_flags), lo, hi, nn, n_words, max_l)
+        return Pairs(n, ptr(d_chrom), ptr(d_a_start), ptr(d_b_end), ptr(d_l), ptr(d_flags), lo, hi, nn, n_words, max_l, 0)
 
     def scan(self, pairs: Pairs, d_out, stream=0):
         self._check(self.lib.fc_scan(self.h, C.byref(self.params), C.byref(pairs), ptr(d_out), stream))

@@ -1,0 +1,78 @@
+"""
+ctypes face of the native SAM ingest (csrc/ingest.cu, fc_ingest_*): parses chunks of SAM text into struct-of-arrays rows
+for fragments made of one mate with at most one supplementary record; everything else comes back as byte ranges for the
+python path (pipeline.Run.add_fragment).  Host code only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class IngestParams(C.Structure):
+    _fields_ = [("asize", C.c_int32), ("margin", C.c_int32), ("min_uniq_qual", C.c_int32), ("nolinear", C.c_int32)]
+
+
+_P = C.c_void_p
+
+
+class IngestOut(C.Structure):
+    _fields_ = [
+        ("cap", C.c_int64), ("chrom", _P), ("a_start", _P), ("b_end", _P), ("l", _P), ("flags", _P), ("rlo", _P), ("rhi", _P),
+        ("rn", _P), ("n_words", C.c_int32), ("max_l", C.c_int32), ("wden", _P), ("q_a", _P), ("q_b", _P), ("read_hash", _P),
+        ("qname_hash", _P), ("frag_seq", _P), ("qname_off", _P), ("qname_len", _P), ("seq_off", _P), ("seq_len", _P),
+        ("qual_off", _P), ("qual_len", _P), ("cap_complex", C.c_int64), ("cx_start", _P), ("cx_end", _P), ("cx_seq", _P),
+        ("n_rows", C.c_int64), ("n_complex", C.c_int64), ("n_fragments", C.c_int64), ("counters", C.c_double * 8),
+    ]
+
+
+COUNTER_NAMES = ("total_mates", "unmapped_reads", "unspliced_mates", "seg_too_short_skip", "circ_junc_not_unique",
+                 "lin_junc_not_unique")
+
+
+class NativeIngest(object):
+    def __init__(self, asize, margin, min_uniq_qual, nolinear, names, tid2gid, cap=1 << 18, n_words=8, cap_complex=1 << 16):
+        self.lib = _lib.load()
+        p = IngestParams(asize, margin, min_uniq_qual, int(bool(nolinear)))
+        c_names = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        t2g = np.ascontiguousarray(tid2gid, dtype=np.int32)
+        self.h = self.lib.fc_ingest_create(C.byref(p), len(names), c_names, t2g.ctypes.data)
+        if not self.h:
+            raise RuntimeError("fc_ingest_create failed")
+        self.cap, self.n_words = cap, n_words
+        a = self.a = {}
+        for name, dt in (("chrom", np.int32), ("a_start", np.int32), ("b_end", np.int32), ("l", np.int32), ("flags", np.uint8),
+                         ("wden", np.uint8), ("q_a", np.int16), ("q_b", np.int16), ("read_hash", np.uint64),
+                         ("qname_hash", np.uint64), ("frag_seq", np.int64), ("qname_off", np.int64), ("qname_len", np.int32),
+                         ("seq_off", np.int64), ("seq_len", np.int32), ("qual_off", np.int64), ("qual_len", np.int32)):
+            a[name] = np.zeros(cap, dtype=dt)
+        for name in ("rlo", "rhi", "rn"):
+            a[name] = np.zeros(n_words * cap, dtype=np.uint32)
+        for name in ("cx_start", "cx_end", "cx_seq"):
+            a[name] = np.zeros(cap_complex, dtype=np.int64)
+        o = self.out = IngestOut()
+        o.cap, o.n_words, o.cap_complex = cap, n_words, cap_complex
+        for name, arr in a.items():
+            setattr(o, name, arr.ctypes.data)
+
+    def parse(self, buf: bytes, offset: int, final: bool) -> int:
+        """parse buf[offset:]; returns bytes consumed.  Results are in self.out / self.a until the next call."""
+        base = C.cast(C.c_char_p(buf), C.c_void_p).value
+        n = self.lib.fc_ingest_parse(self.h, base + offset, len(buf) - offset, int(final), C.byref(self.out))
+        if n < 0:
+            raise RuntimeError("fc_ingest_parse failed (%d)" % n)
+        return int(n)
+
+    def close(self):
+        if self.h:
+            self.lib.fc_ingest_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -58,6 +58,7 @@ class Options:
     stdout: Optional[str] = None
     batch_pairs: int = 1 << 18  # anchor pairs per GPU batch (ours)
     device: int = 0
+    native: bool = True  # native (C++) SAM ingest for SAM text files
 
 
 def py2_str(x) -> str:
@@ -112,7 +113,7 @@ class Span(object):
 
 
 class Fragment(object):
-    __slots__ = ("name", "mates", "circ", "lin", "unspliced", "broken", "conditional")
+    __slots__ = ("name", "mates", "circ", "lin", "unspliced", "broken", "conditional", "seq")
 
     def __init__(self, name):
         self.name = name
@@ -204,7 +205,10 @@ class Run(object):
         self.n_fragments = 0
         self.n_pairs_scanned = 0
         self.info: Dict[tuple, JunctionInfo] = {}
-        self.reads_out: List[tuple] = []   # (qname, seq, qual, [keys], flags)
+        self.reads_out: List[tuple] = []   # (fragment ordinal, qname, seq, qual, [keys], flags)
+        self.explicit_idx = False          # native ingest: rows carry their own stream position (fragment ordinal * 64 + k)
+        self.cur_seq = 0
+        self.cur_k = 0
         self.multi_out: List[tuple] = []
         self.t_scan = 0.0
         self.eng.agg_reset()
@@ -213,6 +217,7 @@ class Run(object):
     def _reset_batch(self):
         self.b_chrom, self.b_a, self.b_b, self.b_l, self.b_fl = [], [], [], [], []
         self.b_int, self.b_den, self.b_qa, self.b_qb, self.b_rh, self.b_qh = [], [], [], [], [], []
+        self.b_idx = []
         self.frags = []
         self.b_conditional = False
 
@@ -241,6 +246,9 @@ class Run(object):
         # Hit.add: AS - XS with XS defaulting to 0 (find_circ.py:556-559)
         self.b_qa.append(A.AS - (A.XS or 0))
         self.b_qb.append(B.AS - (B.XS or 0))
+        if self.explicit_idx:
+            self.b_idx.append(self.cur_seq * 64 + min(self.cur_k, 63))
+            self.cur_k += 1
         self.b_rh.append(self.eng.hash_read(sp.primary.seq.encode("latin-1")))
         self.b_qh.append(self.eng.hash_bytes(sp.primary.qname.encode("latin-1")))
 
@@ -248,7 +256,11 @@ class Run(object):
         """process_mate x2 + the head of record_hits (find_circ.py:1492-1526, 1560-1574)"""
         opt, N = self.opt, self.N
         self.n_fragments += 1
+        if not self.explicit_idx:
+            self.cur_seq = self.n_fragments
+        self.cur_k = 0
         fr = Fragment(mate2.primary.qname)
+        fr.seq = self.cur_seq
         for mate in (mate1, mate2):
             if mate is None:
                 continue
@@ -302,7 +314,7 @@ class Run(object):
                 np.array(self.b_den, np.uint8), np.clip(np.array(self.b_qa, np.int64), -32768, 32767).astype(np.int16),
                 np.clip(np.array(self.b_qb, np.int64), -32768, 32767).astype(np.int16),
                 np.array(self.b_rh, np.uint64), np.array(self.b_qh, np.uint64), self.idx_base,
-                emit=not two_step, out=hits)
+                emit=not two_step, out=hits, idx=np.array(self.b_idx, np.uint64) if self.explicit_idx else None)
             self.t_scan += time.perf_counter() - t0
             self.n_pairs_scanned += n
         ties_off = ties = None
@@ -469,7 +481,7 @@ class Run(object):
             fl = tuple(sorted(warns))
             for mate in fr.mates:
                 p = mate.primary
-                self.reads_out.append((p.qname, p.seq, p.qual, tuple(junctions), fl))
+                self.reads_out.append((fr.seq, p.qname, p.seq, p.qual, tuple(junctions), fl))
 
     # ------------------------------------------------------------------ driver
     def process(self, records: Iterable[Alignment]):
@@ -479,6 +491,94 @@ class Run(object):
                 continue
             self.add_fragment(mate1, mate2)
         self.flush()
+
+    def process_native(self, fh, chunk_bytes: int = 64 << 20):
+        """SAM text (binary file object, header included) through the native ingest (csrc/ingest.cu); fragments it does
+        not handle go through add_fragment().  Same results as process(), an order of magnitude less host time."""
+        from .ingest import COUNTER_NAMES, NativeIngest
+        from .samio import _parse_sam_line
+
+        opt, N = self.opt, self.N
+        if opt.allhits or opt.noop:
+            raise ValueError("process_native does not cover --all-hits / --noop")
+        tid2gid = [self.eng._chrom_ids.get(n, -1) for n in self.sam_chroms]
+        name2tid = {n: i for i, n in enumerate(self.sam_chroms)}
+        ing = NativeIngest(opt.asize, opt.margin, opt.min_uniq_qual, opt.nolinear, self.sam_chroms, tid2gid,
+                           cap=max(1024, opt.batch_pairs))
+        self.explicit_idx = True
+        a, o = ing.a, ing.out
+        carry = b""
+        eof = False
+        try:
+            while not eof:
+                chunk = fh.read(chunk_bytes)
+                eof = len(chunk) < chunk_bytes
+                buf = carry + chunk if carry else chunk
+                off = 0
+                while True:
+                    used = ing.parse(buf, off, eof)
+                    n = int(o.n_rows)
+                    self.n_fragments += int(o.n_fragments)
+                    for k, name in enumerate(COUNTER_NAMES):
+                        if o.counters[k]:
+                            N[name] += o.counters[k]
+                    if n:
+                        self._native_rows(buf, off, a, n, int(o.max_l), ing)
+                    for k in range(int(o.n_complex)):
+                        s0, s1 = off + int(a["cx_start"][k]), off + int(a["cx_end"][k])
+                        self.cur_seq = int(a["cx_seq"][k])
+                        lines = buf[s0:s1].decode("latin-1").splitlines(True)
+                        recs = [_parse_sam_line(ln, name2tid, 0) for ln in lines if ln.strip() and not ln.startswith("@")]
+                        nf0 = self.n_fragments
+                        for mate1, mate2 in iter_fragments(recs, N):
+                            self.add_fragment(mate1, mate2)
+                        self.n_fragments = nf0 + 1
+                    off += used
+                    if used == 0 or off >= len(buf):
+                        break
+                    if int(o.n_rows) < ing.cap and int(o.n_complex) < int(o.cap_complex) and not eof:
+                        break  # the rest is an incomplete fragment: wait for the next chunk
+                carry = buf[off:]
+                if eof and carry.strip():
+                    raise ValueError("unparsable trailing SAM text")
+            self.flush()
+        finally:
+            ing.close()
+
+    def _native_rows(self, buf, off, a, n, max_l, ing):
+        """scan + record the rows the native ingest produced (single-span fragments: the evidence logic collapses to
+        'first tie is recorded', find_circ.py:1299-1317, 1351-1378), fully vectorised"""
+        N = self.N
+        idx = (a["frag_seq"][:n].astype(np.uint64) * np.uint64(64))
+        t0 = time.perf_counter()
+        hits = self.eng.batch_host_planes(n, a["chrom"], a["a_start"], a["b_end"], a["l"], a["flags"], a["rlo"], a["rhi"], a["rn"],
+                                          ing.n_words, ing.cap, max(max_l, 0), a["wden"], a["q_a"], a["q_b"], a["read_hash"],
+                                          a["qname_hash"], idx=idx, emit=True)
+        self.t_scan += time.perf_counter() - t0
+        self.n_pairs_scanned += n
+        nh = (hits["w2"] & 0xFFFF) > 0
+        circ = (a["flags"][:n] & 1).astype(bool)
+        for key, cnt in (("circ_spliced", np.count_nonzero(nh & circ)), ("circ_no_bp", np.count_nonzero(~nh & circ)),
+                         ("lin_spliced", np.count_nonzero(nh & ~circ)), ("lin_no_bp", np.count_nonzero(~nh & ~circ))):
+            if cnt:  # the reference's counter dict only holds keys that were incremented (find_circ.py:1146)
+                N[key] += float(cnt)
+        rows = np.nonzero(nh)[0]
+        if len(rows) == 0:
+            return
+        chrom = a["chrom"][rows].tolist()
+        start = hits["start"][rows].tolist()
+        end = hits["end"][rows].tolist()
+        strand = np.where(hits["w3"][rows] & 1, "-", "+").tolist()
+        kind = (1 - (a["flags"][rows] & 1)).tolist()
+        seqs = a["frag_seq"][rows].tolist()
+        qo, ql = (a["qname_off"][rows] + off).tolist(), a["qname_len"][rows].tolist()
+        so, sl = (a["seq_off"][rows] + off).tolist(), a["seq_len"][rows].tolist()
+        uo, ul = (a["qual_off"][rows] + off).tolist(), a["qual_len"][rows].tolist()
+        out = self.reads_out
+        for k in range(len(rows)):
+            qual = None if ul[k] < 0 else buf[uo[k]:uo[k] + ul[k]].decode("latin-1")
+            out.append((seqs[k], buf[qo[k]:qo[k] + ql[k]].decode("latin-1"), buf[so[k]:so[k] + sl[k]].decode("latin-1"), qual,
+                        ((chrom[k], start[k], end[k], strand[k], kind[k]),), ()))
 
     # ------------------------------------------------------------------ outputs
     def finalize(self, dist=None, torch_dev=None):
@@ -586,7 +686,9 @@ class Run(object):
         """write_read (find_circ.py:1442-1447)"""
         names = self._names(self.junctions)
         out = []
-        for qname, seq, qual, keys, flags in self.reads_out:
+        if self.explicit_idx:
+            self.reads_out.sort(key=lambda e: e[0])  # native + python paths interleave: restore stream order (stable)
+        for _, qname, seq, qual, keys, flags in self.reads_out:
             head = "%s %s %s" % (qname, ",".join(sorted(names[k] for k in keys)), ",".join(flags))
             out.append("@%s\n%s\n+%s\n%s\n" % (head, seq, head, qual))
         return "".join(out)

@@ -239,3 +239,17 @@ def open_alignments(path: Optional[str]):
     if path.endswith("sam"):
         return read_sam(open(path))
     return read_bam(open(path, "rb"))
+
+
+def sam_header_names(path: str) -> List[str]:
+    """@SQ names of a SAM text file (the native ingest parses the body itself)"""
+    names = []
+    with open(path, "rb") as fh:
+        for line in fh:
+            if not line.startswith(b"@"):
+                break
+            if line.startswith(b"@SQ"):
+                for x in line.rstrip(b"\r\n").split(b"\t")[1:]:
+                    if x.startswith(b"SN:"):
+                        names.append(x[3:].decode("latin-1"))
+    return names

@@ -81,6 +81,7 @@ typedef struct fc_pairs {
   const uint32_t* d_rn;
   int32_t n_words;
   int32_t max_l; /* upper bound of l over the batch (selects the kernel specialisation) */
+  int64_t plane_stride; /* words between consecutive words of one pair in rlo/rhi/rn; 0 = n */
 } fc_pairs;
 
 /* Result of the scan for one pair: the FIRST best-scoring breakpoint (ties keep ascending split position,
@@ -189,6 +190,22 @@ int fc_batch_host(fc_ctx* ctx, const fc_scan_params* p, int64_t n, const int32_t
                   const uint64_t* h_read_hash, const uint64_t* h_qname_hash, uint64_t idx_base, int32_t emit,
                   fc_hit* h_out);
 
+/* fc_batch_host with an explicit stream position per row (h_idx, may be NULL = idx_base + row) */
+int fc_batch_host_idx(fc_ctx* ctx, const fc_scan_params* p, int64_t n, const int32_t* h_chrom, const int32_t* h_a_start,
+                      const int32_t* h_b_end, const int32_t* h_l, const uint8_t* h_flags, const uint8_t* h_ascii,
+                      int32_t stride, const uint8_t* h_wden, const int16_t* h_q_a, const int16_t* h_q_b,
+                      const uint64_t* h_read_hash, const uint64_t* h_qname_hash, const uint64_t* h_idx, uint64_t idx_base,
+                      int32_t emit, fc_hit* h_out);
+
+/* Same as fc_batch_host for rows whose internal read part is already packed as bit planes (what fc_ingest_parse emits):
+ * h_rlo/h_rhi/h_rn are word-major with `plane_stride` words between the words of one pair; h_idx (may be NULL) gives an
+ * explicit stream position per row instead of idx_base + row. */
+int fc_batch_host_planes(fc_ctx* ctx, const fc_scan_params* p, int64_t n, const int32_t* h_chrom, const int32_t* h_a_start,
+                         const int32_t* h_b_end, const int32_t* h_l, const uint8_t* h_flags, const uint32_t* h_rlo,
+                         const uint32_t* h_rhi, const uint32_t* h_rn, int32_t n_words, int64_t plane_stride, int32_t max_l,
+                         const uint8_t* h_wden, const int16_t* h_q_a, const int16_t* h_q_b, const uint64_t* h_read_hash,
+                         const uint64_t* h_qname_hash, const uint64_t* h_idx, uint64_t idx_base, int32_t emit, fc_hit* h_out);
+
 /* Two-step batches: after fc_batch_host(..., emit = 0) the host inspects the hits and decides which pairs are
  * recorded (find_circ.py:1319-1329: the linear spans of a fragment count only when its back-splices resolved to at most
  * one junction); fc_batch_emit_host records the pairs with h_mask[i] != 0 (NULL = all) from the retained device copy. */
@@ -206,6 +223,10 @@ int fc_agg_emit(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, const int32_t* d_c
                 const uint8_t* d_wden, const int16_t* d_q_a, const int16_t* d_q_b, const uint64_t* d_read_hash,
                 const uint64_t* d_qname_hash, const uint8_t* d_mask /* NULL or per-pair 0/1: record this pair */,
                 uint64_t idx_base, void* stream);
+/* same with an explicit stream position per pair (rows of a batch that are not in stream order) */
+int fc_agg_emit_idx(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, const int32_t* d_chrom, const uint8_t* d_flags,
+                    const uint8_t* d_wden, const int16_t* d_q_a, const int16_t* d_q_b, const uint64_t* d_read_hash,
+                    const uint64_t* d_qname_hash, const uint8_t* d_mask, const uint64_t* d_idx, void* stream);
 int fc_agg_append(fc_ctx* ctx, int64_t n, const fc_jrec* d_recs, void* stream); /* records built elsewhere (other ranks) */
 int fc_agg_append_host(fc_ctx* ctx, int64_t n, const fc_jrec* h_recs);
 /* replace the record buffer by n device records (receive side of the exchange); asynchronous, no host synchronisation */
@@ -230,6 +251,51 @@ int fc_agg_emit_p2p(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, const int32_t*
                     const uint8_t* d_wden, const int16_t* d_q_a, const int16_t* d_q_b, const uint64_t* d_read_hash,
                     const uint64_t* d_qname_hash, const uint8_t* d_mask, uint64_t idx_base, void* stream);
 int fc_agg_reset_async(fc_ctx* ctx, void* stream);
+
+/* ------------------------------------------------------------------ native SAM ingest (host code)
+ * Replaces the pysam record loop, MateSegments and adjacent_segment_pairs (find_circ.py:461-469, 976-1140, 1450-1486) for
+ * fragments that consist of one mate with at most one supplementary record; other fragments are returned as byte ranges
+ * for the python implementation of the same logic.  Rows are ready for fc_batch_host_planes. */
+typedef struct fc_ingest fc_ingest;
+typedef struct fc_ingest_params {
+  int32_t asize, margin, min_uniq_qual, nolinear;
+} fc_ingest_params;
+typedef struct fc_ingest_out {
+  int64_t cap;          /* capacity of the per-row arrays (also the stride of the plane arrays) */
+  int32_t* chrom;       /* genome chromosome id */
+  int32_t* a_start;
+  int32_t* b_end;
+  int32_t* l;
+  uint8_t* flags;
+  uint32_t* rlo;        /* [n_words][cap] */
+  uint32_t* rhi;
+  uint32_t* rn;
+  int32_t n_words;
+  int32_t max_l;        /* out */
+  uint8_t* wden;
+  int16_t* q_a;
+  int16_t* q_b;
+  uint64_t* read_hash;
+  uint64_t* qname_hash;
+  int64_t* frag_seq;    /* ordinal of the fragment in the stream */
+  int64_t* qname_off;   /* byte offsets into the parsed text (for the spliced-reads output) */
+  int32_t* qname_len;
+  int64_t* seq_off;
+  int32_t* seq_len;
+  int64_t* qual_off;
+  int32_t* qual_len;    /* -1: '*' */
+  int64_t cap_complex;
+  int64_t* cx_start;    /* byte ranges of fragments left to the python path */
+  int64_t* cx_end;
+  int64_t* cx_seq;
+  int64_t n_rows, n_complex, n_fragments; /* out */
+  double counters[8];   /* out: total_mates, unmapped_reads, unspliced_mates, seg_too_short_skip, circ_junc_not_unique, lin_junc_not_unique */
+} fc_ingest_out;
+fc_ingest* fc_ingest_create(const fc_ingest_params* p, int32_t n_names, const char* const* names, const int32_t* tid2gid);
+void fc_ingest_destroy(fc_ingest* h);
+/* parses complete fragments out of `text`; returns the number of bytes consumed (the caller re-submits the rest together
+ * with the next chunk; final != 0 flushes the last fragment) or a negative error code */
+int64_t fc_ingest_parse(fc_ingest* h, const char* text, int64_t nbytes, int32_t final, fc_ingest_out* out);
 
 /* ------------------------------------------------------------------ utilities */
 void* fc_pinned_alloc(int64_t bytes);

@@ -30,6 +30,7 @@ class FakeEngine:
         self.og = og
         self.chrom_names = list(og.names)
         self.chrom_sizes = [og.size(n) for n in og.names]
+        self._chrom_ids = {n: i for i, n in enumerate(self.chrom_names)}
         self.g = _G(self.chrom_names, [np.frombuffer(og.seqs[n].encode(), dtype=np.uint8).copy() for n in og.names])
 
     def chrom_id(self, name):
@@ -44,13 +45,31 @@ class FakeEngine:
     def agg_reset(self):
         self.recs = []
 
+    def batch_host_planes(self, n, chrom, a_start, b_end, l, flags, rlo, rhi, rn, n_words, plane_stride, max_l, wden, q_a, q_b,
+                          read_hash, qname_hash, idx=None, idx_base=0, emit=True, out=None):
+        """planes back to ASCII (test double only), then the ASCII path"""
+        lmax = max(int(max_l), 1)
+        internal = np.zeros((n, lmax), dtype=np.uint8)
+        for i in range(n):
+            for j in range(max(int(l[i]), 0)):
+                w, b = j >> 5, j & 31
+                if (int(rn[w * plane_stride + i]) >> b) & 1:
+                    internal[i, j] = ord("N")
+                else:
+                    code = ((int(rlo[w * plane_stride + i]) >> b) & 1) | (((int(rhi[w * plane_stride + i]) >> b) & 1) << 1)
+                    internal[i, j] = b"ACGT"[code]
+        fl = flags[:n].copy() & 0xFB
+        return self.batch_host(chrom[:n].copy(), a_start[:n].copy(), b_end[:n].copy(), l[:n].copy(), fl, internal, wden[:n].copy(),
+                               q_a[:n].copy(), q_b[:n].copy(), read_hash[:n].copy(), qname_hash[:n].copy(), idx_base, emit=emit,
+                               out=out, idx=idx)
+
     def batch_host(self, chrom, a_start, b_end, l, flags, internal, wden, q_a, q_b, read_hash, qname_hash, idx_base, emit=True,
-                   out=None, want_hits=True):
+                   out=None, want_hits=True, idx=None):
         p = self.p
         hits = H.harness_scan(self.g, chrom, a_start, b_end, l, flags, internal, p["margin"], p["maxdist"], p["noncanonical"],
                               p["strandpref"])
         self.last = dict(chrom=chrom, a_start=a_start, b_end=b_end, l=l, flags=flags, internal=internal, wden=wden, q_a=q_a,
-                         q_b=q_b, rh=read_hash, qh=qname_hash, hits=hits)
+                         q_b=q_b, rh=read_hash, qh=qname_hash, hits=hits, idx=idx)
         if emit:
             self.batch_emit(None, idx_base)
         res = hits.view(HIT_DTYPE).reshape(-1)
@@ -70,7 +89,7 @@ class FakeEngine:
             r = np.zeros((), dtype=JREC_DTYPE)
             r["chrom"], r["start"], r["end"] = L["chrom"][i], np.int32(np.uint32(h[0]).astype(np.int32)), np.uint32(h[1]).astype(np.int32)
             r["sk"] = (int(h[3]) & 1) | (0 if back else 2) | ((rh & 1) << 2) | (int(L["wden"][i]) << 8) | (((int(h[3]) >> 1) & 0xFFF) << 16)
-            r["idx"] = idx_base + i
+            r["idx"] = idx_base + i if L.get("idx") is None else int(L["idx"][i])
             r["read_hash"], r["qname_hash"] = rh, int(L["qh"][i])
             r["q_left"], r["q_right"] = (L["q_b"][i], L["q_a"][i]) if back else (L["q_a"][i], L["q_b"][i])
             r["n_hits"], r["dist"], r["ov"] = nh, (int(h[2]) >> 16) & 0xFF, int(h[2]) >> 24
@@ -105,7 +124,7 @@ class FakeEngine:
 
     def agg_finalize(self, stream=0):
         acc = {}
-        for r in self.recs:
+        for r in sorted(self.recs, key=lambda x: int(x["idx"])):  # stream order, whatever the arrival order was
             key = (int(r["chrom"]), int(r["start"]), int(r["end"]), int(r["sk"]) & 3)
             a = acc.setdefault(key, dict(first=int(r["idx"]), w=0.0, b=0.0, n=0, ql=[], qr=[], d=[], o=[], nh=[], rh=set(),
                                          qh=set(), pal=set(), sig=0))

@@ -12,15 +12,18 @@ from fake_engine import FakeEngine
 from oracle import find_circ_oracle as O
 
 
+@pytest.mark.parametrize("native", [False, True], ids=["python-ingest", "native-ingest"])
 @pytest.mark.parametrize("case_dir,ref_dir,argv", golden_cases(), ids=golden_ids())
-def test_host_logic_matches_reference(case_dir, ref_dir, argv):
+def test_host_logic_matches_reference(case_dir, ref_dir, argv, native):
     from find_circ2_b200 import cli
 
     opt = cli.parse_args(["-G", os.path.join(case_dir, "genome.fa")] + argv)[0]
     opt.batch_pairs = 211
     eng = FakeEngine(0, opt.asize, opt.margin, opt.maxdist, opt.noncanonical, opt.strandpref)
     eng.load_genome_fasta(opt.genome)
-    out = cli.run_to_strings(opt, os.path.join(case_dir, "input.sam"), engine=eng)
+    if native and opt.allhits:
+        pytest.skip("--all-hits uses the python ingest")
+    out = cli.run_to_strings(opt, os.path.join(case_dir, "input.sam"), engine=eng, native=native)
     rd = lambda n: open(os.path.join(ref_dir, n)).read()  # noqa: E731
     assert O.canonical_bed(out["circ"]) == O.canonical_bed(rd("circ_splice_sites.bed"))
     assert O.canonical_bed(out["lin"]) == O.canonical_bed(rd("lin_splice_sites.bed"))

@@ -142,7 +142,7 @@ int hh_scan(void* h, int margin, int maxdist, int noncanonical, int strandpref, 
   gv.tile_T = use_tiles ? g->T : 0;
   gv.tile_W = use_tiles ? g->W : 0;
   fc::ScanCfg cfg{margin, maxdist, noncanonical, strandpref};
-  fc::ReadView rv{rlo, rhi, rn, n, n_words};
+  fc::ReadView rv{rlo, rhi, rn, n, n_words, n};
   const int need = max_l + 2;
   const int force = mode == 2;
   switch (gv.tile_T) {
