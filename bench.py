@@ -105,6 +105,22 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
+def ascii_to_planes(internal, n_words):
+    """[n, L] ASCII -> (lo, hi, n) bit planes, word-major [n_words * n] uint32 (the layout of fc_pairs.rlo/rhi/rn)"""
+    n, L = internal.shape
+    code = np.full(internal.shape, 4, dtype=np.uint8)
+    up = internal & 0xDF
+    for k, ch in enumerate(b"ACGT"):
+        code[up == ch] = k
+    out = []
+    for plane in ((code & 1) & (code < 4), ((code >> 1) & 1) & (code < 4), code == 4):
+        bits = np.zeros((n, n_words * 32), dtype=np.uint8)
+        bits[:, :L] = plane
+        words = np.packbits(bits, axis=1, bitorder="little").view(np.uint32)  # [n, n_words]
+        out.append(np.ascontiguousarray(words.T).reshape(-1))
+    return out
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -297,11 +313,21 @@ def run_gpu(args):
     h_hits = h_hits_t.numpy().view(HIT_DTYPE)
     h2d = sum(v[1].nbytes for v in pinned.values())
 
-    def step_e2e():
+    # what the native ingest hands over: the internal read part as bit planes (word-major), 3 x 4 x n_words bytes per pair
+    planes_np = ascii_to_planes(soa["internal"], n_words)
+    pl_pin = [pin(planes_np[k]) for k in range(3)]
+    h2d_planes = sum(v[1].nbytes for k, v in pinned.items() if k != "internal") + sum(v[1].nbytes for v in pl_pin)
+
+    def step_e2e(ascii_reads=False):
         eng.agg_reset()
         p = {k: v[1] for k, v in pinned.items()}
-        eng.batch_host(p["chrom"], p["a_start"], p["b_end"], p["l"], p["flags"], p["internal"], p["wden"], p["q_a"], p["q_b"],
-                       p["read_hash"], p["qname_hash"], idx_base, emit=True, out=h_hits)
+        if ascii_reads:
+            eng.batch_host(p["chrom"], p["a_start"], p["b_end"], p["l"], p["flags"], p["internal"], p["wden"], p["q_a"], p["q_b"],
+                           p["read_hash"], p["qname_hash"], idx_base, emit=True, out=h_hits)
+        else:
+            eng.batch_host_planes(n, p["chrom"], p["a_start"], p["b_end"], p["l"], p["flags"], pl_pin[0][1], pl_pin[1][1],
+                                  pl_pin[2][1], n_words, n, max_l, p["wden"], p["q_a"], p["q_b"], p["read_hash"],
+                                  p["qname_hash"], idx=None, idx_base=idx_base, emit=True, out=h_hits)
         if world > 1:
             parallel.exchange_records(eng, dist, dev, 0, upper_bound=n)
         nj = eng.agg_finalize(0)
@@ -349,6 +375,17 @@ def run_gpu(args):
         nj2, junc = step_e2e()
         e2e_s += time.perf_counter() - t0
     barrier()
+    # the same with ASCII read bases in the host buffers (what the python ingest produces)
+    e2e_ascii_s = 0.0
+    step_e2e(True)
+    for _ in range(max(args.steps // 2, 1)):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step_e2e(True)
+        e2e_ascii_s += time.perf_counter() - t0
+    e2e_ascii_step = e2e_ascii_s / max(args.steps // 2, 1)
+    barrier()
     sampler.stop_flag = True
     sampler.join(timeout=2)
     d2h = n * 16 + int(nj2) * 64
@@ -383,8 +420,11 @@ def run_gpu(args):
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "scan_kernel<NP=3,T=1> (csrc/scan.cu)", "bytes_per_pair": BYTES_PER_PAIR, "peak_source": peak_src},
-            "e2e": {"value": total_pairs / e2e_step, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_step * 1e3},
+            "e2e": {"value": total_pairs / e2e_step, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d_planes), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_step * 1e3,
+                    "call": "fc_batch_host_planes + fc_agg_finalize + fc_agg_fetch (pinned host SoA with bit-plane reads, as csrc/ingest.cu emits them)",
+                    "ascii_reads": {"value": n * world / e2e_ascii_step, "h2d_bytes_per_step": int(h2d), "ms_per_step": e2e_ascii_step * 1e3,
+                                    "call": "fc_batch_host (ASCII read bases, packed on the device)"}},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
         }
