@@ -1065,25 +1065,40 @@ __global__ void emit_p2p_kernel(int64_t n, const fc_hit* __restrict__ hits, cons
       dest = (int)(fc_key_hash(r.chrom, r.start, r.end, r.sk, 0x5bd1e995ULL) % (uint64_t)pv.world);
     }
   }
-  const unsigned lane = threadIdx.x & 31;
-  for (int d = 0; d < pv.world; ++d) {
-    const unsigned m = __ballot_sync(0xffffffffu, accept && dest == d);
-    if (!m) continue;
-    const int leader = __ffs((int)m) - 1;
-    unsigned long long base = 0;
-    if ((int)lane == leader) base = atomicAdd_system(pv.cnt[d], (unsigned long long)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (accept && dest == d) {
-      const unsigned long long pos = base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
-      if (pos < pv.capacity) {
-        uint4* dst = reinterpret_cast<uint4*>(pv.recs[d] + pos);
-        const uint4* src = reinterpret_cast<const uint4*>(&r);
-        dst[0] = src[0];
-        dst[1] = src[1];
-        dst[2] = src[2];
-      } else {
-        atomicAdd(overflow, 1ull);
-      }
+  // slot allocation: ONE system-scope atomic per CTA and destination (a shared counter per rank receives the
+  // allocations of every CTA of every rank; per-warp allocation made the owners' counters the bottleneck at 8 GPUs)
+  __shared__ unsigned int s_cnt[8];
+  __shared__ unsigned long long s_base[8];
+  if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  unsigned int local = 0;
+  {
+    // warp-aggregated shared-memory allocation: rank of this record among the CTA's records for its destination
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned amask = __ballot_sync(0xffffffffu, accept);
+    if (accept) {
+      const unsigned peers = __match_any_sync(amask, dest);
+      const int leader = __ffs((int)peers) - 1;
+      unsigned int wbase = 0;
+      if ((int)lane == leader) wbase = atomicAdd(&s_cnt[dest], (unsigned int)__popc(peers));
+      wbase = __shfl_sync(peers, wbase, leader);
+      local = wbase + (unsigned int)__popc(peers & ((1u << lane) - 1u));
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < pv.world && s_cnt[threadIdx.x])
+    s_base[threadIdx.x] = atomicAdd_system(pv.cnt[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+  __syncthreads();
+  if (accept) {
+    const unsigned long long pos = s_base[dest] + local;
+    if (pos < pv.capacity) {
+      uint4* dst = reinterpret_cast<uint4*>(pv.recs[dest] + pos);
+      const uint4* src = reinterpret_cast<const uint4*>(&r);
+      dst[0] = src[0];
+      dst[1] = src[1];
+      dst[2] = src[2];
+    } else {
+      atomicAdd(overflow, 1ull);
     }
   }
 }
@@ -1148,7 +1163,7 @@ extern "C" int fc_agg_emit_p2p(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, con
   pv.capacity = (unsigned long long)a.p2p_min_capacity;
   pv.world = a.p2p_world;
   unsigned long long* counters = (unsigned long long*)a.counters.p;
-  emit_p2p_kernel<<<nblk(n, 256), 256, 0, st>>>(n, d_hits, d_mask, d_chrom, d_flags, d_wden, d_q_a, d_q_b, d_read_hash,
+  emit_p2p_kernel<<<nblk(n, 1024), 1024, 0, st>>>(n, d_hits, d_mask, d_chrom, d_flags, d_wden, d_q_a, d_q_b, d_read_hash,
                                                 d_qname_hash, idx_base, pv, counters + 4);
   FC_LAUNCH_CHECK(ctx);
   a.n_recs = a.p2p_capacity;  // upper bound; the exact count is the (shared) device counter
