@@ -14,6 +14,7 @@
 //     first idx            min  -> discovery order -> junction name                (:684-686)
 //     n_frags              distinct qname hashes                                   (:584-586)
 //     n_uniq               distinct strand-invariant read hashes (palindromes count half, :588-590)
+#include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -56,6 +57,10 @@ __device__ __forceinline__ U128 cas128(U128* addr, U128 cmp, U128 val) {
       : "memory");
   return old;
 }
+
+static_assert(offsetof(JAcc, cw) == 4 && offsetof(JAcc, cb) == 24 && offsetof(JAcc, cb_other) == 40 && offsetof(JAcc, n_frags) == 64 &&
+                  offsetof(JAcc, n_uniq) == 68 && offsetof(JAcc, first_idx) == 80,
+              "accumulate_kernel's 64-bit pair adds depend on this layout");
 
 __global__ void count_hits_kernel(int64_t n, const fc_hit* __restrict__ hits, const uint8_t* __restrict__ mask,
                                   uint32_t* __restrict__ accept) {
@@ -402,26 +407,28 @@ __global__ void __launch_bounds__(256) accumulate_kernel(int64_t n, const fc_jre
     const uint32_t* w = sm + e * ACC_WORDS;
     if (w[0] == 0u) continue;
     JAcc* a = acc + (w[0] - 1u);
-    atomicAdd(&a->n_spanned, w[1]);
-    if (w[2] & 0xFFFFu) atomicAdd(&a->cw[0], w[2] & 0xFFFFu);
-    if (w[2] >> 16) atomicAdd(&a->cw[1], w[2] >> 16);
-    if (w[3] & 0xFFFFu) atomicAdd(&a->cw[2], w[3] & 0xFFFFu);
-    if (w[3] >> 16) atomicAdd(&a->cw[3], w[3] >> 16);
-    if (w[4] & 0xFFFFu) atomicAdd(&a->cw_other, w[4] & 0xFFFFu);
+    // counters: neighbouring 32-bit fields of JAcc are bumped pairwise with one 64-bit add (the sums stay far below
+    // 2^32, so nothing carries into the upper half)
+    unsigned long long* a64 = reinterpret_cast<unsigned long long*>(a);
+    atomicAdd(a64 + 0, (unsigned long long)w[1] | ((unsigned long long)(w[2] & 0xFFFFu) << 32));        // n_spanned, cw[0]
+    if ((w[2] >> 16) | (w[3] & 0xFFFFu))
+      atomicAdd(a64 + 1, (unsigned long long)(w[2] >> 16) | ((unsigned long long)(w[3] & 0xFFFFu) << 32));  // cw[1], cw[2]
+    if ((w[3] >> 16) | (w[4] & 0xFFFFu))
+      atomicAdd(a64 + 2, (unsigned long long)(w[3] >> 16) | ((unsigned long long)(w[4] & 0xFFFFu) << 32));  // cw[3], cw_other
+    if (w[5]) atomicAdd(a64 + 3, (unsigned long long)(w[5] & 0xFFFFu) | ((unsigned long long)(w[5] >> 16) << 32));  // cb[0], cb[1]
+    if (w[6]) atomicAdd(a64 + 4, (unsigned long long)(w[6] & 0xFFFFu) | ((unsigned long long)(w[6] >> 16) << 32));  // cb[2], cb[3]
     if (w[4] >> 16) atomicAdd(&a->cb_other, w[4] >> 16);
-    if (w[5] & 0xFFFFu) atomicAdd(&a->cb[0], w[5] & 0xFFFFu);
-    if (w[5] >> 16) atomicAdd(&a->cb[1], w[5] >> 16);
-    if (w[6] & 0xFFFFu) atomicAdd(&a->cb[2], w[6] & 0xFFFFu);
-    if (w[6] >> 16) atomicAdd(&a->cb[3], w[6] >> 16);
-    if (w[7] & 0xFFFFu) atomicAdd(&a->n_uniq, w[7] & 0xFFFFu);
+    if (w[8] | (w[7] & 0xFFFFu))
+      atomicAdd(a64 + 8, (unsigned long long)w[8] | ((unsigned long long)(w[7] & 0xFFFFu) << 32));          // n_frags, n_uniq
     if (w[7] >> 16) atomicAdd(&a->n_pal, w[7] >> 16);
-    if (w[8]) atomicAdd(&a->n_frags, w[8]);
+    // extrema: fire-and-forget reductions (a look-before-update variant was measured slower: the loads stall, REDs do not)
     atomicMax(&a->max_ql, (int)w[9]);
     atomicMax(&a->max_qr, (int)w[10]);
     atomicMin(&a->min_dist, w[11]);
     atomicMin(&a->min_ov, w[12]);
     atomicMin(&a->min_nh, w[13]);
-    atomicMin(&a->first_idx, *reinterpret_cast<const unsigned long long*>(&w[14]));
+    const unsigned long long fi = *reinterpret_cast<const unsigned long long*>(&w[14]);
+    atomicMin(&a->first_idx, fi);
   }
 }
 
