@@ -403,6 +403,7 @@ def run_gpu(args):
     else:
         total_pairs = n
 
+    n_rec = eng.agg_n_records() if world == 1 else n
     if rank == 0:
         peak, peak_src = peaks()
         achieved = BYTES_PER_PAIR * n / (scan_step * 1e-3) / 1e9
@@ -420,6 +421,11 @@ def run_gpu(args):
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "scan_kernel<NP=3,T=1> (csrc/scan.cu)", "bytes_per_pair": BYTES_PER_PAIR, "peak_source": peak_src},
+            "roofline_merge": {"bound": "hbm", "kernels": "emit + assign + accumulate + finish (csrc/agg.cu)",
+                               "achieved": (48.0 * n_rec + 64.0 * int(nj)) / (max(ms_step - scan_step, 1e-9) * 1e-3) / 1e9, "peak": peak,
+                               "unit": "GB/s", "frac": (48.0 * n_rec + 64.0 * int(nj)) / (max(ms_step - scan_step, 1e-9) * 1e-3) / 1e9 / peak,
+                               "bytes": "48 B x %d records + 64 B x %d junctions (rank 0)" % (n_rec, int(nj)),
+                               "note": "latency/atomic bound, not bandwidth bound: see profiles/"},
             "e2e": {"value": total_pairs / e2e_step, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d_planes), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_step * 1e3,
                     "call": "fc_batch_host_planes + fc_agg_finalize + fc_agg_fetch (pinned host SoA with bit-plane reads, as csrc/ingest.cu emits them)",
