@@ -2,18 +2,19 @@
 //
 // Replaces SpliceSiteStorage.add / Hit.add and the Hit reductions (/root/reference/find_circ.py:486-600, 657-690):
 // instead of one Python dict insert + list appends per accepted span, accepted spans become 48-byte records
-// (fc_jrec); fc_agg_finalize() sorts them by a 64-bit hash of (chrom,start,end,strand,kind) with a stable CUB radix
-// sort (input order = stream order is preserved inside a junction), verifies that equal hashes mean equal keys,
-// and reduces every run:
+// (fc_jrec) and fc_agg_finalize() reduces them per junction (chrom,start,end,strand,kind):
 //     n_spanned            count                                                   (:543)
 //     n_weighted           sum of weights, exact: weights 1/den with den a power of two are order independent;
-//                          junctions holding any other denominator are re-summed sequentially in stream order (:544)
+//                          inputs holding any other denominator are re-summed sequentially in stream order (:544)
 //     n_uniq_bridges       same, over records with both anchor qualities non-zero  (:561-563)
 //     best_qual_left/right max                                                     (:592-593)
 //     edits/overlap/n_hits min                                                     (:727)
 //     first idx            min  -> discovery order -> junction name                (:684-686)
 //     n_frags              distinct qname hashes                                   (:584-586)
 //     n_uniq               distinct strand-invariant read hashes (palindromes count half, :588-590)
+// Two implementations with identical results: a sort-free one (128-bit CAS hash tables + CTA-level pre-aggregation,
+// default) and a sort-based one (stable CUB radix sort + warp-segmented reduction + sequential float replay, fallback).
+// Multi-GPU: the emit kernel can write records straight into the owner rank's buffer over NVLink (emit_p2p_kernel).
 #include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
@@ -232,16 +233,6 @@ __global__ void reduce_kernel(int64_t n, const fc_jrec* __restrict__ s, const ui
     atomicMin(&a->min_nh, mh);
     atomicMin(&a->first_idx, fi);
   }
-}
-
-// (hash, seg) pairs for the two distinct counts
-__global__ void split_hash_kernel(int64_t n, const fc_jrec* __restrict__ s, const uint32_t* __restrict__ seg_incl,
-                                  uint64_t* __restrict__ rh, uint64_t* __restrict__ qh, uint32_t* __restrict__ seg) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  rh[i] = s[i].read_hash;
-  qh[i] = s[i].qname_hash;
-  seg[i] = seg_incl[i] - 1u;
 }
 
 // ---- distinct counts with exact hash sets (128-bit entries, 128-bit CAS) ----------------------------------------
@@ -546,15 +537,6 @@ __global__ void rank_hist_kernel(int64_t n, const uint64_t* __restrict__ key_sor
 inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 int sort_pairs_u64_u32(fc_ctx* ctx, int64_t n, uint64_t* k_in, uint64_t* k_out, uint32_t* v_in, uint32_t* v_out,
-                       int begin_bit, int end_bit, cudaStream_t st) {
-  size_t tmp = 0;
-  FC_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, v_in, v_out, n, begin_bit, end_bit, st));
-  FC_CUDA(ctx, ctx->agg.cub_tmp.reserve(tmp, st, false, 0));
-  FC_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->agg.cub_tmp.p, tmp, k_in, k_out, v_in, v_out, n, begin_bit, end_bit, st));
-  ctx->launches += 1 + (end_bit - begin_bit + 7) / 8;
-  return FC_OK;
-}
-int sort_pairs_u32_u64(fc_ctx* ctx, int64_t n, uint32_t* k_in, uint32_t* k_out, uint64_t* v_in, uint64_t* v_out,
                        int begin_bit, int end_bit, cudaStream_t st) {
   size_t tmp = 0;
   FC_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, v_in, v_out, n, begin_bit, end_bit, st));
