@@ -289,7 +289,7 @@ def run_gpu(args):
             eng.agg_reset_async(stream)
             parallel.stream_barrier(dist, dev)  # every rank's counter is zero before anybody writes
         else:
-            eng.agg_reset()
+            eng.agg_reset_async(stream)  # stays behind the L2-flush kernel in the stream: no host round trip before the scan
         if ev_scan:
             ev_scan[0].record()
         eng.scan(pairs, hits, stream)

@@ -1,0 +1,123 @@
+"""
+The drop-in as a PROCESS: ./find_circ.py run the way the reference is run (file argument, stdin pipe, BAM input),
+its output directory compared with the reference goldens.  Needs the GPU; the BAM reader itself is also checked on CPU.
+"""
+import gzip
+import os
+import struct
+import subprocess
+import sys
+
+import pytest
+
+from conftest import GOLDEN, ROOT
+from oracle import find_circ_oracle as O
+
+
+def sam_to_bam(sam_path, bam_path):
+    """minimal BAM writer (test helper): one BGZF member per 64 KiB, python's gzip writes valid multi-member files"""
+    names, lens, recs = [], [], []
+    text = ""
+    for line in open(sam_path):
+        if line.startswith("@"):
+            text += line
+            if line.startswith("@SQ"):
+                d = dict(x.split(":", 1) for x in line.rstrip("\n").split("\t")[1:])
+                names.append(d["SN"])
+                lens.append(int(d["LN"]))
+        elif line.strip():
+            recs.append(line.rstrip("\n").split("\t"))
+    out = bytearray(b"BAM\x01" + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", len(names)))
+    for n, ln in zip(names, lens):
+        out += struct.pack("<i", len(n) + 1) + n.encode() + b"\x00" + struct.pack("<i", ln)
+    code = {c: i for i, c in enumerate("=ACMGRSVTWYHKDBN")}
+    ops = {c: i for i, c in enumerate("MIDNSHP=X")}
+    import re
+
+    for f in recs:
+        qname = f[0].encode() + b"\x00"
+        tid = names.index(f[2]) if f[2] != "*" else -1
+        cig = [] if f[5] == "*" else [(int(n), ops[c]) for n, c in re.findall(r"(\d+)([MIDNSHP=X])", f[5])]
+        seq = "" if f[9] == "*" else f[9]
+        sb = bytearray()
+        for i in range(0, len(seq), 2):
+            hi = code[seq[i]]
+            lo = code[seq[i + 1]] if i + 1 < len(seq) else 0
+            sb.append((hi << 4) | lo)
+        qual = bytes([0xFF] * len(seq)) if f[10] == "*" else bytes(ord(c) - 33 for c in f[10])
+        tags = bytearray()
+        for t in f[11:]:
+            tag, typ, val = t.split(":", 2)
+            if typ == "i":
+                v = int(val)
+                tags += tag.encode() + (b"c" + struct.pack("<b", v) if -128 <= v < 128 else b"i" + struct.pack("<i", v))
+            else:
+                tags += tag.encode() + b"Z" + val.encode() + b"\x00"
+        body = struct.pack("<iiBBHHHiiii", tid, int(f[3]) - 1, len(qname), int(f[4]), 4680, len(cig), int(f[1]), len(seq), -1, -1, 0)
+        body += qname + b"".join(struct.pack("<I", (n << 4) | o) for n, o in cig) + bytes(sb) + qual + bytes(tags)
+        out += struct.pack("<i", len(body)) + body
+    with open(bam_path, "wb") as fh:
+        for i in range(0, len(out), 60000):
+            fh.write(gzip.compress(bytes(out[i : i + 60000])))
+
+
+def test_bam_reader_equals_sam_reader(tmp_path):
+    from find_circ2_b200 import samio
+
+    sam = os.path.join(GOLDEN, "synth_a", "input.sam")
+    bam = str(tmp_path / "input.bam")
+    sam_to_bam(sam, bam)
+    n1, l1, r1 = samio.read_sam(open(sam))
+    n2, l2, r2 = samio.read_bam(open(bam, "rb"))
+    assert n1 == n2 and l1 == l2
+    a, b = list(r1), list(r2)
+    assert len(a) == len(b) > 2000
+    for x, y in zip(a, b):
+        assert (x.qname, x.flag, x.tid, x.pos, x.cigar, x.seq, x.qual, x.AS, x.XS, x.aend) == (
+            y.qname, y.flag, y.tid, y.pos, y.cigar, y.seq, y.qual, y.AS, y.XS, y.aend)
+
+
+def _compare_dir(out_dir, ref_dir):
+    rd = lambda n: open(os.path.join(ref_dir, n)).read()  # noqa: E731
+    assert O.canonical_bed(open(os.path.join(out_dir, "circ_splice_sites.bed")).read()) == O.canonical_bed(rd("circ_splice_sites.bed"))
+    assert O.canonical_bed(open(os.path.join(out_dir, "lin_splice_sites.bed")).read()) == O.canonical_bed(rd("lin_splice_sites.bed"))
+    assert gzip.open(os.path.join(out_dir, "spliced_reads.fastq.gz"), "rt").read() == rd("spliced_reads.fastq")
+    assert O.canonical_multi(open(os.path.join(out_dir, "multi_events.tsv")).read()) == O.canonical_multi(rd("multi_events.tsv"))
+    log = open(os.path.join(out_dir, "run.log")).read().split("\n")
+    k = [i for i, l in enumerate(log) if l.endswith("run finished")][0]
+    counters = "".join(l.split("\t")[-1] + "\n" for l in log[k + 1 :] if "=" in l)
+    assert counters == rd("counters.txt")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("how", ["file", "stdin", "bam"])
+def test_find_circ_process(tmp_path, how):
+    case = os.path.join(GOLDEN, "synth_a")
+    ref = os.path.join(case, "ref_default")
+    out = str(tmp_path / "run")
+    cmd = [sys.executable, os.path.join(ROOT, "find_circ.py"), "-G", os.path.join(case, "genome.fa"), "-n", "test", "-o", out, "-q"]
+    sam = os.path.join(case, "input.sam")
+    if how == "file":
+        r = subprocess.run(cmd + [sam], capture_output=True, text=True)
+    elif how == "stdin":
+        r = subprocess.run(cmd, stdin=open(sam), capture_output=True, text=True)
+    else:
+        bam = str(tmp_path / "input.bam")
+        sam_to_bam(sam, bam)
+        r = subprocess.run(cmd + [bam], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    _compare_dir(out, ref)
+
+
+@pytest.mark.gpu
+def test_find_circ_process_errors(tmp_path):
+    exe = [sys.executable, os.path.join(ROOT, "find_circ.py")]
+    r = subprocess.run(exe + ["-o", str(tmp_path / "x")], capture_output=True, text=True, stdin=subprocess.DEVNULL)
+    assert r.returncode == 1 and "need to specify" in r.stdout          # find_circ.py:438-440
+    r = subprocess.run(exe + ["-v"], capture_output=True, text=True)
+    assert r.returncode == 0 and "version" in r.stdout                  # find_circ.py:416-418
+    # unknown chromosome in the alignments -> the run aborts with exit 1 (KeyError at find_circ.py:193)
+    case = os.path.join(GOLDEN, "kat3")
+    other = os.path.join(GOLDEN, "cdr1as", "genome.fa")
+    r = subprocess.run(exe + ["-G", other, "-o", str(tmp_path / "y"), "-q", os.path.join(case, "input.sam")], capture_output=True, text=True)
+    assert r.returncode == 1 and "KeyError" in r.stderr
