@@ -31,43 +31,43 @@ USAGE = """
 def build_parser() -> optparse.OptionParser:
     p = optparse.OptionParser(usage=USAGE)
     a = p.add_option
-    a("-v", "--version", dest="version", action="store_true", default=False, help="get version information")
+    a("-v", "--version", dest="version", action="store_true", default=False, help="print the version and exit")
     a("-S", "--system", dest="system", type=str, default="", help="model system database (not supported: needs the byo library)")
-    a("-G", "--genome", dest="genome", type=str, default="", help="path to genome (one multichromosome FASTA file)")
+    a("-G", "--genome", dest="genome", type=str, default="", help="genome as ONE multi-sequence FASTA file")
     a("", "--known-circ", dest="known_circ", type=str, default="", help="file with known circRNA junctions (BED6) [not supported yet]")
     a("", "--known-lin", dest="known_lin", type=str, default="", help="file with known linear splice junctions (BED6) [not supported yet]")
-    a("-o", "--output", dest="output", default="find_circ_run", help="where to store output")
-    a("-q", "--silent", dest="silent", default=False, action="store_true", help="suppress any normal output to stdout")
+    a("-o", "--output", dest="output", default="find_circ_run", help="output directory (created if missing)")
+    a("-q", "--silent", dest="silent", default=False, action="store_true", help="no summary lines on stdout")
     a("", "--stdout", dest="stdout", default=None, choices=["circs", "lins", "reads", "multi", "test"],
-      help="use to direct chosen type of output (circs, lins, reads, multi) to stdout instead of file")
-    a("-n", "--name", dest="name", default="unknown", help="tissue/sample name to use (default='unknown')")
+      help="write this output to stdout instead of its file")
+    a("-n", "--name", dest="name", default="unknown", help="sample name used in junction names and the tissues column [unknown]")
     a("", "--min-uniq-qual", "--min_uniq_qual", dest="min_uniq_qual", type=int, default=2,
-      help="minimal uniqness for anchor alignments to consider (default=2)")
-    a("-a", "--anchor", dest="asize", type=int, default=15, help="anchor size (default=15)")
-    a("-m", "--margin", dest="margin", type=int, default=2, help="maximum nts the BP is allowed to reside within a segment (default=2)")
+      help="smallest AS-XS margin of both segments for a pair to be scanned [2]")
+    a("-a", "--anchor", dest="asize", type=int, default=15, help="minimal aligned length of a segment [15]")
+    a("-m", "--margin", dest="margin", type=int, default=2, help="how far a breakpoint may lie inside a segment [2]")
     a("-d", "--max-mismatch", "--maxdist", dest="maxdist", type=int, default=2,
-      help="maximum mismatches (no indels) allowed in segment extensions (default=2)")
-    a("", "--short-threshold", dest="short_threshold", type=int, default=100, help="minimal genomic span [nt] of a circRNA before it is labeled SHORT (default=100)")
-    a("", "--huge-threshold", dest="huge_threshold", type=int, default=100000, help="maximal genomic span [nt] of a circRNA before it is labeled HUGE (default=100000)")
+      help="mismatches tolerated when extending the segments to the breakpoint [2]")
+    a("", "--short-threshold", dest="short_threshold", type=int, default=100, help="junctions spanning less are labelled SHORT [100]")
+    a("", "--huge-threshold", dest="huge_threshold", type=int, default=100000, help="junctions spanning more are labelled HUGE [100000]")
     a("", "--debug", dest="debug", default=False, action="store_true", help="(accepted, no effect)")
     a("", "--profile", dest="profile", default=False, action="store_true", help="(accepted, no effect)")
     a("", "--non-canonical", "--noncanonical", dest="noncanonical", default=False, action="store_true",
-      help="relax the GU/AG constraint (will produce many more ambiguous counts)")
-    a("", "--all-hits", "--allhits", dest="allhits", default=False, action="store_true", help="in case of ambiguities, report each hit")
+      help="do not insist on GT/AG (CT/AC) at the breakpoint")
+    a("", "--all-hits", "--allhits", dest="allhits", default=False, action="store_true", help="record every tied breakpoint, not only the first")
     a("", "--stranded", dest="stranded", default=False, action="store_true", help="not supported (crashes in the reference: find_circ.py:533)")
     a("", "--strand-pref", "--strandpref", dest="strandpref", default=False, action="store_true",
-      help="prefer splice sites that match annotated direction of transcription")
+      help="break ties in favour of the strand of the read")
     a("", "--half-unique", "--halfunique", "--halfuniq", dest="halfunique", default=False, action="store_true",
-      help="also report junctions where only one anchor aligns uniquely (less likely to be true)")
+      help="keep junctions with a single uniquely placed side")
     a("", "--report-nobridges", "--report_nobridges", "--report_nobridge", dest="report_nobridges", default=False, action="store_true",
-      help="also report junctions lacking at least a single read where both anchors, jointly align uniquely")
+      help="keep junctions without any read whose two segments are both unique")
     a("-B", "--bam", dest="bam", default=False, action="store_true", help="not supported")
-    a("-t", "--throughput", dest="throughput", default=False, action="store_true", help="print information on throughput to stderr")
-    a("", "--chunk-size", "--chunksize", dest="chunksize", type=int, default=100000, help="number of reads to be processed in one chunk (default=100000)")
-    a("", "--noop", dest="noop", default=False, action="store_true", help="Do not search for any junctions. Only process the alignment stream")
+    a("-t", "--throughput", dest="throughput", default=False, action="store_true", help="accepted for compatibility")
+    a("", "--chunk-size", "--chunksize", dest="chunksize", type=int, default=100000, help="accepted for compatibility")
+    a("", "--noop", dest="noop", default=False, action="store_true", help="decode the alignments only, no junction search")
     a("", "--test", dest="test", default=False, action="store_true", help="not supported")
-    a("", "--no-linear", dest="nolinear", default=False, action="store_true", help="Do not investigate linear junctions, unless associated with another backsplice event")
-    a("", "--no-multi", dest="multi_events", default=True, action="store_false", help="Do not record multi-events")
+    a("", "--no-linear", dest="nolinear", default=False, action="store_true", help="ignore linear junctions of fragments without a back-splice")
+    a("", "--no-multi", dest="multi_events", default=True, action="store_false", help="do not write multi_events.tsv rows")
     a("", "--batch-pairs", dest="batch_pairs", type=int, default=1 << 18, help="anchor pairs per GPU batch (default 262144)")
     a("", "--device", dest="device", type=int, default=0, help="CUDA device (default 0)")
     a("", "--python-ingest", dest="native", default=True, action="store_false",

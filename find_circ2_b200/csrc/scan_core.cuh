@@ -315,17 +315,8 @@ FC_HD uint32_t load_tile_window(const GenomeView& g, int64_t gp, Window<NP>& w) 
 // full variant nA/nB are the N planes of the windows (all zero for the lanes without N).
 template <int NP, bool WITH_N>
 FC_HD void scan_planes(const ScanCfg& cfg, const Window<NP>& A, const Window<NP>& B, const uint32_t (&nA)[NP + 1],
-                       const uint32_t (&nB)[NP + 1], int l, bool minus_span, const ReadView& rv, int64_t i,
-                       bool read_n, Best& best) {
-  // the read planes are needed by almost every pair: issue the loads before the signal logic
-  uint32_t rlo[NP], rhi[NP], rnn[NP];
-#pragma unroll
-  for (int k = 0; k < NP; ++k) {
-    const bool have = k < rv.n_words;
-    rlo[k] = have ? ldg32(rv.rlo + (int64_t)k * rv.stride + i) : 0u;
-    rhi[k] = have ? ldg32(rv.rhi + (int64_t)k * rv.stride + i) : 0u;
-    rnn[k] = (WITH_N && read_n && have) ? ldg32(rv.rn + (int64_t)k * rv.stride + i) : 0u;
-  }
+                       const uint32_t (&nB)[NP + 1], int l, bool minus_span, const uint32_t (&rlo)[NP],
+                       const uint32_t (&rhi)[NP], const uint32_t (&rnn)[NP], Best& best) {
   // splice signal at split position x (bit x&31 of word x>>5), codes A=00 C=01 G=10 T=11 (hi,lo):
   //   GT..AG: A[x]=G A[x+1]=T B[x]=A B[x+1]=G ;  CT..AC: A[x]=C A[x+1]=T B[x]=A B[x+1]=C     (find_circ.py:924-954)
   //   <=> A[x+1]==T, B[x]==A, A[x]==B[x+1], A[x] in {C,G};  '-' strand iff A[x]==C (lo bit set); never contains N
@@ -464,6 +455,15 @@ FC_HD void scan_pair(const GenomeView& g, const ScanCfg& cfg, const PairArgs& p,
     extra |= W3_RANGE;
   }
   if (fast) {
+    // the read planes first: their (coalesced) loads are in flight while the tile loads are issued and waited for
+    uint32_t rlo[NP], rhi[NP], rnn[NP];
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      const bool have = k < rv.n_words;
+      rlo[k] = have ? ldg32(rv.rlo + (int64_t)k * rv.stride + i) : 0u;
+      rhi[k] = have ? ldg32(rv.rhi + (int64_t)k * rv.stride + i) : 0u;
+      rnn[k] = (read_n && have) ? ldg32(rv.rn + (int64_t)k * rv.stride + i) : 0u;
+    }
     Window<NP> A, B;
     uint32_t nA[NP + 1], nB[NP + 1];
     bool with_n = read_n;
@@ -491,9 +491,9 @@ FC_HD void scan_pair(const GenomeView& g, const ScanCfg& cfg, const PairArgs& p,
 #pragma unroll
         for (int k = 0; k <= NP; ++k) nA[k] = nB[k] = 0u;
       }
-      scan_planes<NP, true>(cfg, A, B, nA, nB, l, minus_span, rv, i, read_n, best);
+      scan_planes<NP, true>(cfg, A, B, nA, nB, l, minus_span, rlo, rhi, rnn, best);
     } else {
-      scan_planes<NP, false>(cfg, A, B, nA, nB, l, minus_span, rv, i, false, best);
+      scan_planes<NP, false>(cfg, A, B, nA, nB, l, minus_span, rlo, rhi, rnn, best);
     }
   }
   finish(best, p.a_start, p.b_end, l, backsplice, extra, out);
