@@ -34,8 +34,8 @@ def build_parser() -> optparse.OptionParser:
     a("-v", "--version", dest="version", action="store_true", default=False, help="print the version and exit")
     a("-S", "--system", dest="system", type=str, default="", help="model system database (not supported: needs the byo library)")
     a("-G", "--genome", dest="genome", type=str, default="", help="genome as ONE multi-sequence FASTA file")
-    a("", "--known-circ", dest="known_circ", type=str, default="", help="file with known circRNA junctions (BED6) [not supported yet]")
-    a("", "--known-lin", dest="known_lin", type=str, default="", help="file with known linear splice junctions (BED6) [not supported yet]")
+    a("", "--known-circ", dest="known_circ", type=str, default="", help="BED6 file of known circRNA junctions: they keep their names in the output")
+    a("", "--known-lin", dest="known_lin", type=str, default="", help="BED6 file of known linear splice junctions: they keep their names in the output")
     a("-o", "--output", dest="output", default="find_circ_run", help="output directory (created if missing)")
     a("-q", "--silent", dest="silent", default=False, action="store_true", help="no summary lines on stdout")
     a("", "--stdout", dest="stdout", default=None, choices=["circs", "lins", "reads", "multi", "test"],
@@ -80,14 +80,15 @@ def parse_args(argv):
     for bad in ("stranded", "bam", "test"):
         if getattr(o, bad):
             raise SystemExit("option --%s is not supported by this build" % bad)
-    if o.system or o.known_circ or o.known_lin:
-        raise SystemExit("-S/--system and --known-circ/--known-lin are not supported by this build")
+    if o.system:
+        raise SystemExit("-S/--system is not supported by this build")
     opt = Options(
         genome=o.genome, output=o.output, name=o.name, min_uniq_qual=o.min_uniq_qual, asize=o.asize, margin=o.margin,
         maxdist=o.maxdist, short_threshold=o.short_threshold, huge_threshold=o.huge_threshold, noncanonical=o.noncanonical,
         allhits=o.allhits, strandpref=o.strandpref, halfunique=o.halfunique, report_nobridges=o.report_nobridges,
         nolinear=o.nolinear, multi_events=o.multi_events, throughput=o.throughput, chunksize=o.chunksize, noop=o.noop,
         silent=o.silent, stdout=o.stdout, batch_pairs=o.batch_pairs, device=o.device, native=o.native,
+        known_circ=o.known_circ, known_lin=o.known_lin,
     )
     return opt, args, o
 

@@ -59,6 +59,8 @@ class Options:
     batch_pairs: int = 1 << 18  # anchor pairs per GPU batch (ours)
     device: int = 0
     native: bool = True  # native (C++) SAM ingest for SAM text files
+    known_circ: str = ""  # BED6 files of known junctions (find_circ.py:387-388)
+    known_lin: str = ""
 
 
 def py2_str(x) -> str:
@@ -211,7 +213,23 @@ class Run(object):
         self.cur_k = 0
         self.multi_out: List[tuple] = []
         self.t_scan = 0.0
+        self.known: Dict[tuple, str] = {}
+        for kind, path in ((0, opt.known_circ), (1, opt.known_lin)):
+            if path:
+                self._load_known(path, kind)
         self.eng.agg_reset()
+
+    def _load_known(self, path: str, kind: int):
+        """SpliceSiteStorage.load_known_sites (find_circ.py:665-679): a known site keeps its BED name, does not count
+        towards the novel numbering and carries a placeholder splice (edits 10, overlap 10, one breakpoint) that takes
+        part in the minima of the edits / anchor_overlap / breakpoints columns"""
+        gid = {n: k for k, n in enumerate(self.eng.chrom_names)}
+        for line in open(path):
+            if line.startswith("#"):
+                continue
+            chrom, start, end, name, _score, strand = line.rstrip().split("\t")[:6]
+            if chrom in gid:  # a site on a chromosome the genome does not have can never be observed
+                self.known[(gid[chrom], int(start), int(end), strand, kind)] = name
 
     # ------------------------------------------------------------------ batch assembly
     def _reset_batch(self):
@@ -604,12 +622,15 @@ class Run(object):
         cn = self.eng.chrom_names
         for r in junc:
             kind = (int(r["sk"]) >> 1) & 1
-            counts[kind] += 1
             key = (int(r["chrom"]), int(r["start"]), int(r["end"]), "-" if int(r["sk"]) & 1 else "+", kind)
+            if key in self.known:
+                names[key] = self.known[key]
+                continue
+            counts[kind] += 1
             names[key] = "%s_%s_%06d" % (self.opt.name, prefix[kind], counts[kind])
         return names
 
-    def categories(self, r, inf: Optional[JunctionInfo], min_dist) -> List[str]:
+    def categories(self, r, inf: Optional[JunctionInfo], min_dist, min_ov=None, min_nh=None) -> List[str]:
         """Hit.categories (find_circ.py:601-654)"""
         opt = self.opt
         cats = []
@@ -619,9 +640,9 @@ class Run(object):
             cats.append("WARN_NON_UNIQUE_ANCHOR")
         if float(r["n_uniq_bridges"]) == 0:
             cats.append("WARN_NO_UNIQ_BRIDGES")
-        if int(r["min_n_hits"]) > 1:
+        if (int(r["min_n_hits"]) if min_nh is None else min_nh) > 1:
             cats.append("WARN_AMBIGUOUS_BP")
-        ov, ed = int(r["min_ov"]), int(min_dist)
+        ov, ed = (int(r["min_ov"]) if min_ov is None else min_ov), int(min_dist)
         if ov == 0 and ed == 0:
             pass
         elif ov < 2 and ed < 2:
@@ -671,12 +692,15 @@ class Run(object):
             else:
                 flags, fcounts = ["N/A"], [0]
             w = float(r["n_weighted"])
+            min_dist, min_ov, min_nh = int(r["min_dist"]), int(r["min_ov"]), int(r["min_n_hits"])
+            if key in self.known:  # the placeholder splice of a known site (find_circ.py:676)
+                min_dist, min_ov, min_nh = min(min_dist, 10), min(min_ov, 10), 1
             # with --max-mismatch 0 the reference's edit distance is a python bool (find_circ.py:868-870)
-            edits = bool(int(r["min_dist"])) if opt.maxdist == 0 else int(r["min_dist"])
+            edits = bool(min_dist) if opt.maxdist == 0 else min_dist
             cols = [
                 cn[int(r["chrom"])], start, end, names[key], int(r["n_frags"]), strand, w, int(r["n_spanned"]), int(r["n_uniq"]),
-                bridges, ql, qr, opt.name, py2_str(w), edits, int(r["min_ov"]), int(r["min_n_hits"]),
-                decode_signal((sk >> 16) & 0xFFF), "N/A", ",".join(sorted(self.categories(r, inf, int(r["min_dist"])))),
+                bridges, ql, qr, opt.name, py2_str(w), edits, min_ov, min_nh,
+                decode_signal((sk >> 16) & 0xFFF), "N/A", ",".join(sorted(self.categories(r, inf, min_dist, min_ov, min_nh))),
                 ",".join(flags), ",".join(str(c) for c in fcounts),
             ]
             lines.append("\t".join(py2_str(c) for c in cols) + "\n")

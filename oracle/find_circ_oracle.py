@@ -19,7 +19,7 @@ Each function cites the reference lines it follows.  Deliberately mirrored quirk
   * the first SAM record is never checked for being unmapped (find_circ.py:1462-1463);
   * counters anchor_not_uniq / no_uniq_bridges are incremented after the dump and never appear (:1605-1610).
 Not supported (the reference itself crashes or needs absent libraries): --stranded (find_circ.py:533 vs
-:766-776), -S/--system, -B/--bam, --test, --known-circ/--known-lin.
+:766-776), -S/--system, -B/--bam, --test.
 """
 from __future__ import annotations
 
@@ -50,6 +50,8 @@ class Options:
     report_nobridges: bool = False
     nolinear: bool = False
     multi_events: bool = True
+    known_circ: str = ""
+    known_lin: str = ""
 
 
 def py2_str(x) -> str:
@@ -525,11 +527,28 @@ BED_HEADER = [
 class JunctionTable:
     """SpliceSiteStorage, find_circ.py:657-730"""
 
-    def __init__(self, prefix: str, opt: Options):
+    def __init__(self, prefix: str, opt: Options, known: str = ""):
         self.prefix = prefix
         self.opt = opt
         self.sites: Dict[tuple, Junction] = {}
         self.count = 0
+        if known:
+            self.load_known(known)
+
+    def load_known(self, path: str) -> None:
+        """find_circ.py:665-679: BED6 sites are pre-seeded under their own names with a placeholder splice whose
+        dist=10, ov=10, n_hits=1 stay in the per-junction lists (and therefore in the minima that are printed)"""
+        for line in open(path):
+            if line.startswith("#"):
+                continue
+            parts = line.rstrip().split("\t")
+            chrom, start, end, name, _score, strand = parts[:6]
+            coord = (chrom, int(start), int(end), strand)
+            j = Junction(name, coord)
+            j.edits.append(10)
+            j.overlaps.append(10)
+            j.n_hits.append(1)
+            self.sites[coord] = j
 
     def add(self, sp: Splice) -> Junction:
         coord = sp.coord
@@ -546,6 +565,8 @@ class JunctionTable:
         opt = self.opt
         out = []
         for (chrom, start, end, strand), j in self.sites.items():
+            if not j.readnames:
+                continue  # a known site that was not observed (find_circ.py:699-700)
             ql, qr = max(j.quals_left), max(j.quals_right)
             if opt.halfunique:
                 if ql < opt.min_uniq_qual and qr < opt.min_uniq_qual:
@@ -613,8 +634,8 @@ class Run:
         self.chrom_names = list(chrom_names)
         self.opt = opt
         self.N: Dict[str, float] = defaultdict(float)
-        self.circ = JunctionTable("circ", opt)
-        self.lin = JunctionTable("lin", opt)
+        self.circ = JunctionTable("circ", opt, opt.known_circ)
+        self.lin = JunctionTable("lin", opt, opt.known_lin)
         self.reads: List[str] = []
         self.multi: List[str] = []
         self.n_fragments = 0
@@ -831,6 +852,10 @@ def options_from_argv(argv: Sequence[str]) -> Options:
             o.nolinear = True
         elif a == "--no-multi":
             o.multi_events = False
+        elif a == "--known-circ":
+            o.known_circ = next(it)
+        elif a == "--known-lin":
+            o.known_lin = next(it)
         else:
             raise ValueError("unsupported option %r" % a)
     return o

@@ -28,7 +28,7 @@ def golden_cases():
             lines = open(os.path.join(rdir, "cmdline.txt")).read().split("\n")
             if lines[1].strip() != "exit=0":
                 continue
-            out.append((cdir, rdir, lines[0].split()))
+            out.append((cdir, rdir, [a.replace("@CASE@", cdir) for a in lines[0].split()]))
     return out
 
 

@@ -298,7 +298,8 @@ def run_reference(case_dir, tag, args):
         gfa = os.path.join(tmp, "genome.fa")
         shutil.copy(os.path.join(case_dir, "genome.fa"), gfa)
         run_dir = os.path.join(tmp, "run")
-        cmd = [sys.executable, SHIM, "-G", gfa, "-o", run_dir, "-q"] + list(args) + [os.path.join(case_dir, "input.sam")]
+        real = [a.replace("@CASE@", case_dir) for a in args]  # cmdline.txt keeps the placeholder, the tests expand it
+        cmd = [sys.executable, SHIM, "-G", gfa, "-o", run_dir, "-q"] + real + [os.path.join(case_dir, "input.sam")]
         r = subprocess.run(cmd, capture_output=True, text=True)
         os.makedirs(out)
         with open(os.path.join(out, "cmdline.txt"), "w") as fh:
@@ -344,10 +345,34 @@ OPTION_SETS = {
     "uniq0": ["-n", "test", "--min-uniq-qual", "0"],
     "nolinear_nomulti": ["-n", "test", "--no-linear", "--no-multi"],
     "thresholds": ["-n", "test", "--short-threshold", "400", "--huge-threshold", "3000"],
+    "known": ["-n", "test", "--known-circ", "@CASE@/known_circ.bed", "--known-lin", "@CASE@/known_lin.bed"],
 }
 
 
+def write_known_sites(case_dir):
+    """BED6 files for --known-circ / --known-lin (find_circ.py:665-679) from the default run of the case: every third
+    junction under its own name, one with the strand flipped and a few sites that no read supports"""
+    for kind, fn in (("circ", "circ_splice_sites.bed"), ("lin", "lin_splice_sites.bed")):
+        rows = [l.split("\t") for l in open(os.path.join(case_dir, "ref_default", fn)) if not l.startswith("#")]
+        with open(os.path.join(case_dir, "known_%s.bed" % kind), "w") as fh:
+            fh.write("# known %s junctions\n" % kind)
+            for k, r in enumerate(rows):
+                if k % 3 == 0:
+                    fh.write("\t".join([r[0], r[1], r[2], "KNOWN_%s_%d" % (kind.upper(), k), "0", r[5]]) + "\n")
+                elif k % 7 == 1:
+                    fh.write("\t".join([r[0], r[1], r[2], "FLIPPED_%d" % k, "0", "-" if r[5] == "+" else "+"]) + "\n")
+                elif k % 7 == 2:
+                    fh.write("\t".join([r[0], str(int(r[1]) + 1), r[2], "SHIFTED_%d" % k, "0", r[5]]) + "\n")
+            fh.write("chrNotThere\t10\t500\tELSEWHERE\t0\t+\n")
+
+
 def main():
+    if sys.argv[1:] == ["known"]:  # only the runs with known junctions (added after the first set)
+        d = os.path.join(HERE, "synth_a")
+        write_known_sites(d)
+        run_reference(d, "known", OPTION_SETS["known"])
+        run_reference(d, "known_d0", OPTION_SETS["known"] + ["-d", "0", "--min-uniq-qual", "0", "--report-nobridges"])
+        return
     print("kat3")
     d = os.path.join(HERE, "kat3")
     build_ref_case(os.path.join(REF_DATA, "test_ref.fa"), os.path.join(REF_DATA, "test_reads.fa"), d, "kat3")
@@ -364,7 +389,10 @@ def main():
     d = os.path.join(HERE, "synth_a")
     build_synth_case(d, seed=11, n_pairs=900, read_len=100, asize=15, error_rate=0.01)
     for tag, args in OPTION_SETS.items():
+        if tag == "known":
+            write_known_sites(d)
         run_reference(d, tag, args)
+    run_reference(d, "known_d0", OPTION_SETS["known"] + ["-d", "0", "--min-uniq-qual", "0", "--report-nobridges"])
 
     print("synth_b (150-nt reads, 2% errors)")
     d = os.path.join(HERE, "synth_b")
