@@ -40,7 +40,7 @@ def workload(rank, n_pairs, genome_mb, n_circ):
     per = genome_mb * 1000000 // 20
     g = synth.make_genome([per] * 20, seed=1, n_frac=0.005, n_run=(50, 5000), soft_frac=0.0)
     J = synth.plant_junctions(g, n_circ, max(n_circ // 20, 1), seed=2, span=(200, 50000), margin=400)
-    t = synth.make_pairs(g, J, n_pairs, read_len=READ_LEN, asize=ASIZE, seed=3 + 1000 * rank, error_rate=0.005, zipf=1.0,
+    t = synth.make_pairs(g, J, n_pairs, read_len=READ_LEN, asize=ASIZE, seed=3 + 1000 * rank, error_rate=0.005, zipf=float(os.environ.get("FC_BENCH_ZIPF", "1.0")),
                          frac_decoy=0.10, frac_nonuniq=0.02, frac_edge=0.01)
     return g, J, t
 

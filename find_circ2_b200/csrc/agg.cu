@@ -12,8 +12,8 @@
 //     first idx            min  -> discovery order -> junction name                (:684-686)
 //     n_frags              distinct qname hashes                                   (:584-586)
 //     n_uniq               distinct strand-invariant read hashes (palindromes count half, :588-590)
-// Two implementations with identical results: a sort-free one (128-bit CAS hash tables + CTA-level pre-aggregation,
-// default) and a sort-based one (stable CUB radix sort + warp-segmented reduction + sequential float replay, fallback).
+// Two implementations with identical results: a sort-free one (one pass: 128-bit CAS hash tables, per-junction
+// accumulators updated with integer atomics, default) and a sort-based one (stable CUB radix sort + warp-segmented reduction + sequential float replay, fallback).
 // Multi-GPU: the emit kernel can write records straight into the owner rank's buffer over NVLink (emit_p2p_kernel).
 #include <stddef.h>
 #include <stdlib.h>
@@ -63,12 +63,14 @@ static_assert(offsetof(JAcc, cw) == 4 && offsetof(JAcc, cb) == 24 && offsetof(JA
                   offsetof(JAcc, n_uniq) == 68 && offsetof(JAcc, first_idx) == 80,
               "accumulate_kernel's 64-bit pair adds depend on this layout");
 
-__global__ void count_hits_kernel(int64_t n, const fc_hit* __restrict__ hits, const uint8_t* __restrict__ mask,
-                                  uint32_t* __restrict__ accept) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  accept[i] = ((hits[i].w2 & 0xFFFFu) && (!mask || mask[i])) ? 1u : 0u;
-}
+// accepted = the scan found a breakpoint and the caller's mask (if any) keeps the pair
+struct AcceptOp {
+  const fc_hit* hits;
+  const uint8_t* mask;
+  __host__ __device__ uint32_t operator()(int64_t i) const {
+    return ((hits[i].w2 & 0xFFFFu) && (!mask || mask[i])) ? 1u : 0u;
+  }
+};
 
 __global__ void emit_kernel(int64_t n, const fc_hit* __restrict__ hits, const uint8_t* __restrict__ mask,
                             const uint32_t* __restrict__ pos,
@@ -103,9 +105,8 @@ __global__ void emit_kernel(int64_t n, const fc_hit* __restrict__ hits, const ui
   recs[*n_recs + pos[i]] = r;
 }
 
-__global__ void bump_kernel(unsigned long long* n_recs, const uint32_t* __restrict__ pos,
-                            const uint32_t* __restrict__ accept, int64_t n) {
-  *n_recs += (unsigned long long)pos[n - 1] + accept[n - 1];
+__global__ void bump_kernel(unsigned long long* n_recs, const uint32_t* __restrict__ pos, AcceptOp accept, int64_t n) {
+  *n_recs += (unsigned long long)pos[n - 1] + accept(n - 1);
 }
 
 __global__ void key_hash_kernel(int64_t n, const fc_jrec* __restrict__ recs, uint64_t seed, uint64_t* __restrict__ h,
@@ -280,178 +281,373 @@ __global__ void distinct_hash_kernel(int64_t n, const fc_jrec* __restrict__ s, c
 }
 
 // ======================================================================================================================
-// Sort-free aggregation (default).  Junction ids come from an exact 128-bit hash table, the per-junction statistics
-// are pre-aggregated per CTA in shared memory (a junction supported by 10 % of all reads would otherwise serialise
-// ~10^5 atomics on one L2 line) and flushed with integer atomics, the distinct counts use the exact hash sets above.
-// Float sums need stream order only when a weight denominator is not a power of two; such inputs fall back to the
-// sort-based path below.
+// Sort-free aggregation (default): ONE pass over the records.  Every record looks its junction up in a 128-bit
+// open-addressing table whose entries carry the junction id next to the key (one 16-byte load resolves both), bumps
+// the per-junction accumulators (64 bytes, two sectors) with three 64/32-bit reductions, looks at the extrema sector
+// once and only fires an atomic when the record improves one, and inserts (read hash, junction) / (name hash,
+// junction) into one exact hash set for the distinct counts.  Weights are k/8 (denominators 1,2,4,8), so fixed-point
+// sums are exact in any order; inputs with another denominator fall back to the sort-based path below.
+//
+// The distinct set is cleared per call (the memset also leaves it resident in L2, where the probes then hit); the finish
+// kernel zeroes exactly the key slots and accumulators it consumed, so those are never cleared as a whole.
 // ======================================================================================================================
-__device__ __forceinline__ U128 rec_key(const fc_jrec& r) {
-  return U128{((unsigned long long)r.chrom << 32) | (unsigned long long)r.start,
-              ((unsigned long long)r.end << 32) | 0x80000000ull | (unsigned long long)(((r.sk >> 16) & 0xFFFu) << 2) |
-                  (unsigned long long)(r.sk & 3u)};
+struct alignas(64) JAcc2 {
+  unsigned long long spanned_frags;  // n_spanned | n_frags << 32
+  unsigned long long w_b;            // 8 * n_weighted | 8 * n_uniq_bridges << 32
+  unsigned int uniq2;                // 2 per distinct non-palindromic read, 1 per distinct palindromic read
+  unsigned int sig;                  // 12-bit signal code (same for every record of the junction)
+  unsigned long long spare;
+  // extrema sector; everything is kept as a maximum with 0 = "nothing yet"
+  unsigned long long first_inv;      // ~(smallest record position / idx)
+  unsigned int qmax_l, qmax_r;       // best anchor quality + 32769
+  unsigned int inv_dist, inv_ov, inv_nh;  // ~minimum
+  unsigned int slot;                 // slot of the junction in the key table
+};
+static_assert(sizeof(JAcc2) == 64 && offsetof(JAcc2, first_inv) == 32 && offsetof(JAcc2, inv_dist) == 48, "JAcc2 layout");
+
+constexpr unsigned long long KEY_HI_MASK = (1ull << 34) - 1ull;  // chrom (32) | strand, kind (2); junction id + 1 above
+constexpr long long FUSED_MAX_RECORDS = 1ll << 28;                 // keeps 8 * n_spanned and the ids inside their fields
+
+// counters (32-bit words at counters + 8): [0] junction ids handed out, [1] records with another denominator,
+// [2] ids beyond the accumulator array, [3] junctions
+enum { FC_N_ALLOC = 0, FC_N_OTHER = 1, FC_N_OVERFLOW = 2, FC_N_JUNC = 3 };
+
+// Exact set of (value, tag) pairs, insert only.  Probe sequence of an element: first the slot given by the value alone
+// (known before the junction id is, so its sector can be prefetched while the key table is read -- an atomic that
+// misses in L2 is far slower than one that hits), then linear probing from a slot that also depends on the tag (a
+// read sequence that supports very many junctions does not build one long cluster).
+__device__ __forceinline__ unsigned long long set_first_slot(unsigned long long v, unsigned long long mask) {
+  return fc_mix64(v) & mask;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// insert (v1, t1) and (v2, t2); both probe sequences advance together so that their round trips overlap.  The CAS goes
+// first (no load): most inserts find an empty slot, and the returned old entry tells the rest.
+__device__ __forceinline__ void set_insert2(U128* table, unsigned long long mask, unsigned long long v1, unsigned long long t1,
+                                            unsigned long long s1, unsigned long long v2, unsigned long long t2,
+                                            unsigned long long s2, bool& new1, bool& new2) {
+  bool d1 = false, d2 = false, first1 = true, first2 = true;
+  new1 = new2 = false;
+  while (!(d1 && d2)) {
+    U128 o1{0ull, 0ull}, o2{0ull, 0ull};
+    if (!d1) o1 = cas128(table + s1, U128{0ull, 0ull}, U128{v1, t1});
+    if (!d2) o2 = cas128(table + s2, U128{0ull, 0ull}, U128{v2, t2});
+    if (!d1) {
+      if (o1.lo == 0ull && o1.hi == 0ull) {
+        new1 = d1 = true;
+      } else if (o1.lo == v1 && o1.hi == t1) {
+        d1 = true;
+      } else {
+        s1 = first1 ? (fc_mix64(v1 ^ (t1 * 0x9E3779B97F4A7C15ULL)) & mask) : ((s1 + 1ull) & mask);
+        first1 = false;
+      }
+    }
+    if (!d2) {
+      if (o2.lo == 0ull && o2.hi == 0ull) {
+        new2 = d2 = true;
+      } else if (o2.lo == v2 && o2.hi == t2) {
+        d2 = true;
+      } else {
+        s2 = first2 ? (fc_mix64(v2 ^ (t2 * 0x9E3779B97F4A7C15ULL)) & mask) : ((s2 + 1ull) & mask);
+        first2 = false;
+      }
+    }
+  }
 }
 
-__global__ void assign_kernel(int64_t n, const fc_jrec* __restrict__ recs, U128* __restrict__ table, unsigned long long mask,
-                              uint32_t* __restrict__ slot_jid, U128* __restrict__ jkeys, unsigned int* __restrict__ n_junc,
-                              unsigned int* __restrict__ n_other, uint32_t* __restrict__ rec_slot) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const fc_jrec r = recs[i];
-  const U128 key = rec_key(r);
-  unsigned long long slot = fc_mix64(key.lo ^ fc_mix64(key.hi)) & mask;
-  for (;;) {
-    const ulonglong2 cur = __ldcg(reinterpret_cast<const ulonglong2*>(table + slot));
-    if (cur.x == key.lo && cur.y == key.hi) break;
-    if (cur.x == 0ull && cur.y == 0ull) {
-      const U128 old = cas128(table + slot, U128{0ull, 0ull}, key);
-      if (old.lo == 0ull && old.hi == 0ull) {  // this thread created the junction
-        const unsigned int jid = atomicAdd(n_junc, 1u);
-        slot_jid[slot] = jid;
-        jkeys[jid] = key;
+// A junction that collects a few per cent of all reads (expression is heavy-tailed) would otherwise put all of its
+// updates on one L2 sector, and an L2 slice retires about one request per clock for one sector (measured: with a
+// Zipf(1) popularity the direct version spends 4x the time of the uniform case).  So the lanes of a warp that share a
+// junction are combined first, and a junction that shows up at least twice in the CTA (counted in a small
+// shared-memory sketch) is accumulated in a shared-memory table of the CTA and flushed once at the end; junctions seen
+// once per CTA -- the bulk of the distinct ones -- go to global memory directly and never touch the table.
+constexpr int ACC_THREADS = 512;
+constexpr int HOT_ENTRIES = 512;
+constexpr int HOT_BITS = 9;
+constexpr int SKETCH_BITS = 11;
+struct HotTable {
+  unsigned int tag[HOT_ENTRIES];    // junction id + 1, 0 = free
+  unsigned int cnt[HOT_ENTRIES];    // n_spanned | n_frags << 16 (at most one of each per thread of the CTA)
+  unsigned int wb[HOT_ENTRIES];     // 8 * weight | 8 * bridge weight << 16
+  unsigned int uniq2[HOT_ENTRIES];
+  unsigned int qmax_l[HOT_ENTRIES], qmax_r[HOT_ENTRIES], inv_dist[HOT_ENTRIES], inv_ov[HOT_ENTRIES], inv_nh[HOT_ENTRIES];
+  unsigned long long first_inv[HOT_ENTRIES];
+};
+
+__device__ __forceinline__ int hot_find_or_insert(HotTable& t, unsigned int jid) {
+  unsigned int h = (jid * 2654435761u) >> (32 - HOT_BITS);
+#pragma unroll 1
+  for (int probe = 0; probe < 8; ++probe) {
+    const unsigned int old = atomicCAS(&t.tag[h], 0u, jid + 1u);
+    if (old == 0u || old == jid + 1u) return (int)h;
+    h = (h + 1u) & (HOT_ENTRIES - 1);
+  }
+  return -1;  // crowded: the group goes to global memory directly
+}
+
+// extrema of one record (or of one shared-memory entry) against the junction's accumulator: one look at the sector,
+// atomics only for improvements (rare after the first records of a junction)
+__device__ __forceinline__ void extrema_to_global(JAcc2* a, unsigned long long f, unsigned ql, unsigned qr, unsigned idist,
+                                                  unsigned iov, unsigned inh) {
+  const ulonglong2 e0 = __ldcg(reinterpret_cast<const ulonglong2*>(&a->first_inv));
+  const uint4 e1 = __ldcg(reinterpret_cast<const uint4*>(&a->inv_dist));
+  if (f > e0.x) atomicMax(&a->first_inv, f);
+  if (ql > (unsigned)e0.y) atomicMax(&a->qmax_l, ql);
+  if (qr > (unsigned)(e0.y >> 32)) atomicMax(&a->qmax_r, qr);
+  if (idist > e1.x) atomicMax(&a->inv_dist, idist);
+  if (iov > e1.y) atomicMax(&a->inv_ov, iov);
+  if (inh > e1.z) atomicMax(&a->inv_nh, inh);
+}
+
+template <bool ORDERED>
+__global__ void __launch_bounds__(ACC_THREADS) fused_accumulate_kernel(int64_t ub, const unsigned long long* __restrict__ n_ptr,
+                                                               const fc_jrec* __restrict__ recs, U128* __restrict__ keys,
+                                                               unsigned long long kmask, U128* __restrict__ sets,
+                                                               unsigned long long smask, JAcc2* __restrict__ acc,
+                                                               unsigned int acap, unsigned int* __restrict__ ctr,
+                                                               uint32_t* __restrict__ flag, int dbg) {
+  __shared__ HotTable hot;
+  __shared__ unsigned int sketch[1 << SKETCH_BITS];
+  for (int e = threadIdx.x; e < (1 << SKETCH_BITS); e += blockDim.x) sketch[e] = 0u;
+  for (int e = threadIdx.x; e < HOT_ENTRIES; e += blockDim.x) {
+    hot.tag[e] = hot.cnt[e] = hot.wb[e] = hot.uniq2[e] = 0u;
+    hot.qmax_l[e] = hot.qmax_r[e] = hot.inv_dist[e] = hot.inv_ov[e] = hot.inv_nh[e] = 0u;
+    hot.first_inv[e] = 0ull;
+  }
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n = min((int64_t)*n_ptr, ub);  // (a peer-to-peer counter keeps counting past the capacity)
+  if (ORDERED && i < ub) flag[i] = 0u;
+  const bool active = i < n;
+  const unsigned amask = __ballot_sync(0xffffffffu, active);
+  uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0, r2 = r0;
+  unsigned long long s_read = 0ull, s_name = 0ull;
+  unsigned int jid = 0xFFFFFFFFu;
+  if (active) {
+    const uint4* rp = reinterpret_cast<const uint4*>(recs + i);
+    r0 = __ldg(rp);
+    r1 = __ldg(rp + 1);
+    r2 = __ldg(rp + 2);
+    // names and reads share the set: the name's value is salted so that equal hashes of the two kinds stay apart
+    s_read = set_first_slot((unsigned long long)r1.z | ((unsigned long long)r1.w << 32), smask);
+    s_name = set_first_slot(~((unsigned long long)r2.x | ((unsigned long long)r2.y << 32)), smask);
+    prefetch_l2(sets + s_read);
+    prefetch_l2(sets + s_name);
+
+    // ---- junction id
+    const unsigned long long klo = (unsigned long long)r0.y | ((unsigned long long)r0.z << 32);
+    const unsigned long long khi = (unsigned long long)r0.x | ((unsigned long long)(r0.w & 3u) << 32);
+    unsigned long long slot = fc_mix64(klo ^ fc_mix64(khi)) & kmask;
+    for (;;) {
+      // L1-cached look first: entries never change once written, so a cached entry is as good as the one in L2 (the
+      // slot of a popular junction is read by thousands of threads); a cached EMPTY may be stale: ask L2
+      ulonglong2 cur = *reinterpret_cast<const ulonglong2*>(keys + slot);
+      if (cur.x == 0ull && cur.y == 0ull) cur = __ldcg(reinterpret_cast<const ulonglong2*>(keys + slot));
+      if (cur.x == 0ull && cur.y == 0ull) {
+        // ids are handed out before the insert is known to succeed: a lost race leaves an unused id (a hole that the
+        // finish pass skips) instead of making the other threads wait for the winner to publish one
+        const unsigned int j = atomicAdd(&ctr[FC_N_ALLOC], 1u);
+        if (j >= acap) {
+          atomicAdd(&ctr[FC_N_OVERFLOW], 1u);
+          break;
+        }
+        const U128 old = cas128(keys + slot, U128{0ull, 0ull}, U128{klo, khi | ((unsigned long long)(j + 1u) << 34)});
+        if (old.lo == 0ull && old.hi == 0ull) {
+          jid = j;
+          acc[j].sig = (r0.w >> 16) & 0xFFFu;
+          acc[j].slot = (unsigned int)slot;
+          break;
+        }
+        cur.x = old.lo;
+        cur.y = old.hi;
+      }
+      if (cur.x == klo && (cur.y & KEY_HI_MASK) == khi) {
+        jid = (unsigned int)(cur.y >> 34) - 1u;
         break;
       }
-      if (old.lo == key.lo && old.hi == key.hi) break;
+      slot = (slot + 1ull) & kmask;
     }
-    slot = (slot + 1ull) & mask;
   }
-  rec_slot[i] = (uint32_t)slot;
-  const uint32_t den = (r.sk >> 8) & 0xFFu;
-  if (!(den == 1 || den == 2 || den == 4 || den == 8)) atomicAdd(n_other, 1u);
-}
-
-constexpr int ACC_ENTRIES = 1024;  // shared-memory table entries per CTA (2 x the records of a CTA)
-constexpr int ACC_WORDS = 16;      // words per entry
-constexpr int ACC_RECS_PER_THREAD = 2;
-
-__global__ void __launch_bounds__(256) accumulate_kernel(int64_t n, const fc_jrec* __restrict__ recs,
-                                                         const uint32_t* __restrict__ rec_slot,
-                                                         const uint32_t* __restrict__ slot_jid, U128* __restrict__ tab_reads,
-                                                         U128* __restrict__ tab_names, unsigned long long mask,
-                                                         JAcc* __restrict__ acc) {
-  extern __shared__ uint32_t sm[];  // ACC_ENTRIES x ACC_WORDS
-  for (int e = threadIdx.x; e < ACC_ENTRIES; e += blockDim.x) {
-    uint32_t* w = sm + e * ACC_WORDS;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) w[k] = 0u;
-    w[9] = 0x80000000u;  // max_ql as int: INT_MIN
-    w[10] = 0x80000000u;
-    w[11] = w[12] = w[13] = 0xFFFFFFFFu;
-    w[14] = w[15] = 0xFFFFFFFFu;
-  }
+  // ---- how often does the CTA see this junction?
+  const bool ok = jid != 0xFFFFFFFFu;
+  const unsigned int sk_slot = (jid * 0x85EBCA6Bu) >> (32 - SKETCH_BITS);
+  if (ok) atomicAdd(&sketch[sk_slot], 1u);
   __syncthreads();
-  const int64_t base = (int64_t)blockIdx.x * (blockDim.x * ACC_RECS_PER_THREAD);
-#pragma unroll
-  for (int q = 0; q < ACC_RECS_PER_THREAD; ++q) {
-    const int64_t i = base + q * blockDim.x + threadIdx.x;
-    const bool active = i < n;
-    const unsigned amask = __ballot_sync(0xffffffffu, active);
-    if (active) {
-      const fc_jrec r = recs[i];
-      const uint32_t jid = slot_jid[rec_slot[i]];
-      const bool new_read = set_insert(tab_reads, mask, r.read_hash, jid);
-      const bool new_name = set_insert(tab_names, mask, r.qname_hash, jid);
-      // find / create the CTA-local entry of this junction
-      uint32_t e = (jid * 2654435761u) >> 22;  // 10 bits = log2(ACC_ENTRIES)
-      for (;;) {
-        const uint32_t old = atomicCAS(&sm[e * ACC_WORDS], 0u, jid + 1u);
-        if (old == 0u || old == jid + 1u) break;
-        e = (e + 1u) & (ACC_ENTRIES - 1);
+  if (active) {
+    // fc_jrec: chrom,start,end,sk | idx, read_hash | qname_hash, q_left,q_right, n_hits,dist,ov
+    const unsigned long long idx = (unsigned long long)r1.x | ((unsigned long long)r1.y << 32);
+    const unsigned long long read_hash = (unsigned long long)r1.z | ((unsigned long long)r1.w << 32);
+    const unsigned long long qname_hash = (unsigned long long)r2.x | ((unsigned long long)r2.y << 32);
+    const int q_left = (int)(short)(r2.z & 0xFFFFu), q_right = (int)(short)(r2.z >> 16);
+    const unsigned n_hits = r2.w & 0xFFFFu, dist = (r2.w >> 16) & 0xFFu, ov = r2.w >> 24;
+    const unsigned sk = r0.w;
+    JAcc2* a = acc + (ok ? jid : 0u);
+
+    // ---- lanes of the warp that share the junction; a junction seen twice in the CTA goes through shared memory
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned peers = __match_any_sync(amask, jid);
+    const unsigned group = __popc(peers);
+    const bool lead = (int)lane == __ffs((int)peers) - 1;
+    int he = -1;
+    if (ok && (group >= 2u || sketch[sk_slot] >= 2u)) {
+      if (lead) he = hot_find_or_insert(hot, jid);
+      he = __shfl_sync(peers, he, __ffs((int)peers) - 1);
+    }
+
+    // ---- extrema
+    const unsigned long long f = ~(ORDERED ? (unsigned long long)i : idx);
+    const unsigned ql = (unsigned)(q_left + 32769), qr = (unsigned)(q_right + 32769);
+    if (dbg & 2) {
+    } else if (he >= 0) {
+      if (f > hot.first_inv[he]) atomicMax(&hot.first_inv[he], f);
+      if (ql > hot.qmax_l[he]) atomicMax(&hot.qmax_l[he], ql);
+      if (qr > hot.qmax_r[he]) atomicMax(&hot.qmax_r[he], qr);
+      if (~dist > hot.inv_dist[he]) atomicMax(&hot.inv_dist[he], ~dist);
+      if (~ov > hot.inv_ov[he]) atomicMax(&hot.inv_ov[he], ~ov);
+      if (~n_hits > hot.inv_nh[he]) atomicMax(&hot.inv_nh[he], ~n_hits);
+    } else if (ok) {
+      extrema_to_global(a, f, ql, qr, ~dist, ~ov, ~n_hits);
+    }
+
+    // ---- distinct reads / fragment names of the junction
+    const unsigned long long tag = (unsigned long long)(jid + 1u);  // never 0: no entry is all-zero
+    bool new_read = false, new_name = false;
+    if (ok && !(dbg & 1)) set_insert2(sets, smask, read_hash, tag, s_read, qname_hash, tag | (1ull << 32), s_name, new_read, new_name);
+
+    // ---- counters
+    const unsigned den = (sk >> 8) & 0xFFu;
+    const int cls = den == 1 ? 0 : den == 2 ? 1 : den == 4 ? 2 : den == 8 ? 3 : 4;
+    if (cls == 4) atomicAdd(&ctr[FC_N_OTHER], 1u);
+    const unsigned fx = cls < 4 ? (8u >> cls) : 0u;
+    const bool bridge = q_left != 0 && q_right != 0;
+    const bool pal = read_hash & 1ull;
+    if (dbg & 4) {
+    } else if (__all_sync(amask, group == 1u)) {
+      // no two lanes of the warp share a junction (the usual case)
+      if (he >= 0) {
+        atomicAdd(&hot.cnt[he], 1u | ((unsigned)new_name << 16));
+        atomicAdd(&hot.wb[he], fx | ((bridge ? fx : 0u) << 16));
+        if (new_read) atomicAdd(&hot.uniq2[he], pal ? 1u : 2u);
+      } else if (ok) {
+        atomicAdd(&a->spanned_frags, 1ull | ((unsigned long long)new_name << 32));
+        atomicAdd(&a->w_b, (unsigned long long)fx | ((unsigned long long)(bridge ? fx : 0u) << 32));
+        if (new_read) atomicAdd(&a->uniq2, pal ? 1u : 2u);
       }
-      uint32_t* w = sm + e * ACC_WORDS;
-      const uint32_t den = (r.sk >> 8) & 0xFFu;
-      const int cls = den == 1 ? 0 : den == 2 ? 1 : den == 4 ? 2 : den == 8 ? 3 : 4;
-      const bool bridge = r.q_left != 0 && r.q_right != 0;
-      // counters: the lanes of the warp that share the junction add once, through their first lane (a junction
-      // that collects a large share of the reads would otherwise serialise on its shared-memory words)
-      const unsigned peers = __match_any_sync(amask, jid);
-      const bool lead = (int)(threadIdx.x & 31) == __ffs((int)peers) - 1;
-      unsigned add[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // words 1..8
+    } else {
+      unsigned w = 0, b = 0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const unsigned cwk = __popc(__ballot_sync(amask, cls == k) & peers);
-        const unsigned cbk = __popc(__ballot_sync(amask, cls == k && bridge) & peers);
-        add[1 + (k >> 1)] += cwk << (16 * (k & 1));
-        add[4 + (k >> 1)] += cbk << (16 * (k & 1));
+        w += (8u >> k) * __popc(__ballot_sync(amask, cls == k) & peers);
+        b += (8u >> k) * __popc(__ballot_sync(amask, cls == k && bridge) & peers);
       }
-      add[3] = __popc(__ballot_sync(amask, cls == 4) & peers) | (__popc(__ballot_sync(amask, cls == 4 && bridge) & peers) << 16);
-      add[6] = __popc(__ballot_sync(amask, new_read) & peers) | (__popc(__ballot_sync(amask, new_read && (r.read_hash & 1ull)) & peers) << 16);
-      add[7] = __popc(__ballot_sync(amask, new_name) & peers);
-      add[0] = __popc(peers);
-      if (lead) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (add[k]) atomicAdd(&w[1 + k], add[k]);
+      const unsigned names = __popc(__ballot_sync(amask, new_name) & peers);
+      const unsigned u2 = 2u * __popc(__ballot_sync(amask, new_read && !pal) & peers) + __popc(__ballot_sync(amask, new_read && pal) & peers);
+      if (ok && lead) {
+        if (he >= 0) {
+          atomicAdd(&hot.cnt[he], group | (names << 16));
+          atomicAdd(&hot.wb[he], w | (b << 16));
+          if (u2) atomicAdd(&hot.uniq2[he], u2);
+        } else {
+          atomicAdd(&a->spanned_frags, (unsigned long long)group | ((unsigned long long)names << 32));
+          atomicAdd(&a->w_b, (unsigned long long)w | ((unsigned long long)b << 32));
+          if (u2) atomicAdd(&a->uniq2, u2);
+        }
       }
-      // extrema: only touch the word when this record improves it (reads of shared memory broadcast, atomics serialise)
-      if ((int)r.q_left > *reinterpret_cast<volatile int*>(&w[9])) atomicMax(reinterpret_cast<int*>(&w[9]), (int)r.q_left);
-      if ((int)r.q_right > *reinterpret_cast<volatile int*>(&w[10])) atomicMax(reinterpret_cast<int*>(&w[10]), (int)r.q_right);
-      if ((uint32_t)r.dist < *reinterpret_cast<volatile uint32_t*>(&w[11])) atomicMin(&w[11], (uint32_t)r.dist);
-      if ((uint32_t)r.ov < *reinterpret_cast<volatile uint32_t*>(&w[12])) atomicMin(&w[12], (uint32_t)r.ov);
-      if ((uint32_t)r.n_hits < *reinterpret_cast<volatile uint32_t*>(&w[13])) atomicMin(&w[13], (uint32_t)r.n_hits);
-      if ((unsigned long long)r.idx < *reinterpret_cast<volatile unsigned long long*>(&w[14]))
-        atomicMin(reinterpret_cast<unsigned long long*>(&w[14]), (unsigned long long)r.idx);
     }
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < ACC_ENTRIES; e += blockDim.x) {
-    const uint32_t* w = sm + e * ACC_WORDS;
-    if (w[0] == 0u) continue;
-    JAcc* a = acc + (w[0] - 1u);
-    // counters: neighbouring 32-bit fields of JAcc are bumped pairwise with one 64-bit add (the sums stay far below
-    // 2^32, so nothing carries into the upper half)
-    unsigned long long* a64 = reinterpret_cast<unsigned long long*>(a);
-    atomicAdd(a64 + 0, (unsigned long long)w[1] | ((unsigned long long)(w[2] & 0xFFFFu) << 32));        // n_spanned, cw[0]
-    if ((w[2] >> 16) | (w[3] & 0xFFFFu))
-      atomicAdd(a64 + 1, (unsigned long long)(w[2] >> 16) | ((unsigned long long)(w[3] & 0xFFFFu) << 32));  // cw[1], cw[2]
-    if ((w[3] >> 16) | (w[4] & 0xFFFFu))
-      atomicAdd(a64 + 2, (unsigned long long)(w[3] >> 16) | ((unsigned long long)(w[4] & 0xFFFFu) << 32));  // cw[3], cw_other
-    if (w[5]) atomicAdd(a64 + 3, (unsigned long long)(w[5] & 0xFFFFu) | ((unsigned long long)(w[5] >> 16) << 32));  // cb[0], cb[1]
-    if (w[6]) atomicAdd(a64 + 4, (unsigned long long)(w[6] & 0xFFFFu) | ((unsigned long long)(w[6] >> 16) << 32));  // cb[2], cb[3]
-    if (w[4] >> 16) atomicAdd(&a->cb_other, w[4] >> 16);
-    if (w[8] | (w[7] & 0xFFFFu))
-      atomicAdd(a64 + 8, (unsigned long long)w[8] | ((unsigned long long)(w[7] & 0xFFFFu) << 32));          // n_frags, n_uniq
-    if (w[7] >> 16) atomicAdd(&a->n_pal, w[7] >> 16);
-    // extrema: fire-and-forget reductions (a look-before-update variant was measured slower: the loads stall, REDs do not)
-    atomicMax(&a->max_ql, (int)w[9]);
-    atomicMax(&a->max_qr, (int)w[10]);
-    atomicMin(&a->min_dist, w[11]);
-    atomicMin(&a->min_ov, w[12]);
-    atomicMin(&a->min_nh, w[13]);
-    const unsigned long long fi = *reinterpret_cast<const unsigned long long*>(&w[14]);
-    atomicMin(&a->first_idx, fi);
+  if (dbg & 8) return;
+  for (int e = threadIdx.x; e < HOT_ENTRIES; e += blockDim.x) {
+    if (hot.tag[e] == 0u) continue;
+    JAcc2* a = acc + (hot.tag[e] - 1u);
+    extrema_to_global(a, hot.first_inv[e], hot.qmax_l[e], hot.qmax_r[e], hot.inv_dist[e], hot.inv_ov[e], hot.inv_nh[e]);
+    const unsigned c = hot.cnt[e], wb = hot.wb[e], u2 = hot.uniq2[e];
+    atomicAdd(&a->spanned_frags, (unsigned long long)(c & 0xFFFFu) | ((unsigned long long)(c >> 16) << 32));
+    atomicAdd(&a->w_b, (unsigned long long)(wb & 0xFFFFu) | ((unsigned long long)(wb >> 16) << 32));
+    if (u2) atomicAdd(&a->uniq2, u2);
   }
 }
 
-__global__ void finish_hash_kernel(int64_t nj, const JAcc* __restrict__ acc, const U128* __restrict__ jkeys,
-                                   fc_junction* __restrict__ out, uint64_t* __restrict__ order_key,
-                                   uint32_t* __restrict__ order_val) {
-  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= nj) return;
-  const JAcc a = acc[j];
-  const U128 k = jkeys[j];
+__device__ __forceinline__ fc_junction junction_from_acc(const JAcc2& a, const U128& k, unsigned long long first_idx) {
   fc_junction o;
-  o.chrom = (uint32_t)(k.lo >> 32);
+  o.chrom = (uint32_t)k.hi;
   o.start = (uint32_t)k.lo;
-  o.end = (uint32_t)(k.hi >> 32);
-  const uint32_t low = (uint32_t)k.hi;
-  o.sk = (low & 3u) | (((low >> 2) & 0xFFFu) << 16);
-  o.first_idx = a.first_idx;
-  // all weights are k/8 here (checked on the host before this path is taken): any summation order is exact
-  o.n_weighted = (8.0 * a.cw[0] + 4.0 * a.cw[1] + 2.0 * a.cw[2] + 1.0 * a.cw[3]) / 8.0;
-  o.n_uniq_bridges = (8.0 * a.cb[0] + 4.0 * a.cb[1] + 2.0 * a.cb[2] + 1.0 * a.cb[3]) / 8.0;
-  o.n_spanned = a.n_spanned;
-  o.n_frags = a.n_frags;
-  o.n_uniq = a.n_uniq - (a.n_pal + 1) / 2;
-  o.best_q_left = (int16_t)a.max_ql;
-  o.best_q_right = (int16_t)a.max_qr;
-  o.min_n_hits = (uint16_t)a.min_nh;
-  o.min_dist = (uint8_t)a.min_dist;
-  o.min_ov = (uint8_t)a.min_ov;
+  o.end = (uint32_t)(k.lo >> 32);
+  o.sk = ((uint32_t)(k.hi >> 32) & 3u) | (a.sig << 16);
+  o.first_idx = first_idx;
+  o.n_weighted = (double)(uint32_t)a.w_b / 8.0;  // exact: every weight is k/8
+  o.n_uniq_bridges = (double)(uint32_t)(a.w_b >> 32) / 8.0;
+  o.n_spanned = (uint32_t)a.spanned_frags;
+  o.n_frags = (uint32_t)(a.spanned_frags >> 32);
+  // len(uniq)/2 with uniq = {read, revcomp(read)}: a palindromic read contributes one element, not two
+  o.n_uniq = a.uniq2 / 2u;
+  o.best_q_left = (int16_t)((int)a.qmax_l - 32769);
+  o.best_q_right = (int16_t)((int)a.qmax_r - 32769);
+  o.min_n_hits = (uint16_t)~a.inv_nh;
+  o.min_dist = (uint8_t)~a.inv_dist;
+  o.min_ov = (uint8_t)~a.inv_ov;
   o.pad = 0;
-  out[j] = o;
-  order_key[j] = a.first_idx;
-  order_val[j] = (uint32_t)j;
+  return o;
+}
+
+__device__ __forceinline__ void clear_acc(JAcc2* a) {
+  uint4* p = reinterpret_cast<uint4*>(a);
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  p[0] = z;
+  p[1] = z;
+  p[2] = z;
+  p[3] = z;
+}
+
+// records in stream order: the junction whose first record sits at position p is flagged there; an exclusive scan of
+// the flags is the discovery rank
+__global__ void mark_first_kernel(const unsigned int* __restrict__ ctr, unsigned int acap, const JAcc2* __restrict__ acc,
+                                  uint32_t* __restrict__ flag) {
+  const unsigned int n_alloc = min(ctr[FC_N_ALLOC], acap);
+  for (unsigned int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_alloc; j += gridDim.x * blockDim.x) {
+    const unsigned long long sf = acc[j].spanned_frags;
+    if ((uint32_t)sf == 0u) continue;  // an id that lost its insert race
+    flag[~acc[j].first_inv] = j + 1u;
+  }
+}
+
+struct NonZero {
+  __host__ __device__ uint32_t operator()(uint32_t f) const { return f ? 1u : 0u; }
+};
+
+__global__ void finish_ordered_kernel(int64_t ub, const uint32_t* __restrict__ flag, const uint32_t* __restrict__ rank,
+                                      const fc_jrec* __restrict__ recs, JAcc2* __restrict__ acc, U128* __restrict__ keys,
+                                      fc_junction* __restrict__ out, unsigned int* __restrict__ ctr) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= ub) return;
+  const uint32_t f = flag[p];
+  if (p == ub - 1) ctr[FC_N_JUNC] = rank[p] + (f ? 1u : 0u);
+  if (!f) return;
+  JAcc2* ap = acc + (f - 1u);
+  const JAcc2 a = *ap;
+  const ulonglong2 kk = *reinterpret_cast<const ulonglong2*>(keys + a.slot);
+  out[rank[p]] = junction_from_acc(a, U128{kk.x, kk.y}, recs[p].idx);
+  keys[a.slot] = U128{0ull, 0ull};
+  clear_acc(ap);
+}
+
+// records in arbitrary order (peer-to-peer emit, explicit idx): compact in any order, sorted by first idx afterwards
+__global__ void finish_unordered_kernel(unsigned int* __restrict__ ctr, unsigned int acap, JAcc2* __restrict__ acc,
+                                        U128* __restrict__ keys, fc_junction* __restrict__ out,
+                                        uint64_t* __restrict__ order_key, uint32_t* __restrict__ order_val) {
+  const unsigned int n_alloc = min(ctr[FC_N_ALLOC], acap);
+  for (unsigned int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_alloc; j += gridDim.x * blockDim.x) {
+    const JAcc2 a = acc[j];
+    if ((uint32_t)a.spanned_frags == 0u) continue;
+    const unsigned int pos = atomicAdd(&ctr[FC_N_JUNC], 1u);
+    const ulonglong2 kk = *reinterpret_cast<const ulonglong2*>(keys + a.slot);
+    const unsigned long long first_idx = ~a.first_inv;
+    out[pos] = junction_from_acc(a, U128{kk.x, kk.y}, first_idx);
+    order_key[pos] = first_idx;
+    order_val[pos] = pos;
+    keys[a.slot] = U128{0ull, 0ull};
+    clear_acc(acc + j);
+  }
 }
 
 __global__ void finish_kernel(int64_t nj, int64_t n, const JAcc* __restrict__ acc, const fc_jrec* __restrict__ s,
@@ -651,14 +847,19 @@ static int agg_emit_impl(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, const int
   // upper bound of the record count so far (the exact count lives on the device)
   int64_t ub = a.n_recs + n;
   FC_CUDA(ctx, a.recs.reserve((size_t)ub * sizeof(fc_jrec), st, true, (size_t)a.n_recs * sizeof(fc_jrec)));
-  FC_CUDA(ctx, a.scratch[0].reserve((size_t)n * 4, st, false, 0));
   FC_CUDA(ctx, a.scratch[1].reserve((size_t)n * 4, st, false, 0));
-  uint32_t* accept = (uint32_t*)a.scratch[0].p;
   uint32_t* pos = (uint32_t*)a.scratch[1].p;
-  count_hits_kernel<<<nblk(n, 256), 256, 0, st>>>(n, d_hits, d_mask, accept);
-  FC_LAUNCH_CHECK(ctx);
-  rc = scan_u32(ctx, n, accept, pos, false, st);
-  if (rc) return rc;
+  const AcceptOp accept{d_hits, d_mask};
+  {
+    // stable compaction: position of every accepted pair among the accepted pairs of the batch
+    cub::CountingInputIterator<int64_t> iota(0);
+    cub::TransformInputIterator<uint32_t, AcceptOp, cub::CountingInputIterator<int64_t>> it(iota, accept);
+    size_t tmp = 0;
+    FC_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp, it, pos, n, st));
+    FC_CUDA(ctx, a.cub_tmp.reserve(tmp, st, false, 0));
+    FC_CUDA(ctx, cub::DeviceScan::ExclusiveSum(a.cub_tmp.p, tmp, it, pos, n, st));
+    ctx->launches += 2;
+  }
   emit_kernel<<<nblk(n, 256), 256, 0, st>>>(n, d_hits, d_mask, pos, d_chrom, d_flags, d_wden, d_q_a, d_q_b, d_read_hash,
                                             d_qname_hash, idx_base, d_idx, (const unsigned long long*)a.counters.p,
                                             (fc_jrec*)a.recs.p);
@@ -706,7 +907,8 @@ extern "C" int fc_agg_append(fc_ctx* ctx, int64_t n, const fc_jrec* d_recs, void
   FC_CUDA(ctx, a.recs.reserve((size_t)(a.n_recs + n) * sizeof(fc_jrec), st, true, (size_t)a.n_recs * sizeof(fc_jrec)));
   FC_CUDA(ctx, cudaMemcpyAsync((fc_jrec*)a.recs.p + a.n_recs, d_recs, (size_t)n * sizeof(fc_jrec), cudaMemcpyDefault, st));
   a.n_recs += n;
-  a.max_idx = ~0ull;  // records built elsewhere: their idx range is unknown
+  a.max_idx = ~0ull;  // records built elsewhere: their idx range and order are unknown
+  a.unordered = true;
   unsigned long long v = (unsigned long long)a.n_recs;
   FC_CUDA(ctx, cudaMemcpyAsync(a.counters.p, &v, sizeof(v), cudaMemcpyHostToDevice, st));
   FC_CUDA(ctx, cudaStreamSynchronize(st));
@@ -731,6 +933,7 @@ extern "C" int fc_agg_replace(fc_ctx* ctx, int64_t n, const fc_jrec* d_recs, voi
   a.n_recs = n;
   a.n_exact = true;
   a.max_idx = ~0ull;
+  a.unordered = true;
   a.n_junc = -1;
   return FC_OK;
 }
@@ -795,69 +998,148 @@ extern "C" int fc_agg_partition(fc_ctx* ctx, int32_t n_ranks, fc_jrec* d_out, in
   return FC_OK;
 }
 
-// sort-free path; returns -100 when the input needs the sort-based path (non power-of-two weight denominators)
-static int64_t finalize_hash(fc_ctx* ctx, int64_t n, cudaStream_t st) {
+// reserve a table that the fused path keeps clean between calls; a (re)allocation hands out fresh memory: zero it
+static int reserve_clean(fc_ctx* ctx, fc_dbuf& b, size_t bytes, cudaStream_t st) {
+  if (bytes <= b.cap) return FC_OK;
+  FC_CUDA(ctx, b.reserve(bytes, st, false, 0));
+  FC_CUDA(ctx, cudaMemsetAsync(b.p, 0, b.cap, st));
+  return FC_OK;
+}
+
+// FC_AGG_TIMING=1: per-stage device times of the sort-free path on stderr (CUDA events on the caller's stream)
+struct StageTimer {
+  bool on;
+  cudaStream_t st;
+  int n = 0;
+  cudaEvent_t ev[12];
+  const char* name[12];
+  explicit StageTimer(cudaStream_t s) : st(s) {
+    static int flag = -1;
+    if (flag < 0) {
+      const char* e = getenv("FC_AGG_TIMING");
+      flag = (e && e[0] == '1') ? 1 : 0;
+    }
+    on = flag == 1;
+  }
+  void mark(const char* what) {
+    if (!on || n >= 12) return;
+    cudaEventCreate(&ev[n]);
+    cudaEventRecord(ev[n], st);
+    name[n++] = what;
+  }
+  void report() {
+    if (!on) return;
+    for (int k = 1; k < n; ++k) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[k - 1], ev[k]);
+      fprintf(stderr, "%s%s %.1f us", k == 1 ? "[fc_agg_finalize] " : ", ", name[k], ms * 1000.f);
+    }
+    fprintf(stderr, "\n");
+    for (int k = 0; k < n; ++k) cudaEventDestroy(ev[k]);
+    n = 0;
+  }
+};
+
+// sort-free path over the `ub` (upper bound; the exact count is on the device) records of the context; returns -100
+// when the input needs the sort-based path (a weight denominator that is not 1, 2, 4 or 8; too many records)
+static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st) {
   fc_agg& a = ctx->agg;
-  unsigned long long cap = 1024;
-  while (cap < 2ull * (unsigned long long)n) cap <<= 1;
-  FC_CUDA(ctx, a.htab[2].reserve((size_t)cap * 16, st, false, 0));  // junction keys
-  for (int k = 0; k < 3; ++k) {
-    if (k < 2) FC_CUDA(ctx, a.htab[k].reserve((size_t)cap * 16, st, false, 0));
-    FC_CUDA(ctx, cudaMemsetAsync(a.htab[k].p, 0, (size_t)cap * 16, st));
+  if (ub >= FUSED_MAX_RECORDS) return -100;
+  unsigned long long kcap = 1024;
+  while (kcap < 2ull * (unsigned long long)ub) kcap <<= 1;
+  const unsigned long long scap = 2ull * kcap;  // two inserts per record
+  const unsigned int acap = (unsigned int)(ub + ub / 8 + 65536);  // junction ids incl. the ones lost to insert races
+  int rc;
+  StageTimer tm(st);
+  tm.mark("start");
+  if (a.f_dirty) {  // an earlier call failed half-way: start from clean tables
+    a.f_keys.release();
+    a.f_sets.release();
+    a.f_acc.release();
+    a.f_dirty = false;
   }
-  FC_CUDA(ctx, a.scratch[0].reserve((size_t)cap * 4, st, false, 0));   // slot -> junction id
-  FC_CUDA(ctx, a.scratch[1].reserve((size_t)n * 16, st, false, 0));    // junction id -> key
-  FC_CUDA(ctx, a.scratch[2].reserve((size_t)n * 4, st, false, 0));     // record -> slot
-  uint32_t* slot_jid = (uint32_t*)a.scratch[0].p;
-  U128* jkeys = (U128*)a.scratch[1].p;
-  uint32_t* rec_slot = (uint32_t*)a.scratch[2].p;
+  if ((rc = reserve_clean(ctx, a.f_keys, (size_t)kcap * 16, st))) return rc;
+  if ((rc = reserve_clean(ctx, a.f_acc, (size_t)acap * sizeof(JAcc2), st))) return rc;
+  FC_CUDA(ctx, a.f_sets.reserve((size_t)scap * 16, st, false, 0));
+  FC_CUDA(ctx, cudaMemsetAsync(a.f_sets.p, 0, (size_t)scap * 16, st));
+  FC_CUDA(ctx, a.junctions.reserve((size_t)ub * sizeof(fc_junction), st, false, 0));
   unsigned long long* counters = (unsigned long long*)a.counters.p;
-  unsigned int* n_junc = (unsigned int*)(counters + 2);
-  unsigned int* n_other = (unsigned int*)(counters + 3);
-  FC_CUDA(ctx, cudaMemsetAsync(counters + 2, 0, 2 * sizeof(unsigned long long), st));
-  assign_kernel<<<nblk(n, 256), 256, 0, st>>>(n, (const fc_jrec*)a.recs.p, (U128*)a.htab[2].p, cap - 1, slot_jid, jkeys, n_junc,
-                                              n_other, rec_slot);
+  unsigned int* ctr = (unsigned int*)(counters + 8);
+  FC_CUDA(ctx, cudaMemsetAsync(ctr, 0, 4 * sizeof(unsigned int), st));
+  const bool ordered = !a.unordered;
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("FC_AGG_SKIP"); dbg = e ? atoi(e) : 0; }
+  a.f_dirty = true;  // until the finish kernel has run
+  tm.mark("clear");
+  uint32_t* flag = nullptr;
+  uint32_t* rank = nullptr;
+  if (ordered) {
+    FC_CUDA(ctx, a.scratch[0].reserve((size_t)ub * 4, st, false, 0));
+    FC_CUDA(ctx, a.scratch[1].reserve((size_t)ub * 4, st, false, 0));
+    flag = (uint32_t*)a.scratch[0].p;
+    rank = (uint32_t*)a.scratch[1].p;
+    fused_accumulate_kernel<true><<<nblk(ub, ACC_THREADS), ACC_THREADS, 0, st>>>(ub, counters, (const fc_jrec*)a.recs.p, (U128*)a.f_keys.p,
+                                                                 kcap - 1, (U128*)a.f_sets.p, scap - 1, (JAcc2*)a.f_acc.p, acap,
+                                                                 ctr, flag, dbg);
+  } else {
+    fused_accumulate_kernel<false><<<nblk(ub, ACC_THREADS), ACC_THREADS, 0, st>>>(ub, counters, (const fc_jrec*)a.recs.p, (U128*)a.f_keys.p,
+                                                                  kcap - 1, (U128*)a.f_sets.p, scap - 1, (JAcc2*)a.f_acc.p, acap,
+                                                                  ctr, nullptr, dbg);
+  }
   FC_LAUNCH_CHECK(ctx);
-  unsigned long long h[2] = {0, 0};
-  FC_CUDA(ctx, cudaMemcpyAsync(h, counters + 2, sizeof(h), cudaMemcpyDeviceToHost, st));
+  tm.mark("accumulate");
+  const unsigned sweep_blocks = (unsigned)ctx->sm_count * 8u;
+  uint64_t* kA = nullptr;
+  uint64_t* kB = nullptr;
+  uint32_t* vA = nullptr;
+  fc_junction* tmpj = nullptr;
+  if (ordered) {
+    mark_first_kernel<<<sweep_blocks, 256, 0, st>>>(ctr, acap, (const JAcc2*)a.f_acc.p, flag);
+    FC_LAUNCH_CHECK(ctx);
+    cub::TransformInputIterator<uint32_t, NonZero, const uint32_t*> it(flag, NonZero());
+    size_t tmp = 0;
+    FC_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp, it, rank, ub, st));
+    FC_CUDA(ctx, a.cub_tmp.reserve(tmp, st, false, 0));
+    FC_CUDA(ctx, cub::DeviceScan::ExclusiveSum(a.cub_tmp.p, tmp, it, rank, ub, st));
+    ctx->launches += 2;
+    tm.mark("mark+rank");
+    finish_ordered_kernel<<<nblk(ub, 256), 256, 0, st>>>(ub, flag, rank, (const fc_jrec*)a.recs.p, (JAcc2*)a.f_acc.p,
+                                                         (U128*)a.f_keys.p, (fc_junction*)a.junctions.p, ctr);
+    FC_LAUNCH_CHECK(ctx);
+  } else {
+    FC_CUDA(ctx, a.scratch[5].reserve((size_t)ub * sizeof(fc_junction), st, false, 0));
+    FC_CUDA(ctx, a.scratch[3].reserve((size_t)ub * 8, st, false, 0));
+    FC_CUDA(ctx, a.scratch[4].reserve((size_t)ub * 8, st, false, 0));
+    FC_CUDA(ctx, a.scratch[6].reserve((size_t)ub * 8, st, false, 0));
+    tmpj = (fc_junction*)a.scratch[5].p;
+    kA = (uint64_t*)a.scratch[3].p;
+    kB = (uint64_t*)a.scratch[4].p;
+    vA = (uint32_t*)a.scratch[6].p;
+    finish_unordered_kernel<<<sweep_blocks, 256, 0, st>>>(ctr, acap, (JAcc2*)a.f_acc.p, (U128*)a.f_keys.p, tmpj, kA, vA);
+    FC_LAUNCH_CHECK(ctx);
+  }
+  // one round trip: exact record count, junction count, fallback conditions, peer-to-peer overflow
+  tm.mark("finish");
+  unsigned long long h[10];
+  FC_CUDA(ctx, cudaMemcpyAsync(h, counters, sizeof(h), cudaMemcpyDeviceToHost, st));
+  tm.mark("copy");
   FC_CUDA(ctx, cudaStreamSynchronize(st));
-  if ((unsigned int)h[1] != 0) return -100;
-  const int64_t nj = (unsigned int)h[0];
-  FC_CUDA(ctx, a.scratch[7].reserve((size_t)nj * sizeof(JAcc), st, false, 0));
-  JAcc* acc = (JAcc*)a.scratch[7].p;
-  acc_init_kernel<<<nblk(nj, 256), 256, 0, st>>>(nj, acc);
-  FC_LAUNCH_CHECK(ctx);
-  const size_t smem = (size_t)ACC_ENTRIES * ACC_WORDS * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
-    FC_CUDA(ctx, cudaFuncSetAttribute(accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+  tm.report();
+  a.f_dirty = false;
+  a.n_recs = (int64_t)h[0];
+  a.n_exact = true;
+  if (a.p2p_enabled && h[4])
+    return fc_fail(ctx, FC_E_NOMEM, "peer-to-peer record buffer overflow (%llu records dropped): raise the capacity", h[4]);
+  const unsigned int n_other = (unsigned int)(h[8] >> 32), n_overflow = (unsigned int)h[9];
+  const int64_t nj = (int64_t)(h[9] >> 32);
+  if (n_other || n_overflow) return -100;
+  if (!ordered && nj > 0) {
+    uint32_t* vB = vA + ub;
+    rc = sort_pairs_u64_u32(ctx, nj, kA, kB, vA, vB, 0, 64, st);
+    if (rc) return rc;
+    gather_junctions_kernel<<<nblk(nj, 256), 256, 0, st>>>(nj, tmpj, vB, (fc_junction*)a.junctions.p);
+    FC_LAUNCH_CHECK(ctx);
   }
-  const int per_block = 256 * ACC_RECS_PER_THREAD;
-  accumulate_kernel<<<(unsigned)((n + per_block - 1) / per_block), 256, smem, st>>>(
-      n, (const fc_jrec*)a.recs.p, rec_slot, slot_jid, (U128*)a.htab[0].p, (U128*)a.htab[1].p, cap - 1, acc);
-  FC_LAUNCH_CHECK(ctx);
-  FC_CUDA(ctx, a.junctions.reserve((size_t)nj * sizeof(fc_junction), st, false, 0));
-  FC_CUDA(ctx, a.scratch[5].reserve((size_t)nj * sizeof(fc_junction), st, false, 0));
-  FC_CUDA(ctx, a.scratch[3].reserve((size_t)nj * 8, st, false, 0));
-  FC_CUDA(ctx, a.scratch[4].reserve((size_t)nj * 8, st, false, 0));
-  FC_CUDA(ctx, a.scratch[6].reserve((size_t)nj * 8, st, false, 0));
-  fc_junction* tmpj = (fc_junction*)a.scratch[5].p;
-  uint64_t* kA = (uint64_t*)a.scratch[3].p;
-  uint64_t* kB = (uint64_t*)a.scratch[4].p;
-  uint32_t* vA = (uint32_t*)a.scratch[6].p;
-  uint32_t* vB = vA + nj;
-  finish_hash_kernel<<<nblk(nj, 128), 128, 0, st>>>(nj, acc, jkeys, tmpj, kA, vA);
-  FC_LAUNCH_CHECK(ctx);
-  int order_bits = 64;
-  if (a.max_idx != ~0ull) {
-    order_bits = 1;
-    while (order_bits < 64 && (a.max_idx >> order_bits)) order_bits++;
-  }
-  int rc = sort_pairs_u64_u32(ctx, nj, kA, kB, vA, vB, 0, order_bits, st);
-  if (rc) return rc;
-  gather_junctions_kernel<<<nblk(nj, 256), 256, 0, st>>>(nj, tmpj, vB, (fc_junction*)a.junctions.p);
-  FC_LAUNCH_CHECK(ctx);
   a.n_junc = nj;
   return nj;
 }
@@ -866,22 +1148,12 @@ extern "C" int64_t fc_agg_finalize(fc_ctx* ctx, void* stream) {
   if (!ctx) return FC_E_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   fc_agg& a = ctx->agg;
-  int rc = sync_n_recs(ctx, st);
-  if (rc) return rc;
-  const int64_t n = a.n_recs;
-  if (n == 0) {
+  if (!a.counters.p || (a.n_exact && a.n_recs == 0)) {
+    a.n_recs = 0;
     a.n_junc = 0;
     return 0;
   }
-  if (n >= (1ll << 32)) return fc_fail(ctx, FC_E_ARG, "more than 2^32 records on one device");
-  rc = ensure_counters(ctx, st);
-  if (rc) return rc;
-  if (a.p2p_enabled) {
-    unsigned long long ovf = 0;
-    FC_CUDA(ctx, cudaMemcpyAsync(&ovf, (unsigned long long*)a.counters.p + 4, sizeof(ovf), cudaMemcpyDeviceToHost, st));
-    FC_CUDA(ctx, cudaStreamSynchronize(st));
-    if (ovf) return fc_fail(ctx, FC_E_NOMEM, "peer-to-peer record buffer overflow (%llu records dropped): raise the capacity", ovf);
-  }
+  if (a.n_recs >= (1ll << 32)) return fc_fail(ctx, FC_E_ARG, "more than 2^32 records on one device");
   // FC_AGG_MODE=sort forces the sort-based path (tests compare the two)
   static int mode = -1;
   if (mode < 0) {
@@ -889,8 +1161,22 @@ extern "C" int64_t fc_agg_finalize(fc_ctx* ctx, void* stream) {
     mode = (e && e[0] == 's') ? 1 : 0;
   }
   if (mode == 0) {
-    const int64_t r = finalize_hash(ctx, n, st);
+    // no host round trip before the kernels: they are sized by the upper bound and read the exact count on the device
+    const int64_t r = finalize_fused(ctx, a.n_recs, st);
     if (r != -100) return r;
+  }
+  int rc = sync_n_recs(ctx, st);
+  if (rc) return rc;
+  const int64_t n = a.n_recs;
+  if (n == 0) {
+    a.n_junc = 0;
+    return 0;
+  }
+  if (a.p2p_enabled) {
+    unsigned long long ovf = 0;
+    FC_CUDA(ctx, cudaMemcpyAsync(&ovf, (unsigned long long*)a.counters.p + 4, sizeof(ovf), cudaMemcpyDeviceToHost, st));
+    FC_CUDA(ctx, cudaStreamSynchronize(st));
+    if (ovf) return fc_fail(ctx, FC_E_NOMEM, "peer-to-peer record buffer overflow (%llu records dropped): raise the capacity", ovf);
   }
   // scratch layout
   FC_CUDA(ctx, a.scratch[0].reserve((size_t)n * 8, st, false, 0));  // u64 A
@@ -1171,4 +1457,7 @@ void fc_agg_release(fc_ctx* ctx) {
   a.cub_tmp.release();
   a.counters.release();
   for (auto& h : a.htab) h.release();
+  a.f_keys.release();
+  a.f_sets.release();
+  a.f_acc.release();
 }

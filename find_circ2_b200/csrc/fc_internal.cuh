@@ -68,7 +68,10 @@ struct fc_agg {
   fc_dbuf scratch[8];
   fc_dbuf cub_tmp;
   fc_dbuf counters;     // small device counters
-  fc_dbuf htab[3];      // hash sets for the distinct counts (reads, fragment names) and the junction-key table
+  fc_dbuf htab[3];      // sort-based path: hash sets for the distinct counts (reads, fragment names)
+  // sort-free path: junction-key table and accumulators (kept clean between calls), distinct set
+  fc_dbuf f_keys, f_sets, f_acc;
+  bool f_dirty = false;
 };
 
 struct fc_ctx {

@@ -429,3 +429,86 @@ sys.stdout.buffer.write(j.tobytes())
         outs.append(r.stdout)
     assert len(outs[0]) > 64 * 1000
     assert outs[0] == outs[1]
+
+
+def _emit_records(torch, e, recs, idx_base, rng, batches=3, reject_frac=0.2):
+    """feed fc_jrec rows through fc_agg_emit (hits + payload columns on the device), interleaved with pairs that found no
+    breakpoint; idx of the records must be idx_base + row position in the interleaved stream -> returns the rows with
+    their idx rewritten accordingly"""
+    from find_circ2_b200._lib import HIT_DTYPE
+
+    n_acc = len(recs)
+    n = n_acc + int(n_acc * reject_frac) + 3
+    accept = np.zeros(n, dtype=bool)
+    accept[rng.choice(n, size=n_acc, replace=False)] = True
+    pos = np.flatnonzero(accept)
+    hits = np.zeros(n, dtype=HIT_DTYPE)
+    hits["start"][pos] = recs["start"].astype(np.int64).astype(np.int32)
+    hits["end"][pos] = recs["end"].astype(np.int64).astype(np.int32)
+    sk = recs["sk"].astype(np.uint32)
+    hits["w2"][pos] = recs["n_hits"].astype(np.uint32) | (recs["dist"].astype(np.uint32) << 16) | (recs["ov"].astype(np.uint32) << 24)
+    hits["w3"][pos] = (sk & 1) | (((sk >> 16) & 0xFFF) << 1)
+    back = (sk & 2) == 0
+    chrom = np.zeros(n, dtype=np.int32)
+    chrom[pos] = recs["chrom"]
+    flags = np.zeros(n, dtype=np.uint8)
+    flags[pos] = back.astype(np.uint8)  # FC_PF_BACKSPLICE = 1
+    wden = np.ones(n, dtype=np.uint8)
+    wden[pos] = (sk >> 8) & 0xFF
+    q_a = np.zeros(n, dtype=np.int16)
+    q_b = np.zeros(n, dtype=np.int16)
+    q_a[pos] = np.where(back, recs["q_right"], recs["q_left"])
+    q_b[pos] = np.where(back, recs["q_left"], recs["q_right"])
+    rh = rng.integers(0, 1 << 62, n).astype(np.uint64)
+    qh = rng.integers(0, 1 << 62, n).astype(np.uint64)
+    rh[pos] = recs["read_hash"]
+    qh[pos] = recs["qname_hash"]
+    dev = torch.device("cuda:0")
+    tn = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    d_hits = tn(hits.view(np.int32))
+    cols = [tn(chrom), tn(flags), tn(wden), tn(q_a), tn(q_b), tn(rh.view(np.int64)), tn(qh.view(np.int64))]
+    cuts = np.linspace(0, n, batches + 1).astype(int)
+    for lo, hi in zip(cuts, cuts[1:]):
+        if hi > lo:
+            e.agg_emit(hi - lo, d_hits[4 * lo:], *[c[lo:] for c in cols], idx_base + lo, 0)
+    out = recs.copy()
+    out["idx"] = idx_base + pos
+    # bit 2 of sk mirrors the palindrome flag of the read hash (set by the emit kernel)
+    out["sk"] = (out["sk"] & ~np.uint32(4)) | ((out["read_hash"] & np.uint64(1)).astype(np.uint32) << 2)
+    return out
+
+
+POW2 = (1, 1, 1, 2, 2, 4, 8)
+
+
+@pytest.mark.parametrize("hot", [False, True])
+def test_sort_free_aggregation_repeated_calls(torch_cuda, hot):
+    """the sort-free path keeps its key table and accumulators between calls (the finish kernel clears what it consumed):
+    many calls of different sizes on one engine, records in stream order (fc_agg_emit) and in arbitrary
+    order (fc_agg_append), with and without one junction that collects a third of the records"""
+    torch = torch_cuda
+    e = _engine()
+    rng = np.random.default_rng(99)
+    for rep, (n, n_keys) in enumerate([(40000, 900), (700, 40), (150000, 30000), (5, 2), (90000, 17), (150000, 2500), (1, 1),
+                                       (60000, 60000)]):
+        recs = _random_records(n, n_keys, 1000 + rep, dens=POW2)
+        if hot and n > 100:
+            sel = rng.random(n) < 0.34
+            for f in ("chrom", "start", "end"):
+                recs[f][sel] = recs[f][0]
+            recs["sk"][sel] = (recs["sk"][sel] & ~np.uint32(3)) | (recs["sk"][0] & np.uint32(3))
+        e.agg_reset()
+        if rep % 2 == 0:
+            recs = _emit_records(torch, e, recs, 5000 + rep, rng)
+        else:
+            order = rng.permutation(n)
+            e.agg_append_host(recs[order])
+        nj = e.agg_finalize()
+        got = _junction_rows(e.agg_fetch(nj))
+        want = _py_aggregate(recs[np.argsort(recs["idx"], kind="stable")])
+        assert e.agg_n_records() == n
+        assert len(got) == len(want), (rep, n, len(got), len(want))
+        assert got == want, rep
+        assert e.agg_finalize() == nj  # idempotent: the tables were left clean
+        assert _junction_rows(e.agg_fetch(nj)) == want
+    e.close()
