@@ -63,35 +63,49 @@ static_assert(offsetof(JAcc, cw) == 4 && offsetof(JAcc, cb) == 24 && offsetof(JA
                   offsetof(JAcc, n_uniq) == 68 && offsetof(JAcc, first_idx) == 80,
               "accumulate_kernel's 64-bit pair adds depend on this layout");
 
-// accepted = the scan found a breakpoint and the caller's mask (if any) keeps the pair
-struct AcceptOp {
-  const fc_hit* hits;
-  const uint8_t* mask;
-  __host__ __device__ uint32_t operator()(int64_t i) const {
-    return ((hits[i].w2 & 0xFFFFu) && (!mask || mask[i])) ? 1u : 0u;
+// One record per accepted pair (the scan found a breakpoint and the caller's mask, if any, keeps the pair).  The CTA
+// claims its slots with one atomic on the record counter, so the buffer is NOT in stream order: every consumer orders
+// by fc_jrec.idx where order matters (discovery rank, sequential float sums of the sort-based path).
+__global__ void __launch_bounds__(256) emit_kernel(int64_t n, const fc_hit* __restrict__ hits, const uint8_t* __restrict__ mask,
+                                                   const int32_t* __restrict__ chrom, const uint8_t* __restrict__ flags,
+                                                   const uint8_t* __restrict__ wden, const int16_t* __restrict__ q_a,
+                                                   const int16_t* __restrict__ q_b, const uint64_t* __restrict__ read_hash,
+                                                   const uint64_t* __restrict__ qname_hash, uint64_t idx_base,
+                                                   const uint64_t* __restrict__ idx, unsigned long long* __restrict__ n_recs,
+                                                   fc_jrec* __restrict__ recs) {
+  __shared__ unsigned int s_warp[8];
+  __shared__ unsigned long long s_base;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  fc_hit h = {0, 0, 0u, 0u};
+  bool accept = false;
+  if (i < n) {
+    h = hits[i];
+    accept = (h.w2 & 0xFFFFu) != 0u && (!mask || mask[i]);
   }
-};
-
-__global__ void emit_kernel(int64_t n, const fc_hit* __restrict__ hits, const uint8_t* __restrict__ mask,
-                            const uint32_t* __restrict__ pos,
-                            const int32_t* __restrict__ chrom, const uint8_t* __restrict__ flags,
-                            const uint8_t* __restrict__ wden, const int16_t* __restrict__ q_a,
-                            const int16_t* __restrict__ q_b, const uint64_t* __restrict__ read_hash,
-                            const uint64_t* __restrict__ qname_hash, uint64_t idx_base, const uint64_t* __restrict__ idx,
-                            const unsigned long long* __restrict__ n_recs, fc_jrec* __restrict__ recs) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  fc_hit h = hits[i];
-  if ((h.w2 & 0xFFFFu) == 0) return;
-  if (mask && !mask[i]) return;
-  uint32_t fl = flags[i];
-  bool backsplice = fl & FC_PF_BACKSPLICE;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned ballot = __ballot_sync(0xffffffffu, accept);
+  if (lane == 0) s_warp[warp] = __popc(ballot);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const unsigned int c = s_warp[w];
+      s_warp[w] = total;
+      total += c;
+    }
+    s_base = total ? atomicAdd(n_recs, (unsigned long long)total) : 0ull;
+  }
+  __syncthreads();
+  if (!accept) return;
+  const uint32_t fl = flags[i];
+  const bool backsplice = fl & FC_PF_BACKSPLICE;
   fc_jrec r;
   r.chrom = (uint32_t)chrom[i];
   r.start = (uint32_t)h.start;
   r.end = (uint32_t)h.end;
-  uint32_t strand = h.w3 & 1u, sig = (h.w3 >> 1) & 0xFFFu;
-  uint64_t rh = read_hash[i];
+  const uint32_t strand = h.w3 & 1u, sig = (h.w3 >> 1) & 0xFFFu;
+  const uint64_t rh = read_hash[i];
   r.sk = strand | (backsplice ? 0u : 2u) | ((uint32_t)(rh & 1ull) << 2) | ((uint32_t)wden[i] << 8) | (sig << 16);
   r.idx = idx ? idx[i] : idx_base + (uint64_t)i;
   r.read_hash = rh;
@@ -102,11 +116,11 @@ __global__ void emit_kernel(int64_t n, const fc_hit* __restrict__ hits, const ui
   r.n_hits = (uint16_t)(h.w2 & 0xFFFFu);
   r.dist = (uint8_t)((h.w2 >> 16) & 0xFFu);
   r.ov = (uint8_t)(h.w2 >> 24);
-  recs[*n_recs + pos[i]] = r;
-}
-
-__global__ void bump_kernel(unsigned long long* n_recs, const uint32_t* __restrict__ pos, AcceptOp accept, int64_t n) {
-  *n_recs += (unsigned long long)pos[n - 1] + accept(n - 1);
+  uint4* dst = reinterpret_cast<uint4*>(recs + (s_base + s_warp[warp] + __popc(ballot & ((1u << lane) - 1u))));
+  const uint4* src = reinterpret_cast<const uint4*>(&r);
+  dst[0] = src[0];
+  dst[1] = src[1];
+  dst[2] = src[2];
 }
 
 __global__ void key_hash_kernel(int64_t n, const fc_jrec* __restrict__ recs, uint64_t seed, uint64_t* __restrict__ h,
@@ -399,13 +413,13 @@ __device__ __forceinline__ void extrema_to_global(JAcc2* a, unsigned long long f
   if (inh > e1.z) atomicMax(&a->inv_nh, inh);
 }
 
-template <bool ORDERED>
 __global__ void __launch_bounds__(ACC_THREADS) fused_accumulate_kernel(int64_t ub, const unsigned long long* __restrict__ n_ptr,
                                                                const fc_jrec* __restrict__ recs, U128* __restrict__ keys,
                                                                unsigned long long kmask, U128* __restrict__ sets,
                                                                unsigned long long smask, JAcc2* __restrict__ acc,
                                                                unsigned int acap, unsigned int* __restrict__ ctr,
-                                                               uint32_t* __restrict__ flag, int dbg) {
+                                                               uint32_t* __restrict__ flag, int64_t n_flag,
+                                                               uint32_t* __restrict__ tile_count, int64_t n_tiles) {
   __shared__ HotTable hot;
   __shared__ unsigned int sketch[1 << SKETCH_BITS];
   for (int e = threadIdx.x; e < (1 << SKETCH_BITS); e += blockDim.x) sketch[e] = 0u;
@@ -417,7 +431,9 @@ __global__ void __launch_bounds__(ACC_THREADS) fused_accumulate_kernel(int64_t u
   __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t n = min((int64_t)*n_ptr, ub);  // (a peer-to-peer counter keeps counting past the capacity)
-  if (ORDERED && i < ub) flag[i] = 0u;
+  // the rank flags and tile counters of the finish pass are cleared on the way
+  for (int64_t k = i; k < n_flag; k += (int64_t)gridDim.x * blockDim.x) flag[k] = 0u;
+  for (int64_t k = i; k < n_tiles; k += (int64_t)gridDim.x * blockDim.x) tile_count[k] = 0u;
   const bool active = i < n;
   const unsigned amask = __ballot_sync(0xffffffffu, active);
   uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0, r2 = r0;
@@ -495,10 +511,9 @@ __global__ void __launch_bounds__(ACC_THREADS) fused_accumulate_kernel(int64_t u
     }
 
     // ---- extrema
-    const unsigned long long f = ~(ORDERED ? (unsigned long long)i : idx);
+    const unsigned long long f = ~idx;
     const unsigned ql = (unsigned)(q_left + 32769), qr = (unsigned)(q_right + 32769);
-    if (dbg & 2) {
-    } else if (he >= 0) {
+    if (he >= 0) {
       if (f > hot.first_inv[he]) atomicMax(&hot.first_inv[he], f);
       if (ql > hot.qmax_l[he]) atomicMax(&hot.qmax_l[he], ql);
       if (qr > hot.qmax_r[he]) atomicMax(&hot.qmax_r[he], qr);
@@ -512,7 +527,7 @@ __global__ void __launch_bounds__(ACC_THREADS) fused_accumulate_kernel(int64_t u
     // ---- distinct reads / fragment names of the junction
     const unsigned long long tag = (unsigned long long)(jid + 1u);  // never 0: no entry is all-zero
     bool new_read = false, new_name = false;
-    if (ok && !(dbg & 1)) set_insert2(sets, smask, read_hash, tag, s_read, qname_hash, tag | (1ull << 32), s_name, new_read, new_name);
+    if (ok) set_insert2(sets, smask, read_hash, tag, s_read, qname_hash, tag | (1ull << 32), s_name, new_read, new_name);
 
     // ---- counters
     const unsigned den = (sk >> 8) & 0xFFu;
@@ -521,8 +536,7 @@ __global__ void __launch_bounds__(ACC_THREADS) fused_accumulate_kernel(int64_t u
     const unsigned fx = cls < 4 ? (8u >> cls) : 0u;
     const bool bridge = q_left != 0 && q_right != 0;
     const bool pal = read_hash & 1ull;
-    if (dbg & 4) {
-    } else if (__all_sync(amask, group == 1u)) {
+    if (__all_sync(amask, group == 1u)) {
       // no two lanes of the warp share a junction (the usual case)
       if (he >= 0) {
         atomicAdd(&hot.cnt[he], 1u | ((unsigned)new_name << 16));
@@ -556,7 +570,6 @@ __global__ void __launch_bounds__(ACC_THREADS) fused_accumulate_kernel(int64_t u
     }
   }
   __syncthreads();
-  if (dbg & 8) return;
   for (int e = threadIdx.x; e < HOT_ENTRIES; e += blockDim.x) {
     if (hot.tag[e] == 0u) continue;
     JAcc2* a = acc + (hot.tag[e] - 1u);
@@ -599,36 +612,96 @@ __device__ __forceinline__ void clear_acc(JAcc2* a) {
   p[3] = z;
 }
 
-// records in stream order: the junction whose first record sits at position p is flagged there; an exclusive scan of
-// the flags is the discovery rank
+// Discovery order when the idx values of the records fill a known, dense range [idx_lo, idx_lo + range): the junction
+// whose smallest idx is v is flagged at v - idx_lo; its rank is the number of flags before it.  Flags are counted per
+// tile of RANK_TILE positions while they are set; the finish kernel adds the counts of the tiles before its own
+// (given, or summed here when there are few tiles) to a block-wide scan of its tile.
+constexpr int RANK_TILE = 1024;
+
 __global__ void mark_first_kernel(const unsigned int* __restrict__ ctr, unsigned int acap, const JAcc2* __restrict__ acc,
-                                  uint32_t* __restrict__ flag) {
+                                  unsigned long long idx_lo, uint32_t* __restrict__ flag, uint32_t* __restrict__ tile_count) {
   const unsigned int n_alloc = min(ctr[FC_N_ALLOC], acap);
-  for (unsigned int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_alloc; j += gridDim.x * blockDim.x) {
-    const unsigned long long sf = acc[j].spanned_frags;
-    if ((uint32_t)sf == 0u) continue;  // an id that lost its insert race
-    flag[~acc[j].first_inv] = j + 1u;
+  const unsigned int step = gridDim.x * blockDim.x;
+  for (unsigned int j0 = blockIdx.x * blockDim.x; j0 < n_alloc; j0 += step) {  // warp-uniform trip count
+    const unsigned int j = j0 + threadIdx.x;
+    bool real = false;
+    unsigned long long p = 0;
+    if (j < n_alloc && (uint32_t)acc[j].spanned_frags != 0u) {  // (0: an id that lost its insert race)
+      real = true;
+      p = ~acc[j].first_inv - idx_lo;
+      flag[p] = j + 1u;
+    }
+    // early ids are early discoveries: neighbouring lanes mostly hit the same tile, so count once per warp and tile
+    const unsigned int tile = real ? (unsigned int)(p / RANK_TILE) : 0xFFFFFFFFu;
+    const unsigned peers = __match_any_sync(0xffffffffu, tile);
+    if (real && (int)(threadIdx.x & 31) == __ffs((int)peers) - 1) atomicAdd(&tile_count[tile], (unsigned int)__popc(peers));
   }
 }
 
-struct NonZero {
-  __host__ __device__ uint32_t operator()(uint32_t f) const { return f ? 1u : 0u; }
-};
+constexpr int FINISH_THREADS = 256;
+constexpr int FINISH_ITEMS = RANK_TILE / FINISH_THREADS;
+static_assert(FINISH_ITEMS == 4, "finish_dense_kernel reads the flags of a thread as one uint4");
 
-__global__ void finish_ordered_kernel(int64_t ub, const uint32_t* __restrict__ flag, const uint32_t* __restrict__ rank,
-                                      const fc_jrec* __restrict__ recs, JAcc2* __restrict__ acc, U128* __restrict__ keys,
-                                      fc_junction* __restrict__ out, unsigned int* __restrict__ ctr) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= ub) return;
-  const uint32_t f = flag[p];
-  if (p == ub - 1) ctr[FC_N_JUNC] = rank[p] + (f ? 1u : 0u);
-  if (!f) return;
-  JAcc2* ap = acc + (f - 1u);
-  const JAcc2 a = *ap;
-  const ulonglong2 kk = *reinterpret_cast<const ulonglong2*>(keys + a.slot);
-  out[rank[p]] = junction_from_acc(a, U128{kk.x, kk.y}, recs[p].idx);
-  keys[a.slot] = U128{0ull, 0ull};
-  clear_acc(ap);
+__global__ void __launch_bounds__(FINISH_THREADS) finish_dense_kernel(int64_t range, unsigned long long idx_lo,
+                                                                       const uint32_t* __restrict__ flag,
+                                                                       const uint32_t* __restrict__ tile_count,
+                                                                       const uint32_t* __restrict__ tile_base,
+                                                                       JAcc2* __restrict__ acc, U128* __restrict__ keys,
+                                                                       fc_junction* __restrict__ out, unsigned int* __restrict__ ctr,
+                                                                       const unsigned long long* __restrict__ counters,
+                                                                       unsigned long long* __restrict__ h_counters) {
+  typedef cub::BlockScan<uint32_t, FINISH_THREADS> Scan;
+  typedef cub::BlockReduce<uint32_t, FINISH_THREADS> Reduce;
+  __shared__ union {
+    typename Scan::TempStorage scan;
+    typename Reduce::TempStorage reduce;
+  } tmp;
+  __shared__ uint32_t s_base;
+  const bool last = blockIdx.x == gridDim.x - 1;
+  const uint32_t mine = tile_count[blockIdx.x];
+  if (mine == 0u && !last) return;  // (block-uniform) nothing was discovered in this stretch of the stream
+  if (tile_base) {
+    if (threadIdx.x == 0) s_base = tile_base[blockIdx.x];
+  } else {
+    uint32_t part = 0;
+    for (unsigned int t = threadIdx.x; t < blockIdx.x; t += FINISH_THREADS) part += tile_count[t];
+    const uint32_t before = Reduce(tmp.reduce).Sum(part);
+    if (threadIdx.x == 0) s_base = before;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    // everything the host wants to know, written straight into its (mapped, pinned) memory: no copy to wait for
+    ctr[FC_N_JUNC] = s_base + mine;
+    __threadfence();
+    for (int k = 0; k < 10; ++k) h_counters[k] = counters[k];
+    h_counters[9] = (counters[9] & 0xFFFFFFFFull) | ((unsigned long long)(s_base + mine) << 32);
+  }
+  if (mine == 0u) return;
+  const int64_t p0 = (int64_t)blockIdx.x * RANK_TILE + (int64_t)threadIdx.x * FINISH_ITEMS;
+  uint32_t f[FINISH_ITEMS] = {0u, 0u, 0u, 0u};
+  if (p0 + FINISH_ITEMS <= range) {
+    const uint4 v = *reinterpret_cast<const uint4*>(flag + p0);
+    f[0] = v.x;
+    f[1] = v.y;
+    f[2] = v.z;
+    f[3] = v.w;
+  } else {
+    for (int k = 0; k < FINISH_ITEMS; ++k)
+      if (p0 + k < range) f[k] = flag[p0 + k];
+  }
+  uint32_t local = 0;
+  Scan(tmp.scan).ExclusiveSum((f[0] ? 1u : 0u) + (f[1] ? 1u : 0u) + (f[2] ? 1u : 0u) + (f[3] ? 1u : 0u), local);
+  uint32_t o = s_base + local;
+#pragma unroll
+  for (int k = 0; k < FINISH_ITEMS; ++k) {
+    if (!f[k]) continue;
+    JAcc2* ap = acc + (f[k] - 1u);
+    const JAcc2 a = *ap;
+    const ulonglong2 kk = *reinterpret_cast<const ulonglong2*>(keys + a.slot);
+    out[o++] = junction_from_acc(a, U128{kk.x, kk.y}, idx_lo + (unsigned long long)(p0 + k));
+    keys[a.slot] = U128{0ull, 0ull};
+    clear_acc(ap);
+  }
 }
 
 // records in arbitrary order (peer-to-peer emit, explicit idx): compact in any order, sorted by first idx afterwards
@@ -761,6 +834,7 @@ int ensure_counters(fc_ctx* ctx, cudaStream_t st) {
     FC_CUDA(ctx, ctx->agg.counters.reserve(64 * sizeof(unsigned long long), st, false, 0));
     FC_CUDA(ctx, cudaMemsetAsync(ctx->agg.counters.p, 0, 64 * sizeof(unsigned long long), st));
   }
+  if (!ctx->agg.h_pinned) FC_CUDA(ctx, cudaHostAlloc((void**)&ctx->agg.h_pinned, 64 * sizeof(unsigned long long), cudaHostAllocMapped));
   return FC_OK;
 }
 
@@ -808,6 +882,8 @@ void fc_dbuf::release() {
 }
 
 // ------------------------------------------------------------------------------------------------ C ABI
+static int clear_sets_early(fc_ctx* ctx, cudaStream_t st);
+
 extern "C" int fc_agg_reset(fc_ctx* ctx) {
   if (!ctx) return FC_E_ARG;
   ctx->agg.n_recs = 0;
@@ -815,8 +891,9 @@ extern "C" int fc_agg_reset(fc_ctx* ctx) {
   ctx->agg.unordered = false;
   ctx->agg.n_junc = -1;
   ctx->agg.max_idx = 0;
+  ctx->agg.idx_lo = ~0ull;
   if (ctx->agg.counters.p) FC_CUDA(ctx, cudaMemset(ctx->agg.counters.p, 0, 64 * sizeof(unsigned long long)));
-  return FC_OK;
+  return clear_sets_early(ctx, ctx->own_stream);
 }
 
 extern "C" int fc_agg_reset_async(fc_ctx* ctx, void* stream) {
@@ -829,8 +906,9 @@ extern "C" int fc_agg_reset_async(fc_ctx* ctx, void* stream) {
   a.unordered = false;
   a.n_junc = -1;
   a.max_idx = 0;
+  a.idx_lo = ~0ull;
   FC_CUDA(ctx, cudaMemsetAsync(a.counters.p, 0, 64 * sizeof(unsigned long long), (cudaStream_t)stream));
-  return FC_OK;
+  return clear_sets_early(ctx, (cudaStream_t)stream);
 }
 
 static int agg_emit_impl(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, const int32_t* d_chrom, const uint8_t* d_flags,
@@ -847,33 +925,18 @@ static int agg_emit_impl(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, const int
   // upper bound of the record count so far (the exact count lives on the device)
   int64_t ub = a.n_recs + n;
   FC_CUDA(ctx, a.recs.reserve((size_t)ub * sizeof(fc_jrec), st, true, (size_t)a.n_recs * sizeof(fc_jrec)));
-  FC_CUDA(ctx, a.scratch[1].reserve((size_t)n * 4, st, false, 0));
-  uint32_t* pos = (uint32_t*)a.scratch[1].p;
-  const AcceptOp accept{d_hits, d_mask};
-  {
-    // stable compaction: position of every accepted pair among the accepted pairs of the batch
-    cub::CountingInputIterator<int64_t> iota(0);
-    cub::TransformInputIterator<uint32_t, AcceptOp, cub::CountingInputIterator<int64_t>> it(iota, accept);
-    size_t tmp = 0;
-    FC_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp, it, pos, n, st));
-    FC_CUDA(ctx, a.cub_tmp.reserve(tmp, st, false, 0));
-    FC_CUDA(ctx, cub::DeviceScan::ExclusiveSum(a.cub_tmp.p, tmp, it, pos, n, st));
-    ctx->launches += 2;
-  }
-  emit_kernel<<<nblk(n, 256), 256, 0, st>>>(n, d_hits, d_mask, pos, d_chrom, d_flags, d_wden, d_q_a, d_q_b, d_read_hash,
-                                            d_qname_hash, idx_base, d_idx, (const unsigned long long*)a.counters.p,
-                                            (fc_jrec*)a.recs.p);
-  FC_LAUNCH_CHECK(ctx);
-  bump_kernel<<<1, 1, 0, st>>>((unsigned long long*)a.counters.p, pos, accept, n);
+  emit_kernel<<<nblk(n, 256), 256, 0, st>>>(n, d_hits, d_mask, d_chrom, d_flags, d_wden, d_q_a, d_q_b, d_read_hash, d_qname_hash,
+                                            idx_base, d_idx, (unsigned long long*)a.counters.p, (fc_jrec*)a.recs.p);
   FC_LAUNCH_CHECK(ctx);
   a.n_recs = ub;  // upper bound until the next sync
   a.n_exact = false;
   a.n_junc = -1;
+  a.unordered = true;  // slots are claimed per CTA: consumers that need stream order restore it from idx
   if (d_idx) {
-    a.max_idx = ~0ull;
-    a.unordered = true;  // rows are not in stream order: the sort-based path restores it from idx
-  } else if (a.max_idx != ~0ull && idx_base + (uint64_t)n > a.max_idx) {
-    a.max_idx = idx_base + (uint64_t)n;
+    a.max_idx = ~0ull;  // explicit positions: range unknown
+  } else if (a.max_idx != ~0ull) {
+    if (idx_base + (uint64_t)n > a.max_idx) a.max_idx = idx_base + (uint64_t)n;
+    if (idx_base < a.idx_lo) a.idx_lo = idx_base;
   }
   return FC_OK;
 }
@@ -1006,6 +1069,25 @@ static int reserve_clean(fc_ctx* ctx, fc_dbuf& b, size_t bytes, cudaStream_t st)
   return FC_OK;
 }
 
+// The distinct set has to be all-zero when the accumulate kernel starts.  fc_agg_reset* already knows that, so it clears
+// the part the last call dirtied on a side stream: the memset then runs beside the scan kernel of the next batch
+// instead of in front of the accumulate kernel.
+static int clear_sets_early(fc_ctx* ctx, cudaStream_t st) {
+  fc_agg& a = ctx->agg;
+  if (!a.f_sets.p || a.sets_clean || a.sets_used == 0) return FC_OK;
+  if (!a.side) {
+    FC_CUDA(ctx, cudaStreamCreateWithFlags(&a.side, cudaStreamNonBlocking));
+    FC_CUDA(ctx, cudaEventCreateWithFlags(&a.ev_side, cudaEventDisableTiming));
+    FC_CUDA(ctx, cudaEventCreateWithFlags(&a.ev_main, cudaEventDisableTiming));
+  }
+  FC_CUDA(ctx, cudaEventRecord(a.ev_main, st));
+  FC_CUDA(ctx, cudaStreamWaitEvent(a.side, a.ev_main, 0));
+  FC_CUDA(ctx, cudaMemsetAsync(a.f_sets.p, 0, a.sets_used, a.side));
+  FC_CUDA(ctx, cudaEventRecord(a.ev_side, a.side));
+  a.sets_clean = true;
+  return FC_OK;
+}
+
 // FC_AGG_TIMING=1: per-stage device times of the sort-free path on stderr (CUDA events on the caller's stream)
 struct StageTimer {
   bool on;
@@ -1052,7 +1134,10 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st) {
   int rc;
   StageTimer tm(st);
   tm.mark("start");
+  if (a.side) FC_CUDA(ctx, cudaStreamWaitEvent(st, a.ev_side, 0));  // a pending early clear
   if (a.f_dirty) {  // an earlier call failed half-way: start from clean tables
+    if (a.side) FC_CUDA(ctx, cudaStreamSynchronize(a.side));
+    a.sets_clean = false;
     a.f_keys.release();
     a.f_sets.release();
     a.f_acc.release();
@@ -1060,32 +1145,34 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st) {
   }
   if ((rc = reserve_clean(ctx, a.f_keys, (size_t)kcap * 16, st))) return rc;
   if ((rc = reserve_clean(ctx, a.f_acc, (size_t)acap * sizeof(JAcc2), st))) return rc;
-  FC_CUDA(ctx, a.f_sets.reserve((size_t)scap * 16, st, false, 0));
-  FC_CUDA(ctx, cudaMemsetAsync(a.f_sets.p, 0, (size_t)scap * 16, st));
+  if (!(a.sets_clean && (size_t)scap * 16 <= a.sets_used && (size_t)scap * 16 <= a.f_sets.cap)) {
+    FC_CUDA(ctx, a.f_sets.reserve((size_t)scap * 16, st, false, 0));
+    FC_CUDA(ctx, cudaMemsetAsync(a.f_sets.p, 0, (size_t)scap * 16, st));
+  }
+  a.sets_clean = false;
+  a.sets_used = (size_t)scap * 16 > a.sets_used ? (size_t)scap * 16 : a.sets_used;
   FC_CUDA(ctx, a.junctions.reserve((size_t)ub * sizeof(fc_junction), st, false, 0));
   unsigned long long* counters = (unsigned long long*)a.counters.p;
   unsigned int* ctr = (unsigned int*)(counters + 8);
   FC_CUDA(ctx, cudaMemsetAsync(ctr, 0, 4 * sizeof(unsigned int), st));
-  const bool ordered = !a.unordered;
-  static int dbg = -1;
-  if (dbg < 0) { const char* e = getenv("FC_AGG_SKIP"); dbg = e ? atoi(e) : 0; }
+  // discovery rank: flags over the idx range when it is known and about as large as the record count, else a sort
+  const bool dense = a.max_idx != ~0ull && a.idx_lo != ~0ull && a.max_idx > a.idx_lo &&
+                     a.max_idx - a.idx_lo <= 4ull * (unsigned long long)ub + (1ull << 20);
+  const int64_t range = dense ? (int64_t)(a.max_idx - a.idx_lo) : 0;
+  const int64_t n_tiles = (range + RANK_TILE - 1) / RANK_TILE;
   a.f_dirty = true;  // until the finish kernel has run
-  tm.mark("clear");
   uint32_t* flag = nullptr;
-  uint32_t* rank = nullptr;
-  if (ordered) {
-    FC_CUDA(ctx, a.scratch[0].reserve((size_t)ub * 4, st, false, 0));
-    FC_CUDA(ctx, a.scratch[1].reserve((size_t)ub * 4, st, false, 0));
+  uint32_t* tile_count = nullptr;
+  if (dense) {
+    FC_CUDA(ctx, a.scratch[0].reserve((size_t)range * 4, st, false, 0));
+    FC_CUDA(ctx, a.scratch[1].reserve((size_t)n_tiles * 8, st, false, 0));
     flag = (uint32_t*)a.scratch[0].p;
-    rank = (uint32_t*)a.scratch[1].p;
-    fused_accumulate_kernel<true><<<nblk(ub, ACC_THREADS), ACC_THREADS, 0, st>>>(ub, counters, (const fc_jrec*)a.recs.p, (U128*)a.f_keys.p,
-                                                                 kcap - 1, (U128*)a.f_sets.p, scap - 1, (JAcc2*)a.f_acc.p, acap,
-                                                                 ctr, flag, dbg);
-  } else {
-    fused_accumulate_kernel<false><<<nblk(ub, ACC_THREADS), ACC_THREADS, 0, st>>>(ub, counters, (const fc_jrec*)a.recs.p, (U128*)a.f_keys.p,
-                                                                  kcap - 1, (U128*)a.f_sets.p, scap - 1, (JAcc2*)a.f_acc.p, acap,
-                                                                  ctr, nullptr, dbg);
+    tile_count = (uint32_t*)a.scratch[1].p;
   }
+  tm.mark("clear");
+  fused_accumulate_kernel<<<nblk(ub, ACC_THREADS), ACC_THREADS, 0, st>>>(ub, counters, (const fc_jrec*)a.recs.p, (U128*)a.f_keys.p,
+                                                                         kcap - 1, (U128*)a.f_sets.p, scap - 1, (JAcc2*)a.f_acc.p,
+                                                                         acap, ctr, flag, range, tile_count, n_tiles);
   FC_LAUNCH_CHECK(ctx);
   tm.mark("accumulate");
   const unsigned sweep_blocks = (unsigned)ctx->sm_count * 8u;
@@ -1093,18 +1180,22 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st) {
   uint64_t* kB = nullptr;
   uint32_t* vA = nullptr;
   fc_junction* tmpj = nullptr;
-  if (ordered) {
-    mark_first_kernel<<<sweep_blocks, 256, 0, st>>>(ctr, acap, (const JAcc2*)a.f_acc.p, flag);
+  if (dense) {
+    mark_first_kernel<<<sweep_blocks, 256, 0, st>>>(ctr, acap, (const JAcc2*)a.f_acc.p, a.idx_lo, flag, tile_count);
     FC_LAUNCH_CHECK(ctx);
-    cub::TransformInputIterator<uint32_t, NonZero, const uint32_t*> it(flag, NonZero());
-    size_t tmp = 0;
-    FC_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp, it, rank, ub, st));
-    FC_CUDA(ctx, a.cub_tmp.reserve(tmp, st, false, 0));
-    FC_CUDA(ctx, cub::DeviceScan::ExclusiveSum(a.cub_tmp.p, tmp, it, rank, ub, st));
-    ctx->launches += 2;
-    tm.mark("mark+rank");
-    finish_ordered_kernel<<<nblk(ub, 256), 256, 0, st>>>(ub, flag, rank, (const fc_jrec*)a.recs.p, (JAcc2*)a.f_acc.p,
-                                                         (U128*)a.f_keys.p, (fc_junction*)a.junctions.p, ctr);
+    uint32_t* tile_base = nullptr;
+    if (n_tiles > 4096) {  // many tiles: scan the counts once instead of summing them in every block
+      tile_base = tile_count + n_tiles;
+      size_t tmp = 0;
+      FC_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp, tile_count, tile_base, n_tiles, st));
+      FC_CUDA(ctx, a.cub_tmp.reserve(tmp, st, false, 0));
+      FC_CUDA(ctx, cub::DeviceScan::ExclusiveSum(a.cub_tmp.p, tmp, tile_count, tile_base, n_tiles, st));
+      ctx->launches += 2;
+    }
+    tm.mark("mark");
+    finish_dense_kernel<<<(unsigned)n_tiles, FINISH_THREADS, 0, st>>>(range, a.idx_lo, flag, tile_count, tile_base,
+                                                                       (JAcc2*)a.f_acc.p, (U128*)a.f_keys.p,
+                                                                       (fc_junction*)a.junctions.p, ctr, counters, a.h_pinned);
     FC_LAUNCH_CHECK(ctx);
   } else {
     FC_CUDA(ctx, a.scratch[5].reserve((size_t)ub * sizeof(fc_junction), st, false, 0));
@@ -1120,8 +1211,8 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st) {
   }
   // one round trip: exact record count, junction count, fallback conditions, peer-to-peer overflow
   tm.mark("finish");
-  unsigned long long h[10];
-  FC_CUDA(ctx, cudaMemcpyAsync(h, counters, sizeof(h), cudaMemcpyDeviceToHost, st));
+  unsigned long long* h = a.h_pinned;  // pinned + mapped; the dense finish kernel has already written it
+  if (!dense) FC_CUDA(ctx, cudaMemcpyAsync(h, counters, 10 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   tm.mark("copy");
   FC_CUDA(ctx, cudaStreamSynchronize(st));
   tm.report();
@@ -1133,7 +1224,7 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st) {
   const unsigned int n_other = (unsigned int)(h[8] >> 32), n_overflow = (unsigned int)h[9];
   const int64_t nj = (int64_t)(h[9] >> 32);
   if (n_other || n_overflow) return -100;
-  if (!ordered && nj > 0) {
+  if (!dense && nj > 0) {
     uint32_t* vB = vA + ub;
     rc = sort_pairs_u64_u32(ctx, nj, kA, kB, vA, vB, 0, 64, st);
     if (rc) return rc;
@@ -1460,4 +1551,12 @@ void fc_agg_release(fc_ctx* ctx) {
   a.f_keys.release();
   a.f_sets.release();
   a.f_acc.release();
+  if (a.h_pinned) cudaFreeHost(a.h_pinned);
+  a.h_pinned = nullptr;
+  if (a.side) {
+    cudaStreamDestroy(a.side);
+    cudaEventDestroy(a.ev_side);
+    cudaEventDestroy(a.ev_main);
+    a.side = nullptr;
+  }
 }

@@ -58,7 +58,9 @@ struct fc_agg {
   fc_dbuf junctions;    // fc_junction[n_junc]
   int64_t n_junc = -1;  // -1: not finalized
   uint64_t max_idx = 0; // upper bound of fc_jrec.idx seen so far (~0: unknown)
-  bool unordered = false;  // records are not in idx order (peer-to-peer emit)
+  uint64_t idx_lo = ~0ull;  // smallest idx_base of the fc_agg_emit calls
+  bool unordered = false;  // records are not in idx order (emit claims slots per CTA, peer-to-peer emit, append)
+  unsigned long long* h_pinned = nullptr;  // pinned landing zone of the counters
   // fused emit + exchange over peer memory
   bool p2p_enabled = false;
   int p2p_world = 1, p2p_rank = 0;
@@ -72,6 +74,10 @@ struct fc_agg {
   // sort-free path: junction-key table and accumulators (kept clean between calls), distinct set
   fc_dbuf f_keys, f_sets, f_acc;
   bool f_dirty = false;
+  cudaStream_t side = nullptr;  // early clear of the distinct set (see clear_sets_early)
+  cudaEvent_t ev_side = nullptr, ev_main = nullptr;
+  bool sets_clean = false;
+  size_t sets_used = 0;         // bytes of f_sets that calls have touched (and an early clear covers)
 };
 
 struct fc_ctx {
