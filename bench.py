@@ -7,14 +7,17 @@ bench.py -- anchor pairs / second through the breakpoint scan + junction merge (
 
 A step is one pass of the hot path over one batch: config 2 of BASELINE.json -- synthetic 100 Mb genome
 (20 x 5 Mb, 0.5 % N), 10 000 planted circRNAs, 1 M anchor pairs from 100-nt reads (a=20, m=2, d=2), seeds fixed.
-  value   pairs/s with the batch already resident in HBM (scan kernel + record emit + sort/reduce per step)
+  value   pairs/s with the batch already resident in HBM (scan kernel + record emit + junction aggregation per step)
   e2e     the same through the host-buffer C-ABI call fc_batch_host + fc_agg_finalize + fc_agg_fetch:
           pinned host SoA in, per-pair hits and the junction table out, copies inside the timed region
-  roofline  scan kernel only: 82 algorithmic bytes per pair / CUDA-event time of the kernel
+  roofline  the kernel with the longest launch in the step, roofline_other the second one.  scan kernel: 82
+            algorithmic bytes per pair / CUDA-event time of the kernel; aggregation kernel: 48 B per
+            record + 64 B per junction / the library's own CUDA events around the kernel (fc_agg_get_timing)
   cpu_baseline  oracle (python restatement of find_circ.py, one numpy compare per split position) on a bounded sample
 L2 is flushed (256 MiB memset) before every timed step; per-step CUDA events are summed.
 Multi-GPU: pairs are sharded by rank (weak scaling: every rank scans its own 1 M pairs), junction records are
-hash-partitioned by key and exchanged with one all-to-all, every rank reduces its keys.
+hash-partitioned by key and written straight into the owner's buffer over NVLink (fallback: one all-to-all), every
+rank reduces its keys.
 """
 import argparse
 import json
@@ -363,6 +366,21 @@ def run_gpu(args):
         scan_ms += s0.elapsed_time(s1)
     barrier()
     launches = eng.launch_count() - launches0
+    # ---- the aggregation kernel alone: a few more steps with the library's own CUDA events around its stages
+    eng.agg_set_timing(True)
+    acc_us, stage_sum = 0.0, {}
+    for _ in range(args.steps):
+        flush.zero_()
+        step_device()
+        torch.cuda.synchronize()
+        st = eng.agg_get_timing()
+        acc_us += st["accumulate"]
+        for k, v in st.items():
+            stage_sum[k] = stage_sum.get(k, 0.0) + v
+    eng.agg_set_timing(False)
+    acc_step_ms = acc_us / args.steps * 1e-3
+    stages_us = {k: round(v / args.steps, 1) for k, v in stage_sum.items()}
+    barrier()
     # ---- timed: end to end through host buffers (wall clock brackets synchronous calls; device idle otherwise)
     for _ in range(2):
         step_e2e()
@@ -407,6 +425,17 @@ def run_gpu(args):
     if rank == 0:
         peak, peak_src = peaks()
         achieved = BYTES_PER_PAIR * n / (scan_step * 1e-3) / 1e9
+        merge_bytes = 48.0 * n_rec + 64.0 * int(nj)
+        acc_achieved = merge_bytes / (max(acc_step_ms, 1e-9) * 1e-3) / 1e9
+        roof_scan = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": 46.4e6,
+                     "kernel": "scan_kernel<NP=3,T=1> (csrc/scan.cu)", "bytes_per_pair": BYTES_PER_PAIR, "ms": scan_step,
+                     "peak_source": peak_src, "traffic_source": "ncu --set full, profiles/r01_kernels_ncu_summary.txt"}
+        roof_acc = {"bound": "hbm", "achieved": acc_achieved, "peak": peak, "unit": "GB/s", "frac": acc_achieved / peak,
+                    "traffic": 132.7e6, "kernel": "fused_accumulate_kernel (csrc/agg.cu)", "ms": acc_step_ms,
+                    "bytes": "48 B x %d records + 64 B x %d junctions (rank 0)" % (n_rec, int(nj)), "peak_source": peak_src,
+                    "traffic_source": "ncu --set full, profiles/r01_kernels_ncu_summary.txt",
+                    "note": "random 16/32-byte accesses to hash tables: bound by L1/LSU wavefronts and L2 atomics, not by bytes"}
+        dominant, other = (roof_acc, roof_scan) if acc_step_ms > scan_step else (roof_scan, roof_acc)
         line = {
             "metric": "anchor pairs/sec (breakpoint scan + junction merge)", "value": total_pairs / (ms_step * 1e-3),
             "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
@@ -417,15 +446,11 @@ def run_gpu(args):
                 "pairs_scanned_per_gpu": n, "junctions_rank0": int(nj), "l2": "flushed (256 MiB memset) before every timed step",
                 "timing": "per-step CUDA events summed over the steps; max over ranks",
                 "exchange": ("none" if world == 1 else ("fused emit+exchange over peer memory (CUDA IPC, NVLink)" if use_p2p else "partition + NCCL all-to-all")),
-                "scan_ms": scan_step, "merge_ms": ms_step - scan_step, "seeds": {"genome": 1, "junctions": 2, "pairs": "3+1000*rank"},
+                "scan_ms": scan_step, "merge_ms": ms_step - scan_step, "accumulate_kernel_ms": acc_step_ms, "seeds": {"genome": 1, "junctions": 2, "pairs": "3+1000*rank"},
             },
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "scan_kernel<NP=3,T=1> (csrc/scan.cu)", "bytes_per_pair": BYTES_PER_PAIR, "peak_source": peak_src},
-            "roofline_merge": {"bound": "hbm", "kernels": "emit + assign + accumulate + finish (csrc/agg.cu)",
-                               "achieved": (48.0 * n_rec + 64.0 * int(nj)) / (max(ms_step - scan_step, 1e-9) * 1e-3) / 1e9, "peak": peak,
-                               "unit": "GB/s", "frac": (48.0 * n_rec + 64.0 * int(nj)) / (max(ms_step - scan_step, 1e-9) * 1e-3) / 1e9 / peak,
-                               "bytes": "48 B x %d records + 64 B x %d junctions (rank 0)" % (n_rec, int(nj)),
-                               "note": "latency/atomic bound, not bandwidth bound: see profiles/"},
+            "roofline": dominant,        # the kernel with the longest launch inside the step
+            "roofline_other": other,     # the second kernel of the path
+            "merge_stages_us": stages_us,
             "e2e": {"value": total_pairs / e2e_step, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d_planes), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_step * 1e3,
                     "call": "fc_batch_host_planes + fc_agg_finalize + fc_agg_fetch (pinned host SoA with bit-plane reads, as csrc/ingest.cu emits them)",

@@ -113,6 +113,8 @@ SYMBOLS = [
     ("fc_pinned_alloc", _P, [C.c_int64]),
     ("fc_pinned_free", None, [_P]),
     ("fc_device_sync", C.c_int, [_P]),
+    ("fc_agg_set_timing", C.c_int, [_P, C.c_int32]),
+    ("fc_agg_get_timing", C.c_int, [_P, _P]),
     ("fc_launch_count", C.c_int64, [_P]),
     ("fc_hash_bytes", C.c_uint64, [_P, C.c_int64]),
     ("fc_hash_read", C.c_uint64, [_P, C.c_int64, _P]),

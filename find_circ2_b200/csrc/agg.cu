@@ -1088,20 +1088,23 @@ static int clear_sets_early(fc_ctx* ctx, cudaStream_t st) {
   return FC_OK;
 }
 
-// FC_AGG_TIMING=1: per-stage device times of the sort-free path on stderr (CUDA events on the caller's stream)
+// per-stage device times of the sort-free path (CUDA events on the caller's stream): fc_agg_set_timing() keeps them
+// for fc_agg_get_timing(), FC_AGG_TIMING=1 also prints them on stderr
 struct StageTimer {
-  bool on;
+  bool on, print;
+  fc_ctx* ctx;
   cudaStream_t st;
   int n = 0;
   cudaEvent_t ev[12];
   const char* name[12];
-  explicit StageTimer(cudaStream_t s) : st(s) {
+  StageTimer(fc_ctx* c, cudaStream_t s) : ctx(c), st(s) {
     static int flag = -1;
     if (flag < 0) {
       const char* e = getenv("FC_AGG_TIMING");
       flag = (e && e[0] == '1') ? 1 : 0;
     }
-    on = flag == 1;
+    print = flag == 1;
+    on = print || c->agg.timing;
   }
   void mark(const char* what) {
     if (!on || n >= 12) return;
@@ -1114,9 +1117,10 @@ struct StageTimer {
     for (int k = 1; k < n; ++k) {
       float ms = 0.f;
       cudaEventElapsedTime(&ms, ev[k - 1], ev[k]);
-      fprintf(stderr, "%s%s %.1f us", k == 1 ? "[fc_agg_finalize] " : ", ", name[k], ms * 1000.f);
+      if (k - 1 < 8) ctx->agg.stage_us[k - 1] = ms * 1000.f;
+      if (print) fprintf(stderr, "%s%s %.1f us", k == 1 ? "[fc_agg_finalize] " : ", ", name[k], ms * 1000.f);
     }
-    fprintf(stderr, "\n");
+    if (print) fprintf(stderr, "\n");
     for (int k = 0; k < n; ++k) cudaEventDestroy(ev[k]);
     n = 0;
   }
@@ -1132,7 +1136,7 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st) {
   const unsigned long long scap = 2ull * kcap;  // two inserts per record
   const unsigned int acap = (unsigned int)(ub + ub / 8 + 65536);  // junction ids incl. the ones lost to insert races
   int rc;
-  StageTimer tm(st);
+  StageTimer tm(ctx, st);
   tm.mark("start");
   if (a.side) FC_CUDA(ctx, cudaStreamWaitEvent(st, a.ev_side, 0));  // a pending early clear
   if (a.f_dirty) {  // an earlier call failed half-way: start from clean tables
@@ -1366,6 +1370,19 @@ extern "C" int64_t fc_agg_finalize(fc_ctx* ctx, void* stream) {
   FC_LAUNCH_CHECK(ctx);
   a.n_junc = nj;
   return nj;
+}
+
+extern "C" int fc_agg_set_timing(fc_ctx* ctx, int32_t on) {
+  if (!ctx) return FC_E_ARG;
+  ctx->agg.timing = on != 0;
+  for (float& v : ctx->agg.stage_us) v = 0.f;
+  return FC_OK;
+}
+
+extern "C" int fc_agg_get_timing(fc_ctx* ctx, float* out_us /* 5 */) {
+  if (!ctx || !out_us) return FC_E_ARG;
+  for (int k = 0; k < 5; ++k) out_us[k] = ctx->agg.stage_us[k];
+  return FC_OK;
 }
 
 extern "C" int fc_agg_fetch(fc_ctx* ctx, int64_t n, fc_junction* h_out) {

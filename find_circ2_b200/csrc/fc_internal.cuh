@@ -76,6 +76,8 @@ struct fc_agg {
   bool f_dirty = false;
   cudaStream_t side = nullptr;  // early clear of the distinct set (see clear_sets_early)
   cudaEvent_t ev_side = nullptr, ev_main = nullptr;
+  bool timing = false;          // keep the per-stage device times of fc_agg_finalize (fc_agg_set_timing)
+  float stage_us[8] = {};       // clear, accumulate, mark, finish, copy
   bool sets_clean = false;
   size_t sets_used = 0;         // bytes of f_sets that calls have touched (and an early clear covers)
 };

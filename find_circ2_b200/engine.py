@@ -257,6 +257,15 @@ class Engine:
         self._check(self.lib.fc_agg_partition(self.h, n_ranks, ptr(d_out), counts.ctypes.data, stream))
         return counts
 
+    def agg_set_timing(self, on: bool):
+        self._check(self.lib.fc_agg_set_timing(self.h, 1 if on else 0))
+
+    def agg_get_timing(self) -> dict:
+        """device time (us) of the stages of the last agg_finalize on its sort-free path"""
+        out = np.zeros(5, dtype=np.float32)
+        self._check(self.lib.fc_agg_get_timing(self.h, out.ctypes.data))
+        return dict(zip(("clear", "accumulate", "mark", "finish", "copy"), (float(v) for v in out)))
+
     def agg_finalize(self, stream=0) -> int:
         return int(self._check(self.lib.fc_agg_finalize(self.h, stream)))
 

@@ -301,6 +301,11 @@ int64_t fc_ingest_parse(fc_ingest* h, const char* text, int64_t nbytes, int32_t 
 void* fc_pinned_alloc(int64_t bytes);
 void fc_pinned_free(void* p);
 int fc_device_sync(fc_ctx* ctx);
+/* Device time of the stages of the last fc_agg_finalize() call on its sort-free path, measured with CUDA events on the
+ * caller's stream while switched on: out_us[0..4] = table clears, accumulate kernel, first-record marks, finish kernel,
+ * counter copy (bench.py's roofline for the aggregation kernel; no counterpart in the reference). */
+int fc_agg_set_timing(fc_ctx* ctx, int32_t on);
+int fc_agg_get_timing(fc_ctx* ctx, float* out_us);
 /* number of kernels this library has launched in this context (bench.py's gpu_launches) */
 int64_t fc_launch_count(fc_ctx* ctx);
 /* the hash functions the host must use for fc_jrec.read_hash / qname_hash (FNV-1a 64 + finaliser) */
