@@ -321,8 +321,12 @@ def run_gpu(args):
     pl_pin = [pin(planes_np[k]) for k in range(3)]
     h2d_planes = sum(v[1].nbytes for k, v in pinned.items() if k != "internal") + sum(v[1].nbytes for v in pl_pin)
 
+    e2e_parts = {"reset": 0.0, "batch": 0.0, "finalize": 0.0, "fetch": 0.0}
+
     def step_e2e(ascii_reads=False):
+        tp = [time.perf_counter()]
         eng.agg_reset()
+        tp.append(time.perf_counter())
         p = {k: v[1] for k, v in pinned.items()}
         if ascii_reads:
             eng.batch_host(p["chrom"], p["a_start"], p["b_end"], p["l"], p["flags"], p["internal"], p["wden"], p["q_a"], p["q_b"],
@@ -331,10 +335,16 @@ def run_gpu(args):
             eng.batch_host_planes(n, p["chrom"], p["a_start"], p["b_end"], p["l"], p["flags"], pl_pin[0][1], pl_pin[1][1],
                                   pl_pin[2][1], n_words, n, max_l, p["wden"], p["q_a"], p["q_b"], p["read_hash"],
                                   p["qname_hash"], idx=None, idx_base=idx_base, emit=True, out=h_hits)
+        tp.append(time.perf_counter())
         if world > 1:
             parallel.exchange_records(eng, dist, dev, 0, upper_bound=n)
         nj = eng.agg_finalize(0)
-        junc = eng.agg_fetch(nj)
+        tp.append(time.perf_counter())
+        junc = eng.agg_fetch(nj, copy=False)  # read in place (pinned buffer of the engine)
+        tp.append(time.perf_counter())
+        if not ascii_reads:
+            for k, name in enumerate(("reset", "batch", "finalize", "fetch")):
+                e2e_parts[name] += tp[k + 1] - tp[k]
         return nj, junc
 
     def barrier():
@@ -386,6 +396,8 @@ def run_gpu(args):
         step_e2e()
     barrier()
     e2e_s = 0.0
+    for k in e2e_parts:
+        e2e_parts[k] = 0.0
     for _ in range(args.steps):
         flush.zero_()
         torch.cuda.synchronize()
@@ -453,6 +465,7 @@ def run_gpu(args):
             "merge_stages_us": stages_us,
             "e2e": {"value": total_pairs / e2e_step, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d_planes), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_step * 1e3,
+                    "calls_ms": {k: round(v / args.steps * 1e3, 3) for k, v in e2e_parts.items()},
                     "call": "fc_batch_host_planes + fc_agg_finalize + fc_agg_fetch (pinned host SoA with bit-plane reads, as csrc/ingest.cu emits them)",
                     "ascii_reads": {"value": n * world / e2e_ascii_step, "h2d_bytes_per_step": int(h2d), "ms_per_step": e2e_ascii_step * 1e3,
                                     "call": "fc_batch_host (ASCII read bases, packed on the device)"}},

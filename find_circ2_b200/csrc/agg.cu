@@ -911,6 +911,12 @@ extern "C" int fc_agg_reset_async(fc_ctx* ctx, void* stream) {
   return clear_sets_early(ctx, (cudaStream_t)stream);
 }
 
+int fc_agg_reserve_records(fc_ctx* ctx, int64_t extra, cudaStream_t st) {
+  fc_agg& a = ctx->agg;
+  FC_CUDA(ctx, a.recs.reserve((size_t)(a.n_recs + extra) * sizeof(fc_jrec), st, true, (size_t)a.n_recs * sizeof(fc_jrec)));
+  return FC_OK;
+}
+
 static int agg_emit_impl(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, const int32_t* d_chrom, const uint8_t* d_flags,
                            const uint8_t* d_wden, const int16_t* d_q_a, const int16_t* d_q_b,
                            const uint64_t* d_read_hash, const uint64_t* d_qname_hash, const uint8_t* d_mask,

@@ -56,6 +56,11 @@ extern "C" void fc_ctx_destroy(fc_ctx* ctx) {
   fc_agg_release(ctx);
   for (auto& b : ctx->host_path) b.release();
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  if (ctx->own_stream2) {
+    cudaStreamDestroy(ctx->own_stream2);
+    cudaEventDestroy(ctx->ev_chunk[0]);
+    cudaEventDestroy(ctx->ev_chunk[1]);
+  }
   delete ctx;
 }
 

@@ -88,6 +88,8 @@ struct fc_ctx {
   fc_genome genome;
   fc_agg agg;
   cudaStream_t own_stream = nullptr;  // used by the host-buffer convenience calls
+  cudaStream_t own_stream2 = nullptr; // second lane of the chunked host-buffer path
+  cudaEvent_t ev_chunk[2] = {nullptr, nullptr};
   fc_dbuf host_path[16];              // staging for fc_scan_host / fc_batch_host
   int64_t launches = 0;
   int sm_count = 148;
@@ -100,6 +102,7 @@ struct fc_ctx {
 
 int fc_fail(fc_ctx* ctx, int code, const char* fmt, ...);
 int fc_genome_ensure_tiles(fc_ctx* ctx, int w, cudaStream_t st);
+int fc_agg_reserve_records(fc_ctx* ctx, int64_t extra, cudaStream_t st);  // room for `extra` more records, now
 
 #define FC_CUDA(ctx, call)                                                                         \
   do {                                                                                             \

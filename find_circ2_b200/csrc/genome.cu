@@ -451,6 +451,7 @@ int fc_genome_ensure_tiles(fc_ctx* ctx, int w, cudaStream_t st) {
   build_tiles_kernel<<<(unsigned)((n_tiles + threads - 1) / threads), threads, 0, st>>>(g.d_plo, g.d_phi, g.d_pn, n_tiles, T,
                                                                                        S, g.d_tiles);
   FC_LAUNCH_CHECK(ctx);
+  FC_CUDA(ctx, cudaStreamSynchronize(st));  // (rare) scans on other streams may follow at once
   g.tile_T = T;
   g.tile_S = S;
   g.tile_W = cap;

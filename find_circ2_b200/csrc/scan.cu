@@ -418,17 +418,74 @@ extern "C" int fc_batch_host_planes(fc_ctx* ctx, const fc_scan_params* p, int64_
   void* dp[15];
   for (int k = 0; k < 15; ++k) dp[k] = ctx->host_path[k].p;
   const bool payload = h_wden && h_q_a && h_q_b && h_read_hash && h_qname_hash;
+  if (emit && !payload) return fc_fail(ctx, FC_E_ARG, "emit needs the payload arrays");
+  uint64_t* d_idx = nullptr;
+  if (h_idx) {
+    FC_CUDA(ctx, ctx->host_path[15].reserve(8 * N, st, false, 0));
+    d_idx = (uint64_t*)ctx->host_path[15].p;
+  }
+  int rc = FC_OK;
+  if (emit && (rc = fc_agg_reserve_records(ctx, n, st))) return rc;  // no growth while chunks are in flight
+  // The batch goes through in chunks on two streams: while chunk k is scanned and its hits travel back, the columns of
+  // chunk k+1 are already on their way in (PCIe is full duplex and the copy engines run beside the kernels).
+  if (!ctx->own_stream2) {
+    FC_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->own_stream2, cudaStreamNonBlocking));
+    FC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_chunk[0], cudaEventDisableTiming));
+    FC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_chunk[1], cudaEventDisableTiming));
+  }
+  FC_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[0], st));  // everything queued on the main stream so far comes first
+  FC_CUDA(ctx, cudaStreamWaitEvent(ctx->own_stream2, ctx->ev_chunk[0], 0));
+  const int64_t chunk = 1 << 19;
+  const size_t elem[14] = {4, 4, 4, 4, 1, 0, 0, 0, 0, 1, 2, 2, 8, 8};
   const void* src[14] = {h_chrom, h_a_start, h_b_end, h_l, h_flags, nullptr, nullptr, nullptr, nullptr,
                          h_wden, h_q_a, h_q_b, h_read_hash, h_qname_hash};
-  for (int k = 0; k < 14; ++k) {
-    if (!src[k]) continue;
-    FC_CUDA(ctx, cudaMemcpyAsync(dp[k], src[k], k == 4 ? N : sizes[k], cudaMemcpyHostToDevice, st));
-  }
-  // planes: word rows of n entries each (the host arrays may be strided wider)
   const uint32_t* hp[3] = {h_rlo, h_rhi, h_rn};
   void* dpl[3] = {dp[6], dp[7], dp[14]};
-  for (int k = 0; k < 3; ++k)
-    FC_CUDA(ctx, cudaMemcpy2DAsync(dpl[k], 4 * N, hp[k], 4 * (size_t)plane_stride, 4 * N, (size_t)n_words, cudaMemcpyHostToDevice, st));
+  int which = 0;
+  for (int64_t c0 = 0; c0 < n; c0 += chunk, which ^= 1) {
+    const int64_t cn = n - c0 < chunk ? n - c0 : chunk;
+    cudaStream_t cs = which ? ctx->own_stream2 : st;
+    for (int k = 0; k < 14; ++k) {
+      if (!src[k]) continue;
+      FC_CUDA(ctx, cudaMemcpyAsync((char*)dp[k] + elem[k] * c0, (const char*)src[k] + elem[k] * c0, elem[k] * cn,
+                                   cudaMemcpyHostToDevice, cs));
+    }
+    // planes: word rows of n entries each (the host arrays may be strided wider)
+    for (int k = 0; k < 3; ++k)
+      FC_CUDA(ctx, cudaMemcpy2DAsync((char*)dpl[k] + 4 * c0, 4 * N, (const char*)hp[k] + 4 * c0, 4 * (size_t)plane_stride, 4 * cn,
+                                     (size_t)n_words, cudaMemcpyHostToDevice, cs));
+    if (d_idx) FC_CUDA(ctx, cudaMemcpyAsync(d_idx + c0, h_idx + c0, 8 * cn, cudaMemcpyHostToDevice, cs));
+    fc_pairs pc;
+    pc.n = cn;
+    pc.d_chrom = (const int32_t*)dp[0] + c0;
+    pc.d_a_start = (const int32_t*)dp[1] + c0;
+    pc.d_b_end = (const int32_t*)dp[2] + c0;
+    pc.d_l = (const int32_t*)dp[3] + c0;
+    pc.d_flags = (const uint8_t*)dp[4] + c0;
+    pc.d_rlo = (const uint32_t*)dp[6] + c0;
+    pc.d_rhi = (const uint32_t*)dp[7] + c0;
+    pc.d_rn = (const uint32_t*)dp[14] + c0;
+    pc.n_words = n_words;
+    pc.max_l = max_l;
+    pc.plane_stride = n;
+    fc_hit* d_hits = (fc_hit*)dp[8] + c0;
+    if ((rc = fc_scan(ctx, p, &pc, d_hits, cs))) return rc;
+    if (emit) {
+      if (d_idx)
+        rc = fc_agg_emit_idx(ctx, cn, d_hits, pc.d_chrom, pc.d_flags, (const uint8_t*)dp[9] + c0, (const int16_t*)dp[10] + c0,
+                             (const int16_t*)dp[11] + c0, (const uint64_t*)dp[12] + c0, (const uint64_t*)dp[13] + c0, nullptr,
+                             d_idx + c0, cs);
+      else
+        rc = fc_agg_emit(ctx, cn, d_hits, pc.d_chrom, pc.d_flags, (const uint8_t*)dp[9] + c0, (const int16_t*)dp[10] + c0,
+                         (const int16_t*)dp[11] + c0, (const uint64_t*)dp[12] + c0, (const uint64_t*)dp[13] + c0, nullptr,
+                         idx_base + (uint64_t)c0, cs);
+      if (rc) return rc;
+    }
+    if (h_out) FC_CUDA(ctx, cudaMemcpyAsync(h_out + c0, d_hits, sizeof(fc_hit) * cn, cudaMemcpyDeviceToHost, cs));
+  }
+  FC_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[1], ctx->own_stream2));
+  FC_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_chunk[1], 0));
+  FC_CUDA(ctx, cudaStreamSynchronize(st));
   fc_pairs pr;
   pr.n = n;
   pr.d_chrom = (const int32_t*)dp[0];
@@ -442,26 +499,6 @@ extern "C" int fc_batch_host_planes(fc_ctx* ctx, const fc_scan_params* p, int64_
   pr.n_words = n_words;
   pr.max_l = max_l;
   pr.plane_stride = 0;
-  int rc = fc_scan(ctx, p, &pr, (fc_hit*)dp[8], st);
-  if (rc) return rc;
-  uint64_t* d_idx = nullptr;
-  if (h_idx) {
-    FC_CUDA(ctx, ctx->host_path[15].reserve(8 * N, st, false, 0));
-    d_idx = (uint64_t*)ctx->host_path[15].p;
-    FC_CUDA(ctx, cudaMemcpyAsync(d_idx, h_idx, 8 * N, cudaMemcpyHostToDevice, st));
-  }
-  if (emit) {
-    if (!payload) return fc_fail(ctx, FC_E_ARG, "emit needs the payload arrays");
-    if (d_idx)
-      rc = fc_agg_emit_idx(ctx, n, (const fc_hit*)dp[8], pr.d_chrom, pr.d_flags, (const uint8_t*)dp[9], (const int16_t*)dp[10],
-                           (const int16_t*)dp[11], (const uint64_t*)dp[12], (const uint64_t*)dp[13], nullptr, d_idx, st);
-    else
-      rc = fc_agg_emit(ctx, n, (const fc_hit*)dp[8], pr.d_chrom, pr.d_flags, (const uint8_t*)dp[9], (const int16_t*)dp[10],
-                       (const int16_t*)dp[11], (const uint64_t*)dp[12], (const uint64_t*)dp[13], nullptr, idx_base, st);
-    if (rc) return rc;
-  }
-  if (h_out) FC_CUDA(ctx, cudaMemcpyAsync(h_out, dp[8], sizes[8], cudaMemcpyDeviceToHost, st));
-  FC_CUDA(ctx, cudaStreamSynchronize(st));
   ctx->last_n = n;
   ctx->last_pairs = pr;
   ctx->last_has_payload = payload;

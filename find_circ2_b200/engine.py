@@ -39,6 +39,7 @@ class Engine:
         self.chrom_names: List[str] = []
         self.chrom_sizes: List[int] = []
         self._chrom_ids = {}
+        self._fetch_ptr, self._fetch_bytes = None, 0  # pinned landing buffer of agg_fetch
 
     # ------------------------------------------------------------------ plumbing
     def _check(self, rc):
@@ -47,6 +48,9 @@ class Engine:
         return rc
 
     def close(self):
+        if getattr(self, "_fetch_ptr", None):
+            self.lib.fc_pinned_free(self._fetch_ptr)
+            self._fetch_ptr, self._fetch_bytes = None, 0
         if getattr(self, "h", None):
             self.lib.fc_ctx_destroy(self.h)
             self.h = None
@@ -269,11 +273,23 @@ class Engine:
     def agg_finalize(self, stream=0) -> int:
         return int(self._check(self.lib.fc_agg_finalize(self.h, stream)))
 
-    def agg_fetch(self, n: int) -> np.ndarray:
-        out = np.zeros(n, dtype=JUNCTION_DTYPE)
-        if n:
-            self._check(self.lib.fc_agg_fetch(self.h, n, out.ctypes.data))
-        return out
+    def agg_fetch(self, n: int, copy: bool = True) -> np.ndarray:
+        """the junction table of the last agg_finalize; lands in a pinned host buffer of the engine (a pageable
+        destination costs a staged copy).  copy=False returns a view that the next agg_fetch overwrites"""
+        if n == 0:
+            return np.zeros(0, dtype=JUNCTION_DTYPE)
+        need = n * JUNCTION_DTYPE.itemsize
+        if need > self._fetch_bytes:
+            if self._fetch_ptr:
+                self.lib.fc_pinned_free(self._fetch_ptr)
+            self._fetch_bytes = max(need + need // 2, 1 << 20)
+            self._fetch_ptr = self.lib.fc_pinned_alloc(self._fetch_bytes)
+            if not self._fetch_ptr:
+                self._fetch_bytes = 0
+                raise MemoryError("pinned host allocation of %d bytes failed" % need)
+        self._check(self.lib.fc_agg_fetch(self.h, n, self._fetch_ptr))
+        view = np.frombuffer((C.c_char * need).from_address(self._fetch_ptr), dtype=JUNCTION_DTYPE, count=n)
+        return view.copy() if copy else view
 
     # ------------------------------------------------------------------ hashing (host helpers of the ABI)
     def hash_reads(self, seqs: np.ndarray, lens: np.ndarray) -> np.ndarray:
