@@ -281,7 +281,7 @@ def run_gpu(args):
     eng.pack_reads(d["internal"], stride, d["l"], n_words, planes, d["flags"], stream)
     pairs = eng.make_pairs(n, d["chrom"], d["a_start"], d["b_end"], d["l"], d["flags"], planes, n_words, max_l)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    idx_base = rank * (1 << 40)
+    idx_base = rank * args.pairs  # position of the rank's shard in the whole input stream (dense over all ranks)
 
     # multi-GPU: records travel to the rank that owns their key.  Preferred: the emit kernel writes them straight into
     # the owner's buffer over NVLink (CUDA IPC peer memory); fallback: partition + NCCL all-to-all.
@@ -290,7 +290,8 @@ def run_gpu(args):
     def step_device(ev_scan=None):
         if use_p2p:
             eng.agg_reset_async(stream)
-            parallel.stream_barrier(dist, dev)  # every rank's counter is zero before anybody writes
+            eng.agg_set_idx_range(0, world * args.pairs)  # lets the owner rank the junctions without a sort
+            parallel.stream_barrier(dist, dev, eng, stream)  # every rank's counter is zero before anybody writes
         else:
             eng.agg_reset_async(stream)  # stays behind the L2-flush kernel in the stream: no host round trip before the scan
         if ev_scan:
@@ -300,7 +301,7 @@ def run_gpu(args):
             ev_scan[1].record()
         if use_p2p:
             eng.agg_emit_p2p(n, hits, d["chrom"], d["flags"], d["wden"], d["q_a"], d["q_b"], d["read_hash"], d["qname_hash"], idx_base, stream)
-            parallel.stream_barrier(dist, dev)  # every rank's records have landed
+            parallel.stream_barrier(dist, dev, eng, stream)  # every rank's records have landed
         else:
             eng.agg_emit(n, hits, d["chrom"], d["flags"], d["wden"], d["q_a"], d["q_b"], d["read_hash"], d["qname_hash"], idx_base, stream)
             if world > 1:

@@ -109,10 +109,12 @@ SYMBOLS = [
     ("fc_p2p_export", C.c_int, [_P, C.c_int64, _P]),
     ("fc_p2p_connect", C.c_int, [_P, C.c_int32, C.c_int32, _P, _P]),
     ("fc_agg_emit_p2p", C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_uint64, _P]),
+    ("fc_p2p_barrier", C.c_int, [_P, _P]),
     ("fc_agg_reset_async", C.c_int, [_P, _P]),
     ("fc_pinned_alloc", _P, [C.c_int64]),
     ("fc_pinned_free", None, [_P]),
     ("fc_device_sync", C.c_int, [_P]),
+    ("fc_agg_set_idx_range", C.c_int, [_P, C.c_uint64, C.c_uint64]),
     ("fc_agg_set_timing", C.c_int, [_P, C.c_int32]),
     ("fc_agg_get_timing", C.c_int, [_P, _P]),
     ("fc_launch_count", C.c_int64, [_P]),

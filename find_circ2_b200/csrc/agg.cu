@@ -829,6 +829,12 @@ int scan_u32(fc_ctx* ctx, int64_t n, const uint32_t* in, uint32_t* out, bool inc
   return FC_OK;
 }
 
+// counters: words [0, FC_RESET_WORDS) are zeroed by fc_agg_reset*; word FC_BARRIER_WORD counts barrier arrivals for the
+// whole life of the context; word FC_BARRIER_TIMEOUT_WORD (copied to the host by fc_agg_finalize) flags a barrier that gave up
+constexpr int FC_RESET_WORDS = 16;
+constexpr int FC_BARRIER_WORD = 32;
+constexpr int FC_BARRIER_TIMEOUT_WORD = 5;
+
 int ensure_counters(fc_ctx* ctx, cudaStream_t st) {
   if (!ctx->agg.counters.p) {
     FC_CUDA(ctx, ctx->agg.counters.reserve(64 * sizeof(unsigned long long), st, false, 0));
@@ -892,7 +898,8 @@ extern "C" int fc_agg_reset(fc_ctx* ctx) {
   ctx->agg.n_junc = -1;
   ctx->agg.max_idx = 0;
   ctx->agg.idx_lo = ~0ull;
-  if (ctx->agg.counters.p) FC_CUDA(ctx, cudaMemset(ctx->agg.counters.p, 0, 64 * sizeof(unsigned long long)));
+  ctx->agg.range_declared = false;
+  if (ctx->agg.counters.p) FC_CUDA(ctx, cudaMemset(ctx->agg.counters.p, 0, FC_RESET_WORDS * sizeof(unsigned long long)));
   return clear_sets_early(ctx, ctx->own_stream);
 }
 
@@ -907,7 +914,8 @@ extern "C" int fc_agg_reset_async(fc_ctx* ctx, void* stream) {
   a.n_junc = -1;
   a.max_idx = 0;
   a.idx_lo = ~0ull;
-  FC_CUDA(ctx, cudaMemsetAsync(a.counters.p, 0, 64 * sizeof(unsigned long long), (cudaStream_t)stream));
+  a.range_declared = false;
+  FC_CUDA(ctx, cudaMemsetAsync(a.counters.p, 0, FC_RESET_WORDS * sizeof(unsigned long long), (cudaStream_t)stream));
   return clear_sets_early(ctx, (cudaStream_t)stream);
 }
 
@@ -938,7 +946,9 @@ static int agg_emit_impl(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, const int
   a.n_exact = false;
   a.n_junc = -1;
   a.unordered = true;  // slots are claimed per CTA: consumers that need stream order restore it from idx
-  if (d_idx) {
+  if (a.range_declared) {
+    // the caller has declared the idx range of everything that arrives
+  } else if (d_idx) {
     a.max_idx = ~0ull;  // explicit positions: range unknown
   } else if (a.max_idx != ~0ull) {
     if (idx_base + (uint64_t)n > a.max_idx) a.max_idx = idx_base + (uint64_t)n;
@@ -976,7 +986,7 @@ extern "C" int fc_agg_append(fc_ctx* ctx, int64_t n, const fc_jrec* d_recs, void
   FC_CUDA(ctx, a.recs.reserve((size_t)(a.n_recs + n) * sizeof(fc_jrec), st, true, (size_t)a.n_recs * sizeof(fc_jrec)));
   FC_CUDA(ctx, cudaMemcpyAsync((fc_jrec*)a.recs.p + a.n_recs, d_recs, (size_t)n * sizeof(fc_jrec), cudaMemcpyDefault, st));
   a.n_recs += n;
-  a.max_idx = ~0ull;  // records built elsewhere: their idx range and order are unknown
+  if (!a.range_declared) a.max_idx = ~0ull;  // records built elsewhere: their idx range and order are unknown
   a.unordered = true;
   unsigned long long v = (unsigned long long)a.n_recs;
   FC_CUDA(ctx, cudaMemcpyAsync(a.counters.p, &v, sizeof(v), cudaMemcpyHostToDevice, st));
@@ -1001,7 +1011,7 @@ extern "C" int fc_agg_replace(fc_ctx* ctx, int64_t n, const fc_jrec* d_recs, voi
   FC_LAUNCH_CHECK(ctx);
   a.n_recs = n;
   a.n_exact = true;
-  a.max_idx = ~0ull;
+  if (!a.range_declared) a.max_idx = ~0ull;
   a.unordered = true;
   a.n_junc = -1;
   return FC_OK;
@@ -1229,6 +1239,8 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st) {
   a.f_dirty = false;
   a.n_recs = (int64_t)h[0];
   a.n_exact = true;
+  if (a.p2p_enabled && h[FC_BARRIER_TIMEOUT_WORD])
+    return fc_fail(ctx, FC_E_STATE, "a peer-memory barrier timed out: a peer rank did not arrive");
   if (a.p2p_enabled && h[4])
     return fc_fail(ctx, FC_E_NOMEM, "peer-to-peer record buffer overflow (%llu records dropped): raise the capacity", h[4]);
   const unsigned int n_other = (unsigned int)(h[8] >> 32), n_overflow = (unsigned int)h[9];
@@ -1378,6 +1390,14 @@ extern "C" int64_t fc_agg_finalize(fc_ctx* ctx, void* stream) {
   return nj;
 }
 
+extern "C" int fc_agg_set_idx_range(fc_ctx* ctx, uint64_t lo, uint64_t hi) {
+  if (!ctx || hi <= lo) return FC_E_ARG;
+  ctx->agg.idx_lo = lo;
+  ctx->agg.max_idx = hi;
+  ctx->agg.range_declared = true;
+  return FC_OK;
+}
+
 extern "C" int fc_agg_set_timing(fc_ctx* ctx, int32_t on) {
   if (!ctx) return FC_E_ARG;
   ctx->agg.timing = on != 0;
@@ -1418,6 +1438,7 @@ struct P2PView {
   unsigned long long* cnt[8];
   unsigned long long capacity;
   int world;
+  int rank;
 };
 
 __global__ void emit_p2p_kernel(int64_t n, const fc_hit* __restrict__ hits, const uint8_t* __restrict__ mask,
@@ -1551,6 +1572,7 @@ extern "C" int fc_agg_emit_p2p(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, con
   }
   pv.capacity = (unsigned long long)a.p2p_min_capacity;
   pv.world = a.p2p_world;
+  pv.rank = a.p2p_rank;
   unsigned long long* counters = (unsigned long long*)a.counters.p;
   emit_p2p_kernel<<<nblk(n, 1024), 1024, 0, st>>>(n, d_hits, d_mask, d_chrom, d_flags, d_wden, d_q_a, d_q_b, d_read_hash,
                                                 d_qname_hash, idx_base, pv, counters + 4);
@@ -1558,8 +1580,48 @@ extern "C" int fc_agg_emit_p2p(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, con
   a.n_recs = a.p2p_capacity;  // upper bound; the exact count is the (shared) device counter
   a.n_exact = false;
   a.unordered = true;
-  a.max_idx = ~0ull;
+  if (!a.range_declared) a.max_idx = ~0ull;
   a.n_junc = -1;
+  return FC_OK;
+}
+
+// ---- stream-ordered barrier over peer memory ------------------------------------------------------------------
+// Every rank adds 1 to the arrival word of every rank (its own included) and waits until its own word has seen `world`
+// arrivals per barrier so far.  One tiny kernel: a few microseconds over NVLink instead of a collective launch.  The wait
+// is bounded (a peer that died must not hang the GPU): after ~2 s it gives up and raises the flag that the next
+// fc_agg_finalize reports.
+__global__ void p2p_barrier_kernel(P2PView pv, unsigned long long target) {
+  __threadfence_system();  // this rank's earlier peer stores are ordered before its arrival
+  if ((int)threadIdx.x < pv.world) atomicAdd_system(pv.cnt[threadIdx.x] + FC_BARRIER_WORD, 1ull);
+  if (threadIdx.x == 0) {
+    volatile unsigned long long* mine = pv.cnt[pv.rank] + FC_BARRIER_WORD;
+    const long long t0 = clock64();
+    while (*mine < target) {
+      if (clock64() - t0 > 4000000000ll) {  // ~2 s at 2 GHz
+        pv.cnt[pv.rank][FC_BARRIER_TIMEOUT_WORD] = 1ull;
+        break;
+      }
+      __nanosleep(100);
+    }
+    __threadfence_system();
+  }
+}
+
+extern "C" int fc_p2p_barrier(fc_ctx* ctx, void* stream) {
+  if (!ctx) return FC_E_ARG;
+  fc_agg& a = ctx->agg;
+  if (!a.p2p_enabled) return fc_fail(ctx, FC_E_STATE, "fc_p2p_barrier before fc_p2p_connect");
+  P2PView pv;
+  for (int r = 0; r < 8; ++r) {
+    pv.recs[r] = nullptr;
+    pv.cnt[r] = r < a.p2p_world ? (unsigned long long*)a.p2p_cnt[r] : nullptr;
+  }
+  pv.capacity = 0;
+  pv.world = a.p2p_world;
+  pv.rank = a.p2p_rank;
+  a.barrier_epoch++;
+  p2p_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pv, a.barrier_epoch * (unsigned long long)a.p2p_world);
+  FC_LAUNCH_CHECK(ctx);
   return FC_OK;
 }
 

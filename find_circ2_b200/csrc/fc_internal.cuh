@@ -59,6 +59,7 @@ struct fc_agg {
   int64_t n_junc = -1;  // -1: not finalized
   uint64_t max_idx = 0; // upper bound of fc_jrec.idx seen so far (~0: unknown)
   uint64_t idx_lo = ~0ull;  // smallest idx_base of the fc_agg_emit calls
+  bool range_declared = false;  // [idx_lo, max_idx) was given by fc_agg_set_idx_range and holds for every record
   bool unordered = false;  // records are not in idx order (emit claims slots per CTA, peer-to-peer emit, append)
   unsigned long long* h_pinned = nullptr;  // pinned landing zone of the counters
   // fused emit + exchange over peer memory
@@ -67,6 +68,7 @@ struct fc_agg {
   int64_t p2p_capacity = 0, p2p_min_capacity = 0;
   void* p2p_recs[8] = {};
   void* p2p_cnt[8] = {};
+  unsigned long long barrier_epoch = 0;  // fc_p2p_barrier calls so far (the same on every rank)
   fc_dbuf scratch[8];
   fc_dbuf cub_tmp;
   fc_dbuf counters;     // small device counters

@@ -244,6 +244,10 @@ class Engine:
         self._check(self.lib.fc_agg_emit_p2p(self.h, n, ptr(d_hits), ptr(d_chrom), ptr(d_flags), ptr(d_wden), ptr(d_q_a),
                                              ptr(d_q_b), ptr(d_read_hash), ptr(d_qname_hash), ptr(d_mask), idx_base, stream))
 
+    def p2p_barrier(self, stream=0):
+        """stream-ordered barrier of the connected ranks over peer memory (fc_p2p_barrier)"""
+        self._check(self.lib.fc_p2p_barrier(self.h, stream))
+
     def agg_reset_async(self, stream=0):
         self._check(self.lib.fc_agg_reset_async(self.h, stream))
 
@@ -260,6 +264,10 @@ class Engine:
         counts = np.zeros(n_ranks, dtype=np.int64)
         self._check(self.lib.fc_agg_partition(self.h, n_ranks, ptr(d_out), counts.ctypes.data, stream))
         return counts
+
+    def agg_set_idx_range(self, lo: int, hi: int):
+        """every record of this aggregation (local, appended, from peers) has lo <= idx < hi (call after agg_reset*)"""
+        self._check(self.lib.fc_agg_set_idx_range(self.h, int(lo), int(hi)))
 
     def agg_set_timing(self, on: bool):
         self._check(self.lib.fc_agg_set_timing(self.h, 1 if on else 0))

@@ -250,6 +250,11 @@ int fc_p2p_connect(fc_ctx* ctx, int32_t world, int32_t rank, const uint8_t* h_al
 int fc_agg_emit_p2p(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, const int32_t* d_chrom, const uint8_t* d_flags,
                     const uint8_t* d_wden, const int16_t* d_q_a, const int16_t* d_q_b, const uint64_t* d_read_hash,
                     const uint64_t* d_qname_hash, const uint8_t* d_mask, uint64_t idx_base, void* stream);
+/* Stream-ordered barrier of all connected ranks over peer memory (one small kernel: every rank bumps an arrival word on
+ * every rank and waits for its own).  Orders the record stores of fc_agg_emit_p2p before the owners' fc_agg_finalize and
+ * the owners' counter resets before the next emit.  Every rank must call it the same number of times.  A rank that waits
+ * ~2 s gives up; the next fc_agg_finalize then fails with FC_E_STATE. */
+int fc_p2p_barrier(fc_ctx* ctx, void* stream);
 int fc_agg_reset_async(fc_ctx* ctx, void* stream);
 
 /* ------------------------------------------------------------------ native SAM ingest (host code)
@@ -301,6 +306,12 @@ int64_t fc_ingest_parse(fc_ingest* h, const char* text, int64_t nbytes, int32_t 
 void* fc_pinned_alloc(int64_t bytes);
 void fc_pinned_free(void* p);
 int fc_device_sync(fc_ctx* ctx);
+/* Declares (after fc_agg_reset*) that every record of this aggregation -- emitted here, appended, or arriving from peer
+ * ranks -- has lo <= idx < hi.  With a range about as large as the record count fc_agg_finalize ranks the junctions by
+ * discovery order (find_circ.py:684-686) with flags over the range instead of a sort.  A record outside a declared range
+ * is a caller error (undefined order).  Multi-GPU: idx is the position in the whole input stream, the range is the same on
+ * every rank. */
+int fc_agg_set_idx_range(fc_ctx* ctx, uint64_t lo, uint64_t hi);
 /* Device time of the stages of the last fc_agg_finalize() call on its sort-free path, measured with CUDA events on the
  * caller's stream while switched on: out_us[0..4] = table clears, accumulate kernel, first-record marks, finish kernel,
  * counter copy (bench.py's roofline for the aggregation kernel; no counterpart in the reference). */

@@ -51,7 +51,11 @@ def main():
     pairs = e.make_pairs(n, d_chrom, d_a, d_b, d_l, d_fl, planes, n_words, int(l.max()))
     e.scan(pairs, hits, 0)
     pay = (tn(np.ones(n, np.uint8)), tn(qa), tn(qb), tn(rh.view(np.int64)), tn(qh.view(np.int64)))
-    idx_base = rank << 40
+    # stream positions: every rank holds one contiguous shard of the input stream
+    n_cap = torch.tensor([n], dtype=torch.int64, device=dev)
+    dist.all_reduce(n_cap, op=dist.ReduceOp.MAX)
+    n_cap = int(n_cap.item())
+    idx_base = rank * n_cap
 
     def table():
         nj = e.agg_finalize(0)
@@ -70,11 +74,14 @@ def main():
             print("P2P (CUDA IPC) not available on this box -- only the NCCL path was checked")
         ta = tb
     else:
-        for _ in range(3):  # repeated steps: the barriers must keep the ranks apart
+        for it in range(3):  # repeated steps: the barriers must keep the ranks apart
             e.agg_reset_async(0)
-            parallel.stream_barrier(dist, dev)
+            if it > 0:  # declared idx range: discovery rank from flags; undeclared (it == 0): from a sort
+                e.agg_set_idx_range(0, world * n_cap)
+            # the library's peer-memory barrier, and (last round) the NCCL one-element all-reduce
+            parallel.stream_barrier(dist, dev, e if it < 2 else None, 0)
             e.agg_emit_p2p(n, hits, d_chrom, d_fl, *pay, idx_base, 0)
-            parallel.stream_barrier(dist, dev)
+            parallel.stream_barrier(dist, dev, e if it < 2 else None, 0)
             ta = table()
 
     # (c) union on rank 0: gather every rank's hits + payload and aggregate alone
