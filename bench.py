@@ -301,11 +301,17 @@ def run_gpu(args):
             ev_scan[1].record()
         if use_p2p:
             eng.agg_emit_p2p(n, hits, d["chrom"], d["flags"], d["wden"], d["q_a"], d["q_b"], d["read_hash"], d["qname_hash"], idx_base, stream)
+            if ev_scan:
+                ev_scan[2].record()
             parallel.stream_barrier(dist, dev, eng, stream)  # every rank's records have landed
         else:
             eng.agg_emit(n, hits, d["chrom"], d["flags"], d["wden"], d["q_a"], d["q_b"], d["read_hash"], d["qname_hash"], idx_base, stream)
+            if ev_scan:
+                ev_scan[2].record()
             if world > 1:
                 parallel.exchange_records(eng, dist, dev, stream, upper_bound=n)
+        if ev_scan:
+            ev_scan[3].record()
         return eng.agg_finalize(stream)
 
     # ---- pinned host copy of the batch (for `e2e`)
@@ -363,18 +369,21 @@ def run_gpu(args):
     sampler.start()
     time.sleep(0.3)
     # ---- timed: device-resident
-    tot_ms, scan_ms = 0.0, 0.0
+    tot_ms, scan_ms, emit_ms, pre_ms, xchg_ms = 0.0, 0.0, 0.0, 0.0, 0.0
     barrier()
     for _ in range(args.steps):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0, s1, s2, s3 = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         e0.record()
-        nj = step_device((s0, s1))
+        nj = step_device((s0, s1, s2, s3))
         e1.record()
         torch.cuda.synchronize()
         tot_ms += e0.elapsed_time(e1)
         scan_ms += s0.elapsed_time(s1)
+        emit_ms += s1.elapsed_time(s2)
+        pre_ms += e0.elapsed_time(s0)   # reset (+ the first barrier on the multi-GPU path)
+        xchg_ms += s2.elapsed_time(s3)  # second barrier / all-to-all (multi-GPU)
     barrier()
     launches = eng.launch_count() - launches0
     # ---- the aggregation kernel alone: a few more steps with the library's own CUDA events around its stages
@@ -459,7 +468,8 @@ def run_gpu(args):
                 "pairs_scanned_per_gpu": n, "junctions_rank0": int(nj), "l2": "flushed (256 MiB memset) before every timed step",
                 "timing": "per-step CUDA events summed over the steps; max over ranks",
                 "exchange": ("none" if world == 1 else ("fused emit+exchange over peer memory (CUDA IPC, NVLink)" if use_p2p else "partition + NCCL all-to-all")),
-                "scan_ms": scan_step, "merge_ms": ms_step - scan_step, "accumulate_kernel_ms": acc_step_ms, "seeds": {"genome": 1, "junctions": 2, "pairs": "3+1000*rank"},
+                "scan_ms": scan_step, "merge_ms": ms_step - scan_step, "accumulate_kernel_ms": acc_step_ms,
+                "emit_ms": emit_ms / args.steps, "reset_barrier_ms": pre_ms / args.steps, "exchange_barrier_ms": xchg_ms / args.steps, "seeds": {"genome": 1, "junctions": 2, "pairs": "3+1000*rank"},
             },
             "roofline": dominant,        # the kernel with the longest launch inside the step
             "roofline_other": other,     # the second kernel of the path

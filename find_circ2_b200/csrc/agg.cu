@@ -1147,9 +1147,11 @@ struct StageTimer {
 static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st) {
   fc_agg& a = ctx->agg;
   if (ub >= FUSED_MAX_RECORDS) return -100;
-  unsigned long long kcap = 1024;
-  while (kcap < 2ull * (unsigned long long)ub) kcap <<= 1;
-  const unsigned long long scap = 2ull * kcap;  // two inserts per record
+  // key table: one entry per junction, at most one junction per record (load <= 2/3); distinct set: two entries per record
+  // (load <= 2/3 when every read and every name is new, about half of that on real input)
+  unsigned long long kcap = 1024, scap = 2048;
+  while (2ull * kcap < 3ull * (unsigned long long)ub) kcap <<= 1;
+  while (scap < 3ull * (unsigned long long)ub) scap <<= 1;
   const unsigned int acap = (unsigned int)(ub + ub / 8 + 65536);  // junction ids incl. the ones lost to insert races
   int rc;
   StageTimer tm(ctx, st);
@@ -1441,12 +1443,20 @@ struct P2PView {
   int rank;
 };
 
-__global__ void emit_p2p_kernel(int64_t n, const fc_hit* __restrict__ hits, const uint8_t* __restrict__ mask,
-                                const int32_t* __restrict__ chrom, const uint8_t* __restrict__ flags,
-                                const uint8_t* __restrict__ wden, const int16_t* __restrict__ q_a,
-                                const int16_t* __restrict__ q_b, const uint64_t* __restrict__ read_hash,
-                                const uint64_t* __restrict__ qname_hash, uint64_t idx_base, P2PView pv,
-                                unsigned long long* __restrict__ overflow) {
+constexpr int P2P_THREADS = 512;
+
+__global__ void __launch_bounds__(P2P_THREADS) emit_p2p_kernel(int64_t n, const fc_hit* __restrict__ hits,
+                                                               const uint8_t* __restrict__ mask,
+                                                               const int32_t* __restrict__ chrom, const uint8_t* __restrict__ flags,
+                                                               const uint8_t* __restrict__ wden, const int16_t* __restrict__ q_a,
+                                                               const int16_t* __restrict__ q_b, const uint64_t* __restrict__ read_hash,
+                                                               const uint64_t* __restrict__ qname_hash, uint64_t idx_base, P2PView pv,
+                                                               unsigned long long* __restrict__ overflow) {
+  // the CTA's records are first grouped by destination in shared memory, then every destination's group goes out as one
+  // run of consecutive 16-byte stores: full-size write packets on NVLink instead of scattered 16-byte ones
+  __shared__ uint4 s_rec[P2P_THREADS * 3];
+  __shared__ unsigned int s_cnt[8], s_off[9];
+  __shared__ unsigned long long s_base[8];
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool in = i < n;
   fc_jrec r;
@@ -1475,10 +1485,6 @@ __global__ void emit_p2p_kernel(int64_t n, const fc_hit* __restrict__ hits, cons
       dest = (int)(fc_key_hash(r.chrom, r.start, r.end, r.sk, 0x5bd1e995ULL) % (uint64_t)pv.world);
     }
   }
-  // slot allocation: ONE system-scope atomic per CTA and destination (a shared counter per rank receives the
-  // allocations of every CTA of every rank; per-warp allocation made the owners' counters the bottleneck at 8 GPUs)
-  __shared__ unsigned int s_cnt[8];
-  __shared__ unsigned long long s_base[8];
   if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
   __syncthreads();
   unsigned int local = 0;
@@ -1496,18 +1502,37 @@ __global__ void emit_p2p_kernel(int64_t n, const fc_hit* __restrict__ hits, cons
     }
   }
   __syncthreads();
-  if (threadIdx.x < pv.world && s_cnt[threadIdx.x])
+  // slot allocation: ONE system-scope atomic per CTA and destination (a shared counter per rank receives the
+  // allocations of every CTA of every rank; per-warp allocation made the owners' counters the bottleneck at 8 GPUs)
+  if ((int)threadIdx.x < pv.world && s_cnt[threadIdx.x])
     s_base[threadIdx.x] = atomicAdd_system(pv.cnt[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+  if (threadIdx.x == 0) {
+    unsigned int acc = 0;
+    for (int d = 0; d < 8; ++d) {
+      s_off[d] = acc;
+      acc += d < pv.world ? s_cnt[d] : 0u;
+    }
+    s_off[8] = acc;
+  }
   __syncthreads();
   if (accept) {
-    const unsigned long long pos = s_base[dest] + local;
+    const uint4* src = reinterpret_cast<const uint4*>(&r);
+    uint4* dst = s_rec + (size_t)(s_off[dest] + local) * 3;
+    dst[0] = src[0];
+    dst[1] = src[1];
+    dst[2] = src[2];
+  }
+  __syncthreads();
+  const unsigned int words = s_off[8] * 3u;
+  for (unsigned int w = threadIdx.x; w < words; w += blockDim.x) {
+    const unsigned int rec = w / 3u, part = w - rec * 3u;
+    int d = 0;
+#pragma unroll
+    for (int k = 1; k < 8; ++k) d += (k < pv.world && rec >= s_off[k]) ? 1 : 0;
+    const unsigned long long pos = s_base[d] + (rec - s_off[d]);
     if (pos < pv.capacity) {
-      uint4* dst = reinterpret_cast<uint4*>(pv.recs[dest] + pos);
-      const uint4* src = reinterpret_cast<const uint4*>(&r);
-      dst[0] = src[0];
-      dst[1] = src[1];
-      dst[2] = src[2];
-    } else {
+      reinterpret_cast<uint4*>(pv.recs[d] + pos)[part] = s_rec[w];
+    } else if (part == 0u) {
       atomicAdd(overflow, 1ull);
     }
   }
@@ -1574,7 +1599,7 @@ extern "C" int fc_agg_emit_p2p(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, con
   pv.world = a.p2p_world;
   pv.rank = a.p2p_rank;
   unsigned long long* counters = (unsigned long long*)a.counters.p;
-  emit_p2p_kernel<<<nblk(n, 1024), 1024, 0, st>>>(n, d_hits, d_mask, d_chrom, d_flags, d_wden, d_q_a, d_q_b, d_read_hash,
+  emit_p2p_kernel<<<nblk(n, P2P_THREADS), P2P_THREADS, 0, st>>>(n, d_hits, d_mask, d_chrom, d_flags, d_wden, d_q_a, d_q_b, d_read_hash,
                                                 d_qname_hash, idx_base, pv, counters + 4);
   FC_LAUNCH_CHECK(ctx);
   a.n_recs = a.p2p_capacity;  // upper bound; the exact count is the (shared) device counter
