@@ -63,6 +63,38 @@ static_assert(offsetof(JAcc, cw) == 4 && offsetof(JAcc, cb) == 24 && offsetof(JA
                   offsetof(JAcc, n_uniq) == 68 && offsetof(JAcc, first_idx) == 80,
               "accumulate_kernel's 64-bit pair adds depend on this layout");
 
+__device__ __forceinline__ void emit_stage_record(int64_t i, const fc_hit& h, const int32_t* __restrict__ chrom,
+                                                  const uint8_t* __restrict__ flags, const uint8_t* __restrict__ wden,
+                                                  const int16_t* __restrict__ q_a, const int16_t* __restrict__ q_b,
+                                                  const uint64_t* __restrict__ read_hash, const uint64_t* __restrict__ qname_hash,
+                                                  uint64_t idx_base, const uint64_t* __restrict__ idx, uint4* s_rec,
+                                                  unsigned int warp_off, unsigned int ballot, unsigned int lane) {
+  const uint32_t fl = flags[i];
+  const bool backsplice = fl & FC_PF_BACKSPLICE;
+  fc_jrec r;
+  r.chrom = (uint32_t)chrom[i];
+  r.start = (uint32_t)h.start;
+  r.end = (uint32_t)h.end;
+  const uint32_t strand = h.w3 & 1u, sig = (h.w3 >> 1) & 0xFFFu;
+  const uint64_t rh = read_hash[i];
+  r.sk = strand | (backsplice ? 0u : 2u) | ((uint32_t)(rh & 1ull) << 2) | ((uint32_t)wden[i] << 8) | (sig << 16);
+  r.idx = idx ? idx[i] : idx_base + (uint64_t)i;
+  r.read_hash = rh;
+  r.qname_hash = qname_hash[i];
+  // by convention A precedes B in the genome: swap for back-splices (find_circ.py:552-553)
+  r.q_left = backsplice ? q_b[i] : q_a[i];
+  r.q_right = backsplice ? q_a[i] : q_b[i];
+  r.n_hits = (uint16_t)(h.w2 & 0xFFFFu);
+  r.dist = (uint8_t)((h.w2 >> 16) & 0xFFu);
+  r.ov = (uint8_t)(h.w2 >> 24);
+  // group the CTA's records in shared memory and write them as one run of consecutive 16-byte stores
+  uint4* stage = s_rec + (size_t)(warp_off + __popc(ballot & ((1u << lane) - 1u))) * 3;
+  const uint4* src = reinterpret_cast<const uint4*>(&r);
+  stage[0] = src[0];
+  stage[1] = src[1];
+  stage[2] = src[2];
+}
+
 // One record per accepted pair (the scan found a breakpoint and the caller's mask, if any, keeps the pair).  The CTA
 // claims its slots with one atomic on the record counter, so the buffer is NOT in stream order: every consumer orders
 // by fc_jrec.idx where order matters (discovery rank, sequential float sums of the sort-based path).
@@ -74,7 +106,9 @@ __global__ void __launch_bounds__(256) emit_kernel(int64_t n, const fc_hit* __re
                                                    const uint64_t* __restrict__ idx, unsigned long long* __restrict__ n_recs,
                                                    fc_jrec* __restrict__ recs) {
   __shared__ unsigned int s_warp[8];
+  __shared__ unsigned int s_total;
   __shared__ unsigned long long s_base;
+  __shared__ uint4 s_rec[256 * 3];
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   fc_hit h = {0, 0, 0u, 0u};
   bool accept = false;
@@ -94,33 +128,15 @@ __global__ void __launch_bounds__(256) emit_kernel(int64_t n, const fc_hit* __re
       s_warp[w] = total;
       total += c;
     }
+    s_total = total;
     s_base = total ? atomicAdd(n_recs, (unsigned long long)total) : 0ull;
   }
   __syncthreads();
-  if (!accept) return;
-  const uint32_t fl = flags[i];
-  const bool backsplice = fl & FC_PF_BACKSPLICE;
-  fc_jrec r;
-  r.chrom = (uint32_t)chrom[i];
-  r.start = (uint32_t)h.start;
-  r.end = (uint32_t)h.end;
-  const uint32_t strand = h.w3 & 1u, sig = (h.w3 >> 1) & 0xFFFu;
-  const uint64_t rh = read_hash[i];
-  r.sk = strand | (backsplice ? 0u : 2u) | ((uint32_t)(rh & 1ull) << 2) | ((uint32_t)wden[i] << 8) | (sig << 16);
-  r.idx = idx ? idx[i] : idx_base + (uint64_t)i;
-  r.read_hash = rh;
-  r.qname_hash = qname_hash[i];
-  // by convention A precedes B in the genome: swap for back-splices (find_circ.py:552-553)
-  r.q_left = backsplice ? q_b[i] : q_a[i];
-  r.q_right = backsplice ? q_a[i] : q_b[i];
-  r.n_hits = (uint16_t)(h.w2 & 0xFFFFu);
-  r.dist = (uint8_t)((h.w2 >> 16) & 0xFFu);
-  r.ov = (uint8_t)(h.w2 >> 24);
-  uint4* dst = reinterpret_cast<uint4*>(recs + (s_base + s_warp[warp] + __popc(ballot & ((1u << lane) - 1u))));
-  const uint4* src = reinterpret_cast<const uint4*>(&r);
-  dst[0] = src[0];
-  dst[1] = src[1];
-  dst[2] = src[2];
+  if (accept) emit_stage_record(i, h, chrom, flags, wden, q_a, q_b, read_hash, qname_hash, idx_base, idx, s_rec, s_warp[warp],
+                                ballot, lane);
+  __syncthreads();
+  uint4* out = reinterpret_cast<uint4*>(recs + s_base);
+  for (unsigned int w = threadIdx.x; w < s_total * 3u; w += blockDim.x) out[w] = s_rec[w];
 }
 
 __global__ void key_hash_kernel(int64_t n, const fc_jrec* __restrict__ recs, uint64_t seed, uint64_t* __restrict__ h,
