@@ -503,6 +503,9 @@ def test_sort_free_aggregation_repeated_calls(torch_cuda, hot):
         else:
             order = rng.permutation(n)
             e.agg_append_host(recs[order])
+            if rep % 4 == 1:
+                # the caller knows the idx range of what it appended: discovery rank from flags instead of a sort
+                e.agg_set_idx_range(int(recs["idx"].min()), int(recs["idx"].max()) + 1)
         nj = e.agg_finalize()
         got = _junction_rows(e.agg_fetch(nj))
         want = _py_aggregate(recs[np.argsort(recs["idx"], kind="stable")])
