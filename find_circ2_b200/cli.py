@@ -94,14 +94,52 @@ def parse_args(argv):
 
 
 def native_ok(opt: Options, path) -> bool:
-    """the native ingest covers SAM text files; BAM, stdin and --all-hits / --noop use the python reader"""
-    return bool(path) and path != "-" and path.endswith("sam") and not opt.allhits and not opt.noop and opt.native
+    """the native ingest covers SAM text (a file whose name ends in 'sam', or stdin: find_circ.py:461-469); BAM and
+    --all-hits / --noop use the python reader"""
+    text = (not path) or path == "-" or path.endswith("sam")
+    return text and not opt.allhits and not opt.noop and opt.native
+
+
+class _Prefixed(object):
+    """a binary stream with some bytes put back in front of it"""
+
+    def __init__(self, prefix: bytes, fh):
+        self.prefix, self.fh = prefix, fh
+
+    def read(self, n: int) -> bytes:
+        if self.prefix:
+            head, self.prefix = self.prefix[:n], self.prefix[n:]
+            if len(head) == n:
+                return head
+            return head + self.fh.read(n - len(head))
+        return self.fh.read(n)
+
+
+def _stream_header(fh):
+    """@SQ names from the head of a SAM text stream; returns (names, stream positioned at the first record)"""
+    names, first = [], b""
+    while True:
+        line = fh.readline()
+        if not line:
+            break
+        if not line.startswith(b"@"):
+            first = line
+            break
+        if line.startswith(b"@SQ"):
+            for x in line.rstrip(b"\r\n").split(b"\t")[1:]:
+                if x.startswith(b"SN:"):
+                    names.append(x[3:].decode("latin-1"))
+    return names, _Prefixed(first, fh)
 
 
 def run_to_strings(opt: Options, path=None, engine=None, native=None):
     """the whole run, outputs as strings (tests and the single-process CLI share this)"""
     native = native_ok(opt, path) if native is None else native
-    if native:
+    stream = None
+    if native and (not path or path == "-"):
+        names, stream = _stream_header(sys.stdin.buffer)
+        records = None
+    elif native:
         names = samio.sam_header_names(path)
         records = None
     else:
@@ -109,7 +147,9 @@ def run_to_strings(opt: Options, path=None, engine=None, native=None):
     run = Run(opt, names, engine)
     try:
         t0 = time.perf_counter()
-        if native:
+        if stream is not None:
+            run.process_native(stream)
+        elif native:
             with open(path, "rb") as fh:
                 run.process_native(fh)
         else:

@@ -30,3 +30,32 @@ def test_host_logic_matches_reference(case_dir, ref_dir, argv, native):
     assert out["reads"] == rd("spliced_reads.fastq")
     assert O.canonical_multi(out["multi"]) == O.canonical_multi(rd("multi_events.tsv"))
     assert out["counters"] == rd("counters.txt")
+
+
+def test_native_ingest_from_stdin(monkeypatch):
+    """SAM text piped in (`bwa mem ... | find_circ.py`, find_circ.py:461-469) goes through the native ingest too: the
+    header is read off the stream, the body is parsed in chunks"""
+    import io
+    import sys
+
+    from conftest import GOLDEN
+    from find_circ2_b200 import cli
+
+    case_dir = os.path.join(GOLDEN, "synth_a")
+    ref_dir = os.path.join(case_dir, "ref_default")
+    opt = cli.parse_args(["-G", os.path.join(case_dir, "genome.fa"), "-n", "test"])[0]
+    opt.batch_pairs = 97
+    assert cli.native_ok(opt, None) and cli.native_ok(opt, "-") and not cli.native_ok(opt, "x.bam")
+    eng = FakeEngine(0, opt.asize, opt.margin, opt.maxdist, opt.noncanonical, opt.strandpref)
+    eng.load_genome_fasta(opt.genome)
+
+    class Stdin(object):
+        buffer = io.BufferedReader(io.BytesIO(open(os.path.join(case_dir, "input.sam"), "rb").read()))
+
+    monkeypatch.setattr(sys, "stdin", Stdin())
+    out = cli.run_to_strings(opt, None, engine=eng)
+    rd = lambda n: open(os.path.join(ref_dir, n)).read()  # noqa: E731
+    assert O.canonical_bed(out["circ"]) == O.canonical_bed(rd("circ_splice_sites.bed"))
+    assert O.canonical_bed(out["lin"]) == O.canonical_bed(rd("lin_splice_sites.bed"))
+    assert out["reads"] == rd("spliced_reads.fastq")
+    assert out["counters"] == rd("counters.txt")
