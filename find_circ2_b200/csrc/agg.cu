@@ -634,8 +634,9 @@ __device__ __forceinline__ void clear_acc(JAcc2* a) {
 // (given, or summed here when there are few tiles) to a block-wide scan of its tile.
 constexpr int RANK_TILE = 1024;
 
-__global__ void mark_first_kernel(const unsigned int* __restrict__ ctr, unsigned int acap, const JAcc2* __restrict__ acc,
-                                  unsigned long long idx_lo, uint32_t* __restrict__ flag, uint32_t* __restrict__ tile_count) {
+__global__ void mark_first_kernel(unsigned int* __restrict__ ctr, unsigned int acap, const JAcc2* __restrict__ acc,
+                                  unsigned long long idx_lo, unsigned long long range, uint32_t* __restrict__ flag,
+                                  uint32_t* __restrict__ tile_count) {
   const unsigned int n_alloc = min(ctr[FC_N_ALLOC], acap);
   const unsigned int step = gridDim.x * blockDim.x;
   for (unsigned int j0 = blockIdx.x * blockDim.x; j0 < n_alloc; j0 += step) {  // warp-uniform trip count
@@ -643,9 +644,13 @@ __global__ void mark_first_kernel(const unsigned int* __restrict__ ctr, unsigned
     bool real = false;
     unsigned long long p = 0;
     if (j < n_alloc && (uint32_t)acc[j].spanned_frags != 0u) {  // (0: an id that lost its insert race)
-      real = true;
       p = ~acc[j].first_inv - idx_lo;
-      flag[p] = j + 1u;
+      if (p < range) {
+        real = true;
+        flag[p] = j + 1u;
+      } else {
+        atomicAdd(&ctr[FC_N_OVERFLOW], 1u);  // a record outside the declared idx range: the call goes to the sort-based path
+      }
     }
     // early ids are early discoveries: neighbouring lanes mostly hit the same tile, so count once per warp and tile
     const unsigned int tile = real ? (unsigned int)(p / RANK_TILE) : 0xFFFFFFFFu;
@@ -1219,7 +1224,8 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st) {
   uint32_t* vA = nullptr;
   fc_junction* tmpj = nullptr;
   if (dense) {
-    mark_first_kernel<<<sweep_blocks, 256, 0, st>>>(ctr, acap, (const JAcc2*)a.f_acc.p, a.idx_lo, flag, tile_count);
+    mark_first_kernel<<<sweep_blocks, 256, 0, st>>>(ctr, acap, (const JAcc2*)a.f_acc.p, a.idx_lo, (unsigned long long)range, flag,
+                                                    tile_count);
     FC_LAUNCH_CHECK(ctx);
     uint32_t* tile_base = nullptr;
     if (n_tiles > 4096) {  // many tiles: scan the counts once instead of summing them in every block
@@ -1263,6 +1269,11 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st) {
     return fc_fail(ctx, FC_E_NOMEM, "peer-to-peer record buffer overflow (%llu records dropped): raise the capacity", h[4]);
   const unsigned int n_other = (unsigned int)(h[8] >> 32), n_overflow = (unsigned int)h[9];
   const int64_t nj = (int64_t)(h[9] >> 32);
+  if (n_overflow) {  // ids ran out, or a record lies outside a declared idx range: its accumulator was not consumed
+    a.f_dirty = true;
+    a.range_declared = false;
+    a.max_idx = ~0ull;
+  }
   if (n_other || n_overflow) return -100;
   if (!dense && nj > 0) {
     uint32_t* vB = vA + ub;

@@ -308,8 +308,8 @@ void fc_pinned_free(void* p);
 int fc_device_sync(fc_ctx* ctx);
 /* Declares (after fc_agg_reset*) that every record of this aggregation -- emitted here, appended, or arriving from peer
  * ranks -- has lo <= idx < hi.  With a range about as large as the record count fc_agg_finalize ranks the junctions by
- * discovery order (find_circ.py:684-686) with flags over the range instead of a sort.  A record outside a declared range
- * is a caller error (undefined order).  Multi-GPU: idx is the position in the whole input stream, the range is the same on
+ * discovery order (find_circ.py:684-686) with flags over the range instead of a sort.  A junction whose first record lies
+ * outside a declared range is detected: the call then ranks by sort (same result, slower).  Multi-GPU: idx is the position in the whole input stream, the range is the same on
  * every rank. */
 int fc_agg_set_idx_range(fc_ctx* ctx, uint64_t lo, uint64_t hi);
 /* Device time of the stages of the last fc_agg_finalize() call on its sort-free path, measured with CUDA events on the

@@ -515,3 +515,20 @@ def test_sort_free_aggregation_repeated_calls(torch_cuda, hot):
         assert e.agg_finalize() == nj  # idempotent: the tables were left clean
         assert _junction_rows(e.agg_fetch(nj)) == want
     e.close()
+
+
+def test_declared_idx_range_that_is_too_small_still_gives_the_right_table(torch_cuda):
+    """fc_agg_set_idx_range is a promise of the caller; a record outside it must not corrupt anything: the call falls back
+    to ranking by sort and the next calls on the engine work as usual"""
+    e = _engine()
+    rng = np.random.default_rng(5)
+    recs = _random_records(30000, 500, 77, dens=POW2)
+    want = _py_aggregate(recs[np.argsort(recs["idx"], kind="stable")])
+    lo, hi = int(recs["idx"].min()), int(recs["idx"].max()) + 1
+    for declared in ((lo + 1000, hi), (lo, lo + (hi - lo) // 2), (lo, hi)):
+        e.agg_reset()
+        e.agg_append_host(recs[rng.permutation(len(recs))])
+        e.agg_set_idx_range(*declared)
+        nj = e.agg_finalize()
+        assert _junction_rows(e.agg_fetch(nj)) == want, declared
+    e.close()
