@@ -81,6 +81,7 @@ SYMBOLS = [
     ("fc_genome_fetch", C.c_int, [_P, C.c_int32, C.c_int64, C.c_int64, _P]),
     ("fc_pack_reads", C.c_int, [_P, C.c_int64, _P, C.c_int32, _P, C.c_int32, _P, _P, _P, _P, _P]),
     ("fc_scan", C.c_int, [_P, C.POINTER(ScanParams), C.POINTER(Pairs), _P, _P]),
+    ("fc_scan_emit", C.c_int, [_P, C.POINTER(ScanParams), C.POINTER(Pairs), _P, _P, _P, _P, _P, _P, C.c_uint64, _P, _P]),
     ("fc_scan_ties", C.c_int, [_P, C.POINTER(ScanParams), C.POINTER(Pairs), _P, _P, _P, _P]),
     ("fc_scan_host", C.c_int, [_P, C.POINTER(ScanParams), C.c_int64, _P, _P, _P, _P, _P, _P, C.c_int32, _P]),
     ("fc_batch_host", C.c_int, [_P, C.POINTER(ScanParams), C.c_int64, _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P,

@@ -63,80 +63,24 @@ static_assert(offsetof(JAcc, cw) == 4 && offsetof(JAcc, cb) == 24 && offsetof(JA
                   offsetof(JAcc, n_uniq) == 68 && offsetof(JAcc, first_idx) == 80,
               "accumulate_kernel's 64-bit pair adds depend on this layout");
 
-__device__ __forceinline__ void emit_stage_record(int64_t i, const fc_hit& h, const int32_t* __restrict__ chrom,
-                                                  const uint8_t* __restrict__ flags, const uint8_t* __restrict__ wden,
-                                                  const int16_t* __restrict__ q_a, const int16_t* __restrict__ q_b,
-                                                  const uint64_t* __restrict__ read_hash, const uint64_t* __restrict__ qname_hash,
-                                                  uint64_t idx_base, const uint64_t* __restrict__ idx, uint4* s_rec,
-                                                  unsigned int warp_off, unsigned int ballot, unsigned int lane) {
-  const uint32_t fl = flags[i];
-  const bool backsplice = fl & FC_PF_BACKSPLICE;
-  fc_jrec r;
-  r.chrom = (uint32_t)chrom[i];
-  r.start = (uint32_t)h.start;
-  r.end = (uint32_t)h.end;
-  const uint32_t strand = h.w3 & 1u, sig = (h.w3 >> 1) & 0xFFFu;
-  const uint64_t rh = read_hash[i];
-  r.sk = strand | (backsplice ? 0u : 2u) | ((uint32_t)(rh & 1ull) << 2) | ((uint32_t)wden[i] << 8) | (sig << 16);
-  r.idx = idx ? idx[i] : idx_base + (uint64_t)i;
-  r.read_hash = rh;
-  r.qname_hash = qname_hash[i];
-  // by convention A precedes B in the genome: swap for back-splices (find_circ.py:552-553)
-  r.q_left = backsplice ? q_b[i] : q_a[i];
-  r.q_right = backsplice ? q_a[i] : q_b[i];
-  r.n_hits = (uint16_t)(h.w2 & 0xFFFFu);
-  r.dist = (uint8_t)((h.w2 >> 16) & 0xFFu);
-  r.ov = (uint8_t)(h.w2 >> 24);
-  // group the CTA's records in shared memory and write them as one run of consecutive 16-byte stores
-  uint4* stage = s_rec + (size_t)(warp_off + __popc(ballot & ((1u << lane) - 1u))) * 3;
-  const uint4* src = reinterpret_cast<const uint4*>(&r);
-  stage[0] = src[0];
-  stage[1] = src[1];
-  stage[2] = src[2];
-}
-
-// One record per accepted pair (the scan found a breakpoint and the caller's mask, if any, keeps the pair).  The CTA
-// claims its slots with one atomic on the record counter, so the buffer is NOT in stream order: every consumer orders
-// by fc_jrec.idx where order matters (discovery rank, sequential float sums of the sort-based path).
+// One record per accepted pair (the scan found a breakpoint and the caller's mask, if any, keeps the pair); see
+// emit_core.cuh for how a CTA writes its records.
 __global__ void __launch_bounds__(256) emit_kernel(int64_t n, const fc_hit* __restrict__ hits, const uint8_t* __restrict__ mask,
                                                    const int32_t* __restrict__ chrom, const uint8_t* __restrict__ flags,
-                                                   const uint8_t* __restrict__ wden, const int16_t* __restrict__ q_a,
-                                                   const int16_t* __restrict__ q_b, const uint64_t* __restrict__ read_hash,
-                                                   const uint64_t* __restrict__ qname_hash, uint64_t idx_base,
-                                                   const uint64_t* __restrict__ idx, unsigned long long* __restrict__ n_recs,
-                                                   fc_jrec* __restrict__ recs) {
-  __shared__ unsigned int s_warp[8];
-  __shared__ unsigned int s_total;
-  __shared__ unsigned long long s_base;
-  __shared__ uint4 s_rec[256 * 3];
+                                                   fc::EmitArgs e) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   fc_hit h = {0, 0, 0u, 0u};
   bool accept = false;
+  uint32_t c = 0, fl = 0;
   if (i < n) {
     h = hits[i];
     accept = (h.w2 & 0xFFFFu) != 0u && (!mask || mask[i]);
-  }
-  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned ballot = __ballot_sync(0xffffffffu, accept);
-  if (lane == 0) s_warp[warp] = __popc(ballot);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned int total = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
-      const unsigned int c = s_warp[w];
-      s_warp[w] = total;
-      total += c;
+    if (accept) {
+      c = (uint32_t)chrom[i];
+      fl = flags[i];
     }
-    s_total = total;
-    s_base = total ? atomicAdd(n_recs, (unsigned long long)total) : 0ull;
   }
-  __syncthreads();
-  if (accept) emit_stage_record(i, h, chrom, flags, wden, q_a, q_b, read_hash, qname_hash, idx_base, idx, s_rec, s_warp[warp],
-                                ballot, lane);
-  __syncthreads();
-  uint4* out = reinterpret_cast<uint4*>(recs + s_base);
-  for (unsigned int w = threadIdx.x; w < s_total * 3u; w += blockDim.x) out[w] = s_rec[w];
+  fc::emit_block<256>(accept, i, h.start, h.end, h.w2, h.w3, c, fl, e);
 }
 
 __global__ void key_hash_kernel(int64_t n, const fc_jrec* __restrict__ recs, uint64_t seed, uint64_t* __restrict__ h,
@@ -946,35 +890,48 @@ int fc_agg_reserve_records(fc_ctx* ctx, int64_t extra, cudaStream_t st) {
   return FC_OK;
 }
 
+// bookkeeping around an emit (the stand-alone kernel below or the scan kernel that emits on the way, scan.cu)
+int fc_agg_emit_begin(fc_ctx* ctx, int64_t n, cudaStream_t st, fc::EmitArgs* e) {
+  if (n >= (1ll << 32)) return fc_fail(ctx, FC_E_ARG, "batch too large");
+  fc_agg& a = ctx->agg;
+  int rc = ensure_counters(ctx, st);
+  if (rc) return rc;
+  // upper bound of the record count so far (the exact count lives on the device)
+  FC_CUDA(ctx, a.recs.reserve((size_t)(a.n_recs + n) * sizeof(fc_jrec), st, true, (size_t)a.n_recs * sizeof(fc_jrec)));
+  e->n_recs = (unsigned long long*)a.counters.p;
+  e->recs = (fc_jrec*)a.recs.p;
+  return FC_OK;
+}
+
+void fc_agg_emit_end(fc_ctx* ctx, int64_t n, uint64_t idx_base, bool explicit_idx) {
+  fc_agg& a = ctx->agg;
+  a.n_recs += n;  // upper bound until the next sync
+  a.n_exact = false;
+  a.n_junc = -1;
+  a.unordered = true;  // slots are claimed per CTA: consumers that need stream order restore it from idx
+  if (a.range_declared) {
+    // the caller has declared the idx range of everything that arrives
+  } else if (explicit_idx) {
+    a.max_idx = ~0ull;  // explicit positions: range unknown
+  } else if (a.max_idx != ~0ull) {
+    if (idx_base + (uint64_t)n > a.max_idx) a.max_idx = idx_base + (uint64_t)n;
+    if (idx_base < a.idx_lo) a.idx_lo = idx_base;
+  }
+}
+
 static int agg_emit_impl(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, const int32_t* d_chrom, const uint8_t* d_flags,
                            const uint8_t* d_wden, const int16_t* d_q_a, const int16_t* d_q_b,
                            const uint64_t* d_read_hash, const uint64_t* d_qname_hash, const uint8_t* d_mask,
                            uint64_t idx_base, const uint64_t* d_idx, void* stream) {
   if (!ctx || n < 0) return FC_E_ARG;
   if (n == 0) return FC_OK;
-  if (n >= (1ll << 32)) return fc_fail(ctx, FC_E_ARG, "batch too large");
   cudaStream_t st = (cudaStream_t)stream;
-  fc_agg& a = ctx->agg;
-  int rc = ensure_counters(ctx, st);
+  fc::EmitArgs e{d_wden, d_q_a, d_q_b, d_read_hash, d_qname_hash, idx_base, d_idx, nullptr, nullptr};
+  int rc = fc_agg_emit_begin(ctx, n, st, &e);
   if (rc) return rc;
-  // upper bound of the record count so far (the exact count lives on the device)
-  int64_t ub = a.n_recs + n;
-  FC_CUDA(ctx, a.recs.reserve((size_t)ub * sizeof(fc_jrec), st, true, (size_t)a.n_recs * sizeof(fc_jrec)));
-  emit_kernel<<<nblk(n, 256), 256, 0, st>>>(n, d_hits, d_mask, d_chrom, d_flags, d_wden, d_q_a, d_q_b, d_read_hash, d_qname_hash,
-                                            idx_base, d_idx, (unsigned long long*)a.counters.p, (fc_jrec*)a.recs.p);
+  emit_kernel<<<nblk(n, 256), 256, 0, st>>>(n, d_hits, d_mask, d_chrom, d_flags, e);
   FC_LAUNCH_CHECK(ctx);
-  a.n_recs = ub;  // upper bound until the next sync
-  a.n_exact = false;
-  a.n_junc = -1;
-  a.unordered = true;  // slots are claimed per CTA: consumers that need stream order restore it from idx
-  if (a.range_declared) {
-    // the caller has declared the idx range of everything that arrives
-  } else if (d_idx) {
-    a.max_idx = ~0ull;  // explicit positions: range unknown
-  } else if (a.max_idx != ~0ull) {
-    if (idx_base + (uint64_t)n > a.max_idx) a.max_idx = idx_base + (uint64_t)n;
-    if (idx_base < a.idx_lo) a.idx_lo = idx_base;
-  }
+  fc_agg_emit_end(ctx, n, idx_base, d_idx != nullptr);
   return FC_OK;
 }
 

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../include/findcirc_b200.h"
+#include "emit_core.cuh"
 #include "scan_core.cuh"
 
 struct fc_genome {
@@ -105,6 +106,8 @@ struct fc_ctx {
 int fc_fail(fc_ctx* ctx, int code, const char* fmt, ...);
 int fc_genome_ensure_tiles(fc_ctx* ctx, int w, cudaStream_t st);
 int fc_agg_reserve_records(fc_ctx* ctx, int64_t extra, cudaStream_t st);  // room for `extra` more records, now
+int fc_agg_emit_begin(fc_ctx* ctx, int64_t n, cudaStream_t st, fc::EmitArgs* e);  // room + where the records go
+void fc_agg_emit_end(fc_ctx* ctx, int64_t n, uint64_t idx_base, bool explicit_idx);
 
 #define FC_CUDA(ctx, call)                                                                         \
   do {                                                                                             \

@@ -63,6 +63,36 @@ __global__ void __launch_bounds__(BS, MB) scan_kernel(fc::GenomeView g, fc::Scan
   }
 }
 
+// the same scan, and every pair that found a breakpoint becomes a junction record on the way (fc_scan_emit): the hits
+// do not travel to HBM and back before they are turned into records, and one launch less stands in the step
+template <int NP, int T, int BS, int MB>
+__global__ void __launch_bounds__(BS, MB) scan_emit_kernel(fc::GenomeView g, fc::ScanCfg cfg, fc::ReadView rv,
+                                                        const int32_t* __restrict__ chrom,
+                                                        const int32_t* __restrict__ a_start,
+                                                        const int32_t* __restrict__ b_end, const int32_t* __restrict__ l,
+                                                        const uint8_t* __restrict__ flags, fc_hit* __restrict__ out,
+                                                        fc::EmitArgs e) {
+  const int64_t i = (int64_t)blockIdx.x * BS + threadIdx.x;  // one pair per thread: the whole CTA reaches emit_block
+  fc::HitOut h;
+  h.start = h.end = 0;
+  h.w2 = h.w3 = 0u;
+  uint32_t c = 0, fl = 0;
+  if (i < rv.n) {
+    fc::PairArgs p;
+    p.chrom = chrom[i];
+    p.a_start = a_start[i];
+    p.b_end = b_end[i];
+    p.l = l[i];
+    p.flags = flags[i];
+    c = (uint32_t)p.chrom;
+    fl = p.flags;
+    fc::NoEmit ne;
+    fc::scan_pair<NP, T>(g, cfg, p, rv, i, h, ne, false);
+    reinterpret_cast<uint4*>(out)[i] = make_uint4((uint32_t)h.start, (uint32_t)h.end, h.w2, h.w3);
+  }
+  fc::emit_block<BS>((h.w2 & 0xFFFFu) != 0u, i, h.start, h.end, h.w2, h.w3, c, fl, e);
+}
+
 // ---------------------------------------------------------------- --all-hits: every tie of every pair
 struct TieEmit {
   int best;
@@ -144,26 +174,30 @@ extern "C" int fc_pack_reads(fc_ctx* ctx, int64_t n, const uint8_t* d_ascii, int
   return FC_OK;
 }
 
-extern "C" int fc_scan(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs* pr, fc_hit* d_out, void* stream) {
-  int rc = check_pairs(ctx, p, pr);
-  if (rc) return rc;
-  if (pr->n == 0) return FC_OK;
-  cudaStream_t st = (cudaStream_t)stream;
+static int scan_launch(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs* pr, fc_hit* d_out, const fc::EmitArgs* emit,
+                       cudaStream_t st) {
   const int need = pr->max_l + 2;
   if (!p->noncanonical) {
-    rc = fc_genome_ensure_tiles(ctx, need, st);  // no-op when the tile store already covers this window size
+    int rc = fc_genome_ensure_tiles(ctx, need, st);  // no-op when the tile store already covers this window size
     if (rc) return rc;
   }
   fc::ScanCfg cfg{p->margin, p->maxdist, p->noncanonical, p->strandpref};
   fc::GenomeView g = ctx->genome.view();
   fc::ReadView rv{pr->d_rlo, pr->d_rhi, pr->d_rn, pr->n, pr->n_words, pr->plane_stride > 0 ? pr->plane_stride : pr->n};
-#define FC_SCAN_LAUNCH_BS(NP, T, BS, MB)                                                                               \
-  scan_kernel<NP, T, BS, MB><<<(unsigned)((pr->n + BS - 1) / BS), BS, 0, st>>>(g, cfg, rv, pr->d_chrom, pr->d_a_start,   \
-                                                                               pr->d_b_end, pr->d_l, pr->d_flags, d_out)
+#define FC_SCAN_LAUNCH_BS(NP, T, BS, MB)                                                                                \
+  {                                                                                                                     \
+    const unsigned grid = (unsigned)((pr->n + BS - 1) / BS);                                                            \
+    if (emit)                                                                                                           \
+      scan_emit_kernel<NP, T, BS, MB><<<grid, BS, 0, st>>>(g, cfg, rv, pr->d_chrom, pr->d_a_start, pr->d_b_end, pr->d_l, \
+                                                           pr->d_flags, d_out, *emit);                                  \
+    else                                                                                                                \
+      scan_kernel<NP, T, BS, MB><<<grid, BS, 0, st>>>(g, cfg, rv, pr->d_chrom, pr->d_a_start, pr->d_b_end, pr->d_l,      \
+                                                      pr->d_flags, d_out);                                              \
+  }
   // 256-thread CTAs, 48 registers -> 5 CTAs (40 warps) per SM.  Measured alternatives on B200 (round 1): 128- and
   // 192-thread CTAs, register caps 32/40/58, and a persistent software-pipelined variant with L2 prefetch of the next
   // pair's tiles were all equal or slower.
-#define FC_SCAN_LAUNCH(NP, T) FC_SCAN_LAUNCH_BS(NP, T, 256, 5);
+#define FC_SCAN_LAUNCH(NP, T) FC_SCAN_LAUNCH_BS(NP, T, 256, 5)
   // the kernel specialisation follows the tile geometry of the store (scan_core.cuh: tile_geometry)
   switch (g.tile_T) {
     case 1:
@@ -180,6 +214,28 @@ extern "C" int fc_scan(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs* pr,
 #undef FC_SCAN_LAUNCH_BS
 #undef FC_SCAN_LAUNCH
   FC_LAUNCH_CHECK(ctx);
+  return FC_OK;
+}
+
+extern "C" int fc_scan(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs* pr, fc_hit* d_out, void* stream) {
+  int rc = check_pairs(ctx, p, pr);
+  if (rc) return rc;
+  if (pr->n == 0) return FC_OK;
+  return scan_launch(ctx, p, pr, d_out, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int fc_scan_emit(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs* pr, fc_hit* d_out, const uint8_t* d_wden,
+                            const int16_t* d_q_a, const int16_t* d_q_b, const uint64_t* d_read_hash,
+                            const uint64_t* d_qname_hash, uint64_t idx_base, const uint64_t* d_idx, void* stream) {
+  int rc = check_pairs(ctx, p, pr);
+  if (rc) return rc;
+  if (!d_out || !d_wden || !d_q_a || !d_q_b || !d_read_hash || !d_qname_hash) return FC_E_ARG;
+  if (pr->n == 0) return FC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  fc::EmitArgs e{d_wden, d_q_a, d_q_b, d_read_hash, d_qname_hash, idx_base, d_idx, nullptr, nullptr};
+  if ((rc = fc_agg_emit_begin(ctx, pr->n, st, &e))) return rc;
+  if ((rc = scan_launch(ctx, p, pr, d_out, &e, st))) return rc;
+  fc_agg_emit_end(ctx, pr->n, idx_base, d_idx != nullptr);
   return FC_OK;
 }
 
@@ -469,18 +525,13 @@ extern "C" int fc_batch_host_planes(fc_ctx* ctx, const fc_scan_params* p, int64_
     pc.max_l = max_l;
     pc.plane_stride = n;
     fc_hit* d_hits = (fc_hit*)dp[8] + c0;
-    if ((rc = fc_scan(ctx, p, &pc, d_hits, cs))) return rc;
-    if (emit) {
-      if (d_idx)
-        rc = fc_agg_emit_idx(ctx, cn, d_hits, pc.d_chrom, pc.d_flags, (const uint8_t*)dp[9] + c0, (const int16_t*)dp[10] + c0,
-                             (const int16_t*)dp[11] + c0, (const uint64_t*)dp[12] + c0, (const uint64_t*)dp[13] + c0, nullptr,
-                             d_idx + c0, cs);
-      else
-        rc = fc_agg_emit(ctx, cn, d_hits, pc.d_chrom, pc.d_flags, (const uint8_t*)dp[9] + c0, (const int16_t*)dp[10] + c0,
-                         (const int16_t*)dp[11] + c0, (const uint64_t*)dp[12] + c0, (const uint64_t*)dp[13] + c0, nullptr,
-                         idx_base + (uint64_t)c0, cs);
-      if (rc) return rc;
-    }
+    if (emit)  // scan and record in one kernel
+      rc = fc_scan_emit(ctx, p, &pc, d_hits, (const uint8_t*)dp[9] + c0, (const int16_t*)dp[10] + c0, (const int16_t*)dp[11] + c0,
+                        (const uint64_t*)dp[12] + c0, (const uint64_t*)dp[13] + c0, idx_base + (uint64_t)c0,
+                        d_idx ? d_idx + c0 : nullptr, cs);
+    else
+      rc = fc_scan(ctx, p, &pc, d_hits, cs);
+    if (rc) return rc;
     if (h_out) FC_CUDA(ctx, cudaMemcpyAsync(h_out + c0, d_hits, sizeof(fc_hit) * cn, cudaMemcpyDeviceToHost, cs));
   }
   FC_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[1], ctx->own_stream2));

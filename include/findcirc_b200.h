@@ -172,6 +172,12 @@ int fc_pack_reads(fc_ctx* ctx, int64_t n, const uint8_t* d_ascii, int32_t stride
 int fc_scan(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs* pairs, fc_hit* d_out, void* stream);
 /* --all-hits (find_circ.py:1312-1317): d_tie_off[i] = exclusive prefix sum of n_hits over the pairs (n+1 entries);
  * writes every tie of every pair in rank order to d_ties[d_tie_off[i] ...] */
+/* fc_scan and fc_agg_emit in one kernel: every pair that found a breakpoint becomes a junction record (fc_jrec) of the
+ * context on the way, d_out still receives one fc_hit per pair.  Same records as fc_scan followed by fc_agg_emit(d_mask =
+ * NULL) (find_circ.py:854-974 then :1312-1317, 526-582); d_idx may be NULL (idx = idx_base + pair index). */
+int fc_scan_emit(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs* pairs, fc_hit* d_out, const uint8_t* d_wden,
+                 const int16_t* d_q_a, const int16_t* d_q_b, const uint64_t* d_read_hash, const uint64_t* d_qname_hash,
+                 uint64_t idx_base, const uint64_t* d_idx, void* stream);
 int fc_scan_ties(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs* pairs, const fc_hit* d_hits,
                  const int64_t* d_tie_off, fc_hit* d_ties, void* stream);
 /* host-buffer convenience (the reference-facing call): copies the batch in, scans, copies results out.

@@ -532,3 +532,41 @@ def test_declared_idx_range_that_is_too_small_still_gives_the_right_table(torch_
         nj = e.agg_finalize()
         assert _junction_rows(e.agg_fetch(nj)) == want, declared
     e.close()
+
+
+def test_scan_emit_equals_scan_then_emit(torch_cuda):
+    """fc_scan_emit (one kernel) == fc_scan + fc_agg_emit: same hits, same junction table"""
+    torch = torch_cuda
+    g, J, t = _case(100, 20, seed=41, n=7001, error_rate=0.01)
+    chrom, a_start, b_end, l, flags, internal = H.pairs_to_soa(t, 20, 2)
+    n = len(chrom)
+    e = _engine(asize=20)
+    e.load_genome_arrays(g.names, g.seqs)
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(9)
+    wden = rng.choice(np.array([1, 1, 2, 4, 8], dtype=np.uint8), size=n)
+    q_a = (t.as_a - np.maximum(t.xs_a, 0)).astype(np.int16)
+    q_b = (t.as_b - np.maximum(t.xs_b, 0)).astype(np.int16)
+    rh = e.hash_reads(t.reads, np.full(n, t.read_len, dtype=np.int32))
+    qh = np.array([e.hash_bytes(("q%d" % (i // 3)).encode()) for i in range(n)], dtype=np.uint64)
+    n_words = max(1, (int(l.max()) + 31) // 32)
+    tn = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    d_chrom, d_a, d_b, d_l, d_fl, d_asc = tn(chrom), tn(a_start), tn(b_end), tn(l), tn(flags), tn(internal)
+    planes = torch.zeros(3 * n_words * n, dtype=torch.int32, device=dev)
+    e.pack_reads(d_asc, internal.shape[1], d_l, n_words, planes, d_fl, 0)
+    pairs = e.make_pairs(n, d_chrom, d_a, d_b, d_l, d_fl, planes, n_words, int(l.max()))
+    pay = (tn(wden), tn(q_a), tn(q_b), tn(rh.view(np.int64)), tn(qh.view(np.int64)))
+    out1 = torch.zeros(n * 4, dtype=torch.int32, device=dev)
+    out2 = torch.zeros(n * 4, dtype=torch.int32, device=dev)
+    e.agg_reset()
+    e.scan(pairs, out1, 0)
+    e.agg_emit(n, out1, d_chrom, d_fl, *pay, 500, 0)
+    t1 = e.agg_fetch(e.agg_finalize())
+    n1 = e.agg_n_records()
+    e.agg_reset()
+    e.scan_emit(pairs, out2, *pay, 500, 0)
+    t2 = e.agg_fetch(e.agg_finalize())
+    assert e.agg_n_records() == n1 and n1 > 1000
+    assert torch.equal(out1, out2)
+    assert len(t1) > 50 and t1.tobytes() == t2.tobytes()
+    e.close()
