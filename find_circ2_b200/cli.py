@@ -93,6 +93,51 @@ def parse_args(argv):
     return opt, args, o
 
 
+class GzipMembers(object):
+    """spliced_reads.fastq.gz writer (find_circ.py:427, 1442-1447): text in, gzip out.  The text is cut into blocks that
+    worker threads compress on their own (zlib releases the GIL) and that are written one after the other as members of
+    ONE gzip file -- every gzip reader concatenates members.  Level 9 on a single thread, the reference's way, took two
+    thirds of the run time of the whole drop-in."""
+
+    BLOCK = 8 << 20
+
+    def __init__(self, path: str, level: int = 6, threads: int = 0):
+        self.fh = open(path, "wb")
+        self.level = level
+        self.threads = threads or max(1, min(8, (os.cpu_count() or 1)))
+        self.pending = []
+        self.size = 0
+
+    def write(self, text: str):
+        if text:
+            self.pending.append(text)
+            self.size += len(text)
+            if self.size >= 16 * self.BLOCK:
+                self._flush()
+
+    def _flush(self):
+        if not self.pending:
+            return
+        data = "".join(self.pending).encode("latin-1")
+        self.pending, self.size = [], 0
+        blocks = [data[i : i + self.BLOCK] for i in range(0, len(data), self.BLOCK)]
+        if len(blocks) == 1 or self.threads == 1:
+            parts = [gzip.compress(b, compresslevel=self.level) for b in blocks]
+        else:
+            from concurrent.futures import ThreadPoolExecutor
+
+            with ThreadPoolExecutor(self.threads) as pool:
+                parts = list(pool.map(lambda b: gzip.compress(b, compresslevel=self.level), blocks))
+        for part in parts:
+            self.fh.write(part)
+
+    def close(self):
+        self._flush()
+        if self.fh.tell() == 0:
+            self.fh.write(gzip.compress(b""))  # an empty but valid gzip file
+        self.fh.close()
+
+
 def native_ok(opt: Options, path) -> bool:
     """the native ingest covers SAM text (a file whose name ends in 'sam', or stdin: find_circ.py:461-469); BAM and
     --all-hits / --noop use the python reader"""
@@ -290,7 +335,7 @@ def main(argv=None) -> int:
     files = {
         "circs": open(os.path.join(opt.output, "circ_splice_sites.bed"), "w"),
         "lins": open(os.path.join(opt.output, "lin_splice_sites.bed"), "w"),
-        "reads": gzip.open(os.path.join(opt.output, "spliced_reads.fastq.gz"), "wt"),
+        "reads": GzipMembers(os.path.join(opt.output, "spliced_reads.fastq.gz")),
         "multi": open(os.path.join(opt.output, "multi_events.tsv"), "w"),
     }
     if opt.stdout and opt.stdout in files:
