@@ -59,3 +59,26 @@ def test_native_ingest_from_stdin(monkeypatch):
     assert O.canonical_bed(out["lin"]) == O.canonical_bed(rd("lin_splice_sites.bed"))
     assert out["reads"] == rd("spliced_reads.fastq")
     assert out["counters"] == rd("counters.txt")
+
+
+def test_gzip_members_writer(tmp_path):
+    """spliced_reads.fastq.gz is written as several gzip members compressed on worker threads: any gzip reader must see
+    the concatenated text; an empty run still leaves a valid file"""
+    import gzip
+
+    from find_circ2_b200.cli import GzipMembers
+
+    rec = "@r%d circ_000001 \nACGTACGTAC\n+r%d circ_000001 \nIIIIIIIIII\n"
+    text = "".join(rec % (k, k) for k in range(120000))
+    p = str(tmp_path / "reads.fastq.gz")
+    w = GzipMembers(p, threads=3)
+    w.BLOCK = 1 << 20  # several members
+    for i in range(0, len(text), 777777):
+        w.write(text[i:i + 777777])
+    w.close()
+    assert gzip.open(p, "rt").read() == text
+    raw = open(p, "rb").read()
+    assert raw.count(b"\x1f\x8b\x08") >= 4  # more than one member
+    q = str(tmp_path / "empty.fastq.gz")
+    GzipMembers(q).close()
+    assert gzip.open(q, "rt").read() == ""
