@@ -304,15 +304,17 @@ def run_gpu(args):
                 ev_scan[2].record()
                 ev_scan[3].record()
             return eng.agg_finalize(stream)
-        eng.scan(pairs, hits, stream)
-        if ev_scan:
-            ev_scan[1].record()
         if use_p2p:
-            eng.agg_emit_p2p(n, hits, d["chrom"], d["flags"], d["wden"], d["q_a"], d["q_b"], d["read_hash"], d["qname_hash"], idx_base, stream)
+            # scan + records straight into the owner ranks' buffers, one kernel (fc_scan_emit_p2p)
+            eng.scan_emit_p2p(pairs, hits, d["wden"], d["q_a"], d["q_b"], d["read_hash"], d["qname_hash"], idx_base, stream)
             if ev_scan:
+                ev_scan[1].record()
                 ev_scan[2].record()
             parallel.stream_barrier(dist, dev, eng, stream)  # every rank's records have landed
         else:
+            eng.scan(pairs, hits, stream)
+            if ev_scan:
+                ev_scan[1].record()
             eng.agg_emit(n, hits, d["chrom"], d["flags"], d["wden"], d["q_a"], d["q_b"], d["read_hash"], d["qname_hash"], idx_base, stream)
             if ev_scan:
                 ev_scan[2].record()
@@ -456,13 +458,16 @@ def run_gpu(args):
         peak, peak_src = peaks()
         # single GPU: the scan kernel also writes the junction records (48 B per accepted pair) and reads their payload
         # columns (22 B per pair: wden, q_a, q_b, read hash, name hash)
-        scan_bytes = BYTES_PER_PAIR * n + ((48.0 * n_rec + 22.0 * n) if world == 1 else 0.0)
+        fused_scan = world == 1 or use_p2p  # the scan kernel writes the records itself
+        n_emitted = n_rec if world == 1 else 0.9 * n  # (multi-GPU: n_rec counts what this rank RECEIVED; ~90 % of the pairs emit)
+        scan_bytes = BYTES_PER_PAIR * n + ((48.0 * n_emitted + 22.0 * n) if fused_scan else 0.0)
         achieved = scan_bytes / (scan_step * 1e-3) / 1e9
         merge_bytes = 48.0 * n_rec + 64.0 * int(nj)
         acc_achieved = merge_bytes / (max(acc_step_ms, 1e-9) * 1e-3) / 1e9
         roof_scan = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": 46.4e6,
-                     "kernel": ("scan_emit_kernel<NP=3,T=1> (csrc/scan.cu): scan + 48-byte record per accepted pair" if world == 1 else "scan_kernel<NP=3,T=1> (csrc/scan.cu)"),
-                     "bytes_per_pair": BYTES_PER_PAIR + (48.0 * n_rec / n if world == 1 else 0.0), "ms": scan_step,
+                     "kernel": ("scan_emit%s_kernel<NP=3,T=1> (csrc/scan.cu): scan + 48-byte record per accepted pair" % ("" if world == 1 else "_p2p")
+                                if fused_scan else "scan_kernel<NP=3,T=1> (csrc/scan.cu)"),
+                     "bytes_per_pair": scan_bytes / n, "ms": scan_step,
                      "peak_source": peak_src, "traffic_source": "ncu --set full, profiles/r01_kernels_ncu_summary.txt"}
         roof_acc = {"bound": "hbm", "achieved": acc_achieved, "peak": peak, "unit": "GB/s", "frac": acc_achieved / peak,
                     "traffic": 132.7e6, "kernel": "fused_accumulate_kernel (csrc/agg.cu)", "ms": acc_step_ms,

@@ -1419,107 +1419,26 @@ extern "C" const fc_junction* fc_agg_junctions(fc_ctx* ctx) {
 // synchronisation: two stream-ordered barriers (tiny NCCL all-reduces issued by the host) bracket the kernel.
 // Arrival order is arbitrary; the sort-free aggregation does not depend on it and the sort-based fallback re-orders by idx.
 // ======================================================================================================================
-struct P2PView {
-  fc_jrec* recs[8];
-  unsigned long long* cnt[8];
-  unsigned long long capacity;
-  int world;
-  int rank;
-};
-
+using fc::P2PView;
 constexpr int P2P_THREADS = 512;
 
 __global__ void __launch_bounds__(P2P_THREADS) emit_p2p_kernel(int64_t n, const fc_hit* __restrict__ hits,
                                                                const uint8_t* __restrict__ mask,
                                                                const int32_t* __restrict__ chrom, const uint8_t* __restrict__ flags,
-                                                               const uint8_t* __restrict__ wden, const int16_t* __restrict__ q_a,
-                                                               const int16_t* __restrict__ q_b, const uint64_t* __restrict__ read_hash,
-                                                               const uint64_t* __restrict__ qname_hash, uint64_t idx_base, P2PView pv,
-                                                               unsigned long long* __restrict__ overflow) {
-  // the CTA's records are first grouped by destination in shared memory, then every destination's group goes out as one
-  // run of consecutive 16-byte stores: full-size write packets on NVLink instead of scattered 16-byte ones
-  __shared__ uint4 s_rec[P2P_THREADS * 3];
-  __shared__ unsigned int s_cnt[8], s_off[9];
-  __shared__ unsigned long long s_base[8];
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool in = i < n;
-  fc_jrec r;
+                                                               fc::EmitArgs e, P2PView pv, unsigned long long* __restrict__ overflow) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  fc_hit h = {0, 0, 0u, 0u};
   bool accept = false;
-  int dest = 0;
-  if (in) {
-    const fc_hit h = hits[i];
-    accept = (h.w2 & 0xFFFFu) != 0 && (!mask || mask[i]);
+  uint32_t c = 0, fl = 0;
+  if (i < n) {
+    h = hits[i];
+    accept = (h.w2 & 0xFFFFu) != 0u && (!mask || mask[i]);
     if (accept) {
-      const uint32_t fl = flags[i];
-      const bool backsplice = fl & FC_PF_BACKSPLICE;
-      r.chrom = (uint32_t)chrom[i];
-      r.start = (uint32_t)h.start;
-      r.end = (uint32_t)h.end;
-      const uint32_t strand = h.w3 & 1u, sig = (h.w3 >> 1) & 0xFFFu;
-      const uint64_t rh = read_hash[i];
-      r.sk = strand | (backsplice ? 0u : 2u) | ((uint32_t)(rh & 1ull) << 2) | ((uint32_t)wden[i] << 8) | (sig << 16);
-      r.idx = idx_base + (uint64_t)i;
-      r.read_hash = rh;
-      r.qname_hash = qname_hash[i];
-      r.q_left = backsplice ? q_b[i] : q_a[i];
-      r.q_right = backsplice ? q_a[i] : q_b[i];
-      r.n_hits = (uint16_t)(h.w2 & 0xFFFFu);
-      r.dist = (uint8_t)((h.w2 >> 16) & 0xFFu);
-      r.ov = (uint8_t)(h.w2 >> 24);
-      dest = (int)(fc_key_hash(r.chrom, r.start, r.end, r.sk, 0x5bd1e995ULL) % (uint64_t)pv.world);
+      c = (uint32_t)chrom[i];
+      fl = flags[i];
     }
   }
-  if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
-  __syncthreads();
-  unsigned int local = 0;
-  {
-    // warp-aggregated shared-memory allocation: rank of this record among the CTA's records for its destination
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned amask = __ballot_sync(0xffffffffu, accept);
-    if (accept) {
-      const unsigned peers = __match_any_sync(amask, dest);
-      const int leader = __ffs((int)peers) - 1;
-      unsigned int wbase = 0;
-      if ((int)lane == leader) wbase = atomicAdd(&s_cnt[dest], (unsigned int)__popc(peers));
-      wbase = __shfl_sync(peers, wbase, leader);
-      local = wbase + (unsigned int)__popc(peers & ((1u << lane) - 1u));
-    }
-  }
-  __syncthreads();
-  // slot allocation: ONE system-scope atomic per CTA and destination (a shared counter per rank receives the
-  // allocations of every CTA of every rank; per-warp allocation made the owners' counters the bottleneck at 8 GPUs)
-  if ((int)threadIdx.x < pv.world && s_cnt[threadIdx.x])
-    s_base[threadIdx.x] = atomicAdd_system(pv.cnt[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
-  if (threadIdx.x == 0) {
-    unsigned int acc = 0;
-    for (int d = 0; d < 8; ++d) {
-      s_off[d] = acc;
-      acc += d < pv.world ? s_cnt[d] : 0u;
-    }
-    s_off[8] = acc;
-  }
-  __syncthreads();
-  if (accept) {
-    const uint4* src = reinterpret_cast<const uint4*>(&r);
-    uint4* dst = s_rec + (size_t)(s_off[dest] + local) * 3;
-    dst[0] = src[0];
-    dst[1] = src[1];
-    dst[2] = src[2];
-  }
-  __syncthreads();
-  const unsigned int words = s_off[8] * 3u;
-  for (unsigned int w = threadIdx.x; w < words; w += blockDim.x) {
-    const unsigned int rec = w / 3u, part = w - rec * 3u;
-    int d = 0;
-#pragma unroll
-    for (int k = 1; k < 8; ++k) d += (k < pv.world && rec >= s_off[k]) ? 1 : 0;
-    const unsigned long long pos = s_base[d] + (rec - s_off[d]);
-    if (pos < pv.capacity) {
-      reinterpret_cast<uint4*>(pv.recs[d] + pos)[part] = s_rec[w];
-    } else if (part == 0u) {
-      atomicAdd(overflow, 1ull);
-    }
-  }
+  fc::emit_p2p_block<P2P_THREADS>(accept, i, h.start, h.end, h.w2, h.w3, c, fl, e, pv, overflow);
 }
 
 extern "C" int fc_p2p_export(fc_ctx* ctx, int64_t capacity_records, uint8_t* h_handles /* 128 bytes */) {
@@ -1565,32 +1484,44 @@ extern "C" int fc_p2p_connect(fc_ctx* ctx, int32_t world, int32_t rank, const ui
   return FC_OK;
 }
 
-extern "C" int fc_agg_emit_p2p(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, const int32_t* d_chrom, const uint8_t* d_flags,
-                               const uint8_t* d_wden, const int16_t* d_q_a, const int16_t* d_q_b,
-                               const uint64_t* d_read_hash, const uint64_t* d_qname_hash, const uint8_t* d_mask,
-                               uint64_t idx_base, void* stream) {
-  if (!ctx || n < 0) return FC_E_ARG;
+// the peer view of the context and the bookkeeping of a peer emit, shared with the scan kernel that emits on the way
+int fc_agg_p2p_begin(fc_ctx* ctx, fc::P2PView* pv, unsigned long long** overflow) {
   fc_agg& a = ctx->agg;
-  if (!a.p2p_enabled) return fc_fail(ctx, FC_E_STATE, "fc_agg_emit_p2p before fc_p2p_connect");
-  if (n == 0) return FC_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-  P2PView pv;
+  if (!a.p2p_enabled) return fc_fail(ctx, FC_E_STATE, "peer emit before fc_p2p_connect");
   for (int r = 0; r < 8; ++r) {
-    pv.recs[r] = r < a.p2p_world ? (fc_jrec*)a.p2p_recs[r] : nullptr;
-    pv.cnt[r] = r < a.p2p_world ? (unsigned long long*)a.p2p_cnt[r] : nullptr;
+    pv->recs[r] = r < a.p2p_world ? (fc_jrec*)a.p2p_recs[r] : nullptr;
+    pv->cnt[r] = r < a.p2p_world ? (unsigned long long*)a.p2p_cnt[r] : nullptr;
   }
-  pv.capacity = (unsigned long long)a.p2p_min_capacity;
-  pv.world = a.p2p_world;
-  pv.rank = a.p2p_rank;
-  unsigned long long* counters = (unsigned long long*)a.counters.p;
-  emit_p2p_kernel<<<nblk(n, P2P_THREADS), P2P_THREADS, 0, st>>>(n, d_hits, d_mask, d_chrom, d_flags, d_wden, d_q_a, d_q_b, d_read_hash,
-                                                d_qname_hash, idx_base, pv, counters + 4);
-  FC_LAUNCH_CHECK(ctx);
+  pv->capacity = (unsigned long long)a.p2p_min_capacity;
+  pv->world = a.p2p_world;
+  pv->rank = a.p2p_rank;
+  *overflow = (unsigned long long*)a.counters.p + 4;
+  return FC_OK;
+}
+
+void fc_agg_p2p_end(fc_ctx* ctx) {
+  fc_agg& a = ctx->agg;
   a.n_recs = a.p2p_capacity;  // upper bound; the exact count is the (shared) device counter
   a.n_exact = false;
   a.unordered = true;
   if (!a.range_declared) a.max_idx = ~0ull;
   a.n_junc = -1;
+}
+
+extern "C" int fc_agg_emit_p2p(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, const int32_t* d_chrom, const uint8_t* d_flags,
+                               const uint8_t* d_wden, const int16_t* d_q_a, const int16_t* d_q_b,
+                               const uint64_t* d_read_hash, const uint64_t* d_qname_hash, const uint8_t* d_mask,
+                               uint64_t idx_base, void* stream) {
+  if (!ctx || n < 0) return FC_E_ARG;
+  P2PView pv;
+  unsigned long long* overflow = nullptr;
+  int rc = fc_agg_p2p_begin(ctx, &pv, &overflow);
+  if (rc) return rc;
+  if (n == 0) return FC_OK;
+  fc::EmitArgs e{d_wden, d_q_a, d_q_b, d_read_hash, d_qname_hash, idx_base, nullptr, nullptr, nullptr};
+  emit_p2p_kernel<<<nblk(n, P2P_THREADS), P2P_THREADS, 0, (cudaStream_t)stream>>>(n, d_hits, d_mask, d_chrom, d_flags, e, pv, overflow);
+  FC_LAUNCH_CHECK(ctx);
+  fc_agg_p2p_end(ctx);
   return FC_OK;
 }
 

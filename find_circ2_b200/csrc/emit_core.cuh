@@ -7,6 +7,21 @@
 
 #include "../../include/findcirc_b200.h"
 
+// 64-bit mix (splitmix64 finaliser)
+__host__ __device__ inline uint64_t fc_mix64(uint64_t x) {
+  x ^= x >> 30;
+  x *= 0xbf58476d1ce4e5b9ULL;
+  x ^= x >> 27;
+  x *= 0x94d049bb133111ebULL;
+  x ^= x >> 31;
+  return x;
+}
+__host__ __device__ inline uint64_t fc_key_hash(uint32_t chrom, uint32_t start, uint32_t end, uint32_t sk, uint64_t seed) {
+  uint64_t a = ((uint64_t)chrom << 32) | start;
+  uint64_t b = ((uint64_t)end << 32) | (sk & 3u);
+  return fc_mix64(fc_mix64(a + seed) ^ (b * 0x9E3779B97F4A7C15ULL + 0x632BE59BD9B4E019ULL));
+}
+
 namespace fc {
 
 struct EmitArgs {
@@ -20,6 +35,10 @@ struct EmitArgs {
   unsigned long long* n_recs;  // record counter of the context (device)
   fc_jrec* recs;               // record buffer of the context
 };
+
+struct P2PView;
+__device__ __forceinline__ fc_jrec make_record(int64_t i, int32_t h_start, int32_t h_end, uint32_t w2, uint32_t w3, uint32_t chrom,
+                                               uint32_t pair_flags, const EmitArgs& e);
 
 // Called by EVERY thread of a CTA of BS threads (BS a multiple of 32, at most 1024).  `accept` threads hand over their
 // pair (index i, hit words, chromosome id, pair flags).  The CTA claims its slots with one atomic on the record counter,
@@ -49,23 +68,7 @@ __device__ __forceinline__ void emit_block(bool accept, int64_t i, int32_t h_sta
   }
   __syncthreads();
   if (accept) {
-    const bool backsplice = pair_flags & FC_PF_BACKSPLICE;
-    fc_jrec r;
-    r.chrom = chrom;
-    r.start = (uint32_t)h_start;
-    r.end = (uint32_t)h_end;
-    const uint32_t strand = w3 & 1u, sig = (w3 >> 1) & 0xFFFu;
-    const uint64_t rh = e.read_hash[i];
-    r.sk = strand | (backsplice ? 0u : 2u) | ((uint32_t)(rh & 1ull) << 2) | ((uint32_t)e.wden[i] << 8) | (sig << 16);
-    r.idx = e.idx ? e.idx[i] : e.idx_base + (uint64_t)i;
-    r.read_hash = rh;
-    r.qname_hash = e.qname_hash[i];
-    // by convention A precedes B in the genome: swap for back-splices (find_circ.py:552-553)
-    r.q_left = backsplice ? e.q_b[i] : e.q_a[i];
-    r.q_right = backsplice ? e.q_a[i] : e.q_b[i];
-    r.n_hits = (uint16_t)(w2 & 0xFFFFu);
-    r.dist = (uint8_t)((w2 >> 16) & 0xFFu);
-    r.ov = (uint8_t)(w2 >> 24);
+    const fc_jrec r = make_record(i, h_start, h_end, w2, w3, chrom, pair_flags, e);
     uint4* stage = s_rec + (size_t)(s_warp[warp] + __popc(ballot & ((1u << lane) - 1u))) * 3;
     const uint4* src = reinterpret_cast<const uint4*>(&r);
     stage[0] = src[0];
@@ -75,6 +78,105 @@ __device__ __forceinline__ void emit_block(bool accept, int64_t i, int32_t h_sta
   __syncthreads();
   uint4* out = reinterpret_cast<uint4*>(e.recs + s_base);
   for (unsigned int w = threadIdx.x; w < s_total * 3u; w += BS) out[w] = s_rec[w];
+}
+
+// ---- the same towards the rank that owns the junction key (fused emit + exchange over peer memory) --------------------
+struct P2PView {
+  fc_jrec* recs[8];             // record buffer of every rank (peer memory, CUDA IPC)
+  unsigned long long* cnt[8];   // counters of every rank; word 0 = record count
+  unsigned long long capacity;  // records per buffer
+  int world;
+  int rank;
+};
+
+__device__ __forceinline__ fc_jrec make_record(int64_t i, int32_t h_start, int32_t h_end, uint32_t w2, uint32_t w3, uint32_t chrom,
+                                               uint32_t pair_flags, const EmitArgs& e) {
+  const bool backsplice = pair_flags & FC_PF_BACKSPLICE;
+  fc_jrec r;
+  r.chrom = chrom;
+  r.start = (uint32_t)h_start;
+  r.end = (uint32_t)h_end;
+  const uint32_t strand = w3 & 1u, sig = (w3 >> 1) & 0xFFFu;
+  const uint64_t rh = e.read_hash[i];
+  r.sk = strand | (backsplice ? 0u : 2u) | ((uint32_t)(rh & 1ull) << 2) | ((uint32_t)e.wden[i] << 8) | (sig << 16);
+  r.idx = e.idx ? e.idx[i] : e.idx_base + (uint64_t)i;
+  r.read_hash = rh;
+  r.qname_hash = e.qname_hash[i];
+  // by convention A precedes B in the genome: swap for back-splices (find_circ.py:552-553)
+  r.q_left = backsplice ? e.q_b[i] : e.q_a[i];
+  r.q_right = backsplice ? e.q_a[i] : e.q_b[i];
+  r.n_hits = (uint16_t)(w2 & 0xFFFFu);
+  r.dist = (uint8_t)((w2 >> 16) & 0xFFu);
+  r.ov = (uint8_t)(w2 >> 24);
+  return r;
+}
+
+// Called by every thread of a CTA of BS threads.  The CTA's records are grouped by destination rank in shared memory;
+// ONE system-scope atomic per CTA and destination claims the slots in the owner's buffer (per-warp allocation made the
+// owners' counters the bottleneck at 8 GPUs); every group then goes out as one run of consecutive 16-byte stores --
+// full-size write packets on NVLink instead of scattered 16-byte ones.
+template <int BS>
+__device__ __forceinline__ void emit_p2p_block(bool accept, int64_t i, int32_t h_start, int32_t h_end, uint32_t w2, uint32_t w3,
+                                               uint32_t chrom, uint32_t pair_flags, const EmitArgs& e, const P2PView& pv,
+                                               unsigned long long* overflow) {
+  __shared__ uint4 s_rec[BS * 3];
+  __shared__ unsigned int s_cnt[8], s_off[9];
+  __shared__ unsigned long long s_base[8];
+  fc_jrec r;
+  int dest = 0;
+  if (accept) {
+    r = make_record(i, h_start, h_end, w2, w3, chrom, pair_flags, e);
+    dest = (int)(fc_key_hash(r.chrom, r.start, r.end, r.sk, 0x5bd1e995ULL) % (uint64_t)pv.world);
+  }
+  if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  unsigned int local = 0;
+  {
+    // warp-aggregated shared-memory allocation: rank of this record among the CTA's records for its destination
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned amask = __ballot_sync(0xffffffffu, accept);
+    if (accept) {
+      const unsigned peers = __match_any_sync(amask, dest);
+      const int leader = __ffs((int)peers) - 1;
+      unsigned int wbase = 0;
+      if ((int)lane == leader) wbase = atomicAdd(&s_cnt[dest], (unsigned int)__popc(peers));
+      wbase = __shfl_sync(peers, wbase, leader);
+      local = wbase + (unsigned int)__popc(peers & ((1u << lane) - 1u));
+    }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < pv.world && s_cnt[threadIdx.x])
+    s_base[threadIdx.x] = atomicAdd_system(pv.cnt[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+  if (threadIdx.x == 0) {
+    unsigned int acc = 0;
+    for (int d = 0; d < 8; ++d) {
+      s_off[d] = acc;
+      acc += d < pv.world ? s_cnt[d] : 0u;
+    }
+    s_off[8] = acc;
+  }
+  __syncthreads();
+  if (accept) {
+    const uint4* src = reinterpret_cast<const uint4*>(&r);
+    uint4* dst = s_rec + (size_t)(s_off[dest] + local) * 3;
+    dst[0] = src[0];
+    dst[1] = src[1];
+    dst[2] = src[2];
+  }
+  __syncthreads();
+  const unsigned int words = s_off[8] * 3u;
+  for (unsigned int w = threadIdx.x; w < words; w += BS) {
+    const unsigned int rec = w / 3u, part = w - rec * 3u;
+    int d = 0;
+#pragma unroll
+    for (int k = 1; k < 8; ++k) d += (k < pv.world && rec >= s_off[k]) ? 1 : 0;
+    const unsigned long long pos = s_base[d] + (rec - s_off[d]);
+    if (pos < pv.capacity) {
+      reinterpret_cast<uint4*>(pv.recs[d] + pos)[part] = s_rec[w];
+    } else if (part == 0u) {
+      atomicAdd(overflow, 1ull);
+    }
+  }
 }
 
 }  // namespace fc

@@ -108,6 +108,8 @@ int fc_genome_ensure_tiles(fc_ctx* ctx, int w, cudaStream_t st);
 int fc_agg_reserve_records(fc_ctx* ctx, int64_t extra, cudaStream_t st);  // room for `extra` more records, now
 int fc_agg_emit_begin(fc_ctx* ctx, int64_t n, cudaStream_t st, fc::EmitArgs* e);  // room + where the records go
 void fc_agg_emit_end(fc_ctx* ctx, int64_t n, uint64_t idx_base, bool explicit_idx);
+int fc_agg_p2p_begin(fc_ctx* ctx, fc::P2PView* pv, unsigned long long** overflow);  // the peer view of the context
+void fc_agg_p2p_end(fc_ctx* ctx);
 
 #define FC_CUDA(ctx, call)                                                                         \
   do {                                                                                             \
@@ -123,18 +125,3 @@ void fc_agg_emit_end(fc_ctx* ctx, int64_t n, uint64_t idx_base, bool explicit_id
     if (e__ != cudaSuccess)                                                                        \
       return fc_fail((ctx), FC_E_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
-
-// 64-bit mix (splitmix64 finaliser)
-__host__ __device__ inline uint64_t fc_mix64(uint64_t x) {
-  x ^= x >> 30;
-  x *= 0xbf58476d1ce4e5b9ULL;
-  x ^= x >> 27;
-  x *= 0x94d049bb133111ebULL;
-  x ^= x >> 31;
-  return x;
-}
-__host__ __device__ inline uint64_t fc_key_hash(uint32_t chrom, uint32_t start, uint32_t end, uint32_t sk, uint64_t seed) {
-  uint64_t a = ((uint64_t)chrom << 32) | start;
-  uint64_t b = ((uint64_t)end << 32) | (sk & 3u);
-  return fc_mix64(fc_mix64(a + seed) ^ (b * 0x9E3779B97F4A7C15ULL + 0x632BE59BD9B4E019ULL));
-}

@@ -93,6 +93,35 @@ __global__ void __launch_bounds__(BS, MB) scan_emit_kernel(fc::GenomeView g, fc:
   fc::emit_block<BS>((h.w2 & 0xFFFFu) != 0u, i, h.start, h.end, h.w2, h.w3, c, fl, e);
 }
 
+// ... and towards the ranks that own the junction keys (multi-GPU, fc_scan_emit_p2p)
+template <int NP, int T, int BS, int MB>
+__global__ void __launch_bounds__(BS, MB) scan_emit_p2p_kernel(fc::GenomeView g, fc::ScanCfg cfg, fc::ReadView rv,
+                                                            const int32_t* __restrict__ chrom,
+                                                            const int32_t* __restrict__ a_start,
+                                                            const int32_t* __restrict__ b_end, const int32_t* __restrict__ l,
+                                                            const uint8_t* __restrict__ flags, fc_hit* __restrict__ out,
+                                                            fc::EmitArgs e, fc::P2PView pv, unsigned long long* overflow) {
+  const int64_t i = (int64_t)blockIdx.x * BS + threadIdx.x;
+  fc::HitOut h;
+  h.start = h.end = 0;
+  h.w2 = h.w3 = 0u;
+  uint32_t c = 0, fl = 0;
+  if (i < rv.n) {
+    fc::PairArgs p;
+    p.chrom = chrom[i];
+    p.a_start = a_start[i];
+    p.b_end = b_end[i];
+    p.l = l[i];
+    p.flags = flags[i];
+    c = (uint32_t)p.chrom;
+    fl = p.flags;
+    fc::NoEmit ne;
+    fc::scan_pair<NP, T>(g, cfg, p, rv, i, h, ne, false);
+    reinterpret_cast<uint4*>(out)[i] = make_uint4((uint32_t)h.start, (uint32_t)h.end, h.w2, h.w3);
+  }
+  fc::emit_p2p_block<BS>((h.w2 & 0xFFFFu) != 0u, i, h.start, h.end, h.w2, h.w3, c, fl, e, pv, overflow);
+}
+
 // ---------------------------------------------------------------- --all-hits: every tie of every pair
 struct TieEmit {
   int best;
@@ -175,7 +204,7 @@ extern "C" int fc_pack_reads(fc_ctx* ctx, int64_t n, const uint8_t* d_ascii, int
 }
 
 static int scan_launch(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs* pr, fc_hit* d_out, const fc::EmitArgs* emit,
-                       cudaStream_t st) {
+                       cudaStream_t st, const fc::P2PView* pv = nullptr, unsigned long long* overflow = nullptr) {
   const int need = pr->max_l + 2;
   if (!p->noncanonical) {
     int rc = fc_genome_ensure_tiles(ctx, need, st);  // no-op when the tile store already covers this window size
@@ -187,7 +216,10 @@ static int scan_launch(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs* pr,
 #define FC_SCAN_LAUNCH_BS(NP, T, BS, MB)                                                                                \
   {                                                                                                                     \
     const unsigned grid = (unsigned)((pr->n + BS - 1) / BS);                                                            \
-    if (emit)                                                                                                           \
+    if (emit && pv)                                                                                                     \
+      scan_emit_p2p_kernel<NP, T, BS, MB><<<grid, BS, 0, st>>>(g, cfg, rv, pr->d_chrom, pr->d_a_start, pr->d_b_end,      \
+                                                               pr->d_l, pr->d_flags, d_out, *emit, *pv, overflow);      \
+    else if (emit)                                                                                                      \
       scan_emit_kernel<NP, T, BS, MB><<<grid, BS, 0, st>>>(g, cfg, rv, pr->d_chrom, pr->d_a_start, pr->d_b_end, pr->d_l, \
                                                            pr->d_flags, d_out, *emit);                                  \
     else                                                                                                                \
@@ -236,6 +268,22 @@ extern "C" int fc_scan_emit(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs
   if ((rc = fc_agg_emit_begin(ctx, pr->n, st, &e))) return rc;
   if ((rc = scan_launch(ctx, p, pr, d_out, &e, st))) return rc;
   fc_agg_emit_end(ctx, pr->n, idx_base, d_idx != nullptr);
+  return FC_OK;
+}
+
+extern "C" int fc_scan_emit_p2p(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs* pr, fc_hit* d_out, const uint8_t* d_wden,
+                                const int16_t* d_q_a, const int16_t* d_q_b, const uint64_t* d_read_hash,
+                                const uint64_t* d_qname_hash, uint64_t idx_base, void* stream) {
+  int rc = check_pairs(ctx, p, pr);
+  if (rc) return rc;
+  if (!d_out || !d_wden || !d_q_a || !d_q_b || !d_read_hash || !d_qname_hash) return FC_E_ARG;
+  fc::P2PView pv;
+  unsigned long long* overflow = nullptr;
+  if ((rc = fc_agg_p2p_begin(ctx, &pv, &overflow))) return rc;
+  if (pr->n == 0) return FC_OK;
+  fc::EmitArgs e{d_wden, d_q_a, d_q_b, d_read_hash, d_qname_hash, idx_base, nullptr, nullptr, nullptr};
+  if ((rc = scan_launch(ctx, p, pr, d_out, &e, (cudaStream_t)stream, &pv, overflow))) return rc;
+  fc_agg_p2p_end(ctx);
   return FC_OK;
 }
 

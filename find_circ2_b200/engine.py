@@ -199,6 +199,11 @@ class Engine:
         self._check(self.lib.fc_scan_emit(self.h, C.byref(self.params), C.byref(pairs), ptr(d_out), ptr(d_wden), ptr(d_q_a),
                                           ptr(d_q_b), ptr(d_read_hash), ptr(d_qname_hash), idx_base, ptr(d_idx), stream))
 
+    def scan_emit_p2p(self, pairs: Pairs, d_out, d_wden, d_q_a, d_q_b, d_read_hash, d_qname_hash, idx_base, stream=0):
+        """scan + record into the owner ranks' buffers over peer memory, in one kernel (fc_scan_emit_p2p)"""
+        self._check(self.lib.fc_scan_emit_p2p(self.h, C.byref(self.params), C.byref(pairs), ptr(d_out), ptr(d_wden), ptr(d_q_a),
+                                              ptr(d_q_b), ptr(d_read_hash), ptr(d_qname_hash), idx_base, stream))
+
     def scan_ties(self, pairs: Pairs, d_hits, d_tie_off, d_ties, stream=0):
         self._check(self.lib.fc_scan_ties(self.h, C.byref(self.params), C.byref(pairs), ptr(d_hits), ptr(d_tie_off),
                                           ptr(d_ties), stream))

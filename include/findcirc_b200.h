@@ -256,6 +256,10 @@ int fc_p2p_connect(fc_ctx* ctx, int32_t world, int32_t rank, const uint8_t* h_al
 int fc_agg_emit_p2p(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, const int32_t* d_chrom, const uint8_t* d_flags,
                     const uint8_t* d_wden, const int16_t* d_q_a, const int16_t* d_q_b, const uint64_t* d_read_hash,
                     const uint64_t* d_qname_hash, const uint8_t* d_mask, uint64_t idx_base, void* stream);
+/* fc_scan and fc_agg_emit_p2p in one kernel (cf. fc_scan_emit). */
+int fc_scan_emit_p2p(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs* pairs, fc_hit* d_out, const uint8_t* d_wden,
+                     const int16_t* d_q_a, const int16_t* d_q_b, const uint64_t* d_read_hash, const uint64_t* d_qname_hash,
+                     uint64_t idx_base, void* stream);
 /* Stream-ordered barrier of all connected ranks over peer memory (one small kernel: every rank bumps an arrival word on
  * every rank and waits for its own).  Orders the record stores of fc_agg_emit_p2p before the owners' fc_agg_finalize and
  * the owners' counter resets before the next emit.  Every rank must call it the same number of times.  A rank that waits

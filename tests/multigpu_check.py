@@ -80,7 +80,12 @@ def main():
                 e.agg_set_idx_range(0, world * n_cap)
             # the library's peer-memory barrier, and (last round) the NCCL one-element all-reduce
             parallel.stream_barrier(dist, dev, e if it < 2 else None, 0)
-            e.agg_emit_p2p(n, hits, d_chrom, d_fl, *pay, idx_base, 0)
+            if it == 1:  # scan and peer emit in one kernel
+                hits2 = torch.zeros_like(hits)
+                e.scan_emit_p2p(pairs, hits2, *pay, idx_base, 0)
+                assert torch.equal(hits, hits2)
+            else:
+                e.agg_emit_p2p(n, hits, d_chrom, d_fl, *pay, idx_base, 0)
             parallel.stream_barrier(dist, dev, e if it < 2 else None, 0)
             ta = table()
 
