@@ -13,8 +13,9 @@
 //     n_frags              distinct qname hashes                                   (:584-586)
 //     n_uniq               distinct strand-invariant read hashes (palindromes count half, :588-590)
 // Two implementations with identical results: a sort-free one (one pass: 128-bit CAS hash tables, per-junction
-// accumulators updated with integer atomics, default) and a sort-based one (stable CUB radix sort + warp-segmented reduction + sequential float replay, fallback).
-// Multi-GPU: the emit kernel can write records straight into the owner rank's buffer over NVLink (emit_p2p_kernel).
+// accumulators updated with integer atomics, default) and a sort-based one (stable CUB radix sort + warp-segmented
+// reduction + sequential float replay, fallback).  Records are produced by emit_core.cuh -- by a stand-alone kernel here
+// or inside the scan kernel (scan.cu); multi-GPU: straight into the owner rank's buffer over NVLink.
 #include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
@@ -25,7 +26,7 @@
 
 namespace {
 
-struct JAcc {  // per-junction accumulators filled with integer atomics (deterministic)
+struct JAcc {  // per-junction accumulators of the sort-based path, filled with integer atomics (deterministic)
   unsigned int n_spanned;
   unsigned int cw[4];  // records with weight denominator 1,2,4,8
   unsigned int cw_other;
@@ -58,10 +59,6 @@ __device__ __forceinline__ U128 cas128(U128* addr, U128 cmp, U128 val) {
       : "memory");
   return old;
 }
-
-static_assert(offsetof(JAcc, cw) == 4 && offsetof(JAcc, cb) == 24 && offsetof(JAcc, cb_other) == 40 && offsetof(JAcc, n_frags) == 64 &&
-                  offsetof(JAcc, n_uniq) == 68 && offsetof(JAcc, first_idx) == 80,
-              "accumulate_kernel's 64-bit pair adds depend on this layout");
 
 // One record per accepted pair (the scan found a breakpoint and the caller's mask, if any, keeps the pair); see
 // emit_core.cuh for how a CTA writes its records.
