@@ -713,8 +713,10 @@ class Run(object):
         if self.explicit_idx:
             self.reads_out.sort(key=lambda e: e[0])  # native + python paths interleave: restore stream order (stable)
         for _, qname, seq, qual, keys, flags in self.reads_out:
-            head = "%s %s %s" % (qname, ",".join(sorted(names[k] for k in keys)), ",".join(flags))
-            out.append("@%s\n%s\n+%s\n%s\n" % (head, seq, head, qual))
+            # (most reads support one junction and carry no flag: keep that case cheap)
+            nm = names[keys[0]] if len(keys) == 1 else ",".join(sorted(names[k] for k in keys))
+            head = qname + " " + nm + " " + (",".join(flags) if flags else "")
+            out.append("@" + head + "\n" + seq + "\n+" + head + "\n" + str(qual) + "\n")
         return "".join(out)
 
     def multi_text(self) -> str:
