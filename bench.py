@@ -464,13 +464,13 @@ def run_gpu(args):
         achieved = scan_bytes / (scan_step * 1e-3) / 1e9
         merge_bytes = 48.0 * n_rec + 64.0 * int(nj)
         acc_achieved = merge_bytes / (max(acc_step_ms, 1e-9) * 1e-3) / 1e9
-        roof_scan = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": 46.4e6,
+        roof_scan = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": (87.6e6 if fused_scan else 46.4e6),
                      "kernel": ("scan_emit%s_kernel<NP=3,T=1> (csrc/scan.cu): scan + 48-byte record per accepted pair" % ("" if world == 1 else "_p2p")
                                 if fused_scan else "scan_kernel<NP=3,T=1> (csrc/scan.cu)"),
                      "bytes_per_pair": scan_bytes / n, "ms": scan_step,
                      "peak_source": peak_src, "traffic_source": "ncu --set full, profiles/r01_kernels_ncu_summary.txt"}
         roof_acc = {"bound": "hbm", "achieved": acc_achieved, "peak": peak, "unit": "GB/s", "frac": acc_achieved / peak,
-                    "traffic": 132.7e6, "kernel": "fused_accumulate_kernel (csrc/agg.cu)", "ms": acc_step_ms,
+                    "traffic": 130.7e6, "kernel": "fused_accumulate_kernel (csrc/agg.cu)", "ms": acc_step_ms,
                     "bytes": "48 B x %d records + 64 B x %d junctions (rank 0)" % (n_rec, int(nj)), "peak_source": peak_src,
                     "traffic_source": "ncu --set full, profiles/r01_kernels_ncu_summary.txt",
                     "note": "random 16/32-byte accesses to hash tables: bound by L1/LSU wavefronts and L2 atomics, not by bytes"}

@@ -534,13 +534,15 @@ def test_declared_idx_range_that_is_too_small_still_gives_the_right_table(torch_
     e.close()
 
 
-def test_scan_emit_equals_scan_then_emit(torch_cuda):
-    """fc_scan_emit (one kernel) == fc_scan + fc_agg_emit: same hits, same junction table"""
+@pytest.mark.parametrize("read_len,noncanonical", [(100, False), (76, False), (150, False), (250, False), (100, True)])
+def test_scan_emit_equals_scan_then_emit(torch_cuda, read_len, noncanonical):
+    """fc_scan_emit (one kernel) == fc_scan + fc_agg_emit: same hits, same junction table -- for every specialisation of
+    the scan kernel (tile classes T=1/2/4, the per-base path of --non-canonical)"""
     torch = torch_cuda
-    g, J, t = _case(100, 20, seed=41, n=7001, error_rate=0.01)
+    g, J, t = _case(read_len, 20, seed=41 + read_len, n=7001, error_rate=0.01)
     chrom, a_start, b_end, l, flags, internal = H.pairs_to_soa(t, 20, 2)
     n = len(chrom)
-    e = _engine(asize=20)
+    e = _engine(asize=20, noncanonical=noncanonical)
     e.load_genome_arrays(g.names, g.seqs)
     dev = torch.device("cuda:0")
     rng = np.random.default_rng(9)
