@@ -120,6 +120,25 @@ def _full_case(engine_kw, genome_sizes, n_pairs, n_circ, seed, sample=1500):
         assert int(junc["n_frags"][j]) == len(np.unique(qhh[m]))
         pal = np.unique(rhh[m][(rhh[m] & np.uint64(1)) == 1])
         assert int(junc["n_uniq"][j]) == len(np.unique(rhh[m])) - (len(pal) + 1) // 2
+    # the same batch through the chunked host-buffer call that takes bit-plane reads (two-stream chunks, scan kernel that
+    # emits on the way): same hits, same junction table
+    import torch
+
+    dev = torch.device("cuda:0")
+    max_l = int(l.max())
+    n_words = max(1, (max_l + 31) // 32)
+    d_planes = torch.zeros(3 * n_words * n, dtype=torch.int32, device=dev)
+    d_fl = torch.from_numpy(flags.copy()).to(dev)
+    e.pack_reads(torch.from_numpy(np.ascontiguousarray(internal)).to(dev), internal.shape[1], torch.from_numpy(l).to(dev), n_words,
+                 d_planes, d_fl, 0)
+    torch.cuda.synchronize()
+    planes = d_planes.cpu().numpy().view(np.uint32).reshape(3, n_words * n)
+    e.agg_reset()
+    hits2 = e.batch_host_planes(n, chrom, a_start, b_end, l, d_fl.cpu().numpy(), planes[0], planes[1], planes[2], n_words, n, max_l,
+                                np.ones(n, np.uint8), qa, qb, rh, qh, idx=None, idx_base=0, emit=True)
+    assert np.array_equal(hits.view(np.uint32), hits2.view(np.uint32))
+    junc2 = e.agg_fetch(e.agg_finalize())
+    assert junc2.tobytes() == junc.tobytes()
     st = e.genome_stats()
     e.close()
     return st
