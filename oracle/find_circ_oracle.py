@@ -52,6 +52,8 @@ class Options:
     multi_events: bool = True
     known_circ: str = ""
     known_lin: str = ""
+    noop: bool = False   # only group the alignments (find_circ.py:1554-1558)
+    stdout: str = ""     # circs | lins | reads | multi: that output goes to stdout (find_circ.py:453-458)
 
 
 def py2_str(x) -> str:
@@ -738,6 +740,8 @@ class Run:
         opt, N = self.opt, self.N
         for mate1, mate2 in fragments(records, N):
             self.n_fragments += 1
+            if opt.noop:
+                continue
             frag = mate2.primary.qname
             circ_spans, lin_spans, unspliced, broken = [], [], [], []
             for mate in (mate1, mate2):
@@ -852,6 +856,14 @@ def options_from_argv(argv: Sequence[str]) -> Options:
             o.nolinear = True
         elif a == "--no-multi":
             o.multi_events = False
+        elif a == "--noop":
+            o.noop = True
+        elif a == "--stdout":
+            o.stdout = next(it)
+        elif a in ("-t", "--throughput"):
+            pass  # progress on stderr only
+        elif a == "--chunk-size":
+            next(it)
         elif a == "--known-circ":
             o.known_circ = next(it)
         elif a == "--known-lin":

@@ -129,3 +129,22 @@ def harness_scan(g, chrom, a_start, b_end, l, flags, internal, margin, maxdist, 
         return out
     finally:
         lib.hh_genome_free(h)
+
+
+def compare_outputs(circ, lin, reads, multi, counters, ref_dir, argv):
+    """the five outputs of a run against a reference run stored under tests/golden/<case>/ref_*; an output that the run
+    redirects with --stdout is compared with the captured stdout and its file holds one comment line (find_circ.py:453-458)"""
+    rd = lambda n: open(os.path.join(ref_dir, n)).read()  # noqa: E731
+    redirected = argv[argv.index("--stdout") + 1] if "--stdout" in argv else ""
+    files = {"circs": "circ_splice_sites.bed", "lins": "lin_splice_sites.bed", "reads": "spliced_reads.fastq", "multi": "multi_events.tsv"}
+    got = {"circs": circ, "lins": lin, "reads": reads, "multi": multi}
+    canon = {"circs": O.canonical_bed, "lins": O.canonical_bed, "reads": lambda t: t, "multi": O.canonical_multi}
+    for name, fn in files.items():
+        if name == redirected:
+            want = rd("stdout.txt")
+            if name != "reads":  # (the reads file is a gzip stream the reference leaves truncated in this case)
+                assert rd(fn) == "# redirected to stdout\n"
+        else:
+            want = rd(fn)
+        assert canon[name](got[name]) == canon[name](want), name
+    assert counters == rd("counters.txt")

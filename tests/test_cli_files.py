@@ -121,3 +121,32 @@ def test_find_circ_process_errors(tmp_path):
     other = os.path.join(GOLDEN, "cdr1as", "genome.fa")
     r = subprocess.run(exe + ["-G", other, "-o", str(tmp_path / "y"), "-q", os.path.join(case, "input.sam")], capture_output=True, text=True)
     assert r.returncode == 1 and "KeyError" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["noop", "stdout_circs", "stdout_reads"])
+def test_find_circ_process_rare_switches(tmp_path, tag):
+    """--noop (alignments are only grouped, find_circ.py:1554-1558), --stdout NAME (that output goes to stdout, its file
+    keeps one comment line, find_circ.py:453-458), -t / --chunk-size (progress on stderr) -- against reference runs"""
+    case = os.path.join(GOLDEN, "synth_b")
+    ref = os.path.join(case, "ref_" + tag)
+    argv = open(os.path.join(ref, "cmdline.txt")).read().split("\n")[0].split()
+    out = str(tmp_path / "run")
+    cmd = [sys.executable, os.path.join(ROOT, "find_circ.py"), "-G", os.path.join(case, "genome.fa"), "-o", out, "-q"] + argv
+    r = subprocess.run(cmd + [os.path.join(case, "input.sam")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    rd = lambda d, n: open(os.path.join(d, n)).read()  # noqa: E731
+    got = {"circs": rd(out, "circ_splice_sites.bed"), "lins": rd(out, "lin_splice_sites.bed"),
+           "reads": gzip.open(os.path.join(out, "spliced_reads.fastq.gz"), "rt").read(), "multi": rd(out, "multi_events.tsv")}
+    if "--stdout" in argv:
+        name = argv[argv.index("--stdout") + 1]
+        assert got[name] == "# redirected to stdout\n"  # (for `reads` a complete gzip stream; the reference leaves it truncated)
+        got[name] = r.stdout
+    else:
+        assert r.stdout == ""
+    log = rd(out, "run.log").split("\n")
+    k = [i for i, l in enumerate(log) if l.endswith("run finished")][0]
+    counters = "".join(l.split("\t")[-1] + "\n" for l in log[k + 1:] if "=" in l)
+    import helpers as H
+
+    H.compare_outputs(got["circs"], got["lins"], got["reads"], got["multi"], counters, ref, argv)

@@ -8,6 +8,7 @@ import os
 import pytest
 
 from conftest import golden_cases, golden_ids
+import helpers as H
 from oracle import find_circ_oracle as O
 
 
@@ -15,12 +16,7 @@ from oracle import find_circ_oracle as O
 def test_oracle_matches_reference(case_dir, ref_dir, argv):
     opt = O.options_from_argv(argv)
     out = O.run(os.path.join(case_dir, "genome.fa"), os.path.join(case_dir, "input.sam"), opt)
-    rd = lambda n: open(os.path.join(ref_dir, n)).read()  # noqa: E731
-    assert O.canonical_bed(out.circ_bed) == O.canonical_bed(rd("circ_splice_sites.bed"))
-    assert O.canonical_bed(out.lin_bed) == O.canonical_bed(rd("lin_splice_sites.bed"))
-    assert out.reads_fastq == rd("spliced_reads.fastq")
-    assert O.canonical_multi(out.multi_events) == O.canonical_multi(rd("multi_events.tsv"))
-    assert out.counters == rd("counters.txt")
+    H.compare_outputs(out.circ_bed, out.lin_bed, out.reads_fastq, out.multi_events, out.counters, ref_dir, argv)
 
 
 def test_kat1_scan_level():
