@@ -65,7 +65,8 @@ def build_parser() -> optparse.OptionParser:
     a("-t", "--throughput", dest="throughput", default=False, action="store_true", help="accepted for compatibility")
     a("", "--chunk-size", "--chunksize", dest="chunksize", type=int, default=100000, help="accepted for compatibility")
     a("", "--noop", dest="noop", default=False, action="store_true", help="decode the alignments only, no junction search")
-    a("", "--test", dest="test", default=False, action="store_true", help="not supported")
+    a("", "--test", dest="test", default=False, action="store_true",
+      help="write test_results.tsv: every fragment against the structure encoded in its read name (simulated reads)")
     a("", "--no-linear", dest="nolinear", default=False, action="store_true", help="ignore linear junctions of fragments without a back-splice")
     a("", "--no-multi", dest="multi_events", default=True, action="store_false", help="do not write multi_events.tsv rows")
     a("", "--batch-pairs", dest="batch_pairs", type=int, default=1 << 18, help="anchor pairs per GPU batch (default 262144)")
@@ -77,7 +78,7 @@ def build_parser() -> optparse.OptionParser:
 
 def parse_args(argv):
     o, args = build_parser().parse_args(list(argv))
-    for bad in ("stranded", "bam", "test"):
+    for bad in ("stranded", "bam"):
         if getattr(o, bad):
             raise SystemExit("option --%s is not supported by this build" % bad)
     if o.system:
@@ -88,7 +89,7 @@ def parse_args(argv):
         allhits=o.allhits, strandpref=o.strandpref, halfunique=o.halfunique, report_nobridges=o.report_nobridges,
         nolinear=o.nolinear, multi_events=o.multi_events, throughput=o.throughput, chunksize=o.chunksize, noop=o.noop,
         silent=o.silent, stdout=o.stdout, batch_pairs=o.batch_pairs, device=o.device, native=o.native,
-        known_circ=o.known_circ, known_lin=o.known_lin,
+        known_circ=o.known_circ, known_lin=o.known_lin, test=o.test,
     )
     return opt, args, o
 
@@ -142,7 +143,7 @@ def native_ok(opt: Options, path) -> bool:
     """the native ingest covers SAM text (a file whose name ends in 'sam', or stdin: find_circ.py:461-469); BAM and
     --all-hits / --noop use the python reader"""
     text = (not path) or path == "-" or path.endswith("sam")
-    return text and not opt.allhits and not opt.noop and opt.native
+    return text and not opt.allhits and not opt.noop and not opt.test and opt.native
 
 
 class _Prefixed(object):
@@ -206,6 +207,7 @@ def run_to_strings(opt: Options, path=None, engine=None, native=None):
             "lin": run.bed_text(1),
             "reads": run.reads_text(),
             "multi": run.multi_text(),
+            "test": run.test_text(),
             "counters": run.counters_text(),
             "n_fragments": run.n_fragments,
             "n_pairs_scanned": run.n_pairs_scanned,
@@ -373,6 +375,9 @@ def main(argv=None) -> int:
     files["lins"].write(out["lin"])
     files["reads"].write(out["reads"])
     files["multi"].write(out["multi"])
+    if opt.test:
+        with open(os.path.join(opt.output, "test_results.tsv"), "w") as fh:
+            fh.write(out["test"])
     for f in files.values():
         if f is not sys.stdout:
             f.close()

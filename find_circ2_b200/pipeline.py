@@ -59,6 +59,7 @@ class Options:
     batch_pairs: int = 1 << 18  # anchor pairs per GPU batch (ours)
     device: int = 0
     native: bool = True  # native (C++) SAM ingest for SAM text files
+    test: bool = False    # test_results.tsv: every fragment against the truth in its name (find_circ.py:411, 1148-1273)
     known_circ: str = ""  # BED6 files of known junctions (find_circ.py:387-388)
     known_lin: str = ""
 
@@ -170,6 +171,51 @@ def mate_spans(mate: Mate, asize: int, N) -> List[Span]:
     return out
 
 
+def truth_from_name(text: str):
+    """the fragment structure that a simulated read carries behind '___' in its name (find_circ.py:1147-1191): mates are
+    separated by '|', steps by ';'.  O:chrom:start:strand sets the origin, M:n walks n bases, LS:a:b / CS:a:b are a linear /
+    circular splice with both ends relative to the origin.  Origin and position carry over from mate to mate, as upstream."""
+    chrom = strand = None
+    start = end = None
+    lin, circ, unspliced = set(), set(), set()
+    for mate in text.split("|"):
+        spliced = False
+        for step in mate.split(";"):
+            f = step.split(":")
+            if f[0] == "O":
+                chrom, start, strand = f[1], int(f[2]), f[3]
+                end = start
+            elif f[0] == "M":
+                end += int(f[1])
+            elif f[0] in ("LS", "CS"):
+                left, right = int(f[1]) + start, int(f[2]) + start
+                (lin if f[0] == "LS" else circ).add((chrom, left, right, strand))
+                spliced, end = True, (right if f[0] == "LS" else left)
+        if not spliced and chrom:
+            unspliced.add((chrom, start, end, "*"))
+    return lin, circ, unspliced
+
+
+def test_result_row(frag: str, lin_coords, circ_coords, unspliced_coords, broken_coords) -> str:
+    """one line of test_results.tsv (find_circ.py:1194-1273)"""
+    if "___" not in frag:
+        return "\t".join([frag, "N/A", "N/A", "N/A", "N/A"])
+    lin_ref, circ_ref, un_ref = truth_from_name(frag.split("___")[-1])
+
+    def verdict(ref, got, what, ok):
+        flags = []
+        if ref - got:
+            flags.append("MISSED_%s:%s" % (what, ",".join(str(c) for c in sorted(ref - got))))
+        if got - ref:
+            flags.append("SPURIOUS_%s:%s" % (what, ",".join(str(c) for c in sorted(got - ref))))
+        return ";".join(sorted(flags)) if flags else (ok if ref else "N/A")
+
+    broken = "BROKEN_SEGMENTS:" + ";".join(str(b) for b in sorted(broken_coords)) if broken_coords else "N/A"
+    return "\t".join([frag, verdict(lin_ref, set(lin_coords), "LINEAR_JUNCTIONS", "LIN_OK"),
+                      verdict(circ_ref, set(circ_coords), "CIRCULAR_JUNCTIONS", "CIRC_OK"),
+                      verdict(un_ref, set(unspliced_coords), "UNSPLICED", "UNSPLICED_OK"), broken])
+
+
 class JunctionInfo(object):
     """host-side companions of a junction that never reach the GPU: per-fragment flags (find_circ.py:513-524, 632-652)"""
 
@@ -212,6 +258,7 @@ class Run(object):
         self.cur_seq = 0
         self.cur_k = 0
         self.multi_out: List[tuple] = []
+        self.test_out: List[tuple] = []    # (fragment ordinal, row of test_results.tsv)
         self.t_scan = 0.0
         self.known: Dict[tuple, str] = {}
         for kind, path in ((0, opt.known_circ), (1, opt.known_lin)):
@@ -443,6 +490,7 @@ class Run(object):
                 warns.add("SUPPORT_CLOSURE")
 
         lin_cons, lin_incons = set(), set()
+        lin_coords = set()
         for sp in fr.lin:
             if sp.row < 0:
                 N["lin_junc_not_unique"] += 1
@@ -460,6 +508,7 @@ class Run(object):
                 if opt.allhits:
                     host_recs.append((key, sp.row, sub, dist, ov, nh, sig))
                 note(key)
+                lin_coords.add((cname, start, end, strand))
                 if circ_coords:
                     coord = (cname, start, end, strand)
                     if start <= circ_start or end >= circ_end:
@@ -470,6 +519,12 @@ class Run(object):
                         warns.add("SUPPORT_INSIDE_SPLICE_JUNCTION")
                 if not opt.allhits:
                     break
+
+        if opt.test:  # find_circ.py:1380-1394
+            cn = self.eng.chrom_names
+            star = lambda rec: (self.sam_chroms[rec.tid], rec.pos, rec.aend, "*")  # noqa: E731
+            self.test_out.append((fr.seq, test_result_row(fr.name, lin_coords, {(cn[g], s0, e0, st) for g, s0, e0, st, _ in circ_coords},
+                                                          {star(r) for r in fr.unspliced}, {star(r) for r in fr.broken})))
 
         if circ_coords:
             un_cons, un_incons = set(), set()
@@ -517,8 +572,8 @@ class Run(object):
         from .samio import _parse_sam_line
 
         opt, N = self.opt, self.N
-        if opt.allhits or opt.noop:
-            raise ValueError("process_native does not cover --all-hits / --noop")
+        if opt.allhits or opt.noop or opt.test:
+            raise ValueError("process_native does not cover --all-hits / --noop / --test")
         tid2gid = [self.eng._chrom_ids.get(n, -1) for n in self.sam_chroms]
         name2tid = {n: i for i, n in enumerate(self.sam_chroms)}
         ing = NativeIngest(opt.asize, opt.margin, opt.min_uniq_qual, opt.nolinear, self.sam_chroms, tid2gid,
@@ -734,6 +789,10 @@ class Run(object):
             cols.append(",".join("[%s:%d-%d]" % (c, s, e) for c, s, e, _ in sorted(un_incons)) if un_incons else "NO_UNSPLICED_INCONS")
             lines.append("\t".join(cols) + "\n")
         return "".join(lines)
+
+    def test_text(self) -> str:
+        """test_results.tsv (--test), rows in stream order"""
+        return "".join(row + "\n" for _, row in sorted(self.test_out, key=lambda e: e[0]))
 
     def counters_text(self) -> str:
         """the N dump of find_circ.py:1605-1607"""

@@ -19,7 +19,7 @@ Each function cites the reference lines it follows.  Deliberately mirrored quirk
   * the first SAM record is never checked for being unmapped (find_circ.py:1462-1463);
   * counters anchor_not_uniq / no_uniq_bridges are incremented after the dump and never appear (:1605-1610).
 Not supported (the reference itself crashes or needs absent libraries): --stranded (find_circ.py:533 vs
-:766-776), -S/--system, -B/--bam, --test.
+:766-776), -S/--system, -B/--bam.
 """
 from __future__ import annotations
 
@@ -52,6 +52,7 @@ class Options:
     multi_events: bool = True
     known_circ: str = ""
     known_lin: str = ""
+    test: bool = False   # compare every fragment with the truth encoded in its name (find_circ.py:411, 1148-1273)
     noop: bool = False   # only group the alignments (find_circ.py:1554-1558)
     stdout: str = ""     # circs | lins | reads | multi: that output goes to stdout (find_circ.py:453-458)
 
@@ -619,6 +620,60 @@ def multi_event_row(frag: str, circ: Junction, lin_cons, lin_incons, un_cons, un
 # ----------------------------------------------------------------------------------------------
 # the run (find_circ.py:1276-1439, 1490-1610)
 # ----------------------------------------------------------------------------------------------
+def truth_from_name(text: str):
+    """the fragment structure a simulated read carries behind '___' in its name (find_circ.py:1147-1191):
+    mates are separated by '|', steps by ';'.  O:chrom:start:strand sets the origin, M:n walks n bases, LS:a:b / CS:a:b are
+    a linear / circular splice with both ends relative to the origin.  Returns (linear, circular, unspliced) coordinate sets;
+    origin and position carry over from one mate to the next, as they do in the reference."""
+    chrom = strand = None
+    start = end = None
+    lin, circ, unspliced = set(), set(), set()
+    for mate in text.split("|"):
+        spliced = False
+        for step in mate.split(";"):
+            f = step.split(":")
+            if f[0] == "O":
+                chrom, start, strand = f[1], int(f[2]), f[3]
+                end = start
+            elif f[0] == "M":
+                end += int(f[1])
+            elif f[0] == "LS":
+                left, right = int(f[1]) + start, int(f[2]) + start
+                lin.add((chrom, left, right, strand))
+                spliced, end = True, right
+            elif f[0] == "CS":
+                left, right = int(f[1]) + start, int(f[2]) + start
+                circ.add((chrom, left, right, strand))
+                spliced, end = True, left
+        if not spliced and chrom:
+            unspliced.add((chrom, start, end, "*"))  # (strand only with --stranded, which the reference cannot run)
+    return lin, circ, unspliced
+
+
+def test_row(frag: str, lin_coords, circ_coords, unspliced_coords, broken_coords) -> str:
+    """one line of test_results.tsv (find_circ.py:1194-1273)"""
+    if "___" not in frag:
+        return "\t".join([frag, "N/A", "N/A", "N/A", "N/A"])
+    lin_ref, circ_ref, un_ref = truth_from_name(frag.split("___")[-1])
+    listing = lambda coords: ",".join(str(c) for c in sorted(coords))  # noqa: E731
+
+    def verdict(ref, got, what, ok):
+        flags = set()
+        if ref - got:
+            flags.add("MISSED_%s:%s" % (what, listing(ref - got)))
+        if got - ref:
+            flags.add("SPURIOUS_%s:%s" % (what, listing(got - ref)))
+        if flags:
+            return ";".join(sorted(flags))
+        return ok if ref else "N/A"
+
+    cols = [frag, verdict(lin_ref, set(lin_coords), "LINEAR_JUNCTIONS", "LIN_OK"),
+            verdict(circ_ref, set(circ_coords), "CIRCULAR_JUNCTIONS", "CIRC_OK"),
+            verdict(un_ref, set(unspliced_coords), "UNSPLICED", "UNSPLICED_OK"),
+            "BROKEN_SEGMENTS:" + ";".join(str(b) for b in sorted(broken_coords)) if broken_coords else "N/A"]
+    return "\t".join(cols)
+
+
 @dataclasses.dataclass
 class Outputs:
     circ_bed: str
@@ -626,6 +681,7 @@ class Outputs:
     reads_fastq: str
     multi_events: str
     counters: str  # 'key=value' lines as dumped to run.log
+    test_results: str = ""  # --test
     n_fragments: int = 0
     n_spans: int = 0
 
@@ -640,6 +696,7 @@ class Run:
         self.lin = JunctionTable("lin", opt, opt.known_lin)
         self.reads: List[str] = []
         self.multi: List[str] = []
+        self.test_rows: List[str] = []
         self.n_fragments = 0
         self.n_spans = 0
 
@@ -690,6 +747,7 @@ class Run:
                 warns.add("SUPPORT_CLOSURE")
 
         lin_cons, lin_incons = set(), set()
+        lin_coords = set()
         for span in lin_spans:
             if span.uniq < opt.min_uniq_qual:
                 N["lin_junc_not_unique"] += 1
@@ -704,6 +762,7 @@ class Run:
             for sp in splices:
                 lin = self.lin.add(sp)
                 note(lin)
+                lin_coords.add(lin.coord)
                 if circ_coords:
                     if sp.start <= circ_start or sp.end >= circ_end:
                         warns.add("WARN_OUTSIDE_SPLICE_JUNCTION")
@@ -713,6 +772,10 @@ class Run:
                         warns.add("SUPPORT_INSIDE_SPLICE_JUNCTION")
                 if not opt.allhits:
                     break
+
+        if opt.test:  # find_circ.py:1380-1394
+            star = lambda rec: (self.chrom_names[rec.tid], rec.pos, rec.aend, "*")  # noqa: E731
+            self.test_rows.append(test_row(frag, lin_coords, circ_coords, {star(r) for r in unspliced}, {star(r) for r in broken}))
 
         if circ_coords:
             un_cons, un_incons = set(), set()
@@ -776,6 +839,7 @@ class Run:
             reads_fastq="".join(self.reads),
             multi_events="#" + "\t".join(MULTI_HEADER) + "\n" + "".join(r + "\n" for r in self.multi),
             counters=counters,
+            test_results="".join(r + "\n" for r in self.test_rows),
             n_fragments=self.n_fragments,
             n_spans=self.n_spans,
         )
@@ -856,6 +920,8 @@ def options_from_argv(argv: Sequence[str]) -> Options:
             o.nolinear = True
         elif a == "--no-multi":
             o.multi_events = False
+        elif a == "--test":
+            o.test = True
         elif a == "--noop":
             o.noop = True
         elif a == "--stdout":

@@ -312,6 +312,8 @@ def run_reference(case_dir, tag, args):
             return
         for fn in ("circ_splice_sites.bed", "lin_splice_sites.bed", "multi_events.tsv"):
             shutil.copy(os.path.join(run_dir, fn), os.path.join(out, fn))
+        if os.path.exists(os.path.join(run_dir, "test_results.tsv")):  # --test
+            shutil.copy(os.path.join(run_dir, "test_results.tsv"), os.path.join(out, "test_results.tsv"))
         if r.stdout:  # --stdout redirects one of the outputs (find_circ.py:453-458)
             with open(os.path.join(out, "stdout.txt"), "w") as fh:
                 fh.write(r.stdout)
@@ -379,6 +381,11 @@ def main():
         run_reference(d, "noop", ["-n", "test", "--noop"])
         run_reference(d, "stdout_circs", ["-n", "test", "--stdout", "circs"])
         run_reference(d, "stdout_reads", ["-n", "test", "--stdout", "reads", "-t", "--chunk-size", "100"])
+        return
+    if sys.argv[1:] == ["selftest"]:  # --test: the reference's own validation against the truth in the read names
+        run_reference(os.path.join(HERE, "kat3"), "selftest", ["-n", "test", "--test"])
+        run_reference(os.path.join(HERE, "kat3"), "selftest_a20", ["-n", "test", "-a", "20", "--test"])
+        run_reference(os.path.join(HERE, "synth_a"), "selftest", ["-n", "test", "--test"])
         return
     if sys.argv[1:] == ["known"]:  # only the runs with known junctions (added after the first set)
         d = os.path.join(HERE, "synth_a")

@@ -131,7 +131,7 @@ def harness_scan(g, chrom, a_start, b_end, l, flags, internal, margin, maxdist, 
         lib.hh_genome_free(h)
 
 
-def compare_outputs(circ, lin, reads, multi, counters, ref_dir, argv):
+def compare_outputs(circ, lin, reads, multi, counters, ref_dir, argv, test_results=None):
     """the five outputs of a run against a reference run stored under tests/golden/<case>/ref_*; an output that the run
     redirects with --stdout is compared with the captured stdout and its file holds one comment line (find_circ.py:453-458)"""
     rd = lambda n: open(os.path.join(ref_dir, n)).read()  # noqa: E731
@@ -148,3 +148,5 @@ def compare_outputs(circ, lin, reads, multi, counters, ref_dir, argv):
             want = rd(fn)
         assert canon[name](got[name]) == canon[name](want), name
     assert counters == rd("counters.txt")
+    if "--test" in argv:  # test_results.tsv: one row per fragment that reached record_hits, in stream order
+        assert test_results == rd("test_results.tsv")

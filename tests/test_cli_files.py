@@ -124,8 +124,9 @@ def test_find_circ_process_errors(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("tag", ["noop", "stdout_circs", "stdout_reads"])
-def test_find_circ_process_rare_switches(tmp_path, tag):
+@pytest.mark.parametrize("case_name,tag", [("synth_b", "noop"), ("synth_b", "stdout_circs"), ("synth_b", "stdout_reads"),
+                                           ("kat3", "selftest"), ("synth_a", "selftest")])
+def test_find_circ_process_rare_switches(tmp_path, case_name, tag):
     """--noop (alignments are only grouped, find_circ.py:1554-1558), --stdout NAME (that output goes to stdout, its file
     keeps one comment line, find_circ.py:453-458), -t / --chunk-size (progress on stderr) -- against reference runs"""
     case = os.path.join(GOLDEN, "synth_b")
@@ -149,4 +150,5 @@ def test_find_circ_process_rare_switches(tmp_path, tag):
     counters = "".join(l.split("\t")[-1] + "\n" for l in log[k + 1:] if "=" in l)
     import helpers as H
 
-    H.compare_outputs(got["circs"], got["lins"], got["reads"], got["multi"], counters, ref, argv)
+    tests = rd(out, "test_results.tsv") if "--test" in argv else None
+    H.compare_outputs(got["circs"], got["lins"], got["reads"], got["multi"], counters, ref, argv, tests)

@@ -16,7 +16,7 @@ from oracle import find_circ_oracle as O
 def test_oracle_matches_reference(case_dir, ref_dir, argv):
     opt = O.options_from_argv(argv)
     out = O.run(os.path.join(case_dir, "genome.fa"), os.path.join(case_dir, "input.sam"), opt)
-    H.compare_outputs(out.circ_bed, out.lin_bed, out.reads_fastq, out.multi_events, out.counters, ref_dir, argv)
+    H.compare_outputs(out.circ_bed, out.lin_bed, out.reads_fastq, out.multi_events, out.counters, ref_dir, argv, out.test_results)
 
 
 def test_kat1_scan_level():

@@ -22,10 +22,10 @@ def test_host_logic_matches_reference(case_dir, ref_dir, argv, native):
     opt.batch_pairs = 211
     eng = FakeEngine(0, opt.asize, opt.margin, opt.maxdist, opt.noncanonical, opt.strandpref)
     eng.load_genome_fasta(opt.genome)
-    if native and (opt.allhits or opt.noop):
-        pytest.skip("--all-hits and --noop use the python ingest")
+    if native and (opt.allhits or opt.noop or opt.test):
+        pytest.skip("--all-hits, --noop and --test use the python ingest")
     out = cli.run_to_strings(opt, os.path.join(case_dir, "input.sam"), engine=eng, native=native)
-    H.compare_outputs(out["circ"], out["lin"], out["reads"], out["multi"], out["counters"], ref_dir, argv)
+    H.compare_outputs(out["circ"], out["lin"], out["reads"], out["multi"], out["counters"], ref_dir, argv, out["test"])
 
 
 def test_native_ingest_from_stdin(monkeypatch):
