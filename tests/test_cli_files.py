@@ -128,8 +128,9 @@ def test_find_circ_process_errors(tmp_path):
                                            ("kat3", "selftest"), ("synth_a", "selftest")])
 def test_find_circ_process_rare_switches(tmp_path, case_name, tag):
     """--noop (alignments are only grouped, find_circ.py:1554-1558), --stdout NAME (that output goes to stdout, its file
-    keeps one comment line, find_circ.py:453-458), -t / --chunk-size (progress on stderr) -- against reference runs"""
-    case = os.path.join(GOLDEN, "synth_b")
+    keeps one comment line, find_circ.py:453-458), -t / --chunk-size (progress on stderr), --test (test_results.tsv,
+    find_circ.py:1148-1273, 1380-1394) -- against reference runs"""
+    case = os.path.join(GOLDEN, case_name)
     ref = os.path.join(case, "ref_" + tag)
     argv = open(os.path.join(ref, "cmdline.txt")).read().split("\n")[0].split()
     out = str(tmp_path / "run")
