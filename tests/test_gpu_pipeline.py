@@ -8,7 +8,7 @@ import os
 import pytest
 
 from conftest import golden_cases, golden_ids
-from oracle import find_circ_oracle as O
+import helpers as H
 
 pytestmark = pytest.mark.gpu
 
@@ -20,12 +20,7 @@ def test_pipeline_matches_reference(case_dir, ref_dir, argv, batch, native):
 
     opt = cli.parse_args(["-G", os.path.join(case_dir, "genome.fa")] + argv + [os.path.join(case_dir, "input.sam")])[0]
     opt.batch_pairs = batch
-    if native and opt.allhits:
-        native = False  # --all-hits always uses the python ingest
+    if native and (opt.allhits or opt.noop or opt.test):
+        native = False  # --all-hits, --noop and --test always use the python ingest
     out = cli.run_to_strings(opt, os.path.join(case_dir, "input.sam"), native=native)
-    rd = lambda n: open(os.path.join(ref_dir, n)).read()  # noqa: E731
-    assert O.canonical_bed(out["circ"]) == O.canonical_bed(rd("circ_splice_sites.bed"))
-    assert O.canonical_bed(out["lin"]) == O.canonical_bed(rd("lin_splice_sites.bed"))
-    assert out["reads"] == rd("spliced_reads.fastq")
-    assert O.canonical_multi(out["multi"]) == O.canonical_multi(rd("multi_events.tsv"))
-    assert out["counters"] == rd("counters.txt")
+    H.compare_outputs(out["circ"], out["lin"], out["reads"], out["multi"], out["counters"], ref_dir, argv, out["test"])
