@@ -113,6 +113,8 @@ SYMBOLS = [
     ("fc_scan_emit_p2p", C.c_int, [_P, C.POINTER(ScanParams), C.POINTER(Pairs), _P, _P, _P, _P, _P, _P, C.c_uint64, _P]),
     ("fc_p2p_barrier", C.c_int, [_P, _P]),
     ("fc_agg_reset_async", C.c_int, [_P, _P]),
+    ("fc_text_gather", C.c_int64, [_P, C.c_int64, _P, _P, _P]),
+    ("fc_fastq_format", C.c_int64, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, C.c_int64, _P]),
     ("fc_pinned_alloc", _P, [C.c_int64]),
     ("fc_pinned_free", None, [_P]),
     ("fc_device_sync", C.c_int, [_P]),

@@ -391,3 +391,77 @@ extern "C" int64_t fc_ingest_parse(fc_ingest* h, const char* text, int64_t nbyte
   }
   return consumed;
 }
+
+// ---------------------------------------------------------------- spliced reads: keep the text, format it at the end
+// The reads file (find_circ.py:1442-1447) names the junction(s) a read supports, and junction names are only final after
+// the aggregation.  For the rows of the native ingest (one junction, no flags) the host keeps name, sequence and
+// qualities of every spliced read in one compact blob per batch (fc_text_gather) and formats the FASTQ records in one
+// pass when the names are known (fc_fastq_format).
+
+// copies n x 3 substrings of `buf` back to back into `out` (off/len are n x 3, row major; len < 0 = field absent);
+// returns the number of bytes written
+extern "C" int64_t fc_text_gather(const char* buf, int64_t n, const int64_t* off, const int32_t* len, char* out) {
+  if (!buf || !off || !len || !out || n < 0) return FC_E_ARG;
+  int64_t w = 0;
+  for (int64_t k = 0; k < 3 * n; ++k) {
+    if (len[k] > 0) {
+      memcpy(out + w, buf + off[k], (size_t)len[k]);
+      w += len[k];
+    }
+  }
+  return w;
+}
+
+// FASTQ records of n reads whose (name, sequence, qualities) lie back to back in `blob` (lengths in len, n x 3; qualities
+// absent = the text "None", as python prints a missing pysam field): "@<name> <junction> \n<seq>\n+<name> <junction> \n<qual>\n".
+// junction = names[name_off[name_idx[i]] ...].  rec_off[0..n] receives the offset of every record in `out`.
+// Returns the bytes written, or the bytes needed (> out_cap) when `out` is too small.
+extern "C" int64_t fc_fastq_format(const char* blob, int64_t n, const int32_t* len, const int32_t* name_idx, const char* names,
+                                   const int64_t* name_off, const int32_t* name_len, char* out, int64_t out_cap,
+                                   int64_t* rec_off) {
+  if (!blob || !len || !name_idx || !names || !name_off || !name_len || !rec_off || n < 0) return FC_E_ARG;
+  int64_t need = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const int64_t q = len[3 * i] > 0 ? len[3 * i] : 0, s = len[3 * i + 1] > 0 ? len[3 * i + 1] : 0;
+    const int64_t u = len[3 * i + 2] >= 0 ? len[3 * i + 2] : 4;
+    need += 2 * (q + name_len[name_idx[i]] + 3) + 2 + s + 1 + u + 1;
+  }
+  if (need > out_cap || !out) return need;
+  int64_t r = 0, w = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    rec_off[i] = w;
+    const int32_t q = len[3 * i] > 0 ? len[3 * i] : 0, s = len[3 * i + 1] > 0 ? len[3 * i + 1] : 0, u = len[3 * i + 2];
+    const char* qp = blob + r;
+    const char* sp = qp + q;
+    const char* up = sp + s;
+    const char* jn = names + name_off[name_idx[i]];
+    const int32_t jl = name_len[name_idx[i]];
+    for (int pass = 0; pass < 2; ++pass) {
+      out[w++] = pass ? '+' : '@';
+      memcpy(out + w, qp, (size_t)q);
+      w += q;
+      out[w++] = ' ';
+      memcpy(out + w, jn, (size_t)jl);
+      w += jl;
+      out[w++] = ' ';
+      out[w++] = '\n';
+      if (pass == 0) {
+        memcpy(out + w, sp, (size_t)s);
+        w += s;
+        out[w++] = '\n';
+      }
+    }
+    if (u >= 0) {
+      memcpy(out + w, up, (size_t)u);
+      w += u;
+      r += u;
+    } else {
+      memcpy(out + w, "None", 4);
+      w += 4;
+    }
+    out[w++] = '\n';
+    r += q + s;
+  }
+  rec_off[n] = w;
+  return w;
+}

@@ -13,6 +13,7 @@ order python3 would give -- comparisons are made after a canonical sort (BASELIN
 """
 from __future__ import annotations
 
+import ctypes as C
 import dataclasses
 import gzip
 import logging
@@ -258,6 +259,7 @@ class Run(object):
         self.cur_seq = 0
         self.cur_k = 0
         self.multi_out: List[tuple] = []
+        self.native_reads: List[dict] = []  # spliced reads of the native ingest, one compact batch record each
         self.test_out: List[tuple] = []    # (fragment ordinal, row of test_results.tsv)
         self.t_scan = 0.0
         self.known: Dict[tuple, str] = {}
@@ -638,20 +640,23 @@ class Run(object):
         rows = np.nonzero(nh)[0]
         if len(rows) == 0:
             return
-        chrom = a["chrom"][rows].tolist()
-        start = hits["start"][rows].tolist()
-        end = hits["end"][rows].tolist()
-        strand = np.where(hits["w3"][rows] & 1, "-", "+").tolist()
-        kind = (1 - (a["flags"][rows] & 1)).tolist()
-        seqs = a["frag_seq"][rows].tolist()
-        qo, ql = (a["qname_off"][rows] + off).tolist(), a["qname_len"][rows].tolist()
-        so, sl = (a["seq_off"][rows] + off).tolist(), a["seq_len"][rows].tolist()
-        uo, ul = (a["qual_off"][rows] + off).tolist(), a["qual_len"][rows].tolist()
-        out = self.reads_out
-        for k in range(len(rows)):
-            qual = None if ul[k] < 0 else buf[uo[k]:uo[k] + ul[k]].decode("latin-1")
-            out.append((seqs[k], buf[qo[k]:qo[k] + ql[k]].decode("latin-1"), buf[so[k]:so[k] + sl[k]].decode("latin-1"), qual,
-                        ((chrom[k], start[k], end[k], strand[k], kind[k]),), ()))
+        # name, sequence and qualities of the spliced reads go into one compact blob (C++); the FASTQ records are formatted
+        # from it when the junction names are known (reads_text)
+        m = len(rows)
+        off3 = np.empty((m, 3), dtype=np.int64)
+        len3 = np.empty((m, 3), dtype=np.int32)
+        for k, f in enumerate(("qname", "seq", "qual")):
+            off3[:, k] = a[f + "_off"][rows] + off
+            len3[:, k] = a[f + "_len"][rows]
+        blob = np.empty(int(np.maximum(len3, 0).sum()), dtype=np.uint8)
+        base = C.cast(C.c_char_p(buf), C.c_void_p).value
+        got = ing.lib.fc_text_gather(base, m, off3.ctypes.data, len3.ctypes.data, blob.ctypes.data)
+        if got != len(blob):
+            raise RuntimeError("fc_text_gather failed (%d)" % got)
+        self.native_reads.append(dict(
+            seqs=a["frag_seq"][rows].copy(), blob=blob, len3=len3, chrom=a["chrom"][rows].astype(np.int64),
+            start=hits["start"][rows].astype(np.int64), end=hits["end"][rows].astype(np.int64),
+            minus=(hits["w3"][rows] & 1).astype(np.int64), kind=(1 - (a["flags"][rows] & 1)).astype(np.int64)))
 
     # ------------------------------------------------------------------ outputs
     def finalize(self, dist=None, torch_dev=None):
@@ -772,7 +777,45 @@ class Run(object):
             nm = names[keys[0]] if len(keys) == 1 else ",".join(sorted(names[k] for k in keys))
             head = qname + " " + nm + " " + (",".join(flags) if flags else "")
             out.append("@" + head + "\n" + seq + "\n+" + head + "\n" + str(qual) + "\n")
-        return "".join(out)
+        if not self.native_reads:
+            return "".join(out)
+        # the reads of the native ingest: formatted per batch in C++, then merged with the others by stream position
+        from . import _lib
+
+        lib = _lib.load()
+        py_seqs = np.array([e[0] for e in self.reads_out], dtype=np.int64)
+        pieces, done = [], 0
+        for b in self.native_reads:
+            key = np.stack([b["chrom"], b["start"], b["end"], b["minus"], b["kind"]], axis=1)
+            uniq, inverse = np.unique(key, axis=0, return_inverse=True)
+            jn = [names[(int(c), int(s0), int(e0), "-" if mi else "+", int(kd))].encode("latin-1") for c, s0, e0, mi, kd in uniq.tolist()]
+            name_len = np.array([len(x) for x in jn], dtype=np.int32)
+            name_off = np.zeros(len(jn), dtype=np.int64)
+            name_off[1:] = np.cumsum(name_len[:-1])
+            names_blob = b"".join(jn)
+            name_idx = np.ascontiguousarray(inverse.reshape(-1), dtype=np.int32)
+            m = len(name_idx)
+            rec_off = np.zeros(m + 1, dtype=np.int64)
+            args = (b["blob"].ctypes.data, m, b["len3"].ctypes.data, name_idx.ctypes.data, names_blob, name_off.ctypes.data,
+                    name_len.ctypes.data)
+            need = lib.fc_fastq_format(*args, None, 0, rec_off.ctypes.data)
+            text = np.empty(max(int(need), 1), dtype=np.uint8)
+            got = lib.fc_fastq_format(*args, text.ctypes.data, int(need), rec_off.ctypes.data)
+            if got != need:
+                raise RuntimeError("fc_fastq_format failed (%d)" % got)
+            raw = text[:got].tobytes().decode("latin-1")
+            # python-path reads whose stream position falls inside this batch split it
+            lo = 0
+            hi_py = int(np.searchsorted(py_seqs, b["seqs"][-1], side="right")) if m else done
+            for j in range(done, hi_py):
+                cut = int(np.searchsorted(b["seqs"], py_seqs[j], side="left"))
+                pieces.append(raw[int(rec_off[lo]):int(rec_off[cut])])
+                pieces.append(out[j])
+                lo = cut
+            pieces.append(raw[int(rec_off[lo]):])
+            done = max(done, hi_py)
+        pieces.extend(out[done:])
+        return "".join(pieces)
 
     def multi_text(self) -> str:
         """MultiEventRecorder (find_circ.py:733-763)"""

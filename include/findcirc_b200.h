@@ -312,6 +312,15 @@ void fc_ingest_destroy(fc_ingest* h);
  * with the next chunk; final != 0 flushes the last fragment) or a negative error code */
 int64_t fc_ingest_parse(fc_ingest* h, const char* text, int64_t nbytes, int32_t final, fc_ingest_out* out);
 
+/* Spliced reads of the native ingest (write_read, find_circ.py:1442-1447): fc_text_gather copies n x 3 substrings
+ * (name, sequence, qualities; off/len row major, len < 0 = absent) of a text buffer back to back into `out` and returns
+ * the bytes written; fc_fastq_format turns such a blob into FASTQ records "@<name> <junction> \n<seq>\n+<name> <junction>
+ * \n<qual>\n" once the junction names are known (name_idx[i] selects names[name_off[.] .. +name_len[.]]), fills rec_off[0..n]
+ * with the offset of every record and returns the bytes written, or the bytes needed when out_cap is too small. */
+int64_t fc_text_gather(const char* buf, int64_t n, const int64_t* off, const int32_t* len, char* out);
+int64_t fc_fastq_format(const char* blob, int64_t n, const int32_t* len, const int32_t* name_idx, const char* names,
+                        const int64_t* name_off, const int32_t* name_len, char* out, int64_t out_cap, int64_t* rec_off);
+
 /* ------------------------------------------------------------------ utilities */
 void* fc_pinned_alloc(int64_t bytes);
 void fc_pinned_free(void* p);
