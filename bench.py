@@ -7,7 +7,9 @@ bench.py -- anchor pairs / second through the breakpoint scan + junction merge (
 
 A step is one pass of the hot path over one batch: config 2 of BASELINE.json -- synthetic 100 Mb genome
 (20 x 5 Mb, 0.5 % N), 10 000 planted circRNAs, 1 M anchor pairs from 100-nt reads (a=20, m=2, d=2), seeds fixed.
-  value   pairs/s with the batch already resident in HBM (scan kernel + record emit + junction aggregation per step)
+  value   pairs/s with the batch already resident in HBM: one step = four launches -- the scan kernel that writes the
+          junction records on the way (fc_scan_emit), the one-pass aggregation kernel and the two small kernels that rank
+          and convert the junctions (fc_agg_finalize)
   e2e     the same through the host-buffer C-ABI call fc_batch_host + fc_agg_finalize + fc_agg_fetch:
           pinned host SoA in, per-pair hits and the junction table out, copies inside the timed region
   roofline  the kernel with the longest launch in the step, roofline_other the second one.  scan kernel: 82
