@@ -172,7 +172,7 @@ def read_bam(fh) -> Tuple[List[str], List[int], Iterator[Alignment]]:
     names, lengths = [], []
     for _ in range(n_ref):
         (l_name,) = struct.unpack("<i", need(4))
-        names.append(need(l_name)[:-1].decode())
+        names.append(need(l_name)[:-1].decode("latin-1"))
         lengths.append(struct.unpack("<i", need(4))[0])
 
     def it():
@@ -185,7 +185,7 @@ def read_bam(fh) -> Tuple[List[str], List[int], Iterator[Alignment]]:
             b = need(block)
             tid, pos, l_rn, mapq, _bin, n_cig, flag, l_seq, _nt, _np, _tl = struct.unpack("<iiBBHHHiiii", b[:32])
             o = 32
-            qname = b[o : o + l_rn - 1].decode()
+            qname = b[o : o + l_rn - 1].decode("latin-1")
             o += l_rn
             cig = []
             for k in range(n_cig):
@@ -237,7 +237,7 @@ def open_alignments(path: Optional[str]):
     if path is None or path == "-":
         return read_sam(sys.stdin)
     if path.endswith("sam"):
-        return read_sam(open(path))
+        return read_sam(open(path, encoding="latin-1"))  # bytes as they are, like the native ingest
     return read_bam(open(path, "rb"))
 
 
