@@ -113,6 +113,12 @@ SYMBOLS = [
     ("fc_scan_emit_p2p", C.c_int, [_P, C.POINTER(ScanParams), C.POINTER(Pairs), _P, _P, _P, _P, _P, _P, C.c_uint64, _P]),
     ("fc_p2p_barrier", C.c_int, [_P, _P]),
     ("fc_agg_reset_async", C.c_int, [_P, _P]),
+    ("fc_bam_open", _P, [C.c_char_p]),
+    ("fc_bam_close", None, [_P]),
+    ("fc_bam_n_ref", C.c_int32, [_P]),
+    ("fc_bam_ref_name", C.c_char_p, [_P, C.c_int32]),
+    ("fc_bam_ref_length", C.c_int64, [_P, C.c_int32]),
+    ("fc_bam_read_text", C.c_int64, [_P, _P, C.c_int64]),
     ("fc_text_gather", C.c_int64, [_P, C.c_int64, _P, _P, _P]),
     ("fc_fastq_format", C.c_int64, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, C.c_int64, _P]),
     ("fc_pinned_alloc", _P, [C.c_int64]),

@@ -140,10 +140,9 @@ class GzipMembers(object):
 
 
 def native_ok(opt: Options, path) -> bool:
-    """the native ingest covers SAM text (a file whose name ends in 'sam', or stdin: find_circ.py:461-469); BAM and
-    --all-hits / --noop use the python reader"""
-    text = (not path) or path == "-" or path.endswith("sam")
-    return text and not opt.allhits and not opt.noop and not opt.test and opt.native
+    """the native ingest covers SAM text (a file whose name ends in 'sam', or stdin) and BAM (any other name:
+    find_circ.py:461-469); --all-hits / --noop / --test use the python reader"""
+    return not opt.allhits and not opt.noop and not opt.test and opt.native
 
 
 class _Prefixed(object):
@@ -184,6 +183,12 @@ def run_to_strings(opt: Options, path=None, engine=None, native=None):
     stream = None
     if native and (not path or path == "-"):
         names, stream = _stream_header(sys.stdin.buffer)
+        records = None
+    elif native and not path.endswith("sam"):
+        from .ingest import BamText
+
+        stream = BamText(path)  # BAM: inflated and turned into SAM text records in C++ (csrc/bam.cu)
+        names = stream.names
         records = None
     elif native:
         names = samio.sam_header_names(path)

@@ -76,3 +76,47 @@ class NativeIngest(object):
             self.close()
         except Exception:
             pass
+
+
+class BamText(object):
+    """a BAM file as a stream of SAM text records (csrc/bam.cu): `.names` / `.lengths` of the header, `.read(n)` like a
+    binary file -- whole lines only, b"" at the end"""
+
+    def __init__(self, path: str):
+        self.lib = _lib.load()
+        self.h = self.lib.fc_bam_open(path.encode())
+        if not self.h:
+            raise IOError("cannot read '%s' as BAM" % path)
+        n = self.lib.fc_bam_n_ref(self.h)
+        self.names = [self.lib.fc_bam_ref_name(self.h, i).decode("latin-1") for i in range(n)]
+        self.lengths = [int(self.lib.fc_bam_ref_length(self.h, i)) for i in range(n)]
+        self._buf = None
+        self._done = False
+
+    def read(self, n: int) -> bytes:
+        if self._done:
+            return b""
+        n = max(int(n), 1 << 17)
+        if self._buf is None or len(self._buf) < n:
+            self._buf = np.empty(n, dtype=np.uint8)
+        w = 0
+        while n - w >= (1 << 16):
+            got = self.lib.fc_bam_read_text(self.h, self._buf.ctypes.data + w, n - w)
+            if got < 0:
+                raise IOError("truncated or malformed BAM file (%d)" % got)
+            if got == 0:
+                self._done = True
+                break
+            w += int(got)
+        return self._buf[:w].tobytes()
+
+    def close(self):
+        if self.h:
+            self.lib.fc_bam_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -587,10 +587,10 @@ class Run(object):
         try:
             while not eof:
                 chunk = fh.read(chunk_bytes)
-                eof = len(chunk) < chunk_bytes
+                eof = len(chunk) == 0  # (a stream may return short chunks before its end: BAM text comes in whole lines)
                 buf = carry + chunk if carry else chunk
                 off = 0
-                while True:
+                while len(buf):
                     used = ing.parse(buf, off, eof)
                     n = int(o.n_rows)
                     self.n_fragments += int(o.n_fragments)

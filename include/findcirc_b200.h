@@ -312,6 +312,17 @@ void fc_ingest_destroy(fc_ingest* h);
  * with the next chunk; final != 0 flushes the last fragment) or a negative error code */
 int64_t fc_ingest_parse(fc_ingest* h, const char* text, int64_t nbytes, int32_t final, fc_ingest_out* out);
 
+/* BAM input (pysam.Samfile(path, 'rb'), find_circ.py:461-469): the file is inflated (BGZF, zlib) and handed out as SAM
+ * text lines -- the eleven mandatory columns and the AS / XS tags -- for fc_ingest_parse.  fc_bam_read_text fills `out`
+ * (cap >= 64 KiB) with whole lines and returns the bytes written, 0 at the end of the file, FC_E_IO for a broken file. */
+typedef struct fc_bam fc_bam;
+fc_bam* fc_bam_open(const char* path);
+void fc_bam_close(fc_bam* b);
+int32_t fc_bam_n_ref(const fc_bam* b);
+const char* fc_bam_ref_name(const fc_bam* b, int32_t i);
+int64_t fc_bam_ref_length(const fc_bam* b, int32_t i);
+int64_t fc_bam_read_text(fc_bam* b, char* out, int64_t cap);
+
 /* Spliced reads of the native ingest (write_read, find_circ.py:1442-1447): fc_text_gather copies n x 3 substrings
  * (name, sequence, qualities; off/len row major, len < 0 = absent) of a text buffer back to back into `out` and returns
  * the bytes written; fc_fastq_format turns such a blob into FASTQ records "@<name> <junction> \n<seq>\n+<name> <junction>

@@ -28,6 +28,28 @@ def test_host_logic_matches_reference(case_dir, ref_dir, argv, native):
     H.compare_outputs(out["circ"], out["lin"], out["reads"], out["multi"], out["counters"], ref_dir, argv, out["test"])
 
 
+@pytest.mark.parametrize("case,tag", [("synth_a", "default"), ("synth_a", "a20"), ("synth_a", "m4_d3"), ("synth_b", "default"),
+                                      ("kat3", "default"), ("cdr1as", "default"), ("synth_a", "known")])
+def test_native_ingest_from_bam(tmp_path, case, tag):
+    """BAM input goes through the native ingest as well: csrc/bam.cu inflates the file and hands the records to the C++
+    parser as SAM text (find_circ.py:461-469 reads BAM through pysam)"""
+    from conftest import GOLDEN, golden_cases
+    from find_circ2_b200 import cli
+    from test_cli_files import sam_to_bam
+
+    case_dir, ref_dir = os.path.join(GOLDEN, case), os.path.join(GOLDEN, case, "ref_" + tag)
+    argv = [a for c, r, a in golden_cases() if r == ref_dir][0]
+    bam = str(tmp_path / "input.bam")
+    sam_to_bam(os.path.join(case_dir, "input.sam"), bam)
+    opt = cli.parse_args(["-G", os.path.join(case_dir, "genome.fa")] + argv)[0]
+    opt.batch_pairs = 131
+    assert cli.native_ok(opt, bam)
+    eng = FakeEngine(0, opt.asize, opt.margin, opt.maxdist, opt.noncanonical, opt.strandpref)
+    eng.load_genome_fasta(opt.genome)
+    out = cli.run_to_strings(opt, bam, engine=eng)
+    H.compare_outputs(out["circ"], out["lin"], out["reads"], out["multi"], out["counters"], ref_dir, argv, out["test"])
+
+
 def test_native_ingest_from_stdin(monkeypatch):
     """SAM text piped in (`bwa mem ... | find_circ.py`, find_circ.py:461-469) goes through the native ingest too: the
     header is read off the stream, the body is parsed in chunks"""
@@ -41,7 +63,7 @@ def test_native_ingest_from_stdin(monkeypatch):
     ref_dir = os.path.join(case_dir, "ref_default")
     opt = cli.parse_args(["-G", os.path.join(case_dir, "genome.fa"), "-n", "test"])[0]
     opt.batch_pairs = 97
-    assert cli.native_ok(opt, None) and cli.native_ok(opt, "-") and not cli.native_ok(opt, "x.bam")
+    assert cli.native_ok(opt, None) and cli.native_ok(opt, "-") and cli.native_ok(opt, "x.bam")
     eng = FakeEngine(0, opt.asize, opt.margin, opt.maxdist, opt.noncanonical, opt.strandpref)
     eng.load_genome_fasta(opt.genome)
 
