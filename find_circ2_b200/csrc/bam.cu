@@ -42,8 +42,14 @@ inline int32_t le32(const char* p) {
 
 void append_int(std::string& s, long long v) {
   char buf[24];
-  const int n = snprintf(buf, sizeof(buf), "%lld", v);
-  s.append(buf, (size_t)n);
+  int n = 24;
+  unsigned long long u = v < 0 ? 0ull - (unsigned long long)v : (unsigned long long)v;
+  do {
+    buf[--n] = (char)('0' + u % 10);
+    u /= 10;
+  } while (u);
+  if (v < 0) buf[--n] = '-';
+  s.append(buf + n, (size_t)(24 - n));
 }
 
 // one binary record -> one SAM text line (appended to `out`); false on a malformed record
@@ -87,17 +93,25 @@ bool record_to_text(const fc_bam* b, const char* r, size_t len, std::string& out
     out.push_back('*');
   } else {
     static const char code[] = "=ACMGRSVTWYHKDBN";
-    for (int32_t k = 0; k < l_seq; ++k) {
-      const uint8_t byte = (uint8_t)r[o + (size_t)k / 2];
-      out.push_back(code[(k & 1) ? (byte & 15) : (byte >> 4)]);
+    const size_t at = out.size();
+    out.resize(at + (size_t)l_seq);
+    char* d = &out[at];
+    const uint8_t* sq = (const uint8_t*)r + o;
+    for (int32_t k = 0; k + 1 < l_seq; k += 2) {
+      d[k] = code[sq[k >> 1] >> 4];
+      d[k + 1] = code[sq[k >> 1] & 15];
     }
+    if (l_seq & 1) d[l_seq - 1] = code[sq[l_seq >> 1] >> 4];
   }
   o += (size_t)(l_seq + 1) / 2;
   out.push_back('\t');
   if (l_seq == 0 || (uint8_t)r[o] == 0xFF) {
     out.push_back('*');
   } else {
-    for (int32_t k = 0; k < l_seq; ++k) out.push_back((char)((uint8_t)r[o + k] + 33));
+    const size_t at = out.size();
+    out.resize(at + (size_t)l_seq);
+    char* d = &out[at];
+    for (int32_t k = 0; k < l_seq; ++k) d[k] = (char)((uint8_t)r[o + k] + 33);
   }
   o += (size_t)l_seq;
   // optional fields: AS and XS as integers, everything else is skipped
