@@ -199,7 +199,11 @@ def run_to_strings(opt: Options, path=None, engine=None, native=None):
     try:
         t0 = time.perf_counter()
         if stream is not None:
-            run.process_native(stream)
+            try:
+                run.process_native(stream)
+            finally:
+                if hasattr(stream, "close"):
+                    stream.close()
         elif native:
             with open(path, "rb") as fh:
                 run.process_native(fh)

@@ -80,9 +80,10 @@ class NativeIngest(object):
 
 class BamText(object):
     """a BAM file as a stream of SAM text records (csrc/bam.cu): `.names` / `.lengths` of the header, `.read(n)` like a
-    binary file -- whole lines only, b"" at the end"""
+    binary file -- whole lines only, b"" at the end.  A reader thread inflates the next chunk while the caller parses the
+    current one (both are C calls that release the interpreter lock)."""
 
-    def __init__(self, path: str):
+    def __init__(self, path: str, prefetch: int = 2):
         self.lib = _lib.load()
         self.h = self.lib.fc_bam_open(path.encode())
         if not self.h:
@@ -90,27 +91,67 @@ class BamText(object):
         n = self.lib.fc_bam_n_ref(self.h)
         self.names = [self.lib.fc_bam_ref_name(self.h, i).decode("latin-1") for i in range(n)]
         self.lengths = [int(self.lib.fc_bam_ref_length(self.h, i)) for i in range(n)]
-        self._buf = None
+        self._prefetch = prefetch
+        self._queue = None
+        self._thread = None
+        self._stop = False
         self._done = False
+
+    def _fill(self, n: int) -> bytes:
+        """the next chunk of at most n bytes (synchronously); b"" at the end"""
+        buf = np.empty(n, dtype=np.uint8)
+        w = 0
+        while n - w >= (1 << 16):
+            got = self.lib.fc_bam_read_text(self.h, buf.ctypes.data + w, n - w)
+            if got < 0:
+                raise IOError("truncated or malformed BAM file (%d)" % got)
+            if got == 0:
+                break
+            w += int(got)
+        return buf[:w].tobytes()
+
+    def _worker(self, n: int):
+        try:
+            while not self._stop:
+                chunk = self._fill(n)
+                self._queue.put(chunk)
+                if not chunk:
+                    return
+        except Exception as e:  # handed to the reader
+            self._queue.put(e)
 
     def read(self, n: int) -> bytes:
         if self._done:
             return b""
         n = max(int(n), 1 << 17)
-        if self._buf is None or len(self._buf) < n:
-            self._buf = np.empty(n, dtype=np.uint8)
-        w = 0
-        while n - w >= (1 << 16):
-            got = self.lib.fc_bam_read_text(self.h, self._buf.ctypes.data + w, n - w)
-            if got < 0:
-                raise IOError("truncated or malformed BAM file (%d)" % got)
-            if got == 0:
+        if self._prefetch <= 0:
+            chunk = self._fill(n)
+        else:
+            if self._thread is None:
+                import queue
+                import threading
+
+                self._queue = queue.Queue(maxsize=self._prefetch)
+                self._thread = threading.Thread(target=self._worker, args=(n,), daemon=True)
+                self._thread.start()
+            chunk = self._queue.get()
+            if isinstance(chunk, Exception):
                 self._done = True
-                break
-            w += int(got)
-        return self._buf[:w].tobytes()
+                raise chunk
+        if not chunk:
+            self._done = True
+        return chunk
 
     def close(self):
+        self._stop = True
+        if self._thread is not None:
+            while self._thread.is_alive():  # unblock a worker that waits for room in the queue
+                try:
+                    self._queue.get_nowait()
+                except Exception:
+                    pass
+                self._thread.join(timeout=0.05)
+            self._thread = None
         if self.h:
             self.lib.fc_bam_close(self.h)
             self.h = None

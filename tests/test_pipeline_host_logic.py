@@ -100,3 +100,41 @@ def test_gzip_members_writer(tmp_path):
     q = str(tmp_path / "empty.fastq.gz")
     GzipMembers(q).close()
     assert gzip.open(q, "rt").read() == ""
+
+
+def test_bam_text_stream_errors_and_close(tmp_path):
+    """csrc/bam.cu through ingest.BamText: header names, a truncated file raises, close() with chunks still queued returns"""
+    from conftest import GOLDEN
+    from find_circ2_b200.ingest import BamText
+    from test_cli_files import sam_to_bam
+
+    sam = os.path.join(GOLDEN, "synth_a", "input.sam")
+    bam = str(tmp_path / "a.bam")
+    sam_to_bam(sam, bam)
+    b = BamText(bam)
+    assert b.names == ["chr1", "chr2", "chr3"] and b.lengths == [30000, 22000, 9000]
+    first = b.read(1 << 17)
+    n_records = sum(1 for line in open(sam) if not line.startswith("@"))
+    text = first
+    while True:
+        c = b.read(1 << 17)
+        if not c:
+            break
+        text += c
+    assert text.count(b"\n") == n_records and b.read(10) == b""
+    b.close()
+    # closing early (the reader thread holds queued chunks) must not hang
+    b = BamText(bam)
+    b.read(1 << 17)
+    b.close()
+    # truncated file: the stream fails instead of ending silently
+    raw = open(bam, "rb").read()
+    cut = str(tmp_path / "cut.bam")
+    open(cut, "wb").write(raw[: len(raw) * 2 // 3])
+    b = BamText(cut)
+    with pytest.raises(IOError):
+        while b.read(1 << 17):
+            pass
+    b.close()
+    with pytest.raises(IOError):
+        BamText(sam)  # not a BAM file
