@@ -539,7 +539,14 @@ extern "C" int fc_batch_host_planes(fc_ctx* ctx, const fc_scan_params* p, int64_
   }
   FC_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[0], st));  // everything queued on the main stream so far comes first
   FC_CUDA(ctx, cudaStreamWaitEvent(ctx->own_stream2, ctx->ev_chunk[0], 0));
-  const int64_t chunk = 1 << 19;
+  // pairs per chunk (FC_HOST_CHUNK overrides): copies of 4 MiB and more per column run at the full PCIe rate, smaller ones do
+  // not, and that outweighs what the overlap of copies and kernels buys
+  static int64_t chunk = 0;
+  if (chunk == 0) {
+    const char* e = getenv("FC_HOST_CHUNK");
+    chunk = e ? atoll(e) : 0;
+    if (chunk < 1024) chunk = 1 << 20;  // measured on the B200 box at 1 M pairs: 256k 1.63 ms, 512k 1.56 ms, 1M (one chunk) 1.51 ms
+  }
   const size_t elem[14] = {4, 4, 4, 4, 1, 0, 0, 0, 0, 1, 2, 2, 8, 8};
   const void* src[14] = {h_chrom, h_a_start, h_b_end, h_l, h_flags, nullptr, nullptr, nullptr, nullptr,
                          h_wden, h_q_a, h_q_b, h_read_hash, h_qname_hash};
