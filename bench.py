@@ -17,6 +17,8 @@ A step is one pass of the hot path over one batch: config 2 of BASELINE.json -- 
             record + 64 B per junction / the library's own CUDA events around the kernel (fc_agg_get_timing)
   cpu_baseline  oracle (python restatement of find_circ.py, one numpy compare per split position) on a bounded sample
 L2 is flushed (256 MiB memset) before every timed step; per-step CUDA events are summed.
+Experiments only: FC_BENCH_ZIPF=<s> changes the popularity law of the planted junctions (default 1.0, the top junction
+holds 9 % of the records; 0 = uniform); FC_AGG_TIMING=1 prints the stage times of every fc_agg_finalize on stderr.
 Multi-GPU: pairs are sharded by rank (weak scaling: every rank scans its own 1 M pairs), junction records are
 hash-partitioned by key and written straight into the owner's buffer over NVLink (fallback: one all-to-all), every
 rank reduces its keys.
