@@ -295,7 +295,6 @@ def run_gpu(args):
         if use_p2p:
             eng.agg_reset_async(stream)
             eng.agg_set_idx_range(0, world * args.pairs)  # lets the owner rank the junctions without a sort
-            parallel.stream_barrier(dist, dev, eng, stream)  # every rank's counter is zero before anybody writes
         else:
             eng.agg_reset_async(stream)  # stays behind the L2-flush kernel in the stream: no host round trip before the scan
         if ev_scan:

@@ -111,6 +111,9 @@ SYMBOLS = [
     ("fc_p2p_connect", C.c_int, [_P, C.c_int32, C.c_int32, _P, _P]),
     ("fc_agg_emit_p2p", C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_uint64, _P]),
     ("fc_scan_emit_p2p", C.c_int, [_P, C.POINTER(ScanParams), C.POINTER(Pairs), _P, _P, _P, _P, _P, _P, C.c_uint64, _P]),
+    ("fc_p2p_export_local", C.c_int, [_P, C.c_int64, _P, _P]),
+    ("fc_p2p_connect_local", C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P]),
+    ("fc_p2p_set_timeout", C.c_int, [_P, C.c_double]),
     ("fc_p2p_barrier", C.c_int, [_P, _P]),
     ("fc_agg_reset_async", C.c_int, [_P, _P]),
     ("fc_bam_open", _P, [C.c_char_p]),

@@ -370,8 +370,17 @@ __device__ __forceinline__ void extrema_to_global(JAcc2* a, unsigned long long f
   if (inh > e1.z) atomicMax(&a->inv_nh, inh);
 }
 
-__global__ void __launch_bounds__(ACC_THREADS) fused_accumulate_kernel(int64_t ub, const unsigned long long* __restrict__ n_ptr,
-                                                               const fc_jrec* __restrict__ recs, U128* __restrict__ keys,
+// Where the records of a call live: one run behind a counter (local emit), or -- multi-GPU -- `n_slices` slices of
+// slice_cap records, slice s filled by source rank s with counts[s] records (emit_core.cuh: P2PView)
+struct RecSrc {
+  const fc_jrec* base;
+  const unsigned long long* counts;  // n_slices words
+  unsigned long long slice_cap;      // (n_slices == 1: the upper bound of the record count)
+  int n_slices;
+  unsigned long long* total_out;     // n_slices > 1: block 0 writes the exact record count here
+};
+
+__global__ void __launch_bounds__(ACC_THREADS) fused_accumulate_kernel(RecSrc src, U128* __restrict__ keys,
                                                                unsigned long long kmask, U128* __restrict__ sets,
                                                                unsigned long long smask, JAcc2* __restrict__ acc,
                                                                unsigned int acap, unsigned int* __restrict__ ctr,
@@ -387,7 +396,22 @@ __global__ void __launch_bounds__(ACC_THREADS) fused_accumulate_kernel(int64_t u
   }
   __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t n = min((int64_t)*n_ptr, ub);  // (a peer-to-peer counter keeps counting past the capacity)
+  // record i of the call: slice s holds records [prefix(s), prefix(s+1)) (a counter may have counted past its capacity)
+  int64_t n = 0, rec_at = i;
+  {
+    bool found = false;
+#pragma unroll 1
+    for (int sl = 0; sl < src.n_slices; ++sl) {
+      const int64_t c = (int64_t)min(src.counts[sl], src.slice_cap);
+      if (!found && i >= n && i < n + c) {
+        rec_at = (int64_t)sl * (int64_t)src.slice_cap + (i - n);
+        found = true;
+      }
+      n += c;
+    }
+  }
+  if (src.total_out && i == 0) *src.total_out = (unsigned long long)n;
+  const fc_jrec* __restrict__ recs = src.base;
   // the rank flags and tile counters of the finish pass are cleared on the way
   for (int64_t k = i; k < n_flag; k += (int64_t)gridDim.x * blockDim.x) flag[k] = 0u;
   for (int64_t k = i; k < n_tiles; k += (int64_t)gridDim.x * blockDim.x) tile_count[k] = 0u;
@@ -397,7 +421,7 @@ __global__ void __launch_bounds__(ACC_THREADS) fused_accumulate_kernel(int64_t u
   unsigned long long s_read = 0ull, s_name = 0ull;
   unsigned int jid = 0xFFFFFFFFu;
   if (active) {
-    const uint4* rp = reinterpret_cast<const uint4*>(recs + i);
+    const uint4* rp = reinterpret_cast<const uint4*>(recs + rec_at);
     r0 = __ldg(rp);
     r1 = __ldg(rp + 1);
     r2 = __ldg(rp + 2);
@@ -883,6 +907,9 @@ extern "C" int fc_agg_reset_async(fc_ctx* ctx, void* stream) {
 
 int fc_agg_reserve_records(fc_ctx* ctx, int64_t extra, cudaStream_t st) {
   fc_agg& a = ctx->agg;
+  // the counters exist (and their initial memset is queued on `st`) before the caller forks work onto other streams
+  int rc = ensure_counters(ctx, st);
+  if (rc) return rc;
   FC_CUDA(ctx, a.recs.reserve((size_t)(a.n_recs + extra) * sizeof(fc_jrec), st, true, (size_t)a.n_recs * sizeof(fc_jrec)));
   return FC_OK;
 }
@@ -1119,7 +1146,7 @@ struct StageTimer {
 
 // sort-free path over the `ub` (upper bound; the exact count is on the device) records of the context; returns -100
 // when the input needs the sort-based path (a weight denominator that is not 1, 2, 4 or 8; too many records)
-static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st) {
+static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st, const RecSrc& src) {
   fc_agg& a = ctx->agg;
   if (ub >= FUSED_MAX_RECORDS) return -100;
   // key table: one entry per junction, at most one junction per record (load <= 2/3); distinct set: two entries per record
@@ -1167,9 +1194,9 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st) {
     tile_count = (uint32_t*)a.scratch[1].p;
   }
   tm.mark("clear");
-  fused_accumulate_kernel<<<nblk(ub, ACC_THREADS), ACC_THREADS, 0, st>>>(ub, counters, (const fc_jrec*)a.recs.p, (U128*)a.f_keys.p,
-                                                                         kcap - 1, (U128*)a.f_sets.p, scap - 1, (JAcc2*)a.f_acc.p,
-                                                                         acap, ctr, flag, range, tile_count, n_tiles);
+  fused_accumulate_kernel<<<nblk(ub, ACC_THREADS), ACC_THREADS, 0, st>>>(src, (U128*)a.f_keys.p, kcap - 1, (U128*)a.f_sets.p,
+                                                                         scap - 1, (JAcc2*)a.f_acc.p, acap, ctr, flag, range,
+                                                                         tile_count, n_tiles);
   FC_LAUNCH_CHECK(ctx);
   tm.mark("accumulate");
   const unsigned sweep_blocks = (unsigned)ctx->sm_count * 8u;
@@ -1218,7 +1245,8 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st) {
   a.n_recs = (int64_t)h[0];
   a.n_exact = true;
   if (a.p2p_enabled && h[FC_BARRIER_TIMEOUT_WORD])
-    return fc_fail(ctx, FC_E_STATE, "a peer-memory barrier timed out: a peer rank did not arrive");
+    return fc_fail(ctx, FC_E_STATE, "a peer-memory barrier timed out (a peer rank did not arrive in %.0f s): the results of this step are invalid",
+                   a.p2p_timeout_s);
   if (a.p2p_enabled && h[4])
     return fc_fail(ctx, FC_E_NOMEM, "peer-to-peer record buffer overflow (%llu records dropped): raise the capacity", h[4]);
   const unsigned int n_other = (unsigned int)(h[8] >> 32), n_overflow = (unsigned int)h[9];
@@ -1240,39 +1268,100 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st) {
   return nj;
 }
 
+// multi-GPU: the slice counts the source ranks have published for the current step (host copy), clamped to the capacity
+static int p2p_slice_counts(fc_ctx* ctx, cudaStream_t st, unsigned long long* out /* 8 */, int64_t* total) {
+  fc_agg& a = ctx->agg;
+  const int parity = (int)((a.barrier_epoch - 1) & 1ull);
+  unsigned long long blk[64];
+  FC_CUDA(ctx, cudaMemcpyAsync(blk, a.counters.p, sizeof(blk), cudaMemcpyDeviceToHost, st));
+  FC_CUDA(ctx, cudaStreamSynchronize(st));
+  if (blk[FC_BARRIER_TIMEOUT_WORD])
+    return fc_fail(ctx, FC_E_STATE, "a peer-memory barrier timed out (a peer rank did not arrive in %.0f s): the results of this step are invalid",
+                   a.p2p_timeout_s);
+  if (blk[4])
+    return fc_fail(ctx, FC_E_NOMEM, "peer-to-peer record buffer overflow (%llu records of this rank dropped): raise the capacity", blk[4]);
+  const unsigned long long* h = blk + fc::FC_CNT_SLICE + 8 * parity;
+  *total = 0;
+  for (int r = 0; r < 8; ++r) {
+    out[r] = 0;
+    if (r >= a.p2p_world) continue;
+    if (h[r] > (unsigned long long)a.p2p_slice_cap)
+      return fc_fail(ctx, FC_E_NOMEM, "peer-to-peer record buffer overflow (rank %d sent %llu records into a slice of %lld): raise the capacity",
+                     r, h[r], (long long)a.p2p_slice_cap);
+    out[r] = h[r];
+    *total += (int64_t)h[r];
+  }
+  return FC_OK;
+}
+
 extern "C" int64_t fc_agg_finalize(fc_ctx* ctx, void* stream) {
   if (!ctx) return FC_E_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   fc_agg& a = ctx->agg;
-  if (!a.counters.p || (a.n_exact && a.n_recs == 0)) {
+  if (!a.counters.p || (!a.p2p_enabled && a.n_exact && a.n_recs == 0)) {
     a.n_recs = 0;
     a.n_junc = 0;
     return 0;
   }
-  if (a.n_recs >= (1ll << 32)) return fc_fail(ctx, FC_E_ARG, "more than 2^32 records on one device");
   // FC_AGG_MODE=sort forces the sort-based path (tests compare the two)
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("FC_AGG_MODE");
-    mode = (e && e[0] == 's') ? 1 : 0;
+  const char* mode_env = getenv("FC_AGG_MODE");
+  const bool sort_mode = mode_env && mode_env[0] == 's';
+  fc_jrec* rbuf = (fc_jrec*)a.recs.p;  // where the sort-based path finds (and re-orders) the records
+  if (a.p2p_enabled) {
+    // records sit in one slice per source rank in the half of the buffer that belongs to the step the last barrier closed
+    if (a.p2p_open) return fc_fail(ctx, FC_E_STATE, "fc_agg_finalize before the fc_p2p_barrier that ends the step");
+    if (a.barrier_epoch == 0) {
+      a.n_recs = 0;
+      a.n_junc = 0;
+      return 0;
+    }
+    unsigned long long cnt[8];
+    int64_t total = 0;
+    int rc = p2p_slice_counts(ctx, st, cnt, &total);
+    if (rc) return rc;
+    a.n_recs = total;
+    a.n_exact = true;
+    if (total == 0) {
+      a.n_junc = 0;
+      return 0;
+    }
+    if (total >= (1ll << 32)) return fc_fail(ctx, FC_E_ARG, "more than 2^32 records on one device");
+    const int parity = (int)((a.barrier_epoch - 1) & 1ull);
+    const fc_jrec* half = (const fc_jrec*)a.recs.p + (size_t)parity * (size_t)a.p2p_world * (size_t)a.p2p_slice_cap;
+    if (!sort_mode) {
+      RecSrc src{half, (const unsigned long long*)a.counters.p + fc::FC_CNT_SLICE + 8 * parity, (unsigned long long)a.p2p_slice_cap,
+                 a.p2p_world, (unsigned long long*)a.counters.p};
+      // the grid covers the largest slice layout that holds `total` records: thread i serves record i of the concatenation
+      const int64_t r = finalize_fused(ctx, total, st, src);
+      if (r != -100) return r;
+    }
+    // sort-based path: it wants one contiguous run
+    FC_CUDA(ctx, a.p2p_compact.reserve((size_t)total * sizeof(fc_jrec), st, false, 0));
+    int64_t at = 0;
+    for (int r = 0; r < a.p2p_world; ++r) {
+      if (cnt[r])
+        FC_CUDA(ctx, cudaMemcpyAsync((fc_jrec*)a.p2p_compact.p + at, half + (size_t)r * (size_t)a.p2p_slice_cap, (size_t)cnt[r] * sizeof(fc_jrec),
+                                     cudaMemcpyDeviceToDevice, st));
+      at += (int64_t)cnt[r];
+    }
+    rbuf = (fc_jrec*)a.p2p_compact.p;
+    a.unordered = true;
+  } else {
+    if (a.n_recs >= (1ll << 32)) return fc_fail(ctx, FC_E_ARG, "more than 2^32 records on one device");
+    if (!sort_mode) {
+      // no host round trip before the kernels: they are sized by the upper bound and read the exact count on the device
+      RecSrc src{(const fc_jrec*)a.recs.p, (const unsigned long long*)a.counters.p, (unsigned long long)a.n_recs, 1, nullptr};
+      const int64_t r = finalize_fused(ctx, a.n_recs, st, src);
+      if (r != -100) return r;
+    }
+    int rc = sync_n_recs(ctx, st);
+    if (rc) return rc;
   }
-  if (mode == 0) {
-    // no host round trip before the kernels: they are sized by the upper bound and read the exact count on the device
-    const int64_t r = finalize_fused(ctx, a.n_recs, st);
-    if (r != -100) return r;
-  }
-  int rc = sync_n_recs(ctx, st);
-  if (rc) return rc;
+  int rc = FC_OK;
   const int64_t n = a.n_recs;
   if (n == 0) {
     a.n_junc = 0;
     return 0;
-  }
-  if (a.p2p_enabled) {
-    unsigned long long ovf = 0;
-    FC_CUDA(ctx, cudaMemcpyAsync(&ovf, (unsigned long long*)a.counters.p + 4, sizeof(ovf), cudaMemcpyDeviceToHost, st));
-    FC_CUDA(ctx, cudaStreamSynchronize(st));
-    if (ovf) return fc_fail(ctx, FC_E_NOMEM, "peer-to-peer record buffer overflow (%llu records dropped): raise the capacity", ovf);
   }
   // scratch layout
   FC_CUDA(ctx, a.scratch[0].reserve((size_t)n * 8, st, false, 0));  // u64 A
@@ -1294,13 +1383,13 @@ extern "C" int64_t fc_agg_finalize(fc_ctx* ctx, void* stream) {
   if (a.unordered) {
     // records arrived in arbitrary order (peer-to-peer emit): restore stream order first, the stable sort below and the
     // sequential float sums rely on it
-    idx_key_kernel<<<nblk(n, 256), 256, 0, st>>>(n, (const fc_jrec*)a.recs.p, kA, vA);
+    idx_key_kernel<<<nblk(n, 256), 256, 0, st>>>(n, (const fc_jrec*)rbuf, kA, vA);
     FC_LAUNCH_CHECK(ctx);
     rc = sort_pairs_u64_u32(ctx, n, kA, kB, vA, vB, 0, 64, st);
     if (rc) return rc;
-    gather_kernel<<<nblk(n, 256), 256, 0, st>>>(n, (const fc_jrec*)a.recs.p, vB, sorted);
+    gather_kernel<<<nblk(n, 256), 256, 0, st>>>(n, (const fc_jrec*)rbuf, vB, sorted);
     FC_LAUNCH_CHECK(ctx);
-    FC_CUDA(ctx, cudaMemcpyAsync(a.recs.p, sorted, (size_t)n * sizeof(fc_jrec), cudaMemcpyDeviceToDevice, st));
+    FC_CUDA(ctx, cudaMemcpyAsync(rbuf, sorted, (size_t)n * sizeof(fc_jrec), cudaMemcpyDeviceToDevice, st));
     a.unordered = false;
   }
   uint64_t seed = 0x9E3779B97F4A7C15ULL;
@@ -1314,11 +1403,11 @@ extern "C" int64_t fc_agg_finalize(fc_ctx* ctx, void* stream) {
   if (bits > 64) bits = 64;
   for (int attempt = 0; attempt < 4 && !ok; ++attempt, seed = fc_mix64(seed + attempt), bits = 64) {
     const uint64_t hmask = bits >= 64 ? ~0ull : ((1ull << bits) - 1ull);
-    key_hash_kernel<<<nblk(n, 256), 256, 0, st>>>(n, (const fc_jrec*)a.recs.p, seed, kA, vA);
+    key_hash_kernel<<<nblk(n, 256), 256, 0, st>>>(n, (const fc_jrec*)rbuf, seed, kA, vA);
     FC_LAUNCH_CHECK(ctx);
     rc = sort_pairs_u64_u32(ctx, n, kA, kB, vA, vB, 0, bits, st);
     if (rc) return rc;
-    gather_kernel<<<nblk(n, 256), 256, 0, st>>>(n, (const fc_jrec*)a.recs.p, vB, sorted);
+    gather_kernel<<<nblk(n, 256), 256, 0, st>>>(n, (const fc_jrec*)rbuf, vB, sorted);
     FC_LAUNCH_CHECK(ctx);
     FC_CUDA(ctx, cudaMemsetAsync(counters + 1, 0, sizeof(unsigned long long), st));
     heads_kernel<<<nblk(n, 256), 256, 0, st>>>(n, sorted, kB, hmask, head, counters + 1);
@@ -1409,12 +1498,14 @@ extern "C" const fc_junction* fc_agg_junctions(fc_ctx* ctx) {
 }
 
 // ======================================================================================================================
-// Fused emit + exchange over peer memory (multi-GPU, one node).  Every rank exports its record buffer and its record
-// counter with CUDA IPC; the emit kernel of every rank hashes the junction key of each accepted pair to its owner rank,
-// claims slots in the OWNER's buffer with a warp-aggregated system-scope atomicAdd on the owner's counter and stores
-// the 48-byte record straight into the owner's memory over NVLink.  No partition pass, no all-to-all, no host
-// synchronisation: two stream-ordered barriers (tiny NCCL all-reduces issued by the host) bracket the kernel.
-// Arrival order is arbitrary; the sort-free aggregation does not depend on it and the sort-based fallback re-orders by idx.
+// Fused emit + exchange over peer memory (multi-GPU, one node).  Every rank exports its record buffer and its counter
+// block (CUDA IPC between processes; plain device pointers between contexts of one process); the emit kernel of every rank
+// hashes the junction key of each accepted pair to its owner rank and stores the 48-byte record straight into the slice
+// that the owner's buffer reserves for this source (emit_core.cuh) -- slots come from counters in the SOURCE's memory, so
+// no atomic crosses NVLink.  One stream-ordered barrier per step publishes the slice counts to the owners and orders the
+// record stores before the owners' fc_agg_finalize; the buffers have two halves used by alternating steps, so no barrier
+// is needed before the next step's stores.  Arrival order is arbitrary; the sort-free aggregation does not depend on it and
+// the sort-based fallback re-orders by idx.
 // ======================================================================================================================
 using fc::P2PView;
 constexpr int P2P_THREADS = 512;
@@ -1438,21 +1529,53 @@ __global__ void __launch_bounds__(P2P_THREADS) emit_p2p_kernel(int64_t n, const 
   fc::emit_p2p_block<P2P_THREADS>(accept, i, h.start, h.end, h.w2, h.w3, c, fl, e, pv, overflow);
 }
 
-extern "C" int fc_p2p_export(fc_ctx* ctx, int64_t capacity_records, uint8_t* h_handles /* 128 bytes */) {
-  if (!ctx || capacity_records <= 0 || !h_handles) return FC_E_ARG;
+static int p2p_reserve(fc_ctx* ctx, int64_t capacity_records) {
   fc_agg& a = ctx->agg;
   cudaStream_t st = ctx->own_stream;
   int rc = ensure_counters(ctx, st);
   if (rc) return rc;
-  FC_CUDA(ctx, a.recs.reserve((size_t)capacity_records * sizeof(fc_jrec), st, false, 0));
+  // two halves (alternating steps) of `capacity` records each
+  FC_CUDA(ctx, a.recs.reserve(2 * (size_t)capacity_records * sizeof(fc_jrec), st, false, 0));
   FC_CUDA(ctx, cudaStreamSynchronize(st));
-  a.p2p_capacity = (int64_t)(a.recs.cap / sizeof(fc_jrec));
+  a.p2p_capacity = capacity_records;
+  return FC_OK;
+}
+
+extern "C" int fc_p2p_export(fc_ctx* ctx, int64_t capacity_records, uint8_t* h_handles /* 128 bytes */) {
+  if (!ctx || capacity_records <= 0 || !h_handles) return FC_E_ARG;
+  fc_agg& a = ctx->agg;
+  int rc = p2p_reserve(ctx, capacity_records);
+  if (rc) return rc;
   cudaIpcMemHandle_t h0, h1;
   FC_CUDA(ctx, cudaIpcGetMemHandle(&h0, a.recs.p));
   FC_CUDA(ctx, cudaIpcGetMemHandle(&h1, a.counters.p));
   memcpy(h_handles, &h0, 64);
   memcpy(h_handles + 64, &h1, 64);
-  memcpy(h_handles + 56, &a.p2p_capacity, 0);  // (capacity travels separately)
+  return FC_OK;
+}
+
+// the same for contexts of ONE process on one device: plain device pointers instead of IPC handles
+extern "C" int fc_p2p_export_local(fc_ctx* ctx, int64_t capacity_records, void** out_recs, void** out_counters) {
+  if (!ctx || capacity_records <= 0 || !out_recs || !out_counters) return FC_E_ARG;
+  int rc = p2p_reserve(ctx, capacity_records);
+  if (rc) return rc;
+  *out_recs = ctx->agg.recs.p;
+  *out_counters = ctx->agg.counters.p;
+  return FC_OK;
+}
+
+static int p2p_finish_connect(fc_ctx* ctx, int32_t world, int32_t rank, const int64_t* h_capacities) {
+  fc_agg& a = ctx->agg;
+  int64_t cap = a.p2p_capacity;
+  for (int r = 0; r < world; ++r)
+    if (h_capacities[r] < cap) cap = h_capacities[r];
+  a.p2p_world = world;
+  a.p2p_rank = rank;
+  a.p2p_slice_cap = cap / world;
+  if (a.p2p_slice_cap < 1) return fc_fail(ctx, FC_E_ARG, "peer-to-peer capacity %lld too small for %d ranks", (long long)cap, world);
+  a.p2p_enabled = true;
+  a.p2p_open = false;
+  a.barrier_epoch = 0;
   return FC_OK;
 }
 
@@ -1460,11 +1583,8 @@ extern "C" int fc_p2p_connect(fc_ctx* ctx, int32_t world, int32_t rank, const ui
                               const int64_t* h_capacities /* world */) {
   if (!ctx || world < 1 || world > 8 || rank < 0 || rank >= world || !h_all_handles || !h_capacities) return FC_E_ARG;
   fc_agg& a = ctx->agg;
-  a.p2p_world = world;
-  a.p2p_rank = rank;
-  int64_t cap = a.p2p_capacity;
+  if (a.p2p_capacity <= 0) return fc_fail(ctx, FC_E_STATE, "fc_p2p_connect before fc_p2p_export");
   for (int r = 0; r < world; ++r) {
-    if (h_capacities[r] < cap) cap = h_capacities[r];
     if (r == rank) {
       a.p2p_recs[r] = a.recs.p;
       a.p2p_cnt[r] = a.counters.p;
@@ -1476,32 +1596,59 @@ extern "C" int fc_p2p_connect(fc_ctx* ctx, int32_t world, int32_t rank, const ui
     FC_CUDA(ctx, cudaIpcOpenMemHandle(&a.p2p_recs[r], h0, cudaIpcMemLazyEnablePeerAccess));
     FC_CUDA(ctx, cudaIpcOpenMemHandle(&a.p2p_cnt[r], h1, cudaIpcMemLazyEnablePeerAccess));
   }
-  a.p2p_min_capacity = cap;
-  a.p2p_enabled = true;
+  a.p2p_ipc = true;
+  a.p2p_local = false;
+  return p2p_finish_connect(ctx, world, rank, h_capacities);
+}
+
+extern "C" int fc_p2p_connect_local(fc_ctx* ctx, int32_t world, int32_t rank, void* const* recs, void* const* counters,
+                                    const int64_t* h_capacities) {
+  if (!ctx || world < 1 || world > 8 || rank < 0 || rank >= world || !recs || !counters || !h_capacities) return FC_E_ARG;
+  fc_agg& a = ctx->agg;
+  if (a.p2p_capacity <= 0) return fc_fail(ctx, FC_E_STATE, "fc_p2p_connect_local before fc_p2p_export_local");
+  for (int r = 0; r < world; ++r) {
+    a.p2p_recs[r] = r == rank ? a.recs.p : recs[r];
+    a.p2p_cnt[r] = r == rank ? a.counters.p : counters[r];
+  }
+  a.p2p_ipc = false;
+  a.p2p_local = true;
+  return p2p_finish_connect(ctx, world, rank, h_capacities);
+}
+
+extern "C" int fc_p2p_set_timeout(fc_ctx* ctx, double seconds) {
+  if (!ctx || !(seconds > 0.0)) return FC_E_ARG;
+  ctx->agg.p2p_timeout_s = seconds;
   return FC_OK;
+}
+
+static void p2p_view(const fc_agg& a, P2PView* pv) {
+  for (int r = 0; r < 8; ++r) {
+    pv->recs[r] = r < a.p2p_world ? (fc_jrec*)a.p2p_recs[r] : nullptr;
+    pv->cnt[r] = r < a.p2p_world ? (unsigned long long*)a.p2p_cnt[r] : nullptr;
+  }
+  pv->slice_cap = (unsigned long long)a.p2p_slice_cap;
+  pv->world = a.p2p_world;
+  pv->rank = a.p2p_rank;
+  pv->parity = (int)(a.barrier_epoch & 1ull);
 }
 
 // the peer view of the context and the bookkeeping of a peer emit, shared with the scan kernel that emits on the way
 int fc_agg_p2p_begin(fc_ctx* ctx, fc::P2PView* pv, unsigned long long** overflow) {
   fc_agg& a = ctx->agg;
   if (!a.p2p_enabled) return fc_fail(ctx, FC_E_STATE, "peer emit before fc_p2p_connect");
-  for (int r = 0; r < 8; ++r) {
-    pv->recs[r] = r < a.p2p_world ? (fc_jrec*)a.p2p_recs[r] : nullptr;
-    pv->cnt[r] = r < a.p2p_world ? (unsigned long long*)a.p2p_cnt[r] : nullptr;
-  }
-  pv->capacity = (unsigned long long)a.p2p_min_capacity;
-  pv->world = a.p2p_world;
-  pv->rank = a.p2p_rank;
+  p2p_view(a, pv);
   *overflow = (unsigned long long*)a.counters.p + 4;
   return FC_OK;
 }
 
-void fc_agg_p2p_end(fc_ctx* ctx) {
+void fc_agg_p2p_end(fc_ctx* ctx, uint64_t idx_base, int64_t n) {
   fc_agg& a = ctx->agg;
-  a.n_recs = a.p2p_capacity;  // upper bound; the exact count is the (shared) device counter
+  a.p2p_open = true;  // until the barrier that ends the step
   a.n_exact = false;
   a.unordered = true;
   if (!a.range_declared) a.max_idx = ~0ull;
+  (void)idx_base;
+  (void)n;
   a.n_junc = -1;
 }
 
@@ -1514,27 +1661,38 @@ extern "C" int fc_agg_emit_p2p(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, con
   unsigned long long* overflow = nullptr;
   int rc = fc_agg_p2p_begin(ctx, &pv, &overflow);
   if (rc) return rc;
-  if (n == 0) return FC_OK;
+  if (n == 0) {
+    fc_agg_p2p_end(ctx, idx_base, 0);  // an empty shard still owns keys: its peers' records must be reduced
+    return FC_OK;
+  }
   fc::EmitArgs e{d_wden, d_q_a, d_q_b, d_read_hash, d_qname_hash, idx_base, nullptr, nullptr, nullptr};
   emit_p2p_kernel<<<nblk(n, P2P_THREADS), P2P_THREADS, 0, (cudaStream_t)stream>>>(n, d_hits, d_mask, d_chrom, d_flags, e, pv, overflow);
   FC_LAUNCH_CHECK(ctx);
-  fc_agg_p2p_end(ctx);
+  fc_agg_p2p_end(ctx, idx_base, n);
   return FC_OK;
 }
 
 // ---- stream-ordered barrier over peer memory ------------------------------------------------------------------
-// Every rank adds 1 to the arrival word of every rank (its own included) and waits until its own word has seen `world`
-// arrivals per barrier so far.  One tiny kernel: a few microseconds over NVLink instead of a collective launch.  The wait
-// is bounded (a peer that died must not hang the GPU): after ~2 s it gives up and raises the flag that the next
-// fc_agg_finalize reports.
-__global__ void p2p_barrier_kernel(P2PView pv, unsigned long long target) {
-  __threadfence_system();  // this rank's earlier peer stores are ordered before its arrival
+// Ends a step: every rank (1) publishes how many records it has put into its slice of every owner, (2) adds 1 to the
+// arrival word of every rank (its own included) and (3) waits until its own word has seen `world` arrivals per barrier so
+// far -- then every peer's records and counts have landed here.  One tiny kernel: a few microseconds over NVLink instead
+// of a collective launch.  The wait is bounded (a peer that died must not hang the GPU): after `timeout_cycles` it gives
+// up and raises the flag that makes the next fc_agg_finalize fail with FC_E_STATE -- the step's results are then invalid.
+// wait == 0 (contexts of one process on one device, launched one after the other): publish and arrive only.
+__global__ void p2p_barrier_kernel(P2PView pv, unsigned long long target, long long timeout_cycles, int wait) {
+  if ((int)threadIdx.x < pv.world) {
+    const unsigned long long sent = pv.cnt[pv.rank][fc::FC_CNT_SRC + threadIdx.x];
+    pv.cnt[threadIdx.x][fc::FC_CNT_SLICE + 8 * pv.parity + pv.rank] = sent;
+    pv.cnt[pv.rank][fc::FC_CNT_SRC + threadIdx.x] = 0ull;  // the next step starts from empty slices
+  }
+  __threadfence_system();  // this rank's record stores and counts are ordered before its arrival
+  __syncwarp();
   if ((int)threadIdx.x < pv.world) atomicAdd_system(pv.cnt[threadIdx.x] + FC_BARRIER_WORD, 1ull);
-  if (threadIdx.x == 0) {
+  if (wait && threadIdx.x == 0) {
     volatile unsigned long long* mine = pv.cnt[pv.rank] + FC_BARRIER_WORD;
     const long long t0 = clock64();
     while (*mine < target) {
-      if (clock64() - t0 > 4000000000ll) {  // ~2 s at 2 GHz
+      if (clock64() - t0 > timeout_cycles) {
         pv.cnt[pv.rank][FC_BARRIER_TIMEOUT_WORD] = 1ull;
         break;
       }
@@ -1549,21 +1707,26 @@ extern "C" int fc_p2p_barrier(fc_ctx* ctx, void* stream) {
   fc_agg& a = ctx->agg;
   if (!a.p2p_enabled) return fc_fail(ctx, FC_E_STATE, "fc_p2p_barrier before fc_p2p_connect");
   P2PView pv;
-  for (int r = 0; r < 8; ++r) {
-    pv.recs[r] = nullptr;
-    pv.cnt[r] = r < a.p2p_world ? (unsigned long long*)a.p2p_cnt[r] : nullptr;
-  }
-  pv.capacity = 0;
-  pv.world = a.p2p_world;
-  pv.rank = a.p2p_rank;
+  p2p_view(a, &pv);
   a.barrier_epoch++;
-  p2p_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pv, a.barrier_epoch * (unsigned long long)a.p2p_world);
+  a.p2p_open = false;
+  const long long cycles = (long long)(a.p2p_timeout_s * 2.0e9);  // clock64 ticks at <= 2 GHz: at least the requested time
+  p2p_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pv, a.barrier_epoch * (unsigned long long)a.p2p_world, cycles,
+                                                         a.p2p_local ? 0 : 1);
   FC_LAUNCH_CHECK(ctx);
   return FC_OK;
 }
 
 void fc_agg_release(fc_ctx* ctx) {
   fc_agg& a = ctx->agg;
+  if (a.p2p_ipc)
+    for (int r = 0; r < a.p2p_world; ++r)
+      if (r != a.p2p_rank) {
+        if (a.p2p_recs[r]) cudaIpcCloseMemHandle(a.p2p_recs[r]);
+        if (a.p2p_cnt[r]) cudaIpcCloseMemHandle(a.p2p_cnt[r]);
+      }
+  a.p2p_enabled = false;
+  a.p2p_compact.release();
   a.recs.release();
   a.junctions.release();
   for (auto& s : a.scratch) s.release();

@@ -55,6 +55,7 @@ extern "C" void fc_ctx_destroy(fc_ctx* ctx) {
   fc_genome_release(ctx);
   fc_agg_release(ctx);
   for (auto& b : ctx->host_path) b.release();
+  ctx->tie_off.release();
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->own_stream2) {
     cudaStreamDestroy(ctx->own_stream2);

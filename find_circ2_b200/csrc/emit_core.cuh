@@ -81,13 +81,21 @@ __device__ __forceinline__ void emit_block(bool accept, int64_t i, int32_t h_sta
 }
 
 // ---- the same towards the rank that owns the junction key (fused emit + exchange over peer memory) --------------------
+// Every rank's record buffer is cut into 2 x world SLICES of slice_cap records: slice (parity, s) of rank d receives the
+// records that source rank s sends to owner d in the steps of that parity.  A source therefore allocates its slots with
+// counters in its OWN memory (device-scope atomics, no NVLink round trip) and only the 48-byte records cross the wire;
+// the counts are published to the owners by the barrier kernel that ends the step (agg.cu: p2p_barrier_kernel).  Two
+// parities: a rank may already write step k+1 into a peer that still reduces step k.
 struct P2PView {
-  fc_jrec* recs[8];             // record buffer of every rank (peer memory, CUDA IPC)
-  unsigned long long* cnt[8];   // counters of every rank; word 0 = record count
-  unsigned long long capacity;  // records per buffer
+  fc_jrec* recs[8];             // record buffer of every rank (peer memory)
+  unsigned long long* cnt[8];   // counter block of every rank (peer memory)
+  unsigned long long slice_cap; // records per slice
   int world;
   int rank;
+  int parity;                   // 0 / 1: which half of the buffers this step uses
 };
+constexpr int FC_CNT_SRC = 16;    // counter words [16, 24): records this rank has sent to destination d in this step
+constexpr int FC_CNT_SLICE = 40;  // counter words [40, 56): [parity][source] records received from source in the step
 
 __device__ __forceinline__ fc_jrec make_record(int64_t i, int32_t h_start, int32_t h_end, uint32_t w2, uint32_t w3, uint32_t chrom,
                                                uint32_t pair_flags, const EmitArgs& e) {
@@ -112,9 +120,9 @@ __device__ __forceinline__ fc_jrec make_record(int64_t i, int32_t h_start, int32
 }
 
 // Called by every thread of a CTA of BS threads.  The CTA's records are grouped by destination rank in shared memory;
-// ONE system-scope atomic per CTA and destination claims the slots in the owner's buffer (per-warp allocation made the
-// owners' counters the bottleneck at 8 GPUs); every group then goes out as one run of consecutive 16-byte stores --
-// full-size write packets on NVLink instead of scattered 16-byte ones.
+// one device-scope atomic per CTA and destination on the SOURCE's own counters claims the slots of the source's slice
+// in the owner's buffer; every group then goes out as one run of consecutive 16-byte stores -- full-size write packets
+// on NVLink instead of scattered 16-byte ones, and nothing on the CTA's critical path crosses the wire.
 template <int BS>
 __device__ __forceinline__ void emit_p2p_block(bool accept, int64_t i, int32_t h_start, int32_t h_end, uint32_t w2, uint32_t w3,
                                                uint32_t chrom, uint32_t pair_flags, const EmitArgs& e, const P2PView& pv,
@@ -146,7 +154,7 @@ __device__ __forceinline__ void emit_p2p_block(bool accept, int64_t i, int32_t h
   }
   __syncthreads();
   if ((int)threadIdx.x < pv.world && s_cnt[threadIdx.x])
-    s_base[threadIdx.x] = atomicAdd_system(pv.cnt[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+    s_base[threadIdx.x] = atomicAdd(pv.cnt[pv.rank] + FC_CNT_SRC + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
   if (threadIdx.x == 0) {
     unsigned int acc = 0;
     for (int d = 0; d < 8; ++d) {
@@ -165,14 +173,15 @@ __device__ __forceinline__ void emit_p2p_block(bool accept, int64_t i, int32_t h
   }
   __syncthreads();
   const unsigned int words = s_off[8] * 3u;
+  const unsigned long long slice0 = (unsigned long long)(pv.parity * pv.world + pv.rank) * pv.slice_cap;
   for (unsigned int w = threadIdx.x; w < words; w += BS) {
     const unsigned int rec = w / 3u, part = w - rec * 3u;
     int d = 0;
 #pragma unroll
     for (int k = 1; k < 8; ++k) d += (k < pv.world && rec >= s_off[k]) ? 1 : 0;
     const unsigned long long pos = s_base[d] + (rec - s_off[d]);
-    if (pos < pv.capacity) {
-      reinterpret_cast<uint4*>(pv.recs[d] + pos)[part] = s_rec[w];
+    if (pos < pv.slice_cap) {
+      reinterpret_cast<uint4*>(pv.recs[d] + slice0 + pos)[part] = s_rec[w];
     } else if (part == 0u) {
       atomicAdd(overflow, 1ull);
     }

@@ -65,12 +65,18 @@ struct fc_agg {
   unsigned long long* h_pinned = nullptr;  // pinned landing zone of the counters
   // fused emit + exchange over peer memory
   bool p2p_enabled = false;
+  bool p2p_local = false;  // peers are contexts of this process on this device (tests): the barrier publishes, never waits
+  bool p2p_ipc = false;    // the peer pointers were opened with cudaIpcOpenMemHandle (to be closed)
+  bool p2p_open = false;   // records were sent since the last barrier: the owners cannot reduce yet
   int p2p_world = 1, p2p_rank = 0;
-  int64_t p2p_capacity = 0, p2p_min_capacity = 0;
+  int64_t p2p_capacity = 0;   // records this rank can receive per step (its buffer holds two such halves)
+  int64_t p2p_slice_cap = 0;  // records per (parity, source) slice = min capacity / world
   void* p2p_recs[8] = {};
   void* p2p_cnt[8] = {};
-  unsigned long long barrier_epoch = 0;  // fc_p2p_barrier calls so far (the same on every rank)
+  unsigned long long barrier_epoch = 0;  // fc_p2p_barrier calls so far (the same on every rank); its low bit = parity
+  double p2p_timeout_s = 60.0;           // how long the barrier kernel waits for a peer before it gives up
   fc_dbuf scratch[8];
+  fc_dbuf p2p_compact;  // sort-based path, multi-GPU: the slices of a step as one run
   fc_dbuf cub_tmp;
   fc_dbuf counters;     // small device counters
   fc_dbuf htab[3];      // sort-based path: hash sets for the distinct counts (reads, fragment names)
@@ -94,6 +100,7 @@ struct fc_ctx {
   cudaStream_t own_stream2 = nullptr; // second lane of the chunked host-buffer path
   cudaEvent_t ev_chunk[2] = {nullptr, nullptr};
   fc_dbuf host_path[16];              // staging for fc_scan_host / fc_batch_host
+  fc_dbuf tie_off;                    // fc_batch_ties_host: exclusive prefix sums of n_hits
   int64_t launches = 0;
   int sm_count = 148;
   // device state of the last fc_batch_host call (two-step batches)
@@ -109,7 +116,7 @@ int fc_agg_reserve_records(fc_ctx* ctx, int64_t extra, cudaStream_t st);  // roo
 int fc_agg_emit_begin(fc_ctx* ctx, int64_t n, cudaStream_t st, fc::EmitArgs* e);  // room + where the records go
 void fc_agg_emit_end(fc_ctx* ctx, int64_t n, uint64_t idx_base, bool explicit_idx);
 int fc_agg_p2p_begin(fc_ctx* ctx, fc::P2PView* pv, unsigned long long** overflow);  // the peer view of the context
-void fc_agg_p2p_end(fc_ctx* ctx);
+void fc_agg_p2p_end(fc_ctx* ctx, uint64_t idx_base, int64_t n);
 
 #define FC_CUDA(ctx, call)                                                                         \
   do {                                                                                             \

@@ -280,10 +280,13 @@ extern "C" int fc_scan_emit_p2p(fc_ctx* ctx, const fc_scan_params* p, const fc_p
   fc::P2PView pv;
   unsigned long long* overflow = nullptr;
   if ((rc = fc_agg_p2p_begin(ctx, &pv, &overflow))) return rc;
-  if (pr->n == 0) return FC_OK;
+  if (pr->n == 0) {
+    fc_agg_p2p_end(ctx, idx_base, 0);  // an empty shard still OWNS keys: peers may have written into this rank's buffer
+    return FC_OK;
+  }
   fc::EmitArgs e{d_wden, d_q_a, d_q_b, d_read_hash, d_qname_hash, idx_base, nullptr, nullptr, nullptr};
   if ((rc = scan_launch(ctx, p, pr, d_out, &e, (cudaStream_t)stream, &pv, overflow))) return rc;
-  fc_agg_p2p_end(ctx);
+  fc_agg_p2p_end(ctx, idx_base, pr->n);
   return FC_OK;
 }
 
@@ -378,6 +381,7 @@ extern "C" int fc_batch_host_idx(fc_ctx* ctx, const fc_scan_params* p, int64_t n
                                  const uint64_t* h_qname_hash, const uint64_t* h_idx, uint64_t idx_base, int32_t emit,
                                  fc_hit* h_out) {
   if (!ctx || !p || n < 0) return FC_E_ARG;
+  ctx->last_n = 0;  // the retained batch is only valid after a call that succeeded
   if (n == 0) return FC_OK;
   FC_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->own_stream;
@@ -391,10 +395,8 @@ extern "C" int fc_batch_host_idx(fc_ctx* ctx, const fc_scan_params* p, int64_t n
                       sizeof(fc_hit) * N, N, 2 * N, 2 * N, 8 * N, 8 * N};
   for (int k = 0; k < 14; ++k) FC_CUDA(ctx, ctx->host_path[k].reserve(sizes[k], st, false, 0));
   FC_CUDA(ctx, ctx->host_path[14].reserve(sizes[6], st, false, 0));
-  void** d = nullptr;
   void* dp[14];
   for (int k = 0; k < 14; ++k) dp[k] = ctx->host_path[k].p;
-  (void)d;
   const void* src[14] = {h_chrom, h_a_start, h_b_end, h_l, h_flags, h_ascii, nullptr, nullptr, nullptr,
                          h_wden, h_q_a, h_q_b, h_read_hash, h_qname_hash};
   for (int k = 0; k < 14; ++k) {
@@ -464,8 +466,6 @@ extern "C" int fc_batch_emit_host(fc_ctx* ctx, const uint8_t* h_mask, uint64_t i
     d_mask = (uint8_t*)ctx->host_path[15].p + 8 * (size_t)n;
     FC_CUDA(ctx, cudaMemcpyAsync(d_mask, h_mask, (size_t)n, cudaMemcpyHostToDevice, st));
   }
-  void** dp = nullptr;
-  (void)dp;
   int rc;
   if (d_idx)
     rc = fc_agg_emit_idx(ctx, n, (const fc_hit*)ctx->host_path[8].p, ctx->last_pairs.d_chrom, ctx->last_pairs.d_flags,
@@ -490,11 +490,12 @@ extern "C" int fc_batch_ties_host(fc_ctx* ctx, const fc_scan_params* p, const in
   const int64_t n = ctx->last_n;
   const int64_t total = h_tie_off[n];
   if (total <= 0) return FC_OK;
-  FC_CUDA(ctx, ctx->host_path[15].reserve((size_t)(n + 1) * 8, st, false, 0));
+  // (the tie offsets have their own buffer: host_path[15] may hold the explicit stream positions of the batch)
+  FC_CUDA(ctx, ctx->tie_off.reserve((size_t)(n + 1) * 8, st, false, 0));
   fc_dbuf& tb = ctx->agg.scratch[0];
   FC_CUDA(ctx, tb.reserve((size_t)total * sizeof(fc_hit), st, false, 0));
-  FC_CUDA(ctx, cudaMemcpyAsync(ctx->host_path[15].p, h_tie_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
-  int rc = fc_scan_ties(ctx, p, &ctx->last_pairs, (const fc_hit*)ctx->host_path[8].p, (const int64_t*)ctx->host_path[15].p,
+  FC_CUDA(ctx, cudaMemcpyAsync(ctx->tie_off.p, h_tie_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+  int rc = fc_scan_ties(ctx, p, &ctx->last_pairs, (const fc_hit*)ctx->host_path[8].p, (const int64_t*)ctx->tie_off.p,
                         (fc_hit*)tb.p, st);
   if (rc) return rc;
   FC_CUDA(ctx, cudaMemcpyAsync(h_ties, tb.p, (size_t)total * sizeof(fc_hit), cudaMemcpyDeviceToHost, st));
@@ -511,6 +512,7 @@ extern "C" int fc_batch_host_planes(fc_ctx* ctx, const fc_scan_params* p, int64_
                                     const uint64_t* h_read_hash, const uint64_t* h_qname_hash, const uint64_t* h_idx,
                                     uint64_t idx_base, int32_t emit, fc_hit* h_out) {
   if (!ctx || !p || n < 0 || n_words < 1 || plane_stride < n) return FC_E_ARG;
+  ctx->last_n = 0;  // the retained batch is only valid after a call that succeeded
   if (n == 0) return FC_OK;
   FC_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->own_stream;

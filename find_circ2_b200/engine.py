@@ -249,6 +249,21 @@ class Engine:
         capacities = np.ascontiguousarray(capacities, dtype=np.int64)
         self._check(self.lib.fc_p2p_connect(self.h, world, rank, handles.ctypes.data, capacities.ctypes.data))
 
+    def p2p_export_local(self, capacity_records: int):
+        """(record buffer, counter block) device pointers for contexts of the same process (fc_p2p_export_local)"""
+        recs, cnt = C.c_void_p(), C.c_void_p()
+        self._check(self.lib.fc_p2p_export_local(self.h, int(capacity_records), C.byref(recs), C.byref(cnt)))
+        return recs.value, cnt.value
+
+    def p2p_connect_local(self, world: int, rank: int, recs, counters, capacities):
+        r = (C.c_void_p * world)(*recs)
+        c = (C.c_void_p * world)(*counters)
+        capacities = np.ascontiguousarray(capacities, dtype=np.int64)
+        self._check(self.lib.fc_p2p_connect_local(self.h, world, rank, r, c, capacities.ctypes.data))
+
+    def p2p_set_timeout(self, seconds: float):
+        self._check(self.lib.fc_p2p_set_timeout(self.h, float(seconds)))
+
     def agg_emit_p2p(self, n, d_hits, d_chrom, d_flags, d_wden, d_q_a, d_q_b, d_read_hash, d_qname_hash, idx_base, stream=0,
                      d_mask=None):
         self._check(self.lib.fc_agg_emit_p2p(self.h, n, ptr(d_hits), ptr(d_chrom), ptr(d_flags), ptr(d_wden), ptr(d_q_a),

@@ -99,8 +99,8 @@ def p2p_setup(eng, dist, dev, capacity_records: int) -> bool:
 
 def stream_barrier(dist, dev, eng=None, stream=0, _cache={}):
     """a barrier that orders the STREAMS of all ranks without blocking the host.  With an engine whose peers are connected
-    (p2p_setup) it is the library's own kernel over peer memory (fc_p2p_barrier, a few microseconds); otherwise a
-    one-element NCCL all-reduce"""
+    (p2p_setup) it is the library's own kernel over peer memory (fc_p2p_barrier, a few microseconds; it also ENDS a step of
+    the peer emit: exactly one per step, see include/findcirc_b200.h); otherwise a one-element NCCL all-reduce"""
     if eng is not None:
         eng.p2p_barrier(stream)
         return

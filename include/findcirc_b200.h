@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FC_ABI_VERSION 1
+#define FC_ABI_VERSION 2
 
 /* error codes */
 #define FC_OK 0
@@ -246,13 +246,25 @@ int fc_agg_fetch(fc_ctx* ctx, int64_t n, fc_junction* h_out); /* sorted by first
 const fc_junction* fc_agg_junctions(fc_ctx* ctx);             /* device pointer, after finalize */
 
 /* ------------------------------------------------------------------ fused emit + exchange over peer memory (one node)
- * Every rank exports its record buffer and counter (fc_p2p_export -> 128 handle bytes, exchanged by the host with any
- * collective), opens its peers' (fc_p2p_connect) and from then on fc_agg_emit_p2p writes each record directly into the
- * buffer of the rank that owns its junction key (hash(key) % world) over NVLink.  Per step the host issues
- * fc_agg_reset_async, a stream-ordered barrier, the scan, fc_agg_emit_p2p, a second barrier and fc_agg_finalize. */
-int fc_p2p_export(fc_ctx* ctx, int64_t capacity_records, uint8_t* h_handles /* 128 bytes */);
+ * The multi-GPU form of SpliceSiteStorage.add (find_circ.py:681-690): junction keys are owned by rank hash(key) % world.
+ * Every rank exports its record buffer and counter block (fc_p2p_export -> 128 handle bytes, exchanged by the host with any
+ * collective), opens its peers' (fc_p2p_connect) and from then on fc_scan_emit_p2p / fc_agg_emit_p2p write each record
+ * directly into the owner's buffer over NVLink: the buffer of rank d is cut into 2 x world slices of capacity/world
+ * records, slice (parity, s) receives what source s sends in the steps of that parity, so a source allocates slots with
+ * counters in its OWN memory and no atomic crosses the wire.  One step =
+ *     fc_agg_reset_async, [fc_scan_emit_p2p | fc_agg_emit_p2p]*, fc_p2p_barrier, fc_agg_finalize
+ * with exactly one barrier per step on every rank (it publishes the slice counts and orders the stores before the owners'
+ * reduce; the two parities make a barrier before the next step's stores unnecessary).  fc_agg_finalize before the barrier
+ * fails with FC_E_STATE; a slice that overflows fails the step with FC_E_NOMEM on the source and on the owner. */
+int fc_p2p_export(fc_ctx* ctx, int64_t capacity_records /* per step and rank */, uint8_t* h_handles /* 128 bytes */);
 int fc_p2p_connect(fc_ctx* ctx, int32_t world, int32_t rank, const uint8_t* h_all_handles /* world x 128 */,
                    const int64_t* h_capacities /* world */);
+/* the same between contexts of ONE process on ONE device (how the single-GPU test suite drives the peer kernels): plain
+ * device pointers instead of IPC handles; the barrier of such a context publishes and never waits -- the caller runs the
+ * ranks one after the other on one stream (all emits, then all barriers, then the finalizes). */
+int fc_p2p_export_local(fc_ctx* ctx, int64_t capacity_records, void** out_recs, void** out_counters);
+int fc_p2p_connect_local(fc_ctx* ctx, int32_t world, int32_t rank, void* const* recs, void* const* counters,
+                         const int64_t* h_capacities);
 int fc_agg_emit_p2p(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, const int32_t* d_chrom, const uint8_t* d_flags,
                     const uint8_t* d_wden, const int16_t* d_q_a, const int16_t* d_q_b, const uint64_t* d_read_hash,
                     const uint64_t* d_qname_hash, const uint8_t* d_mask, uint64_t idx_base, void* stream);
@@ -260,11 +272,13 @@ int fc_agg_emit_p2p(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, const int32_t*
 int fc_scan_emit_p2p(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs* pairs, fc_hit* d_out, const uint8_t* d_wden,
                      const int16_t* d_q_a, const int16_t* d_q_b, const uint64_t* d_read_hash, const uint64_t* d_qname_hash,
                      uint64_t idx_base, void* stream);
-/* Stream-ordered barrier of all connected ranks over peer memory (one small kernel: every rank bumps an arrival word on
- * every rank and waits for its own).  Orders the record stores of fc_agg_emit_p2p before the owners' fc_agg_finalize and
- * the owners' counter resets before the next emit.  Every rank must call it the same number of times.  A rank that waits
- * ~2 s gives up; the next fc_agg_finalize then fails with FC_E_STATE. */
+/* Stream-ordered barrier of all connected ranks over peer memory (one small kernel: every rank publishes its slice counts,
+ * bumps an arrival word on every rank and waits for its own).  Every rank must call it exactly once per step.  A rank
+ * that has waited longer than the timeout (default 60 s, fc_p2p_set_timeout; the wait is stream-ordered behind the
+ * rank's own work, so the timeout must cover the load imbalance between ranks, host ingest included) gives up: the
+ * next fc_agg_finalize then fails with FC_E_STATE and the results of that step are invalid. */
 int fc_p2p_barrier(fc_ctx* ctx, void* stream);
+int fc_p2p_set_timeout(fc_ctx* ctx, double seconds);
 int fc_agg_reset_async(fc_ctx* ctx, void* stream);
 
 /* ------------------------------------------------------------------ native SAM ingest (host code)

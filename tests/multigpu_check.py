@@ -74,19 +74,17 @@ def main():
             print("P2P (CUDA IPC) not available on this box -- only the NCCL path was checked")
         ta = tb
     else:
-        for it in range(3):  # repeated steps: the barriers must keep the ranks apart
+        for it in range(4):  # repeated steps: the two halves of the peer buffers alternate, one barrier per step
             e.agg_reset_async(0)
             if it > 0:  # declared idx range: discovery rank from flags; undeclared (it == 0): from a sort
                 e.agg_set_idx_range(0, world * n_cap)
-            # the library's peer-memory barrier, and (last round) the NCCL one-element all-reduce
-            parallel.stream_barrier(dist, dev, e if it < 2 else None, 0)
-            if it == 1:  # scan and peer emit in one kernel
+            if it % 2 == 1:  # scan and peer emit in one kernel
                 hits2 = torch.zeros_like(hits)
                 e.scan_emit_p2p(pairs, hits2, *pay, idx_base, 0)
                 assert torch.equal(hits, hits2)
             else:
                 e.agg_emit_p2p(n, hits, d_chrom, d_fl, *pay, idx_base, 0)
-            parallel.stream_barrier(dist, dev, e if it < 2 else None, 0)
+            parallel.stream_barrier(dist, dev, e, 0)  # ends the step: slice counts published, stores ordered
             ta = table()
 
     # (c) union on rank 0: gather every rank's hits + payload and aggregate alone

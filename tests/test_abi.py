@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     assert set(declared) == bound, (set(declared) ^ bound)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.fc_abi_version() == 1
+    assert lib.fc_abi_version() == 2
 
 
 def test_struct_sizes_match_header():
