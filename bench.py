@@ -2,32 +2,34 @@
 """
 bench.py -- anchor pairs / second through the breakpoint scan + junction merge (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]          this repo's CUDA path
-  python bench.py --impl reference ...                          the reference algorithm on the host cores (oracle port)
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|3|4|5]     this repo's CUDA path
+  python bench.py --impl reference ...                                       the reference algorithm on the host cores (oracle port)
 
-A step is one pass of the hot path over one batch: config 2 of BASELINE.json -- synthetic 100 Mb genome
-(20 x 5 Mb, 0.5 % N), 10 000 planted circRNAs, 1 M anchor pairs from 100-nt reads (a=20, m=2, d=2), seeds fixed.
-  value   pairs/s with the batch already resident in HBM: one step = four launches -- the scan kernel that writes the
-          junction records on the way (fc_scan_emit), the one-pass aggregation kernel and the two small kernels that rank
-          and convert the junctions (fc_agg_finalize)
-  e2e     the same through the host-buffer C-ABI call fc_batch_host + fc_agg_finalize + fc_agg_fetch:
-          pinned host SoA in, per-pair hits and the junction table out, copies inside the timed region
-  roofline  the kernel with the longest launch in the step, roofline_other the second one.  scan kernel: 82
-            algorithmic bytes per pair / CUDA-event time of the kernel; aggregation kernel: 48 B per
-            record + 64 B per junction / the library's own CUDA events around the kernel (fc_agg_get_timing)
-  cpu_baseline  oracle (python restatement of find_circ.py, one numpy compare per split position) on a bounded sample
-L2 is flushed (256 MiB memset) before every timed step; per-step CUDA events are summed.
-Experiments only: FC_BENCH_ZIPF=<s> changes the popularity law of the planted junctions (default 1.0, the top junction
-holds 9 % of the records; 0 = uniform); FC_AGG_TIMING=1 prints the stage times of every fc_agg_finalize on stderr.
-Multi-GPU: pairs are sharded by rank (weak scaling: every rank scans its own 1 M pairs), junction records are
-hash-partitioned by key and written straight into the owner's buffer over NVLink (fallback: one all-to-all), every
-rank reduces its keys.
+Default workload = BASELINE.json configs[2], the configuration the metric's "1/2/4/8 B200" is quoted on: hg19-sized synthetic
+genome (3.1 Gb, replicated per GPU), 100k planted circRNAs, 50 M anchor pairs from 2x100-nt mate pairs in the WHOLE job,
+sharded over the ranks by contiguous ranges of the input stream (strong scaling).  A step is one pass of the hot path over
+the rank's shard, resident in HBM as one batch.
+  value     pairs/s, batch resident in HBM: scan kernel that writes the junction records on the way (N>1: straight into the
+            owner ranks' buffers over NVLink), one barrier, aggregation (accumulate, rank, finish)
+  e2e       the same through the host-buffer C-ABI call: pinned host SoA in, per-pair hits and the junction table out,
+            copies inside the timed region
+  roofline  the kernel with the longest launch in the step, roofline_other the second one.  scan: 82 (l=64) / 119 (l=114)
+            algorithmic bytes per pair / CUDA-event time of the scan+emit kernel; aggregation: 48 B per record +
+            64 B per junction / the library's own CUDA events around the accumulate kernel (fc_agg_get_timing)
+  parity_checked  N=1: the whole drop-in (both ingest paths) on a prefix of the same workload against the oracle, all five
+            outputs; N>1: the owners' junction tables of a peer-memory step, gathered to rank 0, against one context
+            aggregating the union
+  cpu_baseline    oracle (python restatement of find_circ.py, one numpy compare per split position) on a bounded prefix
+  other_configs   (N=1) configs[1], configs[3] at 1/2/3 % errors and the per-GPU slice of configs[4], device-resident lines
+Inputs are far larger than L2 (config 3: 3.8 GB of batch columns, 3.2 GB of genome tiles); configs whose batch fits L2 are
+flushed (256 MiB memset) before every timed step.  Workloads: bench_workload.py (seeded, device independent).
 """
 import argparse
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -36,46 +38,12 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-ASIZE, MARGIN, MAXDIST = 20, 2, 2
-READ_LEN = 100
-BYTES_PER_PAIR = 16 + (READ_LEN - 2 * (ASIZE - MARGIN) + 3) // 4 + 2 * ((READ_LEN - 2 * (ASIZE - MARGIN) + 2 + 3) // 4) + 16  # 82
+METRIC = "anchor pairs/sec (breakpoint scan + junction merge)"
 
 
-def workload(rank, n_pairs, genome_mb, n_circ):
-    from find_circ2_b200 import synth
-
-    per = genome_mb * 1000000 // 20
-    g = synth.make_genome([per] * 20, seed=1, n_frac=0.005, n_run=(50, 5000), soft_frac=0.0)
-    J = synth.plant_junctions(g, n_circ, max(n_circ // 20, 1), seed=2, span=(200, 50000), margin=400)
-    t = synth.make_pairs(g, J, n_pairs, read_len=READ_LEN, asize=ASIZE, seed=3 + 1000 * rank, error_rate=0.005, zipf=float(os.environ.get("FC_BENCH_ZIPF", "1.0")),
-                         frac_decoy=0.10, frac_nonuniq=0.02, frac_edge=0.01)
-    return g, J, t
-
-
-def soa_from_table(t, eng):
-    """what ingest produces for 2-segment reads (find_circ.py:1058-1140, 821-848): scan inputs + aggregation payload"""
-    eff = ASIZE - MARGIN
-    R = t.read_len
-    uniq_a = np.where(t.xs_a >= 0, t.as_a - t.xs_a, t.as_a)
-    uniq_b = np.where(t.xs_b >= 0, t.as_b - t.xs_b, t.as_b)
-    keep = np.minimum(uniq_a, uniq_b) >= 2  # is_uniq filter happens before the scan (find_circ.py:1299-1301)
-    idx = np.nonzero(keep)[0]
-    n = len(idx)
-    soa = dict(
-        chrom=t.chrom[idx].astype(np.int32),
-        a_start=(t.a_pos[idx] + eff).astype(np.int32),
-        b_end=(t.b_pos[idx] + t.b_len[idx] - eff).astype(np.int32),
-        l=np.full(n, R - 2 * eff, dtype=np.int32),
-        flags=(((t.b_pos[idx] - (t.a_pos[idx] + t.a_len[idx])) < 0).astype(np.uint8) | (t.reverse[idx].astype(np.uint8) << 1)),
-        internal=np.ascontiguousarray(t.reads[idx, eff : R - eff]),
-        wden=np.ones(n, dtype=np.uint8),
-        q_a=(t.as_a[idx] - np.maximum(t.xs_a[idx], 0)).astype(np.int16),
-        q_b=(t.as_b[idx] - np.maximum(t.xs_b[idx], 0)).astype(np.int16),
-    )
-    soa["read_hash"] = eng.hash_reads(t.reads[idx], np.full(n, R, dtype=np.int32))
-    names = t.name_id[idx].astype(np.uint64)
-    soa["qname_hash"] = (names * np.uint64(0x9E3779B97F4A7C15)) ^ (names >> np.uint64(7))
-    return soa, idx
+def bytes_per_pair(cfg):
+    l = cfg.read_len - 2 * (cfg.asize - cfg.margin)
+    return 16 + (l + 3) // 4 + 2 * ((l + 2 + 3) // 4) + 16  # 82 at l = 64, 119 at l = 114
 
 
 class ClockSampler(threading.Thread):
@@ -95,7 +63,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def summary(self):
         sm, mx, reasons = [], 0, set()
@@ -112,22 +80,6 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def ascii_to_planes(internal, n_words):
-    """[n, L] ASCII -> (lo, hi, n) bit planes, word-major [n_words * n] uint32 (the layout of fc_pairs.rlo/rhi/rn)"""
-    n, L = internal.shape
-    code = np.full(internal.shape, 4, dtype=np.uint8)
-    up = internal & 0xDF
-    for k, ch in enumerate(b"ACGT"):
-        code[up == ch] = k
-    out = []
-    for plane in ((code & 1) & (code < 4), ((code >> 1) & 1) & (code < 4), code == 4):
-        bits = np.zeros((n, n_words * 32), dtype=np.uint8)
-        bits[:, :L] = plane
-        words = np.packbits(bits, axis=1, bitorder="little").view(np.uint32)  # [n, n_words]
-        out.append(np.ascontiguousarray(words.T).reshape(-1))
-    return out
-
-
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -138,113 +90,107 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-# ------------------------------------------------------------------------------------------------ CPU side
-def oracle_records(g, t, idx):
-    """SAM records (decoded, untimed) for the sample rows"""
+# ------------------------------------------------------------------------------------------------ CPU side (oracle)
+def sample_sam(spec, cols):
+    """SAM text lines (header first) of a prefix of the workload: BWA-MEM style two-segment records, mates flagged"""
+    import bench_workload as W
     from find_circ2_b200 import synth
-    from oracle import find_circ_oracle as O
 
-    lines = []
-    for i in idx:
-        lines += synth.bwa_records_for_pair(g, t, int(i), "r%d" % int(t.name_id[i]))
-    names, recs = O.read_sam(synth.sam_header(g).splitlines(True) + lines)
-    return names, list(recs)
+    pt = W.pair_table(cols)
+
+    class G(object):
+        names = spec.names
+        sizes = [int(x) for x in spec.sizes]
+
+    lines = synth.sam_header(G).splitlines(True)
+    paired = spec.cfg.paired
+    for i in range(len(pt)):
+        flag = (0x41 if i % 2 == 0 else 0x81) if paired else 0
+        lines += synth.bwa_records_for_pair(G, pt, i, "r%d" % int(pt.name_id[i]), base_flag=flag)
+    return lines
 
 
-def oracle_genome(g):
+def oracle_genome(spec, cols):
+    """the oracle's genome object over the stretches of the (never materialised) genome that the sample touches"""
+    import bench_workload as W
     from oracle import find_circ_oracle as O
 
     og = O.Genome.__new__(O.Genome)
-    og.names = list(g.names)
-    og.seqs = {n: s.tobytes().decode() for n, s in zip(g.names, g.seqs)}
+    og.names = list(spec.names)
+    og.seqs = W.sparse_genome(spec, cols)
     return og
 
 
-_CPU_GENOME = None  # (oracle genome, @SQ names): inherited by forked workers instead of being pickled
+_CPU_STATE = None  # (oracle genome, @SQ names, options): inherited by forked workers instead of being pickled
 
 
 def _cpu_shard(recs):
     from oracle import find_circ_oracle as O
 
-    og, names = _CPU_GENOME
+    og, names, opt = _CPU_STATE
     t0 = time.perf_counter()
-    r = O.Run(og, names, O.Options(asize=ASIZE, margin=MARGIN, maxdist=MAXDIST))
+    r = O.Run(og, names, opt)
     r.process(recs)
-    r.outputs()
-    return time.perf_counter() - t0, r.n_spans
+    out = r.outputs()
+    return time.perf_counter() - t0, out
 
 
-def cpu_baseline(g, t, n_sample, procs=1):
-    """scan + aggregation of the oracle on n_sample pairs; SAM decoding is done before the clock starts"""
-    global _CPU_GENOME
-    idx = np.arange(min(n_sample, len(t)))
-    names, recs = oracle_records(g, t, idx)
-    _CPU_GENOME = (oracle_genome(g), names)
+def _cpu_shard_time(recs):
+    return _cpu_shard(recs)[0]
+
+
+def oracle_options(cfg):
+    from oracle import find_circ_oracle as O
+
+    return O.Options(asize=cfg.asize, margin=cfg.margin, maxdist=cfg.maxdist, min_uniq_qual=cfg.min_uniq, name="bench")
+
+
+def cpu_run(spec, cols, lines, procs=1):
+    """scan + aggregation of the oracle on the sample; SAM decoding and the genome stretches are ready before the clock starts.
+    Returns (seconds, outputs of the single-process run or None)"""
+    global _CPU_STATE
+    from oracle import find_circ_oracle as O
+
+    names, recs = O.read_sam(lines)
+    recs = list(recs)
+    _CPU_STATE = (oracle_genome(spec, cols), names, oracle_options(spec.cfg))
     if procs <= 1:
-        dt, spans = _cpu_shard(recs)
-        return len(idx) / dt, dt
+        return _cpu_shard(recs)
     import multiprocessing as mp
 
-    # shard by fragment (records of one read stay together: 2 records per read here)
-    per = (len(recs) // 2 + procs - 1) // procs * 2
-    shards = [recs[k : k + per] for k in range(0, len(recs), per)]
+    # shard by fragment: 2 records per read, 4 per mate pair -- cut on multiples of 4
+    per = (len(recs) // 4 + procs - 1) // procs * 4
+    shards = [recs[k: k + per] for k in range(0, len(recs), per)]
     with mp.get_context("fork").Pool(procs) as pool:
         pool.map(len, shards[:1])  # workers are up before the clock starts
         t0 = time.perf_counter()
-        pool.map(_cpu_shard, shards, chunksize=1)
+        pool.map(_cpu_shard_time, shards, chunksize=1)
         dt = time.perf_counter() - t0
-    return len(idx) / dt, dt
-
-
-def host_ingest(g, t, n_sample, eng):
-    """host ingest reported separately (north_star): SAM text -> fragments -> struct-of-arrays batches in the python host of
-    the drop-in (find_circ2_b200/pipeline.py), measured on a sample by running the whole CLI path and subtracting the time
-    spent inside GPU calls"""
-    import tempfile
-
-    from find_circ2_b200 import cli, synth
-
-    idx = np.arange(min(n_sample, len(t)))
-    with tempfile.TemporaryDirectory() as tmp:
-        sam = os.path.join(tmp, "sample.sam")
-        with open(sam, "w") as fh:
-            fh.write(synth.sam_header(g))
-            for i in idx:
-                fh.writelines(synth.bwa_records_for_pair(g, t, int(i), "r%d" % int(t.name_id[i])))
-        res = {}
-        for tag, native in (("python", False), ("native", True)):
-            opt = cli.parse_args(["-G", "unused", "-a", str(ASIZE), "-n", "bench"])[0]
-            out = cli.run_to_strings(opt, sam, engine=eng, native=native)
-            host_s = out["seconds_total"] - out["seconds_gpu_calls"]
-            res[tag] = {"pairs_per_s": len(idx) / host_s, "seconds_host": host_s, "seconds_gpu_calls": out["seconds_gpu_calls"]}
-    return {"value": res["native"]["pairs_per_s"], "unit": "pairs/s",
-            "kind": "SAM text -> fragments -> SoA batches -> writers on the host, GPU calls excluded; native = csrc/ingest.cu (C++), python = pipeline.py",
-            "sample": "%d reads" % len(idx), "native": res["native"], "python": res["python"]}
+    return dt, None
 
 
 def run_reference(args):
+    import bench_workload as W
+
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cfg = W.configs()[args.config]
     cores = os.cpu_count() or 1
-    g, J, t = workload(0, max(args.cpu_sample * cores, 1000), args.genome_mb, args.n_circ)
-    n_sample = len(t)
-    vals = []
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        cpu_baseline(g, t, min(2000, n_sample), 1)
-    for _ in range(args.steps):
-        v, dt = cpu_baseline(g, t, n_sample, cores)
-        vals.append((v, dt))
-    v = float(np.mean([x[0] for x in vals]))
-    ms = float(np.mean([x[1] for x in vals])) * 1e3
+    spec = W.Spec(cfg)
+    n_sample = max(args.cpu_sample * cores, 2000) // 4 * 4
+    cols = W.make_pairs(spec, 0, n_sample, "cpu")
+    lines = sample_sam(spec, cols)
+    if args.warmup:
+        cpu_run(spec, cols, lines[: 2000 + len(spec.names) + 3], 1)
+    secs = [cpu_run(spec, cols, lines, cores)[0] for _ in range(args.steps)]
+    v = float(np.mean([n_sample / s for s in secs]))
     line = {
-        "impl": "reference", "metric": "anchor pairs/sec (breakpoint scan + junction merge)", "value": v, "unit": "pairs/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "configs[1]: synthetic %d Mb genome, %d planted circRNAs, 100-nt reads, a=20 m=2 d=2" % (args.genome_mb, args.n_circ),
-                   "sample_pairs_per_step": n_sample},
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": cfg.scaling,
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": {"workload": cfg.workload},
         "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
-                         "sample": "%d pairs per step, sharded %d ways by read with multiprocessing; SAM decode untimed" % (n_sample, cores)},
+                         "sample": "the first %d pairs of the workload per step, sharded %d ways by fragment with multiprocessing; SAM decode untimed" % (n_sample, cores)},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -252,9 +198,408 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU side
+class Shard(object):
+    """one rank's part of a workload, resident on the device in the layout the library scans"""
+
+    def __init__(self, eng, spec, i0, i1, dev, flat, error_rate=None):
+        import torch
+
+        import bench_workload as W
+
+        cfg = spec.cfg
+        cols = W.make_pairs(spec, i0, i1, dev, flat=flat, error_rate=error_rate)
+        s = W.soa(cols, cfg)
+        del cols
+        self.n = n = int(s["row"].numel())
+        self.n_in = i1 - i0
+        self.max_l = int(s["l"].max().item()) if n else 0
+        self.n_words = max(1, (self.max_l + 31) // 32)
+        self.stride = int(s["internal"].shape[1])
+        stream = torch.cuda.current_stream().cuda_stream
+        s["read_hash"] = torch.empty(n, dtype=torch.int64, device=dev)
+        eng.hash_reads_device(s["reads"], cfg.read_len, s["read_hash"], stream)
+        nm = s["name_id"]
+        s["qname_hash"] = (nm * (0x9E3779B97F4A7C15 - (1 << 64))) ^ ((nm >> 7) & ((1 << 57) - 1))
+        torch.cuda.synchronize()
+        del s["reads"], s["name_id"], s["row"]
+        self.planes = torch.zeros(3 * self.n_words * n, dtype=torch.int32, device=dev)
+        eng.pack_reads(s["internal"], self.stride, s["l"], self.n_words, self.planes, s["flags"], stream)
+        torch.cuda.synchronize()
+        self.d = s
+        self.hits = torch.zeros(n * 4, dtype=torch.int32, device=dev)
+        self.pairs = self._pairs(eng, n)
+        self.pay = (s["wden"], s["q_a"], s["q_b"], s["read_hash"], s["qname_hash"])
+
+    def _pairs(self, eng, m):
+        """fc_pairs over the first m rows (the planes keep the stride of the whole shard)"""
+        from find_circ2_b200._lib import Pairs, ptr
+
+        d = self.d
+        base, step = ptr(self.planes), 4 * self.n * self.n_words
+        return Pairs(m, ptr(d["chrom"]), ptr(d["a_start"]), ptr(d["b_end"]), ptr(d["l"]), ptr(d["flags"]), base, base + step,
+                     base + 2 * step, self.n_words, self.max_l, self.n)
+
+
+def dropin_parity(eng, spec, cfg, n_sample):
+    """the whole drop-in (SAM text -> native / python ingest -> GPU -> five outputs) on a prefix of the workload against the
+    oracle; also what `ingest` (host decoding rate) and `cpu_baseline` are taken from"""
+    import bench_workload as W
+    from find_circ2_b200 import cli
+    from oracle import find_circ_oracle as O
+
+    cols = W.make_pairs(spec, 0, n_sample, "cpu")
+    lines = sample_sam(spec, cols)
+    cpu_s, want = cpu_run(spec, cols, lines, 1)
+    res = {}
+    ok = True
+    with tempfile.TemporaryDirectory() as tmp:
+        sam = os.path.join(tmp, "sample.sam")
+        with open(sam, "w") as fh:
+            fh.writelines(lines)
+        for tag, native in (("python", False), ("native", True)):
+            opt = cli.parse_args(["-G", "unused", "-a", str(cfg.asize), "-m", str(cfg.margin), "-d", str(cfg.maxdist), "-n", "bench",
+                                  "--min-uniq-qual", str(cfg.min_uniq)])[0]
+            out = cli.run_to_strings(opt, sam, engine=eng, native=native)
+            same = (O.canonical_bed(out["circ"]) == O.canonical_bed(want.circ_bed) and O.canonical_bed(out["lin"]) == O.canonical_bed(want.lin_bed)
+                    and out["reads"] == want.reads_fastq and O.canonical_multi(out["multi"]) == O.canonical_multi(want.multi_events)
+                    and out["counters"] == want.counters)
+            ok = ok and same
+            host_s = out["seconds_total"] - out["seconds_gpu_calls"]
+            res[tag] = {"pairs_per_s": n_sample / host_s, "seconds_host": host_s, "seconds_gpu_calls": out["seconds_gpu_calls"], "equals_oracle": same}
+    n_rows = len(want.circ_bed.splitlines()) + len(want.lin_bed.splitlines()) - 2
+    parity = {"ok": ok and n_rows > 0, "against": "oracle (oracle/find_circ_oracle.py), all five outputs of the drop-in, native and python ingest",
+              "pairs": n_sample, "junction_rows": n_rows}
+    ingest = {"value": res["native"]["pairs_per_s"], "unit": "pairs/s",
+              "kind": "SAM text -> fragments -> SoA batches -> writers on the host, GPU calls excluded; native = csrc/ingest.cu (C++), python = pipeline.py",
+              "sample": "%d pairs" % n_sample, "native": res["native"], "python": res["python"]}
+    cpu = {"value": n_sample / cpu_s, "unit": "pairs/s", "cores": 1, "kind": "port",
+           "sample": "first %d pairs of the same workload, oracle scan+aggregation single process (%.1f s); SAM decode untimed" % (n_sample, cpu_s)}
+    return parity, ingest, cpu
+
+
+def multi_gpu_parity(eng, sh, dist, dev, idx_base, total, m=100000):
+    """a peer-memory step on the first m rows of every rank's shard: owners' tables gathered to rank 0 == a second context
+    on rank 0 that scans every rank's prefix itself and aggregates the union"""
+    import torch
+
+    from find_circ2_b200 import parallel
+    from find_circ2_b200.engine import Engine
+
+    world, rank = dist.get_world_size(), dist.get_rank()
+    m = min(m, sh.n)
+    stream = torch.cuda.current_stream().cuda_stream
+    eng.agg_reset_async(stream)
+    eng.agg_set_idx_range(0, total)
+    eng.scan_emit_p2p(sh._pairs(eng, m), sh.hits, *sh.pay, idx_base, stream)
+    parallel.stream_barrier(dist, dev, eng, stream)
+    nj = eng.agg_finalize(stream)
+    got = parallel.gather_junctions(eng.agg_fetch(nj), dist, dev)
+    # rank 0 alone: every rank ships the columns of its prefix (plain NCCL gathers of tensors)
+    keys = ("chrom", "a_start", "b_end", "l", "flags", "internal", "wden", "q_a", "q_b", "read_hash", "qname_hash")
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([m], dtype=torch.int64, device=dev))
+    sizes = [int(x.item()) for x in sizes]
+    mx = max(sizes)
+    parts = {}
+    for k in keys:
+        v = sh.d[k][:m]
+        pad = torch.zeros((mx,) + tuple(v.shape[1:]), dtype=v.dtype, device=dev)
+        pad[:m] = v
+        bufs = [torch.zeros_like(pad) for _ in range(world)] if rank == 0 else None
+        dist.gather(pad, bufs, dst=0)
+        parts[k] = bufs
+    bases = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(bases, torch.tensor([idx_base], dtype=torch.int64, device=dev))
+    ok, n_junc = True, 0
+    if rank == 0:
+        e2 = Engine(device=dev.index, asize=eng.params.asize, margin=eng.params.margin, maxdist=eng.params.maxdist)
+        e2.share_genome(eng)
+        e2.agg_reset()
+        for r, mr in enumerate(sizes):
+            if mr == 0:
+                continue
+            c = {k: parts[k][r][:mr].contiguous() for k in parts}
+            planes = torch.zeros(3 * sh.n_words * mr, dtype=torch.int32, device=dev)
+            e2.pack_reads(c["internal"], sh.stride, c["l"], sh.n_words, planes, c["flags"], stream)
+            pr = e2.make_pairs(mr, c["chrom"], c["a_start"], c["b_end"], c["l"], c["flags"], planes, sh.n_words, sh.max_l)
+            hits = torch.zeros(mr * 4, dtype=torch.int32, device=dev)
+            e2.scan_emit(pr, hits, c["wden"], c["q_a"], c["q_b"], c["read_hash"], c["qname_hash"], int(bases[r].item()), stream)
+            torch.cuda.synchronize()
+        want = e2.agg_fetch(e2.agg_finalize(stream))
+        e2.close()
+        ok, n_junc = (got.tobytes() == want.tobytes() and len(want) > 0), len(want)
+    flag = torch.tensor([1 if ok else 0, n_junc], dtype=torch.int64, device=dev)
+    dist.broadcast(flag, 0)
+    return bool(flag[0].item()), int(flag[1].item())
+
+
+def bench_config(args, cfg, dist, dev, primary, error_rate=None):
+    import torch
+
+    import bench_workload as W
+    from find_circ2_b200 import parallel
+    from find_circ2_b200._lib import HIT_DTYPE
+    from find_circ2_b200.engine import Engine
+
+    rank = dist.get_rank() if dist is not None else 0
+    world = dist.get_world_size() if dist is not None else 1
+    local = dev.index
+    t_setup = time.perf_counter()
+    eng = Engine(device=local, asize=cfg.asize, margin=cfg.margin, maxdist=cfg.maxdist)
+    spec = W.Spec(cfg)
+    flat = spec.materialize(dev)
+    eng.load_genome_arrays(spec.names, spec.chrom_arrays(flat))
+    total = args.pairs if (primary and args.pairs) else cfg.n_pairs
+    if cfg.scaling == "weak":
+        total *= world
+    per = total // world // 2 * 2
+    total = per * world
+    sh = Shard(eng, spec, rank * per, (rank + 1) * per, dev, flat, error_rate=error_rate)
+    del flat
+    torch.cuda.empty_cache()
+    n = sh.n
+    d = sh.d
+    idx_base = rank * per  # position of the rank's shard in the whole input stream (dense over all ranks)
+    stream = torch.cuda.current_stream().cuda_stream
+    bpp = bytes_per_pair(cfg)
+    batch_bytes = n * (17 + 12 * sh.n_words + 21)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if batch_bytes < (512 << 20) else None
+    setup_s = time.perf_counter() - t_setup
+
+    # multi-GPU: records travel to the rank that owns their key, written by the scan kernel straight into the owner's
+    # buffer over NVLink (CUDA IPC peer memory); fallback: partition + NCCL all-to-all
+    use_p2p = world > 1 and not args.no_p2p and parallel.p2p_setup(eng, dist, dev, int(2.2 * n) + (1 << 16))
+
+    def step_device(ev=None):
+        eng.agg_reset_async(stream)  # stays behind the previous step in the stream: no host round trip before the scan
+        if world > 1:
+            eng.agg_set_idx_range(0, total)  # lets the owner rank the junctions without a sort
+        if ev:
+            ev[0].record()
+        if world == 1:
+            eng.scan_emit(sh.pairs, sh.hits, *sh.pay, idx_base, stream)  # scan + record in one kernel (fc_scan_emit)
+            if ev:
+                ev[1].record()
+                ev[2].record()
+        elif use_p2p:
+            eng.scan_emit_p2p(sh.pairs, sh.hits, *sh.pay, idx_base, stream)  # records land in the owner ranks' buffers
+            if ev:
+                ev[1].record()
+            parallel.stream_barrier(dist, dev, eng, stream)  # ends the step: counts published, every rank's records have landed
+            if ev:
+                ev[2].record()
+        else:
+            eng.scan(sh.pairs, sh.hits, stream)
+            eng.agg_emit(n, sh.hits, d["chrom"], d["flags"], *sh.pay, idx_base, stream)
+            if ev:
+                ev[1].record()
+            parallel.exchange_records(eng, dist, dev, stream, upper_bound=n)
+            if ev:
+                ev[2].record()
+        return eng.agg_finalize(stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def do_flush():
+        if flush is not None:
+            flush.zero_()
+
+    steps = args.steps if primary else max(3, args.steps // 4)
+    warm = max(args.warmup, 3) if primary else 3
+    for _ in range(warm):
+        do_flush()
+        nj = step_device()
+    barrier()
+    launches0 = eng.launch_count()
+    sampler = None
+    if primary:
+        sampler = ClockSampler(local)
+        sampler.start()
+        time.sleep(0.2)
+    # ---- timed: device-resident
+    tot_ms = scan_ms = xchg_ms = 0.0
+    barrier()
+    for _ in range(steps):
+        do_flush()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e0.record()
+        nj = step_device(ev)
+        e1.record()
+        torch.cuda.synchronize()
+        tot_ms += e0.elapsed_time(e1)
+        scan_ms += ev[0].elapsed_time(ev[1])
+        xchg_ms += ev[1].elapsed_time(ev[2])
+    barrier()
+    launches = eng.launch_count() - launches0
+    n_rec = eng.agg_n_records()
+    # ---- the aggregation kernel alone: a few more steps with the library's own CUDA events around its stages
+    eng.agg_set_timing(True)
+    stage_sum = {}
+    k_acc = max(2, steps // 4)
+    for _ in range(k_acc):
+        do_flush()
+        step_device()
+        torch.cuda.synchronize()
+        for k, v in eng.agg_get_timing().items():
+            stage_sum[k] = stage_sum.get(k, 0.0) + v
+    eng.agg_set_timing(False)
+    stages_us = {k: round(v / k_acc, 1) for k, v in stage_sum.items()}
+    acc_step_ms = stages_us["accumulate"] * 1e-3
+    barrier()
+    # ---- one step with the ordered gather of the junction tables to rank 0 inside (find_circ.py:684-686 across ranks)
+    gather_ms = None
+    if world > 1 and primary:
+        for it in range(2):
+            barrier()
+            t0 = time.perf_counter()
+            nj = step_device()
+            parallel.gather_junctions(eng.agg_fetch(nj), dist, dev)
+            torch.cuda.synchronize()
+            gather_ms = (time.perf_counter() - t0) * 1e3
+    ms_step = tot_ms / steps
+    scan_step = scan_ms / steps
+
+    # ---- timed: end to end through host buffers (wall clock brackets synchronous calls; device idle otherwise)
+    e2e = None
+    if primary and not use_p2p:
+        def pin(t):
+            h = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            h.copy_(t)
+            return h, h.numpy()
+        cols = ("chrom", "a_start", "b_end", "l", "flags", "wden", "q_a", "q_b", "read_hash", "qname_hash")
+        pinned = {k: pin(d[k]) for k in cols}
+        pl = sh.planes.view(3, sh.n_words * n)
+        pl_pin = [pin(pl[k]) for k in range(3)]
+        h_hits_t = torch.empty(n * 16, dtype=torch.uint8).pin_memory()
+        h_hits = h_hits_t.numpy().view(HIT_DTYPE)
+        h2d = sum(v[1].nbytes for v in pinned.values()) + sum(v[1].nbytes for v in pl_pin)
+        parts = {"reset": 0.0, "batch": 0.0, "finalize": 0.0, "fetch": 0.0}
+
+        def step_e2e():
+            tp = [time.perf_counter()]
+            eng.agg_reset()
+            tp.append(time.perf_counter())
+            p = {k: v[1] for k, v in pinned.items()}
+            eng.batch_host_planes(n, p["chrom"], p["a_start"], p["b_end"], p["l"], p["flags"], pl_pin[0][1].view(np.uint32),
+                                  pl_pin[1][1].view(np.uint32), pl_pin[2][1].view(np.uint32), sh.n_words, n, sh.max_l, p["wden"],
+                                  p["q_a"], p["q_b"], p["read_hash"].view(np.uint64), p["qname_hash"].view(np.uint64), idx=None,
+                                  idx_base=idx_base, emit=True, out=h_hits)
+            tp.append(time.perf_counter())
+            if world > 1:
+                parallel.exchange_records(eng, dist, dev, 0, upper_bound=n)
+            njj = eng.agg_finalize(0)
+            tp.append(time.perf_counter())
+            junc = eng.agg_fetch(njj, copy=False)  # read in place (pinned buffer of the engine)
+            tp.append(time.perf_counter())
+            for k, name in enumerate(("reset", "batch", "finalize", "fetch")):
+                parts[name] += tp[k + 1] - tp[k]
+            return njj, junc
+
+        e2e_steps = max(3, steps // 2)
+        for _ in range(2):
+            step_e2e()
+        barrier()
+        for k in parts:
+            parts[k] = 0.0
+        e2e_s = 0.0
+        for _ in range(e2e_steps):
+            do_flush()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            nj2, junc = step_e2e()
+            e2e_s += time.perf_counter() - t0
+        barrier()
+        e2e = {"s_step": e2e_s / e2e_steps, "h2d": int(h2d), "d2h": n * 16 + int(nj2) * 64,
+               "calls_ms": {k: round(v / e2e_steps * 1e3, 3) for k, v in parts.items()}}
+        del pinned, pl_pin, h_hits_t
+    if sampler is not None:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+
+    # ---- parity
+    parity = ingest = cpu = None
+    if primary or args.check_all:
+        if world > 1 and use_p2p:
+            ok, n_union = multi_gpu_parity(eng, sh, dist, dev, idx_base, total)
+            parity = {"ok": ok, "against": "one context aggregating the union of all ranks' prefixes (rank 0), byte for byte after the ordered gather",
+                      "pairs": "first 100000 rows of every rank's shard", "junction_rows": n_union}
+        elif world == 1:
+            parity, ingest, cpu = dropin_parity(eng, spec, cfg, min(args.cpu_sample, per) // 4 * 4)
+
+    # ---- reductions over ranks
+    e2e_step = e2e["s_step"] if e2e else 0.0
+    if world > 1:
+        v = torch.tensor([ms_step, scan_step, e2e_step, acc_step_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        ms_step, scan_step, e2e_step, acc_step_ms = [float(x) for x in v.tolist()]
+        cnt = torch.tensor([n, n_rec, int(nj)], dtype=torch.int64, device=dev)
+        dist.all_reduce(cnt)
+        total_pairs, total_rec, total_junc = [int(x) for x in cnt.tolist()]
+    else:
+        total_pairs, total_rec, total_junc = n, n_rec, int(nj)
+    peak, peak_src = peaks()
+    achieved = bpp * n / (scan_step * 1e-3) / 1e9
+    merge_bytes = 48.0 * n_rec + 64.0 * int(nj)
+    acc_achieved = merge_bytes / (max(acc_step_ms, 1e-9) * 1e-3) / 1e9
+    fused = world == 1 or use_p2p
+    roof_scan = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                 "kernel": ("scan_emit%s_kernel (csrc/scan.cu): breakpoint scan; also writes a 48-byte record per accepted pair" % ("" if world == 1 else "_p2p")
+                            if fused else "scan_kernel (csrc/scan.cu)"),
+                 "bytes_per_pair": bpp, "pairs": n, "ms": scan_step, "peak_source": peak_src}
+    roof_acc = {"bound": "hbm", "achieved": acc_achieved, "peak": peak, "unit": "GB/s", "frac": acc_achieved / peak, "traffic": None,
+                "kernel": "fused_accumulate_kernel (csrc/agg.cu)", "ms": acc_step_ms,
+                "bytes": "48 B x %d records + 64 B x %d junctions (rank 0)" % (n_rec, int(nj)), "peak_source": peak_src}
+    dominant, other = (roof_acc, roof_scan) if acc_step_ms > scan_step else (roof_scan, roof_acc)
+    res = {
+        "value": total_pairs / (ms_step * 1e-3), "ms_per_step": ms_step, "steps": steps, "warmup": warm,
+        "workload": cfg.workload + (" [substitution rate %.0f%%]" % (100 * error_rate) if error_rate is not None else ""),
+        "detail": {
+            "pairs_scanned": total_pairs, "pairs_scanned_rank0": n, "pairs_in": total, "records": total_rec, "junctions": total_junc,
+            "l2": ("flushed (256 MiB memset) before every timed step" if flush is not None else "inputs larger than L2 (%.1f GB of batch columns per GPU)" % (batch_bytes / 1e9)),
+            "timing": "per-step CUDA events summed over the steps; max over ranks",
+            "exchange": ("none" if world == 1 else ("scan kernel writes records into the owners' slices over peer memory (CUDA IPC, NVLink), one barrier per step" if use_p2p else "partition + NCCL all-to-all")),
+            "scan_ms": scan_step, "exchange_barrier_ms": xchg_ms / steps, "merge_ms": ms_step - scan_step - xchg_ms / steps,
+            "accumulate_kernel_ms": acc_step_ms, "merge_stages_us": stages_us, "step_with_ordered_gather_ms": gather_ms,
+            "setup_s": round(setup_s, 1), "seeds": {"workload": cfg.seed},
+        },
+        "roofline": dominant, "roofline_other": other, "gpu_launches": int(launches),
+        "parity_checked": bool(parity and parity["ok"]), "parity": parity,
+    }
+    if e2e:
+        res["e2e"] = {"value": total_pairs / e2e_step, "unit": "pairs/s", "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                      "ms_per_step": e2e_step * 1e3, "calls_ms": e2e["calls_ms"],
+                      "call": "fc_batch_host_planes + fc_agg_finalize + fc_agg_fetch (pinned host SoA with bit-plane reads, as csrc/ingest.cu emits them)"}
+    if sampler is not None:
+        res["clocks"] = sampler.summary()
+    if ingest:
+        res["ingest"] = ingest
+    if cpu:
+        res["cpu_baseline"] = cpu
+    if parity is not None and not parity["ok"]:
+        sys.stderr.write("bench.py: PARITY CHECK FAILED for config %s: %r\n" % (cfg.name, parity))
+    eng.close()
+    del sh
+    torch.cuda.empty_cache()
+    return res
+
+
+def _brief(r):
+    return {"workload": r["workload"], "value": r["value"], "unit": "pairs/s", "ms_per_step": r["ms_per_step"], "steps": r["steps"],
+            "roofline": {k: r["roofline"][k] for k in ("kernel", "frac", "achieved", "ms")},
+            "roofline_other": {k: r["roofline_other"][k] for k in ("kernel", "frac", "achieved", "ms")},
+            "pairs_scanned": r["detail"]["pairs_scanned"], "records": r["detail"]["records"], "junctions": r["detail"]["junctions"],
+            "merge_stages_us": r["detail"]["merge_stages_us"], "parity_checked": r["parity_checked"]}
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
+
+    import bench_workload as W
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -263,255 +608,32 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from find_circ2_b200.engine import Engine
-    from find_circ2_b200._lib import HIT_DTYPE, JREC_DTYPE
-    from find_circ2_b200 import parallel
-
-    eng = Engine(device=local, asize=ASIZE, margin=MARGIN, maxdist=MAXDIST)
-    g, J, t = workload(rank, args.pairs, args.genome_mb, args.n_circ)
-    eng.load_genome_arrays(g.names, g.seqs)
-    soa, idx = soa_from_table(t, eng)
-    n = len(idx)
-    max_l = int(soa["l"].max())
-    n_words = max(1, (max_l + 31) // 32)
-    stride = soa["internal"].shape[1]
-
-    # ---- device-resident copy of the batch (for `value`)
-    tn = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
-    d = {k: tn(v if v.dtype != np.uint64 else v.view(np.int64)) for k, v in soa.items()}
-    planes = torch.zeros(3 * n_words * n, dtype=torch.int32, device=dev)
-    hits = torch.zeros(n * 4, dtype=torch.int32, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
-    eng.pack_reads(d["internal"], stride, d["l"], n_words, planes, d["flags"], stream)
-    pairs = eng.make_pairs(n, d["chrom"], d["a_start"], d["b_end"], d["l"], d["flags"], planes, n_words, max_l)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    idx_base = rank * args.pairs  # position of the rank's shard in the whole input stream (dense over all ranks)
-
-    # multi-GPU: records travel to the rank that owns their key.  Preferred: the emit kernel writes them straight into
-    # the owner's buffer over NVLink (CUDA IPC peer memory); fallback: partition + NCCL all-to-all.
-    use_p2p = world > 1 and not args.no_p2p and parallel.p2p_setup(eng, dist, dev, int(2.5 * n) + (1 << 16))
-
-    def step_device(ev_scan=None):
-        if use_p2p:
-            eng.agg_reset_async(stream)
-            eng.agg_set_idx_range(0, world * args.pairs)  # lets the owner rank the junctions without a sort
-        else:
-            eng.agg_reset_async(stream)  # stays behind the L2-flush kernel in the stream: no host round trip before the scan
-        if ev_scan:
-            ev_scan[0].record()
-        if world == 1:
-            # scan + record in one kernel (fc_scan_emit)
-            eng.scan_emit(pairs, hits, d["wden"], d["q_a"], d["q_b"], d["read_hash"], d["qname_hash"], idx_base, stream)
-            if ev_scan:
-                ev_scan[1].record()
-                ev_scan[2].record()
-                ev_scan[3].record()
-            return eng.agg_finalize(stream)
-        if use_p2p:
-            # scan + records straight into the owner ranks' buffers, one kernel (fc_scan_emit_p2p)
-            eng.scan_emit_p2p(pairs, hits, d["wden"], d["q_a"], d["q_b"], d["read_hash"], d["qname_hash"], idx_base, stream)
-            if ev_scan:
-                ev_scan[1].record()
-                ev_scan[2].record()
-            parallel.stream_barrier(dist, dev, eng, stream)  # every rank's records have landed
-        else:
-            eng.scan(pairs, hits, stream)
-            if ev_scan:
-                ev_scan[1].record()
-            eng.agg_emit(n, hits, d["chrom"], d["flags"], d["wden"], d["q_a"], d["q_b"], d["read_hash"], d["qname_hash"], idx_base, stream)
-            if ev_scan:
-                ev_scan[2].record()
-            if world > 1:
-                parallel.exchange_records(eng, dist, dev, stream, upper_bound=n)
-        if ev_scan:
-            ev_scan[3].record()
-        return eng.agg_finalize(stream)
-
-    # ---- pinned host copy of the batch (for `e2e`)
-    def pin(a):
-        tt = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        return tt, tt.numpy()
-    pinned = {k: pin(v) for k, v in soa.items()}
-    h_hits_t = torch.empty(n * 16, dtype=torch.uint8).pin_memory()
-    h_hits = h_hits_t.numpy().view(HIT_DTYPE)
-    h2d = sum(v[1].nbytes for v in pinned.values())
-
-    # what the native ingest hands over: the internal read part as bit planes (word-major), 3 x 4 x n_words bytes per pair
-    planes_np = ascii_to_planes(soa["internal"], n_words)
-    pl_pin = [pin(planes_np[k]) for k in range(3)]
-    h2d_planes = sum(v[1].nbytes for k, v in pinned.items() if k != "internal") + sum(v[1].nbytes for v in pl_pin)
-
-    e2e_parts = {"reset": 0.0, "batch": 0.0, "finalize": 0.0, "fetch": 0.0}
-
-    def step_e2e(ascii_reads=False):
-        tp = [time.perf_counter()]
-        eng.agg_reset()
-        tp.append(time.perf_counter())
-        p = {k: v[1] for k, v in pinned.items()}
-        if ascii_reads:
-            eng.batch_host(p["chrom"], p["a_start"], p["b_end"], p["l"], p["flags"], p["internal"], p["wden"], p["q_a"], p["q_b"],
-                           p["read_hash"], p["qname_hash"], idx_base, emit=True, out=h_hits)
-        else:
-            eng.batch_host_planes(n, p["chrom"], p["a_start"], p["b_end"], p["l"], p["flags"], pl_pin[0][1], pl_pin[1][1],
-                                  pl_pin[2][1], n_words, n, max_l, p["wden"], p["q_a"], p["q_b"], p["read_hash"],
-                                  p["qname_hash"], idx=None, idx_base=idx_base, emit=True, out=h_hits)
-        tp.append(time.perf_counter())
-        if world > 1:
-            parallel.exchange_records(eng, dist, dev, 0, upper_bound=n)
-        nj = eng.agg_finalize(0)
-        tp.append(time.perf_counter())
-        junc = eng.agg_fetch(nj, copy=False)  # read in place (pinned buffer of the engine)
-        tp.append(time.perf_counter())
-        if not ascii_reads:
-            for k, name in enumerate(("reset", "batch", "finalize", "fetch")):
-                e2e_parts[name] += tp[k + 1] - tp[k]
-        return nj, junc
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # warm-up
-    for _ in range(max(args.warmup, 3)):
-        flush.zero_()
-        nj = step_device()
-    barrier()
-    launches0 = eng.launch_count()
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.3)
-    # ---- timed: device-resident
-    tot_ms, scan_ms, emit_ms, pre_ms, xchg_ms = 0.0, 0.0, 0.0, 0.0, 0.0
-    barrier()
-    for _ in range(args.steps):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0, s1, s2, s3 = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        e0.record()
-        nj = step_device((s0, s1, s2, s3))
-        e1.record()
-        torch.cuda.synchronize()
-        tot_ms += e0.elapsed_time(e1)
-        scan_ms += s0.elapsed_time(s1)
-        emit_ms += s1.elapsed_time(s2)
-        pre_ms += e0.elapsed_time(s0)   # reset (+ the first barrier on the multi-GPU path)
-        xchg_ms += s2.elapsed_time(s3)  # second barrier / all-to-all (multi-GPU)
-    barrier()
-    launches = eng.launch_count() - launches0
-    # ---- the aggregation kernel alone: a few more steps with the library's own CUDA events around its stages
-    eng.agg_set_timing(True)
-    acc_us, stage_sum = 0.0, {}
-    for _ in range(args.steps):
-        flush.zero_()
-        step_device()
-        torch.cuda.synchronize()
-        st = eng.agg_get_timing()
-        acc_us += st["accumulate"]
-        for k, v in st.items():
-            stage_sum[k] = stage_sum.get(k, 0.0) + v
-    eng.agg_set_timing(False)
-    acc_step_ms = acc_us / args.steps * 1e-3
-    stages_us = {k: round(v / args.steps, 1) for k, v in stage_sum.items()}
-    barrier()
-    # ---- timed: end to end through host buffers (wall clock brackets synchronous calls; device idle otherwise)
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    e2e_s = 0.0
-    for k in e2e_parts:
-        e2e_parts[k] = 0.0
-    for _ in range(args.steps):
-        flush.zero_()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        nj2, junc = step_e2e()
-        e2e_s += time.perf_counter() - t0
-    barrier()
-    # the same with ASCII read bases in the host buffers (what the python ingest produces)
-    e2e_ascii_s = 0.0
-    step_e2e(True)
-    for _ in range(max(args.steps // 2, 1)):
-        flush.zero_()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        step_e2e(True)
-        e2e_ascii_s += time.perf_counter() - t0
-    e2e_ascii_step = e2e_ascii_s / max(args.steps // 2, 1)
-    barrier()
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
-    d2h = n * 16 + int(nj2) * 64
-
-    ms_step = tot_ms / args.steps
-    scan_step = scan_ms / args.steps
-    e2e_step = e2e_s / args.steps
-    if world > 1:
-        v = torch.tensor([ms_step, scan_step, e2e_step], dtype=torch.float64, device=dev)
-        dist.all_reduce(v, op=dist.ReduceOp.MAX)
-        ms_step, scan_step, e2e_step = [float(x) for x in v.tolist()]
-        cnt = torch.tensor([n], dtype=torch.int64, device=dev)
-        dist.all_reduce(cnt)
-        total_pairs = int(cnt.item())
-    else:
-        total_pairs = n
-
-    n_rec = eng.agg_n_records() if world == 1 else n
+    cfgs = W.configs()
+    cfg = cfgs[args.config]
+    r = bench_config(args, cfg, dist if world > 1 else None, dev, primary=True)
+    line = {
+        "metric": METRIC, "value": r["value"], "unit": "pairs/s", "n_gpus": world, "steps": r["steps"], "warmup": r["warmup"],
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": cfg.scaling, "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic", "config": {"workload": r["workload"]},
+    }
+    for k in ("detail", "roofline", "roofline_other", "e2e", "gpu_launches", "clocks", "parity_checked", "parity", "ingest", "cpu_baseline"):
+        if k in r:
+            line[k] = r[k]
+    line.setdefault("e2e", None)
+    if world == 1 and not args.no_extra:
+        others = {}
+        for name in [c for c in ("2", "4", "5") if c != args.config]:
+            c2 = cfgs[name]
+            if name == "4":
+                for er in (0.01, 0.02, 0.03):
+                    others["4@%d%%" % round(100 * er)] = _brief(bench_config(args, c2, None, dev, primary=False, error_rate=er))
+            else:
+                others[name] = _brief(bench_config(args, c2, None, dev, primary=False))
+        line["other_configs"] = others
     if rank == 0:
-        peak, peak_src = peaks()
-        # single GPU: the scan kernel also writes the junction records (48 B per accepted pair) and reads their payload
-        # columns (22 B per pair: wden, q_a, q_b, read hash, name hash)
-        fused_scan = world == 1 or use_p2p  # the scan kernel writes the records itself
-        n_emitted = n_rec if world == 1 else 0.9 * n  # (multi-GPU: n_rec counts what this rank RECEIVED; ~90 % of the pairs emit)
-        scan_bytes = BYTES_PER_PAIR * n + ((48.0 * n_emitted + 22.0 * n) if fused_scan else 0.0)
-        achieved = scan_bytes / (scan_step * 1e-3) / 1e9
-        merge_bytes = 48.0 * n_rec + 64.0 * int(nj)
-        acc_achieved = merge_bytes / (max(acc_step_ms, 1e-9) * 1e-3) / 1e9
-        roof_scan = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": (87.6e6 if fused_scan else 46.4e6),
-                     "kernel": ("scan_emit%s_kernel<NP=3,T=1> (csrc/scan.cu): scan + 48-byte record per accepted pair" % ("" if world == 1 else "_p2p")
-                                if fused_scan else "scan_kernel<NP=3,T=1> (csrc/scan.cu)"),
-                     "bytes_per_pair": scan_bytes / n, "ms": scan_step,
-                     "peak_source": peak_src, "traffic_source": "ncu --set full, profiles/r01_kernels_ncu_summary.txt"}
-        roof_acc = {"bound": "hbm", "achieved": acc_achieved, "peak": peak, "unit": "GB/s", "frac": acc_achieved / peak,
-                    "traffic": 130.7e6, "kernel": "fused_accumulate_kernel (csrc/agg.cu)", "ms": acc_step_ms,
-                    "bytes": "48 B x %d records + 64 B x %d junctions (rank 0)" % (n_rec, int(nj)), "peak_source": peak_src,
-                    "traffic_source": "ncu --set full, profiles/r01_kernels_ncu_summary.txt",
-                    "note": "random 16/32-byte accesses to hash tables: bound by L1/LSU wavefronts and L2 atomics, not by bytes"}
-        dominant, other = (roof_acc, roof_scan) if acc_step_ms > scan_step else (roof_scan, roof_acc)
-        line = {
-            "metric": "anchor pairs/sec (breakpoint scan + junction merge)", "value": total_pairs / (ms_step * 1e-3),
-            "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {
-                "workload": "configs[1]: synthetic %d Mb genome (20 chrom, 0.5%% N), %d planted circRNAs, %d anchor pairs/GPU from 100-nt reads, a=20 m=2 d=2, 0.5%% substitutions, 10%% decoys"
-                            % (args.genome_mb, args.n_circ, args.pairs),
-                "pairs_scanned_per_gpu": n, "junctions_rank0": int(nj), "l2": "flushed (256 MiB memset) before every timed step",
-                "timing": "per-step CUDA events summed over the steps; max over ranks",
-                "exchange": ("none" if world == 1 else ("fused emit+exchange over peer memory (CUDA IPC, NVLink)" if use_p2p else "partition + NCCL all-to-all")),
-                "scan_ms": scan_step, "merge_ms": ms_step - scan_step, "accumulate_kernel_ms": acc_step_ms,
-                "emit_ms": emit_ms / args.steps, "reset_barrier_ms": pre_ms / args.steps, "exchange_barrier_ms": xchg_ms / args.steps, "seeds": {"genome": 1, "junctions": 2, "pairs": "3+1000*rank"},
-            },
-            "roofline": dominant,        # the kernel with the longest launch inside the step
-            "roofline_other": other,     # the second kernel of the path
-            "merge_stages_us": stages_us,
-            "e2e": {"value": total_pairs / e2e_step, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d_planes), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_step * 1e3,
-                    "calls_ms": {k: round(v / args.steps * 1e3, 3) for k, v in e2e_parts.items()},
-                    "call": "fc_batch_host_planes + fc_agg_finalize + fc_agg_fetch (pinned host SoA with bit-plane reads, as csrc/ingest.cu emits them)",
-                    "ascii_reads": {"value": n * world / e2e_ascii_step, "h2d_bytes_per_step": int(h2d), "ms_per_step": e2e_ascii_step * 1e3,
-                                    "call": "fc_batch_host (ASCII read bases, packed on the device)"}},
-            "gpu_launches": int(launches),
-            "clocks": sampler.summary(),
-        }
-        if world == 1:
-            line["ingest"] = host_ingest(g, t, min(args.cpu_sample, 20000), eng)
-            v, dt = cpu_baseline(g, t, args.cpu_sample, 1)
-            line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": 1, "kind": "port",
-                                    "sample": "first %d pairs of the same workload, oracle scan+aggregation single process (%.1f s); SAM decode untimed" % (args.cpu_sample, dt)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-    eng.close()
 
 
 def main():
@@ -520,11 +642,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs", type=int, default=1000000)
-    ap.add_argument("--genome-mb", type=int, default=100)
-    ap.add_argument("--n-circ", type=int, default=10000)
+    ap.add_argument("--config", default="3", choices=["2", "3", "4", "5"], help="BASELINE.json configs[1..4]")
+    ap.add_argument("--pairs", type=int, default=0, help="override the pair count of the primary config")
     ap.add_argument("--cpu-sample", type=int, default=20000)
-    ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: use partition + NCCL all-to-all instead of peer-memory emit")
+    ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: partition + NCCL all-to-all instead of peer-memory emit")
+    ap.add_argument("--no-extra", action="store_true", help="N=1: skip the lines of the other configs")
+    ap.add_argument("--check-all", action="store_true", help="run the parity check on the other configs too")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

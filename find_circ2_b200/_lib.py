@@ -73,6 +73,7 @@ SYMBOLS = [
     ("fc_last_error", C.c_char_p, [_P]),
     ("fc_genome_load_fasta", C.c_int, [_P, C.c_char_p]),
     ("fc_genome_load_ascii", C.c_int, [_P, C.c_int32, _P, _P, _P]),
+    ("fc_genome_share", C.c_int, [_P, _P]),
     ("fc_genome_n_chrom", C.c_int, [_P]),
     ("fc_genome_chrom_name", C.c_int, [_P, C.c_int32, C.c_char_p, C.c_int32]),
     ("fc_genome_chrom_size", C.c_int64, [_P, C.c_int32]),
@@ -134,6 +135,7 @@ SYMBOLS = [
     ("fc_hash_bytes", C.c_uint64, [_P, C.c_int64]),
     ("fc_hash_read", C.c_uint64, [_P, C.c_int64, _P]),
     ("fc_hash_reads_host", C.c_int, [C.c_int64, _P, C.c_int32, _P, _P, _P]),
+    ("fc_hash_reads_device", C.c_int, [_P, C.c_int64, _P, C.c_int32, _P, C.c_int32, _P, _P]),
 ]
 
 _lib = None

@@ -126,6 +126,47 @@ extern "C" uint64_t fc_hash_read(const uint8_t* seq, int64_t n, int32_t* is_pali
   return h;
 }
 
+// the same on the device: one thread per read (rows of a fixed-stride byte matrix in device memory)
+__constant__ uint8_t c_comp[256];
+__global__ void hash_reads_kernel(int64_t n, const uint8_t* __restrict__ seq, int32_t stride, const int32_t* __restrict__ len,
+                                  int32_t fixed_len, uint64_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* row = seq + i * (int64_t)stride;
+  const int m = len ? len[i] : fixed_len;
+  uint64_t hf = 0xcbf29ce484222325ULL, hr = 0xcbf29ce484222325ULL;
+  bool pal = true;
+  for (int k = 0; k < m; ++k) {
+    const uint8_t f = row[k], r = c_comp[row[m - 1 - k]];
+    hf = (hf ^ f) * 0x100000001b3ULL;
+    hr = (hr ^ r) * 0x100000001b3ULL;
+    pal = pal && (f == r);
+  }
+  hf = fc_mix64(hf + (uint64_t)m);
+  hr = fc_mix64(hr + (uint64_t)m);
+  uint64_t h = hf < hr ? hf : hr;
+  out[i] = (h & ~1ull) | (pal ? 1ull : 0ull);
+}
+
+extern "C" int fc_hash_reads_device(fc_ctx* ctx, int64_t n, const uint8_t* d_seq, int32_t stride, const int32_t* d_len,
+                                    int32_t fixed_len, uint64_t* d_out, void* stream) {
+  if (!ctx || n < 0 || !d_seq || !d_out || (!d_len && fixed_len < 0)) return FC_E_ARG;
+  if (n == 0) return FC_OK;
+  static bool table_up = false;  // (per process and device image; the table is constant)
+  if (!table_up) {
+    uint8_t comp[256];
+    for (int i = 0; i < 256; ++i) comp[i] = (uint8_t)i;
+    const char* a = "ACGTKMRYSWBVHDNacgtkmryswbvhdn";
+    const char* b = "TGCAMKYRSWVBDHNtgcamkyrswvbdhn";
+    for (int i = 0; a[i]; ++i) comp[(uint8_t)a[i]] = (uint8_t)b[i];
+    FC_CUDA(ctx, cudaMemcpyToSymbol(c_comp, comp, 256));
+    table_up = true;
+  }
+  hash_reads_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(n, d_seq, stride, d_len, fixed_len, d_out);
+  FC_LAUNCH_CHECK(ctx);
+  return FC_OK;
+}
+
 extern "C" int fc_hash_reads_host(int64_t n, const uint8_t* h_seq, int32_t stride, const int32_t* h_len, uint64_t* h_out,
                                   uint8_t* h_pal) {
   if (n < 0 || !h_seq || !h_len || !h_out) return FC_E_ARG;

@@ -13,6 +13,7 @@
 
 struct fc_genome {
   bool loaded = false;
+  bool shared = false;  // a view of another context's store (fc_genome_share): never freed or rebuilt here
   std::vector<std::string> names;
   std::vector<int64_t> sizes;
   std::vector<int64_t> offs;  // global base offset of each chromosome

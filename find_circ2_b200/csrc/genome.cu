@@ -128,6 +128,10 @@ __global__ void fetch_kernel(fc::GenomeView g, int64_t gp, int64_t n, char* __re
 }
 
 void genome_free(fc_genome& g) {
+  if (g.shared) {
+    g = fc_genome();
+    return;
+  }
   cudaFree(g.d_plo);
   cudaFree(g.d_phi);
   cudaFree(g.d_pn);
@@ -434,6 +438,7 @@ int fc_genome_ensure_tiles(fc_ctx* ctx, int w, cudaStream_t st) {
   if (w < 8) w = 8;
   if (w > 256) w = 256;
   if (g.d_tiles && w <= g.tile_W) return FC_OK;
+  if (g.shared) return fc_fail(ctx, FC_E_STATE, "a shared genome store cannot rebuild its tiles for %d-base windows: scan on the owning context first", w);
   int T, P, cap;
   fc::tile_geometry(w, T, P, cap);
   const int S = fc::TILE_STRIDE;
@@ -461,3 +466,14 @@ int fc_genome_ensure_tiles(fc_ctx* ctx, int w, cudaStream_t st) {
 }
 
 void fc_genome_release(fc_ctx* ctx) { genome_free(ctx->genome); }
+
+// a second context of the same process and device looks at the store of `src` (no copy); src must outlive dst
+extern "C" int fc_genome_share(fc_ctx* dst, fc_ctx* src) {
+  if (!dst || !src || dst == src) return FC_E_ARG;
+  if (!src->genome.loaded) return fc_fail(dst, FC_E_NOGENOME, "the source context holds no genome");
+  if (dst->device != src->device) return fc_fail(dst, FC_E_ARG, "contexts live on different devices");
+  genome_free(dst->genome);
+  dst->genome = src->genome;
+  dst->genome.shared = true;
+  return FC_OK;
+}

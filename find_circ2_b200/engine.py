@@ -96,6 +96,11 @@ class Engine:
         self._check(self.lib.fc_genome_load_ascii(self.h, n, c_names, c_seqs, sizes.ctypes.data))
         self._refresh_chroms()
 
+    def share_genome(self, other: "Engine"):
+        """use the device store of another engine of this process on the same device (no second copy)"""
+        self._check(self.lib.fc_genome_share(self.h, other.h))
+        self._refresh_chroms()
+
     def chrom_id(self, name: str) -> int:
         """KeyError for unknown chromosomes, as the reference raises (find_circ.py:193)"""
         return self._chrom_ids[name]
@@ -332,6 +337,11 @@ class Engine:
         self._check(self.lib.fc_hash_reads_host(len(lens), seqs.ctypes.data, seqs.shape[1], lens.ctypes.data,
                                                 out.ctypes.data, None))
         return out
+
+    def hash_reads_device(self, d_seqs, fixed_len: int, d_out, stream=0):
+        """strand-invariant read hashes of device rows ([n, stride] uint8 tensor -> int64/uint64 tensor of n)"""
+        n, stride = int(d_seqs.shape[0]), int(d_seqs.shape[1])
+        self._check(self.lib.fc_hash_reads_device(self.h, n, ptr(d_seqs), stride, None, int(fixed_len), ptr(d_out), stream))
 
     def hash_read(self, seq: bytes) -> int:
         return int(self.lib.fc_hash_read(seq, len(seq), None))

@@ -152,6 +152,9 @@ int fc_genome_load_fasta(fc_ctx* ctx, const char* path);
 /* n_chrom sequences given as ASCII in host memory (synthetic genomes; avoids a FASTA round trip) */
 int fc_genome_load_ascii(fc_ctx* ctx, int32_t n_chrom, const char* const* names, const uint8_t* const* seqs,
                          const int64_t* sizes);
+/* dst looks at the device store of src (another context of this process on the same device) instead of loading its own
+ * copy; src must outlive dst, and reads longer than the store's current tile class must be scanned on src first */
+int fc_genome_share(fc_ctx* dst, fc_ctx* src);
 int fc_genome_n_chrom(fc_ctx* ctx);
 int fc_genome_chrom_name(fc_ctx* ctx, int32_t i, char* buf, int32_t cap);
 int64_t fc_genome_chrom_size(fc_ctx* ctx, int32_t i);
@@ -370,6 +373,10 @@ uint64_t fc_hash_read(const uint8_t* seq, int64_t n, int32_t* is_palindrome);
 /* vectorised: rows of a fixed-stride matrix */
 int fc_hash_reads_host(int64_t n, const uint8_t* h_seq, int32_t stride, const int32_t* h_len, uint64_t* h_out,
                        uint8_t* h_pal);
+
+/* the same on device rows (one thread per read); d_len may be NULL: every row holds fixed_len letters */
+int fc_hash_reads_device(fc_ctx* ctx, int64_t n, const uint8_t* d_seq, int32_t stride, const int32_t* d_len, int32_t fixed_len,
+                         uint64_t* d_out, void* stream);
 
 #ifdef __cplusplus
 }
