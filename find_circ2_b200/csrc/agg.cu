@@ -251,40 +251,81 @@ __global__ void distinct_hash_kernel(int64_t n, const fc_jrec* __restrict__ s, c
   }
 }
 
-// ======================================================================================================================
-// Sort-free aggregation (default): ONE pass over the records.  Every record looks its junction up in a 128-bit
-// open-addressing table whose entries carry the junction id next to the key (one 16-byte load resolves both), bumps
-// the per-junction accumulators (64 bytes, two sectors) with three 64/32-bit reductions, looks at the extrema sector
-// once and only fires an atomic when the record improves one, and inserts (read hash, junction) / (name hash,
-// junction) into one exact hash set for the distinct counts.  Weights are k/8 (denominators 1,2,4,8), so fixed-point
-// sums are exact in any order; inputs with another denominator fall back to the sort-based path below.
-//
-// The distinct set is cleared per call (the memset also leaves it resident in L2, where the probes then hit); the finish
-// kernel zeroes exactly the key slots and accumulators it consumed, so those are never cleared as a whole.
-// ======================================================================================================================
-struct alignas(64) JAcc2 {
-  unsigned long long spanned_frags;  // n_spanned | n_frags << 32
-  unsigned long long w_b;            // 8 * n_weighted | 8 * n_uniq_bridges << 32
-  unsigned int uniq2;                // 2 per distinct non-palindromic read, 1 per distinct palindromic read
-  unsigned int sig;                  // 12-bit signal code (same for every record of the junction)
-  unsigned long long spare;
-  // extrema sector; everything is kept as a maximum with 0 = "nothing yet"
-  unsigned long long first_inv;      // ~(smallest record position / idx)
-  unsigned int qmax_l, qmax_r;       // best anchor quality + 32769
-  unsigned int inv_dist, inv_ov, inv_nh;  // ~minimum
-  unsigned int slot;                 // slot of the junction in the key table
+// Where the records of a call live: one run behind a counter (local emit), or -- multi-GPU -- `n_slices` slices of
+// slice_cap records, slice s filled by source rank s with counts[s] records (emit_core.cuh: P2PView)
+struct RecSrc {
+  const fc_jrec* base;
+  const unsigned long long* counts;  // n_slices words
+  unsigned long long slice_cap;      // (n_slices == 1: the upper bound of the record count)
+  int n_slices;
+  unsigned long long* total_out;     // n_slices > 1: block 0 writes the exact record count here
 };
-static_assert(sizeof(JAcc2) == 64 && offsetof(JAcc2, first_inv) == 32 && offsetof(JAcc2, inv_dist) == 48, "JAcc2 layout");
 
-constexpr unsigned long long KEY_HI_MASK = (1ull << 34) - 1ull;  // chrom (32) | strand, kind (2); junction id + 1 above
-constexpr long long FUSED_MAX_RECORDS = 1ll << 28;                 // keeps 8 * n_spanned and the ids inside their fields
+// ======================================================================================================================
+// Sort-free aggregation (default): ONE pass over the records.  Every junction lives in one 64-byte slot of an
+// open-addressing table: the first sector holds its identity AND its extrema (one 32-byte load tells a record whether
+// the slot is its junction and whether it improves any extreme -- it rarely does after a junction's first records), the
+// second sector holds the counters.  A record of a junction that is not new costs: that one load, ONE reduction
+// (n_spanned and the weight travel in one 64-bit word; everything that is unusual -- a read seen before, a fragment seen
+// before, an anchor without uniqueness, a palindromic read -- is counted by its own, rare, reduction and subtracted at
+// the end) and the insert of (read hash, junction) into one exact hash set for the distinct counts.  Weights are k/8
+// (denominators 1,2,4,8), so fixed-point sums are exact in any order; inputs with another denominator fall back to the
+// sort-based path below.
+//
+// The distinct set is cleared per call; the finish kernel zeroes exactly the slots it consumed, so the junction table is
+// never cleared as a whole.
+// ======================================================================================================================
+struct alignas(64) JSlot {
+  // sector 0: identity + extrema (everything is kept as a maximum, all-zero = nothing yet = identity of max)
+  unsigned long long klo;        // start | end << 32
+  unsigned long long khi;        // chrom | (strand, kind) << 32 | KEY_OCC
+  unsigned long long first_inv;  // ~(smallest record position / idx)
+  unsigned long long ext;        // (q_left + 32768) | (q_right + 32768) << 16 | (255 - ov) << 32 | (255 - dist) << 40 | (65535 - n_hits) << 48
+  // sector 1: counters
+  unsigned long long c0;         // n_spanned | 8 * n_weighted << 32
+  unsigned long long c1;         // rare: 8 * weight of records that are no unique bridge | records whose fragment name is not new << 32
+  unsigned long long c2;         // rare: 2 per record whose read was seen before + 1 per new palindromic read
+  unsigned int sig;              // 12-bit signal code (same for every record of the junction)
+  unsigned int pad;
+};
+static_assert(sizeof(JSlot) == 64 && offsetof(JSlot, first_inv) == 16 && offsetof(JSlot, c0) == 32, "JSlot layout");
 
-// counters (32-bit words at counters + 8): [0] junction ids handed out, [1] records with another denominator,
-// [2] ids beyond the accumulator array, [3] junctions
+constexpr unsigned long long KEY_OCC = 1ull << 63;
+constexpr long long FUSED_MAX_RECORDS = 1ll << 28;  // keeps 8 * n_spanned and the slot numbers inside their fields
+constexpr uint32_t SK_NAME_KNOWN = 8u, SK_NAME_DUP = 16u;  // fc_jrec.sk: the emitter already knows whether the fragment is new to the junction
+
+// counters (32-bit words at counters + 8): [0] junctions listed, [1] records with another denominator,
+// [2] list overflow / records outside a declared idx range, [3] junctions
 enum { FC_N_ALLOC = 0, FC_N_OTHER = 1, FC_N_OVERFLOW = 2, FC_N_JUNC = 3 };
 
+__device__ __forceinline__ unsigned long long ext_pack(int q_left, int q_right, unsigned dist, unsigned ov, unsigned n_hits) {
+  const unsigned lo = (unsigned)(q_left + 32768) | ((unsigned)(q_right + 32768) << 16);
+  const unsigned hi = (255u - ov) | ((255u - dist) << 8) | ((65535u - n_hits) << 16);
+  return (unsigned long long)lo | ((unsigned long long)hi << 32);
+}
+// field-wise maximum of two packed extrema words
+__device__ __forceinline__ unsigned long long ext_max(unsigned long long a, unsigned long long b) {
+  const unsigned alo = (unsigned)a, blo = (unsigned)b, ahi = (unsigned)(a >> 32), bhi = (unsigned)(b >> 32);
+  const unsigned lo = __vmaxu2(alo, blo);
+  const unsigned hi = (__vmaxu2(ahi, bhi) & 0xFFFF0000u) | (__vmaxu4(ahi, bhi) & 0x0000FFFFu);
+  return (unsigned long long)lo | ((unsigned long long)hi << 32);
+}
+// f / x: extrema of one record (or of one shared-memory entry); cur_f / cur_x: what a (possibly stale: maxima only grow,
+// so an old value can only cause a needless attempt) look at the slot showed
+__device__ __forceinline__ void extrema_to_global(JSlot* s, unsigned long long f, unsigned long long x, unsigned long long cur_f,
+                                                  unsigned long long cur_x) {
+  if (f > cur_f) atomicMax(&s->first_inv, f);
+  unsigned long long want = ext_max(cur_x, x);
+  while (want != cur_x) {
+    const unsigned long long old = atomicCAS(&s->ext, cur_x, want);
+    if (old == cur_x) break;
+    cur_x = old;
+    want = ext_max(cur_x, x);
+  }
+}
+
 // Exact set of (value, tag) pairs, insert only.  Probe sequence of an element: first the slot given by the value alone
-// (known before the junction id is, so its sector can be prefetched while the key table is read -- an atomic that
+// (known before the junction is, so its sector can be prefetched while the junction table is read -- an atomic that
 // misses in L2 is far slower than one that hits), then linear probing from a slot that also depends on the tag (a
 // read sequence that supports very many junctions does not build one long cluster).
 __device__ __forceinline__ unsigned long long set_first_slot(unsigned long long v, unsigned long long mask) {
@@ -292,12 +333,12 @@ __device__ __forceinline__ unsigned long long set_first_slot(unsigned long long 
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// insert (v1, t1) and (v2, t2); both probe sequences advance together so that their round trips overlap.  The CAS goes
-// first (no load): most inserts find an empty slot, and the returned old entry tells the rest.
+// insert (v1, t1) and, when with2, (v2, t2); both probe sequences advance together so that their round trips overlap.
+// The CAS goes first (no load): most inserts find an empty slot, and the returned old entry tells the rest.
 __device__ __forceinline__ void set_insert2(U128* table, unsigned long long mask, unsigned long long v1, unsigned long long t1,
-                                            unsigned long long s1, unsigned long long v2, unsigned long long t2,
+                                            unsigned long long s1, bool with2, unsigned long long v2, unsigned long long t2,
                                             unsigned long long s2, bool& new1, bool& new2) {
-  bool d1 = false, d2 = false, first1 = true, first2 = true;
+  bool d1 = false, d2 = !with2, first1 = true, first2 = true;
   new1 = new2 = false;
   while (!(d1 && d2)) {
     U128 o1{0ull, 0ull}, o2{0ull, 0ull};
@@ -337,10 +378,10 @@ constexpr int HOT_ENTRIES = 512;
 constexpr int HOT_BITS = 9;
 constexpr int SKETCH_BITS = 11;
 struct HotTable {
-  unsigned int tag[HOT_ENTRIES];    // junction id + 1, 0 = free
-  unsigned int cnt[HOT_ENTRIES];    // n_spanned | n_frags << 16 (at most one of each per thread of the CTA)
-  unsigned int wb[HOT_ENTRIES];     // 8 * weight | 8 * bridge weight << 16
-  unsigned int uniq2[HOT_ENTRIES];
+  unsigned int tag[HOT_ENTRIES];    // junction slot + 1, 0 = free
+  unsigned int c0[HOT_ENTRIES];     // n_spanned | 8 * weight << 16 (at most 512 records of weight <= 1 per CTA)
+  unsigned int c1[HOT_ENTRIES];     // 8 * non-bridge weight | names seen before << 16
+  unsigned int c2[HOT_ENTRIES];
   unsigned int qmax_l[HOT_ENTRIES], qmax_r[HOT_ENTRIES], inv_dist[HOT_ENTRIES], inv_ov[HOT_ENTRIES], inv_nh[HOT_ENTRIES];
   unsigned long long first_inv[HOT_ENTRIES];
 };
@@ -356,41 +397,22 @@ __device__ __forceinline__ int hot_find_or_insert(HotTable& t, unsigned int jid)
   return -1;  // crowded: the group goes to global memory directly
 }
 
-// extrema of one record (or of one shared-memory entry) against the junction's accumulator: one look at the sector,
-// atomics only for improvements (rare after the first records of a junction)
-__device__ __forceinline__ void extrema_to_global(JAcc2* a, unsigned long long f, unsigned ql, unsigned qr, unsigned idist,
-                                                  unsigned iov, unsigned inh) {
-  const ulonglong2 e0 = __ldcg(reinterpret_cast<const ulonglong2*>(&a->first_inv));
-  const uint4 e1 = __ldcg(reinterpret_cast<const uint4*>(&a->inv_dist));
-  if (f > e0.x) atomicMax(&a->first_inv, f);
-  if (ql > (unsigned)e0.y) atomicMax(&a->qmax_l, ql);
-  if (qr > (unsigned)(e0.y >> 32)) atomicMax(&a->qmax_r, qr);
-  if (idist > e1.x) atomicMax(&a->inv_dist, idist);
-  if (iov > e1.y) atomicMax(&a->inv_ov, iov);
-  if (inh > e1.z) atomicMax(&a->inv_nh, inh);
+// one 32-byte sector (identity + extrema of a slot)
+__device__ __forceinline__ void ld_sector(const JSlot* s, unsigned long long (&v)[4]) {
+  asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(s));
 }
 
-// Where the records of a call live: one run behind a counter (local emit), or -- multi-GPU -- `n_slices` slices of
-// slice_cap records, slice s filled by source rank s with counts[s] records (emit_core.cuh: P2PView)
-struct RecSrc {
-  const fc_jrec* base;
-  const unsigned long long* counts;  // n_slices words
-  unsigned long long slice_cap;      // (n_slices == 1: the upper bound of the record count)
-  int n_slices;
-  unsigned long long* total_out;     // n_slices > 1: block 0 writes the exact record count here
-};
-
-__global__ void __launch_bounds__(ACC_THREADS) fused_accumulate_kernel(RecSrc src, U128* __restrict__ keys,
+__global__ void __launch_bounds__(ACC_THREADS) fused_accumulate_kernel(RecSrc src, JSlot* __restrict__ slots,
                                                                unsigned long long kmask, U128* __restrict__ sets,
-                                                               unsigned long long smask, JAcc2* __restrict__ acc,
-                                                               unsigned int acap, unsigned int* __restrict__ ctr,
+                                                               unsigned long long smask, unsigned int* __restrict__ list,
+                                                               unsigned int lcap, unsigned int* __restrict__ ctr,
                                                                uint32_t* __restrict__ flag, int64_t n_flag,
                                                                uint32_t* __restrict__ tile_count, int64_t n_tiles) {
   __shared__ HotTable hot;
   __shared__ unsigned int sketch[1 << SKETCH_BITS];
   for (int e = threadIdx.x; e < (1 << SKETCH_BITS); e += blockDim.x) sketch[e] = 0u;
   for (int e = threadIdx.x; e < HOT_ENTRIES; e += blockDim.x) {
-    hot.tag[e] = hot.cnt[e] = hot.wb[e] = hot.uniq2[e] = 0u;
+    hot.tag[e] = hot.c0[e] = hot.c1[e] = hot.c2[e] = 0u;
     hot.qmax_l[e] = hot.qmax_r[e] = hot.inv_dist[e] = hot.inv_ov[e] = hot.inv_nh[e] = 0u;
     hot.first_inv[e] = 0ull;
   }
@@ -418,57 +440,61 @@ __global__ void __launch_bounds__(ACC_THREADS) fused_accumulate_kernel(RecSrc sr
   const bool active = i < n;
   const unsigned amask = __ballot_sync(0xffffffffu, active);
   uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0, r2 = r0;
-  unsigned long long s_read = 0ull, s_name = 0ull;
-  unsigned int jid = 0xFFFFFFFFu;
+  unsigned long long s_read = 0ull, s_name = 0ull, cur_f = 0ull, cur_x = 0ull;
+  unsigned int jid = 0xFFFFFFFFu;  // slot number of the record's junction
+  bool name_known = false;
   if (active) {
     const uint4* rp = reinterpret_cast<const uint4*>(recs + rec_at);
     r0 = __ldg(rp);
     r1 = __ldg(rp + 1);
     r2 = __ldg(rp + 2);
+    name_known = (r0.w & SK_NAME_KNOWN) != 0u;
     // names and reads share the set: the name's value is salted so that equal hashes of the two kinds stay apart
     s_read = set_first_slot((unsigned long long)r1.z | ((unsigned long long)r1.w << 32), smask);
-    s_name = set_first_slot(~((unsigned long long)r2.x | ((unsigned long long)r2.y << 32)), smask);
     prefetch_l2(sets + s_read);
-    prefetch_l2(sets + s_name);
+    if (!name_known) {
+      s_name = set_first_slot(~((unsigned long long)r2.x | ((unsigned long long)r2.y << 32)), smask);
+      prefetch_l2(sets + s_name);
+    }
 
-    // ---- junction id
+    // ---- the junction's slot
     const unsigned long long klo = (unsigned long long)r0.y | ((unsigned long long)r0.z << 32);
-    const unsigned long long khi = (unsigned long long)r0.x | ((unsigned long long)(r0.w & 3u) << 32);
+    const unsigned long long khi = (unsigned long long)r0.x | ((unsigned long long)(r0.w & 3u) << 32) | KEY_OCC;
     unsigned long long slot = fc_mix64(klo ^ fc_mix64(khi)) & kmask;
     for (;;) {
-      // L1-cached look first: entries never change once written, so a cached entry is as good as the one in L2 (the
-      // slot of a popular junction is read by thousands of threads); a cached EMPTY may be stale: ask L2
-      ulonglong2 cur = *reinterpret_cast<const ulonglong2*>(keys + slot);
-      if (cur.x == 0ull && cur.y == 0ull) cur = __ldcg(reinterpret_cast<const ulonglong2*>(keys + slot));
-      if (cur.x == 0ull && cur.y == 0ull) {
-        // ids are handed out before the insert is known to succeed: a lost race leaves an unused id (a hole that the
-        // finish pass skips) instead of making the other threads wait for the winner to publish one
-        const unsigned int j = atomicAdd(&ctr[FC_N_ALLOC], 1u);
-        if (j >= acap) {
-          atomicAdd(&ctr[FC_N_OVERFLOW], 1u);
-          break;
-        }
-        const U128 old = cas128(keys + slot, U128{0ull, 0ull}, U128{klo, khi | ((unsigned long long)(j + 1u) << 34)});
+      // L1-cached look: the identity never changes once written and the extrema only grow, so a cached copy is as
+      // good as the one in L2 (the slot of a popular junction is read by thousands of threads); a cached EMPTY may be
+      // stale: the compare-and-swap below then returns the real owner
+      unsigned long long v[4];
+      ld_sector(slots + slot, v);
+      if (v[0] == 0ull && v[1] == 0ull) {
+        const U128 old = cas128(reinterpret_cast<U128*>(slots + slot), U128{0ull, 0ull}, U128{klo, khi});
         if (old.lo == 0ull && old.hi == 0ull) {
-          jid = j;
-          acc[j].sig = (r0.w >> 16) & 0xFFFu;
-          acc[j].slot = (unsigned int)slot;
+          jid = (unsigned int)slot;  // a new junction: list it for the finish pass
+          slots[slot].sig = (r0.w >> 16) & 0xFFFu;
+          const unsigned int pos = atomicAdd(&ctr[FC_N_ALLOC], 1u);
+          if (pos < lcap)
+            list[pos] = (unsigned int)slot;
+          else
+            atomicAdd(&ctr[FC_N_OVERFLOW], 1u);
           break;
         }
-        cur.x = old.lo;
-        cur.y = old.hi;
+        v[0] = old.lo;
+        v[1] = old.hi;
+        v[2] = v[3] = 0ull;  // extrema unknown: "nothing yet" is a valid (stale) view
       }
-      if (cur.x == klo && (cur.y & KEY_HI_MASK) == khi) {
-        jid = (unsigned int)(cur.y >> 34) - 1u;
+      if (v[0] == klo && v[1] == khi) {
+        jid = (unsigned int)slot;
+        cur_f = v[2];
+        cur_x = v[3];
         break;
       }
       slot = (slot + 1ull) & kmask;
     }
   }
   // ---- how often does the CTA see this junction?
-  const bool ok = jid != 0xFFFFFFFFu;
   const unsigned int sk_slot = (jid * 0x85EBCA6Bu) >> (32 - SKETCH_BITS);
-  if (ok) atomicAdd(&sketch[sk_slot], 1u);
+  if (active) atomicAdd(&sketch[sk_slot], 1u);
   __syncthreads();
   if (active) {
     // fc_jrec: chrom,start,end,sk | idx, read_hash | qname_hash, q_left,q_right, n_hits,dist,ov
@@ -478,7 +504,7 @@ __global__ void __launch_bounds__(ACC_THREADS) fused_accumulate_kernel(RecSrc sr
     const int q_left = (int)(short)(r2.z & 0xFFFFu), q_right = (int)(short)(r2.z >> 16);
     const unsigned n_hits = r2.w & 0xFFFFu, dist = (r2.w >> 16) & 0xFFu, ov = r2.w >> 24;
     const unsigned sk = r0.w;
-    JAcc2* a = acc + (ok ? jid : 0u);
+    JSlot* a = slots + jid;
 
     // ---- lanes of the warp that share the junction; a junction seen twice in the CTA goes through shared memory
     const unsigned lane = threadIdx.x & 31;
@@ -486,29 +512,31 @@ __global__ void __launch_bounds__(ACC_THREADS) fused_accumulate_kernel(RecSrc sr
     const unsigned group = __popc(peers);
     const bool lead = (int)lane == __ffs((int)peers) - 1;
     int he = -1;
-    if (ok && (group >= 2u || sketch[sk_slot] >= 2u)) {
+    if (group >= 2u || sketch[sk_slot] >= 2u) {
       if (lead) he = hot_find_or_insert(hot, jid);
       he = __shfl_sync(peers, he, __ffs((int)peers) - 1);
     }
 
     // ---- extrema
     const unsigned long long f = ~idx;
-    const unsigned ql = (unsigned)(q_left + 32769), qr = (unsigned)(q_right + 32769);
     if (he >= 0) {
+      const unsigned ql = (unsigned)(q_left + 32768), qr = (unsigned)(q_right + 32768);
+      const unsigned idist = 255u - dist, iov = 255u - ov, inh = 65535u - n_hits;
       if (f > hot.first_inv[he]) atomicMax(&hot.first_inv[he], f);
       if (ql > hot.qmax_l[he]) atomicMax(&hot.qmax_l[he], ql);
       if (qr > hot.qmax_r[he]) atomicMax(&hot.qmax_r[he], qr);
-      if (~dist > hot.inv_dist[he]) atomicMax(&hot.inv_dist[he], ~dist);
-      if (~ov > hot.inv_ov[he]) atomicMax(&hot.inv_ov[he], ~ov);
-      if (~n_hits > hot.inv_nh[he]) atomicMax(&hot.inv_nh[he], ~n_hits);
-    } else if (ok) {
-      extrema_to_global(a, f, ql, qr, ~dist, ~ov, ~n_hits);
+      if (idist > hot.inv_dist[he]) atomicMax(&hot.inv_dist[he], idist);
+      if (iov > hot.inv_ov[he]) atomicMax(&hot.inv_ov[he], iov);
+      if (inh > hot.inv_nh[he]) atomicMax(&hot.inv_nh[he], inh);
+    } else {
+      extrema_to_global(a, f, ext_pack(q_left, q_right, dist, ov, n_hits), cur_f, cur_x);
     }
 
     // ---- distinct reads / fragment names of the junction
-    const unsigned long long tag = (unsigned long long)(jid + 1u);  // never 0: no entry is all-zero
+    const unsigned long long tag = (unsigned long long)jid + 1ull;  // never 0: no entry is all-zero
     bool new_read = false, new_name = false;
-    if (ok) set_insert2(sets, smask, read_hash, tag, s_read, qname_hash, tag | (1ull << 32), s_name, new_read, new_name);
+    set_insert2(sets, smask, read_hash, tag, s_read, !name_known, qname_hash, tag | (1ull << 32), s_name, new_read, new_name);
+    const bool dup_name = name_known ? (sk & SK_NAME_DUP) != 0u : !new_name;
 
     // ---- counters
     const unsigned den = (sk >> 8) & 0xFFu;
@@ -516,36 +544,37 @@ __global__ void __launch_bounds__(ACC_THREADS) fused_accumulate_kernel(RecSrc sr
     if (cls == 4) atomicAdd(&ctr[FC_N_OTHER], 1u);
     const unsigned fx = cls < 4 ? (8u >> cls) : 0u;
     const bool bridge = q_left != 0 && q_right != 0;
-    const bool pal = read_hash & 1ull;
+    const unsigned nb = bridge ? 0u : fx;
+    const unsigned c2 = new_read ? (unsigned)(read_hash & 1ull) : 2u;  // (bit 0 of the hash flags a palindromic read)
     if (__all_sync(amask, group == 1u)) {
       // no two lanes of the warp share a junction (the usual case)
       if (he >= 0) {
-        atomicAdd(&hot.cnt[he], 1u | ((unsigned)new_name << 16));
-        atomicAdd(&hot.wb[he], fx | ((bridge ? fx : 0u) << 16));
-        if (new_read) atomicAdd(&hot.uniq2[he], pal ? 1u : 2u);
-      } else if (ok) {
-        atomicAdd(&a->spanned_frags, 1ull | ((unsigned long long)new_name << 32));
-        atomicAdd(&a->w_b, (unsigned long long)fx | ((unsigned long long)(bridge ? fx : 0u) << 32));
-        if (new_read) atomicAdd(&a->uniq2, pal ? 1u : 2u);
+        atomicAdd(&hot.c0[he], 1u | (fx << 16));
+        if (nb | (unsigned)dup_name) atomicAdd(&hot.c1[he], nb | ((unsigned)dup_name << 16));
+        if (c2) atomicAdd(&hot.c2[he], c2);
+      } else {
+        atomicAdd(&a->c0, 1ull | ((unsigned long long)fx << 32));
+        if (nb | (unsigned)dup_name) atomicAdd(&a->c1, (unsigned long long)nb | ((unsigned long long)dup_name << 32));
+        if (c2) atomicAdd(&a->c2, (unsigned long long)c2);
       }
     } else {
       unsigned w = 0, b = 0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         w += (8u >> k) * __popc(__ballot_sync(amask, cls == k) & peers);
-        b += (8u >> k) * __popc(__ballot_sync(amask, cls == k && bridge) & peers);
+        b += (8u >> k) * __popc(__ballot_sync(amask, cls == k && !bridge) & peers);
       }
-      const unsigned names = __popc(__ballot_sync(amask, new_name) & peers);
-      const unsigned u2 = 2u * __popc(__ballot_sync(amask, new_read && !pal) & peers) + __popc(__ballot_sync(amask, new_read && pal) & peers);
-      if (ok && lead) {
+      const unsigned dups = __popc(__ballot_sync(amask, dup_name) & peers);
+      const unsigned c2s = 2u * __popc(__ballot_sync(amask, c2 == 2u) & peers) + __popc(__ballot_sync(amask, c2 == 1u) & peers);
+      if (lead) {
         if (he >= 0) {
-          atomicAdd(&hot.cnt[he], group | (names << 16));
-          atomicAdd(&hot.wb[he], w | (b << 16));
-          if (u2) atomicAdd(&hot.uniq2[he], u2);
+          atomicAdd(&hot.c0[he], group | (w << 16));
+          if (b | dups) atomicAdd(&hot.c1[he], b | (dups << 16));
+          if (c2s) atomicAdd(&hot.c2[he], c2s);
         } else {
-          atomicAdd(&a->spanned_frags, (unsigned long long)group | ((unsigned long long)names << 32));
-          atomicAdd(&a->w_b, (unsigned long long)w | ((unsigned long long)b << 32));
-          if (u2) atomicAdd(&a->uniq2, u2);
+          atomicAdd(&a->c0, (unsigned long long)group | ((unsigned long long)w << 32));
+          if (b | dups) atomicAdd(&a->c1, (unsigned long long)b | ((unsigned long long)dups << 32));
+          if (c2s) atomicAdd(&a->c2, (unsigned long long)c2s);
         }
       }
     }
@@ -553,38 +582,43 @@ __global__ void __launch_bounds__(ACC_THREADS) fused_accumulate_kernel(RecSrc sr
   __syncthreads();
   for (int e = threadIdx.x; e < HOT_ENTRIES; e += blockDim.x) {
     if (hot.tag[e] == 0u) continue;
-    JAcc2* a = acc + (hot.tag[e] - 1u);
-    extrema_to_global(a, hot.first_inv[e], hot.qmax_l[e], hot.qmax_r[e], hot.inv_dist[e], hot.inv_ov[e], hot.inv_nh[e]);
-    const unsigned c = hot.cnt[e], wb = hot.wb[e], u2 = hot.uniq2[e];
-    atomicAdd(&a->spanned_frags, (unsigned long long)(c & 0xFFFFu) | ((unsigned long long)(c >> 16) << 32));
-    atomicAdd(&a->w_b, (unsigned long long)(wb & 0xFFFFu) | ((unsigned long long)(wb >> 16) << 32));
-    if (u2) atomicAdd(&a->uniq2, u2);
+    JSlot* a = slots + (hot.tag[e] - 1u);
+    const unsigned long long x = (unsigned long long)(hot.qmax_l[e] | (hot.qmax_r[e] << 16)) |
+                                 ((unsigned long long)(hot.inv_ov[e] | (hot.inv_dist[e] << 8) | (hot.inv_nh[e] << 16)) << 32);
+    const ulonglong2 cur = __ldcg(reinterpret_cast<const ulonglong2*>(&a->first_inv));
+    extrema_to_global(a, hot.first_inv[e], x, cur.x, cur.y);
+    const unsigned c0 = hot.c0[e], c1 = hot.c1[e], c2 = hot.c2[e];
+    atomicAdd(&a->c0, (unsigned long long)(c0 & 0xFFFFu) | ((unsigned long long)(c0 >> 16) << 32));
+    if (c1) atomicAdd(&a->c1, (unsigned long long)(c1 & 0xFFFFu) | ((unsigned long long)(c1 >> 16) << 32));
+    if (c2) atomicAdd(&a->c2, (unsigned long long)c2);
   }
 }
 
-__device__ __forceinline__ fc_junction junction_from_acc(const JAcc2& a, const U128& k, unsigned long long first_idx) {
+__device__ __forceinline__ fc_junction junction_from_slot(const JSlot& a, unsigned long long first_idx) {
   fc_junction o;
-  o.chrom = (uint32_t)k.hi;
-  o.start = (uint32_t)k.lo;
-  o.end = (uint32_t)(k.lo >> 32);
-  o.sk = ((uint32_t)(k.hi >> 32) & 3u) | (a.sig << 16);
+  o.chrom = (uint32_t)a.khi;
+  o.start = (uint32_t)a.klo;
+  o.end = (uint32_t)(a.klo >> 32);
+  o.sk = ((uint32_t)(a.khi >> 32) & 3u) | (a.sig << 16);
   o.first_idx = first_idx;
-  o.n_weighted = (double)(uint32_t)a.w_b / 8.0;  // exact: every weight is k/8
-  o.n_uniq_bridges = (double)(uint32_t)(a.w_b >> 32) / 8.0;
-  o.n_spanned = (uint32_t)a.spanned_frags;
-  o.n_frags = (uint32_t)(a.spanned_frags >> 32);
+  const uint32_t n_spanned = (uint32_t)a.c0, w8 = (uint32_t)(a.c0 >> 32);
+  o.n_weighted = (double)w8 / 8.0;  // exact: every weight is k/8
+  o.n_uniq_bridges = (double)(w8 - (uint32_t)a.c1) / 8.0;
+  o.n_spanned = n_spanned;
+  o.n_frags = n_spanned - (uint32_t)(a.c1 >> 32);
   // len(uniq)/2 with uniq = {read, revcomp(read)}: a palindromic read contributes one element, not two
-  o.n_uniq = a.uniq2 / 2u;
-  o.best_q_left = (int16_t)((int)a.qmax_l - 32769);
-  o.best_q_right = (int16_t)((int)a.qmax_r - 32769);
-  o.min_n_hits = (uint16_t)~a.inv_nh;
-  o.min_dist = (uint8_t)~a.inv_dist;
-  o.min_ov = (uint8_t)~a.inv_ov;
+  o.n_uniq = (2u * n_spanned - (uint32_t)a.c2) / 2u;
+  const uint32_t lo = (uint32_t)a.ext, hi = (uint32_t)(a.ext >> 32);
+  o.best_q_left = (int16_t)((int)(lo & 0xFFFFu) - 32768);
+  o.best_q_right = (int16_t)((int)(lo >> 16) - 32768);
+  o.min_n_hits = (uint16_t)(65535u - (hi >> 16));
+  o.min_dist = (uint8_t)(255u - ((hi >> 8) & 0xFFu));
+  o.min_ov = (uint8_t)(255u - (hi & 0xFFu));
   o.pad = 0;
   return o;
 }
 
-__device__ __forceinline__ void clear_acc(JAcc2* a) {
+__device__ __forceinline__ void clear_slot(JSlot* a) {
   uint4* p = reinterpret_cast<uint4*>(a);
   const uint4 z = make_uint4(0u, 0u, 0u, 0u);
   p[0] = z;
@@ -599,25 +633,26 @@ __device__ __forceinline__ void clear_acc(JAcc2* a) {
 // (given, or summed here when there are few tiles) to a block-wide scan of its tile.
 constexpr int RANK_TILE = 1024;
 
-__global__ void mark_first_kernel(unsigned int* __restrict__ ctr, unsigned int acap, const JAcc2* __restrict__ acc,
-                                  unsigned long long idx_lo, unsigned long long range, uint32_t* __restrict__ flag,
-                                  uint32_t* __restrict__ tile_count) {
-  const unsigned int n_alloc = min(ctr[FC_N_ALLOC], acap);
+__global__ void mark_first_kernel(unsigned int* __restrict__ ctr, unsigned int lcap, const unsigned int* __restrict__ list,
+                                  const JSlot* __restrict__ slots, unsigned long long idx_lo, unsigned long long range,
+                                  uint32_t* __restrict__ flag, uint32_t* __restrict__ tile_count) {
+  const unsigned int n_alloc = min(ctr[FC_N_ALLOC], lcap);
   const unsigned int step = gridDim.x * blockDim.x;
   for (unsigned int j0 = blockIdx.x * blockDim.x; j0 < n_alloc; j0 += step) {  // warp-uniform trip count
     const unsigned int j = j0 + threadIdx.x;
     bool real = false;
     unsigned long long p = 0;
-    if (j < n_alloc && (uint32_t)acc[j].spanned_frags != 0u) {  // (0: an id that lost its insert race)
-      p = ~acc[j].first_inv - idx_lo;
+    if (j < n_alloc) {
+      const unsigned int slot = list[j];
+      p = ~slots[slot].first_inv - idx_lo;
       if (p < range) {
         real = true;
-        flag[p] = j + 1u;
+        flag[p] = slot + 1u;
       } else {
         atomicAdd(&ctr[FC_N_OVERFLOW], 1u);  // a record outside the declared idx range: the call goes to the sort-based path
       }
     }
-    // early ids are early discoveries: neighbouring lanes mostly hit the same tile, so count once per warp and tile
+    // early list entries are early discoveries: neighbouring lanes mostly hit the same tile, so count once per warp and tile
     const unsigned int tile = real ? (unsigned int)(p / RANK_TILE) : 0xFFFFFFFFu;
     const unsigned peers = __match_any_sync(0xffffffffu, tile);
     if (real && (int)(threadIdx.x & 31) == __ffs((int)peers) - 1) atomicAdd(&tile_count[tile], (unsigned int)__popc(peers));
@@ -632,8 +667,8 @@ __global__ void __launch_bounds__(FINISH_THREADS) finish_dense_kernel(int64_t ra
                                                                        const uint32_t* __restrict__ flag,
                                                                        const uint32_t* __restrict__ tile_count,
                                                                        const uint32_t* __restrict__ tile_base,
-                                                                       JAcc2* __restrict__ acc, U128* __restrict__ keys,
-                                                                       fc_junction* __restrict__ out, unsigned int* __restrict__ ctr,
+                                                                       JSlot* __restrict__ slots, fc_junction* __restrict__ out,
+                                                                       unsigned int* __restrict__ ctr,
                                                                        const unsigned long long* __restrict__ counters,
                                                                        unsigned long long* __restrict__ h_counters) {
   typedef cub::BlockScan<uint32_t, FINISH_THREADS> Scan;
@@ -681,31 +716,27 @@ __global__ void __launch_bounds__(FINISH_THREADS) finish_dense_kernel(int64_t ra
 #pragma unroll
   for (int k = 0; k < FINISH_ITEMS; ++k) {
     if (!f[k]) continue;
-    JAcc2* ap = acc + (f[k] - 1u);
-    const JAcc2 a = *ap;
-    const ulonglong2 kk = *reinterpret_cast<const ulonglong2*>(keys + a.slot);
-    out[o++] = junction_from_acc(a, U128{kk.x, kk.y}, idx_lo + (unsigned long long)(p0 + k));
-    keys[a.slot] = U128{0ull, 0ull};
-    clear_acc(ap);
+    JSlot* ap = slots + (f[k] - 1u);
+    const JSlot a = *ap;
+    out[o++] = junction_from_slot(a, idx_lo + (unsigned long long)(p0 + k));
+    clear_slot(ap);
   }
 }
 
 // records in arbitrary order (peer-to-peer emit, explicit idx): compact in any order, sorted by first idx afterwards
-__global__ void finish_unordered_kernel(unsigned int* __restrict__ ctr, unsigned int acap, JAcc2* __restrict__ acc,
-                                        U128* __restrict__ keys, fc_junction* __restrict__ out,
+__global__ void finish_unordered_kernel(unsigned int* __restrict__ ctr, unsigned int lcap, const unsigned int* __restrict__ list,
+                                        JSlot* __restrict__ slots, fc_junction* __restrict__ out,
                                         uint64_t* __restrict__ order_key, uint32_t* __restrict__ order_val) {
-  const unsigned int n_alloc = min(ctr[FC_N_ALLOC], acap);
+  const unsigned int n_alloc = min(ctr[FC_N_ALLOC], lcap);
   for (unsigned int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_alloc; j += gridDim.x * blockDim.x) {
-    const JAcc2 a = acc[j];
-    if ((uint32_t)a.spanned_frags == 0u) continue;
+    JSlot* ap = slots + list[j];
+    const JSlot a = *ap;
     const unsigned int pos = atomicAdd(&ctr[FC_N_JUNC], 1u);
-    const ulonglong2 kk = *reinterpret_cast<const ulonglong2*>(keys + a.slot);
     const unsigned long long first_idx = ~a.first_inv;
-    out[pos] = junction_from_acc(a, U128{kk.x, kk.y}, first_idx);
+    out[pos] = junction_from_slot(a, first_idx);
     order_key[pos] = first_idx;
     order_val[pos] = pos;
-    keys[a.slot] = U128{0ull, 0ull};
-    clear_acc(acc + j);
+    clear_slot(ap);
   }
 }
 
@@ -1149,12 +1180,12 @@ struct StageTimer {
 static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st, const RecSrc& src) {
   fc_agg& a = ctx->agg;
   if (ub >= FUSED_MAX_RECORDS) return -100;
-  // key table: one entry per junction, at most one junction per record (load <= 2/3); distinct set: two entries per record
-  // (load <= 2/3 when every read and every name is new, about half of that on real input)
+  // junction table: one 64-byte slot per junction, at most one junction per record (load <= 0.8); distinct set: up to two
+  // entries per record (load <= 2/3 when every read and every name is new)
   unsigned long long kcap = 1024, scap = 2048;
-  while (2ull * kcap < 3ull * (unsigned long long)ub) kcap <<= 1;
+  while (4ull * kcap < 5ull * (unsigned long long)ub) kcap <<= 1;
   while (scap < 3ull * (unsigned long long)ub) scap <<= 1;
-  const unsigned int acap = (unsigned int)(ub + ub / 8 + 65536);  // junction ids incl. the ones lost to insert races
+  const unsigned int lcap = (unsigned int)ub + 1024u;  // list of the occupied slots (one entry per junction)
   int rc;
   StageTimer tm(ctx, st);
   tm.mark("start");
@@ -1164,11 +1195,10 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st, const Re
     a.sets_clean = false;
     a.f_keys.release();
     a.f_sets.release();
-    a.f_acc.release();
     a.f_dirty = false;
   }
-  if ((rc = reserve_clean(ctx, a.f_keys, (size_t)kcap * 16, st))) return rc;
-  if ((rc = reserve_clean(ctx, a.f_acc, (size_t)acap * sizeof(JAcc2), st))) return rc;
+  if ((rc = reserve_clean(ctx, a.f_keys, (size_t)kcap * sizeof(JSlot), st))) return rc;
+  FC_CUDA(ctx, a.f_acc.reserve((size_t)lcap * sizeof(unsigned int), st, false, 0));
   if (!(a.sets_clean && (size_t)scap * 16 <= a.sets_used && (size_t)scap * 16 <= a.f_sets.cap)) {
     FC_CUDA(ctx, a.f_sets.reserve((size_t)scap * 16, st, false, 0));
     FC_CUDA(ctx, cudaMemsetAsync(a.f_sets.p, 0, (size_t)scap * 16, st));
@@ -1194,8 +1224,8 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st, const Re
     tile_count = (uint32_t*)a.scratch[1].p;
   }
   tm.mark("clear");
-  fused_accumulate_kernel<<<nblk(ub, ACC_THREADS), ACC_THREADS, 0, st>>>(src, (U128*)a.f_keys.p, kcap - 1, (U128*)a.f_sets.p,
-                                                                         scap - 1, (JAcc2*)a.f_acc.p, acap, ctr, flag, range,
+  fused_accumulate_kernel<<<nblk(ub, ACC_THREADS), ACC_THREADS, 0, st>>>(src, (JSlot*)a.f_keys.p, kcap - 1, (U128*)a.f_sets.p,
+                                                                         scap - 1, (unsigned int*)a.f_acc.p, lcap, ctr, flag, range,
                                                                          tile_count, n_tiles);
   FC_LAUNCH_CHECK(ctx);
   tm.mark("accumulate");
@@ -1205,8 +1235,8 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st, const Re
   uint32_t* vA = nullptr;
   fc_junction* tmpj = nullptr;
   if (dense) {
-    mark_first_kernel<<<sweep_blocks, 256, 0, st>>>(ctr, acap, (const JAcc2*)a.f_acc.p, a.idx_lo, (unsigned long long)range, flag,
-                                                    tile_count);
+    mark_first_kernel<<<sweep_blocks, 256, 0, st>>>(ctr, lcap, (const unsigned int*)a.f_acc.p, (const JSlot*)a.f_keys.p, a.idx_lo,
+                                                    (unsigned long long)range, flag, tile_count);
     FC_LAUNCH_CHECK(ctx);
     uint32_t* tile_base = nullptr;
     if (n_tiles > 4096) {  // many tiles: scan the counts once instead of summing them in every block
@@ -1219,8 +1249,8 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st, const Re
     }
     tm.mark("mark");
     finish_dense_kernel<<<(unsigned)n_tiles, FINISH_THREADS, 0, st>>>(range, a.idx_lo, flag, tile_count, tile_base,
-                                                                       (JAcc2*)a.f_acc.p, (U128*)a.f_keys.p,
-                                                                       (fc_junction*)a.junctions.p, ctr, counters, a.h_pinned);
+                                                                       (JSlot*)a.f_keys.p, (fc_junction*)a.junctions.p, ctr, counters,
+                                                                       a.h_pinned);
     FC_LAUNCH_CHECK(ctx);
   } else {
     FC_CUDA(ctx, a.scratch[5].reserve((size_t)ub * sizeof(fc_junction), st, false, 0));
@@ -1231,7 +1261,7 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st, const Re
     kA = (uint64_t*)a.scratch[3].p;
     kB = (uint64_t*)a.scratch[4].p;
     vA = (uint32_t*)a.scratch[6].p;
-    finish_unordered_kernel<<<sweep_blocks, 256, 0, st>>>(ctr, acap, (JAcc2*)a.f_acc.p, (U128*)a.f_keys.p, tmpj, kA, vA);
+    finish_unordered_kernel<<<sweep_blocks, 256, 0, st>>>(ctr, lcap, (const unsigned int*)a.f_acc.p, (JSlot*)a.f_keys.p, tmpj, kA, vA);
     FC_LAUNCH_CHECK(ctx);
   }
   // one round trip: exact record count, junction count, fallback conditions, peer-to-peer overflow
