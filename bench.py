@@ -229,6 +229,20 @@ class Shard(object):
         self.hits = torch.zeros(n * 4, dtype=torch.int32, device=dev)
         self.pairs = self._pairs(eng, n)
         self.pay = (s["wden"], s["q_a"], s["q_b"], s["read_hash"], s["qname_hash"])
+        # the packed form the scan kernels read (what a native ingest writes directly): 16-byte descriptors, read rows, q words
+        self.nw = eng.batch_words(self.max_l)
+        self.meta = torch.zeros(n * 4, dtype=torch.int32, device=dev)
+        self.rows = torch.zeros(n * 2 * self.nw, dtype=torch.int32, device=dev)
+        self.rn_rows = torch.zeros(n * self.nw, dtype=torch.int32, device=dev)
+        self.q = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.batch = eng.pack_batch(self.pairs, self.meta, self.rows, self.rn_rows, s["wden"], s["q_a"], s["q_b"], self.q, None, stream)
+        torch.cuda.synchronize()
+
+    def batch_prefix(self, m):
+        from find_circ2_b200._lib import Batch
+
+        b = self.batch
+        return Batch(m, b.d_meta, b.d_reads, b.d_rn, b.n_words, b.max_l)
 
     def _pairs(self, eng, m):
         """fc_pairs over the first m rows (the planes keep the stride of the whole shard)"""
@@ -290,7 +304,7 @@ def multi_gpu_parity(eng, sh, dist, dev, idx_base, total, m=100000):
     stream = torch.cuda.current_stream().cuda_stream
     eng.agg_reset_async(stream)
     eng.agg_set_idx_range(0, total)
-    eng.scan_emit_p2p(sh._pairs(eng, m), sh.hits, *sh.pay, idx_base, stream)
+    eng.scan_emit_batch(sh.batch_prefix(m), sh.hits, sh.q, sh.d["read_hash"], sh.d["qname_hash"], idx_base, stream)
     parallel.stream_barrier(dist, dev, eng, stream)
     nj = eng.agg_finalize(stream)
     got = parallel.gather_junctions(eng.agg_fetch(nj), dist, dev)
@@ -377,12 +391,14 @@ def bench_config(args, cfg, dist, dev, primary, error_rate=None):
         if ev:
             ev[0].record()
         if world == 1:
-            eng.scan_emit(sh.pairs, sh.hits, *sh.pay, idx_base, stream)  # scan + record in one kernel (fc_scan_emit)
+            # scan + record in one kernel (fc_scan_emit_batch)
+            eng.scan_emit_batch(sh.batch, sh.hits, sh.q, d["read_hash"], d["qname_hash"], idx_base, stream)
             if ev:
                 ev[1].record()
                 ev[2].record()
         elif use_p2p:
-            eng.scan_emit_p2p(sh.pairs, sh.hits, *sh.pay, idx_base, stream)  # records land in the owner ranks' buffers
+            # the same kernel, records land in the owner ranks' buffers (the context is connected to its peers)
+            eng.scan_emit_batch(sh.batch, sh.hits, sh.q, d["read_hash"], d["qname_hash"], idx_base, stream)
             if ev:
                 ev[1].record()
             parallel.stream_barrier(dist, dev, eng, stream)  # ends the step: counts published, every rank's records have landed

@@ -47,6 +47,12 @@ class Pairs(C.Structure):
     ]
 
 
+class Batch(C.Structure):
+    """fc_batch: the packed layout the scan kernels read"""
+    _fields_ = [("n", C.c_int64), ("d_meta", C.c_void_p), ("d_reads", C.c_void_p), ("d_rn", C.c_void_p), ("n_words", C.c_int32),
+                ("max_l", C.c_int32)]
+
+
 # numpy views of the C structs
 HIT_DTYPE = np.dtype([("start", "<i4"), ("end", "<i4"), ("w2", "<u4"), ("w3", "<u4")])
 JREC_DTYPE = np.dtype(
@@ -77,12 +83,17 @@ SYMBOLS = [
     ("fc_genome_n_chrom", C.c_int, [_P]),
     ("fc_genome_chrom_name", C.c_int, [_P, C.c_int32, C.c_char_p, C.c_int32]),
     ("fc_genome_chrom_size", C.c_int64, [_P, C.c_int32]),
+    ("fc_genome_chrom_offset", C.c_int64, [_P, C.c_int32]),
     ("fc_genome_chrom_id", C.c_int, [_P, C.c_char_p]),
     ("fc_genome_stats", C.c_int, [_P, _P]),
     ("fc_genome_fetch", C.c_int, [_P, C.c_int32, C.c_int64, C.c_int64, _P]),
     ("fc_pack_reads", C.c_int, [_P, C.c_int64, _P, C.c_int32, _P, C.c_int32, _P, _P, _P, _P, _P]),
     ("fc_scan", C.c_int, [_P, C.POINTER(ScanParams), C.POINTER(Pairs), _P, _P]),
     ("fc_scan_emit", C.c_int, [_P, C.POINTER(ScanParams), C.POINTER(Pairs), _P, _P, _P, _P, _P, _P, C.c_uint64, _P, _P]),
+    ("fc_batch_words", C.c_int32, [C.c_int32]),
+    ("fc_batch_pack", C.c_int, [_P, C.POINTER(Pairs), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    ("fc_scan_batch", C.c_int, [_P, C.POINTER(ScanParams), _P, _P, _P]),
+    ("fc_scan_emit_batch", C.c_int, [_P, C.POINTER(ScanParams), _P, _P, _P, _P, _P, C.c_uint64, _P, _P]),
     ("fc_scan_ties", C.c_int, [_P, C.POINTER(ScanParams), C.POINTER(Pairs), _P, _P, _P, _P]),
     ("fc_scan_host", C.c_int, [_P, C.POINTER(ScanParams), C.c_int64, _P, _P, _P, _P, _P, _P, C.c_int32, _P]),
     ("fc_batch_host", C.c_int, [_P, C.POINTER(ScanParams), C.c_int64, _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P,

@@ -77,7 +77,9 @@ __global__ void __launch_bounds__(256) emit_kernel(int64_t n, const fc_hit* __re
       fl = flags[i];
     }
   }
-  fc::emit_block<256>(accept, i, h.start, h.end, h.w2, h.w3, c, fl, e);
+  fc_jrec r;
+  if (accept) r = fc::make_record(i, h.start, h.end, h.w2, h.w3, c, fl, e);
+  fc::emit_block<256>(accept, r, e.n_recs, e.recs);
 }
 
 __global__ void key_hash_kernel(int64_t n, const fc_jrec* __restrict__ recs, uint64_t seed, uint64_t* __restrict__ h,
@@ -1556,7 +1558,9 @@ __global__ void __launch_bounds__(P2P_THREADS) emit_p2p_kernel(int64_t n, const 
       fl = flags[i];
     }
   }
-  fc::emit_p2p_block<P2P_THREADS>(accept, i, h.start, h.end, h.w2, h.w3, c, fl, e, pv, overflow);
+  fc_jrec r;
+  if (accept) r = fc::make_record(i, h.start, h.end, h.w2, h.w3, c, fl, e);
+  fc::emit_p2p_block<P2P_THREADS>(accept, r, pv, overflow);
 }
 
 static int p2p_reserve(fc_ctx* ctx, int64_t capacity_records) {

@@ -1,5 +1,6 @@
 // api.cu -- context life cycle, error reporting, pinned memory and the host-side hash helpers of the C ABI
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "fc_internal.cuh"
@@ -42,6 +43,10 @@ extern "C" int fc_ctx_create(int device, fc_ctx** out) {
     delete ctx;
     return fc_fail(nullptr, FC_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
   }
+  if (const char* e = getenv("FC_HOST_CHUNK")) {
+    const long long v = atoll(e);
+    if (v >= 1024) ctx->host_chunk = v;
+  }
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (ctx->sm_count <= 0) ctx->sm_count = 148;
   *out = ctx;
@@ -56,6 +61,7 @@ extern "C" void fc_ctx_destroy(fc_ctx* ctx) {
   fc_agg_release(ctx);
   for (auto& b : ctx->host_path) b.release();
   ctx->tie_off.release();
+  for (auto& b : ctx->pk) b.release();
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->own_stream2) {
     cudaStreamDestroy(ctx->own_stream2);

@@ -36,17 +36,12 @@ struct EmitArgs {
   fc_jrec* recs;               // record buffer of the context
 };
 
-struct P2PView;
-__device__ __forceinline__ fc_jrec make_record(int64_t i, int32_t h_start, int32_t h_end, uint32_t w2, uint32_t w3, uint32_t chrom,
-                                               uint32_t pair_flags, const EmitArgs& e);
-
 // Called by EVERY thread of a CTA of BS threads (BS a multiple of 32, at most 1024).  `accept` threads hand over their
-// pair (index i, hit words, chromosome id, pair flags).  The CTA claims its slots with one atomic on the record counter,
-// groups the records in shared memory and writes them as one run of consecutive 16-byte stores; the buffer is therefore
-// NOT in stream order -- every consumer orders by fc_jrec.idx where order matters.
+// record.  The CTA claims its slots with one atomic on the record counter, groups the records in shared memory and
+// writes them as one run of consecutive 16-byte stores; the buffer is therefore NOT in stream order -- every consumer
+// orders by fc_jrec.idx where order matters.
 template <int BS>
-__device__ __forceinline__ void emit_block(bool accept, int64_t i, int32_t h_start, int32_t h_end, uint32_t w2, uint32_t w3,
-                                           uint32_t chrom, uint32_t pair_flags, const EmitArgs& e) {
+__device__ __forceinline__ void emit_block(bool accept, const fc_jrec& r, unsigned long long* n_recs, fc_jrec* recs) {
   __shared__ unsigned int s_warp[BS / 32];
   __shared__ unsigned int s_total;
   __shared__ unsigned long long s_base;
@@ -64,11 +59,10 @@ __device__ __forceinline__ void emit_block(bool accept, int64_t i, int32_t h_sta
       total += c;
     }
     s_total = total;
-    s_base = total ? atomicAdd(e.n_recs, (unsigned long long)total) : 0ull;
+    s_base = total ? atomicAdd(n_recs, (unsigned long long)total) : 0ull;
   }
   __syncthreads();
   if (accept) {
-    const fc_jrec r = make_record(i, h_start, h_end, w2, w3, chrom, pair_flags, e);
     uint4* stage = s_rec + (size_t)(s_warp[warp] + __popc(ballot & ((1u << lane) - 1u))) * 3;
     const uint4* src = reinterpret_cast<const uint4*>(&r);
     stage[0] = src[0];
@@ -76,7 +70,7 @@ __device__ __forceinline__ void emit_block(bool accept, int64_t i, int32_t h_sta
     stage[2] = src[2];
   }
   __syncthreads();
-  uint4* out = reinterpret_cast<uint4*>(e.recs + s_base);
+  uint4* out = reinterpret_cast<uint4*>(recs + s_base);
   for (unsigned int w = threadIdx.x; w < s_total * 3u; w += BS) out[w] = s_rec[w];
 }
 
@@ -97,26 +91,32 @@ struct P2PView {
 constexpr int FC_CNT_SRC = 16;    // counter words [16, 24): records this rank has sent to destination d in this step
 constexpr int FC_CNT_SLICE = 40;  // counter words [40, 56): [parity][source] records received from source in the step
 
-__device__ __forceinline__ fc_jrec make_record(int64_t i, int32_t h_start, int32_t h_end, uint32_t w2, uint32_t w3, uint32_t chrom,
-                                               uint32_t pair_flags, const EmitArgs& e) {
+// one Hit.add() call as a record (find_circ.py:526-582): hit words of the scan + the payload of the pair
+__device__ __forceinline__ fc_jrec make_record_from(int32_t h_start, int32_t h_end, uint32_t w2, uint32_t w3, uint32_t chrom,
+                                                    uint32_t pair_flags, uint32_t wden, int16_t q_a, int16_t q_b, uint64_t rh,
+                                                    uint64_t qh, uint64_t idx) {
   const bool backsplice = pair_flags & FC_PF_BACKSPLICE;
   fc_jrec r;
   r.chrom = chrom;
   r.start = (uint32_t)h_start;
   r.end = (uint32_t)h_end;
   const uint32_t strand = w3 & 1u, sig = (w3 >> 1) & 0xFFFu;
-  const uint64_t rh = e.read_hash[i];
-  r.sk = strand | (backsplice ? 0u : 2u) | ((uint32_t)(rh & 1ull) << 2) | ((uint32_t)e.wden[i] << 8) | (sig << 16);
-  r.idx = e.idx ? e.idx[i] : e.idx_base + (uint64_t)i;
+  r.sk = strand | (backsplice ? 0u : 2u) | ((uint32_t)(rh & 1ull) << 2) | (wden << 8) | (sig << 16);
+  r.idx = idx;
   r.read_hash = rh;
-  r.qname_hash = e.qname_hash[i];
+  r.qname_hash = qh;
   // by convention A precedes B in the genome: swap for back-splices (find_circ.py:552-553)
-  r.q_left = backsplice ? e.q_b[i] : e.q_a[i];
-  r.q_right = backsplice ? e.q_a[i] : e.q_b[i];
+  r.q_left = backsplice ? q_b : q_a;
+  r.q_right = backsplice ? q_a : q_b;
   r.n_hits = (uint16_t)(w2 & 0xFFFFu);
   r.dist = (uint8_t)((w2 >> 16) & 0xFFu);
   r.ov = (uint8_t)(w2 >> 24);
   return r;
+}
+__device__ __forceinline__ fc_jrec make_record(int64_t i, int32_t h_start, int32_t h_end, uint32_t w2, uint32_t w3, uint32_t chrom,
+                                               uint32_t pair_flags, const EmitArgs& e) {
+  return make_record_from(h_start, h_end, w2, w3, chrom, pair_flags, e.wden[i], e.q_a[i], e.q_b[i], e.read_hash[i], e.qname_hash[i],
+                          e.idx ? e.idx[i] : e.idx_base + (uint64_t)i);
 }
 
 // Called by every thread of a CTA of BS threads.  The CTA's records are grouped by destination rank in shared memory;
@@ -124,18 +124,12 @@ __device__ __forceinline__ fc_jrec make_record(int64_t i, int32_t h_start, int32
 // in the owner's buffer; every group then goes out as one run of consecutive 16-byte stores -- full-size write packets
 // on NVLink instead of scattered 16-byte ones, and nothing on the CTA's critical path crosses the wire.
 template <int BS>
-__device__ __forceinline__ void emit_p2p_block(bool accept, int64_t i, int32_t h_start, int32_t h_end, uint32_t w2, uint32_t w3,
-                                               uint32_t chrom, uint32_t pair_flags, const EmitArgs& e, const P2PView& pv,
-                                               unsigned long long* overflow) {
+__device__ __forceinline__ void emit_p2p_block(bool accept, const fc_jrec& r, const P2PView& pv, unsigned long long* overflow) {
   __shared__ uint4 s_rec[BS * 3];
   __shared__ unsigned int s_cnt[8], s_off[9];
   __shared__ unsigned long long s_base[8];
-  fc_jrec r;
   int dest = 0;
-  if (accept) {
-    r = make_record(i, h_start, h_end, w2, w3, chrom, pair_flags, e);
-    dest = (int)(fc_key_hash(r.chrom, r.start, r.end, r.sk, 0x5bd1e995ULL) % (uint64_t)pv.world);
-  }
+  if (accept) dest = (int)(fc_key_hash(r.chrom, r.start, r.end, r.sk, 0x5bd1e995ULL) % (uint64_t)pv.world);
   if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
   __syncthreads();
   unsigned int local = 0;

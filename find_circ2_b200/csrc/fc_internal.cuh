@@ -102,7 +102,9 @@ struct fc_ctx {
   cudaEvent_t ev_chunk[2] = {nullptr, nullptr};
   fc_dbuf host_path[16];              // staging for fc_scan_host / fc_batch_host
   fc_dbuf tie_off;                    // fc_batch_ties_host: exclusive prefix sums of n_hits
+  fc_dbuf pk[4];                      // packed form (fc_batch) of an fc_pairs batch: descriptors, read rows, N rows, q
   int64_t launches = 0;
+  int64_t host_chunk = 1 << 20;       // pairs per chunk of the chunked host-buffer call (FC_HOST_CHUNK at fc_ctx_create)
   int sm_count = 148;
   // device state of the last fc_batch_host call (two-step batches)
   int64_t last_n = 0;

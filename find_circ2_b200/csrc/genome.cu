@@ -392,6 +392,11 @@ extern "C" int64_t fc_genome_chrom_size(fc_ctx* ctx, int32_t i) {
   return ctx->genome.sizes[i];
 }
 
+extern "C" int64_t fc_genome_chrom_offset(fc_ctx* ctx, int32_t i) {
+  if (!ctx || !ctx->genome.loaded || i < 0 || i >= (int32_t)ctx->genome.offs.size()) return -1;
+  return ctx->genome.offs[i];
+}
+
 extern "C" int fc_genome_chrom_id(fc_ctx* ctx, const char* name) {
   if (!ctx || !name) return -1;
   for (size_t i = 0; i < ctx->genome.names.size(); ++i)

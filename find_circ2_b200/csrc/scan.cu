@@ -41,85 +41,159 @@ __global__ void pack_reads_kernel(int64_t n, const uint8_t* __restrict__ ascii, 
   if (any) flags[i] |= (uint8_t)FC_PF_READ_N;
 }
 
+// ---------------------------------------------------------------- SoA batch -> packed batch (fc_batch)
+// One thread per pair.  The 16-byte descriptor carries the GLOBAL coordinates of both windows (so that the scan needs no
+// chromosome table before it can fetch its tiles) and the validity verdict of find_circ.py:194-211 (both windows must
+// touch the chromosome); the read planes go from word-major columns to one row per pair (one vector load in the scan).
+__global__ void pack_batch_kernel(fc::GenomeView g, int64_t n, const int32_t* __restrict__ chrom, const int32_t* __restrict__ a_start,
+                                  const int32_t* __restrict__ b_end, const int32_t* __restrict__ l, const uint8_t* __restrict__ flags,
+                                  const uint8_t* __restrict__ wden, const uint8_t* __restrict__ frag, fc::ReadView rv, int nw_out,
+                                  uint4* __restrict__ meta, uint32_t* __restrict__ reads, uint32_t* __restrict__ rn_out,
+                                  const int16_t* __restrict__ q_a, const int16_t* __restrict__ q_b, uint32_t* __restrict__ q_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t c = chrom[i], li = l[i];
+  uint32_t fl = flags[i] & 7u;
+  int64_t ga = 0, gb = 0;
+  bool ok = false;
+  if (li >= 0 && c >= 0 && c < g.n_chrom && li + 2 <= g.pad) {
+    const int64_t size = g.chrom_size[c];
+    const int w = li + 2;
+    const int64_t as = a_start[i], be = b_end[i];
+    ok = (uint64_t)(as + w) <= (uint64_t)(size + w) && (uint64_t)be <= (uint64_t)(size + w);
+    if (ok) {
+      const int64_t off = g.chrom_off[c];
+      ga = off + as;
+      gb = off + be - w;
+    }
+  }
+  if (!ok) fl |= FC_META_INVALID | (li < 0 ? FC_META_NEGATIVE : 0u);
+  const uint32_t fr = frag ? (uint32_t)(frag[i] & 15u) : 15u;  // 15 = (3,3): nothing known about the fragment's other rows
+  const uint32_t lfield = ok ? (uint32_t)li : 0u;
+  meta[i] = make_uint4((uint32_t)ga, (uint32_t)gb,
+                       (uint32_t)(ga >> 32) | ((uint32_t)(gb >> 32) << 6) | (lfield << 12) | (fl << 24) | (fr << 28),
+                       ((uint32_t)c & 0xFFFFFFu) | ((uint32_t)(wden ? wden[i] : 1u) << 24));
+  uint32_t* row = reads + i * (int64_t)(2 * nw_out);
+  for (int k = 0; k < nw_out; ++k) {
+    const bool have = k < rv.n_words;
+    row[k] = have ? rv.rlo[(int64_t)k * rv.stride + i * rv.pair_stride] : 0u;
+    row[nw_out + k] = have ? rv.rhi[(int64_t)k * rv.stride + i * rv.pair_stride] : 0u;
+  }
+  if ((fl & FC_PF_READ_N) && rn_out)
+    for (int k = 0; k < nw_out; ++k)
+      rn_out[i * (int64_t)nw_out + k] = k < rv.n_words ? rv.rn[(int64_t)k * rv.stride + i * rv.rn_pair_stride] : 0u;
+  if (q_out) q_out[i] = (uint32_t)(uint16_t)q_a[i] | ((uint32_t)(uint16_t)q_b[i] << 16);
+}
+
 // ---------------------------------------------------------------- the scan
-template <int NP, int T, int BS, int MB>
-__global__ void __launch_bounds__(BS, MB) scan_kernel(fc::GenomeView g, fc::ScanCfg cfg, fc::ReadView rv,
-                                                   const int32_t* __restrict__ chrom,
-                                                   const int32_t* __restrict__ a_start,
-                                                   const int32_t* __restrict__ b_end, const int32_t* __restrict__ l,
-                                                   const uint8_t* __restrict__ flags, fc_hit* __restrict__ out) {
-  const int64_t n = rv.n;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    fc::PairArgs p;
-    p.chrom = chrom[i];
-    p.a_start = a_start[i];
-    p.b_end = b_end[i];
-    p.l = l[i];
-    p.flags = flags[i];
-    fc::HitOut h;
-    fc::NoEmit ne;
-    fc::scan_pair<NP, T>(g, cfg, p, rv, i, h, ne, false);
-    reinterpret_cast<uint4*>(out)[i] = make_uint4((uint32_t)h.start, (uint32_t)h.end, h.w2, h.w3);
+struct BatchView {
+  const uint4* meta;
+  const uint32_t* reads;  // rows of 2 * nw words
+  const uint32_t* rn;     // rows of nw words (pairs flagged READ_N only)
+  int64_t n;
+  int32_t nw;
+};
+struct Payload {  // what becomes of an accepted pair (emit_core.cuh)
+  const uint32_t* q;  // q_a | q_b << 16
+  const uint64_t* read_hash;
+  const uint64_t* qname_hash;
+  uint64_t idx_base;
+  const uint64_t* idx;
+  unsigned long long* n_recs;
+  fc_jrec* recs;
+};
+
+// the read planes of pair i: one vector load per pair when the row is 8 or 16 bytes, two or four for 32 / 64 bytes
+// (nw is uniform over the launch: the branches do not diverge)
+template <int NP>
+__device__ __forceinline__ void load_read_row(const uint32_t* __restrict__ reads, int64_t i, int nw, uint32_t (&rlo)[NP],
+                                              uint32_t (&rhi)[NP]) {
+#pragma unroll
+  for (int k = 0; k < NP; ++k) rlo[k] = rhi[k] = 0u;
+  if (nw == 2) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(reads) + i);
+    rlo[0] = v.x;
+    rhi[0] = v.z;
+    if constexpr (NP >= 2) {
+      rlo[1] = v.y;
+      rhi[1] = v.w;
+    }
+  } else if (nw == 1) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(reads) + i);
+    rlo[0] = v.x;
+    rhi[0] = v.y;
+  } else if (nw == 4) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(reads) + 2 * i), c = __ldg(reinterpret_cast<const uint4*>(reads) + 2 * i + 1);
+    const uint32_t lo[4] = {a.x, a.y, a.z, a.w}, hi[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int k = 0; k < (NP < 4 ? NP : 4); ++k) {
+      rlo[k] = lo[k];
+      rhi[k] = hi[k];
+    }
+  } else {  // any other row length: scalar loads
+    const uint32_t* row = reads + i * (int64_t)(2 * nw);
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      if (k < nw) {
+        rlo[k] = __ldg(row + k);
+        rhi[k] = __ldg(row + nw + k);
+      }
+    }
   }
 }
 
-// the same scan, and every pair that found a breakpoint becomes a junction record on the way (fc_scan_emit): the hits
-// do not travel to HBM and back before they are turned into records, and one launch less stands in the step
-template <int NP, int T, int BS, int MB>
-__global__ void __launch_bounds__(BS, MB) scan_emit_kernel(fc::GenomeView g, fc::ScanCfg cfg, fc::ReadView rv,
-                                                        const int32_t* __restrict__ chrom,
-                                                        const int32_t* __restrict__ a_start,
-                                                        const int32_t* __restrict__ b_end, const int32_t* __restrict__ l,
-                                                        const uint8_t* __restrict__ flags, fc_hit* __restrict__ out,
-                                                        fc::EmitArgs e) {
-  const int64_t i = (int64_t)blockIdx.x * BS + threadIdx.x;  // one pair per thread: the whole CTA reaches emit_block
+// MODE 0: hits only; 1: every pair that found a breakpoint becomes a junction record of this context on the way (the hits
+// do not travel to HBM and back before they are turned into records, and one launch less stands in the step); 2: the
+// records go to the ranks that own their junction keys (multi-GPU)
+template <int NP, int T, int BS, int MB, int MODE>
+__global__ void __launch_bounds__(BS, MB) scan_kernel(fc::GenomeView g, fc::ScanCfg cfg, BatchView b, fc_hit* __restrict__ out,
+                                                   Payload e, fc::P2PView pv, unsigned long long* overflow) {
+  const int64_t i = (int64_t)blockIdx.x * BS + threadIdx.x;  // one pair per thread: the whole CTA reaches the emit
   fc::HitOut h;
   h.start = h.end = 0;
   h.w2 = h.w3 = 0u;
-  uint32_t c = 0, fl = 0;
-  if (i < rv.n) {
-    fc::PairArgs p;
-    p.chrom = chrom[i];
-    p.a_start = a_start[i];
-    p.b_end = b_end[i];
-    p.l = l[i];
-    p.flags = flags[i];
-    c = (uint32_t)p.chrom;
-    fl = p.flags;
-    fc::NoEmit ne;
-    fc::scan_pair<NP, T>(g, cfg, p, rv, i, h, ne, false);
+  uint4 m = make_uint4(0u, 0u, 0u, 0u);
+  if (i < b.n) {
+    m = __ldg(b.meta + i);
+    uint32_t rlo[NP], rhi[NP];
+    load_read_row<NP>(b.reads, i, b.nw, rlo, rhi);
+    const int64_t ga = (int64_t)m.x | ((int64_t)(m.z & 63u) << 32), gb = (int64_t)m.y | ((int64_t)((m.z >> 6) & 63u) << 32);
+    const int l = (int)((m.z >> 12) & 0xFFFu);
+    const uint32_t fl = (m.z >> 24) & 15u;
+    const bool backsplice = fl & 1u, minus_span = fl & 2u, read_n = fl & 4u;
+    fc::Best best;
+    best.init();
+    uint32_t extra = 0;
+    int64_t off = 0;
+    if (!(fl & FC_META_INVALID)) {
+      off = g.chrom_off[m.w & 0xFFFFFFu];  // (needed only to print the hit: in flight beside the tile loads)
+      fc::ReadView rv{b.reads, b.reads + b.nw, b.rn, b.n, b.nw, 1, 2 * (int64_t)b.nw, (int64_t)b.nw};
+      if (cfg.noncanonical || (l + 2 > 32 * NP)) {
+        extra |= fc::W3_SLOW;
+        fc::NoEmit ne;
+        fc::scan_per_base(g, cfg, ga, gb, l, minus_span, rv, i, read_n, best, ne);
+      } else {
+        fc::scan_fast<NP, T>(g, cfg, ga, gb, l, minus_span, read_n, rlo, rhi, rv, i, best);
+      }
+    } else if (!(fl & FC_META_NEGATIVE)) {
+      extra |= fc::W3_RANGE;
+    }
+    fc::finish(best, (int32_t)(ga - off), (int32_t)(gb + l + 2 - off), l, backsplice, extra, h);
     reinterpret_cast<uint4*>(out)[i] = make_uint4((uint32_t)h.start, (uint32_t)h.end, h.w2, h.w3);
   }
-  fc::emit_block<BS>((h.w2 & 0xFFFFu) != 0u, i, h.start, h.end, h.w2, h.w3, c, fl, e);
-}
-
-// ... and towards the ranks that own the junction keys (multi-GPU, fc_scan_emit_p2p)
-template <int NP, int T, int BS, int MB>
-__global__ void __launch_bounds__(BS, MB) scan_emit_p2p_kernel(fc::GenomeView g, fc::ScanCfg cfg, fc::ReadView rv,
-                                                            const int32_t* __restrict__ chrom,
-                                                            const int32_t* __restrict__ a_start,
-                                                            const int32_t* __restrict__ b_end, const int32_t* __restrict__ l,
-                                                            const uint8_t* __restrict__ flags, fc_hit* __restrict__ out,
-                                                            fc::EmitArgs e, fc::P2PView pv, unsigned long long* overflow) {
-  const int64_t i = (int64_t)blockIdx.x * BS + threadIdx.x;
-  fc::HitOut h;
-  h.start = h.end = 0;
-  h.w2 = h.w3 = 0u;
-  uint32_t c = 0, fl = 0;
-  if (i < rv.n) {
-    fc::PairArgs p;
-    p.chrom = chrom[i];
-    p.a_start = a_start[i];
-    p.b_end = b_end[i];
-    p.l = l[i];
-    p.flags = flags[i];
-    c = (uint32_t)p.chrom;
-    fl = p.flags;
-    fc::NoEmit ne;
-    fc::scan_pair<NP, T>(g, cfg, p, rv, i, h, ne, false);
-    reinterpret_cast<uint4*>(out)[i] = make_uint4((uint32_t)h.start, (uint32_t)h.end, h.w2, h.w3);
+  if constexpr (MODE != 0) {
+    const bool accept = (h.w2 & 0xFFFFu) != 0u;
+    fc_jrec r;
+    if (accept) {
+      const uint32_t q = e.q[i];
+      r = fc::make_record_from(h.start, h.end, h.w2, h.w3, m.w & 0xFFFFFFu, (m.z >> 24) & 7u, m.w >> 24, (int16_t)(q & 0xFFFFu),
+                               (int16_t)(q >> 16), e.read_hash[i], e.qname_hash[i], e.idx ? e.idx[i] : e.idx_base + (uint64_t)i);
+    }
+    if constexpr (MODE == 1)
+      fc::emit_block<BS>(accept, r, e.n_recs, e.recs);
+    else
+      fc::emit_p2p_block<BS>(accept, r, pv, overflow);
   }
-  fc::emit_p2p_block<BS>((h.w2 & 0xFFFFu) != 0u, i, h.start, h.end, h.w2, h.w3, c, fl, e, pv, overflow);
 }
 
 // ---------------------------------------------------------------- --all-hits: every tie of every pair
@@ -203,28 +277,35 @@ extern "C" int fc_pack_reads(fc_ctx* ctx, int64_t n, const uint8_t* d_ascii, int
   return FC_OK;
 }
 
-static int scan_launch(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs* pr, fc_hit* d_out, const fc::EmitArgs* emit,
-                       cudaStream_t st, const fc::P2PView* pv = nullptr, unsigned long long* overflow = nullptr) {
-  const int need = pr->max_l + 2;
+// storage words per plane and pair of a packed batch whose longest internal read part has max_l bases
+static int batch_words(int max_l) {
+  const int w = max_l > 0 ? (max_l + 31) / 32 : 1;
+  if (w > 8) return w;
+  int nw = 1;
+  while (nw < w) nw <<= 1;
+  return nw;
+}
+
+static int scan_launch(fc_ctx* ctx, const fc_scan_params* p, const BatchView& b, int max_l, fc_hit* d_out, int mode, const Payload& e,
+                       cudaStream_t st, const fc::P2PView* pvp = nullptr, unsigned long long* overflow = nullptr) {
+  const int need = max_l + 2;
   if (!p->noncanonical) {
     int rc = fc_genome_ensure_tiles(ctx, need, st);  // no-op when the tile store already covers this window size
     if (rc) return rc;
   }
   fc::ScanCfg cfg{p->margin, p->maxdist, p->noncanonical, p->strandpref};
   fc::GenomeView g = ctx->genome.view();
-  fc::ReadView rv{pr->d_rlo, pr->d_rhi, pr->d_rn, pr->n, pr->n_words, pr->plane_stride > 0 ? pr->plane_stride : pr->n};
-#define FC_SCAN_LAUNCH_BS(NP, T, BS, MB)                                                                                \
-  {                                                                                                                     \
-    const unsigned grid = (unsigned)((pr->n + BS - 1) / BS);                                                            \
-    if (emit && pv)                                                                                                     \
-      scan_emit_p2p_kernel<NP, T, BS, MB><<<grid, BS, 0, st>>>(g, cfg, rv, pr->d_chrom, pr->d_a_start, pr->d_b_end,      \
-                                                               pr->d_l, pr->d_flags, d_out, *emit, *pv, overflow);      \
-    else if (emit)                                                                                                      \
-      scan_emit_kernel<NP, T, BS, MB><<<grid, BS, 0, st>>>(g, cfg, rv, pr->d_chrom, pr->d_a_start, pr->d_b_end, pr->d_l, \
-                                                           pr->d_flags, d_out, *emit);                                  \
-    else                                                                                                                \
-      scan_kernel<NP, T, BS, MB><<<grid, BS, 0, st>>>(g, cfg, rv, pr->d_chrom, pr->d_a_start, pr->d_b_end, pr->d_l,      \
-                                                      pr->d_flags, d_out);                                              \
+  fc::P2PView pv = {};
+  if (pvp) pv = *pvp;
+#define FC_SCAN_LAUNCH_BS(NP, T, BS, MB)                                                               \
+  {                                                                                                    \
+    const unsigned grid = (unsigned)((b.n + BS - 1) / BS);                                             \
+    if (mode == 2)                                                                                     \
+      scan_kernel<NP, T, BS, MB, 2><<<grid, BS, 0, st>>>(g, cfg, b, d_out, e, pv, overflow);           \
+    else if (mode == 1)                                                                                \
+      scan_kernel<NP, T, BS, MB, 1><<<grid, BS, 0, st>>>(g, cfg, b, d_out, e, pv, overflow);           \
+    else                                                                                               \
+      scan_kernel<NP, T, BS, MB, 0><<<grid, BS, 0, st>>>(g, cfg, b, d_out, e, pv, overflow);           \
   }
   // 256-thread CTAs, 48 registers -> 5 CTAs (40 warps) per SM.  Measured alternatives on B200 (round 1): 128- and
   // 192-thread CTAs, register caps 32/40/58, and a persistent software-pipelined variant with L2 prefetch of the next
@@ -249,11 +330,55 @@ static int scan_launch(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs* pr,
   return FC_OK;
 }
 
+// fc_pairs (struct of arrays, word-major planes) -> packed batch in the context's scratch, rows [row0, row0 + n) of a
+// scratch sized for `rows` rows (the chunks of one host-buffer call share it)
+static int pack_soa(fc_ctx* ctx, const fc_pairs* pr, const uint8_t* d_wden, const int16_t* d_q_a, const int16_t* d_q_b,
+                    const uint8_t* d_frag, cudaStream_t st, int64_t row0, int64_t rows, BatchView* out, const uint32_t** q_out) {
+  const int nw = batch_words(pr->max_l > 0 ? pr->max_l : 0);
+  const bool want_q = d_q_a && d_q_b;
+  const size_t R = (size_t)rows;
+  FC_CUDA(ctx, ctx->pk[0].reserve(16 * R, st, false, 0));
+  FC_CUDA(ctx, ctx->pk[1].reserve(8 * R * nw, st, false, 0));
+  FC_CUDA(ctx, ctx->pk[2].reserve(4 * R * nw, st, false, 0));
+  if (want_q) FC_CUDA(ctx, ctx->pk[3].reserve(4 * R, st, false, 0));
+  uint4* meta = (uint4*)ctx->pk[0].p + row0;
+  uint32_t* reads = (uint32_t*)ctx->pk[1].p + (size_t)row0 * 2 * nw;
+  uint32_t* rn = (uint32_t*)ctx->pk[2].p + (size_t)row0 * nw;
+  uint32_t* q = want_q ? (uint32_t*)ctx->pk[3].p + row0 : nullptr;
+  fc::ReadView rv{pr->d_rlo, pr->d_rhi, pr->d_rn, pr->n, pr->n_words, pr->plane_stride > 0 ? pr->plane_stride : pr->n};
+  pack_batch_kernel<<<(unsigned)((pr->n + 255) / 256), 256, 0, st>>>(ctx->genome.view(), pr->n, pr->d_chrom, pr->d_a_start, pr->d_b_end,
+                                                                  pr->d_l, pr->d_flags, d_wden, d_frag, rv, nw, meta, reads, rn, d_q_a,
+                                                                  d_q_b, q);
+  FC_LAUNCH_CHECK(ctx);
+  *out = BatchView{meta, reads, rn, pr->n, nw};
+  if (q_out) *q_out = q;
+  return FC_OK;
+}
+
 extern "C" int fc_scan(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs* pr, fc_hit* d_out, void* stream) {
   int rc = check_pairs(ctx, p, pr);
   if (rc) return rc;
   if (pr->n == 0) return FC_OK;
-  return scan_launch(ctx, p, pr, d_out, nullptr, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  BatchView b;
+  if ((rc = pack_soa(ctx, pr, nullptr, nullptr, nullptr, nullptr, st, 0, pr->n, &b, nullptr))) return rc;
+  return scan_launch(ctx, p, b, pr->max_l, d_out, 0, Payload{}, st);
+}
+
+// (row0 / rows: see pack_soa)
+static int scan_emit_soa(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs* pr, fc_hit* d_out, const uint8_t* d_wden,
+                         const int16_t* d_q_a, const int16_t* d_q_b, const uint64_t* d_read_hash, const uint64_t* d_qname_hash,
+                         uint64_t idx_base, const uint64_t* d_idx, cudaStream_t st, int64_t row0, int64_t rows) {
+  BatchView b;
+  const uint32_t* q = nullptr;
+  int rc = pack_soa(ctx, pr, d_wden, d_q_a, d_q_b, nullptr, st, row0, rows, &b, &q);
+  if (rc) return rc;
+  fc::EmitArgs ea{d_wden, d_q_a, d_q_b, d_read_hash, d_qname_hash, idx_base, d_idx, nullptr, nullptr};
+  if ((rc = fc_agg_emit_begin(ctx, pr->n, st, &ea))) return rc;
+  Payload e{q, d_read_hash, d_qname_hash, idx_base, d_idx, ea.n_recs, ea.recs};
+  if ((rc = scan_launch(ctx, p, b, pr->max_l, d_out, 1, e, st))) return rc;
+  fc_agg_emit_end(ctx, pr->n, idx_base, d_idx != nullptr);
+  return FC_OK;
 }
 
 extern "C" int fc_scan_emit(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs* pr, fc_hit* d_out, const uint8_t* d_wden,
@@ -263,12 +388,8 @@ extern "C" int fc_scan_emit(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs
   if (rc) return rc;
   if (!d_out || !d_wden || !d_q_a || !d_q_b || !d_read_hash || !d_qname_hash) return FC_E_ARG;
   if (pr->n == 0) return FC_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-  fc::EmitArgs e{d_wden, d_q_a, d_q_b, d_read_hash, d_qname_hash, idx_base, d_idx, nullptr, nullptr};
-  if ((rc = fc_agg_emit_begin(ctx, pr->n, st, &e))) return rc;
-  if ((rc = scan_launch(ctx, p, pr, d_out, &e, st))) return rc;
-  fc_agg_emit_end(ctx, pr->n, idx_base, d_idx != nullptr);
-  return FC_OK;
+  return scan_emit_soa(ctx, p, pr, d_out, d_wden, d_q_a, d_q_b, d_read_hash, d_qname_hash, idx_base, d_idx, (cudaStream_t)stream, 0,
+                       pr->n);
 }
 
 extern "C" int fc_scan_emit_p2p(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs* pr, fc_hit* d_out, const uint8_t* d_wden,
@@ -284,9 +405,80 @@ extern "C" int fc_scan_emit_p2p(fc_ctx* ctx, const fc_scan_params* p, const fc_p
     fc_agg_p2p_end(ctx, idx_base, 0);  // an empty shard still OWNS keys: peers may have written into this rank's buffer
     return FC_OK;
   }
-  fc::EmitArgs e{d_wden, d_q_a, d_q_b, d_read_hash, d_qname_hash, idx_base, nullptr, nullptr, nullptr};
-  if ((rc = scan_launch(ctx, p, pr, d_out, &e, (cudaStream_t)stream, &pv, overflow))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  BatchView b;
+  const uint32_t* q = nullptr;
+  if ((rc = pack_soa(ctx, pr, d_wden, d_q_a, d_q_b, nullptr, st, 0, pr->n, &b, &q))) return rc;
+  Payload e{q, d_read_hash, d_qname_hash, idx_base, nullptr, nullptr, nullptr};
+  if ((rc = scan_launch(ctx, p, b, pr->max_l, d_out, 2, e, st, &pv, overflow))) return rc;
   fc_agg_p2p_end(ctx, idx_base, pr->n);
+  return FC_OK;
+}
+
+// ---------------------------------------------------------------- packed batches (fc_batch): what a native ingest hands over
+static int check_batch(fc_ctx* ctx, const fc_scan_params* p, const fc_batch* b) {
+  if (!ctx || !p || !b) return FC_E_ARG;
+  if (!ctx->genome.loaded) return fc_fail(ctx, FC_E_NOGENOME, "scan called before a genome was loaded");
+  if (p->asize <= 0 || p->margin < 0 || p->margin >= p->asize || p->maxdist < 0 || p->maxdist > 255 || p->margin > 255)
+    return fc_fail(ctx, FC_E_ARG, "bad scan parameters (asize=%d margin=%d maxdist=%d)", p->asize, p->margin, p->maxdist);
+  if (b->n < 0 || b->n_words < 1 || b->max_l < 0) return fc_fail(ctx, FC_E_ARG, "bad batch (n=%lld n_words=%d max_l=%d)", (long long)b->n, b->n_words, b->max_l);
+  if (b->max_l + 2 > FC_GENOME_PAD)
+    return fc_fail(ctx, FC_E_ARG, "internal read length %d exceeds the genome padding (%d)", b->max_l, FC_GENOME_PAD);
+  if (b->n > 0 && b->n_words * 32 < b->max_l) return fc_fail(ctx, FC_E_ARG, "n_words=%d too small for max_l=%d", b->n_words, b->max_l);
+  if (b->n > 0 && (!b->d_meta || !b->d_reads)) return FC_E_ARG;
+  return FC_OK;
+}
+
+extern "C" int fc_batch_words(int32_t max_l) { return batch_words(max_l); }
+
+extern "C" int fc_batch_pack(fc_ctx* ctx, const fc_pairs* pr, const uint8_t* d_wden, const int16_t* d_q_a, const int16_t* d_q_b,
+                             const uint8_t* d_frag, void* d_meta, uint32_t* d_reads, uint32_t* d_rn, uint32_t* d_q, void* stream) {
+  if (!ctx || !pr || pr->n < 0 || !d_meta || !d_reads) return FC_E_ARG;
+  if (!ctx->genome.loaded) return fc_fail(ctx, FC_E_NOGENOME, "fc_batch_pack before a genome was loaded (the descriptors hold genome coordinates)");
+  if ((d_q != nullptr) != (d_q_a && d_q_b)) return FC_E_ARG;
+  if (pr->n == 0) return FC_OK;
+  const int nw = batch_words(pr->max_l > 0 ? pr->max_l : 0);
+  fc::ReadView rv{pr->d_rlo, pr->d_rhi, pr->d_rn, pr->n, pr->n_words, pr->plane_stride > 0 ? pr->plane_stride : pr->n};
+  pack_batch_kernel<<<(unsigned)((pr->n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ctx->genome.view(), pr->n, pr->d_chrom, pr->d_a_start,
+                                                                                    pr->d_b_end, pr->d_l, pr->d_flags, d_wden, d_frag, rv, nw,
+                                                                                    (uint4*)d_meta, d_reads, d_rn, d_q_a, d_q_b, d_q);
+  FC_LAUNCH_CHECK(ctx);
+  return FC_OK;
+}
+
+extern "C" int fc_scan_batch(fc_ctx* ctx, const fc_scan_params* p, const fc_batch* b, fc_hit* d_out, void* stream) {
+  int rc = check_batch(ctx, p, b);
+  if (rc) return rc;
+  if (b->n == 0) return FC_OK;
+  BatchView v{(const uint4*)b->d_meta, b->d_reads, b->d_rn, b->n, b->n_words};
+  return scan_launch(ctx, p, v, b->max_l, d_out, 0, Payload{}, (cudaStream_t)stream);
+}
+
+extern "C" int fc_scan_emit_batch(fc_ctx* ctx, const fc_scan_params* p, const fc_batch* b, fc_hit* d_out, const uint32_t* d_q,
+                                  const uint64_t* d_read_hash, const uint64_t* d_qname_hash, uint64_t idx_base, const uint64_t* d_idx,
+                                  void* stream) {
+  int rc = check_batch(ctx, p, b);
+  if (rc) return rc;
+  if (!d_out || !d_q || !d_read_hash || !d_qname_hash) return FC_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  BatchView v{(const uint4*)b->d_meta, b->d_reads, b->d_rn, b->n, b->n_words};
+  if (ctx->agg.p2p_enabled) {  // connected to peers: every record goes to the rank that owns its key
+    fc::P2PView pv;
+    unsigned long long* overflow = nullptr;
+    if ((rc = fc_agg_p2p_begin(ctx, &pv, &overflow))) return rc;
+    if (b->n > 0) {
+      Payload e{d_q, d_read_hash, d_qname_hash, idx_base, d_idx, nullptr, nullptr};
+      if ((rc = scan_launch(ctx, p, v, b->max_l, d_out, 2, e, st, &pv, overflow))) return rc;
+    }
+    fc_agg_p2p_end(ctx, idx_base, b->n);
+    return FC_OK;
+  }
+  if (b->n == 0) return FC_OK;
+  fc::EmitArgs ea{};
+  if ((rc = fc_agg_emit_begin(ctx, b->n, st, &ea))) return rc;
+  Payload e{d_q, d_read_hash, d_qname_hash, idx_base, d_idx, ea.n_recs, ea.recs};
+  if ((rc = scan_launch(ctx, p, v, b->max_l, d_out, 1, e, st))) return rc;
+  fc_agg_emit_end(ctx, b->n, idx_base, d_idx != nullptr);
   return FC_OK;
 }
 
@@ -543,12 +735,7 @@ extern "C" int fc_batch_host_planes(fc_ctx* ctx, const fc_scan_params* p, int64_
   FC_CUDA(ctx, cudaStreamWaitEvent(ctx->own_stream2, ctx->ev_chunk[0], 0));
   // pairs per chunk (FC_HOST_CHUNK overrides): copies of 4 MiB and more per column run at the full PCIe rate, smaller ones do
   // not, and that outweighs what the overlap of copies and kernels buys
-  static int64_t chunk = 0;
-  if (chunk == 0) {
-    const char* e = getenv("FC_HOST_CHUNK");
-    chunk = e ? atoll(e) : 0;
-    if (chunk < 1024) chunk = 1 << 20;  // measured on the B200 box at 1 M pairs: 256k 1.63 ms, 512k 1.56 ms, 1M (one chunk) 1.51 ms
-  }
+  const int64_t chunk = ctx->host_chunk;  // (fc_ctx_create: FC_HOST_CHUNK or 1 M pairs -- measured on the B200 box at 1 M pairs: 256k 1.63 ms, 512k 1.56 ms, one chunk 1.51 ms)
   const size_t elem[14] = {4, 4, 4, 4, 1, 0, 0, 0, 0, 1, 2, 2, 8, 8};
   const void* src[14] = {h_chrom, h_a_start, h_b_end, h_l, h_flags, nullptr, nullptr, nullptr, nullptr,
                          h_wden, h_q_a, h_q_b, h_read_hash, h_qname_hash};
@@ -582,13 +769,20 @@ extern "C" int fc_batch_host_planes(fc_ctx* ctx, const fc_scan_params* p, int64_
     pc.max_l = max_l;
     pc.plane_stride = n;
     fc_hit* d_hits = (fc_hit*)dp[8] + c0;
-    if (emit)  // scan and record in one kernel
-      rc = fc_scan_emit(ctx, p, &pc, d_hits, (const uint8_t*)dp[9] + c0, (const int16_t*)dp[10] + c0, (const int16_t*)dp[11] + c0,
-                        (const uint64_t*)dp[12] + c0, (const uint64_t*)dp[13] + c0, idx_base + (uint64_t)c0,
-                        d_idx ? d_idx + c0 : nullptr, cs);
-    else
-      rc = fc_scan(ctx, p, &pc, d_hits, cs);
-    if (rc) return rc;
+    if (emit) {  // scan and record in one kernel
+      rc = scan_emit_soa(ctx, p, &pc, d_hits, (const uint8_t*)dp[9] + c0, (const int16_t*)dp[10] + c0, (const int16_t*)dp[11] + c0,
+                         (const uint64_t*)dp[12] + c0, (const uint64_t*)dp[13] + c0, idx_base + (uint64_t)c0,
+                         d_idx ? d_idx + c0 : nullptr, cs, c0, n);
+    } else {
+      BatchView bv;
+      rc = pack_soa(ctx, &pc, nullptr, nullptr, nullptr, nullptr, cs, c0, n, &bv, nullptr);
+      if (!rc) rc = scan_launch(ctx, p, bv, max_l, d_hits, 0, Payload{}, cs);
+    }
+    if (rc) {
+      cudaStreamSynchronize(ctx->own_stream2);  // nothing of this call stays in flight behind the error
+      cudaStreamSynchronize(st);
+      return rc;
+    }
     if (h_out) FC_CUDA(ctx, cudaMemcpyAsync(h_out + c0, d_hits, sizeof(fc_hit) * cn, cudaMemcpyDeviceToHost, cs));
   }
   FC_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[1], ctx->own_stream2));

@@ -181,19 +181,26 @@ FC_HD int gcode(const GenomeView& g, int64_t gp) {  // 0..3, 4 = N
   return (int)(((ldg32(g.plo + w) >> sh) & 1u) | (((ldg32(g.phi + w) >> sh) & 1u) << 1));
 }
 
+// Read planes of a batch: word w of pair i of the lo / hi plane at [i * pair_stride + w * stride], of the N plane at
+// [i * rn_pair_stride + w * stride]; base j in word j>>5, bit j&31.
+//   word-major (fc_pairs):  pair_stride = rn_pair_stride = 1, stride = plane stride (>= n)
+//   row-major  (fc_batch):  rows [lo words | hi words], rhi = rlo + NW, pair_stride = 2 NW, rn_pair_stride = NW, stride = 1
 struct ReadView {
-  const uint32_t* rlo;  // word-major: word w of pair i at [w*n + i], base j in word j>>5, bit j&31
+  const uint32_t* rlo;
   const uint32_t* rhi;
   const uint32_t* rn;
   int64_t n;       // pairs
   int32_t n_words; // words per pair and plane
-  int64_t stride;  // distance (in words) between word w and word w+1 of one pair (>= n)
+  int64_t stride;  // distance (in words) between word w and word w+1 of one pair
+  int64_t pair_stride = 1;
+  int64_t rn_pair_stride = 1;
 };
 
 FC_HD int rcode(const ReadView& rv, int64_t i, int j, bool has_n) {
-  const int64_t a = (int64_t)(j >> 5) * rv.stride + i;
+  const int64_t w = (int64_t)(j >> 5) * rv.stride;
+  const int64_t a = w + i * rv.pair_stride;
   const uint32_t sh = (uint32_t)(j & 31);
-  if (has_n && ((ldg32(rv.rn + a) >> sh) & 1u)) return 4;
+  if (has_n && ((ldg32(rv.rn + w + i * rv.rn_pair_stride) >> sh) & 1u)) return 4;
   return (int)(((ldg32(rv.rlo + a) >> sh) & 1u) | (((ldg32(rv.rhi + a) >> sh) & 1u) << 1));
 }
 FC_HD uint32_t comp_code(uint32_t c) { return c == 4 ? 4u : 3u - c; }
@@ -406,12 +413,7 @@ FC_HD void scan_planes(const ScanCfg& cfg, const Window<NP>& A, const Window<NP>
   }
 }
 
-// ---------------------------------------------------------------- one pair
-struct PairArgs {
-  int32_t chrom, a_start, b_end, l;
-  uint32_t flags;  // FC_PF_*
-};
-
+// ---------------------------------------------------------------- windows by global coordinate, read planes in registers
 FC_HD bool warp_any(bool p) {
 #if defined(__CUDA_ARCH__)
   return __any_sync(__activemask(), p);
@@ -420,7 +422,53 @@ FC_HD bool warp_any(bool p) {
 #endif
 }
 
-// NP: 32-base words per window held in registers; T: sectors per tile of the tile store (0: no tile store)
+// NP: 32-base words per window held in registers; T: sectors per tile of the tile store (0: no tile store).
+// ga / gb: global coordinates of the first base of the donor / acceptor window (l + 2 <= 32 NP bases each).
+template <int NP, int T>
+FC_HD void scan_fast(const GenomeView& g, const ScanCfg& cfg, int64_t ga, int64_t gb, int l, bool minus_span, bool read_n,
+                     const uint32_t (&rlo)[NP], const uint32_t (&rhi)[NP], const ReadView& rv, int64_t i, Best& best) {
+  Window<NP> A, B;
+  uint32_t nA[NP + 1], nB[NP + 1], rnn[NP];
+  bool with_n = read_n;
+  bool tiled = false;
+  if constexpr (T > 0) {
+    if (l + 2 <= g.tile_W) {
+      const uint32_t fl = load_tile_window<NP, T>(g, ga, A) | load_tile_window<NP, T>(g, gb, B);
+      with_n = with_n || (fl & TILE_FLAG_N);
+      tiled = true;
+    }
+  }
+  if (!tiled) {
+    load_plane<NP>(g.plo, ga, A.lo);
+    load_plane<NP>(g.phi, ga, A.hi);
+    load_plane<NP>(g.plo, gb, B.lo);
+    load_plane<NP>(g.phi, gb, B.hi);
+    with_n = true;  // no summary without tiles: always consult the N plane
+  }
+  // one variant per warp (the lanes that reached this point): the N-aware one only if some lane needs it
+  if (warp_any(with_n)) {
+#pragma unroll
+    for (int k = 0; k < NP; ++k)
+      rnn[k] = (read_n && k < rv.n_words) ? ldg32(rv.rn + (int64_t)k * rv.stride + i * rv.rn_pair_stride) : 0u;
+    if (with_n) {
+      load_plane<NP>(g.pn, ga, nA);
+      load_plane<NP>(g.pn, gb, nB);
+    } else {
+#pragma unroll
+      for (int k = 0; k <= NP; ++k) nA[k] = nB[k] = 0u;
+    }
+    scan_planes<NP, true>(cfg, A, B, nA, nB, l, minus_span, rlo, rhi, rnn, best);
+  } else {
+    scan_planes<NP, false>(cfg, A, B, nA, nB, l, minus_span, rlo, rhi, rnn, best);
+  }
+}
+
+// ---------------------------------------------------------------- one pair
+struct PairArgs {
+  int32_t chrom, a_start, b_end, l;
+  uint32_t flags;  // FC_PF_*
+};
+
 template <int NP, int T, class Emit>
 FC_HD void scan_pair(const GenomeView& g, const ScanCfg& cfg, const PairArgs& p, const ReadView& rv, int64_t i,
                      HitOut& out, Emit& emit, bool force_per_base) {
@@ -456,45 +504,14 @@ FC_HD void scan_pair(const GenomeView& g, const ScanCfg& cfg, const PairArgs& p,
   }
   if (fast) {
     // the read planes first: their (coalesced) loads are in flight while the tile loads are issued and waited for
-    uint32_t rlo[NP], rhi[NP], rnn[NP];
+    uint32_t rlo[NP], rhi[NP];
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
       const bool have = k < rv.n_words;
-      rlo[k] = have ? ldg32(rv.rlo + (int64_t)k * rv.stride + i) : 0u;
-      rhi[k] = have ? ldg32(rv.rhi + (int64_t)k * rv.stride + i) : 0u;
-      rnn[k] = (read_n && have) ? ldg32(rv.rn + (int64_t)k * rv.stride + i) : 0u;
+      rlo[k] = have ? ldg32(rv.rlo + (int64_t)k * rv.stride + i * rv.pair_stride) : 0u;
+      rhi[k] = have ? ldg32(rv.rhi + (int64_t)k * rv.stride + i * rv.pair_stride) : 0u;
     }
-    Window<NP> A, B;
-    uint32_t nA[NP + 1], nB[NP + 1];
-    bool with_n = read_n;
-    bool tiled = false;
-    if constexpr (T > 0) {
-      if (l + 2 <= g.tile_W) {
-        const uint32_t fl = load_tile_window<NP, T>(g, ga, A) | load_tile_window<NP, T>(g, gb, B);
-        with_n = with_n || (fl & TILE_FLAG_N);
-        tiled = true;
-      }
-    }
-    if (!tiled) {
-      load_plane<NP>(g.plo, ga, A.lo);
-      load_plane<NP>(g.phi, ga, A.hi);
-      load_plane<NP>(g.plo, gb, B.lo);
-      load_plane<NP>(g.phi, gb, B.hi);
-      with_n = true;  // no summary without tiles: always consult the N plane
-    }
-    // one variant per warp (the lanes that reached this point): the N-aware one only if some lane needs it
-    if (warp_any(with_n)) {
-      if (with_n) {
-        load_plane<NP>(g.pn, ga, nA);
-        load_plane<NP>(g.pn, gb, nB);
-      } else {
-#pragma unroll
-        for (int k = 0; k <= NP; ++k) nA[k] = nB[k] = 0u;
-      }
-      scan_planes<NP, true>(cfg, A, B, nA, nB, l, minus_span, rlo, rhi, rnn, best);
-    } else {
-      scan_planes<NP, false>(cfg, A, B, nA, nB, l, minus_span, rlo, rhi, rnn, best);
-    }
+    scan_fast<NP, T>(g, cfg, ga, gb, l, minus_span, read_n, rlo, rhi, rv, i, best);
   }
   finish(best, p.a_start, p.b_end, l, backsplice, extra, out);
 }

@@ -16,7 +16,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import HIT_DTYPE, JREC_DTYPE, JUNCTION_DTYPE, FindCircError, Pairs, ScanParams, ptr
+from ._lib import HIT_DTYPE, JREC_DTYPE, JUNCTION_DTYPE, Batch, FindCircError, Pairs, ScanParams, ptr
 
 SIG_LETTERS = "ACGTN"
 
@@ -208,6 +208,29 @@ class Engine:
         """scan + record into the owner ranks' buffers over peer memory, in one kernel (fc_scan_emit_p2p)"""
         self._check(self.lib.fc_scan_emit_p2p(self.h, C.byref(self.params), C.byref(pairs), ptr(d_out), ptr(d_wden), ptr(d_q_a),
                                               ptr(d_q_b), ptr(d_read_hash), ptr(d_qname_hash), idx_base, stream))
+
+    # ---- packed batches (fc_batch): the layout the scan kernels read
+    def batch_words(self, max_l: int) -> int:
+        return int(self.lib.fc_batch_words(int(max_l)))
+
+    def pack_batch(self, pairs: Pairs, d_meta, d_reads, d_rn, d_wden=None, d_q_a=None, d_q_b=None, d_q=None, d_frag=None, stream=0) -> Batch:
+        """convert an fc_pairs batch on the device (fc_batch_pack); d_meta: 16 bytes per pair, d_reads: 2 * batch_words words
+        per pair, d_rn: batch_words words per pair, d_q (with d_q_a / d_q_b): one word per pair"""
+        self._check(self.lib.fc_batch_pack(self.h, C.byref(pairs), ptr(d_wden), ptr(d_q_a), ptr(d_q_b), ptr(d_frag), ptr(d_meta),
+                                           ptr(d_reads), ptr(d_rn), ptr(d_q), stream))
+        return Batch(pairs.n, ptr(d_meta), ptr(d_reads), ptr(d_rn), self.batch_words(pairs.max_l), pairs.max_l)
+
+    def scan_batch(self, batch: Batch, d_out, stream=0):
+        self._check(self.lib.fc_scan_batch(self.h, C.byref(self.params), C.byref(batch), ptr(d_out), stream))
+
+    def scan_emit_batch(self, batch: Batch, d_out, d_q, d_read_hash, d_qname_hash, idx_base, stream=0, d_idx=None):
+        """scan + record in one kernel; on a context connected to peers the records go to the ranks that own their keys"""
+        self._check(self.lib.fc_scan_emit_batch(self.h, C.byref(self.params), C.byref(batch), ptr(d_out), ptr(d_q), ptr(d_read_hash),
+                                                ptr(d_qname_hash), idx_base, ptr(d_idx), stream))
+
+    def chrom_offset(self, i: int) -> int:
+        """genome coordinate of base 0 of chromosome i (what fc_batch descriptors are made of)"""
+        return int(self.lib.fc_genome_chrom_offset(self.h, int(i)))
 
     def scan_ties(self, pairs: Pairs, d_hits, d_tie_off, d_ties, stream=0):
         self._check(self.lib.fc_scan_ties(self.h, C.byref(self.params), C.byref(pairs), ptr(d_hits), ptr(d_tie_off),

@@ -84,6 +84,28 @@ typedef struct fc_pairs {
   int64_t plane_stride; /* words between consecutive words of one pair in rlo/rhi/rn; 0 = n */
 } fc_pairs;
 
+/* The same batch in the layout the scan kernels read (fc_pairs batches are converted on the device with fc_batch_pack; a
+ * native ingest writes it directly).  One 16-byte descriptor per pair, four 32-bit words:
+ *   w0  low 32 bits of ga = genome coordinate of A_flank[0]  (fc_genome_chrom_offset(chrom) + a_start)
+ *   w1  low 32 bits of gb = genome coordinate of B_flank[0]  (fc_genome_chrom_offset(chrom) + b_end - (l + 2))
+ *   w2  bits 0-5 ga >> 32, 6-11 gb >> 32, 12-23 l, 24-26 FC_PF_BACKSPLICE / MINUS / READ_N, 27 FC_META_INVALID (a window
+ *       lies outside its chromosome, the chromosome is unknown or l < 0: no hit; ga, gb, l are then 0),
+ *       28-29 / 30-31 rows of the same fragment before / after this one in the batch (3,3 = unknown)
+ *   w3  bits 0-23 chromosome id, 24-31 weight denominator (find_circ.py:1084)
+ * and the internal read part as one row per pair: n_words words of the lo plane, then n_words words of the hi plane
+ * (d_reads), n_words words of the N plane (d_rn; read only for pairs flagged FC_PF_READ_N, may be NULL when none is).
+ * n_words = fc_batch_words(max_l): ceil(max_l / 32) rounded up to 1, 2, 4 or 8 (rows are loaded with one vector load). */
+#define FC_META_INVALID 8u
+#define FC_META_NEGATIVE 16u /* internal to fc_batch_pack: never stored */
+typedef struct fc_batch {
+  int64_t n;
+  const void* d_meta;
+  const uint32_t* d_reads;
+  const uint32_t* d_rn;
+  int32_t n_words;
+  int32_t max_l;
+} fc_batch;
+
 /* Result of the scan for one pair: the FIRST best-scoring breakpoint (ties keep ascending split position,
  * '+' before '-', find_circ.py:966-974) and the number of ties.  16 bytes, one coalesced store per pair.
  *   start,end  BED coordinates after the back-splice / linear correction (find_circ.py:929-945); valid iff n_hits>0
@@ -158,6 +180,7 @@ int fc_genome_share(fc_ctx* dst, fc_ctx* src);
 int fc_genome_n_chrom(fc_ctx* ctx);
 int fc_genome_chrom_name(fc_ctx* ctx, int32_t i, char* buf, int32_t cap);
 int64_t fc_genome_chrom_size(fc_ctx* ctx, int32_t i);
+int64_t fc_genome_chrom_offset(fc_ctx* ctx, int32_t i); /* genome coordinate of base 0 of chromosome i (fc_batch descriptors) */
 int fc_genome_chrom_id(fc_ctx* ctx, const char* name); /* -1 unknown (the reference raises KeyError, :193) */
 /* stats[0]=total bases, [1]=N bases, [2]=other non-ACGT letters stored as N, [3]=device bytes */
 int fc_genome_stats(fc_ctx* ctx, int64_t stats[4]);
@@ -183,6 +206,17 @@ int fc_scan_emit(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs* pairs, fc
                  uint64_t idx_base, const uint64_t* d_idx, void* stream);
 int fc_scan_ties(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs* pairs, const fc_hit* d_hits,
                  const int64_t* d_tie_off, fc_hit* d_ties, void* stream);
+/* packed batches: fc_batch_pack converts an fc_pairs batch (d_wden NULL = 1; d_frag NULL = nothing known about fragments,
+ * else bits 0-1 / 2-3 of a byte per pair = rows of the same fragment before / after; d_q receives q_a | q_b << 16 when
+ * d_q_a / d_q_b are given); fc_scan_batch = fc_scan, fc_scan_emit_batch = fc_scan_emit -- or fc_scan_emit_p2p when the
+ * context is connected to peers (fc_p2p_connect) */
+int32_t fc_batch_words(int32_t max_l);
+int fc_batch_pack(fc_ctx* ctx, const fc_pairs* pairs, const uint8_t* d_wden, const int16_t* d_q_a, const int16_t* d_q_b,
+                  const uint8_t* d_frag, void* d_meta, uint32_t* d_reads, uint32_t* d_rn, uint32_t* d_q, void* stream);
+int fc_scan_batch(fc_ctx* ctx, const fc_scan_params* p, const fc_batch* batch, fc_hit* d_out, void* stream);
+int fc_scan_emit_batch(fc_ctx* ctx, const fc_scan_params* p, const fc_batch* batch, fc_hit* d_out, const uint32_t* d_q,
+                       const uint64_t* d_read_hash, const uint64_t* d_qname_hash, uint64_t idx_base, const uint64_t* d_idx,
+                       void* stream);
 /* host-buffer convenience (the reference-facing call): copies the batch in, scans, copies results out.
  * h_ascii rows hold the internal read bases.  Pinned host memory makes the copies asynchronous. */
 int fc_scan_host(fc_ctx* ctx, const fc_scan_params* p, int64_t n, const int32_t* h_chrom, const int32_t* h_a_start,
