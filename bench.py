@@ -221,7 +221,17 @@ class Shard(object):
         nm = s["name_id"]
         s["qname_hash"] = (nm * (0x9E3779B97F4A7C15 - (1 << 64))) ^ ((nm >> 7) & ((1 << 57) - 1))
         torch.cuda.synchronize()
-        del s["reads"], s["name_id"], s["row"]
+        # rows of one fragment (same read name) are neighbours: how many come before / after each row (fc_batch descriptors,
+        # bits 28-31); read names are unique per fragment in this workload, so the scan kernel may settle n_frags locally
+        back = torch.zeros(n, dtype=torch.int32, device=dev)
+        fwd = torch.zeros(n, dtype=torch.int32, device=dev)
+        for k in (1, 2, 3, 4):
+            if n > k:
+                eq = (nm[k:] == nm[:-k]).to(torch.int32)
+                back[k:] += eq
+                fwd[:-k] += eq
+        frag = torch.where((back > 3) | (fwd > 3) | (back + fwd > 3), torch.full_like(back, 15), back | (fwd << 2)).to(torch.uint8)
+        del s["reads"], s["name_id"], s["row"], back, fwd
         self.planes = torch.zeros(3 * self.n_words * n, dtype=torch.int32, device=dev)
         eng.pack_reads(s["internal"], self.stride, s["l"], self.n_words, self.planes, s["flags"], stream)
         torch.cuda.synchronize()
@@ -235,7 +245,7 @@ class Shard(object):
         self.rows = torch.zeros(n * 2 * self.nw, dtype=torch.int32, device=dev)
         self.rn_rows = torch.zeros(n * self.nw, dtype=torch.int32, device=dev)
         self.q = torch.zeros(n, dtype=torch.int32, device=dev)
-        self.batch = eng.pack_batch(self.pairs, self.meta, self.rows, self.rn_rows, s["wden"], s["q_a"], s["q_b"], self.q, None, stream)
+        self.batch = eng.pack_batch(self.pairs, self.meta, self.rows, self.rn_rows, s["wden"], s["q_a"], s["q_b"], self.q, frag, stream)
         torch.cuda.synchronize()
 
     def batch_prefix(self, m):

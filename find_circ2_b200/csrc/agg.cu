@@ -294,7 +294,7 @@ static_assert(sizeof(JSlot) == 64 && offsetof(JSlot, first_inv) == 16 && offseto
 
 constexpr unsigned long long KEY_OCC = 1ull << 63;
 constexpr long long FUSED_MAX_RECORDS = 1ll << 28;  // keeps 8 * n_spanned and the slot numbers inside their fields
-constexpr uint32_t SK_NAME_KNOWN = 8u, SK_NAME_DUP = 16u;  // fc_jrec.sk: the emitter already knows whether the fragment is new to the junction
+constexpr uint32_t SK_NAME_KNOWN = FC_SK_NAME_KNOWN, SK_NAME_DUP = FC_SK_NAME_DUP;  // the emitter already knows whether the fragment is new to the junction
 
 // counters (32-bit words at counters + 8): [0] junctions listed, [1] records with another denominator,
 // [2] list overflow / records outside a declared idx range, [3] junctions
@@ -336,35 +336,47 @@ __device__ __forceinline__ unsigned long long set_first_slot(unsigned long long 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // insert (v1, t1) and, when with2, (v2, t2); both probe sequences advance together so that their round trips overlap.
-// The CAS goes first (no load): most inserts find an empty slot, and the returned old entry tells the rest.
+// The CAS goes first (no load): most inserts find an empty slot, and the returned old entry tells the rest.  Probe
+// sequence of an element: the slot given by its value alone, that slot's neighbour in the same 32-byte sector (the
+// sector is in L2 by then), then linear probing from a slot that also depends on the tag.
+struct SetProbe {
+  unsigned long long s;
+  int k;
+  __device__ __forceinline__ void next(unsigned long long v, unsigned long long t, unsigned long long mask) {
+    if (k == 0)
+      s ^= 1ull;
+    else if (k == 1)
+      s = fc_mix64(v ^ (t * 0x9E3779B97F4A7C15ULL)) & mask;
+    else
+      s = (s + 1ull) & mask;
+    ++k;
+  }
+};
 __device__ __forceinline__ void set_insert2(U128* table, unsigned long long mask, unsigned long long v1, unsigned long long t1,
                                             unsigned long long s1, bool with2, unsigned long long v2, unsigned long long t2,
                                             unsigned long long s2, bool& new1, bool& new2) {
-  bool d1 = false, d2 = !with2, first1 = true, first2 = true;
+  bool d1 = false, d2 = !with2;
+  SetProbe p1{s1, 0}, p2{s2, 0};
   new1 = new2 = false;
   while (!(d1 && d2)) {
     U128 o1{0ull, 0ull}, o2{0ull, 0ull};
-    if (!d1) o1 = cas128(table + s1, U128{0ull, 0ull}, U128{v1, t1});
-    if (!d2) o2 = cas128(table + s2, U128{0ull, 0ull}, U128{v2, t2});
+    if (!d1) o1 = cas128(table + p1.s, U128{0ull, 0ull}, U128{v1, t1});
+    if (!d2) o2 = cas128(table + p2.s, U128{0ull, 0ull}, U128{v2, t2});
     if (!d1) {
-      if (o1.lo == 0ull && o1.hi == 0ull) {
+      if (o1.lo == 0ull && o1.hi == 0ull)
         new1 = d1 = true;
-      } else if (o1.lo == v1 && o1.hi == t1) {
+      else if (o1.lo == v1 && o1.hi == t1)
         d1 = true;
-      } else {
-        s1 = first1 ? (fc_mix64(v1 ^ (t1 * 0x9E3779B97F4A7C15ULL)) & mask) : ((s1 + 1ull) & mask);
-        first1 = false;
-      }
+      else
+        p1.next(v1, t1, mask);
     }
     if (!d2) {
-      if (o2.lo == 0ull && o2.hi == 0ull) {
+      if (o2.lo == 0ull && o2.hi == 0ull)
         new2 = d2 = true;
-      } else if (o2.lo == v2 && o2.hi == t2) {
+      else if (o2.lo == v2 && o2.hi == t2)
         d2 = true;
-      } else {
-        s2 = first2 ? (fc_mix64(v2 ^ (t2 * 0x9E3779B97F4A7C15ULL)) & mask) : ((s2 + 1ull) & mask);
-        first2 = false;
-      }
+      else
+        p2.next(v2, t2, mask);
     }
   }
 }
@@ -372,28 +384,39 @@ __device__ __forceinline__ void set_insert2(U128* table, unsigned long long mask
 // A junction that collects a few per cent of all reads (expression is heavy-tailed) would otherwise put all of its
 // updates on one L2 sector, and an L2 slice retires about one request per clock for one sector (measured: with a
 // Zipf(1) popularity the direct version spends 4x the time of the uniform case).  So the lanes of a warp that share a
-// junction are combined first, and a junction that shows up at least twice in the CTA (counted in a small
-// shared-memory sketch) is accumulated in a shared-memory table of the CTA and flushed once at the end; junctions seen
-// once per CTA -- the bulk of the distinct ones -- go to global memory directly and never touch the table.
+// junction are combined first, and a junction that the CTA has met before (counted in a small shared-memory sketch) is
+// accumulated in a shared-memory table of the CTA and flushed at the end of the CTA's chunk of records; junctions seen
+// once per chunk -- the bulk of the distinct ones -- go to global memory directly and never touch the table.
+// A CTA walks its chunk tile by tile WITHOUT barriers in between (the sketch is only a hint: whichever way a record
+// goes, it ends up in the junction's slot), so the warps hide each other's memory round trips.
 constexpr int ACC_THREADS = 512;
+constexpr int ACC_MAX_TILES = 16;  // tiles of ACC_THREADS records per chunk (between two flushes of the shared-memory table)
 constexpr int HOT_ENTRIES = 512;
 constexpr int HOT_BITS = 9;
-constexpr int SKETCH_BITS = 11;
+constexpr int SKETCH_BITS = 13;
 struct HotTable {
   unsigned int tag[HOT_ENTRIES];    // junction slot + 1, 0 = free
-  unsigned int c0[HOT_ENTRIES];     // n_spanned | 8 * weight << 16 (at most 512 records of weight <= 1 per CTA)
-  unsigned int c1[HOT_ENTRIES];     // 8 * non-bridge weight | names seen before << 16
+  unsigned int c0[HOT_ENTRIES];     // n_spanned | 8 * weight << 14 (a chunk holds at most 8192 records of weight <= 1)
+  unsigned int c1[HOT_ENTRIES];     // names seen before | 8 * non-bridge weight << 14
   unsigned int c2[HOT_ENTRIES];
   unsigned int qmax_l[HOT_ENTRIES], qmax_r[HOT_ENTRIES], inv_dist[HOT_ENTRIES], inv_ov[HOT_ENTRIES], inv_nh[HOT_ENTRIES];
   unsigned long long first_inv[HOT_ENTRIES];
 };
+static_assert(ACC_MAX_TILES * ACC_THREADS < (1 << 14) && ACC_MAX_TILES * ACC_THREADS * 8 < (1 << 18), "hot-table fields");
 
-__device__ __forceinline__ int hot_find_or_insert(HotTable& t, unsigned int jid) {
+// entry of junction `jid` in the CTA's table; `insert`: claim a free entry when it has none (-1: none / table crowded).
+// A plain load finds a junction that is already there -- the usual case for a popular one -- without an atomic.
+__device__ __forceinline__ int hot_find_or_insert(HotTable& t, unsigned int jid, bool insert) {
   unsigned int h = (jid * 2654435761u) >> (32 - HOT_BITS);
 #pragma unroll 1
   for (int probe = 0; probe < 8; ++probe) {
-    const unsigned int old = atomicCAS(&t.tag[h], 0u, jid + 1u);
-    if (old == 0u || old == jid + 1u) return (int)h;
+    unsigned int cur = *reinterpret_cast<volatile unsigned int*>(&t.tag[h]);
+    if (cur == 0u) {
+      if (!insert) return -1;
+      cur = atomicCAS(&t.tag[h], 0u, jid + 1u);
+      if (cur == 0u) return (int)h;
+    }
+    if (cur == jid + 1u) return (int)h;
     h = (h + 1u) & (HOT_ENTRIES - 1);
   }
   return -1;  // crowded: the group goes to global memory directly
@@ -404,195 +427,207 @@ __device__ __forceinline__ void ld_sector(const JSlot* s, unsigned long long (&v
   asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(s));
 }
 
-__global__ void __launch_bounds__(ACC_THREADS) fused_accumulate_kernel(RecSrc src, JSlot* __restrict__ slots,
-                                                               unsigned long long kmask, U128* __restrict__ sets,
-                                                               unsigned long long smask, unsigned int* __restrict__ list,
-                                                               unsigned int lcap, unsigned int* __restrict__ ctr,
-                                                               uint32_t* __restrict__ flag, int64_t n_flag,
-                                                               uint32_t* __restrict__ tile_count, int64_t n_tiles) {
+__global__ void __launch_bounds__(ACC_THREADS, 2) fused_accumulate_kernel(RecSrc src, int chunk_tiles, int exp_, JSlot* __restrict__ slots,
+                                                                  unsigned long long kmask, U128* __restrict__ sets,
+                                                                  unsigned long long smask, unsigned int* __restrict__ list,
+                                                                  unsigned int lcap, unsigned int* __restrict__ ctr,
+                                                                  uint4* __restrict__ flag4, int64_t n_flag4,
+                                                                  uint32_t* __restrict__ tile_count, int64_t n_tiles) {
   __shared__ HotTable hot;
-  __shared__ unsigned int sketch[1 << SKETCH_BITS];
-  for (int e = threadIdx.x; e < (1 << SKETCH_BITS); e += blockDim.x) sketch[e] = 0u;
-  for (int e = threadIdx.x; e < HOT_ENTRIES; e += blockDim.x) {
-    hot.tag[e] = hot.c0[e] = hot.c1[e] = hot.c2[e] = 0u;
-    hot.qmax_l[e] = hot.qmax_r[e] = hot.inv_dist[e] = hot.inv_ov[e] = hot.inv_nh[e] = 0u;
-    hot.first_inv[e] = 0ull;
-  }
-  __syncthreads();
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  // record i of the call: slice s holds records [prefix(s), prefix(s+1)) (a counter may have counted past its capacity)
-  int64_t n = 0, rec_at = i;
-  {
-    bool found = false;
-#pragma unroll 1
-    for (int sl = 0; sl < src.n_slices; ++sl) {
-      const int64_t c = (int64_t)min(src.counts[sl], src.slice_cap);
-      if (!found && i >= n && i < n + c) {
-        rec_at = (int64_t)sl * (int64_t)src.slice_cap + (i - n);
-        found = true;
-      }
-      n += c;
-    }
-  }
-  if (src.total_out && i == 0) *src.total_out = (unsigned long long)n;
-  const fc_jrec* __restrict__ recs = src.base;
+  __shared__ __align__(16) unsigned char sketch[1 << SKETCH_BITS];
   // the rank flags and tile counters of the finish pass are cleared on the way
-  for (int64_t k = i; k < n_flag; k += (int64_t)gridDim.x * blockDim.x) flag[k] = 0u;
-  for (int64_t k = i; k < n_tiles; k += (int64_t)gridDim.x * blockDim.x) tile_count[k] = 0u;
-  const bool active = i < n;
-  const unsigned amask = __ballot_sync(0xffffffffu, active);
-  uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0, r2 = r0;
-  unsigned long long s_read = 0ull, s_name = 0ull, cur_f = 0ull, cur_x = 0ull;
-  unsigned int jid = 0xFFFFFFFFu;  // slot number of the record's junction
-  bool name_known = false;
-  if (active) {
-    const uint4* rp = reinterpret_cast<const uint4*>(recs + rec_at);
-    r0 = __ldg(rp);
-    r1 = __ldg(rp + 1);
-    r2 = __ldg(rp + 2);
-    name_known = (r0.w & SK_NAME_KNOWN) != 0u;
-    // names and reads share the set: the name's value is salted so that equal hashes of the two kinds stay apart
-    s_read = set_first_slot((unsigned long long)r1.z | ((unsigned long long)r1.w << 32), smask);
-    prefetch_l2(sets + s_read);
-    if (!name_known) {
-      s_name = set_first_slot(~((unsigned long long)r2.x | ((unsigned long long)r2.y << 32)), smask);
-      prefetch_l2(sets + s_name);
-    }
+  {
+    const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gs = (int64_t)gridDim.x * blockDim.x;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (int64_t k = gi; k < n_flag4; k += gs) flag4[k] = z;
+    for (int64_t k = gi; k < n_tiles; k += gs) tile_count[k] = 0u;
+  }
+  // records of the call: slice s holds records [prefix(s), prefix(s+1)) (a counter may have counted past its capacity)
+  int64_t n = 0;
+#pragma unroll 1
+  for (int sl = 0; sl < src.n_slices; ++sl) n += (int64_t)min(src.counts[sl], src.slice_cap);
+  if (src.total_out && blockIdx.x == 0 && threadIdx.x == 0) *src.total_out = (unsigned long long)n;
+  const fc_jrec* __restrict__ recs = src.base;
+  const int64_t chunk_recs = (int64_t)chunk_tiles * ACC_THREADS;
+  const unsigned lane = threadIdx.x & 31;
 
-    // ---- the junction's slot
-    const unsigned long long klo = (unsigned long long)r0.y | ((unsigned long long)r0.z << 32);
-    const unsigned long long khi = (unsigned long long)r0.x | ((unsigned long long)(r0.w & 3u) << 32) | KEY_OCC;
-    unsigned long long slot = fc_mix64(klo ^ fc_mix64(khi)) & kmask;
-    for (;;) {
-      // L1-cached look: the identity never changes once written and the extrema only grow, so a cached copy is as
-      // good as the one in L2 (the slot of a popular junction is read by thousands of threads); a cached EMPTY may be
-      // stale: the compare-and-swap below then returns the real owner
-      unsigned long long v[4];
-      ld_sector(slots + slot, v);
-      if (v[0] == 0ull && v[1] == 0ull) {
-        const U128 old = cas128(reinterpret_cast<U128*>(slots + slot), U128{0ull, 0ull}, U128{klo, khi});
-        if (old.lo == 0ull && old.hi == 0ull) {
-          jid = (unsigned int)slot;  // a new junction: list it for the finish pass
-          slots[slot].sig = (r0.w >> 16) & 0xFFFu;
-          const unsigned int pos = atomicAdd(&ctr[FC_N_ALLOC], 1u);
-          if (pos < lcap)
-            list[pos] = (unsigned int)slot;
-          else
-            atomicAdd(&ctr[FC_N_OVERFLOW], 1u);
+#pragma unroll 1
+  for (int64_t c0 = (int64_t)blockIdx.x * chunk_recs; c0 < n; c0 += (int64_t)gridDim.x * chunk_recs) {
+    for (int e = threadIdx.x; e < (1 << SKETCH_BITS) / 4; e += ACC_THREADS) reinterpret_cast<unsigned int*>(sketch)[e] = 0u;
+    for (int e = threadIdx.x; e < HOT_ENTRIES; e += ACC_THREADS) {
+      hot.tag[e] = hot.c0[e] = hot.c1[e] = hot.c2[e] = 0u;
+      hot.qmax_l[e] = hot.qmax_r[e] = hot.inv_dist[e] = hot.inv_ov[e] = hot.inv_nh[e] = 0u;
+      hot.first_inv[e] = 0ull;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int t = 0; t < chunk_tiles; ++t) {
+      const int64_t i = c0 + (int64_t)t * ACC_THREADS + threadIdx.x;
+      const bool active = i < n;
+      const unsigned amask = __ballot_sync(0xffffffffu, active);
+      if (!active) continue;  // (trailing lanes of the last tile; the masks below name the active lanes only)
+      int64_t rec_at = i;
+      if (src.n_slices > 1) {
+        int64_t before = 0;
+#pragma unroll 1
+        for (int sl = 0; sl < src.n_slices; ++sl) {
+          const int64_t c = (int64_t)min(src.counts[sl], src.slice_cap);
+          if (i >= before && i < before + c) rec_at = (int64_t)sl * (int64_t)src.slice_cap + (i - before);
+          before += c;
+        }
+      }
+      const uint4* rp = reinterpret_cast<const uint4*>(recs + rec_at);
+      const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2);
+      // fc_jrec: chrom,start,end,sk | idx, read_hash | qname_hash, q_left,q_right, n_hits,dist,ov
+      const unsigned sk = r0.w;
+      const unsigned long long idx = (unsigned long long)r1.x | ((unsigned long long)r1.y << 32);
+      const unsigned long long read_hash = (unsigned long long)r1.z | ((unsigned long long)r1.w << 32);
+      const unsigned long long qname_hash = (unsigned long long)r2.x | ((unsigned long long)r2.y << 32);
+      const bool name_known = (sk & SK_NAME_KNOWN) != 0u;
+      // names and reads share the set: the name's value is salted so that equal hashes of the two kinds stay apart
+      const unsigned long long s_read = set_first_slot(read_hash, smask);
+      unsigned long long s_name = 0ull;
+      if (!(exp_ & 64)) prefetch_l2(sets + s_read);
+      if (!name_known) {
+        s_name = set_first_slot(~qname_hash, smask);
+        if (!(exp_ & 64)) prefetch_l2(sets + s_name);
+      }
+
+      // ---- the junction's slot
+      const unsigned long long klo = (unsigned long long)r0.y | ((unsigned long long)r0.z << 32);
+      const unsigned long long khi = (unsigned long long)r0.x | ((unsigned long long)(sk & 3u) << 32) | KEY_OCC;
+      unsigned long long slot = fc_mix64(klo ^ fc_mix64(khi)) & kmask, cur_f = 0ull, cur_x = 0ull;
+      for (; !(exp_ & 32);) {
+        // L1-cached look: the identity never changes once written and the extrema only grow, so a cached copy is as
+        // good as the one in L2 (the slot of a popular junction is read by thousands of threads); a cached EMPTY may be
+        // stale: the compare-and-swap below then returns the real owner
+        unsigned long long v[4];
+        ld_sector(slots + slot, v);
+        if (v[0] == 0ull && v[1] == 0ull) {
+          const U128 old = cas128(reinterpret_cast<U128*>(slots + slot), U128{0ull, 0ull}, U128{klo, khi});
+          if (old.lo == 0ull && old.hi == 0ull) {
+            slots[slot].sig = (sk >> 16) & 0xFFFu;  // a new junction: list it for the finish pass
+            const unsigned int pos = atomicAdd(&ctr[FC_N_ALLOC], 1u);
+            if (pos < lcap)
+              list[pos] = (unsigned int)slot;
+            else
+              atomicAdd(&ctr[FC_N_OVERFLOW], 1u);
+            break;
+          }
+          v[0] = old.lo;
+          v[1] = old.hi;
+          v[2] = v[3] = 0ull;  // extrema unknown: "nothing yet" is a valid (stale) view
+        }
+        if (v[0] == klo && v[1] == khi) {
+          cur_f = v[2];
+          cur_x = v[3];
           break;
         }
-        v[0] = old.lo;
-        v[1] = old.hi;
-        v[2] = v[3] = 0ull;  // extrema unknown: "nothing yet" is a valid (stale) view
+        slot = (slot + 1ull) & kmask;
       }
-      if (v[0] == klo && v[1] == khi) {
-        jid = (unsigned int)slot;
-        cur_f = v[2];
-        cur_x = v[3];
-        break;
+      const unsigned int jid = (unsigned int)slot;  // slot number = the junction's id in this call
+      JSlot* a = slots + jid;
+
+      // ---- has the CTA met this junction before (in this chunk)?  lanes of the warp that share it are combined
+      // (the sketch is a hint, so its counters are bumped without atomics: a lost increment only delays the promotion)
+      volatile unsigned char* sk_cnt = sketch + ((jid * 0x85EBCA6Bu) >> (32 - SKETCH_BITS));
+      const unsigned int seen = *sk_cnt;
+      if (seen < 255u) *sk_cnt = (unsigned char)(seen + 1u);
+      const unsigned peers = __match_any_sync(amask, jid);
+      const unsigned group = __popc(peers);
+      const int leader = __ffs((int)peers) - 1;
+      const bool lead = (int)lane == leader;
+      int he = -1;
+      if (!(exp_ & 16)) {
+        if (lead) he = hot_find_or_insert(hot, jid, seen >= 1u || group >= 2u);
+        he = __shfl_sync(peers, he, leader);
       }
-      slot = (slot + 1ull) & kmask;
-    }
-  }
-  // ---- how often does the CTA see this junction?
-  const unsigned int sk_slot = (jid * 0x85EBCA6Bu) >> (32 - SKETCH_BITS);
-  if (active) atomicAdd(&sketch[sk_slot], 1u);
-  __syncthreads();
-  if (active) {
-    // fc_jrec: chrom,start,end,sk | idx, read_hash | qname_hash, q_left,q_right, n_hits,dist,ov
-    const unsigned long long idx = (unsigned long long)r1.x | ((unsigned long long)r1.y << 32);
-    const unsigned long long read_hash = (unsigned long long)r1.z | ((unsigned long long)r1.w << 32);
-    const unsigned long long qname_hash = (unsigned long long)r2.x | ((unsigned long long)r2.y << 32);
-    const int q_left = (int)(short)(r2.z & 0xFFFFu), q_right = (int)(short)(r2.z >> 16);
-    const unsigned n_hits = r2.w & 0xFFFFu, dist = (r2.w >> 16) & 0xFFu, ov = r2.w >> 24;
-    const unsigned sk = r0.w;
-    JSlot* a = slots + jid;
 
-    // ---- lanes of the warp that share the junction; a junction seen twice in the CTA goes through shared memory
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned peers = __match_any_sync(amask, jid);
-    const unsigned group = __popc(peers);
-    const bool lead = (int)lane == __ffs((int)peers) - 1;
-    int he = -1;
-    if (group >= 2u || sketch[sk_slot] >= 2u) {
-      if (lead) he = hot_find_or_insert(hot, jid);
-      he = __shfl_sync(peers, he, __ffs((int)peers) - 1);
-    }
-
-    // ---- extrema
-    const unsigned long long f = ~idx;
-    if (he >= 0) {
-      const unsigned ql = (unsigned)(q_left + 32768), qr = (unsigned)(q_right + 32768);
-      const unsigned idist = 255u - dist, iov = 255u - ov, inh = 65535u - n_hits;
-      if (f > hot.first_inv[he]) atomicMax(&hot.first_inv[he], f);
-      if (ql > hot.qmax_l[he]) atomicMax(&hot.qmax_l[he], ql);
-      if (qr > hot.qmax_r[he]) atomicMax(&hot.qmax_r[he], qr);
-      if (idist > hot.inv_dist[he]) atomicMax(&hot.inv_dist[he], idist);
-      if (iov > hot.inv_ov[he]) atomicMax(&hot.inv_ov[he], iov);
-      if (inh > hot.inv_nh[he]) atomicMax(&hot.inv_nh[he], inh);
-    } else {
-      extrema_to_global(a, f, ext_pack(q_left, q_right, dist, ov, n_hits), cur_f, cur_x);
-    }
-
-    // ---- distinct reads / fragment names of the junction
-    const unsigned long long tag = (unsigned long long)jid + 1ull;  // never 0: no entry is all-zero
-    bool new_read = false, new_name = false;
-    set_insert2(sets, smask, read_hash, tag, s_read, !name_known, qname_hash, tag | (1ull << 32), s_name, new_read, new_name);
-    const bool dup_name = name_known ? (sk & SK_NAME_DUP) != 0u : !new_name;
-
-    // ---- counters
-    const unsigned den = (sk >> 8) & 0xFFu;
-    const int cls = den == 1 ? 0 : den == 2 ? 1 : den == 4 ? 2 : den == 8 ? 3 : 4;
-    if (cls == 4) atomicAdd(&ctr[FC_N_OTHER], 1u);
-    const unsigned fx = cls < 4 ? (8u >> cls) : 0u;
-    const bool bridge = q_left != 0 && q_right != 0;
-    const unsigned nb = bridge ? 0u : fx;
-    const unsigned c2 = new_read ? (unsigned)(read_hash & 1ull) : 2u;  // (bit 0 of the hash flags a palindromic read)
-    if (__all_sync(amask, group == 1u)) {
-      // no two lanes of the warp share a junction (the usual case)
+      // ---- extrema
+      const int q_left = (int)(short)(r2.z & 0xFFFFu), q_right = (int)(short)(r2.z >> 16);
+      const unsigned n_hits = r2.w & 0xFFFFu, dist = (r2.w >> 16) & 0xFFu, ov = r2.w >> 24;
+      const unsigned long long f = ~idx;
       if (he >= 0) {
-        atomicAdd(&hot.c0[he], 1u | (fx << 16));
-        if (nb | (unsigned)dup_name) atomicAdd(&hot.c1[he], nb | ((unsigned)dup_name << 16));
-        if (c2) atomicAdd(&hot.c2[he], c2);
-      } else {
-        atomicAdd(&a->c0, 1ull | ((unsigned long long)fx << 32));
-        if (nb | (unsigned)dup_name) atomicAdd(&a->c1, (unsigned long long)nb | ((unsigned long long)dup_name << 32));
-        if (c2) atomicAdd(&a->c2, (unsigned long long)c2);
+        const unsigned ql = (unsigned)(q_left + 32768), qr = (unsigned)(q_right + 32768);
+        const unsigned idist = 255u - dist, iov = 255u - ov, inh = 65535u - n_hits;
+        if (f > hot.first_inv[he]) atomicMax(&hot.first_inv[he], f);
+        if (ql > hot.qmax_l[he]) atomicMax(&hot.qmax_l[he], ql);
+        if (qr > hot.qmax_r[he]) atomicMax(&hot.qmax_r[he], qr);
+        if (idist > hot.inv_dist[he]) atomicMax(&hot.inv_dist[he], idist);
+        if (iov > hot.inv_ov[he]) atomicMax(&hot.inv_ov[he], iov);
+        if (inh > hot.inv_nh[he]) atomicMax(&hot.inv_nh[he], inh);
+      } else if (!(exp_ & 8)) {
+        extrema_to_global(a, f, ext_pack(q_left, q_right, dist, ov, n_hits), cur_f, cur_x);
       }
-    } else {
-      unsigned w = 0, b = 0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        w += (8u >> k) * __popc(__ballot_sync(amask, cls == k) & peers);
-        b += (8u >> k) * __popc(__ballot_sync(amask, cls == k && !bridge) & peers);
-      }
-      const unsigned dups = __popc(__ballot_sync(amask, dup_name) & peers);
-      const unsigned c2s = 2u * __popc(__ballot_sync(amask, c2 == 2u) & peers) + __popc(__ballot_sync(amask, c2 == 1u) & peers);
-      if (lead) {
+
+      // ---- distinct reads / fragment names of the junction
+      const unsigned long long tag = (unsigned long long)jid + 1ull;  // never 0: no entry is all-zero
+      bool new_read = false, new_name = false;
+      if (exp_ & 1) {
+        new_read = true;
+        if (!(exp_ & 2)) set_insert2(sets, smask, qname_hash, tag | (1ull << 32), s_name, false, 0ull, 0ull, 0ull, new_name, new_read), new_read = true;
+        else new_name = true;
+      } else
+      set_insert2(sets, smask, read_hash, tag, s_read, !name_known && !(exp_ & 2), qname_hash, tag | (1ull << 32), s_name, new_read, new_name);
+      if (exp_ & 2) new_name = true;
+      const bool dup_name = name_known ? (sk & SK_NAME_DUP) != 0u : !new_name;
+
+      // ---- counters
+      const unsigned den = (sk >> 8) & 0xFFu;
+      const int cls = den == 1 ? 0 : den == 2 ? 1 : den == 4 ? 2 : den == 8 ? 3 : 4;
+      if (cls == 4) atomicAdd(&ctr[FC_N_OTHER], 1u);
+      const unsigned fx = cls < 4 ? (8u >> cls) : 0u;
+      const bool bridge = q_left != 0 && q_right != 0;
+      const unsigned nb = bridge ? 0u : fx;
+      const unsigned c2 = new_read ? (unsigned)(read_hash & 1ull) : 2u;  // (bit 0 of the hash flags a palindromic read)
+      if (exp_ & 4) {
+      } else if (__all_sync(amask, group == 1u)) {
+        // no two lanes of the warp share a junction (the usual case)
         if (he >= 0) {
-          atomicAdd(&hot.c0[he], group | (w << 16));
-          if (b | dups) atomicAdd(&hot.c1[he], b | (dups << 16));
-          if (c2s) atomicAdd(&hot.c2[he], c2s);
+          atomicAdd(&hot.c0[he], 1u | (fx << 14));
+          if (nb | (unsigned)dup_name) atomicAdd(&hot.c1[he], (unsigned)dup_name | (nb << 14));
+          if (c2) atomicAdd(&hot.c2[he], c2);
         } else {
-          atomicAdd(&a->c0, (unsigned long long)group | ((unsigned long long)w << 32));
-          if (b | dups) atomicAdd(&a->c1, (unsigned long long)b | ((unsigned long long)dups << 32));
-          if (c2s) atomicAdd(&a->c2, (unsigned long long)c2s);
+          atomicAdd(&a->c0, 1ull | ((unsigned long long)fx << 32));
+          if (nb | (unsigned)dup_name) atomicAdd(&a->c1, (unsigned long long)nb | ((unsigned long long)dup_name << 32));
+          if (c2) atomicAdd(&a->c2, (unsigned long long)c2);
+        }
+      } else {
+        unsigned w = 0, b = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          w += (8u >> k) * __popc(__ballot_sync(amask, cls == k) & peers);
+          b += (8u >> k) * __popc(__ballot_sync(amask, cls == k && !bridge) & peers);
+        }
+        const unsigned dups = __popc(__ballot_sync(amask, dup_name) & peers);
+        const unsigned c2s = 2u * __popc(__ballot_sync(amask, c2 == 2u) & peers) + __popc(__ballot_sync(amask, c2 == 1u) & peers);
+        if (lead) {
+          if (he >= 0) {
+            atomicAdd(&hot.c0[he], group | (w << 14));
+            if (b | dups) atomicAdd(&hot.c1[he], dups | (b << 14));
+            if (c2s) atomicAdd(&hot.c2[he], c2s);
+          } else {
+            atomicAdd(&a->c0, (unsigned long long)group | ((unsigned long long)w << 32));
+            if (b | dups) atomicAdd(&a->c1, (unsigned long long)b | ((unsigned long long)dups << 32));
+            if (c2s) atomicAdd(&a->c2, (unsigned long long)c2s);
+          }
         }
       }
     }
-  }
-  __syncthreads();
-  for (int e = threadIdx.x; e < HOT_ENTRIES; e += blockDim.x) {
-    if (hot.tag[e] == 0u) continue;
-    JSlot* a = slots + (hot.tag[e] - 1u);
-    const unsigned long long x = (unsigned long long)(hot.qmax_l[e] | (hot.qmax_r[e] << 16)) |
-                                 ((unsigned long long)(hot.inv_ov[e] | (hot.inv_dist[e] << 8) | (hot.inv_nh[e] << 16)) << 32);
-    const ulonglong2 cur = __ldcg(reinterpret_cast<const ulonglong2*>(&a->first_inv));
-    extrema_to_global(a, hot.first_inv[e], x, cur.x, cur.y);
-    const unsigned c0 = hot.c0[e], c1 = hot.c1[e], c2 = hot.c2[e];
-    atomicAdd(&a->c0, (unsigned long long)(c0 & 0xFFFFu) | ((unsigned long long)(c0 >> 16) << 32));
-    if (c1) atomicAdd(&a->c1, (unsigned long long)(c1 & 0xFFFFu) | ((unsigned long long)(c1 >> 16) << 32));
-    if (c2) atomicAdd(&a->c2, (unsigned long long)c2);
+    __syncthreads();
+    for (int e = threadIdx.x; e < HOT_ENTRIES; e += ACC_THREADS) {
+      if (hot.tag[e] == 0u) continue;
+      JSlot* a = slots + (hot.tag[e] - 1u);
+      const unsigned long long x = (unsigned long long)(hot.qmax_l[e] | (hot.qmax_r[e] << 16)) |
+                                   ((unsigned long long)(hot.inv_ov[e] | (hot.inv_dist[e] << 8) | (hot.inv_nh[e] << 16)) << 32);
+      const ulonglong2 cur = __ldcg(reinterpret_cast<const ulonglong2*>(&a->first_inv));
+      extrema_to_global(a, hot.first_inv[e], x, cur.x, cur.y);
+      const unsigned c0v = hot.c0[e], c1v = hot.c1[e], c2v = hot.c2[e];
+      if (c0v) atomicAdd(&a->c0, (unsigned long long)(c0v & 0x3FFFu) | ((unsigned long long)(c0v >> 14) << 32));
+      if (c1v) atomicAdd(&a->c1, (unsigned long long)(c1v >> 14) | ((unsigned long long)(c1v & 0x3FFFu) << 32));
+      if (c2v) atomicAdd(&a->c2, (unsigned long long)c2v);
+    }
+    __syncthreads();  // the table is re-initialised for the next chunk
   }
 }
 
@@ -1220,15 +1255,28 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st, const Re
   uint32_t* flag = nullptr;
   uint32_t* tile_count = nullptr;
   if (dense) {
-    FC_CUDA(ctx, a.scratch[0].reserve((size_t)range * 4, st, false, 0));
+    FC_CUDA(ctx, a.scratch[0].reserve((size_t)range * 4 + 16, st, false, 0));  // (cleared 16 bytes at a time)
     FC_CUDA(ctx, a.scratch[1].reserve((size_t)n_tiles * 8, st, false, 0));
     flag = (uint32_t*)a.scratch[0].p;
     tile_count = (uint32_t*)a.scratch[1].p;
   }
   tm.mark("clear");
-  fused_accumulate_kernel<<<nblk(ub, ACC_THREADS), ACC_THREADS, 0, st>>>(src, (JSlot*)a.f_keys.p, kcap - 1, (U128*)a.f_sets.p,
-                                                                         scap - 1, (unsigned int*)a.f_acc.p, lcap, ctr, flag, range,
-                                                                         tile_count, n_tiles);
+  {
+    // persistent CTAs: two per SM, each walks chunks of up to ACC_MAX_TILES tiles of ACC_THREADS records; small inputs get
+    // shorter chunks so that every SM has work
+    const int64_t tiles = (ub + ACC_THREADS - 1) / ACC_THREADS;
+    const int64_t ctas = (int64_t)ctx->sm_count * 2;
+    int chunk_tiles = (int)((tiles + 2 * ctas - 1) / (2 * ctas));
+    chunk_tiles = chunk_tiles < 1 ? 1 : (chunk_tiles > ACC_MAX_TILES ? ACC_MAX_TILES : chunk_tiles);
+    const int64_t chunks = (tiles + chunk_tiles - 1) / chunk_tiles;
+    const unsigned grid = (unsigned)(chunks < ctas ? chunks : ctas);
+    // the L2 prefetch of the set slots pays while the set fits L2 (-7 % at 1 M records) and costs 20 % when it does not
+    const char* ee = getenv("FC_ACC_EXP");
+    const int exp_flags = (ee ? atoi(ee) : 0) | ((size_t)scap * 16 > ((size_t)64 << 20) ? 64 : 0);
+    fused_accumulate_kernel<<<grid, ACC_THREADS, 0, st>>>(src, chunk_tiles, exp_flags, (JSlot*)a.f_keys.p, kcap - 1, (U128*)a.f_sets.p, scap - 1,
+                                                          (unsigned int*)a.f_acc.p, lcap, ctr, (uint4*)flag, (range + 3) / 4, tile_count,
+                                                          n_tiles);
+  }
   FC_LAUNCH_CHECK(ctx);
   tm.mark("accumulate");
   const unsigned sweep_blocks = (unsigned)ctx->sm_count * 8u;

@@ -183,11 +183,28 @@ __global__ void __launch_bounds__(BS, MB) scan_kernel(fc::GenomeView g, fc::Scan
   }
   if constexpr (MODE != 0) {
     const bool accept = (h.w2 & 0xFFFFu) != 0u;
+    // Is this the first record of its FRAGMENT for its junction (n_frags = distinct read names per junction,
+    // find_circ.py:584-586)?  The rows of a fragment are neighbours and the descriptor says how many come before and after:
+    // when they all sit in this warp the answer is a few shuffles, and the aggregation needs no name set for the record.
+    const uint32_t fr = m.z >> 28, back = fr & 3u, fwd = fr >> 2;
+    const unsigned lane = threadIdx.x & 31;
+    const bool known = fr != 15u && lane >= back && lane + fwd < 32u;
+    bool dup = false;
+    if (__any_sync(0xffffffffu, known && back != 0u)) {
+      const uint32_t kw = (h.w3 & 1u) | (((m.z >> 24) & 1u) << 1) | ((m.w & 0xFFFFFFu) << 2) | ((uint32_t)accept << 31);
+#pragma unroll
+      for (int k = 1; k <= 3; ++k) {
+        const uint32_t okw = __shfl_up_sync(0xffffffffu, kw, k);
+        const int32_t os = __shfl_up_sync(0xffffffffu, h.start, k), oe = __shfl_up_sync(0xffffffffu, h.end, k);
+        if ((uint32_t)k <= back && known && accept && okw == kw && os == h.start && oe == h.end) dup = true;
+      }
+    }
     fc_jrec r;
     if (accept) {
       const uint32_t q = e.q[i];
       r = fc::make_record_from(h.start, h.end, h.w2, h.w3, m.w & 0xFFFFFFu, (m.z >> 24) & 7u, m.w >> 24, (int16_t)(q & 0xFFFFu),
                                (int16_t)(q >> 16), e.read_hash[i], e.qname_hash[i], e.idx ? e.idx[i] : e.idx_base + (uint64_t)i);
+      if (known) r.sk |= FC_SK_NAME_KNOWN | (dup ? FC_SK_NAME_DUP : 0u);
     }
     if constexpr (MODE == 1)
       fc::emit_block<BS>(accept, r, e.n_recs, e.recs);

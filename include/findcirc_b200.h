@@ -122,11 +122,16 @@ typedef struct fc_hit {
 
 /* 48-byte junction record: one per Hit.add() call (find_circ.py:526-582); this is also the unit exchanged
  * between GPUs (hash-partitioned by key). */
+#define FC_SK_NAME_KNOWN 8u
+#define FC_SK_NAME_DUP 16u
 typedef struct fc_jrec {
   uint32_t chrom;
   uint32_t start;
   uint32_t end;
   uint32_t sk;         /* bit0 strand '-', bit1 kind (1 = linear table), bit2 read is its own reverse complement,
+                          bit3 FC_SK_NAME_KNOWN: bit4 (FC_SK_NAME_DUP) tells whether an earlier record of the same fragment
+                          already supports this junction, qname_hash need not be consulted (set by the scan kernels from the
+                          fragment fields of fc_batch descriptors; valid only when a read name occurs in ONE fragment),
                           bits 8-15 weight denominator (weight = 1/den, find_circ.py:1084), bits 16-27 signal */
   uint64_t idx;        /* position in the input stream (orders names and float sums, find_circ.py:684-686, 544) */
   uint64_t read_hash;  /* strand-invariant hash of primary.seq (n_uniq, find_circ.py:581-590) */

@@ -47,5 +47,5 @@ for r in rows[hi + 1 :]:
     tot += v
     tots += s
 print("total warp-instructions %d, samples %d" % (tot, tots))
-for ln, (v, s, t, k) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+for ln, (v, s, t, k) in sorted(agg.items(), key=lambda kv: -kv[1][int(__import__("os").environ.get("SORTCOL","0"))])[:top]:
     print("%10d %5.1f%%  samples %5.1f%%  lanes %4.1f  sass %3d  %s" % (v, 100.0 * v / tot, 100.0 * s / max(tots, 1), t / max(v, 1), k, ln))

@@ -572,3 +572,66 @@ def test_scan_emit_equals_scan_then_emit(torch_cuda, read_len, noncanonical):
     assert torch.equal(out1, out2)
     assert len(t1) > 50 and t1.tobytes() == t2.tobytes()
     e.close()
+
+
+@pytest.mark.parametrize("read_len", [100, 150, 44])
+def test_packed_batch_with_fragment_rows_equals_soa_path(torch_cuda, read_len):
+    """fc_batch_pack + fc_scan_emit_batch with the fragment fields of the descriptors (the scan kernel settles n_frags with
+    shuffles, records carry FC_SK_NAME_KNOWN) == fc_scan_emit on the fc_pairs batch (every record goes through the name set):
+    same hits, same junction table.  Fragments of 1..6 rows, rows of one fragment often on the same junction, fragments
+    straddling warp boundaries (32 rows) and one that is too long for the 2-bit fields."""
+    torch = torch_cuda
+    g, J, t = _case(read_len, 20, seed=77 + read_len, n=9000, error_rate=0.01)
+    chrom, a_start, b_end, l, flags, internal = H.pairs_to_soa(t, 20, 2)
+    n = len(chrom)
+    rng = np.random.default_rng(5)
+    # fragments: runs of rows that share a read name; make the rows of a run copies of its first row now and then
+    sizes = rng.choice([1, 1, 1, 2, 2, 3, 4, 5, 6], size=n)
+    frag_id = np.repeat(np.arange(len(sizes)), sizes)[:n]
+    first = np.concatenate([[0], np.nonzero(np.diff(frag_id))[0] + 1])
+    first_of = first[np.searchsorted(first, np.arange(n), side="right") - 1]
+    copy = rng.random(n) < 0.5
+    src = np.where(copy, first_of, np.arange(n))
+    chrom, a_start, b_end, l, flags, internal = (x[src] for x in (chrom, a_start, b_end, l, flags, internal))
+    reads = t.reads[src]
+    e = _engine(asize=20)
+    e.load_genome_arrays(g.names, g.seqs)
+    dev = torch.device("cuda:0")
+    q_a = (t.as_a - np.maximum(t.xs_a, 0)).astype(np.int16)[src]
+    q_b = (t.as_b - np.maximum(t.xs_b, 0)).astype(np.int16)[src]
+    wden = rng.choice(np.array([1, 1, 2, 4], dtype=np.uint8), size=n)
+    rh = e.hash_reads(reads, np.full(n, t.read_len, dtype=np.int32))
+    qh = np.array([e.hash_bytes(b"frag%d" % f) for f in frag_id], dtype=np.uint64)
+    back = np.arange(n) - first_of
+    size_of = np.bincount(frag_id)[frag_id]
+    fwd = size_of - 1 - back
+    frag = np.where(size_of > 4, 15, back | (fwd << 2)).astype(np.uint8)
+    n_words = max(1, (int(l.max()) + 31) // 32)
+    tn = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    d_chrom, d_a, d_b, d_l, d_fl, d_asc = tn(chrom), tn(a_start), tn(b_end), tn(l), tn(flags), tn(internal)
+    planes = torch.zeros(3 * n_words * n, dtype=torch.int32, device=dev)
+    e.pack_reads(d_asc, internal.shape[1], d_l, n_words, planes, d_fl, 0)
+    pairs = e.make_pairs(n, d_chrom, d_a, d_b, d_l, d_fl, planes, n_words, int(l.max()))
+    pay = (tn(wden), tn(q_a), tn(q_b), tn(rh.view(np.int64)), tn(qh.view(np.int64)))
+    out1 = torch.zeros(n * 4, dtype=torch.int32, device=dev)
+    out2 = torch.zeros(n * 4, dtype=torch.int32, device=dev)
+    e.agg_reset()
+    e.scan_emit(pairs, out1, *pay, 0, 0)
+    t1 = e.agg_fetch(e.agg_finalize())
+    nw = e.batch_words(int(l.max()))
+    meta = torch.zeros(n * 4, dtype=torch.int32, device=dev)
+    rows = torch.zeros(n * 2 * nw, dtype=torch.int32, device=dev)
+    rn_rows = torch.zeros(n * nw, dtype=torch.int32, device=dev)
+    q = torch.zeros(n, dtype=torch.int32, device=dev)
+    for fr in (None, tn(frag)):
+        batch = e.pack_batch(pairs, meta, rows, rn_rows, pay[0], pay[1], pay[2], q, fr, 0)
+        e.agg_reset()
+        e.scan_emit_batch(batch, out2, q, pay[3], pay[4], 0, 0)
+        t2 = e.agg_fetch(e.agg_finalize())
+        assert torch.equal(out1, out2)
+        assert len(t1) > 50 and t1.tobytes() == t2.tobytes()
+    assert (t1["n_frags"] < t1["n_spanned"]).any()
+    out3 = torch.zeros(n * 4, dtype=torch.int32, device=dev)
+    e.scan_batch(batch, out3, 0)
+    assert torch.equal(out1, out3)
+    e.close()
