@@ -278,21 +278,23 @@ struct RecSrc {
 // never cleared as a whole.
 // ======================================================================================================================
 struct alignas(64) JSlot {
-  // sector 0: identity + extrema (everything is kept as a maximum, all-zero = nothing yet = identity of max)
-  unsigned long long klo;        // start | end << 32
-  unsigned long long khi;        // chrom | (strand, kind) << 32 | KEY_OCC
-  unsigned long long first_inv;  // ~(smallest record position / idx)
-  unsigned long long ext;        // (q_left + 32768) | (q_right + 32768) << 16 | (255 - ov) << 32 | (255 - dist) << 40 | (65535 - n_hits) << 48
-  // sector 1: counters
-  unsigned long long c0;         // n_spanned | 8 * n_weighted << 32
-  unsigned long long c1;         // rare: 8 * weight of records that are no unique bridge | records whose fragment name is not new << 32
-  unsigned long long c2;         // rare: 2 per record whose read was seen before + 1 per new palindromic read
-  unsigned int sig;              // 12-bit signal code (same for every record of the junction)
+  // sector 0: everything an ordinary record looks at or changes (maxima: all-zero = nothing yet = identity of max)
+  unsigned long long klo;  // start | end << 32
+  unsigned long long kf;   // KEY_OCC | chrom (24 bits) << 39 | (strand, kind) << 37 | first: FIRST_MAX - (smallest idx - idx base)
+  unsigned long long c0;   // n_spanned | 8 * n_weighted << 32
+  unsigned long long ext;  // (q_left + 32768) | (q_right + 32768) << 16 | (255 - ov) << 32 | (255 - dist) << 40 | (65535 - n_hits) << 48
+  // sector 1: what few records touch
+  unsigned long long c1;   // 8 * weight of records that are no unique bridge | records whose fragment name is not new << 32
+  unsigned long long c2;   // 2 per record whose read was seen before + 1 per new palindromic read
+  unsigned int sig;        // 12-bit signal code (same for every record of the junction)
   unsigned int pad;
+  unsigned long long spare;
 };
-static_assert(sizeof(JSlot) == 64 && offsetof(JSlot, first_inv) == 16 && offsetof(JSlot, c0) == 32, "JSlot layout");
+static_assert(sizeof(JSlot) == 64 && offsetof(JSlot, c0) == 16 && offsetof(JSlot, c1) == 32, "JSlot layout");
 
 constexpr unsigned long long KEY_OCC = 1ull << 63;
+constexpr int FIRST_BITS = 37;  // record positions relative to the call's idx base: 1.4e11
+constexpr unsigned long long FIRST_MAX = (1ull << FIRST_BITS) - 1ull;
 constexpr long long FUSED_MAX_RECORDS = 1ll << 28;  // keeps 8 * n_spanned and the slot numbers inside their fields
 constexpr uint32_t SK_NAME_KNOWN = FC_SK_NAME_KNOWN, SK_NAME_DUP = FC_SK_NAME_DUP;  // the emitter already knows whether the fragment is new to the junction
 
@@ -312,11 +314,11 @@ __device__ __forceinline__ unsigned long long ext_max(unsigned long long a, unsi
   const unsigned hi = (__vmaxu2(ahi, bhi) & 0xFFFF0000u) | (__vmaxu4(ahi, bhi) & 0x0000FFFFu);
   return (unsigned long long)lo | ((unsigned long long)hi << 32);
 }
-// f / x: extrema of one record (or of one shared-memory entry); cur_f / cur_x: what a (possibly stale: maxima only grow,
-// so an old value can only cause a needless attempt) look at the slot showed
-__device__ __forceinline__ void extrema_to_global(JSlot* s, unsigned long long f, unsigned long long x, unsigned long long cur_f,
+// kf / x: identity + first position and extrema of one record (or of one shared-memory entry); cur_kf / cur_x: what a
+// (possibly stale: maxima only grow, so an old value can only cause a needless attempt) look at the slot showed
+__device__ __forceinline__ void extrema_to_global(JSlot* s, unsigned long long kf, unsigned long long x, unsigned long long cur_kf,
                                                   unsigned long long cur_x) {
-  if (f > cur_f) atomicMax(&s->first_inv, f);
+  if (kf > cur_kf) atomicMax(&s->kf, kf);  // (the identity bits are the same for every record of the junction)
   unsigned long long want = ext_max(cur_x, x);
   while (want != cur_x) {
     const unsigned long long old = atomicCAS(&s->ext, cur_x, want);
@@ -384,23 +386,23 @@ __device__ __forceinline__ void set_insert2(U128* table, unsigned long long mask
 // A junction that collects a few per cent of all reads (expression is heavy-tailed) would otherwise put all of its
 // updates on one L2 sector, and an L2 slice retires about one request per clock for one sector (measured: with a
 // Zipf(1) popularity the direct version spends 4x the time of the uniform case).  So the lanes of a warp that share a
-// junction are combined first, and a junction that the CTA has met before (counted in a small shared-memory sketch) is
-// accumulated in a shared-memory table of the CTA and flushed at the end of the CTA's chunk of records; junctions seen
-// once per chunk -- the bulk of the distinct ones -- go to global memory directly and never touch the table.
-// A CTA walks its chunk tile by tile WITHOUT barriers in between (the sketch is only a hint: whichever way a record
-// goes, it ends up in the junction's slot), so the warps hide each other's memory round trips.
+// junction are combined first, and a junction that two lanes of one warp have shared once enters a shared-memory table
+// of the CTA, is accumulated there (found with a plain load) and flushed at the end of the CTA's chunk of records;
+// the bulk of the distinct junctions never meet that condition, go to global memory directly and never touch the table.
+// A CTA walks its chunk tile by tile WITHOUT barriers in between (whichever way a record goes, it ends up in the
+// junction's slot), so the warps hide each other's memory round trips.  Measured on the B200 (config 3, 44 M records):
+// without the table 9.96 ms, with it 3.6 ms; a count-min sketch as a second admission rule changed nothing.
 constexpr int ACC_THREADS = 512;
 constexpr int ACC_MAX_TILES = 16;  // tiles of ACC_THREADS records per chunk (between two flushes of the shared-memory table)
 constexpr int HOT_ENTRIES = 512;
 constexpr int HOT_BITS = 9;
-constexpr int SKETCH_BITS = 13;
 struct HotTable {
   unsigned int tag[HOT_ENTRIES];    // junction slot + 1, 0 = free
   unsigned int c0[HOT_ENTRIES];     // n_spanned | 8 * weight << 14 (a chunk holds at most 8192 records of weight <= 1)
   unsigned int c1[HOT_ENTRIES];     // names seen before | 8 * non-bridge weight << 14
   unsigned int c2[HOT_ENTRIES];
   unsigned int qmax_l[HOT_ENTRIES], qmax_r[HOT_ENTRIES], inv_dist[HOT_ENTRIES], inv_ov[HOT_ENTRIES], inv_nh[HOT_ENTRIES];
-  unsigned long long first_inv[HOT_ENTRIES];
+  unsigned long long first_inv[HOT_ENTRIES];  // identity | first position, as JSlot.kf
 };
 static_assert(ACC_MAX_TILES * ACC_THREADS < (1 << 14) && ACC_MAX_TILES * ACC_THREADS * 8 < (1 << 18), "hot-table fields");
 
@@ -427,14 +429,13 @@ __device__ __forceinline__ void ld_sector(const JSlot* s, unsigned long long (&v
   asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(s));
 }
 
-__global__ void __launch_bounds__(ACC_THREADS, 2) fused_accumulate_kernel(RecSrc src, int chunk_tiles, int exp_, JSlot* __restrict__ slots,
+__global__ void __launch_bounds__(ACC_THREADS, 2) fused_accumulate_kernel(RecSrc src, int chunk_tiles, int prefetch, unsigned long long idx_base, JSlot* __restrict__ slots,
                                                                   unsigned long long kmask, U128* __restrict__ sets,
                                                                   unsigned long long smask, unsigned int* __restrict__ list,
                                                                   unsigned int lcap, unsigned int* __restrict__ ctr,
                                                                   uint4* __restrict__ flag4, int64_t n_flag4,
                                                                   uint32_t* __restrict__ tile_count, int64_t n_tiles) {
   __shared__ HotTable hot;
-  __shared__ __align__(16) unsigned char sketch[1 << SKETCH_BITS];
   // the rank flags and tile counters of the finish pass are cleared on the way
   {
     const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gs = (int64_t)gridDim.x * blockDim.x;
@@ -453,7 +454,6 @@ __global__ void __launch_bounds__(ACC_THREADS, 2) fused_accumulate_kernel(RecSrc
 
 #pragma unroll 1
   for (int64_t c0 = (int64_t)blockIdx.x * chunk_recs; c0 < n; c0 += (int64_t)gridDim.x * chunk_recs) {
-    for (int e = threadIdx.x; e < (1 << SKETCH_BITS) / 4; e += ACC_THREADS) reinterpret_cast<unsigned int*>(sketch)[e] = 0u;
     for (int e = threadIdx.x; e < HOT_ENTRIES; e += ACC_THREADS) {
       hot.tag[e] = hot.c0[e] = hot.c1[e] = hot.c2[e] = 0u;
       hot.qmax_l[e] = hot.qmax_r[e] = hot.inv_dist[e] = hot.inv_ov[e] = hot.inv_nh[e] = 0u;
@@ -487,89 +487,95 @@ __global__ void __launch_bounds__(ACC_THREADS, 2) fused_accumulate_kernel(RecSrc
       // names and reads share the set: the name's value is salted so that equal hashes of the two kinds stay apart
       const unsigned long long s_read = set_first_slot(read_hash, smask);
       unsigned long long s_name = 0ull;
-      if (!(exp_ & 64)) prefetch_l2(sets + s_read);
+      if (prefetch) prefetch_l2(sets + s_read);
       if (!name_known) {
         s_name = set_first_slot(~qname_hash, smask);
-        if (!(exp_ & 64)) prefetch_l2(sets + s_name);
+        if (prefetch) prefetch_l2(sets + s_name);
       }
 
       // ---- the junction's slot
       const unsigned long long klo = (unsigned long long)r0.y | ((unsigned long long)r0.z << 32);
-      const unsigned long long khi = (unsigned long long)r0.x | ((unsigned long long)(sk & 3u) << 32) | KEY_OCC;
-      unsigned long long slot = fc_mix64(klo ^ fc_mix64(khi)) & kmask, cur_f = 0ull, cur_x = 0ull;
-      for (; !(exp_ & 32);) {
-        // L1-cached look: the identity never changes once written and the extrema only grow, so a cached copy is as
+      const unsigned long long rel = idx - idx_base;
+      // (a position or chromosome number beyond the slot's fields: the call falls back to the sort-based path)
+      if ((rel >> FIRST_BITS) != 0ull || (r0.x >> 24) != 0u) atomicAdd(&ctr[FC_N_OTHER], 1u);
+      const unsigned long long kid = KEY_OCC | ((unsigned long long)(r0.x & 0xFFFFFFu) << 39) | ((unsigned long long)(sk & 3u) << 37);
+      const unsigned long long kf = kid | (FIRST_MAX - (rel & FIRST_MAX));
+      unsigned long long slot = fc_mix64(klo ^ fc_mix64(kid)) & kmask, cur_kf = 0ull, cur_x = 0ull;
+      bool fresh = false;
+      for (;;) {
+        // L1-cached look: the identity never changes once written and the maxima only grow, so a cached copy is as
         // good as the one in L2 (the slot of a popular junction is read by thousands of threads); a cached EMPTY may be
         // stale: the compare-and-swap below then returns the real owner
         unsigned long long v[4];
         ld_sector(slots + slot, v);
         if (v[0] == 0ull && v[1] == 0ull) {
-          const U128 old = cas128(reinterpret_cast<U128*>(slots + slot), U128{0ull, 0ull}, U128{klo, khi});
+          const U128 old = cas128(reinterpret_cast<U128*>(slots + slot), U128{0ull, 0ull}, U128{klo, kf});
           if (old.lo == 0ull && old.hi == 0ull) {
-            slots[slot].sig = (sk >> 16) & 0xFFFu;  // a new junction: list it for the finish pass
-            const unsigned int pos = atomicAdd(&ctr[FC_N_ALLOC], 1u);
-            if (pos < lcap)
-              list[pos] = (unsigned int)slot;
-            else
-              atomicAdd(&ctr[FC_N_OVERFLOW], 1u);
+            fresh = true;  // a new junction (listed for the finish pass below)
+            cur_kf = kf;
             break;
           }
           v[0] = old.lo;
           v[1] = old.hi;
-          v[2] = v[3] = 0ull;  // extrema unknown: "nothing yet" is a valid (stale) view
+          v[3] = 0ull;  // extrema unknown: "nothing yet" is a valid (stale) view
         }
-        if (v[0] == klo && v[1] == khi) {
-          cur_f = v[2];
+        if (v[0] == klo && (v[1] >> FIRST_BITS) == (kid >> FIRST_BITS)) {
+          cur_kf = v[1];
           cur_x = v[3];
           break;
         }
         slot = (slot + 1ull) & kmask;
       }
+      {
+        // new junctions of the warp: one atomic for all of them claims their places in the list
+        const unsigned fm = __ballot_sync(amask, fresh);
+        if (fm) {
+          const int fl = __ffs((int)fm) - 1;
+          unsigned int base = 0;
+          if ((int)lane == fl) base = atomicAdd(&ctr[FC_N_ALLOC], (unsigned int)__popc(fm));
+          base = __shfl_sync(amask, base, fl);
+          if (fresh) {
+            const unsigned int pos = base + (unsigned int)__popc(fm & ((1u << lane) - 1u));
+            if (pos < lcap)
+              list[pos] = (unsigned int)slot;
+            else
+              atomicAdd(&ctr[FC_N_OVERFLOW], 1u);
+            slots[slot].sig = (sk >> 16) & 0xFFFu;
+          }
+        }
+      }
       const unsigned int jid = (unsigned int)slot;  // slot number = the junction's id in this call
       JSlot* a = slots + jid;
 
-      // ---- has the CTA met this junction before (in this chunk)?  lanes of the warp that share it are combined
-      // (the sketch is a hint, so its counters are bumped without atomics: a lost increment only delays the promotion)
-      volatile unsigned char* sk_cnt = sketch + ((jid * 0x85EBCA6Bu) >> (32 - SKETCH_BITS));
-      const unsigned int seen = *sk_cnt;
-      if (seen < 255u) *sk_cnt = (unsigned char)(seen + 1u);
+      // ---- lanes of the warp that share the junction are combined; is it in the CTA's table (or does it belong there)?
       const unsigned peers = __match_any_sync(amask, jid);
       const unsigned group = __popc(peers);
       const int leader = __ffs((int)peers) - 1;
       const bool lead = (int)lane == leader;
       int he = -1;
-      if (!(exp_ & 16)) {
-        if (lead) he = hot_find_or_insert(hot, jid, seen >= 1u || group >= 2u);
-        he = __shfl_sync(peers, he, leader);
-      }
+      if (lead) he = hot_find_or_insert(hot, jid, group >= 2u);
+      he = __shfl_sync(peers, he, leader);
 
       // ---- extrema
       const int q_left = (int)(short)(r2.z & 0xFFFFu), q_right = (int)(short)(r2.z >> 16);
       const unsigned n_hits = r2.w & 0xFFFFu, dist = (r2.w >> 16) & 0xFFu, ov = r2.w >> 24;
-      const unsigned long long f = ~idx;
       if (he >= 0) {
         const unsigned ql = (unsigned)(q_left + 32768), qr = (unsigned)(q_right + 32768);
         const unsigned idist = 255u - dist, iov = 255u - ov, inh = 65535u - n_hits;
-        if (f > hot.first_inv[he]) atomicMax(&hot.first_inv[he], f);
+        if (kf > hot.first_inv[he]) atomicMax(&hot.first_inv[he], kf);
         if (ql > hot.qmax_l[he]) atomicMax(&hot.qmax_l[he], ql);
         if (qr > hot.qmax_r[he]) atomicMax(&hot.qmax_r[he], qr);
         if (idist > hot.inv_dist[he]) atomicMax(&hot.inv_dist[he], idist);
         if (iov > hot.inv_ov[he]) atomicMax(&hot.inv_ov[he], iov);
         if (inh > hot.inv_nh[he]) atomicMax(&hot.inv_nh[he], inh);
-      } else if (!(exp_ & 8)) {
-        extrema_to_global(a, f, ext_pack(q_left, q_right, dist, ov, n_hits), cur_f, cur_x);
+      } else {
+        extrema_to_global(a, kf, ext_pack(q_left, q_right, dist, ov, n_hits), cur_kf, cur_x);
       }
 
       // ---- distinct reads / fragment names of the junction
       const unsigned long long tag = (unsigned long long)jid + 1ull;  // never 0: no entry is all-zero
       bool new_read = false, new_name = false;
-      if (exp_ & 1) {
-        new_read = true;
-        if (!(exp_ & 2)) set_insert2(sets, smask, qname_hash, tag | (1ull << 32), s_name, false, 0ull, 0ull, 0ull, new_name, new_read), new_read = true;
-        else new_name = true;
-      } else
-      set_insert2(sets, smask, read_hash, tag, s_read, !name_known && !(exp_ & 2), qname_hash, tag | (1ull << 32), s_name, new_read, new_name);
-      if (exp_ & 2) new_name = true;
+      set_insert2(sets, smask, read_hash, tag, s_read, !name_known, qname_hash, tag | (1ull << 32), s_name, new_read, new_name);
       const bool dup_name = name_known ? (sk & SK_NAME_DUP) != 0u : !new_name;
 
       // ---- counters
@@ -580,8 +586,7 @@ __global__ void __launch_bounds__(ACC_THREADS, 2) fused_accumulate_kernel(RecSrc
       const bool bridge = q_left != 0 && q_right != 0;
       const unsigned nb = bridge ? 0u : fx;
       const unsigned c2 = new_read ? (unsigned)(read_hash & 1ull) : 2u;  // (bit 0 of the hash flags a palindromic read)
-      if (exp_ & 4) {
-      } else if (__all_sync(amask, group == 1u)) {
+      if (__all_sync(amask, group == 1u)) {
         // no two lanes of the warp share a junction (the usual case)
         if (he >= 0) {
           atomicAdd(&hot.c0[he], 1u | (fx << 14));
@@ -620,8 +625,7 @@ __global__ void __launch_bounds__(ACC_THREADS, 2) fused_accumulate_kernel(RecSrc
       JSlot* a = slots + (hot.tag[e] - 1u);
       const unsigned long long x = (unsigned long long)(hot.qmax_l[e] | (hot.qmax_r[e] << 16)) |
                                    ((unsigned long long)(hot.inv_ov[e] | (hot.inv_dist[e] << 8) | (hot.inv_nh[e] << 16)) << 32);
-      const ulonglong2 cur = __ldcg(reinterpret_cast<const ulonglong2*>(&a->first_inv));
-      extrema_to_global(a, hot.first_inv[e], x, cur.x, cur.y);
+      extrema_to_global(a, hot.first_inv[e], x, __ldcg(&a->kf), __ldcg(&a->ext));
       const unsigned c0v = hot.c0[e], c1v = hot.c1[e], c2v = hot.c2[e];
       if (c0v) atomicAdd(&a->c0, (unsigned long long)(c0v & 0x3FFFu) | ((unsigned long long)(c0v >> 14) << 32));
       if (c1v) atomicAdd(&a->c1, (unsigned long long)(c1v >> 14) | ((unsigned long long)(c1v & 0x3FFFu) << 32));
@@ -633,10 +637,10 @@ __global__ void __launch_bounds__(ACC_THREADS, 2) fused_accumulate_kernel(RecSrc
 
 __device__ __forceinline__ fc_junction junction_from_slot(const JSlot& a, unsigned long long first_idx) {
   fc_junction o;
-  o.chrom = (uint32_t)a.khi;
+  o.chrom = (uint32_t)(a.kf >> 39) & 0xFFFFFFu;
   o.start = (uint32_t)a.klo;
   o.end = (uint32_t)(a.klo >> 32);
-  o.sk = ((uint32_t)(a.khi >> 32) & 3u) | (a.sig << 16);
+  o.sk = ((uint32_t)(a.kf >> 37) & 3u) | (a.sig << 16);
   o.first_idx = first_idx;
   const uint32_t n_spanned = (uint32_t)a.c0, w8 = (uint32_t)(a.c0 >> 32);
   o.n_weighted = (double)w8 / 8.0;  // exact: every weight is k/8
@@ -681,7 +685,7 @@ __global__ void mark_first_kernel(unsigned int* __restrict__ ctr, unsigned int l
     unsigned long long p = 0;
     if (j < n_alloc) {
       const unsigned int slot = list[j];
-      p = ~slots[slot].first_inv - idx_lo;
+      p = FIRST_MAX - (slots[slot].kf & FIRST_MAX);  // (relative to idx_lo: the idx base of the accumulate pass)
       if (p < range) {
         real = true;
         flag[p] = slot + 1u;
@@ -762,14 +766,14 @@ __global__ void __launch_bounds__(FINISH_THREADS) finish_dense_kernel(int64_t ra
 
 // records in arbitrary order (peer-to-peer emit, explicit idx): compact in any order, sorted by first idx afterwards
 __global__ void finish_unordered_kernel(unsigned int* __restrict__ ctr, unsigned int lcap, const unsigned int* __restrict__ list,
-                                        JSlot* __restrict__ slots, fc_junction* __restrict__ out,
+                                        unsigned long long idx_base, JSlot* __restrict__ slots, fc_junction* __restrict__ out,
                                         uint64_t* __restrict__ order_key, uint32_t* __restrict__ order_val) {
   const unsigned int n_alloc = min(ctr[FC_N_ALLOC], lcap);
   for (unsigned int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_alloc; j += gridDim.x * blockDim.x) {
     JSlot* ap = slots + list[j];
     const JSlot a = *ap;
     const unsigned int pos = atomicAdd(&ctr[FC_N_JUNC], 1u);
-    const unsigned long long first_idx = ~a.first_inv;
+    const unsigned long long first_idx = idx_base + (FIRST_MAX - (a.kf & FIRST_MAX));
     out[pos] = junction_from_slot(a, first_idx);
     order_key[pos] = first_idx;
     order_val[pos] = pos;
@@ -1250,6 +1254,7 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st, const Re
   const bool dense = a.max_idx != ~0ull && a.idx_lo != ~0ull && a.max_idx > a.idx_lo &&
                      a.max_idx - a.idx_lo <= 4ull * (unsigned long long)ub + (1ull << 20);
   const int64_t range = dense ? (int64_t)(a.max_idx - a.idx_lo) : 0;
+  const unsigned long long idx_base = a.idx_lo != ~0ull ? a.idx_lo : 0ull;  // record positions are kept relative to it (JSlot.kf)
   const int64_t n_tiles = (range + RANK_TILE - 1) / RANK_TILE;
   a.f_dirty = true;  // until the finish kernel has run
   uint32_t* flag = nullptr;
@@ -1271,9 +1276,8 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st, const Re
     const int64_t chunks = (tiles + chunk_tiles - 1) / chunk_tiles;
     const unsigned grid = (unsigned)(chunks < ctas ? chunks : ctas);
     // the L2 prefetch of the set slots pays while the set fits L2 (-7 % at 1 M records) and costs 20 % when it does not
-    const char* ee = getenv("FC_ACC_EXP");
-    const int exp_flags = (ee ? atoi(ee) : 0) | ((size_t)scap * 16 > ((size_t)64 << 20) ? 64 : 0);
-    fused_accumulate_kernel<<<grid, ACC_THREADS, 0, st>>>(src, chunk_tiles, exp_flags, (JSlot*)a.f_keys.p, kcap - 1, (U128*)a.f_sets.p, scap - 1,
+    const int prefetch = (size_t)scap * 16 <= ((size_t)64 << 20) ? 1 : 0;
+    fused_accumulate_kernel<<<grid, ACC_THREADS, 0, st>>>(src, chunk_tiles, prefetch, idx_base, (JSlot*)a.f_keys.p, kcap - 1, (U128*)a.f_sets.p, scap - 1,
                                                           (unsigned int*)a.f_acc.p, lcap, ctr, (uint4*)flag, (range + 3) / 4, tile_count,
                                                           n_tiles);
   }
@@ -1311,7 +1315,7 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st, const Re
     kA = (uint64_t*)a.scratch[3].p;
     kB = (uint64_t*)a.scratch[4].p;
     vA = (uint32_t*)a.scratch[6].p;
-    finish_unordered_kernel<<<sweep_blocks, 256, 0, st>>>(ctr, lcap, (const unsigned int*)a.f_acc.p, (JSlot*)a.f_keys.p, tmpj, kA, vA);
+    finish_unordered_kernel<<<sweep_blocks, 256, 0, st>>>(ctr, lcap, (const unsigned int*)a.f_acc.p, idx_base, (JSlot*)a.f_keys.p, tmpj, kA, vA);
     FC_LAUNCH_CHECK(ctx);
   }
   // one round trip: exact record count, junction count, fallback conditions, peer-to-peer overflow
