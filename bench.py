@@ -329,9 +329,10 @@ def multi_gpu_parity(eng, sh, dist, dev, idx_base, total, m=100000):
         v = sh.d[k][:m]
         pad = torch.zeros((mx,) + tuple(v.shape[1:]), dtype=v.dtype, device=dev)
         pad[:m] = v
-        bufs = [torch.zeros_like(pad) for _ in range(world)] if rank == 0 else None
-        dist.gather(pad, bufs, dst=0)
-        parts[k] = bufs
+        raw = pad.view(torch.uint8).reshape(-1)  # (NCCL has no 16-bit integer type: ship bytes)
+        bufs = [torch.zeros_like(raw) for _ in range(world)] if rank == 0 else None
+        dist.gather(raw, bufs, dst=0)
+        parts[k] = [b.view(v.dtype).reshape(pad.shape) for b in bufs] if rank == 0 else None
     bases = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
     dist.all_gather(bases, torch.tensor([idx_base], dtype=torch.int64, device=dev))
     ok, n_junc = True, 0

@@ -990,6 +990,9 @@ int fc_agg_reserve_records(fc_ctx* ctx, int64_t extra, cudaStream_t st) {
 int fc_agg_emit_begin(fc_ctx* ctx, int64_t n, cudaStream_t st, fc::EmitArgs* e) {
   if (n >= (1ll << 32)) return fc_fail(ctx, FC_E_ARG, "batch too large");
   fc_agg& a = ctx->agg;
+  if (a.p2p_enabled)
+    return fc_fail(ctx, FC_E_STATE, "this context is connected to peers and reduces what they send: record with the peer emit (fc_scan_emit_batch, "
+                                    "fc_scan_emit_p2p, fc_agg_emit_p2p), or aggregate locally in another context");
   int rc = ensure_counters(ctx, st);
   if (rc) return rc;
   // upper bound of the record count so far (the exact count lives on the device)
@@ -1053,6 +1056,7 @@ extern "C" int fc_agg_append(fc_ctx* ctx, int64_t n, const fc_jrec* d_recs, void
   if (n == 0) return FC_OK;
   cudaStream_t st = (cudaStream_t)stream;
   fc_agg& a = ctx->agg;
+  if (a.p2p_enabled) return fc_fail(ctx, FC_E_STATE, "fc_agg_append on a context that is connected to peers");
   int rc = ensure_counters(ctx, st);
   if (rc) return rc;
   rc = sync_n_recs(ctx, st);

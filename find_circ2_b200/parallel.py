@@ -113,25 +113,29 @@ def stream_barrier(dist, dev, eng=None, stream=0, _cache={}):
 
 
 def gather_junctions(junctions: np.ndarray, dist, dev):
-    """ordered gather of every rank's junction table to rank 0 (rows sorted by first_idx = discovery order)"""
+    """ordered gather of every rank's junction table to rank 0: rows sorted by first_idx = discovery order, which is what
+    the junction names count (find_circ.py:684-686).  Tables travel device to device (NCCL on GPUs, gloo on CPU) and are
+    merged by one sort on rank 0's device; the other ranks get None."""
     import torch
 
     world = dist.get_world_size()
     if world == 1:
         return junctions
     rank = dist.get_rank()
-    raw = np.ascontiguousarray(junctions).view(np.uint8).reshape(-1)
-    n_local = torch.tensor([raw.size], dtype=torch.int64, device=dev)
+    row = junctions.dtype.itemsize  # 64
+    raw = torch.from_numpy(np.ascontiguousarray(junctions).view(np.uint8).reshape(-1).copy())
+    n_local = torch.tensor([len(junctions)], dtype=torch.int64, device=dev)
     sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
     dist.all_gather(sizes, n_local)
     sizes = [int(s.item()) for s in sizes]
     mx = max(max(sizes), 1)
-    buf = torch.zeros(mx, dtype=torch.uint8, device=dev)
-    buf[: raw.size] = torch.from_numpy(raw.copy()).to(dev)
-    bufs = [torch.zeros(mx, dtype=torch.uint8, device=dev) for _ in range(world)]
-    dist.all_gather(bufs, buf)
+    buf = torch.zeros(mx * row, dtype=torch.uint8, device=dev)
+    buf[: raw.numel()] = raw.to(dev, non_blocking=True)
+    bufs = [torch.zeros_like(buf) for _ in range(world)] if rank == 0 else None
+    dist.gather(buf, bufs, dst=0)
     if rank != 0:
         return None
-    parts = [b[:s].cpu().numpy().view(junctions.dtype) for b, s in zip(bufs, sizes)]
-    allj = np.concatenate(parts) if parts else junctions
-    return allj[np.argsort(allj["first_idx"], kind="stable")]
+    allj = torch.cat([b[: s * row] for b, s in zip(bufs, sizes)]).view(torch.int64).reshape(-1, row // 8)
+    # column 2 = first_idx (positions in the input stream, far below 2^63; equal values do not occur across ranks)
+    order = torch.sort(allj[:, 2], stable=True).indices
+    return allj[order].contiguous().view(torch.uint8).cpu().numpy().reshape(-1).view(junctions.dtype)
