@@ -490,59 +490,92 @@ def bench_config(args, cfg, dist, dev, primary, error_rate=None):
     ms_step = tot_ms / steps
     scan_step = scan_ms / steps
 
-    # ---- timed: end to end through host buffers (wall clock brackets synchronous calls; device idle otherwise)
+    # ---- timed: end to end through host buffers.  The batch sits in pinned host memory in the layout an ingest writes
+    # (fc_batch descriptors, read rows, q words, read hashes, the N planes as a sparse list); a step streams it through the
+    # slots of an fc_stream in chunks -- copy in, scan + record, compact results back, all overlapped -- then ends the
+    # step (N>1: barrier), reduces and fetches the junction table.
     e2e = None
-    if primary and not use_p2p:
+    if primary:
+        from find_circ2_b200.engine import HostStream
+
         def pin(t):
             h = torch.empty(t.shape, dtype=t.dtype).pin_memory()
             h.copy_(t)
-            return h, h.numpy()
-        cols = ("chrom", "a_start", "b_end", "l", "flags", "wden", "q_a", "q_b", "read_hash", "qname_hash")
-        pinned = {k: pin(d[k]) for k in cols}
-        pl = sh.planes.view(3, sh.n_words * n)
-        pl_pin = [pin(pl[k]) for k in range(3)]
-        h_hits_t = torch.empty(n * 16, dtype=torch.uint8).pin_memory()
-        h_hits = h_hits_t.numpy().view(HIT_DTYPE)
-        h2d = sum(v[1].nbytes for v in pinned.values()) + sum(v[1].nbytes for v in pl_pin)
-        parts = {"reset": 0.0, "batch": 0.0, "finalize": 0.0, "fetch": 0.0}
+            return h.numpy()
+        h_meta = pin(sh.meta)
+        h_rows = pin(sh.rows)
+        h_q = pin(sh.q)
+        h_rh = pin(d["read_hash"])
+        flagged = torch.nonzero((d["flags"] & 4) != 0)[:, 0]
+        h_rn_idx = flagged.to(torch.int32).cpu().numpy()
+        h_rn_rows = sh.rn_rows.view(n, sh.nw)[flagged].contiguous().cpu().numpy()
+        h_se = torch.empty(n * 2, dtype=torch.int32).pin_memory().numpy()
+        mw_total = (n + 31) // 32 + 8
+        h_hm = torch.empty(mw_total, dtype=torch.int32).pin_memory().numpy()
+        h_sm = torch.empty(mw_total, dtype=torch.int32).pin_memory().numpy()
+        cap = min(n, args.e2e_chunk) // 32 * 32 or n
+        n_slots = 3
+        hs = HostStream(eng, n_slots, cap, sh.nw)
+        chunks = []
+        for c0 in range(0, n, cap):
+            c1 = min(n, c0 + cap)
+            lo, hi = np.searchsorted(h_rn_idx, [c0, c1])
+            chunks.append((c0, c1, (h_rn_idx[lo:hi] - c0).astype(np.uint32), np.ascontiguousarray(h_rn_rows[lo:hi])))
+        h2d = h_meta.nbytes + h_rows.nbytes + h_q.nbytes + h_rh.nbytes + h_rn_idx.nbytes + h_rn_rows.nbytes
+        parts = {"reset": 0.0, "stream": 0.0, "finalize": 0.0, "fetch": 0.0}
 
         def step_e2e():
             tp = [time.perf_counter()]
             eng.agg_reset()
-            tp.append(time.perf_counter())
-            p = {k: v[1] for k, v in pinned.items()}
-            eng.batch_host_planes(n, p["chrom"], p["a_start"], p["b_end"], p["l"], p["flags"], pl_pin[0][1].view(np.uint32),
-                                  pl_pin[1][1].view(np.uint32), pl_pin[2][1].view(np.uint32), sh.n_words, n, sh.max_l, p["wden"],
-                                  p["q_a"], p["q_b"], p["read_hash"].view(np.uint64), p["qname_hash"].view(np.uint64), idx=None,
-                                  idx_base=idx_base, emit=True, out=h_hits)
-            tp.append(time.perf_counter())
             if world > 1:
+                eng.agg_set_idx_range(0, total)
+            tp.append(time.perf_counter())
+            for k, (c0, c1, rn_i, rn_r) in enumerate(chunks):
+                slot = k % n_slots
+                hs.wait(slot)
+                hs.submit(slot, c1 - c0, h_meta[4 * c0:], h_rows[2 * sh.nw * c0:], sh.nw, sh.max_l, q=h_q[c0:], read_hash=h_rh[c0:],
+                          idx_base=idx_base + c0, rn_idx=rn_i if len(rn_i) else None, rn_rows=rn_r if len(rn_i) else None, emit=True,
+                          out_mode=2, out_hits=h_se[2 * c0:], out_hit_mask=h_hm[c0 // 32:], out_strand_mask=h_sm[c0 // 32:])
+            hs.wait_all()
+            tp.append(time.perf_counter())
+            if use_p2p:
+                parallel.stream_barrier(dist, dev, eng, 0)
+            elif world > 1:
                 parallel.exchange_records(eng, dist, dev, 0, upper_bound=n)
             njj = eng.agg_finalize(0)
             tp.append(time.perf_counter())
             junc = eng.agg_fetch(njj, copy=False)  # read in place (pinned buffer of the engine)
             tp.append(time.perf_counter())
-            for k, name in enumerate(("reset", "batch", "finalize", "fetch")):
+            for k, name in enumerate(("reset", "stream", "finalize", "fetch")):
                 parts[name] += tp[k + 1] - tp[k]
             return njj, junc
 
         e2e_steps = max(3, steps // 2)
         for _ in range(2):
-            step_e2e()
+            nj2, junc = step_e2e()
+        # the streamed path gives the junction table of the device-resident path, and the compact hits are the hits
+        e2e_ok = int(nj2) == int(nj)
+        hits_dev = sh.hits.view(n, 4)
+        got_mask = torch.from_numpy(h_hm[: (n + 31) // 32].copy()).to(dev)
+        want_hit = (hits_dev[:, 2] & 0xFFFF) != 0
+        bits = ((got_mask[torch.arange(n, device=dev) // 32] >> (torch.arange(n, device=dev) % 32)) & 1).bool()
+        e2e_ok = e2e_ok and bool(torch.equal(bits, want_hit)) and bool(torch.equal(torch.from_numpy(h_se.copy()).to(dev).view(n, 2)[want_hit], hits_dev[:, :2][want_hit]))
+        del got_mask, bits, want_hit
         barrier()
         for k in parts:
             parts[k] = 0.0
         e2e_s = 0.0
         for _ in range(e2e_steps):
             do_flush()
-            torch.cuda.synchronize()
+            barrier()
             t0 = time.perf_counter()
             nj2, junc = step_e2e()
             e2e_s += time.perf_counter() - t0
         barrier()
-        e2e = {"s_step": e2e_s / e2e_steps, "h2d": int(h2d), "d2h": n * 16 + int(nj2) * 64,
-               "calls_ms": {k: round(v / e2e_steps * 1e3, 3) for k, v in parts.items()}}
-        del pinned, pl_pin, h_hits_t
+        hs.close()
+        e2e = {"s_step": e2e_s / e2e_steps, "h2d": int(h2d), "d2h": n * 8 + 8 * ((n + 31) // 32) + int(nj2) * 64, "ok": e2e_ok,
+               "chunk_rows": cap, "slots": n_slots, "calls_ms": {k: round(v / e2e_steps * 1e3, 3) for k, v in parts.items()}}
+        del h_meta, h_rows, h_q, h_rh, h_se, h_hm, h_sm
     if sampler is not None:
         sampler.stop_flag = True
         sampler.join(timeout=2)
@@ -599,7 +632,8 @@ def bench_config(args, cfg, dist, dev, primary, error_rate=None):
     if e2e:
         res["e2e"] = {"value": total_pairs / e2e_step, "unit": "pairs/s", "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                       "ms_per_step": e2e_step * 1e3, "calls_ms": e2e["calls_ms"],
-                      "call": "fc_batch_host_planes + fc_agg_finalize + fc_agg_fetch (pinned host SoA with bit-plane reads, as csrc/ingest.cu emits them)"}
+                      "equals_device_path": e2e["ok"], "chunk_rows": e2e["chunk_rows"], "slots": e2e["slots"],
+                      "call": "fc_stream_submit / fc_stream_wait over %d slots + fc_agg_finalize + fc_agg_fetch: pinned host batch in fc_batch layout (16-B descriptors, read rows, q, read hash; N planes as a sparse list), compact hits (start, end, 2 bit masks) back" % e2e["slots"]}
     if sampler is not None:
         res["clocks"] = sampler.summary()
     if ingest:
@@ -672,6 +706,7 @@ def main():
     ap.add_argument("--config", default="3", choices=["2", "3", "4", "5"], help="BASELINE.json configs[1..4]")
     ap.add_argument("--pairs", type=int, default=0, help="override the pair count of the primary config")
     ap.add_argument("--cpu-sample", type=int, default=20000)
+    ap.add_argument("--e2e-chunk", type=int, default=4 << 20, help="rows per streamed host batch of the e2e path")
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: partition + NCCL all-to-all instead of peer-memory emit")
     ap.add_argument("--no-extra", action="store_true", help="N=1: skip the lines of the other configs")
     ap.add_argument("--check-all", action="store_true", help="run the parity check on the other configs too")

@@ -53,6 +53,14 @@ class Batch(C.Structure):
                 ("max_l", C.c_int32)]
 
 
+class HostBatch(C.Structure):
+    """fc_host_batch: one batch in fc_batch layout in (pinned) host memory, for fc_stream_submit"""
+    _fields_ = [("n", C.c_int64), ("meta", C.c_void_p), ("reads", C.c_void_p), ("rn_idx", C.c_void_p), ("rn_rows", C.c_void_p),
+                ("n_rn", C.c_int64), ("q", C.c_void_p), ("read_hash", C.c_void_p), ("qname_hash", C.c_void_p), ("idx", C.c_void_p),
+                ("idx_base", C.c_uint64), ("n_words", C.c_int32), ("max_l", C.c_int32), ("emit", C.c_int32), ("out_mode", C.c_int32),
+                ("out_hits", C.c_void_p), ("out_hit_mask", C.c_void_p), ("out_strand_mask", C.c_void_p)]
+
+
 # numpy views of the C structs
 HIT_DTYPE = np.dtype([("start", "<i4"), ("end", "<i4"), ("w2", "<u4"), ("w3", "<u4")])
 JREC_DTYPE = np.dtype(
@@ -94,6 +102,11 @@ SYMBOLS = [
     ("fc_batch_pack", C.c_int, [_P, C.POINTER(Pairs), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     ("fc_scan_batch", C.c_int, [_P, C.POINTER(ScanParams), _P, _P, _P]),
     ("fc_scan_emit_batch", C.c_int, [_P, C.POINTER(ScanParams), _P, _P, _P, _P, _P, C.c_uint64, _P, _P]),
+    ("fc_stream_create", C.c_int, [_P, C.c_int32, C.c_int64, C.c_int32, C.POINTER(_P)]),
+    ("fc_stream_destroy", None, [_P]),
+    ("fc_stream_submit", C.c_int, [_P, C.c_int32, C.POINTER(ScanParams), _P]),
+    ("fc_stream_wait", C.c_int, [_P, C.c_int32]),
+    ("fc_stream_query", C.c_int, [_P, C.c_int32]),
     ("fc_scan_ties", C.c_int, [_P, C.POINTER(ScanParams), C.POINTER(Pairs), _P, _P, _P, _P]),
     ("fc_scan_host", C.c_int, [_P, C.POINTER(ScanParams), C.c_int64, _P, _P, _P, _P, _P, _P, C.c_int32, _P]),
     ("fc_batch_host", C.c_int, [_P, C.POINTER(ScanParams), C.c_int64, _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P,

@@ -1337,6 +1337,8 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st, const Re
                    a.p2p_timeout_s);
   if (a.p2p_enabled && h[4])
     return fc_fail(ctx, FC_E_NOMEM, "peer-to-peer record buffer overflow (%llu records dropped): raise the capacity", h[4]);
+  if (h[6])
+    return fc_fail(ctx, FC_E_ARG, "%llu records came without a read-name hash and without fragment fields in their descriptors", h[6]);
   const unsigned int n_other = (unsigned int)(h[8] >> 32), n_overflow = (unsigned int)h[9];
   const int64_t nj = (int64_t)(h[9] >> 32);
   if (n_overflow) {  // ids ran out, or a record lies outside a declared idx range: its accumulator was not consumed
@@ -1368,6 +1370,8 @@ static int p2p_slice_counts(fc_ctx* ctx, cudaStream_t st, unsigned long long* ou
                    a.p2p_timeout_s);
   if (blk[4])
     return fc_fail(ctx, FC_E_NOMEM, "peer-to-peer record buffer overflow (%llu records of this rank dropped): raise the capacity", blk[4]);
+  if (blk[6])
+    return fc_fail(ctx, FC_E_ARG, "%llu records came without a read-name hash and without fragment fields in their descriptors", blk[6]);
   const unsigned long long* h = blk + fc::FC_CNT_SLICE + 8 * parity;
   *total = 0;
   for (int r = 0; r < 8; ++r) {
@@ -1444,6 +1448,11 @@ extern "C" int64_t fc_agg_finalize(fc_ctx* ctx, void* stream) {
     }
     int rc = sync_n_recs(ctx, st);
     if (rc) return rc;
+    unsigned long long no_name = 0;
+    FC_CUDA(ctx, cudaMemcpyAsync(&no_name, (unsigned long long*)a.counters.p + 6, sizeof(no_name), cudaMemcpyDeviceToHost, st));
+    FC_CUDA(ctx, cudaStreamSynchronize(st));
+    if (no_name)
+      return fc_fail(ctx, FC_E_ARG, "%llu records came without a read-name hash and without fragment fields in their descriptors", no_name);
   }
   int rc = FC_OK;
   const int64_t n = a.n_recs;

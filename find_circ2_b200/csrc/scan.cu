@@ -4,6 +4,8 @@
 // Replaces JunctionSpan.find_breakpoints (/root/reference/find_circ.py:854-974); see scan_core.cuh.
 #include <stdlib.h>
 
+#include <vector>
+
 #include "fc_internal.cuh"
 
 namespace {
@@ -101,6 +103,7 @@ struct Payload {  // what becomes of an accepted pair (emit_core.cuh)
   const uint64_t* idx;
   unsigned long long* n_recs;
   fc_jrec* recs;
+  unsigned long long* no_name;  // counts records that have neither a name hash nor fragment fields (fc_agg_finalize then fails)
 };
 
 // the read planes of pair i: one vector load per pair when the row is 8 or 16 bytes, two or four for 32 / 64 bytes
@@ -202,9 +205,17 @@ __global__ void __launch_bounds__(BS, MB) scan_kernel(fc::GenomeView g, fc::Scan
     fc_jrec r;
     if (accept) {
       const uint32_t q = e.q[i];
+      // a batch without name hashes: the rows of a fragment share the stream position of its first row as their name
+      // (read names are unique per fragment on this path, so that is as good as a hash of the name)
+      const int64_t first_row = i - (int64_t)(fr != 15u ? back : 0u);
+      const uint64_t qh = e.qname_hash ? e.qname_hash[i]
+                                       : fc_mix64((e.idx ? e.idx[first_row < 0 ? 0 : first_row] : e.idx_base + (uint64_t)first_row) ^ 0x6a09e667f3bcc909ULL);
       r = fc::make_record_from(h.start, h.end, h.w2, h.w3, m.w & 0xFFFFFFu, (m.z >> 24) & 7u, m.w >> 24, (int16_t)(q & 0xFFFFu),
-                               (int16_t)(q >> 16), e.read_hash[i], e.qname_hash[i], e.idx ? e.idx[i] : e.idx_base + (uint64_t)i);
-      if (known) r.sk |= FC_SK_NAME_KNOWN | (dup ? FC_SK_NAME_DUP : 0u);
+                               (int16_t)(q >> 16), e.read_hash[i], qh, e.idx ? e.idx[i] : e.idx_base + (uint64_t)i);
+      if (known)
+        r.sk |= FC_SK_NAME_KNOWN | (dup ? FC_SK_NAME_DUP : 0u);
+      else if (!e.qname_hash && fr == 15u)
+        atomicAdd(e.no_name, 1ull);
     }
     if constexpr (MODE == 1)
       fc::emit_block<BS>(accept, r, e.n_recs, e.recs);
@@ -392,7 +403,7 @@ static int scan_emit_soa(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs* p
   if (rc) return rc;
   fc::EmitArgs ea{d_wden, d_q_a, d_q_b, d_read_hash, d_qname_hash, idx_base, d_idx, nullptr, nullptr};
   if ((rc = fc_agg_emit_begin(ctx, pr->n, st, &ea))) return rc;
-  Payload e{q, d_read_hash, d_qname_hash, idx_base, d_idx, ea.n_recs, ea.recs};
+  Payload e{q, d_read_hash, d_qname_hash, idx_base, d_idx, ea.n_recs, ea.recs, nullptr};
   if ((rc = scan_launch(ctx, p, b, pr->max_l, d_out, 1, e, st))) return rc;
   fc_agg_emit_end(ctx, pr->n, idx_base, d_idx != nullptr);
   return FC_OK;
@@ -426,7 +437,7 @@ extern "C" int fc_scan_emit_p2p(fc_ctx* ctx, const fc_scan_params* p, const fc_p
   BatchView b;
   const uint32_t* q = nullptr;
   if ((rc = pack_soa(ctx, pr, d_wden, d_q_a, d_q_b, nullptr, st, 0, pr->n, &b, &q))) return rc;
-  Payload e{q, d_read_hash, d_qname_hash, idx_base, nullptr, nullptr, nullptr};
+  Payload e{q, d_read_hash, d_qname_hash, idx_base, nullptr, nullptr, nullptr, nullptr};
   if ((rc = scan_launch(ctx, p, b, pr->max_l, d_out, 2, e, st, &pv, overflow))) return rc;
   fc_agg_p2p_end(ctx, idx_base, pr->n);
   return FC_OK;
@@ -471,20 +482,18 @@ extern "C" int fc_scan_batch(fc_ctx* ctx, const fc_scan_params* p, const fc_batc
   return scan_launch(ctx, p, v, b->max_l, d_out, 0, Payload{}, (cudaStream_t)stream);
 }
 
-extern "C" int fc_scan_emit_batch(fc_ctx* ctx, const fc_scan_params* p, const fc_batch* b, fc_hit* d_out, const uint32_t* d_q,
-                                  const uint64_t* d_read_hash, const uint64_t* d_qname_hash, uint64_t idx_base, const uint64_t* d_idx,
-                                  void* stream) {
-  int rc = check_batch(ctx, p, b);
-  if (rc) return rc;
-  if (!d_out || !d_q || !d_read_hash || !d_qname_hash) return FC_E_ARG;
-  cudaStream_t st = (cudaStream_t)stream;
+// scan + record a packed batch: into this context's aggregator, or -- connected to peers -- into the owners' buffers
+static int scan_emit_batch(fc_ctx* ctx, const fc_scan_params* p, const fc_batch* b, fc_hit* d_out, const uint32_t* d_q,
+                           const uint64_t* d_read_hash, const uint64_t* d_qname_hash, uint64_t idx_base, const uint64_t* d_idx,
+                           cudaStream_t st) {
+  int rc;
   BatchView v{(const uint4*)b->d_meta, b->d_reads, b->d_rn, b->n, b->n_words};
   if (ctx->agg.p2p_enabled) {  // connected to peers: every record goes to the rank that owns its key
     fc::P2PView pv;
     unsigned long long* overflow = nullptr;
     if ((rc = fc_agg_p2p_begin(ctx, &pv, &overflow))) return rc;
     if (b->n > 0) {
-      Payload e{d_q, d_read_hash, d_qname_hash, idx_base, d_idx, nullptr, nullptr};
+      Payload e{d_q, d_read_hash, d_qname_hash, idx_base, d_idx, nullptr, nullptr, overflow + 2};
       if ((rc = scan_launch(ctx, p, v, b->max_l, d_out, 2, e, st, &pv, overflow))) return rc;
     }
     fc_agg_p2p_end(ctx, idx_base, b->n);
@@ -493,10 +502,19 @@ extern "C" int fc_scan_emit_batch(fc_ctx* ctx, const fc_scan_params* p, const fc
   if (b->n == 0) return FC_OK;
   fc::EmitArgs ea{};
   if ((rc = fc_agg_emit_begin(ctx, b->n, st, &ea))) return rc;
-  Payload e{d_q, d_read_hash, d_qname_hash, idx_base, d_idx, ea.n_recs, ea.recs};
+  Payload e{d_q, d_read_hash, d_qname_hash, idx_base, d_idx, ea.n_recs, ea.recs, ea.n_recs + 6};
   if ((rc = scan_launch(ctx, p, v, b->max_l, d_out, 1, e, st))) return rc;
   fc_agg_emit_end(ctx, b->n, idx_base, d_idx != nullptr);
   return FC_OK;
+}
+
+extern "C" int fc_scan_emit_batch(fc_ctx* ctx, const fc_scan_params* p, const fc_batch* b, fc_hit* d_out, const uint32_t* d_q,
+                                  const uint64_t* d_read_hash, const uint64_t* d_qname_hash, uint64_t idx_base, const uint64_t* d_idx,
+                                  void* stream) {
+  int rc = check_batch(ctx, p, b);
+  if (rc) return rc;
+  if (!d_out || !d_q || !d_read_hash) return FC_E_ARG;
+  return scan_emit_batch(ctx, p, b, d_out, d_q, d_read_hash, d_qname_hash, idx_base, d_idx, (cudaStream_t)stream);
 }
 
 extern "C" int fc_scan_ties(fc_ctx* ctx, const fc_scan_params* p, const fc_pairs* pr, const fc_hit* d_hits,
@@ -823,4 +841,175 @@ extern "C" int fc_batch_host_planes(fc_ctx* ctx, const fc_scan_params* p, int64_
   ctx->last_has_payload = payload;
   ctx->last_has_idx = h_idx != nullptr;
   return FC_OK;
+}
+
+// ---------------------------------------------------------------- streamed host batches (fc_stream)
+// The reference's main loop reads, scans and records one fragment after the other (find_circ.py:1535-1574); here the host
+// fills batch k+1 while batch k is copied, scanned, recorded and its hits travel back -- every slot has its own stream.
+struct fc_stream_slot {
+  cudaStream_t st = nullptr;
+  cudaEvent_t done = nullptr;
+  bool busy = false;
+  fc_dbuf buf[12];  // meta, reads, q, read_hash, qname_hash, idx, rn (dense), rn_idx, rn_rows, hits, compact, masks
+};
+struct fc_stream {
+  fc_ctx* ctx = nullptr;
+  int64_t cap = 0;
+  int32_t max_words = 0;
+  std::vector<fc_stream_slot> slots;
+};
+
+namespace {
+__global__ void scatter_rn_kernel(int64_t n_rn, const uint32_t* __restrict__ rows_idx, const uint32_t* __restrict__ rows, int nw,
+                                  uint32_t* __restrict__ dense) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_rn * nw) return;
+  const int64_t r = t / nw;
+  const int k = (int)(t - r * nw);
+  dense[(int64_t)rows_idx[r] * nw + k] = rows[t];
+}
+
+// fc_hit[n] -> (start, end) pairs + one bit per pair "has a breakpoint" + one bit per pair "minus strand"
+__global__ void compact_hits_kernel(int64_t n, const fc_hit* __restrict__ hits, int2* __restrict__ se, uint32_t* __restrict__ hit_mask,
+                                    uint32_t* __restrict__ strand_mask) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool hit = false, minus = false;
+  if (i < n) {
+    const uint4 h = reinterpret_cast<const uint4*>(hits)[i];
+    hit = (h.z & 0xFFFFu) != 0u;
+    minus = hit && (h.w & 1u);
+    se[i] = make_int2((int)h.x, (int)h.y);
+  }
+  const unsigned hm = __ballot_sync(0xffffffffu, hit), sm = __ballot_sync(0xffffffffu, minus);
+  if ((threadIdx.x & 31) == 0 && i < n) {
+    hit_mask[i >> 5] = hm;
+    strand_mask[i >> 5] = sm;
+  }
+}
+}  // namespace
+
+extern "C" int fc_stream_create(fc_ctx* ctx, int32_t n_slots, int64_t cap_rows, int32_t max_words, fc_stream** out) {
+  if (!ctx || !out || n_slots < 1 || n_slots > 16 || cap_rows < 1 || max_words < 1) return FC_E_ARG;
+  *out = nullptr;
+  FC_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = fc_agg_reserve_records(ctx, 0, ctx->own_stream);  // the counters exist before any slot's stream touches them
+  if (rc) return rc;
+  FC_CUDA(ctx, cudaStreamSynchronize(ctx->own_stream));
+  fc_stream* fs = new fc_stream();
+  fs->ctx = ctx;
+  fs->cap = cap_rows;
+  fs->max_words = max_words;
+  fs->slots.resize(n_slots);
+  const size_t C = (size_t)cap_rows, W = (size_t)max_words;
+  const size_t sizes[12] = {16 * C, 8 * C * W, 4 * C, 8 * C, 8 * C, 8 * C, 4 * C * W, 4 * C, 4 * C * W, 16 * C, 8 * C, 8 * ((C + 31) / 32) + 64};
+  for (auto& sl : fs->slots) {
+    cudaError_t e = cudaStreamCreateWithFlags(&sl.st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming);
+    for (int k = 0; k < 12 && e == cudaSuccess; ++k) e = sl.buf[k].reserve(sizes[k], sl.st, false, 0);
+    if (e != cudaSuccess) {
+      fc_stream_destroy(fs);
+      return fc_fail(ctx, FC_E_CUDA, "fc_stream_create: %s", cudaGetErrorString(e));
+    }
+  }
+  *out = fs;
+  return FC_OK;
+}
+
+extern "C" void fc_stream_destroy(fc_stream* fs) {
+  if (!fs) return;
+  cudaSetDevice(fs->ctx->device);
+  for (auto& sl : fs->slots) {
+    if (sl.st) cudaStreamSynchronize(sl.st);
+    for (auto& b : sl.buf) b.release();
+    if (sl.done) cudaEventDestroy(sl.done);
+    if (sl.st) cudaStreamDestroy(sl.st);
+  }
+  delete fs;
+}
+
+extern "C" int fc_stream_submit(fc_stream* fs, int32_t slot, const fc_scan_params* p, const fc_host_batch* hb) {
+  if (!fs || !hb || !p || slot < 0 || slot >= (int32_t)fs->slots.size()) return FC_E_ARG;
+  fc_ctx* ctx = fs->ctx;
+  fc_stream_slot& sl = fs->slots[slot];
+  if (sl.busy) return fc_fail(ctx, FC_E_STATE, "fc_stream_submit: slot %d is in flight (fc_stream_wait first)", slot);
+  const int64_t n = hb->n;
+  if (n < 0 || n > fs->cap || hb->n_words < 1 || hb->n_words > fs->max_words || hb->n_rn < 0 || hb->n_rn > n)
+    return fc_fail(ctx, FC_E_ARG, "fc_stream_submit: batch of %lld rows x %d words does not fit the slots (%lld x %d)", (long long)n, hb->n_words,
+                   (long long)fs->cap, fs->max_words);
+  if (n == 0) return FC_OK;
+  if (!hb->meta || !hb->reads || (hb->emit && (!hb->q || !hb->read_hash)) || (hb->n_rn && (!hb->rn_idx || !hb->rn_rows))) return FC_E_ARG;
+  if (hb->out_mode == 1 && !hb->out_hits) return FC_E_ARG;
+  if (hb->out_mode == 2 && (!hb->out_hits || !hb->out_hit_mask || !hb->out_strand_mask)) return FC_E_ARG;
+  FC_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = sl.st;
+  const size_t N = (size_t)n, W = (size_t)hb->n_words;
+  auto dp = [&](int k) { return sl.buf[k].p; };
+  FC_CUDA(ctx, cudaMemcpyAsync(dp(0), hb->meta, 16 * N, cudaMemcpyHostToDevice, st));
+  FC_CUDA(ctx, cudaMemcpyAsync(dp(1), hb->reads, 8 * N * W, cudaMemcpyHostToDevice, st));
+  if (hb->emit) {
+    FC_CUDA(ctx, cudaMemcpyAsync(dp(2), hb->q, 4 * N, cudaMemcpyHostToDevice, st));
+    FC_CUDA(ctx, cudaMemcpyAsync(dp(3), hb->read_hash, 8 * N, cudaMemcpyHostToDevice, st));
+    if (hb->qname_hash) FC_CUDA(ctx, cudaMemcpyAsync(dp(4), hb->qname_hash, 8 * N, cudaMemcpyHostToDevice, st));
+    if (hb->idx) FC_CUDA(ctx, cudaMemcpyAsync(dp(5), hb->idx, 8 * N, cudaMemcpyHostToDevice, st));
+  }
+  if (hb->n_rn) {  // the N planes of the few reads that have any: a sparse list, scattered into the dense rows the scan reads
+    FC_CUDA(ctx, cudaMemcpyAsync(dp(7), hb->rn_idx, 4 * (size_t)hb->n_rn, cudaMemcpyHostToDevice, st));
+    FC_CUDA(ctx, cudaMemcpyAsync(dp(8), hb->rn_rows, 4 * (size_t)hb->n_rn * W, cudaMemcpyHostToDevice, st));
+    const int64_t t = hb->n_rn * (int64_t)W;
+    scatter_rn_kernel<<<(unsigned)((t + 255) / 256), 256, 0, st>>>(hb->n_rn, (const uint32_t*)dp(7), (const uint32_t*)dp(8), (int)W,
+                                                                 (uint32_t*)dp(6));
+    FC_LAUNCH_CHECK(ctx);
+  }
+  fc_batch b{n, dp(0), (const uint32_t*)dp(1), (const uint32_t*)dp(6), hb->n_words, hb->max_l};
+  int rc = check_batch(ctx, p, &b);
+  if (rc) return rc;
+  fc_hit* d_hits = (fc_hit*)dp(9);
+  if (hb->emit) {
+    fc_agg& a = ctx->agg;
+    if (!a.p2p_enabled && (size_t)(a.n_recs + n) * sizeof(fc_jrec) > a.recs.cap) {
+      // the record buffer has to grow: nothing may be in flight on the other slots' streams while it moves
+      FC_CUDA(ctx, cudaDeviceSynchronize());
+      const int64_t extra = a.n_recs + n > 2 * n ? a.n_recs + n : 2 * n;  // (at least doubling)
+      if ((rc = fc_agg_reserve_records(ctx, extra, st))) return rc;
+    }
+    rc = scan_emit_batch(ctx, p, &b, d_hits, (const uint32_t*)dp(2), (const uint64_t*)dp(3), hb->qname_hash ? (const uint64_t*)dp(4) : nullptr,
+                         hb->idx_base, hb->idx ? (const uint64_t*)dp(5) : nullptr, st);
+  } else {
+    BatchView v{(const uint4*)b.d_meta, b.d_reads, b.d_rn, b.n, b.n_words};
+    rc = scan_launch(ctx, p, v, b.max_l, d_hits, 0, Payload{}, st);
+  }
+  if (rc) return rc;
+  if (hb->out_mode == 1) {
+    FC_CUDA(ctx, cudaMemcpyAsync(hb->out_hits, d_hits, 16 * N, cudaMemcpyDeviceToHost, st));
+  } else if (hb->out_mode == 2) {
+    uint32_t* masks = (uint32_t*)dp(11);
+    const size_t mw = (N + 31) / 32;
+    compact_hits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, d_hits, (int2*)dp(10), masks, masks + mw);
+    FC_LAUNCH_CHECK(ctx);
+    FC_CUDA(ctx, cudaMemcpyAsync(hb->out_hits, dp(10), 8 * N, cudaMemcpyDeviceToHost, st));
+    FC_CUDA(ctx, cudaMemcpyAsync(hb->out_hit_mask, masks, 4 * mw, cudaMemcpyDeviceToHost, st));
+    FC_CUDA(ctx, cudaMemcpyAsync(hb->out_strand_mask, masks + mw, 4 * mw, cudaMemcpyDeviceToHost, st));
+  }
+  FC_CUDA(ctx, cudaEventRecord(sl.done, st));
+  sl.busy = true;
+  return FC_OK;
+}
+
+extern "C" int fc_stream_wait(fc_stream* fs, int32_t slot) {
+  if (!fs || slot < 0 || slot >= (int32_t)fs->slots.size()) return FC_E_ARG;
+  fc_stream_slot& sl = fs->slots[slot];
+  if (!sl.busy) return FC_OK;
+  FC_CUDA(fs->ctx, cudaEventSynchronize(sl.done));
+  sl.busy = false;
+  return FC_OK;
+}
+
+extern "C" int fc_stream_query(fc_stream* fs, int32_t slot) {
+  if (!fs || slot < 0 || slot >= (int32_t)fs->slots.size()) return FC_E_ARG;
+  fc_stream_slot& sl = fs->slots[slot];
+  if (!sl.busy) return 1;
+  const cudaError_t e = cudaEventQuery(sl.done);
+  if (e == cudaSuccess) return 1;
+  if (e == cudaErrorNotReady) return 0;
+  return fc_fail(fs->ctx, FC_E_CUDA, "fc_stream_query: %s", cudaGetErrorString(e));
 }

@@ -16,13 +16,51 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import HIT_DTYPE, JREC_DTYPE, JUNCTION_DTYPE, Batch, FindCircError, Pairs, ScanParams, ptr
+from ._lib import HIT_DTYPE, JREC_DTYPE, JUNCTION_DTYPE, Batch, FindCircError, HostBatch, Pairs, ScanParams, ptr
 
 SIG_LETTERS = "ACGTN"
 
 
 def decode_signal(code: int) -> str:
     return "".join(SIG_LETTERS[(code >> (3 * k)) & 7] for k in range(4))
+
+
+class HostStream:
+    """fc_stream: batches in fc_batch layout go from (pinned) host arrays through copy, scan, record and back without the host
+    waiting in between; the caller fills batch k+1 while batch k is in flight (find_circ.py:1535-1574 as a pipeline)"""
+
+    def __init__(self, eng: "Engine", n_slots: int, cap_rows: int, max_words: int):
+        self.eng = eng
+        self.n_slots = n_slots
+        h = C.c_void_p()
+        eng._check(eng.lib.fc_stream_create(eng.h, n_slots, int(cap_rows), int(max_words), C.byref(h)))
+        self.h = h
+        self._keep = [None] * n_slots  # the arrays of a batch stay alive while it is in flight
+
+    def submit(self, slot: int, n: int, meta, reads, n_words: int, max_l: int, q=None, read_hash=None, qname_hash=None, idx=None,
+               idx_base: int = 0, rn_idx=None, rn_rows=None, emit: bool = True, out_mode: int = 0, out_hits=None, out_hit_mask=None,
+               out_strand_mask=None):
+        hb = HostBatch(int(n), ptr(meta), ptr(reads), ptr(rn_idx), ptr(rn_rows), 0 if rn_idx is None else len(rn_idx), ptr(q),
+                       ptr(read_hash), ptr(qname_hash), ptr(idx), int(idx_base), int(n_words), int(max_l), int(bool(emit)), int(out_mode),
+                       ptr(out_hits), ptr(out_hit_mask), ptr(out_strand_mask))
+        self._keep[slot] = (meta, reads, q, read_hash, qname_hash, idx, rn_idx, rn_rows, out_hits, out_hit_mask, out_strand_mask)
+        self.eng._check(self.eng.lib.fc_stream_submit(self.h, slot, C.byref(self.eng.params), C.byref(hb)))
+
+    def wait(self, slot: int):
+        self.eng._check(self.eng.lib.fc_stream_wait(self.h, slot))
+        self._keep[slot] = None
+
+    def wait_all(self):
+        for k in range(self.n_slots):
+            self.wait(k)
+
+    def query(self, slot: int) -> bool:
+        return bool(self.eng._check(self.eng.lib.fc_stream_query(self.h, slot)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.eng.lib.fc_stream_destroy(self.h)
+            self.h = None
 
 
 class Engine:

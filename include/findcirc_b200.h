@@ -90,7 +90,9 @@ typedef struct fc_pairs {
  *   w1  low 32 bits of gb = genome coordinate of B_flank[0]  (fc_genome_chrom_offset(chrom) + b_end - (l + 2))
  *   w2  bits 0-5 ga >> 32, 6-11 gb >> 32, 12-23 l, 24-26 FC_PF_BACKSPLICE / MINUS / READ_N, 27 FC_META_INVALID (a window
  *       lies outside its chromosome, the chromosome is unknown or l < 0: no hit; ga, gb, l are then 0),
- *       28-29 / 30-31 rows of the same fragment before / after this one in the batch (3,3 = unknown)
+ *       28-29 / 30-31 rows of the same fragment before / after this one (3,3 = unknown).  The rows of a fragment are
+ *       neighbours; they lie in one batch, or -- batches that continue one another with idx = idx_base + row -- the batch
+ *       boundary that cuts the fragment falls on a multiple of 32 rows
  *   w3  bits 0-23 chromosome id, 24-31 weight denominator (find_circ.py:1084)
  * and the internal read part as one row per pair: n_words words of the lo plane, then n_words words of the hi plane
  * (d_reads), n_words words of the N plane (d_rn; read only for pairs flagged FC_PF_READ_N, may be NULL when none is).
@@ -253,6 +255,49 @@ int fc_batch_host_planes(fc_ctx* ctx, const fc_scan_params* p, int64_t n, const 
                          const uint32_t* h_rhi, const uint32_t* h_rn, int32_t n_words, int64_t plane_stride, int32_t max_l,
                          const uint8_t* h_wden, const int16_t* h_q_a, const int16_t* h_q_b, const uint64_t* h_read_hash,
                          const uint64_t* h_qname_hash, const uint64_t* h_idx, uint64_t idx_base, int32_t emit, fc_hit* h_out);
+
+/* ---- streamed host batches: the main loop of the reference (find_circ.py:1535-1574: read, scan, record, one fragment at a
+ * time) as a pipeline of batches.  A stream owns n_slots device-side slots (own CUDA stream each) for batches of up to
+ * cap_rows rows x max_words read words; fc_stream_submit queues, without waiting, the copy of one batch in fc_batch layout
+ * from HOST memory (pinned -- fc_pinned_alloc -- for the copies to overlap), the scan, the recording of the pairs with a
+ * breakpoint when emit != 0 (into this context, or into the owner ranks' buffers when the context is connected to peers)
+ * and the copy of the results back; fc_stream_wait blocks until the slot's results are in host memory.  The caller owns all
+ * host arrays between submit and wait and fills batch k+1 meanwhile.  Every slot must be waited for before fc_agg_finalize.
+ *   meta, reads          fc_batch descriptors and read rows (n_words words per plane)
+ *   rn_idx, rn_rows      the N planes as a sparse list: row numbers (ascending or not) and n_words words per listed row, for
+ *                        the rows flagged FC_PF_READ_N
+ *   q, read_hash         emit: q_a | q_b << 16 and the strand-invariant read hash per row
+ *   qname_hash           emit: may be NULL when every row carries fragment fields (descriptor bits 28-31 != 3,3) and a read name
+ *                        occurs in one fragment only: the fragment's first row then stands in for the name
+ *   idx                  emit: explicit stream position per row, NULL = idx_base + row
+ *   out_mode             0 nothing comes back; 1 out_hits = fc_hit[n]; 2 out_hits = int32 (start, end) per row, out_hit_mask /
+ *                        out_strand_mask = one bit per row (row i: word i / 32, bit i % 32): has a breakpoint / '-' strand */
+typedef struct fc_stream fc_stream;
+typedef struct fc_host_batch {
+  int64_t n;
+  const void* meta;
+  const uint32_t* reads;
+  const uint32_t* rn_idx;
+  const uint32_t* rn_rows;
+  int64_t n_rn;
+  const uint32_t* q;
+  const uint64_t* read_hash;
+  const uint64_t* qname_hash;
+  const uint64_t* idx;
+  uint64_t idx_base;
+  int32_t n_words;
+  int32_t max_l;
+  int32_t emit;
+  int32_t out_mode;
+  void* out_hits;
+  uint32_t* out_hit_mask;
+  uint32_t* out_strand_mask;
+} fc_host_batch;
+int fc_stream_create(fc_ctx* ctx, int32_t n_slots, int64_t cap_rows, int32_t max_words, fc_stream** out);
+void fc_stream_destroy(fc_stream* s);
+int fc_stream_submit(fc_stream* s, int32_t slot, const fc_scan_params* p, const fc_host_batch* batch);
+int fc_stream_wait(fc_stream* s, int32_t slot);
+int fc_stream_query(fc_stream* s, int32_t slot); /* 1: the slot is free / its results have landed, 0: in flight, < 0: error */
 
 /* Two-step batches: after fc_batch_host(..., emit = 0) the host inspects the hits and decides which pairs are
  * recorded (find_circ.py:1319-1329: the linear spans of a fragment count only when its back-splices resolved to at most
