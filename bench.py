@@ -667,6 +667,9 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from find_circ2_b200 import parallel
+
+    numa = parallel.bind_to_gpu_numa(local) if world > 1 else {}
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     cfgs = W.configs()
@@ -681,6 +684,8 @@ def run_gpu(args):
         if k in r:
             line[k] = r[k]
     line.setdefault("e2e", None)
+    if numa:
+        line["detail"]["host_binding"] = numa
     if world == 1 and not args.no_extra:
         others = {}
         for name in [c for c in ("2", "4", "5") if c != args.config]:

@@ -33,6 +33,43 @@ def _buffer(tag, nbytes, dev):
     return t
 
 
+def bind_to_gpu_numa(device_index: int) -> dict:
+    """pin this process (and, by first touch, the pinned buffers it allocates afterwards) to the NUMA node its GPU hangs
+    off: with one process per GPU the host-to-device copies of all ranks otherwise funnel through node 0's memory.
+    Returns what was done ({} when the topology cannot be read)."""
+    import os
+
+    try:
+        import torch
+
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id  # attribute exists in torch >= 2.4
+    except Exception:
+        bus = None
+    try:
+        if bus is None:
+            import subprocess
+
+            bus = subprocess.run(["nvidia-smi", "-i", str(device_index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                 capture_output=True, text=True, timeout=10).stdout.strip()
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:  # nvidia-smi prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return {}
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {}
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except Exception:
+        return {}
+
+
 def exchange_records(eng, dist, dev, stream=0, upper_bound=None):
     """hash-partition this rank's junction records and swap them with the other ranks; afterwards the engine's
     aggregator holds exactly the records whose keys this rank owns.  Returns (sent_bytes, received_bytes).
