@@ -71,6 +71,8 @@ def build_parser() -> optparse.OptionParser:
     a("", "--no-multi", dest="multi_events", default=True, action="store_false", help="do not write multi_events.tsv rows")
     a("", "--batch-pairs", dest="batch_pairs", type=int, default=1 << 18, help="anchor pairs per GPU batch (default 262144)")
     a("", "--device", dest="device", type=int, default=0, help="CUDA device (default 0)")
+    a("", "--gpus", dest="gpus", type=int, default=1,
+      help="GPUs of this node to use (default 1): the run is re-launched as one process per GPU; needs a SAM text file as input")
     a("", "--python-ingest", dest="native", default=True, action="store_false",
       help="decode SAM text in python instead of the native (C++) ingest")
     return p
@@ -175,6 +177,152 @@ def _stream_header(fh):
                 if x.startswith(b"SN:"):
                     names.append(x[3:].decode("latin-1"))
     return names, _Prefixed(first, fh)
+
+
+class _Range(object):
+    """bytes [start, end) of a binary file as a stream"""
+
+    def __init__(self, fh, start: int, end: int):
+        self.fh, self.left = fh, max(0, end - start)
+        fh.seek(start)
+
+    def read(self, n: int) -> bytes:
+        if self.left <= 0:
+            return b""
+        data = self.fh.read(min(n, self.left))
+        self.left -= len(data)
+        return data
+
+
+def _fragment_boundary(fh, pos: int, body_start: int, size: int) -> int:
+    """where the part of the stream that starts nominally at byte `pos` really starts: the first line at or after pos whose
+    read name differs from the name of the line before it (a fragment = consecutive records of one name,
+    find_circ.py:1450-1486).  Every rank applies the same rule to its start and to its end."""
+    if pos <= body_start:
+        return body_start
+    if pos >= size:
+        return size
+    fh.seek(pos - 1)
+    fh.readline()  # finish the line that pos falls into (or the newline right before pos)
+    first = fh.readline()
+    if not first:
+        return size
+    name = first.split(b"\t", 1)[0]
+    while True:
+        at = fh.tell()
+        line = fh.readline()
+        if not line:
+            return size
+        if line.split(b"\t", 1)[0] != name:
+            return at
+
+
+def sam_ranges(path: str, world: int):
+    """(header names, [(start, end)] * world, body start): contiguous byte ranges of a SAM text file cut on fragment boundaries"""
+    size = os.path.getsize(path)
+    with open(path, "rb") as fh:
+        names = []
+        while True:
+            at = fh.tell()
+            line = fh.readline()
+            if not line or not line.startswith(b"@"):
+                body = at
+                break
+            if line.startswith(b"@SQ"):
+                for x in line.rstrip(b"\r\n").split(b"\t")[1:]:
+                    if x.startswith(b"SN:"):
+                        names.append(x[3:].decode("latin-1"))
+        cuts = [_fragment_boundary(fh, body + (size - body) * r // world, body, size) for r in range(world)] + [size]
+    for r in range(1, world + 1):
+        cuts[r] = max(cuts[r], cuts[r - 1])
+    return names, [(cuts[r], cuts[r + 1]) for r in range(world)], body
+
+
+def _merge_host_state(run: Run, parts):
+    """rank 0: fold the host-side companions of the other ranks' parts of the stream into `run` (parts in rank order =
+    stream order): counters, per-junction flags, spliced reads, multi-event rows"""
+    from collections import defaultdict
+
+    run.N = defaultdict(float)
+    run.info = {}
+    run.reads_out, run.native_reads, run.multi_out, run.test_out = [], [], [], []
+    run.n_fragments = run.n_pairs_scanned = 0
+    run.t_scan = 0.0
+    for p in parts:
+        for k, v in p["N"].items():
+            run.N[k] += v
+        for key, (flags, read_flags) in p["info"].items():
+            inf = run._info(key)
+            for f, c in flags.items():
+                inf.flags[f] += c
+            for name, fl in read_flags.items():
+                inf.read_flags[name] |= fl
+        run.reads_out.extend(p["reads_out"])
+        run.native_reads.extend(p["native_reads"])
+        run.multi_out.extend(p["multi_out"])
+        run.test_out.extend(p["test_out"])
+        run.n_fragments += p["n_fragments"]
+        run.n_pairs_scanned += p["n_pairs_scanned"]
+        run.t_scan = max(run.t_scan, p["t_scan"])
+
+
+def run_distributed(opt: Options, path, dist, torch_dev, engine=None):
+    """the whole run on world_size GPUs of one node (one process each, launched by torchrun or by --gpus N): every rank takes
+    a contiguous part of the SAM text file, cut where the read name changes; stream positions stay global (rank r numbers
+    its fragments from r * stride), so junction names (find_circ.py:684-686) and every per-junction column come out as in
+    a single-process run; junction records travel to the rank that owns their key, junction rows and the host-side
+    companions are gathered to rank 0, which alone returns the outputs (the other ranks return None)."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if not path or path == "-" or not path.endswith("sam"):
+        raise ValueError("a multi-GPU run needs a SAM text FILE (every rank reads its own byte range of it)")
+    if not native_ok(opt, path):
+        raise ValueError("a multi-GPU run uses the native ingest: --all-hits, --noop, --test and --python-ingest are single-GPU options")
+    names, ranges, body = sam_ranges(path, world)
+    stride = max(1, max(e - s for s, e in ranges) // 16 + 1)  # more than the fragments any rank can hold (a SAM line is > 16 bytes)
+    run = Run(opt, names, engine)
+    try:
+        t0 = time.perf_counter()
+        start, end = ranges[rank]
+        run.cur_seq = run.n_fragments = 0
+        with open(path, "rb") as fh:
+            run.process_native(_Range(fh, start, end), first_fragment=rank * stride, at_stream_start=(start == body))
+        t1 = time.perf_counter()
+        run.finalize(dist, torch_dev)
+        part = {"N": dict(run.N), "info": {k: (dict(v.flags), {n: set(f) for n, f in v.read_flags.items()}) for k, v in run.info.items()},
+                "reads_out": run.reads_out, "native_reads": run.native_reads, "multi_out": run.multi_out, "test_out": run.test_out,
+                "n_fragments": run.n_fragments, "n_pairs_scanned": run.n_pairs_scanned, "t_scan": run.t_scan}
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object(part, parts, dst=0)
+        if rank != 0:
+            return None
+        _merge_host_state(run, parts)
+        return {
+            "circ": run.bed_text(0), "lin": run.bed_text(1), "reads": run.reads_text(), "multi": run.multi_text(), "test": run.test_text(),
+            "counters": run.counters_text(), "n_fragments": run.n_fragments, "n_pairs_scanned": run.n_pairs_scanned,
+            "seconds_ingest_and_scan": t1 - t0, "seconds_gpu_calls": run.t_scan, "seconds_total": time.perf_counter() - t0,
+        }
+    finally:
+        run.close()
+
+
+def distributed_context(device_ok: bool = True):
+    """(dist, torch device) when this process is one rank of a torchrun launch (RANK / WORLD_SIZE > 1 in the environment)"""
+    if int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+        return None, None
+    import torch
+    import torch.distributed as dist
+
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if device_ok and torch.cuda.is_available():
+        torch.cuda.set_device(local)
+        dev = torch.device("cuda", local)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=dev)
+    else:
+        dev = torch.device("cpu")
+        if not dist.is_initialized():
+            dist.init_process_group("gloo")
+    return dist, dev
 
 
 def run_to_strings(opt: Options, path=None, engine=None, native=None):
@@ -337,6 +485,33 @@ def main(argv=None) -> int:
     if not opt.genome:
         print("need to specify either model system database (-S) or genome FASTA file (-G).")
         return 1
+    if raw.gpus > 1 and int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+        # one process per GPU: hand the same command line to torchrun (rank 0 writes the outputs)
+        import socket
+        import subprocess
+
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        script = os.path.abspath(sys.argv[0]) if sys.argv and os.path.exists(sys.argv[0]) else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "find_circ.py")
+        return subprocess.call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(raw.gpus), "--master-addr",
+                                "127.0.0.1", "--master-port", str(port), script] + list(argv))
+    dist, torch_dev = distributed_context()
+    rank = dist.get_rank() if dist is not None else 0
+    if dist is not None:
+        from . import parallel
+
+        opt.device = torch_dev.index if torch_dev.type == "cuda" else 0
+        if torch_dev.type == "cuda":
+            parallel.bind_to_gpu_numa(opt.device)
+    if rank != 0:
+        # the other ranks scan their part of the input and hand everything to rank 0
+        try:
+            run_distributed(opt, args[0] if args else None, dist, torch_dev)
+            return 0
+        except Exception:
+            sys.stderr.write(traceback.format_exc())
+            return 1
     if not os.path.isdir(opt.output):
         os.makedirs(opt.output)
     fmt = "%(asctime)-20s\t%(levelname)s\t%(name)s\t%(message)s"
@@ -358,7 +533,7 @@ def main(argv=None) -> int:
     log.info("reading from %s" % (path or "stdin"))
     t0 = time.time()
     try:
-        out = run_to_strings(opt, path)
+        out = run_distributed(opt, path, dist, torch_dev) if dist is not None else run_to_strings(opt, path)
     except KeyboardInterrupt:
         logging.warning("KeyboardInterrupt by user")
         return 1

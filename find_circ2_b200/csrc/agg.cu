@@ -280,7 +280,7 @@ struct RecSrc {
 struct alignas(64) JSlot {
   // sector 0: everything an ordinary record looks at or changes (maxima: all-zero = nothing yet = identity of max)
   unsigned long long klo;  // start | end << 32
-  unsigned long long kf;   // KEY_OCC | chrom (24 bits) << 39 | (strand, kind) << 37 | first: FIRST_MAX - (smallest idx - idx base)
+  unsigned long long kf;   // KEY_OCC | chrom (20 bits) << 43 | (strand, kind) << 41 | first: FIRST_MAX - (smallest idx - idx base)
   unsigned long long c0;   // n_spanned | 8 * n_weighted << 32
   unsigned long long ext;  // (q_left + 32768) | (q_right + 32768) << 16 | (255 - ov) << 32 | (255 - dist) << 40 | (65535 - n_hits) << 48
   // sector 1: what few records touch
@@ -293,7 +293,8 @@ struct alignas(64) JSlot {
 static_assert(sizeof(JSlot) == 64 && offsetof(JSlot, c0) == 16 && offsetof(JSlot, c1) == 32, "JSlot layout");
 
 constexpr unsigned long long KEY_OCC = 1ull << 63;
-constexpr int FIRST_BITS = 37;  // record positions relative to the call's idx base: 1.4e11
+constexpr int FIRST_BITS = 41;  // record positions relative to the call's idx base: 2.2e12 (a native ingest numbers 64 per fragment)
+constexpr int CHROM_BITS = 20;  // chromosome numbers (a call with more falls back to the sort-based path)
 constexpr unsigned long long FIRST_MAX = (1ull << FIRST_BITS) - 1ull;
 constexpr long long FUSED_MAX_RECORDS = 1ll << 28;  // keeps 8 * n_spanned and the slot numbers inside their fields
 constexpr uint32_t SK_NAME_KNOWN = FC_SK_NAME_KNOWN, SK_NAME_DUP = FC_SK_NAME_DUP;  // the emitter already knows whether the fragment is new to the junction
@@ -497,8 +498,9 @@ __global__ void __launch_bounds__(ACC_THREADS, 2) fused_accumulate_kernel(RecSrc
       const unsigned long long klo = (unsigned long long)r0.y | ((unsigned long long)r0.z << 32);
       const unsigned long long rel = idx - idx_base;
       // (a position or chromosome number beyond the slot's fields: the call falls back to the sort-based path)
-      if ((rel >> FIRST_BITS) != 0ull || (r0.x >> 24) != 0u) atomicAdd(&ctr[FC_N_OTHER], 1u);
-      const unsigned long long kid = KEY_OCC | ((unsigned long long)(r0.x & 0xFFFFFFu) << 39) | ((unsigned long long)(sk & 3u) << 37);
+      if ((rel >> FIRST_BITS) != 0ull || (r0.x >> CHROM_BITS) != 0u) atomicAdd(&ctr[FC_N_OTHER], 1u);
+      const unsigned long long kid = KEY_OCC | ((unsigned long long)(r0.x & ((1u << CHROM_BITS) - 1u)) << (FIRST_BITS + 2)) |
+                                     ((unsigned long long)(sk & 3u) << FIRST_BITS);
       const unsigned long long kf = kid | (FIRST_MAX - (rel & FIRST_MAX));
       unsigned long long slot = fc_mix64(klo ^ fc_mix64(kid)) & kmask, cur_kf = 0ull, cur_x = 0ull;
       bool fresh = false;
@@ -637,10 +639,10 @@ __global__ void __launch_bounds__(ACC_THREADS, 2) fused_accumulate_kernel(RecSrc
 
 __device__ __forceinline__ fc_junction junction_from_slot(const JSlot& a, unsigned long long first_idx) {
   fc_junction o;
-  o.chrom = (uint32_t)(a.kf >> 39) & 0xFFFFFFu;
+  o.chrom = (uint32_t)(a.kf >> (FIRST_BITS + 2)) & ((1u << CHROM_BITS) - 1u);
   o.start = (uint32_t)a.klo;
   o.end = (uint32_t)(a.klo >> 32);
-  o.sk = ((uint32_t)(a.kf >> 37) & 3u) | (a.sig << 16);
+  o.sk = ((uint32_t)(a.kf >> FIRST_BITS) & 3u) | (a.sig << 16);
   o.first_idx = first_idx;
   const uint32_t n_spanned = (uint32_t)a.c0, w8 = (uint32_t)(a.c0 >> 32);
   o.n_weighted = (double)w8 / 8.0;  // exact: every weight is k/8

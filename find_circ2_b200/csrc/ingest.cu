@@ -188,6 +188,16 @@ extern "C" fc_ingest* fc_ingest_create(const fc_ingest_params* p, int32_t n_name
 
 extern "C" void fc_ingest_destroy(fc_ingest* h) { delete h; }
 
+// a parser that starts in the middle of the input stream (one rank of a multi-GPU run): ordinal of its first fragment,
+// and whether its first record is the first record of the whole stream (which the reference never checks for the
+// "unmapped" flag, find_circ.py:1462-1463)
+extern "C" int fc_ingest_set_position(fc_ingest* h, int64_t first_fragment, int32_t at_stream_start) {
+  if (!h || first_fragment < 0) return FC_E_ARG;
+  h->g.frag_seq = first_fragment;
+  h->g.first_record = at_stream_start != 0;
+  return FC_OK;
+}
+
 extern "C" int64_t fc_ingest_parse(fc_ingest* h, const char* text, int64_t nbytes, int32_t final, fc_ingest_out* o) {
   if (!h || !text || !o || nbytes < 0) return FC_E_ARG;
   Ingest& g = h->g;
@@ -345,6 +355,13 @@ extern "C" int64_t fc_ingest_parse(fc_ingest* h, const char* text, int64_t nbyte
     }
     g.parse_line(text, line_off, line_len, r);
     if (!have_frag) {
+      if (!g.first_record && r.ok && (r.flag & 0x4)) {
+        // an unmapped record where a chunk (or a rank's part of the stream) begins: counted and skipped like any other;
+        // only the very first record of the stream escapes that check (find_circ.py:1462-1467)
+        o->counters[C_UNMAPPED] += 1;
+        consumed = pos;
+        continue;
+      }
       frag.clear();
       frag.push_back(r);
       frag_start = line_off;

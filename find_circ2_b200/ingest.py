@@ -34,7 +34,8 @@ COUNTER_NAMES = ("total_mates", "unmapped_reads", "unspliced_mates", "seg_too_sh
 
 
 class NativeIngest(object):
-    def __init__(self, asize, margin, min_uniq_qual, nolinear, names, tid2gid, cap=1 << 18, n_words=8, cap_complex=1 << 16):
+    def __init__(self, asize, margin, min_uniq_qual, nolinear, names, tid2gid, cap=1 << 18, n_words=8, cap_complex=1 << 16,
+                 first_fragment=0, at_stream_start=True):
         self.lib = _lib.load()
         p = IngestParams(asize, margin, min_uniq_qual, int(bool(nolinear)))
         c_names = (C.c_char_p * len(names))(*[n.encode() for n in names])
@@ -42,6 +43,9 @@ class NativeIngest(object):
         self.h = self.lib.fc_ingest_create(C.byref(p), len(names), c_names, t2g.ctypes.data)
         if not self.h:
             raise RuntimeError("fc_ingest_create failed")
+        if first_fragment or not at_stream_start:
+            if self.lib.fc_ingest_set_position(self.h, int(first_fragment), int(bool(at_stream_start))) != 0:
+                raise RuntimeError("fc_ingest_set_position failed")
         self.cap, self.n_words = cap, n_words
         a = self.a = {}
         for name, dt in (("chrom", np.int32), ("a_start", np.int32), ("b_end", np.int32), ("l", np.int32), ("flags", np.uint8),

@@ -567,9 +567,10 @@ class Run(object):
             self.add_fragment(mate1, mate2)
         self.flush()
 
-    def process_native(self, fh, chunk_bytes: int = 64 << 20):
+    def process_native(self, fh, chunk_bytes: int = 64 << 20, first_fragment: int = 0, at_stream_start: bool = True):
         """SAM text (binary file object, header included) through the native ingest (csrc/ingest.cu); fragments it does
-        not handle go through add_fragment().  Same results as process(), an order of magnitude less host time."""
+        not handle go through add_fragment().  Same results as process(), an order of magnitude less host time.
+        first_fragment / at_stream_start: this stream is a part of a larger one (one rank of a multi-GPU run)."""
         from .ingest import COUNTER_NAMES, NativeIngest
         from .samio import _parse_sam_line
 
@@ -579,7 +580,7 @@ class Run(object):
         tid2gid = [self.eng._chrom_ids.get(n, -1) for n in self.sam_chroms]
         name2tid = {n: i for i, n in enumerate(self.sam_chroms)}
         ing = NativeIngest(opt.asize, opt.margin, opt.min_uniq_qual, opt.nolinear, self.sam_chroms, tid2gid,
-                           cap=max(1024, opt.batch_pairs))
+                           cap=max(1024, opt.batch_pairs), first_fragment=first_fragment, at_stream_start=at_stream_start)
         self.explicit_idx = True
         a, o = ing.a, ing.out
         carry = b""

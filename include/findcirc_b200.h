@@ -409,6 +409,10 @@ typedef struct fc_ingest_out {
 } fc_ingest_out;
 fc_ingest* fc_ingest_create(const fc_ingest_params* p, int32_t n_names, const char* const* names, const int32_t* tid2gid);
 void fc_ingest_destroy(fc_ingest* h);
+/* a parser that starts inside the stream (one rank of a multi-GPU run takes a byte range of the file, cut where the read
+ * name changes): ordinal of its first fragment; at_stream_start = 0 unless its first record is the first of the whole
+ * stream -- the only record the reference never checks for the "unmapped" flag (find_circ.py:1462-1463) */
+int fc_ingest_set_position(fc_ingest* h, int64_t first_fragment, int32_t at_stream_start);
 /* parses complete fragments out of `text`; returns the number of bytes consumed (the caller re-submits the rest together
  * with the next chunk; final != 0 flushes the last fragment) or a negative error code */
 int64_t fc_ingest_parse(fc_ingest* h, const char* text, int64_t nbytes, int32_t final, fc_ingest_out* out);

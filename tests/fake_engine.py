@@ -122,6 +122,26 @@ class FakeEngine:
         for r in recs:
             self.recs.append(r.copy())
 
+    # ---- multi-rank exchange (find_circ2_b200.parallel.exchange_records): partition by a key hash, replace by what arrives
+    def agg_n_records(self):
+        return len(self.recs)
+
+    def agg_partition(self, world, send, stream=0):
+        import torch
+
+        recs = np.array(self.recs, dtype=JREC_DTYPE) if self.recs else np.zeros(0, dtype=JREC_DTYPE)
+        k = (recs["chrom"].astype(np.uint64) * np.uint64(1000003) + recs["start"].astype(np.int64).astype(np.uint64) * np.uint64(10007)
+             + recs["end"].astype(np.int64).astype(np.uint64) * np.uint64(101) + (recs["sk"] & 3).astype(np.uint64))
+        d = (k % np.uint64(world)).astype(np.int64)
+        order = np.argsort(d, kind="stable")
+        raw = np.ascontiguousarray(recs[order]).view(np.uint8).reshape(-1)
+        send[: raw.size] = torch.from_numpy(raw.copy())
+        return np.bincount(d, minlength=world).astype(np.int64)
+
+    def agg_replace_device(self, n, recv, stream=0):
+        arr = recv[: n * 48].numpy().view(JREC_DTYPE).copy()
+        self.recs = [arr[i] for i in range(n)]
+
     def agg_finalize(self, stream=0):
         acc = {}
         for r in sorted(self.recs, key=lambda x: int(x["idx"])):  # stream order, whatever the arrival order was

@@ -108,6 +108,23 @@ def main():
         assert tb.tobytes() == tc.tobytes(), "NCCL path differs from the single-GPU aggregation"
         print("multigpu_check OK: world=%d, %d junctions, p2p=%s" % (world, len(tc), ok))
     dist.barrier()
+    # the whole drop-in on `world` GPUs against runs of the reference itself (tests/golden)
+    from conftest import golden_cases
+    from find_circ2_b200 import cli
+
+    done = 0
+    for case_dir, ref_dir, argv in golden_cases():
+        if os.path.basename(ref_dir) not in ("ref_default", "ref_a20", "ref_uniq0_half_nobridge") or "--stdout" in argv:
+            continue
+        opt = cli.parse_args(["-G", os.path.join(case_dir, "genome.fa")] + argv)[0]
+        opt.device, opt.batch_pairs = local, 257
+        out = cli.run_distributed(opt, os.path.join(case_dir, "input.sam"), dist, dev)
+        if rank == 0:
+            H.compare_outputs(out["circ"], out["lin"], out["reads"], out["multi"], out["counters"], ref_dir, argv)
+            done += 1
+        dist.barrier()
+    if rank == 0:
+        print("multigpu_check OK: drop-in on %d GPUs reproduces %d reference runs" % (world, done))
     dist.destroy_process_group()
     e.close()
 
