@@ -897,8 +897,8 @@ constexpr int FC_BARRIER_TIMEOUT_WORD = 5;
 
 int ensure_counters(fc_ctx* ctx, cudaStream_t st) {
   if (!ctx->agg.counters.p) {
-    FC_CUDA(ctx, ctx->agg.counters.reserve(64 * sizeof(unsigned long long), st, false, 0));
-    FC_CUDA(ctx, cudaMemsetAsync(ctx->agg.counters.p, 0, 64 * sizeof(unsigned long long), st));
+    FC_CUDA(ctx, ctx->agg.counters.reserve(fc::FC_CNT_WORDS * sizeof(unsigned long long), st, false, 0));
+    FC_CUDA(ctx, cudaMemsetAsync(ctx->agg.counters.p, 0, fc::FC_CNT_WORDS * sizeof(unsigned long long), st));
   }
   if (!ctx->agg.h_pinned) FC_CUDA(ctx, cudaHostAlloc((void**)&ctx->agg.h_pinned, 64 * sizeof(unsigned long long), cudaHostAllocMapped));
   return FC_OK;
@@ -1782,9 +1782,9 @@ extern "C" int fc_agg_emit_p2p(fc_ctx* ctx, int64_t n, const fc_hit* d_hits, con
 // wait == 0 (contexts of one process on one device, launched one after the other): publish and arrive only.
 __global__ void p2p_barrier_kernel(P2PView pv, unsigned long long target, long long timeout_cycles, int wait) {
   if ((int)threadIdx.x < pv.world) {
-    const unsigned long long sent = pv.cnt[pv.rank][fc::FC_CNT_SRC + threadIdx.x];
+    const unsigned long long sent = pv.cnt[pv.rank][fc::FC_CNT_SRC + fc::FC_CNT_SRC_STRIDE * threadIdx.x];
     pv.cnt[threadIdx.x][fc::FC_CNT_SLICE + 8 * pv.parity + pv.rank] = sent;
-    pv.cnt[pv.rank][fc::FC_CNT_SRC + threadIdx.x] = 0ull;  // the next step starts from empty slices
+    pv.cnt[pv.rank][fc::FC_CNT_SRC + fc::FC_CNT_SRC_STRIDE * threadIdx.x] = 0ull;  // the next step starts from empty slices
   }
   __threadfence_system();  // this rank's record stores and counts are ordered before its arrival
   __syncwarp();

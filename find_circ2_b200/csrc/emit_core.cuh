@@ -36,10 +36,22 @@ struct EmitArgs {
   fc_jrec* recs;               // record buffer of the context
 };
 
+// ---- bulk asynchronous copies shared memory -> global memory (TMA, UBLKCP): one instruction moves a CTA's whole run of
+// records, to local HBM or to a peer over NVLink, instead of hundreds of 16-byte stores through the LSU
+__device__ __forceinline__ void smem_writes_before_bulk() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {  // 16-byte aligned, bytes % 16 == 0
+  const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_and_release() {  // the issuing thread may leave once the source has been read
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // Called by EVERY thread of a CTA of BS threads (BS a multiple of 32, at most 1024).  `accept` threads hand over their
 // record.  The CTA claims its slots with one atomic on the record counter, groups the records in shared memory and
-// writes them as one run of consecutive 16-byte stores; the buffer is therefore NOT in stream order -- every consumer
-// orders by fc_jrec.idx where order matters.
+// writes them as ONE bulk copy; the buffer is therefore NOT in stream order -- every consumer orders by fc_jrec.idx
+// where order matters.
 template <int BS>
 __device__ __forceinline__ void emit_block(bool accept, const fc_jrec& r, unsigned long long* n_recs, fc_jrec* recs) {
   __shared__ unsigned int s_warp[BS / 32];
@@ -68,10 +80,13 @@ __device__ __forceinline__ void emit_block(bool accept, const fc_jrec& r, unsign
     stage[0] = src[0];
     stage[1] = src[1];
     stage[2] = src[2];
+    smem_writes_before_bulk();
   }
   __syncthreads();
-  uint4* out = reinterpret_cast<uint4*>(recs + s_base);
-  for (unsigned int w = threadIdx.x; w < s_total * 3u; w += BS) out[w] = s_rec[w];
+  if (threadIdx.x == 0 && s_total) {
+    bulk_store(recs + s_base, s_rec, s_total * (unsigned int)sizeof(fc_jrec));
+    bulk_commit_and_release();
+  }
 }
 
 // ---- the same towards the rank that owns the junction key (fused emit + exchange over peer memory) --------------------
@@ -88,7 +103,9 @@ struct P2PView {
   int rank;
   int parity;                   // 0 / 1: which half of the buffers this step uses
 };
-constexpr int FC_CNT_SRC = 16;    // counter words [16, 24): records this rank has sent to destination d in this step
+constexpr int FC_CNT_WORDS = 256;      // 64-bit words of a context's counter block
+constexpr int FC_CNT_SRC = 64;         // word FC_CNT_SRC + FC_CNT_SRC_STRIDE * d: records this rank has sent to destination d in this step;
+constexpr int FC_CNT_SRC_STRIDE = 16;  // one 128-byte line each: every CTA of the scan bumps all of them, a shared sector would serialise in one L2 slice
 constexpr int FC_CNT_SLICE = 40;  // counter words [40, 56): [parity][source] records received from source in the step
 
 // one Hit.add() call as a record (find_circ.py:526-582): hit words of the scan + the payload of the pair
@@ -148,7 +165,7 @@ __device__ __forceinline__ void emit_p2p_block(bool accept, const fc_jrec& r, co
   }
   __syncthreads();
   if ((int)threadIdx.x < pv.world && s_cnt[threadIdx.x])
-    s_base[threadIdx.x] = atomicAdd(pv.cnt[pv.rank] + FC_CNT_SRC + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
+    s_base[threadIdx.x] = atomicAdd(pv.cnt[pv.rank] + FC_CNT_SRC + FC_CNT_SRC_STRIDE * threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
   if (threadIdx.x == 0) {
     unsigned int acc = 0;
     for (int d = 0; d < 8; ++d) {
@@ -164,20 +181,21 @@ __device__ __forceinline__ void emit_p2p_block(bool accept, const fc_jrec& r, co
     dst[0] = src[0];
     dst[1] = src[1];
     dst[2] = src[2];
+    smem_writes_before_bulk();
   }
   __syncthreads();
-  const unsigned int words = s_off[8] * 3u;
-  const unsigned long long slice0 = (unsigned long long)(pv.parity * pv.world + pv.rank) * pv.slice_cap;
-  for (unsigned int w = threadIdx.x; w < words; w += BS) {
-    const unsigned int rec = w / 3u, part = w - rec * 3u;
-    int d = 0;
-#pragma unroll
-    for (int k = 1; k < 8; ++k) d += (k < pv.world && rec >= s_off[k]) ? 1 : 0;
-    const unsigned long long pos = s_base[d] + (rec - s_off[d]);
-    if (pos < pv.slice_cap) {
-      reinterpret_cast<uint4*>(pv.recs[d] + slice0 + pos)[part] = s_rec[w];
-    } else if (part == 0u) {
-      atomicAdd(overflow, 1ull);
+  // one bulk copy per destination: the run goes over NVLink (or into local HBM) in full-size packets and no thread of
+  // the CTA spends load/store slots on it
+  if ((int)threadIdx.x < pv.world && s_cnt[threadIdx.x]) {
+    const int d = (int)threadIdx.x;
+    const unsigned long long base = s_base[d];
+    unsigned long long room = base < pv.slice_cap ? pv.slice_cap - base : 0ull;
+    const unsigned int cnt = s_cnt[d] < room ? s_cnt[d] : (unsigned int)room;
+    if (cnt < s_cnt[d]) atomicAdd(overflow, (unsigned long long)(s_cnt[d] - cnt));
+    if (cnt) {
+      const unsigned long long slice0 = (unsigned long long)(pv.parity * pv.world + pv.rank) * pv.slice_cap;
+      bulk_store(pv.recs[d] + slice0 + base, s_rec + (size_t)s_off[d] * 3, cnt * (unsigned int)sizeof(fc_jrec));
+      bulk_commit_and_release();
     }
   }
 }

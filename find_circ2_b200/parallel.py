@@ -42,7 +42,8 @@ def bind_to_gpu_numa(device_index: int) -> dict:
     try:
         import torch
 
-        bus = torch.cuda.get_device_properties(device_index).pci_bus_id  # attribute exists in torch >= 2.4
+        pr = torch.cuda.get_device_properties(device_index)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
     except Exception:
         bus = None
     try:
