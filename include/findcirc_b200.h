@@ -437,6 +437,16 @@ int64_t fc_text_gather(const char* buf, int64_t n, const int64_t* off, const int
 int64_t fc_fastq_format(const char* blob, int64_t n, const int32_t* len, const int32_t* name_idx, const char* names,
                         const int64_t* name_off, const int32_t* name_len, char* out, int64_t out_cap, int64_t* rec_off);
 
+/* ------------------------------------------------------------------ keyed merge of junction tables
+ * The arithmetic of merge_bed.py (merge_bed.py:88-142; column map :117-130): the n rows of ALL input tables (host arrays; row
+ * order = file after file, as merge_bed.py reads them) are grouped by (chrom, start, end, strand) on the device; groups are
+ * numbered in key order.  Per group: h_support = bit mask of the inputs (h_src, < 64) that have the key (merge_bed.py:80-86),
+ * and every numeric column c (h_vals[c * n + row]) reduced over the group's rows in input order with h_op[c] = 0 sum, 1 max,
+ * 2 min into h_out[c * n_groups + group].  h_group_of_row tells the host which rows to join for the text columns. */
+int fc_merge_tables(fc_ctx* ctx, int64_t n, const uint32_t* h_chrom, const int32_t* h_start, const int32_t* h_end,
+                    const uint8_t* h_strand, const uint8_t* h_src, int32_t n_cols, const double* h_vals, const uint8_t* h_op,
+                    int64_t* out_n_groups, uint32_t* h_group_of_row, uint64_t* h_support, double* h_out);
+
 /* ------------------------------------------------------------------ utilities */
 void* fc_pinned_alloc(int64_t bytes);
 void fc_pinned_free(void* p);

@@ -1,0 +1,1 @@
+in0_liver.bed in1_brain.bed in2_hek.bed
