@@ -119,6 +119,7 @@ SYMBOLS = [
     ("fc_ingest_create", _P, [_P, C.c_int32, _P, _P]),
     ("fc_ingest_destroy", None, [_P]),
     ("fc_ingest_set_position", C.c_int, [_P, C.c_int64, C.c_int32]),
+    ("fc_ingest_position", C.c_int64, [_P]),
     ("fc_ingest_parse", C.c_int64, [_P, _P, C.c_int64, C.c_int32, _P]),
     ("fc_agg_reset", C.c_int, [_P]),
     ("fc_agg_emit", C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_uint64, _P]),

@@ -191,6 +191,8 @@ extern "C" void fc_ingest_destroy(fc_ingest* h) { delete h; }
 // a parser that starts in the middle of the input stream (one rank of a multi-GPU run): ordinal of its first fragment,
 // and whether its first record is the first record of the whole stream (which the reference never checks for the
 // "unmapped" flag, find_circ.py:1462-1463)
+extern "C" int64_t fc_ingest_position(fc_ingest* h) { return h ? h->g.frag_seq : -1; }  // ordinal the next fragment will get
+
 extern "C" int fc_ingest_set_position(fc_ingest* h, int64_t first_fragment, int32_t at_stream_start) {
   if (!h || first_fragment < 0) return FC_E_ARG;
   h->g.frag_seq = first_fragment;

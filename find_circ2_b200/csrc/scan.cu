@@ -160,6 +160,12 @@ __global__ void __launch_bounds__(BS, MB) scan_kernel(fc::GenomeView g, fc::Scan
     m = __ldg(b.meta + i);
     uint32_t rlo[NP], rhi[NP];
     load_read_row<NP>(b.reads, i, b.nw, rlo, rhi);
+    if constexpr (MODE != 0) {
+      // the payload of the record is only looked at after the scan: bring it into L2 now, beside the tile loads
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(e.read_hash + i));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(e.q + i));
+      if (e.qname_hash) asm volatile("prefetch.global.L2 [%0];" ::"l"(e.qname_hash + i));
+    }
     const int64_t ga = (int64_t)m.x | ((int64_t)(m.z & 63u) << 32), gb = (int64_t)m.y | ((int64_t)((m.z >> 6) & 63u) << 32);
     const int l = (int)((m.z >> 12) & 0xFFFu);
     const uint32_t fl = (m.z >> 24) & 15u;

@@ -62,10 +62,29 @@ class NativeIngest(object):
         for name, arr in a.items():
             setattr(o, name, arr.ctypes.data)
 
-    def parse(self, buf: bytes, offset: int, final: bool) -> int:
+    def set_position(self, first_fragment: int, at_stream_start: bool):
+        if self.lib.fc_ingest_set_position(self.h, int(first_fragment), int(bool(at_stream_start))) != 0:
+            raise RuntimeError("fc_ingest_set_position failed")
+
+    def next_fragment(self) -> int:
+        return int(self.lib.fc_ingest_position(self.h))
+
+    def snapshot(self, n: int) -> dict:
+        """copies of the first n rows of the output arrays (planes as [n_words][n]): what a worker thread hands over"""
+        out = {}
+        for k, v in self.a.items():
+            if k.startswith("cx_"):
+                continue
+            if k in ("rlo", "rhi", "rn"):
+                out[k] = np.ascontiguousarray(v.reshape(self.n_words, self.cap)[:, :n]).reshape(-1)
+            else:
+                out[k] = v[:n].copy()
+        return out
+
+    def parse(self, buf: bytes, offset: int, final: bool, end: int = -1) -> int:
         """parse buf[offset:]; returns bytes consumed.  Results are in self.out / self.a until the next call."""
         base = C.cast(C.c_char_p(buf), C.c_void_p).value
-        n = self.lib.fc_ingest_parse(self.h, base + offset, len(buf) - offset, int(final), C.byref(self.out))
+        n = self.lib.fc_ingest_parse(self.h, base + offset, (len(buf) if end < 0 else end) - offset, int(final), C.byref(self.out))
         if n < 0:
             raise RuntimeError("fc_ingest_parse failed (%d)" % n)
         return int(n)

@@ -60,6 +60,8 @@ class Options:
     batch_pairs: int = 1 << 18  # anchor pairs per GPU batch (ours)
     device: int = 0
     native: bool = True  # native (C++) SAM ingest for SAM text files
+    ingest_threads: int = 0  # parser threads of the native ingest (0: one per core, at most 16)
+    ingest_piece_bytes: int = 4 << 20  # chunks of SAM text larger than this are cut into one piece per thread
     test: bool = False    # test_results.tsv: every fragment against the truth in its name (find_circ.py:411, 1148-1273)
     known_circ: str = ""  # BED6 files of known junctions (find_circ.py:387-388)
     known_lin: str = ""
@@ -215,6 +217,35 @@ def test_result_row(frag: str, lin_coords, circ_coords, unspliced_coords, broken
     return "\t".join([frag, verdict(lin_ref, set(lin_coords), "LINEAR_JUNCTIONS", "LIN_OK"),
                       verdict(circ_ref, set(circ_coords), "CIRCULAR_JUNCTIONS", "CIRC_OK"),
                       verdict(un_ref, set(unspliced_coords), "UNSPLICED", "UNSPLICED_OK"), broken])
+
+
+def _piece_cuts(buf: bytes, pieces: int):
+    """offsets that cut a chunk of SAM text into `pieces` parts on fragment boundaries (a line whose read name differs from
+    the line before it, find_circ.py:1450-1486): the parts can be parsed independently"""
+    n = len(buf)
+    cuts = [0]
+    for k in range(1, pieces):
+        pos = buf.find(b"\n", max(n * k // pieces, cuts[-1]))
+        if pos < 0:
+            break
+        ls = pos + 1  # start of a line; skip the rest of its fragment
+        if ls >= n:
+            break
+        name = buf[ls:buf.find(b"\t", ls)]
+        while True:
+            nl = buf.find(b"\n", ls)
+            if nl < 0:
+                ls = n
+                break
+            ls = nl + 1
+            if ls >= n or buf[ls:buf.find(b"\t", ls)] != name:
+                break
+        if ls >= n:
+            break
+        if ls > cuts[-1]:
+            cuts.append(ls)
+    cuts.append(n)
+    return cuts
 
 
 class JunctionInfo(object):
@@ -579,56 +610,104 @@ class Run(object):
             raise ValueError("process_native does not cover --all-hits / --noop / --test")
         tid2gid = [self.eng._chrom_ids.get(n, -1) for n in self.sam_chroms]
         name2tid = {n: i for i, n in enumerate(self.sam_chroms)}
-        ing = NativeIngest(opt.asize, opt.margin, opt.min_uniq_qual, opt.nolinear, self.sam_chroms, tid2gid,
-                           cap=max(1024, opt.batch_pairs), first_fragment=first_fragment, at_stream_start=at_stream_start)
+        threads = int(getattr(opt, "ingest_threads", 0) or 0) or max(1, min(16, os.cpu_count() or 1))
+        cap = max(1024, opt.batch_pairs)
+        mk = lambda first, at_start: NativeIngest(opt.asize, opt.margin, opt.min_uniq_qual, opt.nolinear, self.sam_chroms, tid2gid,  # noqa: E731
+                                                  cap=cap, first_fragment=first, at_stream_start=at_start)
+        ings = [mk(first_fragment, at_stream_start)]
         self.explicit_idx = True
-        a, o = ing.a, ing.out
         carry = b""
         eof = False
+        pool = None
+
+        def consume(buf, off, a, n, max_l, n_frag, counters, complex_ranges, plane_stride):
+            """what one fc_ingest_parse call produced: rows -> GPU, fragments it left -> python"""
+            self.n_fragments += n_frag
+            for k, name in enumerate(COUNTER_NAMES):
+                if counters[k]:
+                    N[name] += counters[k]
+            if n:
+                self._native_rows(buf, off, a, n, max_l, ings[0].n_words, plane_stride, ings[0].lib)
+            for s0, s1, seq in complex_ranges:
+                self.cur_seq = seq
+                lines = buf[off + s0:off + s1].decode("latin-1").splitlines(True)
+                recs = [_parse_sam_line(ln, name2tid, 0) for ln in lines if ln.strip() and not ln.startswith("@")]
+                nf0 = self.n_fragments
+                for mate1, mate2 in iter_fragments(recs, N):
+                    self.add_fragment(mate1, mate2)
+                self.n_fragments = nf0 + 1
+
+        def parse_piece(ing, buf, start, end, final, keep):
+            """parse buf[start:end] with one handle; keep=False: hand every call's output straight to consume() (single
+            thread), keep=True: return snapshots for the main thread.  Returns (results, offset reached)"""
+            a, o = ing.a, ing.out
+            off, out = start, []
+            while off < end:
+                used = ing.parse(buf, off, final, end)
+                n = int(o.n_rows)
+                cx = [(int(a["cx_start"][k]), int(a["cx_end"][k]), int(a["cx_seq"][k])) for k in range(int(o.n_complex))]
+                if keep:
+                    out.append((off, n, int(o.max_l), int(o.n_fragments), [o.counters[k] for k in range(8)], cx, ing.snapshot(n)))
+                else:
+                    consume(buf, off, a, n, int(o.max_l), int(o.n_fragments), [o.counters[k] for k in range(8)], cx, ing.cap)
+                off += used
+                if used == 0:
+                    break
+                if n < ing.cap and len(cx) < int(o.cap_complex) and not final:
+                    break  # the rest is an incomplete fragment: wait for the next chunk
+            return out, off
+
         try:
             while not eof:
                 chunk = fh.read(chunk_bytes)
                 eof = len(chunk) == 0  # (a stream may return short chunks before its end: BAM text comes in whole lines)
                 buf = carry + chunk if carry else chunk
-                off = 0
-                while len(buf):
-                    used = ing.parse(buf, off, eof)
-                    n = int(o.n_rows)
-                    self.n_fragments += int(o.n_fragments)
-                    for k, name in enumerate(COUNTER_NAMES):
-                        if o.counters[k]:
-                            N[name] += o.counters[k]
-                    if n:
-                        self._native_rows(buf, off, a, n, int(o.max_l), ing)
-                    for k in range(int(o.n_complex)):
-                        s0, s1 = off + int(a["cx_start"][k]), off + int(a["cx_end"][k])
-                        self.cur_seq = int(a["cx_seq"][k])
-                        lines = buf[s0:s1].decode("latin-1").splitlines(True)
-                        recs = [_parse_sam_line(ln, name2tid, 0) for ln in lines if ln.strip() and not ln.startswith("@")]
-                        nf0 = self.n_fragments
-                        for mate1, mate2 in iter_fragments(recs, N):
-                            self.add_fragment(mate1, mate2)
-                        self.n_fragments = nf0 + 1
-                    off += used
-                    if used == 0 or off >= len(buf):
-                        break
-                    if int(o.n_rows) < ing.cap and int(o.n_complex) < int(o.cap_complex) and not eof:
-                        break  # the rest is an incomplete fragment: wait for the next chunk
+                if not len(buf):
+                    break
+                cuts = _piece_cuts(buf, threads) if threads > 1 and len(buf) > int(getattr(opt, "ingest_piece_bytes", 4 << 20)) else [0, len(buf)]
+                if len(cuts) == 2:
+                    _, off = parse_piece(ings[0], buf, 0, len(buf), eof, False)
+                else:
+                    if pool is None:
+                        from concurrent.futures import ThreadPoolExecutor
+
+                        pool = ThreadPoolExecutor(threads)
+                    while len(ings) < len(cuts) - 1:
+                        ings.append(mk(0, False))
+                    # every piece numbers its fragments from its own base: more than it can hold apart (a SAM line is > 16 bytes)
+                    stride = max(b - a0 for a0, b in zip(cuts, cuts[1:])) // 16 + 2
+                    next_ord = ings[0].next_fragment()
+                    jobs = []
+                    for k in range(len(cuts) - 1):
+                        if k:
+                            ings[k].set_position(next_ord + k * stride, False)
+                        last = k == len(cuts) - 2
+                        jobs.append(pool.submit(parse_piece, ings[k], buf, cuts[k], cuts[k + 1], eof if last else True, True))
+                    off = 0
+                    for k, job in enumerate(jobs):
+                        results, end_off = job.result()
+                        for (o0, n, max_l, n_frag, counters, cx, arrays) in results:
+                            consume(buf, o0, arrays, n, max_l, n_frag, counters, cx, n)
+                        off = end_off
+                    ings[0].set_position(next_ord + (len(cuts) - 1) * stride, False)
                 carry = buf[off:]
                 if eof and carry.strip():
                     raise ValueError("unparsable trailing SAM text")
             self.flush()
         finally:
-            ing.close()
+            if pool is not None:
+                pool.shutdown()
+            for ing in ings:
+                ing.close()
 
-    def _native_rows(self, buf, off, a, n, max_l, ing):
+    def _native_rows(self, buf, off, a, n, max_l, n_words, plane_stride, lib):
         """scan + record the rows the native ingest produced (single-span fragments: the evidence logic collapses to
         'first tie is recorded', find_circ.py:1299-1317, 1351-1378), fully vectorised"""
         N = self.N
         idx = (a["frag_seq"][:n].astype(np.uint64) * np.uint64(64))
         t0 = time.perf_counter()
         hits = self.eng.batch_host_planes(n, a["chrom"], a["a_start"], a["b_end"], a["l"], a["flags"], a["rlo"], a["rhi"], a["rn"],
-                                          ing.n_words, ing.cap, max(max_l, 0), a["wden"], a["q_a"], a["q_b"], a["read_hash"],
+                                          n_words, plane_stride, max(max_l, 0), a["wden"], a["q_a"], a["q_b"], a["read_hash"],
                                           a["qname_hash"], idx=idx, emit=True)
         self.t_scan += time.perf_counter() - t0
         self.n_pairs_scanned += n
@@ -651,7 +730,7 @@ class Run(object):
             len3[:, k] = a[f + "_len"][rows]
         blob = np.empty(int(np.maximum(len3, 0).sum()), dtype=np.uint8)
         base = C.cast(C.c_char_p(buf), C.c_void_p).value
-        got = ing.lib.fc_text_gather(base, m, off3.ctypes.data, len3.ctypes.data, blob.ctypes.data)
+        got = lib.fc_text_gather(base, m, off3.ctypes.data, len3.ctypes.data, blob.ctypes.data)
         if got != len(blob):
             raise RuntimeError("fc_text_gather failed (%d)" % got)
         self.native_reads.append(dict(

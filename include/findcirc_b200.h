@@ -413,6 +413,7 @@ void fc_ingest_destroy(fc_ingest* h);
  * name changes): ordinal of its first fragment; at_stream_start = 0 unless its first record is the first of the whole
  * stream -- the only record the reference never checks for the "unmapped" flag (find_circ.py:1462-1463) */
 int fc_ingest_set_position(fc_ingest* h, int64_t first_fragment, int32_t at_stream_start);
+int64_t fc_ingest_position(fc_ingest* h); /* the ordinal the next fragment will get */
 /* parses complete fragments out of `text`; returns the number of bytes consumed (the caller re-submits the rest together
  * with the next chunk; final != 0 flushes the last fragment) or a negative error code */
 int64_t fc_ingest_parse(fc_ingest* h, const char* text, int64_t nbytes, int32_t final, fc_ingest_out* out);

@@ -28,6 +28,25 @@ def test_host_logic_matches_reference(case_dir, ref_dir, argv, native):
     H.compare_outputs(out["circ"], out["lin"], out["reads"], out["multi"], out["counters"], ref_dir, argv, out["test"])
 
 
+@pytest.mark.parametrize("threads", [2, 5])
+@pytest.mark.parametrize("case,tag", [("synth_a", "default"), ("synth_a", "a20"), ("synth_b", "default"), ("kat3", "default"),
+                                      ("synth_a", "uniq0_half_nobridge"), ("synth_a", "nolinear_nomulti")])
+def test_native_ingest_on_parser_threads(case, tag, threads):
+    """the SAM text of a chunk is cut into pieces on fragment boundaries and parsed by several threads (own parser handle and
+    fragment numbering each): same outputs as the reference, whatever the cut"""
+    from conftest import GOLDEN, golden_cases
+    from find_circ2_b200 import cli
+
+    case_dir, ref_dir = os.path.join(GOLDEN, case), os.path.join(GOLDEN, case, "ref_" + tag)
+    argv = [a for c, r, a in golden_cases() if r == ref_dir][0]
+    opt = cli.parse_args(["-G", os.path.join(case_dir, "genome.fa")] + argv)[0]
+    opt.batch_pairs, opt.ingest_threads, opt.ingest_piece_bytes = 149, threads, 1
+    eng = FakeEngine(0, opt.asize, opt.margin, opt.maxdist, opt.noncanonical, opt.strandpref)
+    eng.load_genome_fasta(opt.genome)
+    out = cli.run_to_strings(opt, os.path.join(case_dir, "input.sam"), engine=eng, native=True)
+    H.compare_outputs(out["circ"], out["lin"], out["reads"], out["multi"], out["counters"], ref_dir, argv, out["test"])
+
+
 @pytest.mark.parametrize("case,tag", [("synth_a", "default"), ("synth_a", "a20"), ("synth_a", "m4_d3"), ("synth_b", "default"),
                                       ("kat3", "default"), ("cdr1as", "default"), ("synth_a", "known")])
 def test_native_ingest_from_bam(tmp_path, case, tag):
