@@ -107,7 +107,7 @@ class GzipMembers(object):
     def __init__(self, path: str, level: int = 6, threads: int = 0):
         self.fh = open(path, "wb")
         self.level = level
-        self.threads = threads or max(1, min(8, (os.cpu_count() or 1)))
+        self.threads = threads or max(1, min(16, (os.cpu_count() or 1)))
         self.pending = []
         self.size = 0
 

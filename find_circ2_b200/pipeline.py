@@ -219,6 +219,22 @@ def test_result_row(frag: str, lin_coords, circ_coords, unspliced_coords, broken
                       verdict(un_ref, set(unspliced_coords), "UNSPLICED", "UNSPLICED_OK"), broken])
 
 
+def _unique_rows(key: np.ndarray):
+    """np.unique(key, axis=0, return_inverse=True) for an [n, 5] int64 matrix of junction identities, by way of one 64-bit
+    mix per row (a 1-D sort instead of a lexicographic one); rows that share a mix are verified, a clash falls back"""
+    if len(key) == 0:
+        return key, np.zeros(0, dtype=np.int64)
+    k = key.astype(np.uint64)
+    h = k[:, 0] * np.uint64(0x9E3779B97F4A7C15)
+    for c in range(1, k.shape[1]):
+        h = (h ^ (h >> np.uint64(29))) * np.uint64(0xBF58476D1CE4E5B9) + k[:, c] * np.uint64(0x94D049BB133111EB)
+    uh, first, inverse = np.unique(h, return_index=True, return_inverse=True)
+    uniq = key[first]
+    if not np.array_equal(uniq[inverse], key):
+        return np.unique(key, axis=0, return_inverse=True)
+    return uniq, inverse
+
+
 def _piece_cuts(buf: bytes, pieces: int):
     """offsets that cut a chunk of SAM text into `pieces` parts on fragment boundaries (a line whose read name differs from
     the line before it, find_circ.py:1450-1486): the parts can be parsed independently"""
@@ -756,6 +772,9 @@ class Run(object):
 
     def _names(self, junc) -> Dict[tuple, str]:
         """discovery-order names, counting junctions that are filtered from the output too (find_circ.py:683-686)"""
+        cached = getattr(self, "_names_cache", None)
+        if cached is not None and cached[0] is junc:
+            return cached[1]
         names = {}
         counts = [0, 0]
         prefix = ("circ", "lin")
@@ -768,6 +787,7 @@ class Run(object):
                 continue
             counts[kind] += 1
             names[key] = "%s_%s_%06d" % (self.opt.name, prefix[kind], counts[kind])
+        self._names_cache = (junc, names)
         return names
 
     def categories(self, r, inf: Optional[JunctionInfo], min_dist, min_ov=None, min_nh=None) -> List[str]:
@@ -866,8 +886,7 @@ class Run(object):
         py_seqs = np.array([e[0] for e in self.reads_out], dtype=np.int64)
         pieces, done = [], 0
         for b in self.native_reads:
-            key = np.stack([b["chrom"], b["start"], b["end"], b["minus"], b["kind"]], axis=1)
-            uniq, inverse = np.unique(key, axis=0, return_inverse=True)
+            uniq, inverse = _unique_rows(np.stack([b["chrom"], b["start"], b["end"], b["minus"], b["kind"]], axis=1))
             jn = [names[(int(c), int(s0), int(e0), "-" if mi else "+", int(kd))].encode("latin-1") for c, s0, e0, mi, kd in uniq.tolist()]
             name_len = np.array([len(x) for x in jn], dtype=np.int32)
             name_off = np.zeros(len(jn), dtype=np.int64)

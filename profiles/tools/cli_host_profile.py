@@ -36,3 +36,4 @@ with tempfile.TemporaryDirectory() as tmp:
     dt = time.perf_counter() - t0
     print("second run %.2f s  -> %.0f reads/s" % (dt, n / dt))
     pstats.Stats(pr).sort_stats("cumulative").print_stats(22)
+    pstats.Stats(pr).sort_stats("cumulative").print_stats("find_circ2_b200|numpy", 30)
