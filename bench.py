@@ -142,7 +142,8 @@ def _cpu_shard_time(recs):
 def oracle_options(cfg):
     from oracle import find_circ_oracle as O
 
-    return O.Options(asize=cfg.asize, margin=cfg.margin, maxdist=cfg.maxdist, min_uniq_qual=cfg.min_uniq, name="bench")
+    return O.Options(asize=cfg.asize, margin=cfg.margin, maxdist=cfg.maxdist, min_uniq_qual=cfg.min_uniq, name="bench",
+                     halfunique=cfg.halfunique, report_nobridges=cfg.report_nobridges)
 
 
 def cpu_run(spec, cols, lines, procs=1):
@@ -264,14 +265,19 @@ class Shard(object):
                      base + 2 * step, self.n_words, self.max_l, self.n)
 
 
-def dropin_parity(eng, spec, cfg, n_sample):
+def cli_argv(cfg):
+    return (["-G", "unused", "-a", str(cfg.asize), "-m", str(cfg.margin), "-d", str(cfg.maxdist), "-n", "bench", "--min-uniq-qual",
+             str(cfg.min_uniq)] + (["--halfuniq"] if cfg.halfunique else []) + (["--report_nobridge"] if cfg.report_nobridges else []))
+
+
+def dropin_parity(eng, spec, cfg, n_sample, large=True, error_rate=None):
     """the whole drop-in (SAM text -> native / python ingest -> GPU -> five outputs) on a prefix of the workload against the
     oracle; also what `ingest` (host decoding rate) and `cpu_baseline` are taken from"""
     import bench_workload as W
     from find_circ2_b200 import cli
     from oracle import find_circ_oracle as O
 
-    cols = W.make_pairs(spec, 0, n_sample, "cpu")
+    cols = W.make_pairs(spec, 0, n_sample, "cpu", error_rate=error_rate)
     lines = sample_sam(spec, cols)
     cpu_s, want = cpu_run(spec, cols, lines, 1)
     res = {}
@@ -281,8 +287,7 @@ def dropin_parity(eng, spec, cfg, n_sample):
         with open(sam, "w") as fh:
             fh.writelines(lines)
         for tag, native in (("python", False), ("native", True)):
-            opt = cli.parse_args(["-G", "unused", "-a", str(cfg.asize), "-m", str(cfg.margin), "-d", str(cfg.maxdist), "-n", "bench",
-                                  "--min-uniq-qual", str(cfg.min_uniq)])[0]
+            opt = cli.parse_args(cli_argv(cfg))[0]
             out = cli.run_to_strings(opt, sam, engine=eng, native=native)
             same = (O.canonical_bed(out["circ"]) == O.canonical_bed(want.circ_bed) and O.canonical_bed(out["lin"]) == O.canonical_bed(want.lin_bed)
                     and out["reads"] == want.reads_fastq and O.canonical_multi(out["multi"]) == O.canonical_multi(want.multi_events)
@@ -294,6 +299,11 @@ def dropin_parity(eng, spec, cfg, n_sample):
         # the native ingest covers), the 20 k-read SAM text replicated under fresh read names
         import dataclasses
 
+        if not large:
+            n_rows = len(want.circ_bed.splitlines()) + len(want.lin_bed.splitlines()) - 2
+            return ({"ok": ok and n_rows > 0, "against": "oracle, all five outputs of the drop-in, native and python ingest", "pairs": n_sample,
+                     "junction_rows": n_rows}, None, None)
+
         spec_u = W.Spec(dataclasses.replace(cfg, paired=False))
         body = "".join(sample_sam(spec_u, W.make_pairs(spec_u, 0, n_sample, "cpu"))).encode()
         head_end = body.find(b"\nr") + 1  # (header lines start with @, read names with r)
@@ -304,8 +314,7 @@ def dropin_parity(eng, spec, cfg, n_sample):
             fh.write(header)
             for k in range(copies):
                 fh.write(recs.replace(b"\nr", b"\nc%dr" % k)[1:])
-        opt = cli.parse_args(["-G", "unused", "-a", str(cfg.asize), "-m", str(cfg.margin), "-d", str(cfg.maxdist), "-n", "bench",
-                              "--min-uniq-qual", str(cfg.min_uniq)])[0]
+        opt = cli.parse_args(cli_argv(cfg))[0]
         out = cli.run_to_strings(opt, big, engine=eng, native=True)
         host_s = out["seconds_ingest_and_scan"] - out["seconds_gpu_calls"]
         threads = opt.ingest_threads or max(1, min(16, os.cpu_count() or 1))
@@ -616,6 +625,9 @@ def bench_config(args, cfg, dist, dev, primary, error_rate=None):
                       "pairs": "first 100000 rows of every rank's shard", "junction_rows": n_union}
         elif world == 1:
             parity, ingest, cpu = dropin_parity(eng, spec, cfg, min(args.cpu_sample, per) // 4 * 4)
+    elif world == 1:
+        # the other configs: a short prefix of each through the whole drop-in against the oracle
+        parity, _, _ = dropin_parity(eng, spec, cfg, 4000, large=False, error_rate=error_rate)
 
     # ---- reductions over ranks
     e2e_step = e2e["s_step"] if e2e else 0.0

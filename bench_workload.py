@@ -94,6 +94,8 @@ class Config:
     seed: int = 1
     scaling: str = "strong"   # how n_pairs relates to the GPU count: "strong" = whole job fixed, "weak" = per GPU
     min_uniq: int = 2         # the is_uniq pre-filter of find_circ.py:1299-1301 (0: keep everything, the fmt-1.2 behaviour)
+    halfunique: bool = False        # --halfuniq: keep junctions with one uniquely placed side (find_circ.py:706-713)
+    report_nobridges: bool = False  # --report_nobridge: keep junctions without a unique bridge (find_circ.py:715-717)
     workload: str = ""
 
 
@@ -105,6 +107,7 @@ def configs() -> Dict[str, Config]:
         "3": Config("3", HG19_SIZES, 100000, 5000, 50000000, paired=True,
                     workload="configs[2]: hg19-sized synthetic genome (3.1 Gb, 24 chrom, 0.5% N, replicated per GPU), 100k planted circRNAs, 50M anchor pairs in the whole job from 2x100-nt mate pairs (mates share a name), a=20 m=2 d=2, 0.5% substitutions, 10% decoys"),
         "4": Config("4", [5000000] * 20, 10000, 500, 4000000, read_len=150, error_rate=0.02, scaling="weak", min_uniq=0, frac_nonuniq=0.10,
+                    halfunique=True, report_nobridges=True,
                     workload="configs[3]: 100 Mb genome, 150-nt reads (l=114), 1/2/3% substitutions, no per-span uniqueness filter (--halfuniq --report_nobridge semantics: one-sided anchors and zero-bridge junctions stay in), 4M anchor pairs per GPU"),
         "5": Config("5", HG19_SIZES, 10000000, 100000, 500000000 // 8, zipf=0.6, scaling="weak",
                     workload="configs[4]: 500M anchor pairs over 8 GPUs = 62.5M per GPU, 10M distinct planted junctions (Zipf 0.6 tail: most junctions carry 1-5 reads), hg19-sized genome"),

@@ -160,3 +160,69 @@ def test_hg19_sized_coordinates():
              48129895, 51304566, 155270560]  # chr1..22, X (test_data/test_norm.sam:1-93 lists the hg19 lengths)
     st = _full_case({}, sizes, 2000000, 100000, seed=5, sample=800)
     assert st["bases"] == sum(sizes)
+
+
+def test_config5_shaped_aggregation(monkeypatch):
+    """BASELINE.json configs[4] in miniature on one GPU: 6 M junction records over 1.2 M distinct junctions with a Zipf(0.6)
+    tail (most junctions carry 1-5 reads), repeated read sequences and fragment names, weights 1, 1/2, 1/4, 1/8 -- the
+    one-pass table (64-byte slots, exact hash set) and the sort-based reduce must give the same table, byte for byte, and the
+    table must equal a numpy group-by"""
+    from find_circ2_b200._lib import JREC_DTYPE
+    from find_circ2_b200.engine import Engine
+
+    rng = np.random.default_rng(55)
+    n, nj = 6000000, 1200000
+    w = 1.0 / np.power(np.arange(1, nj + 1, dtype=np.float64), 0.6)
+    jx = rng.choice(nj, size=n, p=w / w.sum())
+    jc = rng.integers(0, 24, size=nj).astype(np.uint32)
+    js = rng.integers(1000, 200000000, size=nj).astype(np.int32)
+    je = (js + rng.integers(200, 50000, size=nj)).astype(np.int32)
+    jk = rng.integers(0, 4, size=nj).astype(np.uint32)
+    recs = np.zeros(n, dtype=JREC_DTYPE)
+    recs["chrom"], recs["start"], recs["end"] = jc[jx], js[jx], je[jx]
+    den = rng.choice(np.array([1, 1, 1, 2, 4, 8], dtype=np.uint32), size=n)
+    rh = rng.integers(0, 1 << 62, size=n, dtype=np.int64).astype(np.uint64) << np.uint64(1)
+    dup = rng.random(n) < 0.1
+    rh[dup] = rh[rng.integers(0, n, size=int(dup.sum()))]  # repeated reads (some inside one junction, most not)
+    rh[rng.random(n) < 0.01] |= np.uint64(1)                # palindromic reads
+    recs["sk"] = jk[jx] | ((rh & np.uint64(1)).astype(np.uint32) << 2) | (den << 8) | (np.uint32(0x2D2) << 16)
+    recs["idx"] = np.arange(n, dtype=np.uint64) + np.uint64(1000)
+    recs["read_hash"] = rh
+    recs["qname_hash"] = (np.arange(n, dtype=np.uint64) // np.uint64(2)) * np.uint64(0x9E3779B97F4A7C15)
+    recs["q_left"] = rng.integers(0, 60, size=n)
+    recs["q_right"] = rng.integers(0, 60, size=n)
+    recs["n_hits"] = rng.integers(1, 4, size=n)
+    recs["dist"] = rng.integers(0, 3, size=n)
+    recs["ov"] = rng.integers(0, 3, size=n)
+    e = Engine(device=0, asize=20)
+    tables = []
+    for mode in ("", "sort"):
+        monkeypatch.setenv("FC_AGG_MODE", mode)
+        e.agg_reset()
+        e.agg_append_host(recs)
+        tables.append(e.agg_fetch(e.agg_finalize()))
+    monkeypatch.setenv("FC_AGG_MODE", "")
+    a, b = tables
+    assert len(a) == len(np.unique(jx)) and a.tobytes() == b.tobytes()
+    # against numpy: counts, weights and distinct reads / names of every junction
+    key = jx
+    order = np.argsort(key, kind="stable")
+    ks = key[order]
+    starts = np.concatenate([[0], np.nonzero(np.diff(ks))[0] + 1])
+    cnt = np.diff(np.concatenate([starts, [n]]))
+    first = recs["idx"][order][starts]
+    by_first = np.argsort(first)
+    assert np.array_equal(a["first_idx"], first[by_first])
+    assert np.array_equal(a["n_spanned"].astype(np.int64), cnt[by_first])
+    wsum = np.add.reduceat((1.0 / den[order]), starts)
+    assert np.array_equal(a["n_weighted"], wsum[by_first])
+    pair = np.stack([ks, rh[order].view(np.int64)], axis=1)
+    up = np.unique(pair, axis=0)
+    n_reads = np.bincount(np.searchsorted(np.unique(ks), up[:, 0]), minlength=len(starts))
+    pal = up[(up[:, 1] & 1) == 1]
+    n_pal = np.bincount(np.searchsorted(np.unique(ks), pal[:, 0]), minlength=len(starts))
+    assert np.array_equal(a["n_uniq"].astype(np.int64), (n_reads - (n_pal + 1) // 2)[by_first])
+    qn = np.stack([ks, recs["qname_hash"][order].view(np.int64)], axis=1)
+    n_names = np.bincount(np.searchsorted(np.unique(ks), np.unique(qn, axis=0)[:, 0]), minlength=len(starts))
+    assert np.array_equal(a["n_frags"].astype(np.int64), n_names[by_first])
+    e.close()
