@@ -350,7 +350,7 @@ def multi_gpu_parity(eng, sh, dist, dev, idx_base, total, m=100000):
     stream = torch.cuda.current_stream().cuda_stream
     eng.agg_reset_async(stream)
     eng.agg_set_idx_range(0, total)
-    eng.scan_emit_batch(sh.batch_prefix(m), sh.hits, sh.q, sh.d["read_hash"], sh.d["qname_hash"], idx_base, stream)
+    eng.scan_emit_batch(sh.batch_prefix(m), sh.hits, sh.q, sh.d["read_hash"], None, idx_base, stream)
     parallel.stream_barrier(dist, dev, eng, stream)
     nj = eng.agg_finalize(stream)
     got = parallel.gather_junctions(eng.agg_fetch(nj), dist, dev)
@@ -438,14 +438,14 @@ def bench_config(args, cfg, dist, dev, primary, error_rate=None):
         if ev:
             ev[0].record()
         if world == 1:
-            # scan + record in one kernel (fc_scan_emit_batch)
-            eng.scan_emit_batch(sh.batch, sh.hits, sh.q, d["read_hash"], d["qname_hash"], idx_base, stream)
+            # scan + record in one kernel (fc_scan_emit_batch); no name hashes: the descriptors carry the fragment fields
+            eng.scan_emit_batch(sh.batch, sh.hits, sh.q, d["read_hash"], None, idx_base, stream)
             if ev:
                 ev[1].record()
                 ev[2].record()
         elif use_p2p:
             # the same kernel, records land in the owner ranks' buffers (the context is connected to its peers)
-            eng.scan_emit_batch(sh.batch, sh.hits, sh.q, d["read_hash"], d["qname_hash"], idx_base, stream)
+            eng.scan_emit_batch(sh.batch, sh.hits, sh.q, d["read_hash"], None, idx_base, stream)
             if ev:
                 ev[1].record()
             parallel.stream_barrier(dist, dev, eng, stream)  # ends the step: counts published, every rank's records have landed

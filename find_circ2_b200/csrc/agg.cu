@@ -394,12 +394,17 @@ __device__ __forceinline__ void set_insert2(U128* table, unsigned long long mask
 // junction's slot), so the warps hide each other's memory round trips.  Measured on the B200 (config 3, 44 M records):
 // without the table 9.96 ms, with it 3.6 ms; a count-min sketch as a second admission rule changed nothing.
 constexpr int ACC_THREADS = 512;
-constexpr int ACC_MAX_TILES = 16;  // tiles of ACC_THREADS records per chunk (between two flushes of the shared-memory table)
+// Measured on the B200 (configs 3 and 5): 3 CTAs per SM (40 registers, spills), chunks of 16 instead of 30 tiles, 8 instead
+// of 2 probes of the shared-memory table and an L2 prefetch of the next tile's records all change the kernel time by < 3 %:
+// it is bound by the rate of random DRAM sector accesses (~32 G/s on this part), not by latency or issue slots.
+#define FC_ACC_MIN_CTAS 2
+#define FC_HOT_PROBES 2
+constexpr int ACC_MAX_TILES = 30;  // tiles of ACC_THREADS records per chunk (between two flushes of the shared-memory table)
 constexpr int HOT_ENTRIES = 512;
 constexpr int HOT_BITS = 9;
 struct HotTable {
   unsigned int tag[HOT_ENTRIES];    // junction slot + 1, 0 = free
-  unsigned int c0[HOT_ENTRIES];     // n_spanned | 8 * weight << 14 (a chunk holds at most 8192 records of weight <= 1)
+  unsigned int c0[HOT_ENTRIES];     // n_spanned | 8 * weight << 14 (a chunk holds fewer than 16384 records of weight <= 1)
   unsigned int c1[HOT_ENTRIES];     // names seen before | 8 * non-bridge weight << 14
   unsigned int c2[HOT_ENTRIES];
   unsigned int qmax_l[HOT_ENTRIES], qmax_r[HOT_ENTRIES], inv_dist[HOT_ENTRIES], inv_ov[HOT_ENTRIES], inv_nh[HOT_ENTRIES];
@@ -412,7 +417,7 @@ static_assert(ACC_MAX_TILES * ACC_THREADS < (1 << 14) && ACC_MAX_TILES * ACC_THR
 __device__ __forceinline__ int hot_find_or_insert(HotTable& t, unsigned int jid, bool insert) {
   unsigned int h = (jid * 2654435761u) >> (32 - HOT_BITS);
 #pragma unroll 1
-  for (int probe = 0; probe < 8; ++probe) {
+  for (int probe = 0; probe < FC_HOT_PROBES; ++probe) {  // (2 probes: a miss is the common case and must stay cheap)
     unsigned int cur = *reinterpret_cast<volatile unsigned int*>(&t.tag[h]);
     if (cur == 0u) {
       if (!insert) return -1;
@@ -430,7 +435,7 @@ __device__ __forceinline__ void ld_sector(const JSlot* s, unsigned long long (&v
   asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(s));
 }
 
-__global__ void __launch_bounds__(ACC_THREADS, 2) fused_accumulate_kernel(RecSrc src, int chunk_tiles, int prefetch, unsigned long long idx_base, JSlot* __restrict__ slots,
+__global__ void __launch_bounds__(ACC_THREADS, FC_ACC_MIN_CTAS) fused_accumulate_kernel(RecSrc src, int chunk_tiles, int prefetch, unsigned long long idx_base, JSlot* __restrict__ slots,
                                                                   unsigned long long kmask, U128* __restrict__ sets,
                                                                   unsigned long long smask, unsigned int* __restrict__ list,
                                                                   unsigned int lcap, unsigned int* __restrict__ ctr,
@@ -1276,7 +1281,7 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st, const Re
     // persistent CTAs: two per SM, each walks chunks of up to ACC_MAX_TILES tiles of ACC_THREADS records; small inputs get
     // shorter chunks so that every SM has work
     const int64_t tiles = (ub + ACC_THREADS - 1) / ACC_THREADS;
-    const int64_t ctas = (int64_t)ctx->sm_count * 2;
+    const int64_t ctas = (int64_t)ctx->sm_count * FC_ACC_MIN_CTAS;
     int chunk_tiles = (int)((tiles + 2 * ctas - 1) / (2 * ctas));
     chunk_tiles = chunk_tiles < 1 ? 1 : (chunk_tiles > ACC_MAX_TILES ? ACC_MAX_TILES : chunk_tiles);
     const int64_t chunks = (tiles + chunk_tiles - 1) / chunk_tiles;
