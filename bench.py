@@ -179,7 +179,10 @@ def run_reference(args):
     cfg = W.configs()[args.config]
     cores = os.cpu_count() or 1
     spec = W.Spec(cfg)
-    n_sample = max(args.cpu_sample * cores, 2000) // 4 * 4
+    # a bounded prefix of the workload per step, sized so that the whole run takes about two minutes: the oracle scans
+    # ~1.7 k pairs/s per core (one numpy compare per split position, as the reference does)
+    n_sample = int(1500 * cores * 120 / (args.steps + 1 + (1 if args.warmup else 0)))
+    n_sample = max(4000, min(n_sample, 2000000, args.cpu_sample * cores * 4)) // 4 * 4
     cols = W.make_pairs(spec, 0, n_sample, "cpu")
     lines = sample_sam(spec, cols)
     if args.warmup:

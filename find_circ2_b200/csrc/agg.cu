@@ -397,6 +397,9 @@ constexpr int ACC_THREADS = 512;
 // Measured on the B200 (configs 3 and 5): 3 CTAs per SM (40 registers, spills), chunks of 16 instead of 30 tiles, 8 instead
 // of 2 probes of the shared-memory table and an L2 prefetch of the next tile's records all change the kernel time by < 3 %:
 // it is bound by the rate of random DRAM sector accesses (~32 G/s on this part), not by latency or issue slots.
+// Also tried: two L2-resident bit filters in front of the read set so that only (read, junction) pairs whose bit is hit
+// twice reach the exact set (a second pass) -- the first pass drops to 1.9-3.3 ms at config 3, but reads repeat so often in
+// popular junctions that the second pass handles most records anyway: no gain overall.
 #define FC_ACC_MIN_CTAS 2
 #define FC_HOT_PROBES 2
 constexpr int ACC_MAX_TILES = 30;  // tiles of ACC_THREADS records per chunk (between two flushes of the shared-memory table)

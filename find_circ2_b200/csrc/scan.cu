@@ -344,6 +344,7 @@ static int scan_launch(fc_ctx* ctx, const fc_scan_params* p, const BatchView& b,
   // 256-thread CTAs, 48 registers -> 5 CTAs (40 warps) per SM.  Measured alternatives on B200 (round 1): 128- and
   // 192-thread CTAs, register caps 32/40/58, and a persistent software-pipelined variant with L2 prefetch of the next
   // pair's tiles were all equal or slower.
+  // (multi-GPU: 512-thread CTAs, i.e. twice as long NVLink runs per destination, change nothing either)
 #define FC_SCAN_LAUNCH(NP, T) FC_SCAN_LAUNCH_BS(NP, T, 256, 5)
   // the kernel specialisation follows the tile geometry of the store (scan_core.cuh: tile_geometry)
   switch (g.tile_T) {
