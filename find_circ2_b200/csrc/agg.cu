@@ -355,16 +355,31 @@ struct SetProbe {
     ++k;
   }
 };
+// (entries never change once written, so a look through L1 is as good as one at L2; an EMPTY seen there may be stale: the
+// compare-and-swap then returns the real owner)
+__device__ __forceinline__ U128 set_peek(const U128* p) {
+  U128 v;
+  asm volatile("ld.global.ca.v2.u64 {%0,%1}, [%2];" : "=l"(v.lo), "=l"(v.hi) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ void set_insert2(U128* table, unsigned long long mask, unsigned long long v1, unsigned long long t1,
                                             unsigned long long s1, bool with2, unsigned long long v2, unsigned long long t2,
-                                            unsigned long long s2, bool& new1, bool& new2) {
+                                            unsigned long long s2, bool peek, bool& new1, bool& new2) {
   bool d1 = false, d2 = !with2;
   SetProbe p1{s1, 0}, p2{s2, 0};
   new1 = new2 = false;
   while (!(d1 && d2)) {
+    // look first when the set is larger than L2: in a popular junction most reads have been seen before, an element that
+    // is already there is found by a (cacheable) load, and a load that misses to DRAM is cheaper than an atomic that does
+    // (measured, 50 M records: 3.59 -> 3.24 ms; 54 M records over 10 M junctions: 12.2 -> 8.5 ms).  A set that fits L2 has
+    // had its slots prefetched and goes straight to the atomic (the look costs 15 % there: one more round trip).
     U128 o1{0ull, 0ull}, o2{0ull, 0ull};
-    if (!d1) o1 = cas128(table + p1.s, U128{0ull, 0ull}, U128{v1, t1});
-    if (!d2) o2 = cas128(table + p2.s, U128{0ull, 0ull}, U128{v2, t2});
+    if (peek && !d1) o1 = set_peek(table + p1.s);
+    if (peek && !d2) o2 = set_peek(table + p2.s);
+    if (!d1 && o1.lo == 0ull && o1.hi == 0ull) o1 = cas128(table + p1.s, U128{0ull, 0ull}, U128{v1, t1});
+    else if (!d1 && !(o1.lo == v1 && o1.hi == t1)) o1.lo = ~v1;  // (somebody else's: probe on; cannot equal mine or be empty)
+    if (!d2 && o2.lo == 0ull && o2.hi == 0ull) o2 = cas128(table + p2.s, U128{0ull, 0ull}, U128{v2, t2});
+    else if (!d2 && !(o2.lo == v2 && o2.hi == t2)) o2.lo = ~v2;
     if (!d1) {
       if (o1.lo == 0ull && o1.hi == 0ull)
         new1 = d1 = true;
@@ -585,7 +600,7 @@ __global__ void __launch_bounds__(ACC_THREADS, FC_ACC_MIN_CTAS) fused_accumulate
       // ---- distinct reads / fragment names of the junction
       const unsigned long long tag = (unsigned long long)jid + 1ull;  // never 0: no entry is all-zero
       bool new_read = false, new_name = false;
-      set_insert2(sets, smask, read_hash, tag, s_read, !name_known, qname_hash, tag | (1ull << 32), s_name, new_read, new_name);
+      set_insert2(sets, smask, read_hash, tag, s_read, !name_known, qname_hash, tag | (1ull << 32), s_name, !prefetch, new_read, new_name);
       const bool dup_name = name_known ? (sk & SK_NAME_DUP) != 0u : !new_name;
 
       // ---- counters
