@@ -298,17 +298,14 @@ def dropin_parity(eng, spec, cfg, n_sample, large=True, error_rate=None):
             ok = ok and same
             host_s = out["seconds_total"] - out["seconds_gpu_calls"]
             res[tag] = {"pairs_per_s": n_sample / host_s, "seconds_host": host_s, "seconds_gpu_calls": out["seconds_gpu_calls"], "equals_oracle": same}
-        # host ingest at a size where fixed costs vanish: single-end reads of the same genome (one span per read: the rows
-        # the native ingest covers), the 20 k-read SAM text replicated under fresh read names
-        import dataclasses
-
+        # host ingest at a size where fixed costs vanish: the SAM text of the sample (the workload's own fragments: mate
+        # pairs with both mates spliced in configs[2]) replicated under fresh read names
         if not large:
             n_rows = len(want.circ_bed.splitlines()) + len(want.lin_bed.splitlines()) - 2
             return ({"ok": ok and n_rows > 0, "against": "oracle, all five outputs of the drop-in, native and python ingest", "pairs": n_sample,
                      "junction_rows": n_rows}, None, None)
 
-        spec_u = W.Spec(dataclasses.replace(cfg, paired=False))
-        body = "".join(sample_sam(spec_u, W.make_pairs(spec_u, 0, n_sample, "cpu"))).encode()
+        body = "".join(lines).encode()
         head_end = body.find(b"\nr") + 1  # (header lines start with @, read names with r)
         header, recs = body[:head_end], b"\n" + body[head_end:]
         big = os.path.join(tmp, "ingest.sam")
@@ -329,11 +326,12 @@ def dropin_parity(eng, spec, cfg, n_sample, large=True, error_rate=None):
     parity = {"ok": ok and n_rows > 0, "against": "oracle (oracle/find_circ_oracle.py), all five outputs of the drop-in, native and python ingest",
               "pairs": n_sample, "junction_rows": n_rows}
     ingest = {"value": res["native_large"]["pairs_per_s"], "unit": "pairs/s",
-              "kind": "host time, GPU calls excluded.  value = native_large: SAM text -> fragments -> rows for the GPU (csrc/ingest.cu on parser "
-                      "threads, single-end reads with one span each; the junction aggregation and the text writers that follow are "
-                      "seconds_writers); native / python = the whole host path (writers included) on the %d-pair prefix of the bench "
-                      "workload itself (mate pairs: fragments of two spliced mates are handed to pipeline.py by the native ingest)" % n_sample,
-              "sample": "%d single-end reads" % res["native_large"]["reads"], "native_large": res["native_large"], "native": res["native"],
+              "kind": "host time, GPU calls excluded.  value = native_large: SAM text -> mates -> fragments -> rows and fragment records "
+                      "for the GPU (csrc/ingest.cu on parser threads) -> evidence rules over the batch (pipeline._native_batch), on the "
+                      "workload's own fragments (%s); the junction aggregation and the text writers that follow are seconds_writers.  "
+                      "native / python = the whole host path (writers included) on the %d-pair prefix alone"
+                      % ("mate pairs, both mates spliced" if cfg.paired else "single-end reads, one span each", n_sample),
+              "sample": "%d reads (the %d-pair prefix x %d)" % (res["native_large"]["reads"], n_sample, copies), "native_large": res["native_large"], "native": res["native"],
               "python": res["python"]}
     cpu = {"value": n_sample / cpu_s, "unit": "pairs/s", "cores": 1, "kind": "port",
            "sample": "first %d pairs of the same workload, oracle scan+aggregation single process (%.1f s); SAM decode untimed" % (n_sample, cpu_s)}

@@ -244,22 +244,18 @@ def _merge_host_state(run: Run, parts):
     from collections import defaultdict
 
     run.N = defaultdict(float)
-    run.info = {}
-    run.reads_out, run.native_reads, run.multi_out, run.test_out = [], [], [], []
+    run._ev_py, run.ev_native, run._info_cache = [], [], None
+    run.reads_out, run.native_reads, run.multi_out, run.native_multi, run.test_out = [], [], [], [], []
     run.n_fragments = run.n_pairs_scanned = 0
     run.t_scan = 0.0
     for p in parts:
         for k, v in p["N"].items():
             run.N[k] += v
-        for key, (flags, read_flags) in p["info"].items():
-            inf = run._info(key)
-            for f, c in flags.items():
-                inf.flags[f] += c
-            for name, fl in read_flags.items():
-                inf.read_flags[name] |= fl
+        run.ev_native.append(p["events"])
         run.reads_out.extend(p["reads_out"])
         run.native_reads.extend(p["native_reads"])
         run.multi_out.extend(p["multi_out"])
+        run.native_multi.extend(p["native_multi"])
         run.test_out.extend(p["test_out"])
         run.n_fragments += p["n_fragments"]
         run.n_pairs_scanned += p["n_pairs_scanned"]
@@ -288,7 +284,7 @@ def run_distributed(opt: Options, path, dist, torch_dev, engine=None):
             run.process_native(_Range(fh, start, end), first_fragment=rank * stride, at_stream_start=(start == body))
         t1 = time.perf_counter()
         run.finalize(dist, torch_dev)
-        part = {"N": dict(run.N), "info": {k: (dict(v.flags), {n: set(f) for n, f in v.read_flags.items()}) for k, v in run.info.items()},
+        part = {"N": dict(run.N), "events": run.events(), "native_multi": run.native_multi,
                 "reads_out": run.reads_out, "native_reads": run.native_reads, "multi_out": run.multi_out, "test_out": run.test_out,
                 "n_fragments": run.n_fragments, "n_pairs_scanned": run.n_pairs_scanned, "t_scan": run.t_scan}
         parts = [None] * world if rank == 0 else None

@@ -2,13 +2,16 @@
 //
 // The reference decodes every record through pysam and builds Python objects per read
 // (/root/reference/find_circ.py:461-469, 1450-1486, 976-1140, 821-852); a python host that does the same is three orders
-// of magnitude slower than the scan kernel.  This file parses SAM text in C++ and emits, for every fragment that consists
-// of ONE mate with at most one supplementary record (single-end two-segment reads: the bulk of real input), the
-// struct-of-arrays row the GPU needs: window coordinates, flags, the internal read part already as bit planes,
-// anchor qualities and the read / name hashes -- ready to be copied to the device as they are.
-// Everything else (paired mates, three or more segments, records it cannot interpret) is handed back as a byte range
-// and goes through the python implementation of the same logic (find_circ2_b200/pipeline.py), so the two paths together
-// cover exactly what the reference covers.  Counters are accumulated here only for the fragments handled here.
+// of magnitude slower than the scan kernel.  This file parses SAM text in C++, groups the records into mates and
+// fragments, forms the anchor pairs ("spans") of every mate and emits, for every fragment with at most two spans in
+// total (single-end two-segment reads, mate pairs with one or both mates spliced, three-segment mates: the bulk of real
+// input), the struct-of-arrays rows the GPU needs -- window coordinates, flags, the internal read part already as bit
+// planes, anchor qualities and the read / name hashes, ready to be copied to the device as they are -- plus one record
+// per fragment with what the evidence rules of record_hits (find_circ.py:1276-1439) need besides the scan's answers
+// (pipeline.py applies them to whole batches at once).
+// Everything else (three or more spans, a third mate, records it cannot interpret) is handed back as a byte range and
+// goes through the python implementation of the same logic (find_circ2_b200/pipeline.py), so the two paths together cover
+// exactly what the reference covers.  Counters are accumulated here only for the fragments handled here.
 #include <string.h>
 
 #include <string>
@@ -206,6 +209,7 @@ extern "C" int64_t fc_ingest_parse(fc_ingest* h, const char* text, int64_t nbyte
   const fc_ingest_params& P = g.p;
   const int eff = P.asize - P.margin;
   o->n_rows = 0;
+  o->n_frag_records = 0;
   o->n_complex = 0;
   o->n_fragments = 0;
   o->max_l = 0;
@@ -216,121 +220,212 @@ extern "C" int64_t fc_ingest_parse(fc_ingest* h, const char* text, int64_t nbyte
   frag.reserve(8);
   int64_t frag_start = 0;      // byte offset of the first line of the current fragment
   int64_t frag_unmapped = 0;   // unmapped records skipped inside the current fragment's byte range
-  bool frag_switch = false;    // a mate switch happened
+  bool force_python = false;   // a line the parser could not interpret lies in or next to the fragment
   bool have_frag = false;
   int64_t consumed = 0;
 
+  auto leave_to_python = [&](int64_t frag_end) -> bool {
+    if (o->n_complex >= o->cap_complex) return false;
+    o->cx_start[o->n_complex] = frag_start;
+    o->cx_end[o->n_complex] = frag_end;
+    o->cx_seq[o->n_complex] = g.frag_seq;
+    o->n_complex++;
+    o->n_fragments++;
+    g.frag_seq++;
+    return true;
+  };
+
+  // one anchor pair of a mate (JunctionSpan, find_circ.py:821-852)
+  struct SpanC {
+    const Rec *A, *B, *primary;
+    int q_start, q_end, den;
+    bool backsplice, queued;
+  };
+  constexpr int MAX_REC = 16;
+
   auto finish = [&](int64_t frag_end) -> bool {
     // returns false when the output arrays are full (the fragment is then NOT consumed)
-    const size_t nrec = frag.size();
-    bool complex = frag_switch || nrec > 2;
+    const int nrec = (int)frag.size();
+    bool complex = force_python || nrec > MAX_REC || (frag[0].flag & 0x4) != 0;
     for (const Rec& r : frag) complex = complex || !r.ok;
-    const Rec& p = frag[0];
+    if (complex) return leave_to_python(frag_end);
     double add[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    bool row = false;
-    const Rec *A = nullptr, *B = nullptr;
-    int q_start = 0, q_end = 0;
-    bool backsplice = false;
-    if (!complex) {
-      add[C_TOTAL_MATES] += 1;
-      add[C_UNMAPPED] += (double)frag_unmapped;
-      bool proper2 = false;
-      if (nrec == 2) {
-        const Rec& s = frag[1];
-        proper2 = s.tid == p.tid && ((s.flag ^ p.flag) & 0x10) == 0;
+    // ---- mates (find_circ.py:1450-1486): a record whose read1 flag differs from the current mate's primary starts the
+    // other mate; a third mate would push the first one out -- left to python
+    int mate_of[MAX_REC], prim[2] = {0, 0}, n_mates = 1;
+    mate_of[0] = 0;
+    for (int k = 1; k < nrec; ++k) {
+      if (((frag[k].flag ^ frag[prim[n_mates - 1]].flag) & 0x40) != 0) {
+        if (n_mates == 2) return leave_to_python(frag_end);
+        prim[n_mates++] = k;
       }
-      if (!proper2) {
+      mate_of[k] = n_mates - 1;
+    }
+    add[C_TOTAL_MATES] += n_mates;
+    add[C_UNMAPPED] += (double)frag_unmapped;
+    // ---- segments and spans of every mate (MateSegments / adjacent_segment_pairs, find_circ.py:976-1140)
+    SpanC circ[3], lin[3];
+    int n_circ = 0, n_lin = 0;
+    const Rec* unspliced = nullptr;
+    bool broken = false;
+    for (int m = 0; m < n_mates; ++m) {
+      const Rec& p = frag[prim[m]];
+      int proper[MAX_REC], n_proper = 0, n_other = 0;
+      for (int k = 0; k < nrec; ++k) {
+        if (mate_of[k] != m) continue;
+        const Rec& r = frag[k];
+        if (r.tid == p.tid && ((r.flag ^ p.flag) & 0x10) == 0) proper[n_proper++] = k;
+        else ++n_other;
+      }
+      if (n_proper < 2) {
         add[C_UNSPLICED] += 1;
-      } else {
-        const Rec& s = frag[1];
-        if (!p.has_seq || !s.has_seq || !p.has_cigar || !s.has_cigar || (p.flag & 0x4)) {
-          complex = true;  // python raises on these, keep its behaviour
+        if (!unspliced) unspliced = &p;
+        continue;
+      }
+      if (n_proper - 1 > 255) return leave_to_python(frag_end);  // (python raises on these)
+      for (int k = 0; k < n_proper; ++k) {
+        const Rec& r = frag[proper[k]];
+        if (!r.has_seq || !r.has_cigar) return leave_to_python(frag_end);  // python raises on these, keep its behaviour
+      }
+      // stable order by the start of the aligned part in the read
+      for (int i = 1; i < n_proper; ++i) {
+        const int v = proper[i];
+        int j = i - 1;
+        while (j >= 0 && frag[proper[j]].clip_start > frag[v].clip_start) { proper[j + 1] = proper[j]; --j; }
+        proper[j + 1] = v;
+      }
+      const int L = (int)p.seq.size();
+      int lo = L, hi = 0;
+      for (int k = 0; k + 1 < n_proper; ++k) {
+        const Rec *a = &frag[proper[k]], *b = &frag[proper[k + 1]];
+        if (a->qlen < P.asize || b->qlen < P.asize) {
+          add[C_TOO_SHORT] += 1;
+          continue;
+        }
+        SpanC sp;
+        sp.A = a;
+        sp.B = b;
+        sp.primary = &p;
+        sp.q_start = a->clip_start < b->clip_start ? a->clip_start : b->clip_start;
+        const int ea = a->clip_start + a->qlen, eb = b->clip_start + b->qlen;
+        sp.q_end = ea > eb ? ea : eb;
+        sp.den = n_proper - 1;
+        sp.backsplice = (b->pos - a->aend) < 0;
+        sp.queued = false;
+        if (!a->has_AS || !b->has_AS) return leave_to_python(frag_end);
+        if (sp.q_start < lo) lo = sp.q_start;
+        if (sp.q_end > hi) hi = sp.q_end;
+        if (sp.backsplice) {
+          if (n_circ == 3) return leave_to_python(frag_end);
+          circ[n_circ++] = sp;
         } else {
-          const Rec* a = &p;
-          const Rec* b = &s;
-          if (s.clip_start < p.clip_start) { a = &s; b = &p; }
-          const int la = a->qlen, lb = b->qlen;
-          if (la < P.asize || lb < P.asize) {
-            add[C_TOO_SHORT] += 1;
-          } else {
-            A = a;
-            B = b;
-            q_start = a->clip_start < b->clip_start ? a->clip_start : b->clip_start;
-            const int ea = a->clip_start + la, eb = b->clip_start + lb;
-            q_end = ea > eb ? ea : eb;
-            backsplice = (B->pos - A->aend) < 0;
-            if (P.nolinear && !backsplice) {
-              // fragment without back-splice candidates is dropped before record_hits (find_circ.py:1568-1569)
-            } else if (!A->has_AS || !B->has_AS) {
-              complex = true;
-            } else {
-              const int ua = A->has_XS ? A->AS - A->XS : A->AS, ub = B->has_XS ? B->AS - B->XS : B->AS;
-              const int uniq = ua < ub ? ua : ub;
-              if (uniq < P.min_uniq_qual) add[backsplice ? C_CIRC_NOT_UNIQ : C_LIN_NOT_UNIQ] += 1;
-              else row = true;
-            }
-          }
+          if (n_lin == 3) return leave_to_python(frag_end);
+          lin[n_lin++] = sp;
         }
       }
+      if ((hi < L - P.asize || lo > P.asize) && n_other > 0) broken = true;
     }
-    int gid = -1;
-    if (row) {
-      gid = (A->tid >= 0 && A->tid < (int)g.tid2gid.size()) ? g.tid2gid[A->tid] : -1;
-      if (gid < 0) { complex = true; row = false; }
+    // ---- the head of record_hits (find_circ.py:1560-1574): which spans go to the scan
+    const bool dropped = (n_circ == 0 && P.nolinear) || (n_circ + n_lin == 0);
+    int n_rows_new = 0;
+    SpanC* spans[2] = {nullptr, nullptr};
+    int n_sp = 0;
+    if (!dropped) {
+      if (n_circ + n_lin > 2 || (P.nolinear && n_circ > 0 && n_lin > 0)) return leave_to_python(frag_end);
+      for (int k = 0; k < n_circ; ++k) spans[n_sp++] = &circ[k];
+      for (int k = 0; k < n_lin; ++k) spans[n_sp++] = &lin[k];
+      for (int k = 0; k < n_sp; ++k) {
+        SpanC& sp = *spans[k];
+        const int ua = sp.A->has_XS ? sp.A->AS - sp.A->XS : sp.A->AS, ub = sp.B->has_XS ? sp.B->AS - sp.B->XS : sp.B->AS;
+        if ((ua < ub ? ua : ub) < P.min_uniq_qual) {
+          add[sp.backsplice ? C_CIRC_NOT_UNIQ : C_LIN_NOT_UNIQ] += 1;
+          continue;
+        }
+        const int tid = sp.A->tid;
+        if (tid < 0 || tid >= (int)g.tid2gid.size() || g.tid2gid[tid] < 0) return leave_to_python(frag_end);  // (python raises)
+        const int plen = (int)sp.primary->seq.size();
+        int qs = sp.q_start < plen ? sp.q_start : plen, qe = sp.q_end < plen ? sp.q_end : plen;
+        if (qe < qs) qe = qs;
+        const int l = qe - qs - 2 * eff;
+        // read longer than the caller's plane buffer: let the python path deal with it
+        if (l > 0 && (l + 31) / 32 > o->n_words) return leave_to_python(frag_end);
+        sp.queued = true;
+        ++n_rows_new;
+      }
     }
-    if (complex) {
-      if (o->n_complex >= o->cap_complex) return false;
-      o->cx_start[o->n_complex] = frag_start;
-      o->cx_end[o->n_complex] = frag_end;
-      o->cx_seq[o->n_complex] = g.frag_seq;
-      o->n_complex++;
-    } else {
-      if (row) {
-        if (o->n_rows >= o->cap) return false;
+    if (n_rows_new) {
+      for (int m = 0; m < n_mates; ++m)
+        if (!frag[prim[m]].has_seq) return leave_to_python(frag_end);  // (python fails when it prints such a read)
+      if (o->n_rows + n_rows_new > o->cap) return false;
+      const int64_t fi = o->n_frag_records;
+      o->f_seq[fi] = g.frag_seq;
+      o->f_row0[fi] = (int32_t)o->n_rows;
+      o->f_nsp[fi] = (uint8_t)n_sp;
+      uint8_t kind = 0, state = 0;
+      int kq = 0;
+      for (int k = 0; k < n_sp; ++k) {
+        const SpanC& sp = *spans[k];
+        if (sp.backsplice) kind |= (uint8_t)(1u << k);
+        if (!sp.queued) continue;
+        state |= (uint8_t)(1u << k);
         const int64_t i = o->n_rows;
+        const Rec& p = *sp.primary;
         const int plen = (int)p.seq.size();
-        int qs = q_start < plen ? q_start : plen, qe = q_end < plen ? q_end : plen;
+        int qs = sp.q_start < plen ? sp.q_start : plen, qe = sp.q_end < plen ? sp.q_end : plen;
         if (qe < qs) qe = qs;
         const int L = qe - qs;
         const int l = L - 2 * eff;
         sv internal;
-        if (eff > 0 && L - eff > eff) internal = p.seq.substr((size_t)(qs + eff), (size_t)(L - 2 * eff));
-        if ((int)((internal.size() + 31) / 32) > o->n_words) {
-          // read longer than the caller's plane buffer: let the python path deal with it
-          if (o->n_complex >= o->cap_complex) return false;
-          o->cx_start[o->n_complex] = frag_start;
-          o->cx_end[o->n_complex] = frag_end;
-          o->cx_seq[o->n_complex] = g.frag_seq;
-          o->n_complex++;
-          for (int k = 0; k < 8; ++k) add[k] = 0;
-          row = false;
-        } else {
-          o->chrom[i] = gid;
-          o->a_start[i] = A->pos + eff;
-          o->b_end[i] = B->aend - eff;
-          o->l[i] = l;
-          bool any_n = false;
-          pack_planes(internal, o->n_words, o->cap, i, o->rlo, o->rhi, o->rn, any_n);
-          o->flags[i] = (uint8_t)((backsplice ? 1 : 0) | ((p.flag & 0x10) ? 2 : 0) | (any_n ? 4 : 0));
-          o->wden[i] = 1;
-          const int qa = A->AS - (A->has_XS ? A->XS : 0), qb = B->AS - (B->has_XS ? B->XS : 0);
-          o->q_a[i] = (int16_t)(qa < -32768 ? -32768 : (qa > 32767 ? 32767 : qa));
-          o->q_b[i] = (int16_t)(qb < -32768 ? -32768 : (qb > 32767 ? 32767 : qb));
-          o->read_hash[i] = fc_hash_read(reinterpret_cast<const uint8_t*>(p.seq.data()), (int64_t)p.seq.size(), nullptr);
-          o->qname_hash[i] = fc_hash_bytes(reinterpret_cast<const uint8_t*>(p.qname.data()), (int64_t)p.qname.size());
-          o->frag_seq[i] = g.frag_seq;
-          o->qname_off[i] = p.qname.data() - text;
-          o->qname_len[i] = (int32_t)p.qname.size();
-          o->seq_off[i] = p.seq.data() - text;
-          o->seq_len[i] = (int32_t)p.seq.size();
-          o->qual_off[i] = p.has_qual ? p.qual.data() - text : 0;
-          o->qual_len[i] = p.has_qual ? (int32_t)p.qual.size() : -1;
-          if (l > o->max_l) o->max_l = l;
-          o->n_rows++;
-        }
+        if (L - eff > eff) internal = p.seq.substr((size_t)(qs + eff), (size_t)(L - 2 * eff));
+        o->chrom[i] = g.tid2gid[sp.A->tid];
+        o->a_start[i] = sp.A->pos + eff;
+        o->b_end[i] = sp.B->aend - eff;
+        o->l[i] = l;
+        bool any_n = false;
+        pack_planes(internal, o->n_words, o->cap, i, o->rlo, o->rhi, o->rn, any_n);
+        o->flags[i] = (uint8_t)((sp.backsplice ? 1 : 0) | ((p.flag & 0x10) ? 2 : 0) | (any_n ? 4 : 0));
+        o->wden[i] = (uint8_t)sp.den;
+        const int qa = sp.A->AS - (sp.A->has_XS ? sp.A->XS : 0), qb = sp.B->AS - (sp.B->has_XS ? sp.B->XS : 0);
+        o->q_a[i] = (int16_t)(qa < -32768 ? -32768 : (qa > 32767 ? 32767 : qa));
+        o->q_b[i] = (int16_t)(qb < -32768 ? -32768 : (qb > 32767 ? 32767 : qb));
+        o->read_hash[i] = fc_hash_read(reinterpret_cast<const uint8_t*>(p.seq.data()), (int64_t)p.seq.size(), nullptr);
+        o->qname_hash[i] = fc_hash_bytes(reinterpret_cast<const uint8_t*>(p.qname.data()), (int64_t)p.qname.size());
+        o->frag_seq[i] = g.frag_seq;
+        o->idx_k[i] = (uint8_t)kq++;
+        if (l > o->max_l) o->max_l = l;
+        o->n_rows++;
       }
-      for (int k = 0; k < 8; ++k) o->counters[k] += add[k];
+      o->f_kind[fi] = kind;
+      o->f_state[fi] = state;
+      uint8_t ff = (uint8_t)((n_mates == 2 ? FC_FR_TWO_MATES : 0u) | (broken ? FC_FR_BROKEN : 0u));
+      o->f_un_tid[fi] = o->f_un_pos[fi] = o->f_un_aend[fi] = 0;
+      if (unspliced) {
+        ff |= FC_FR_UNSPLICED;
+        if (n_circ > 0 && circ[0].primary->tid != unspliced->tid) ff |= FC_FR_OTHER_CHROM;
+        o->f_un_tid[fi] = unspliced->tid;
+        o->f_un_pos[fi] = unspliced->pos;
+        o->f_un_aend[fi] = unspliced->aend;
+      }
+      o->f_flags[fi] = ff;
+      for (int m = 0; m < 2; ++m) {
+        int64_t* off = o->f_txt_off + (fi * 2 + m) * 3;
+        int32_t* len = o->f_txt_len + (fi * 2 + m) * 3;
+        if (m >= n_mates) {
+          off[0] = off[1] = off[2] = 0;
+          len[0] = len[1] = len[2] = -2;
+          continue;
+        }
+        const Rec& p = frag[prim[m]];
+        off[0] = p.qname.data() - text;
+        len[0] = (int32_t)p.qname.size();
+        off[1] = p.has_seq ? p.seq.data() - text : 0;
+        len[1] = p.has_seq ? (int32_t)p.seq.size() : -1;
+        off[2] = p.has_qual ? p.qual.data() - text : 0;
+        len[2] = p.has_qual ? (int32_t)p.qual.size() : -1;
+      }
+      o->n_frag_records++;
     }
+    for (int k = 0; k < 8; ++k) o->counters[k] += add[k];
     o->n_fragments++;
     g.frag_seq++;
     return true;
@@ -368,7 +463,7 @@ extern "C" int64_t fc_ingest_parse(fc_ingest* h, const char* text, int64_t nbyte
       frag.push_back(r);
       frag_start = line_off;
       frag_unmapped = 0;
-      frag_switch = false;
+      force_python = false;
       have_frag = true;
       g.first_record = false;
       continue;
@@ -379,13 +474,12 @@ extern "C" int64_t fc_ingest_parse(fc_ingest* h, const char* text, int64_t nbyte
     }
     const Rec& p = frag[0];
     if (r.ok && p.ok && r.qname == p.qname) {
-      if (((r.flag ^ frag.back().flag) & 0x40) != 0 || ((r.flag ^ p.flag) & 0x40) != 0) frag_switch = true;
       frag.push_back(r);
       continue;
     }
     if (!r.ok || !p.ok) {
       // unparsable line: make the whole neighbourhood complex and let python report it
-      frag_switch = true;
+      force_python = true;
       if (!r.ok && p.ok) {
         frag.push_back(r);
         continue;
@@ -401,7 +495,7 @@ extern "C" int64_t fc_ingest_parse(fc_ingest* h, const char* text, int64_t nbyte
     frag.push_back(r);
     frag_start = line_off;
     frag_unmapped = 0;
-    frag_switch = false;
+    force_python = false;
   }
   if (final && have_frag && pos >= nbytes) {
     if (!finish(nbytes)) return frag_start;
@@ -432,8 +526,8 @@ extern "C" int64_t fc_text_gather(const char* buf, int64_t n, const int64_t* off
 }
 
 // FASTQ records of n reads whose (name, sequence, qualities) lie back to back in `blob` (lengths in len, n x 3; qualities
-// absent = the text "None", as python prints a missing pysam field): "@<name> <junction> \n<seq>\n+<name> <junction> \n<qual>\n".
-// junction = names[name_off[name_idx[i]] ...].  rec_off[0..n] receives the offset of every record in `out`.
+// absent = the text "None", as python prints a missing pysam field): "@<name> <tail>\n<seq>\n+<name> <tail>\n<qual>\n".
+// tail ("<junction names> <flags>") = names[name_off[name_idx[i]] ...].  rec_off[0..n] receives the offset of every record in `out`.
 // Returns the bytes written, or the bytes needed (> out_cap) when `out` is too small.
 extern "C" int64_t fc_fastq_format(const char* blob, int64_t n, const int32_t* len, const int32_t* name_idx, const char* names,
                                    const int64_t* name_off, const int32_t* name_len, char* out, int64_t out_cap,
@@ -443,7 +537,7 @@ extern "C" int64_t fc_fastq_format(const char* blob, int64_t n, const int32_t* l
   for (int64_t i = 0; i < n; ++i) {
     const int64_t q = len[3 * i] > 0 ? len[3 * i] : 0, s = len[3 * i + 1] > 0 ? len[3 * i + 1] : 0;
     const int64_t u = len[3 * i + 2] >= 0 ? len[3 * i + 2] : 4;
-    need += 2 * (q + name_len[name_idx[i]] + 3) + 2 + s + 1 + u + 1;
+    need += 2 * (q + name_len[name_idx[i]] + 2) + 2 + s + 1 + u + 1;
   }
   if (need > out_cap || !out) return need;
   int64_t r = 0, w = 0;
@@ -462,7 +556,6 @@ extern "C" int64_t fc_fastq_format(const char* blob, int64_t n, const int32_t* l
       out[w++] = ' ';
       memcpy(out + w, jn, (size_t)jl);
       w += jl;
-      out[w++] = ' ';
       out[w++] = '\n';
       if (pass == 0) {
         memcpy(out + w, sp, (size_t)s);

@@ -1,7 +1,7 @@
 """
 ctypes face of the native SAM ingest (csrc/ingest.cu, fc_ingest_*): parses chunks of SAM text into struct-of-arrays rows
-for fragments made of one mate with at most one supplementary record; everything else comes back as byte ranges for the
-python path (pipeline.Run.add_fragment).  Host code only.
+plus one record per fragment, for fragments of one or two mates with at most two anchor pairs in total; everything else
+comes back as byte ranges for the python path (pipeline.Run.add_fragment).  Host code only.
 """
 from __future__ import annotations
 
@@ -23,11 +23,22 @@ class IngestOut(C.Structure):
     _fields_ = [
         ("cap", C.c_int64), ("chrom", _P), ("a_start", _P), ("b_end", _P), ("l", _P), ("flags", _P), ("rlo", _P), ("rhi", _P),
         ("rn", _P), ("n_words", C.c_int32), ("max_l", C.c_int32), ("wden", _P), ("q_a", _P), ("q_b", _P), ("read_hash", _P),
-        ("qname_hash", _P), ("frag_seq", _P), ("qname_off", _P), ("qname_len", _P), ("seq_off", _P), ("seq_len", _P),
-        ("qual_off", _P), ("qual_len", _P), ("cap_complex", C.c_int64), ("cx_start", _P), ("cx_end", _P), ("cx_seq", _P),
-        ("n_rows", C.c_int64), ("n_complex", C.c_int64), ("n_fragments", C.c_int64), ("counters", C.c_double * 8),
+        ("qname_hash", _P), ("frag_seq", _P), ("idx_k", _P),
+        ("f_seq", _P), ("f_row0", _P), ("f_nsp", _P), ("f_kind", _P), ("f_state", _P), ("f_flags", _P), ("f_un_tid", _P),
+        ("f_un_pos", _P), ("f_un_aend", _P), ("f_txt_off", _P), ("f_txt_len", _P),
+        ("cap_complex", C.c_int64), ("cx_start", _P), ("cx_end", _P), ("cx_seq", _P),
+        ("n_rows", C.c_int64), ("n_frag_records", C.c_int64), ("n_complex", C.c_int64), ("n_fragments", C.c_int64),
+        ("counters", C.c_double * 8),
     ]
 
+
+FR_UNSPLICED, FR_OTHER_CHROM, FR_BROKEN, FR_TWO_MATES = 1, 2, 4, 8  # fc_ingest_out.f_flags
+
+ROW_FIELDS = (("chrom", np.int32), ("a_start", np.int32), ("b_end", np.int32), ("l", np.int32), ("flags", np.uint8),
+              ("wden", np.uint8), ("q_a", np.int16), ("q_b", np.int16), ("read_hash", np.uint64), ("qname_hash", np.uint64),
+              ("frag_seq", np.int64), ("idx_k", np.uint8))
+FRAG_FIELDS = (("f_seq", np.int64), ("f_row0", np.int32), ("f_nsp", np.uint8), ("f_kind", np.uint8), ("f_state", np.uint8),
+               ("f_flags", np.uint8), ("f_un_tid", np.int32), ("f_un_pos", np.int32), ("f_un_aend", np.int32))
 
 COUNTER_NAMES = ("total_mates", "unmapped_reads", "unspliced_mates", "seg_too_short_skip", "circ_junc_not_unique",
                  "lin_junc_not_unique")
@@ -48,11 +59,10 @@ class NativeIngest(object):
                 raise RuntimeError("fc_ingest_set_position failed")
         self.cap, self.n_words = cap, n_words
         a = self.a = {}
-        for name, dt in (("chrom", np.int32), ("a_start", np.int32), ("b_end", np.int32), ("l", np.int32), ("flags", np.uint8),
-                         ("wden", np.uint8), ("q_a", np.int16), ("q_b", np.int16), ("read_hash", np.uint64),
-                         ("qname_hash", np.uint64), ("frag_seq", np.int64), ("qname_off", np.int64), ("qname_len", np.int32),
-                         ("seq_off", np.int64), ("seq_len", np.int32), ("qual_off", np.int64), ("qual_len", np.int32)):
+        for name, dt in ROW_FIELDS + FRAG_FIELDS:
             a[name] = np.zeros(cap, dtype=dt)
+        a["f_txt_off"] = np.zeros(6 * cap, dtype=np.int64)
+        a["f_txt_len"] = np.zeros(6 * cap, dtype=np.int32)
         for name in ("rlo", "rhi", "rn"):
             a[name] = np.zeros(n_words * cap, dtype=np.uint32)
         for name in ("cx_start", "cx_end", "cx_seq"):
@@ -69,16 +79,18 @@ class NativeIngest(object):
     def next_fragment(self) -> int:
         return int(self.lib.fc_ingest_position(self.h))
 
-    def snapshot(self, n: int) -> dict:
-        """copies of the first n rows of the output arrays (planes as [n_words][n]): what a worker thread hands over"""
+    def snapshot(self, n: int, m: int) -> dict:
+        """copies of the first n rows / m fragment records of the output arrays (planes as [n_words][n]): what a worker
+        thread hands over"""
         out = {}
-        for k, v in self.a.items():
-            if k.startswith("cx_"):
-                continue
-            if k in ("rlo", "rhi", "rn"):
-                out[k] = np.ascontiguousarray(v.reshape(self.n_words, self.cap)[:, :n]).reshape(-1)
-            else:
-                out[k] = v[:n].copy()
+        for k, _ in ROW_FIELDS:
+            out[k] = self.a[k][:n].copy()
+        for k, _ in FRAG_FIELDS:
+            out[k] = self.a[k][:m].copy()
+        out["f_txt_off"] = self.a["f_txt_off"][:6 * m].copy()
+        out["f_txt_len"] = self.a["f_txt_len"][:6 * m].copy()
+        for k in ("rlo", "rhi", "rn"):
+            out[k] = np.ascontiguousarray(self.a[k].reshape(self.n_words, self.cap)[:, :n]).reshape(-1)
         return out
 
     def parse(self, buf: bytes, offset: int, final: bool, end: int = -1) -> int:

@@ -264,14 +264,36 @@ def _piece_cuts(buf: bytes, pieces: int):
     return cuts
 
 
-class JunctionInfo(object):
-    """host-side companions of a junction that never reach the GPU: per-fragment flags (find_circ.py:513-524, 632-652)"""
+# per-fragment evidence flags of record_hits (find_circ.py:1331-1437) as bits, in the order sorted() gives their names
+FLAG_NAMES = sorted(["BROKEN_SEGMENTS", "SUPPORT_CLOSURE", "SUPPORT_INSIDE_MATE", "SUPPORT_INSIDE_SPLICE_JUNCTION",
+                     "WARN_MULTI_BACKSPLICE", "WARN_OTHER_CHROM_MATE", "WARN_OUTSIDE_MATE", "WARN_OUTSIDE_SPLICE_JUNCTION",
+                     "WARN_UNRESOLVED_EXTRA_BACKSPLICE", "WARN_UNRESOLVED_LINSPLICE"])
+FLAG_BIT = {n: 1 << k for k, n in enumerate(FLAG_NAMES)}
+FLAGS_NOT_WARN = sum(b for n, b in FLAG_BIT.items() if not n.startswith("WARN"))
+_FLAG_TEXT: Dict[int, str] = {}
 
-    __slots__ = ("flags", "read_flags")
+
+def flag_names(mask: int) -> Tuple[str, ...]:
+    return tuple(n for k, n in enumerate(FLAG_NAMES) if (mask >> k) & 1)
+
+
+def flag_text(mask: int) -> str:
+    t = _FLAG_TEXT.get(mask)
+    if t is None:
+        t = _FLAG_TEXT[mask] = ",".join(flag_names(mask))
+    return t
+
+
+class JunctionInfo(object):
+    """what the fragments' evidence flags add up to for one junction (the flags / read_flags dicts of find_circ.py:541-547,
+    1433-1437): occurrences per flag, and over the distinct fragment names the number without BROKEN_SEGMENTS and the
+    number of (name, non-WARN flag) combinations"""
+
+    __slots__ = ("flags", "n_names", "unbroken", "unwarned")
 
     def __init__(self):
-        self.flags: Dict[str, int] = defaultdict(int)
-        self.read_flags: Dict[str, set] = defaultdict(set)
+        self.flags: Dict[str, int] = {}
+        self.n_names = self.unbroken = self.unwarned = 0
 
 
 BED_HEADER = [
@@ -300,12 +322,17 @@ class Run(object):
         self.idx_base = 0
         self.n_fragments = 0
         self.n_pairs_scanned = 0
-        self.info: Dict[tuple, JunctionInfo] = {}
+        # evidence flags: one event (junction key, fragment-name hash, flag mask) per fragment and junction; summed up per
+        # junction when the tables are written (junction_info)
+        self._ev_py: List[tuple] = []      # python path: (chrom id, start, end, minus, kind, name hash, mask)
+        self.ev_native: List[tuple] = []   # native path: (keys [n, 5] int64, name hashes uint64, masks uint32) per batch
+        self._info_cache = None
         self.reads_out: List[tuple] = []   # (fragment ordinal, qname, seq, qual, [keys], flags)
         self.explicit_idx = False          # native ingest: rows carry their own stream position (fragment ordinal * 64 + k)
         self.cur_seq = 0
         self.cur_k = 0
-        self.multi_out: List[tuple] = []
+        self.multi_out: List[tuple] = []   # (fragment ordinal, name, circ key, lin cons, lin incons, mate cons, mate incons)
+        self.native_multi: List[dict] = []  # the same of the native ingest, arrays per batch
         self.native_reads: List[dict] = []  # spliced reads of the native ingest, one compact batch record each
         self.test_out: List[tuple] = []    # (fragment ordinal, row of test_results.tsv)
         self.t_scan = 0.0
@@ -476,11 +503,56 @@ class Run(object):
             return [self._hit_fields(ties[k]) for k in range(int(ties_off[sp.row]), int(ties_off[sp.row + 1]))]
         return [self._hit_fields(h)]
 
-    def _info(self, key) -> JunctionInfo:
-        inf = self.info.get(key)
-        if inf is None:
-            inf = self.info[key] = JunctionInfo()
-        return inf
+    def _event(self, key, name: str, mask: int):
+        if mask:
+            gid, start, end, strand, kind = key
+            self._ev_py.append((gid, start, end, 1 if strand == "-" else 0, kind, self.eng.hash_bytes(name.encode("latin-1")), mask))
+
+    def events(self):
+        """all evidence events so far as arrays: keys [n, 5] (chrom id, start, end, minus, kind), name hashes, flag masks"""
+        ks = [e[0] for e in self.ev_native]
+        hs = [e[1] for e in self.ev_native]
+        ms = [e[2] for e in self.ev_native]
+        if self._ev_py:
+            ks.append(np.array([e[:5] for e in self._ev_py], dtype=np.int64).reshape(-1, 5))
+            hs.append(np.array([e[5] for e in self._ev_py], dtype=np.uint64))
+            ms.append(np.array([e[6] for e in self._ev_py], dtype=np.uint32))
+        if not ks:
+            return np.zeros((0, 5), np.int64), np.zeros(0, np.uint64), np.zeros(0, np.uint32)
+        return np.concatenate(ks), np.concatenate(hs), np.concatenate(ms)
+
+    def junction_info(self) -> Dict[tuple, JunctionInfo]:
+        """the events summed up per junction.  A fragment name stands for itself through its 64-bit hash, like in the
+        fragment count of the aggregation (collision bound)."""
+        n_ev = len(self._ev_py) + sum(len(e[2]) for e in self.ev_native)
+        if self._info_cache is not None and self._info_cache[0] == n_ev:
+            return self._info_cache[1]
+        K, H, M = self.events()
+        out: Dict[tuple, JunctionInfo] = {}
+        if len(M):
+            order = np.lexsort((H, K[:, 4], K[:, 3], K[:, 2], K[:, 1], K[:, 0]))
+            K, H, M = K[order], H[order], M[order]
+            new_key = np.ones(len(M), dtype=bool)
+            new_key[1:] = (K[1:] != K[:-1]).any(axis=1)
+            new_name = new_key.copy()
+            new_name[1:] |= H[1:] != H[:-1]
+            key_start = np.nonzero(new_key)[0]
+            name_start = np.nonzero(new_name)[0]
+            per_flag = [np.add.reduceat(((M >> k) & 1).astype(np.int64), key_start) for k in range(len(FLAG_NAMES))]
+            name_mask = np.bitwise_or.reduceat(M, name_start)
+            name_key = np.cumsum(new_key)[name_start] - 1  # the junction every distinct name belongs to
+            n_names = np.bincount(name_key, minlength=len(key_start))
+            unbroken = np.bincount(name_key, weights=(name_mask & FLAG_BIT["BROKEN_SEGMENTS"]) == 0, minlength=len(key_start))
+            good = name_mask & np.uint32(FLAGS_NOT_WARN)
+            pop = sum(((good >> k) & 1).astype(np.int64) for k in range(len(FLAG_NAMES)))
+            unwarned = np.bincount(name_key, weights=pop, minlength=len(key_start))
+            for j, k0 in enumerate(key_start.tolist()):
+                gid, start, end, minus, kind = K[k0].tolist()
+                inf = out[(gid, start, end, "-" if minus else "+", kind)] = JunctionInfo()
+                inf.flags = {FLAG_NAMES[k]: int(per_flag[k][j]) for k in range(len(FLAG_NAMES)) if per_flag[k][j]}
+                inf.n_names, inf.unbroken, inf.unwarned = int(n_names[j]), int(unbroken[j]), int(unwarned[j])
+        self._info_cache = (n_ev, out)
+        return out
 
     def _record_hits(self, fr: Fragment, hits, mask, ties_off, ties, host_recs):
         """record_hits (find_circ.py:1276-1439) on the GPU's answers; junction identity = (chrom id, start, end, strand, kind)"""
@@ -523,8 +595,7 @@ class Run(object):
         if len(circ_coords) > 1:
             for key in circ_coords:
                 warns.add("WARN_MULTI_BACKSPLICE")
-                self._info(key).flags["WARN_MULTI_BACKSPLICE"] += 1
-                self._info(key).read_flags[fr.name].add("WARN_MULTI_BACKSPLICE")
+                self._event(key, fr.name, FLAG_BIT["WARN_MULTI_BACKSPLICE"])
                 note(key)
             skip_linear()
             return self._finish_fragment(fr, junctions, warns)
@@ -591,11 +662,8 @@ class Run(object):
             if fr.broken:
                 warns.add("BROKEN_SEGMENTS")
             if (un_cons or un_incons or lin_cons or lin_incons) and opt.multi_events:
-                self.multi_out.append((fr.name, circ_key, lin_cons, lin_incons, un_cons, un_incons))
-            inf = self._info(circ_key)
-            for w in warns:
-                inf.flags[w] += 1
-                inf.read_flags[fr.name].add(w)
+                self.multi_out.append((fr.seq, fr.name, circ_key, lin_cons, lin_incons, un_cons, un_incons))
+            self._event(circ_key, fr.name, sum(FLAG_BIT[w] for w in warns))
         return self._finish_fragment(fr, junctions, warns)
 
     def _finish_fragment(self, fr: Fragment, junctions, warns):
@@ -636,14 +704,15 @@ class Run(object):
         eof = False
         pool = None
 
-        def consume(buf, off, a, n, max_l, n_frag, counters, complex_ranges, plane_stride):
-            """what one fc_ingest_parse call produced: rows -> GPU, fragments it left -> python"""
+        def consume(buf, off, a, n, m, max_l, n_frag, counters, complex_ranges, plane_stride):
+            """what one fc_ingest_parse call produced: rows and fragment records -> GPU + evidence rules, fragments it
+            left -> python"""
             self.n_fragments += n_frag
             for k, name in enumerate(COUNTER_NAMES):
                 if counters[k]:
                     N[name] += counters[k]
             if n:
-                self._native_rows(buf, off, a, n, max_l, ings[0].n_words, plane_stride, ings[0].lib)
+                self._native_batch(buf, off, a, n, m, max_l, ings[0].n_words, plane_stride, ings[0].lib)
             for s0, s1, seq in complex_ranges:
                 self.cur_seq = seq
                 lines = buf[off + s0:off + s1].decode("latin-1").splitlines(True)
@@ -660,17 +729,17 @@ class Run(object):
             off, out = start, []
             while off < end:
                 used = ing.parse(buf, off, final, end)
-                n = int(o.n_rows)
+                n, m = int(o.n_rows), int(o.n_frag_records)
                 cx = [(int(a["cx_start"][k]), int(a["cx_end"][k]), int(a["cx_seq"][k])) for k in range(int(o.n_complex))]
                 if keep:
-                    out.append((off, n, int(o.max_l), int(o.n_fragments), [o.counters[k] for k in range(8)], cx, ing.snapshot(n)))
+                    out.append((off, n, m, int(o.max_l), int(o.n_fragments), [o.counters[k] for k in range(8)], cx, ing.snapshot(n, m)))
                 else:
-                    consume(buf, off, a, n, int(o.max_l), int(o.n_fragments), [o.counters[k] for k in range(8)], cx, ing.cap)
+                    consume(buf, off, a, n, m, int(o.max_l), int(o.n_fragments), [o.counters[k] for k in range(8)], cx, ing.cap)
                 off += used
                 if used == 0:
                     break
-                if n < ing.cap and len(cx) < int(o.cap_complex) and not final:
-                    break  # the rest is an incomplete fragment: wait for the next chunk
+                if n < ing.cap - 1 and len(cx) < int(o.cap_complex) and not final:
+                    break  # (a fragment has up to two rows) the rest is an incomplete fragment: wait for the next chunk
             return out, off
 
         try:
@@ -702,8 +771,8 @@ class Run(object):
                     off = 0
                     for k, job in enumerate(jobs):
                         results, end_off = job.result()
-                        for (o0, n, max_l, n_frag, counters, cx, arrays) in results:
-                            consume(buf, o0, arrays, n, max_l, n_frag, counters, cx, n)
+                        for (o0, n, m, max_l, n_frag, counters, cx, arrays) in results:
+                            consume(buf, o0, arrays, n, m, max_l, n_frag, counters, cx, n)
                         off = end_off
                     ings[0].set_position(next_ord + (len(cuts) - 1) * stride, False)
                 carry = buf[off:]
@@ -716,43 +785,118 @@ class Run(object):
             for ing in ings:
                 ing.close()
 
-    def _native_rows(self, buf, off, a, n, max_l, n_words, plane_stride, lib):
-        """scan + record the rows the native ingest produced (single-span fragments: the evidence logic collapses to
-        'first tie is recorded', find_circ.py:1299-1317, 1351-1378), fully vectorised"""
-        N = self.N
-        idx = (a["frag_seq"][:n].astype(np.uint64) * np.uint64(64))
+    def _native_batch(self, buf, off, a, n, m, max_l, n_words, plane_stride, lib):
+        """scan + record the n rows of m fragments the native ingest produced, then the evidence rules of record_hits
+        (find_circ.py:1276-1439) for all fragments at once: with at most two spans per fragment (back-splices first) every
+        rule is a comparison between the fragment's columns -- same outcome as _record_hits(), which stays the reading
+        of the reference for everything else"""
+        from .ingest import FR_BROKEN, FR_OTHER_CHROM, FR_TWO_MATES, FR_UNSPLICED
+
+        N, opt, B = self.N, self.opt, FLAG_BIT
+        idx = a["frag_seq"][:n].astype(np.uint64) * np.uint64(64) + a["idx_k"][:n].astype(np.uint64)
         t0 = time.perf_counter()
         hits = self.eng.batch_host_planes(n, a["chrom"], a["a_start"], a["b_end"], a["l"], a["flags"], a["rlo"], a["rhi"], a["rn"],
                                           n_words, plane_stride, max(max_l, 0), a["wden"], a["q_a"], a["q_b"], a["read_hash"],
                                           a["qname_hash"], idx=idx, emit=True)
         self.t_scan += time.perf_counter() - t0
         self.n_pairs_scanned += n
-        nh = (hits["w2"] & 0xFFFF) > 0
-        circ = (a["flags"][:n] & 1).astype(bool)
-        for key, cnt in (("circ_spliced", np.count_nonzero(nh & circ)), ("circ_no_bp", np.count_nonzero(~nh & circ)),
-                         ("lin_spliced", np.count_nonzero(nh & ~circ)), ("lin_no_bp", np.count_nonzero(~nh & ~circ))):
+        has = (hits["w2"] & 0xFFFF) > 0
+        state, kind, ff = a["f_state"][:m], a["f_kind"][:m], a["f_flags"][:m]
+        row0 = a["f_row0"][:m].astype(np.int64)
+        two = a["f_nsp"][:m] == 2
+        queued = [(state & 1) > 0, (state & 2) > 0]
+        row = [np.where(queued[0], row0, 0), np.where(queued[1], row0 + (state & 1), 0)]
+        circ = [(kind & 1) > 0, (kind & 2) > 0]
+        lin = [~circ[0], two & ~circ[1]]
+        hit = [queued[j] & has[row[j]] for j in (0, 1)]
+        count = np.count_nonzero
+        for key, cnt in (("circ_spliced", sum(count(circ[j] & hit[j]) for j in (0, 1))),
+                         ("circ_no_bp", sum(count(circ[j] & queued[j] & ~hit[j]) for j in (0, 1))),
+                         ("lin_spliced", sum(count(lin[j] & hit[j]) for j in (0, 1))),
+                         ("lin_no_bp", sum(count(lin[j] & queued[j] & ~hit[j]) for j in (0, 1)))):
             if cnt:  # the reference's counter dict only holds keys that were incremented (find_circ.py:1146)
                 N[key] += float(cnt)
-        rows = np.nonzero(nh)[0]
-        if len(rows) == 0:
+        if not (hit[0].any() or hit[1].any()):
             return
-        # name, sequence and qualities of the spliced reads go into one compact blob (C++); the FASTQ records are formatted
-        # from it when the junction names are known (reads_text)
-        m = len(rows)
-        off3 = np.empty((m, 3), dtype=np.int64)
-        len3 = np.empty((m, 3), dtype=np.int32)
-        for k, f in enumerate(("qname", "seq", "qual")):
-            off3[:, k] = a[f + "_off"][rows] + off
-            len3[:, k] = a[f + "_len"][rows]
-        blob = np.empty(int(np.maximum(len3, 0).sum()), dtype=np.uint8)
+        # junction of every span: chrom id, start, end, minus, kind
+        chrom = a["chrom"][:n].astype(np.int64)
+        h_start, h_end, h_minus = hits["start"].astype(np.int64), hits["end"].astype(np.int64), (hits["w3"] & 1).astype(np.int64)
+        key = [np.stack([chrom[row[j]], h_start[row[j]], h_end[row[j]], h_minus[row[j]], lin[j].astype(np.int64)], axis=1) for j in (0, 1)]
+        ch = [circ[j] & hit[j] for j in (0, 1)]
+        both = ch[0] & ch[1]
+        multi = both & (key[0] != key[1]).any(axis=1)     # two different back-splices (find_circ.py:1319-1329)
+        circ_any = ch[0] | ch[1]
+        single = circ_any & ~multi
+        ck = np.where(ch[1][:, None], key[1], key[0])      # the (last) back-splice of the fragment
+        cs, ce = ck[:, 1], ck[:, 2]
+        W = np.zeros(m, dtype=np.uint32)
+
+        def flag(cond, name):
+            W[cond] |= np.uint32(B[name])
+
+        flag((circ[0] & queued[0] & ~hit[0]) | (circ[1] & queued[1] & ~hit[1]), "WARN_UNRESOLVED_EXTRA_BACKSPLICE")
+        flag(single & circ[0] & circ[1], "SUPPORT_CLOSURE")
+        lin_ev, lin_out = [], []
+        for j in (0, 1):
+            flag(lin[j] & queued[j] & ~hit[j], "WARN_UNRESOLVED_LINSPLICE")
+            ev = lin[j] & hit[j] & single
+            outside = (key[j][:, 1] <= cs) | (key[j][:, 2] >= ce)
+            flag(ev & outside, "WARN_OUTSIDE_SPLICE_JUNCTION")
+            flag(ev & ~outside, "SUPPORT_INSIDE_SPLICE_JUNCTION")
+            lin_ev.append(ev)
+            lin_out.append(outside)
+        un = ((ff & FR_UNSPLICED) > 0) & single
+        un_other = un & ((ff & FR_OTHER_CHROM) > 0)
+        un_pos, un_aend = a["f_un_pos"][:m].astype(np.int64), a["f_un_aend"][:m].astype(np.int64)
+        un_outside = un & ~un_other & ((un_pos + opt.asize <= cs) | (un_aend - opt.asize >= ce))
+        flag(un_other, "WARN_OTHER_CHROM_MATE")
+        flag(un_outside, "WARN_OUTSIDE_MATE")
+        flag(un & ~un_other & ~un_outside, "SUPPORT_INSIDE_MATE")
+        flag(single & ((ff & FR_BROKEN) > 0), "BROKEN_SEGMENTS")
+        W[multi] = B["WARN_MULTI_BACKSPLICE"]
+        name_hash = a["qname_hash"][:n][row0]
+        # ---- per-junction flags (find_circ.py:1325-1327, 1433-1437)
+        ev1 = np.nonzero(single & (W != 0))[0]
+        evm = np.nonzero(multi)[0]
+        if len(ev1) or len(evm):
+            self.ev_native.append((np.concatenate([ck[ev1], key[0][evm], key[1][evm]]),
+                                   np.concatenate([name_hash[ev1], name_hash[evm], name_hash[evm]]),
+                                   np.concatenate([W[ev1], W[evm], W[evm]])))
+        txt_off = a["f_txt_off"][:6 * m].reshape(m, 2, 3)
+        txt_len = a["f_txt_len"][:6 * m].reshape(m, 2, 3)
         base = C.cast(C.c_char_p(buf), C.c_void_p).value
-        got = lib.fc_text_gather(base, m, off3.ctypes.data, len3.ctypes.data, blob.ctypes.data)
-        if got != len(blob):
-            raise RuntimeError("fc_text_gather failed (%d)" % got)
-        self.native_reads.append(dict(
-            seqs=a["frag_seq"][rows].copy(), blob=blob, len3=len3, chrom=a["chrom"][rows].astype(np.int64),
-            start=hits["start"][rows].astype(np.int64), end=hits["end"][rows].astype(np.int64),
-            minus=(hits["w3"][rows] & 1).astype(np.int64), kind=(1 - (a["flags"][rows] & 1)).astype(np.int64)))
+
+        def gather(off3, len3):
+            blob = np.empty(int(np.maximum(len3, 0).sum()), dtype=np.uint8)
+            got = lib.fc_text_gather(base, len(len3), off3.ctypes.data, len3.ctypes.data, blob.ctypes.data)
+            if got != len(blob):
+                raise RuntimeError("fc_text_gather failed (%d)" % got)
+            return blob
+
+        # ---- multi-event rows (find_circ.py:1429-1431)
+        if opt.multi_events:
+            me = np.nonzero(lin_ev[0] | lin_ev[1] | un)[0]
+            if len(me):
+                off3 = np.ascontiguousarray(txt_off[me, 0] + off)
+                len3 = np.ascontiguousarray(txt_len[me, 0])
+                len3[:, 1:] = -1  # (the name only)
+                self.native_multi.append(dict(
+                    seqs=a["f_seq"][:m][me].copy(), names=gather(off3, len3), name_len=len3[:, 0].copy(), ck=ck[me],
+                    lin=[(lin_ev[j][me], lin_out[j][me], key[j][me]) for j in (0, 1)],
+                    un=(un[me], (un_other | un_outside)[me], a["f_un_tid"][:m][me].copy(), un_pos[me], un_aend[me])))
+        # ---- the reads of every fragment with a junction (find_circ.py:1439, 1442-1447): name, sequence and qualities of
+        # both mates go into one compact blob (C++); the FASTQ records are formatted from it when the junction names are
+        # known (reads_text)
+        fr = np.nonzero(hit[0] | hit[1])[0]
+        first = np.where(hit[0][fr, None], key[0][fr], key[1][fr])
+        second = np.where((hit[0] & hit[1])[fr, None] & (key[0][fr] != key[1][fr]).any(axis=1)[:, None], key[1][fr], -1)
+        n_mates = 1 + ((ff[fr] & FR_TWO_MATES) > 0)
+        who = np.repeat(np.arange(len(fr)), n_mates)
+        mate = np.arange(len(who)) - np.repeat(np.cumsum(n_mates) - n_mates, n_mates)
+        off3 = np.ascontiguousarray(txt_off[fr[who], mate] + off)
+        len3 = np.ascontiguousarray(txt_len[fr[who], mate])
+        self.native_reads.append(dict(seqs=a["f_seq"][:m][fr[who]].copy(), blob=gather(off3, len3), len3=len3,
+                                      k0=first[who], k1=second[who], mask=W[fr[who]].astype(np.int64)))
 
     # ------------------------------------------------------------------ outputs
     def finalize(self, dist=None, torch_dev=None):
@@ -814,12 +958,10 @@ class Run(object):
             cats.append("SHORT")
         elif span > opt.huge_threshold:
             cats.append("HUGE")
-        if inf is not None and inf.read_flags:
-            unbroken = sum(1 for fl in inf.read_flags.values() if "BROKEN_SEGMENTS" not in fl)
-            unwarned = sum(1 for fl in inf.read_flags.values() for w in fl if not w.startswith("WARN"))
-            if not unbroken:
+        if inf is not None and inf.n_names:
+            if not inf.unbroken:
                 cats.append("WARN_ALWAYS_BROKEN")
-            if not unwarned:
+            if not inf.unwarned:
                 cats.append("WARN_ALWAYS_WARN")
         return cats
 
@@ -828,6 +970,7 @@ class Run(object):
         opt = self.opt
         names = self._names(self.junctions)
         cn = self.eng.chrom_names
+        info = self.junction_info()
         lines = ["#" + "\t".join(BED_HEADER) + "\n"]
         for r in self.junctions:
             sk = int(r["sk"])
@@ -845,7 +988,7 @@ class Run(object):
             start, end = int(r["start"]), int(r["end"])
             strand = "-" if sk & 1 else "+"
             key = (int(r["chrom"]), start, end, strand, kind)
-            inf = self.info.get(key)
+            inf = info.get(key)
             if inf is not None and inf.flags:
                 flags = sorted(inf.flags)
                 fcounts = [inf.flags[f] for f in flags]
@@ -886,8 +1029,13 @@ class Run(object):
         py_seqs = np.array([e[0] for e in self.reads_out], dtype=np.int64)
         pieces, done = [], 0
         for b in self.native_reads:
-            uniq, inverse = _unique_rows(np.stack([b["chrom"], b["start"], b["end"], b["minus"], b["kind"]], axis=1))
-            jn = [names[(int(c), int(s0), int(e0), "-" if mi else "+", int(kd))].encode("latin-1") for c, s0, e0, mi, kd in uniq.tolist()]
+            uniq, inverse = _unique_rows(np.concatenate([b["k0"], b["k1"], b["mask"][:, None]], axis=1))
+            jn = []
+            for u in uniq.tolist():
+                nm = names[(u[0], u[1], u[2], "-" if u[3] else "+", u[4])]
+                if u[5] >= 0:
+                    nm = ",".join(sorted((nm, names[(u[5], u[6], u[7], "-" if u[8] else "+", u[9])])))
+                jn.append((nm + " " + flag_text(u[10])).encode("latin-1"))
             name_len = np.array([len(x) for x in jn], dtype=np.int32)
             name_off = np.zeros(len(jn), dtype=np.int64)
             name_off[1:] = np.cumsum(name_len[:-1])
@@ -916,12 +1064,36 @@ class Run(object):
         pieces.extend(out[done:])
         return "".join(pieces)
 
+    def _multi_rows(self):
+        """python-path and native rows together, in stream order"""
+        rows = list(self.multi_out)
+        cn = self.eng.chrom_names
+        for b in self.native_multi:
+            ends = np.cumsum(b["name_len"])
+            text = b["names"].tobytes().decode("latin-1")
+            ck = b["ck"].tolist()
+            lin = [(ev.tolist(), out.tolist(), key.tolist()) for ev, out, key in b["lin"]]
+            un_ev, un_out, un_tid, un_pos, un_aend = (x.tolist() for x in b["un"])
+            for k, seq in enumerate(b["seqs"].tolist()):
+                sets = (set(), set(), set(), set())  # lin cons, lin incons, mate cons, mate incons
+                for ev, out, key in lin:
+                    if ev[k]:
+                        g, s0, e0, mi, _ = key[k]
+                        sets[1 if out[k] else 0].add((cn[g], s0, e0, "-" if mi else "+"))
+                if un_ev[k]:
+                    sets[3 if un_out[k] else 2].add((self.sam_chroms[un_tid[k]], un_pos[k], un_aend[k], "*"))
+                g, s0, e0, mi, kd = ck[k]
+                rows.append((seq, text[int(ends[k]) - int(b["name_len"][k]):int(ends[k])], (g, s0, e0, "-" if mi else "+", kd)) + sets)
+        if self.native_multi or self.explicit_idx:
+            rows.sort(key=lambda e: e[0])
+        return rows
+
     def multi_text(self) -> str:
         """MultiEventRecorder (find_circ.py:733-763)"""
         names = self._names(self.junctions)
         cn = self.eng.chrom_names
         lines = ["#" + "\t".join(MULTI_HEADER) + "\n"]
-        for frag, ck, lin_cons, lin_incons, un_cons, un_incons in self.multi_out:
+        for _, frag, ck, lin_cons, lin_incons, un_cons, un_incons in self._multi_rows():
             score = len(lin_cons) - 10 * len(lin_incons) + len(un_cons) - 10 * len(un_incons)
             gid, start, end, strand, _ = ck
             cols = [cn[gid], str(start), str(end), "ME:" + names[ck], str(score), strand, frag]

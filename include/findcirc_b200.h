@@ -369,15 +369,25 @@ int fc_p2p_set_timeout(fc_ctx* ctx, double seconds);
 int fc_agg_reset_async(fc_ctx* ctx, void* stream);
 
 /* ------------------------------------------------------------------ native SAM ingest (host code)
- * Replaces the pysam record loop, MateSegments and adjacent_segment_pairs (find_circ.py:461-469, 976-1140, 1450-1486) for
- * fragments that consist of one mate with at most one supplementary record; other fragments are returned as byte ranges
- * for the python implementation of the same logic.  Rows are ready for fc_batch_host_planes. */
+ * Replaces the pysam record loop, MateSegments, adjacent_segment_pairs and the head of record_hits (find_circ.py:461-469,
+ * 976-1140, 1450-1486, 1492-1526, 1560-1574) for fragments of one or two mates whose segments form at most two anchor
+ * pairs ("spans") in total -- single-end two-segment reads, mate pairs with one or both mates spliced, a mate with three
+ * segments -- and for every fragment without a span (counters only).  Other fragments (three or more spans, a third mate,
+ * --no-linear with back-splice and linear spans in one fragment, records the parser cannot interpret) come back as byte
+ * ranges for the python implementation of the same logic.  Rows are ready for fc_batch_host_planes; the rows of one
+ * fragment are adjacent (back-splice spans first, find_circ.py:1299, 1351) and its fragment record tells the host what the
+ * evidence rules of record_hits (find_circ.py:1276-1439) need besides the scan's answers. */
 typedef struct fc_ingest fc_ingest;
 typedef struct fc_ingest_params {
   int32_t asize, margin, min_uniq_qual, nolinear;
 } fc_ingest_params;
+/* fragment record flags */
+#define FC_FR_UNSPLICED 1u   /* the fragment has an unspliced mate (un_tid / un_pos / un_aend) */
+#define FC_FR_OTHER_CHROM 2u /* ... which lies on another chromosome than the first back-splice span's read */
+#define FC_FR_BROKEN 4u      /* segments on other chromosomes / strands next to a span that leaves a read end uncovered */
+#define FC_FR_TWO_MATES 8u
 typedef struct fc_ingest_out {
-  int64_t cap;          /* capacity of the per-row arrays (also the stride of the plane arrays) */
+  int64_t cap;          /* capacity of the per-row and per-fragment arrays (also the stride of the plane arrays) */
   int32_t* chrom;       /* genome chromosome id */
   int32_t* a_start;
   int32_t* b_end;
@@ -393,18 +403,25 @@ typedef struct fc_ingest_out {
   int16_t* q_b;
   uint64_t* read_hash;
   uint64_t* qname_hash;
-  int64_t* frag_seq;    /* ordinal of the fragment in the stream */
-  int64_t* qname_off;   /* byte offsets into the parsed text (for the spliced-reads output) */
-  int32_t* qname_len;
-  int64_t* seq_off;
-  int32_t* seq_len;
-  int64_t* qual_off;
-  int32_t* qual_len;    /* -1: '*' */
+  int64_t* frag_seq;    /* ordinal of the row's fragment in the stream */
+  uint8_t* idx_k;       /* the row's place among the fragment's rows: stream position = frag_seq * 64 + idx_k */
+  /* one record per fragment that has rows */
+  int64_t* f_seq;       /* ordinal of the fragment */
+  int32_t* f_row0;      /* its first row */
+  uint8_t* f_nsp;       /* spans: 1 or 2, back-splices first */
+  uint8_t* f_kind;      /* bit j: span j is a back-splice */
+  uint8_t* f_state;     /* bit j: span j has a row (its anchors are unique enough) */
+  uint8_t* f_flags;     /* FC_FR_* */
+  int32_t* f_un_tid;    /* the unspliced mate: SAM reference index, start, end */
+  int32_t* f_un_pos;
+  int32_t* f_un_aend;
+  int64_t* f_txt_off;   /* [cap][2 mates][name, sequence, qualities]: byte offsets into the parsed text */
+  int32_t* f_txt_len;   /* -1: '*', -2: no second mate */
   int64_t cap_complex;
   int64_t* cx_start;    /* byte ranges of fragments left to the python path */
   int64_t* cx_end;
   int64_t* cx_seq;
-  int64_t n_rows, n_complex, n_fragments; /* out */
+  int64_t n_rows, n_frag_records, n_complex, n_fragments; /* out */
   double counters[8];   /* out: total_mates, unmapped_reads, unspliced_mates, seg_too_short_skip, circ_junc_not_unique, lin_junc_not_unique */
 } fc_ingest_out;
 fc_ingest* fc_ingest_create(const fc_ingest_params* p, int32_t n_names, const char* const* names, const int32_t* tid2gid);
@@ -431,9 +448,10 @@ int64_t fc_bam_read_text(fc_bam* b, char* out, int64_t cap);
 
 /* Spliced reads of the native ingest (write_read, find_circ.py:1442-1447): fc_text_gather copies n x 3 substrings
  * (name, sequence, qualities; off/len row major, len < 0 = absent) of a text buffer back to back into `out` and returns
- * the bytes written; fc_fastq_format turns such a blob into FASTQ records "@<name> <junction> \n<seq>\n+<name> <junction>
- * \n<qual>\n" once the junction names are known (name_idx[i] selects names[name_off[.] .. +name_len[.]]), fills rec_off[0..n]
- * with the offset of every record and returns the bytes written, or the bytes needed when out_cap is too small. */
+ * the bytes written; fc_fastq_format turns such a blob into FASTQ records "@<name> <tail>\n<seq>\n+<name> <tail>\n<qual>\n"
+ * once the junction names are known (tail = "<junction names> <flags>"; name_idx[i] selects names[name_off[.] ..
+ * +name_len[.]]), fills rec_off[0..n] with the offset of every record and returns the bytes written, or the bytes needed
+ * when out_cap is too small. */
 int64_t fc_text_gather(const char* buf, int64_t n, const int64_t* off, const int32_t* len, char* out);
 int64_t fc_fastq_format(const char* blob, int64_t n, const int32_t* len, const int32_t* name_idx, const char* names,
                         const int64_t* name_off, const int32_t* name_len, char* out, int64_t out_cap, int64_t* rec_off);
