@@ -300,8 +300,10 @@ constexpr long long FUSED_MAX_RECORDS = 1ll << 28;  // keeps 8 * n_spanned and t
 constexpr uint32_t SK_NAME_KNOWN = FC_SK_NAME_KNOWN, SK_NAME_DUP = FC_SK_NAME_DUP;  // the emitter already knows whether the fragment is new to the junction
 
 // counters (32-bit words at counters + 8): [0] junctions listed, [1] records with another denominator,
-// [2] list overflow / records outside a declared idx range, [3] junctions
-enum { FC_N_ALLOC = 0, FC_N_OTHER = 1, FC_N_OVERFLOW = 2, FC_N_JUNC = 3 };
+// [2] list overflow / records outside a declared idx range, [3] junctions, [4] set entries that found their partition
+// full, [5] partitions whose shared-memory set ran full (either: the call is repeated with the global set)
+enum { FC_N_ALLOC = 0, FC_N_OTHER = 1, FC_N_OVERFLOW = 2, FC_N_JUNC = 3, FC_N_PART_OVF = 4, FC_N_SET_FULL = 5 };
+constexpr int FC_N_CTR = 6;
 
 __device__ __forceinline__ unsigned long long ext_pack(int q_left, int q_right, unsigned dist, unsigned ov, unsigned n_hits) {
   const unsigned lo = (unsigned)(q_left + 32768) | ((unsigned)(q_right + 32768) << 16);
@@ -315,11 +317,18 @@ __device__ __forceinline__ unsigned long long ext_max(unsigned long long a, unsi
   const unsigned hi = (__vmaxu2(ahi, bhi) & 0xFFFF0000u) | (__vmaxu4(ahi, bhi) & 0x0000FFFFu);
   return (unsigned long long)lo | ((unsigned long long)hi << 32);
 }
+// does x beat cur in any field?  (the usual answer is no; ext_max is only worth computing after a yes)
+__device__ __forceinline__ bool ext_improves(unsigned long long cur, unsigned long long x) {
+  const unsigned clo = (unsigned)cur, xlo = (unsigned)x, chi = (unsigned)(cur >> 32), xhi = (unsigned)(x >> 32);
+  return (xlo & 0xFFFFu) > (clo & 0xFFFFu) || (xlo >> 16) > (clo >> 16) || (xhi & 0xFFu) > (chi & 0xFFu) ||
+         ((xhi >> 8) & 0xFFu) > ((chi >> 8) & 0xFFu) || (xhi >> 16) > (chi >> 16);
+}
 // kf / x: identity + first position and extrema of one record (or of one shared-memory entry); cur_kf / cur_x: what a
 // (possibly stale: maxima only grow, so an old value can only cause a needless attempt) look at the slot showed
 __device__ __forceinline__ void extrema_to_global(JSlot* s, unsigned long long kf, unsigned long long x, unsigned long long cur_kf,
                                                   unsigned long long cur_x) {
   if (kf > cur_kf) atomicMax(&s->kf, kf);  // (the identity bits are the same for every record of the junction)
+  if (!ext_improves(cur_x, x)) return;
   unsigned long long want = ext_max(cur_x, x);
   while (want != cur_x) {
     const unsigned long long old = atomicCAS(&s->ext, cur_x, want);
@@ -399,6 +408,69 @@ __device__ __forceinline__ void set_insert2(U128* table, unsigned long long mask
   }
 }
 
+// ---- Partitioned distinct counts (inputs whose set would not fit L2) -------------------------------------------------
+// A global hash set costs every record one random DRAM sector (and the part sustains only ~30 G of those per second).
+// Instead, pass 1 turns every (read, junction) -- and every (fragment name, junction) that the scan kernel could not
+// settle -- into a 16-byte entry {64-bit key, junction | flags} and appends it to one of n_parts partitions chosen by
+// an independent hash of the same pair; pass 2 (distinct_parts_kernel) walks each partition with an exact set in SHARED
+// memory and adds what it finds to the junctions' counters.  Equal pairs meet in one partition, so the counts are the
+// ones of the global set; the distinct elements spread evenly whatever the popularity of the junctions is, and the
+// traffic is one sequential 16-byte write and read per record.  Two pairs are taken for equal when their 64-bit keys
+// AND partitions agree: ~2^-64 per pair of elements of one partition (DESIGN.md section 2 has the bound per run).
+// Copies of an element (the same read sequence on a popular junction comes thousands of times) would crowd its
+// partition: each CTA of pass 1 keeps the keys it sent last in a small direct-mapped cache and counts a hit as the
+// duplicate it is.
+struct PartView {
+  uint4* ent;           // n_parts x pcap entries
+  unsigned int* cur;    // fill count of partition p at cur[8 * p] (own sector each); all zero between calls
+  unsigned int n_parts;
+  unsigned int pcap;
+};
+constexpr unsigned PART_NAME = 1u << 31, PART_PALIN = 1u << 30, PART_JID = (1u << 30) - 1u;  // (slot numbers stay below 2^30: FUSED_MAX_RECORDS)
+constexpr int RECENT_SETS = 2048;     // per-CTA cache of keys sent before: 2 ways x 8 bytes per set (32 KB, dynamic shared memory)
+constexpr int PSET_ENTRIES = 8192;    // shared-memory set of pass 2 (64 KB: three CTAs per SM)
+constexpr int PSET_TARGET = 2600;     // elements per partition the host aims at (load 0.32; 0.64 when every name goes through it too)
+constexpr int PART_THREADS = 512;
+
+// key (never 0) and partition of the pair (value, tag).  The value is a 64-bit hash already, so x = v ^ t * odd is a
+// bijection of v for every tag and as uniform as v is; the partition mixes x with the tag once more, so two pairs with
+// equal keys and different tags (which need v' = v ^ const, 2^-64 for hashes) still part ways in all but 1/n_parts cases.
+__device__ __forceinline__ unsigned long long part_key(unsigned long long v, unsigned long long t, unsigned int n_parts, unsigned int& part) {
+  const unsigned long long x = v ^ (t * 0x9E3779B97F4A7C15ULL);
+  unsigned int m = (unsigned int)(x >> 32) * 0x85EBCA6Bu ^ (unsigned int)x * 0xC2B2AE35u ^ ((unsigned int)t + (unsigned int)(t >> 32)) * 0x27D4EB2Fu;
+  m ^= m >> 16;
+  m *= 0x85EBCA6Bu;
+  m ^= m >> 13;
+  m *= 0xC2B2AE35u;
+  m ^= m >> 16;
+  part = __umulhi(m, n_parts);
+  return x ? x : 1ull;
+}
+// claim a place in the key's partition unless this CTA has sent the same key before and still remembers it (returns
+// false: a repeat).  The memory is a two-way cache with a protected way: a key enters way 1 and moves to way 0 when it comes
+// again, so the few thousand keys that make up most of the repeats are not pushed out by the stream of keys that come
+// once.  Every value in the cache is a key that was sent, whatever the races between the lanes do to it.
+__device__ __forceinline__ bool part_claim(const PartView& pv, unsigned long long* recent, unsigned long long k, unsigned int part, unsigned int& pos) {
+  volatile unsigned long long* rc = recent + 2u * ((unsigned int)(k >> 20) & (RECENT_SETS - 1));
+  const unsigned long long w0 = rc[0], w1 = rc[1];
+  if (w0 == k) return false;
+  if (w1 == k) {
+    rc[0] = k;
+    rc[1] = w0;
+    return false;
+  }
+  rc[1] = k;
+  pos = atomicAdd(pv.cur + 8u * part, 1u);  // (nobody looks at the answer before part_store: the round trip stays off the critical path)
+  return true;
+}
+__device__ __forceinline__ void part_store(const PartView& pv, unsigned long long k, unsigned int part, unsigned int pos, unsigned int word,
+                                           unsigned int* ctr) {
+  if (pos < pv.pcap)
+    pv.ent[(size_t)part * pv.pcap + pos] = make_uint4((unsigned int)k, (unsigned int)(k >> 32), word, 0u);
+  else
+    atomicAdd(&ctr[FC_N_PART_OVF], 1u);
+}
+
 // A junction that collects a few per cent of all reads (expression is heavy-tailed) would otherwise put all of its
 // updates on one L2 sector, and an L2 slice retires about one request per clock for one sector (measured: with a
 // Zipf(1) popularity the direct version spends 4x the time of the uniform case).  So the lanes of a warp that share a
@@ -409,12 +481,14 @@ __device__ __forceinline__ void set_insert2(U128* table, unsigned long long mask
 // junction's slot), so the warps hide each other's memory round trips.  Measured on the B200 (config 3, 44 M records):
 // without the table 9.96 ms, with it 3.6 ms; a count-min sketch as a second admission rule changed nothing.
 constexpr int ACC_THREADS = 512;
-// Measured on the B200 (configs 3 and 5): 3 CTAs per SM (40 registers, spills), chunks of 16 instead of 30 tiles, 8 instead
-// of 2 probes of the shared-memory table and an L2 prefetch of the next tile's records all change the kernel time by < 3 %:
-// it is bound by the rate of random DRAM sector accesses (~32 G/s on this part), not by latency or issue slots.
-// Also tried: two L2-resident bit filters in front of the read set so that only (read, junction) pairs whose bit is hit
-// twice reach the exact set (a second pass) -- the first pass drops to 1.9-3.3 ms at config 3, but reads repeat so often in
-// popular junctions that the second pass handles most records anyway: no gain overall.
+// History of what was measured on the B200 (configs 3 and 5) while the kernel still used one global set for every input:
+// 3 CTAs per SM (40 registers, spills), chunks of 16 instead of 30 tiles, 8 instead of 2 probes of the shared-memory table
+// and an L2 prefetch of the next tile's records all changed the kernel time by < 3 %; two L2-resident bit filters in front
+// of the read set (only pairs whose bit is hit twice reach the exact set in a second pass) gained nothing because reads
+// repeat so often in popular junctions.  With the set partitioned (above) the kernel is a chain of three dependent
+// round trips per record -- record, junction slot, partition cursor -- and what pays is taking them off the critical
+// path costs more (registers, shared-memory traffic) than it hides: a three-deep software pipeline over the tiles of a chunk
+// (record, then slot sector one tile ahead) measured 6 % slower than the plain loop below.
 #define FC_ACC_MIN_CTAS 2
 #define FC_HOT_PROBES 2
 constexpr int ACC_MAX_TILES = 30;  // tiles of ACC_THREADS records per chunk (between two flushes of the shared-memory table)
@@ -425,7 +499,7 @@ struct HotTable {
   unsigned int c0[HOT_ENTRIES];     // n_spanned | 8 * weight << 14 (a chunk holds fewer than 16384 records of weight <= 1)
   unsigned int c1[HOT_ENTRIES];     // names seen before | 8 * non-bridge weight << 14
   unsigned int c2[HOT_ENTRIES];
-  unsigned int qmax_l[HOT_ENTRIES], qmax_r[HOT_ENTRIES], inv_dist[HOT_ENTRIES], inv_ov[HOT_ENTRIES], inv_nh[HOT_ENTRIES];
+  unsigned long long ext[HOT_ENTRIES];        // packed extrema, as JSlot.ext
   unsigned long long first_inv[HOT_ENTRIES];  // identity | first position, as JSlot.kf
 };
 static_assert(ACC_MAX_TILES * ACC_THREADS < (1 << 14) && ACC_MAX_TILES * ACC_THREADS * 8 < (1 << 18), "hot-table fields");
@@ -453,13 +527,42 @@ __device__ __forceinline__ void ld_sector(const JSlot* s, unsigned long long (&v
   asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(s));
 }
 
+// where record i of the call lives (several slices: the concatenation of what the source ranks sent)
+__device__ __forceinline__ const uint4* rec_ptr(const RecSrc& src, int64_t i) {
+  int64_t rec_at = i;
+  if (src.n_slices > 1) {
+    int64_t before = 0;
+#pragma unroll 1
+    for (int sl = 0; sl < src.n_slices; ++sl) {
+      const int64_t c = (int64_t)min(src.counts[sl], src.slice_cap);
+      if (i >= before && i < before + c) rec_at = (int64_t)sl * (int64_t)src.slice_cap + (i - before);
+      before += c;
+    }
+  }
+  return reinterpret_cast<const uint4*>(src.base + rec_at);
+}
+// first word of a record (chrom, start, end, sk) -> the slot's key words and where its probe sequence starts
+__device__ __forceinline__ void key_of(const uint4& r0, unsigned long long& klo, unsigned long long& kid) {
+  klo = (unsigned long long)r0.y | ((unsigned long long)r0.z << 32);
+  kid = KEY_OCC | ((unsigned long long)(r0.x & ((1u << CHROM_BITS) - 1u)) << (FIRST_BITS + 2)) | ((unsigned long long)(r0.w & 3u) << FIRST_BITS);
+}
+__device__ __forceinline__ unsigned long long slot_of(unsigned long long klo, unsigned long long kid, unsigned long long kmask) {
+  return fc_mix64(klo ^ ((kid >> FIRST_BITS) * 0x9E3779B97F4A7C15ULL)) & kmask;
+}
+
+// SETS: 0 = one global set (inputs whose set fits L2), 1 = partitioned (PartView; distinct_parts_kernel follows).
+template <int SETS>
 __global__ void __launch_bounds__(ACC_THREADS, FC_ACC_MIN_CTAS) fused_accumulate_kernel(RecSrc src, int chunk_tiles, int prefetch, unsigned long long idx_base, JSlot* __restrict__ slots,
                                                                   unsigned long long kmask, U128* __restrict__ sets,
-                                                                  unsigned long long smask, unsigned int* __restrict__ list,
+                                                                  unsigned long long smask, PartView pv, unsigned int* __restrict__ list,
                                                                   unsigned int lcap, unsigned int* __restrict__ ctr,
                                                                   uint4* __restrict__ flag4, int64_t n_flag4,
                                                                   uint32_t* __restrict__ tile_count, int64_t n_tiles) {
   __shared__ HotTable hot;
+  extern __shared__ unsigned long long recent[];  // SETS == 1: 2 * RECENT_SETS words
+  if (SETS == 1) {
+    for (int e = threadIdx.x; e < 2 * RECENT_SETS; e += ACC_THREADS) recent[e] = 0ull;  // (the first barrier below orders this)
+  }
   // the rank flags and tile counters of the finish pass are cleared on the way
   {
     const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gs = (int64_t)gridDim.x * blockDim.x;
@@ -472,35 +575,25 @@ __global__ void __launch_bounds__(ACC_THREADS, FC_ACC_MIN_CTAS) fused_accumulate
 #pragma unroll 1
   for (int sl = 0; sl < src.n_slices; ++sl) n += (int64_t)min(src.counts[sl], src.slice_cap);
   if (src.total_out && blockIdx.x == 0 && threadIdx.x == 0) *src.total_out = (unsigned long long)n;
-  const fc_jrec* __restrict__ recs = src.base;
   const int64_t chunk_recs = (int64_t)chunk_tiles * ACC_THREADS;
   const unsigned lane = threadIdx.x & 31;
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
 
 #pragma unroll 1
   for (int64_t c0 = (int64_t)blockIdx.x * chunk_recs; c0 < n; c0 += (int64_t)gridDim.x * chunk_recs) {
     for (int e = threadIdx.x; e < HOT_ENTRIES; e += ACC_THREADS) {
       hot.tag[e] = hot.c0[e] = hot.c1[e] = hot.c2[e] = 0u;
-      hot.qmax_l[e] = hot.qmax_r[e] = hot.inv_dist[e] = hot.inv_ov[e] = hot.inv_nh[e] = 0u;
+      hot.ext[e] = 0ull;
       hot.first_inv[e] = 0ull;
     }
     __syncthreads();
+    int64_t i = c0 + threadIdx.x;
 #pragma unroll 1
-    for (int t = 0; t < chunk_tiles; ++t) {
-      const int64_t i = c0 + (int64_t)t * ACC_THREADS + threadIdx.x;
+    for (int t = 0; t < chunk_tiles; ++t, i += ACC_THREADS) {
       const bool active = i < n;
       const unsigned amask = __ballot_sync(0xffffffffu, active);
       if (!active) continue;  // (trailing lanes of the last tile; the masks below name the active lanes only)
-      int64_t rec_at = i;
-      if (src.n_slices > 1) {
-        int64_t before = 0;
-#pragma unroll 1
-        for (int sl = 0; sl < src.n_slices; ++sl) {
-          const int64_t c = (int64_t)min(src.counts[sl], src.slice_cap);
-          if (i >= before && i < before + c) rec_at = (int64_t)sl * (int64_t)src.slice_cap + (i - before);
-          before += c;
-        }
-      }
-      const uint4* rp = reinterpret_cast<const uint4*>(recs + rec_at);
+      const uint4* rp = rec_ptr(src, i);
       const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2);
       // fc_jrec: chrom,start,end,sk | idx, read_hash | qname_hash, q_left,q_right, n_hits,dist,ov
       const unsigned sk = r0.w;
@@ -508,25 +601,27 @@ __global__ void __launch_bounds__(ACC_THREADS, FC_ACC_MIN_CTAS) fused_accumulate
       const unsigned long long read_hash = (unsigned long long)r1.z | ((unsigned long long)r1.w << 32);
       const unsigned long long qname_hash = (unsigned long long)r2.x | ((unsigned long long)r2.y << 32);
       const bool name_known = (sk & SK_NAME_KNOWN) != 0u;
+      unsigned long long klo = 0ull, kid = 0ull, kf = 0ull, cur_kf = 0ull, cur_x = 0ull, s_read = 0ull, s_name = 0ull;
+      bool fresh = false, sent_r = false, sent_n = false;
+      unsigned int part_r = 0u, part_n = 0u, pos_r = 0u, pos_n = 0u;
+      unsigned long long key_r = 0ull, key_n = 0ull;
       // names and reads share the set: the name's value is salted so that equal hashes of the two kinds stay apart
-      const unsigned long long s_read = set_first_slot(read_hash, smask);
-      unsigned long long s_name = 0ull;
-      if (prefetch) prefetch_l2(sets + s_read);
-      if (!name_known) {
-        s_name = set_first_slot(~qname_hash, smask);
-        if (prefetch) prefetch_l2(sets + s_name);
+      if (SETS == 0) {
+        s_read = set_first_slot(read_hash, smask);
+        if (prefetch) prefetch_l2(sets + s_read);
+        if (!name_known) {
+          s_name = set_first_slot(~qname_hash, smask);
+          if (prefetch) prefetch_l2(sets + s_name);
+        }
       }
 
       // ---- the junction's slot
-      const unsigned long long klo = (unsigned long long)r0.y | ((unsigned long long)r0.z << 32);
+      key_of(r0, klo, kid);
       const unsigned long long rel = idx - idx_base;
       // (a position or chromosome number beyond the slot's fields: the call falls back to the sort-based path)
       if ((rel >> FIRST_BITS) != 0ull || (r0.x >> CHROM_BITS) != 0u) atomicAdd(&ctr[FC_N_OTHER], 1u);
-      const unsigned long long kid = KEY_OCC | ((unsigned long long)(r0.x & ((1u << CHROM_BITS) - 1u)) << (FIRST_BITS + 2)) |
-                                     ((unsigned long long)(sk & 3u) << FIRST_BITS);
-      const unsigned long long kf = kid | (FIRST_MAX - (rel & FIRST_MAX));
-      unsigned long long slot = fc_mix64(klo ^ fc_mix64(kid)) & kmask, cur_kf = 0ull, cur_x = 0ull;
-      bool fresh = false;
+      kf = kid | (FIRST_MAX - (rel & FIRST_MAX));
+      unsigned long long slot = slot_of(klo, kid, kmask);
       for (;;) {
         // L1-cached look: the identity never changes once written and the maxima only grow, so a cached copy is as
         // good as the one in L2 (the slot of a popular junction is read by thousands of threads); a cached EMPTY may be
@@ -551,6 +646,19 @@ __global__ void __launch_bounds__(ACC_THREADS, FC_ACC_MIN_CTAS) fused_accumulate
         }
         slot = (slot + 1ull) & kmask;
       }
+      // ---- partitioned distinct counts: claim the places in the partitions now, the answers are used at the very end
+      if (SETS == 1) {
+        const unsigned long long tag = (unsigned long long)(unsigned int)slot + 1ull;
+        key_r = part_key(read_hash, tag, pv.n_parts, part_r);
+        sent_r = part_claim(pv, recent, key_r, part_r, pos_r);
+        if (!name_known) {
+          key_n = part_key(~qname_hash, tag | (1ull << 32), pv.n_parts, part_n);
+          sent_n = part_claim(pv, recent, key_n, part_n, pos_n);
+        }
+      }
+      const unsigned int jid = (unsigned int)slot;  // slot number = the junction's id in this call
+      JSlot* a = slots + jid;
+      const unsigned long long tag = (unsigned long long)jid + 1ull;  // never 0: no set entry is all-zero
       {
         // new junctions of the warp: one atomic for all of them claims their places in the list
         const unsigned fm = __ballot_sync(amask, fresh);
@@ -569,8 +677,6 @@ __global__ void __launch_bounds__(ACC_THREADS, FC_ACC_MIN_CTAS) fused_accumulate
           }
         }
       }
-      const unsigned int jid = (unsigned int)slot;  // slot number = the junction's id in this call
-      JSlot* a = slots + jid;
 
       // ---- lanes of the warp that share the junction are combined; is it in the CTA's table (or does it belong there)?
       const unsigned peers = __match_any_sync(amask, jid);
@@ -584,23 +690,30 @@ __global__ void __launch_bounds__(ACC_THREADS, FC_ACC_MIN_CTAS) fused_accumulate
       // ---- extrema
       const int q_left = (int)(short)(r2.z & 0xFFFFu), q_right = (int)(short)(r2.z >> 16);
       const unsigned n_hits = r2.w & 0xFFFFu, dist = (r2.w >> 16) & 0xFFu, ov = r2.w >> 24;
+      const unsigned long long x = ext_pack(q_left, q_right, dist, ov, n_hits);
       if (he >= 0) {
-        const unsigned ql = (unsigned)(q_left + 32768), qr = (unsigned)(q_right + 32768);
-        const unsigned idist = 255u - dist, iov = 255u - ov, inh = 65535u - n_hits;
         if (kf > hot.first_inv[he]) atomicMax(&hot.first_inv[he], kf);
-        if (ql > hot.qmax_l[he]) atomicMax(&hot.qmax_l[he], ql);
-        if (qr > hot.qmax_r[he]) atomicMax(&hot.qmax_r[he], qr);
-        if (idist > hot.inv_dist[he]) atomicMax(&hot.inv_dist[he], idist);
-        if (iov > hot.inv_ov[he]) atomicMax(&hot.inv_ov[he], iov);
-        if (inh > hot.inv_nh[he]) atomicMax(&hot.inv_nh[he], inh);
+        unsigned long long cx = hot.ext[he], want = cx;
+        if (ext_improves(cx, x)) want = ext_max(cx, x);
+        while (want != cx) {  // (rare once the entry has seen a few records)
+          const unsigned long long old = atomicCAS(&hot.ext[he], cx, want);
+          if (old == cx) break;
+          cx = old;
+          want = ext_max(cx, x);
+        }
       } else {
-        extrema_to_global(a, kf, ext_pack(q_left, q_right, dist, ov, n_hits), cur_kf, cur_x);
+        extrema_to_global(a, kf, x, cur_kf, cur_x);
       }
 
       // ---- distinct reads / fragment names of the junction
-      const unsigned long long tag = (unsigned long long)jid + 1ull;  // never 0: no entry is all-zero
       bool new_read = false, new_name = false;
-      set_insert2(sets, smask, read_hash, tag, s_read, !name_known, qname_hash, tag | (1ull << 32), s_name, !prefetch, new_read, new_name);
+      if (SETS == 0) {
+        set_insert2(sets, smask, read_hash, tag, s_read, !name_known, qname_hash, tag | (1ull << 32), s_name, !prefetch, new_read, new_name);
+      } else {
+        // pass 2 decides; a repeat of a key this CTA has sent before is counted as the duplicate it is right here
+        new_read = sent_r;
+        new_name = sent_n;
+      }
       const bool dup_name = name_known ? (sk & SK_NAME_DUP) != 0u : !new_name;
 
       // ---- counters
@@ -610,7 +723,8 @@ __global__ void __launch_bounds__(ACC_THREADS, FC_ACC_MIN_CTAS) fused_accumulate
       const unsigned fx = cls < 4 ? (8u >> cls) : 0u;
       const bool bridge = q_left != 0 && q_right != 0;
       const unsigned nb = bridge ? 0u : fx;
-      const unsigned c2 = new_read ? (unsigned)(read_hash & 1ull) : 2u;  // (bit 0 of the hash flags a palindromic read)
+      // (bit 0 of the hash flags a palindromic read; partitioned: pass 2 adds what a read that was sent contributes)
+      const unsigned c2 = new_read ? (SETS == 0 ? (unsigned)(read_hash & 1ull) : 0u) : 2u;
       if (__all_sync(amask, group == 1u)) {
         // no two lanes of the warp share a junction (the usual case)
         if (he >= 0) {
@@ -643,14 +757,16 @@ __global__ void __launch_bounds__(ACC_THREADS, FC_ACC_MIN_CTAS) fused_accumulate
           }
         }
       }
+      if (SETS == 1) {
+        if (sent_r) part_store(pv, key_r, part_r, pos_r, jid | ((read_hash & 1ull) ? PART_PALIN : 0u), ctr);
+        if (sent_n) part_store(pv, key_n, part_n, pos_n, jid | PART_NAME, ctr);
+      }
     }
     __syncthreads();
     for (int e = threadIdx.x; e < HOT_ENTRIES; e += ACC_THREADS) {
       if (hot.tag[e] == 0u) continue;
       JSlot* a = slots + (hot.tag[e] - 1u);
-      const unsigned long long x = (unsigned long long)(hot.qmax_l[e] | (hot.qmax_r[e] << 16)) |
-                                   ((unsigned long long)(hot.inv_ov[e] | (hot.inv_dist[e] << 8) | (hot.inv_nh[e] << 16)) << 32);
-      extrema_to_global(a, hot.first_inv[e], x, __ldcg(&a->kf), __ldcg(&a->ext));
+      extrema_to_global(a, hot.first_inv[e], hot.ext[e], __ldcg(&a->kf), __ldcg(&a->ext));
       const unsigned c0v = hot.c0[e], c1v = hot.c1[e], c2v = hot.c2[e];
       if (c0v) atomicAdd(&a->c0, (unsigned long long)(c0v & 0x3FFFu) | ((unsigned long long)(c0v >> 14) << 32));
       if (c1v) atomicAdd(&a->c1, (unsigned long long)(c1v >> 14) | ((unsigned long long)(c1v & 0x3FFFu) << 32));
@@ -659,6 +775,88 @@ __global__ void __launch_bounds__(ACC_THREADS, FC_ACC_MIN_CTAS) fused_accumulate
     __syncthreads();  // the table is re-initialised for the next chunk
   }
 }
+
+// Pass 2 of the partitioned distinct counts: one CTA per partition at a time, an exact set of the partition's 64-bit keys
+// in shared memory.  What an entry adds to its junction (JSlot.c2: 2 per read seen before + 1 per new palindromic read;
+// JSlot.c1 high word: fragment names seen before) is collected per junction in a small shared-memory table first -- the
+// repeats belong to the popular junctions -- and flushed once per partition.  The partition's fill count is zeroed on
+// the way out, so the buffers are clean for the next call.
+constexpr int PADD_ENTRIES = 1024;
+__global__ void __launch_bounds__(PART_THREADS) distinct_parts_kernel(PartView pv, JSlot* __restrict__ slots, unsigned int* __restrict__ ctr) {
+  extern __shared__ unsigned long long pset[];  // PSET_ENTRIES
+  __shared__ unsigned int a_tag[PADD_ENTRIES], a_c2[PADD_ENTRIES], a_c1[PADD_ENTRIES];
+#pragma unroll 1
+  for (unsigned int p = blockIdx.x; p < pv.n_parts; p += gridDim.x) {
+    const unsigned int fill = pv.cur[8u * p];
+    if (fill == 0u) continue;  // (block-uniform)
+    const unsigned int n = fill < pv.pcap ? fill : pv.pcap;
+    {
+      ulonglong2* z = reinterpret_cast<ulonglong2*>(pset);
+      for (int e = threadIdx.x; e < PSET_ENTRIES / 2; e += PART_THREADS) z[e] = make_ulonglong2(0ull, 0ull);
+      for (int e = threadIdx.x; e < PADD_ENTRIES; e += PART_THREADS) a_tag[e] = a_c2[e] = a_c1[e] = 0u;
+    }
+    __syncthreads();
+    const uint4* ent = pv.ent + (size_t)p * pv.pcap;
+#pragma unroll 1
+    for (unsigned int i = threadIdx.x; i < n; i += PART_THREADS) {
+      const uint4 e = __ldcs(ent + i);
+      const unsigned long long k = (unsigned long long)e.x | ((unsigned long long)e.y << 32);
+      unsigned int h = (unsigned int)(k >> 40) & (PSET_ENTRIES - 1);
+      bool fresh = false, placed = false;
+#pragma unroll 1
+      for (int probe = 0; probe < PSET_ENTRIES; ++probe) {
+        unsigned long long cur = pset[h];
+        if (cur == 0ull) cur = atomicCAS(&pset[h], 0ull, k);
+        if (cur == 0ull) {
+          fresh = placed = true;
+          break;
+        }
+        if (cur == k) {
+          placed = true;
+          break;
+        }
+        h = (h + 1u) & (PSET_ENTRIES - 1);
+      }
+      if (!placed) {  // the set is full: the host repeats the call with the global set
+        atomicAdd(&ctr[FC_N_SET_FULL], 1u);
+        continue;
+      }
+      const bool is_name = (e.z & PART_NAME) != 0u;
+      const unsigned int add2 = is_name ? 0u : (fresh ? ((e.z & PART_PALIN) ? 1u : 0u) : 2u);
+      const unsigned int add1 = (is_name && !fresh) ? 1u : 0u;
+      if ((add2 | add1) == 0u) continue;
+      const unsigned int jid = e.z & PART_JID;
+      unsigned int s = (jid * 2654435761u) >> (32 - 10);
+      bool done = false;
+#pragma unroll 1
+      for (int probe = 0; probe < 4 && !done; ++probe) {
+        unsigned int cur = *reinterpret_cast<volatile unsigned int*>(&a_tag[s]);
+        if (cur == 0u) cur = atomicCAS(&a_tag[s], 0u, jid + 1u);
+        if (cur == 0u || cur == jid + 1u) {
+          if (add2) atomicAdd(&a_c2[s], add2);
+          if (add1) atomicAdd(&a_c1[s], add1);
+          done = true;
+        }
+        s = (s + 1u) & (PADD_ENTRIES - 1);
+      }
+      if (!done) {
+        JSlot* a = slots + jid;
+        if (add2) atomicAdd(&a->c2, (unsigned long long)add2);
+        if (add1) atomicAdd(&a->c1, (unsigned long long)add1 << 32);
+      }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < PADD_ENTRIES; e += PART_THREADS) {
+      if (a_tag[e] == 0u) continue;
+      JSlot* a = slots + (a_tag[e] - 1u);
+      if (a_c2[e]) atomicAdd(&a->c2, (unsigned long long)a_c2[e]);
+      if (a_c1[e]) atomicAdd(&a->c1, (unsigned long long)a_c1[e] << 32);
+    }
+    if (threadIdx.x == 0) pv.cur[8u * p] = 0u;
+    __syncthreads();
+  }
+}
+static_assert(PADD_ENTRIES == 1024, "distinct_parts_kernel hashes junctions to 10 bits");
 
 __device__ __forceinline__ fc_junction junction_from_slot(const JSlot& a, unsigned long long first_idx) {
   fc_junction o;
@@ -760,7 +958,7 @@ __global__ void __launch_bounds__(FINISH_THREADS) finish_dense_kernel(int64_t ra
     // everything the host wants to know, written straight into its (mapped, pinned) memory: no copy to wait for
     ctr[FC_N_JUNC] = s_base + mine;
     __threadfence();
-    for (int k = 0; k < 10; ++k) h_counters[k] = counters[k];
+    for (int k = 0; k < 11; ++k) h_counters[k] = counters[k];
     h_counters[9] = (counters[9] & 0xFFFFFFFFull) | ((unsigned long long)(s_base + mine) << 32);
   }
   if (mine == 0u) return;
@@ -1247,7 +1445,7 @@ struct StageTimer {
 
 // sort-free path over the `ub` (upper bound; the exact count is on the device) records of the context; returns -100
 // when the input needs the sort-based path (a weight denominator that is not 1, 2, 4 or 8; too many records)
-static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st, const RecSrc& src) {
+static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st, const RecSrc& src, bool global_set = false) {
   fc_agg& a = ctx->agg;
   if (ub >= FUSED_MAX_RECORDS) return -100;
   // junction table: one 64-byte slot per junction, at most one junction per record (load <= 0.8); distinct set: up to two
@@ -1269,16 +1467,32 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st, const Re
   }
   if ((rc = reserve_clean(ctx, a.f_keys, (size_t)kcap * sizeof(JSlot), st))) return rc;
   FC_CUDA(ctx, a.f_acc.reserve((size_t)lcap * sizeof(unsigned int), st, false, 0));
-  if (!(a.sets_clean && (size_t)scap * 16 <= a.sets_used && (size_t)scap * 16 <= a.f_sets.cap)) {
-    FC_CUDA(ctx, a.f_sets.reserve((size_t)scap * 16, st, false, 0));
-    FC_CUDA(ctx, cudaMemsetAsync(a.f_sets.p, 0, (size_t)scap * 16, st));
+  // distinct counts: one global set while it fits L2, else partitions + shared-memory sets (FC_AGG_SETS=global|part forces one)
+  bool part = (size_t)scap * 16 > ((size_t)64 << 20);
+  if (const char* e = getenv("FC_AGG_SETS")) part = e[0] == 'p' ? true : (e[0] == 'g' ? false : part);
+  if (global_set) part = false;
+  PartView pv{nullptr, nullptr, 0u, 0u};
+  if (part) {
+    pv.n_parts = (unsigned int)((ub + PSET_TARGET - 1) / PSET_TARGET);
+    if (pv.n_parts == 0u) pv.n_parts = 1u;
+    pv.pcap = 4u * PSET_TARGET + 2048u;  // (twice the mean when every name goes through the set too, and as much again for repeats)
+    if (const char* e = getenv("FC_AGG_PART_CAP")) pv.pcap = (unsigned int)atoi(e) > 0 ? (unsigned int)atoi(e) : pv.pcap;  // (tests: force the way back)
+    if ((rc = reserve_clean(ctx, a.f_pcur, (size_t)pv.n_parts * 32, st))) return rc;
+    FC_CUDA(ctx, a.f_part.reserve((size_t)pv.n_parts * pv.pcap * sizeof(uint4), st, false, 0));
+    pv.ent = (uint4*)a.f_part.p;
+    pv.cur = (unsigned int*)a.f_pcur.p;
+  } else {
+    if (!(a.sets_clean && (size_t)scap * 16 <= a.sets_used && (size_t)scap * 16 <= a.f_sets.cap)) {
+      FC_CUDA(ctx, a.f_sets.reserve((size_t)scap * 16, st, false, 0));
+      FC_CUDA(ctx, cudaMemsetAsync(a.f_sets.p, 0, (size_t)scap * 16, st));
+    }
+    a.sets_clean = false;
+    a.sets_used = (size_t)scap * 16 > a.sets_used ? (size_t)scap * 16 : a.sets_used;
   }
-  a.sets_clean = false;
-  a.sets_used = (size_t)scap * 16 > a.sets_used ? (size_t)scap * 16 : a.sets_used;
   FC_CUDA(ctx, a.junctions.reserve((size_t)ub * sizeof(fc_junction), st, false, 0));
   unsigned long long* counters = (unsigned long long*)a.counters.p;
   unsigned int* ctr = (unsigned int*)(counters + 8);
-  FC_CUDA(ctx, cudaMemsetAsync(ctr, 0, 4 * sizeof(unsigned int), st));
+  FC_CUDA(ctx, cudaMemsetAsync(ctr, 0, FC_N_CTR * sizeof(unsigned int), st));
   // discovery rank: flags over the idx range when it is known and about as large as the record count, else a sort
   const bool dense = a.max_idx != ~0ull && a.idx_lo != ~0ull && a.max_idx > a.idx_lo &&
                      a.max_idx - a.idx_lo <= 4ull * (unsigned long long)ub + (1ull << 20);
@@ -1306,12 +1520,26 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st, const Re
     const unsigned grid = (unsigned)(chunks < ctas ? chunks : ctas);
     // the L2 prefetch of the set slots pays while the set fits L2 (-7 % at 1 M records) and costs 20 % when it does not
     const int prefetch = (size_t)scap * 16 <= ((size_t)64 << 20) ? 1 : 0;
-    fused_accumulate_kernel<<<grid, ACC_THREADS, 0, st>>>(src, chunk_tiles, prefetch, idx_base, (JSlot*)a.f_keys.p, kcap - 1, (U128*)a.f_sets.p, scap - 1,
-                                                          (unsigned int*)a.f_acc.p, lcap, ctr, (uint4*)flag, (range + 3) / 4, tile_count,
-                                                          n_tiles);
+    if (part) FC_CUDA(ctx, cudaFuncSetAttribute(fused_accumulate_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * RECENT_SETS * 8));
+    if (part)
+      fused_accumulate_kernel<1><<<grid, ACC_THREADS, 2 * RECENT_SETS * 8, st>>>(src, chunk_tiles, 0, idx_base, (JSlot*)a.f_keys.p, kcap - 1, nullptr, 0ull, pv,
+                                                               (unsigned int*)a.f_acc.p, lcap, ctr, (uint4*)flag, (range + 3) / 4,
+                                                               tile_count, n_tiles);
+    else
+      fused_accumulate_kernel<0><<<grid, ACC_THREADS, 0, st>>>(src, chunk_tiles, prefetch, idx_base, (JSlot*)a.f_keys.p, kcap - 1,
+                                                               (U128*)a.f_sets.p, scap - 1, pv, (unsigned int*)a.f_acc.p, lcap, ctr,
+                                                               (uint4*)flag, (range + 3) / 4, tile_count, n_tiles);
   }
   FC_LAUNCH_CHECK(ctx);
   tm.mark("accumulate");
+  if (part) {
+    FC_CUDA(ctx, cudaFuncSetAttribute(distinct_parts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PSET_ENTRIES * 8));
+    const unsigned want = (unsigned)ctx->sm_count * 3u;
+    distinct_parts_kernel<<<pv.n_parts < want ? pv.n_parts : want, PART_THREADS, PSET_ENTRIES * 8, st>>>(pv, (JSlot*)a.f_keys.p, ctr);
+    FC_LAUNCH_CHECK(ctx);
+    ctx->launches += 1;
+  }
+  tm.mark("distinct");
   const unsigned sweep_blocks = (unsigned)ctx->sm_count * 8u;
   uint64_t* kA = nullptr;
   uint64_t* kB = nullptr;
@@ -1350,7 +1578,7 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st, const Re
   // one round trip: exact record count, junction count, fallback conditions, peer-to-peer overflow
   tm.mark("finish");
   unsigned long long* h = a.h_pinned;  // pinned + mapped; the dense finish kernel has already written it
-  if (!dense) FC_CUDA(ctx, cudaMemcpyAsync(h, counters, 10 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  if (!dense) FC_CUDA(ctx, cudaMemcpyAsync(h, counters, 11 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   tm.mark("copy");
   FC_CUDA(ctx, cudaStreamSynchronize(st));
   tm.report();
@@ -1372,6 +1600,14 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st, const Re
     a.max_idx = ~0ull;
   }
   if (n_other || n_overflow) return -100;
+  if (part && h[10]) {
+    if (tm.print)
+      fprintf(stderr, "[fc_agg_finalize] partitioned distinct counts gave up (%u entries beyond a partition, %u beyond a set): global set\n",
+              (unsigned)h[10], (unsigned)(h[10] >> 32));
+    // a partition or its shared-memory set ran full (copies of one element beyond what the caches absorb, or a hash that
+    // does not spread): every table is clean again, the call is repeated with the global set
+    return finalize_fused(ctx, ub, st, src, true);
+  }
   if (!dense && nj > 0) {
     uint32_t* vB = vA + ub;
     rc = sort_pairs_u64_u32(ctx, nj, kA, kB, vA, vB, 0, 64, st);
@@ -1599,9 +1835,9 @@ extern "C" int fc_agg_set_timing(fc_ctx* ctx, int32_t on) {
   return FC_OK;
 }
 
-extern "C" int fc_agg_get_timing(fc_ctx* ctx, float* out_us /* 5 */) {
+extern "C" int fc_agg_get_timing(fc_ctx* ctx, float* out_us /* 6 */) {
   if (!ctx || !out_us) return FC_E_ARG;
-  for (int k = 0; k < 5; ++k) out_us[k] = ctx->agg.stage_us[k];
+  for (int k = 0; k < 6; ++k) out_us[k] = ctx->agg.stage_us[k];
   return FC_OK;
 }
 

@@ -83,11 +83,12 @@ struct fc_agg {
   fc_dbuf htab[3];      // sort-based path: hash sets for the distinct counts (reads, fragment names)
   // sort-free path: junction-key table and accumulators (kept clean between calls), distinct set
   fc_dbuf f_keys, f_sets, f_acc;
+  fc_dbuf f_part, f_pcur;       // partitioned distinct counts: entries, fill counts (kept all-zero between calls)
   bool f_dirty = false;
   cudaStream_t side = nullptr;  // early clear of the distinct set (see clear_sets_early)
   cudaEvent_t ev_side = nullptr, ev_main = nullptr;
   bool timing = false;          // keep the per-stage device times of fc_agg_finalize (fc_agg_set_timing)
-  float stage_us[8] = {};       // clear, accumulate, mark, finish, copy
+  float stage_us[8] = {};       // clear, accumulate, distinct, mark, finish, copy
   bool sets_clean = false;
   size_t sets_used = 0;         // bytes of f_sets that calls have touched (and an early clear covers)
 };

@@ -365,9 +365,9 @@ class Engine:
 
     def agg_get_timing(self) -> dict:
         """device time (us) of the stages of the last agg_finalize on its sort-free path"""
-        out = np.zeros(5, dtype=np.float32)
+        out = np.zeros(6, dtype=np.float32)
         self._check(self.lib.fc_agg_get_timing(self.h, out.ctypes.data))
-        return dict(zip(("clear", "accumulate", "mark", "finish", "copy"), (float(v) for v in out)))
+        return dict(zip(("clear", "accumulate", "distinct", "mark", "finish", "copy"), (float(v) for v in out)))
 
     def agg_finalize(self, stream=0) -> int:
         return int(self._check(self.lib.fc_agg_finalize(self.h, stream)))

@@ -477,8 +477,8 @@ int fc_device_sync(fc_ctx* ctx);
  * every rank. */
 int fc_agg_set_idx_range(fc_ctx* ctx, uint64_t lo, uint64_t hi);
 /* Device time of the stages of the last fc_agg_finalize() call on its sort-free path, measured with CUDA events on the
- * caller's stream while switched on: out_us[0..4] = table clears, accumulate kernel, first-record marks, finish kernel,
- * counter copy (bench.py's roofline for the aggregation kernel; no counterpart in the reference). */
+ * caller's stream while switched on: out_us[0..5] = table clears, accumulate kernel, distinct-count kernel over the
+ * partitions (0 for inputs whose set fits L2), first-record marks, finish kernel, counter copy (bench.py's roofline for the aggregation kernel; no counterpart in the reference). */
 int fc_agg_set_timing(fc_ctx* ctx, int32_t on);
 int fc_agg_get_timing(fc_ctx* ctx, float* out_us);
 /* number of kernels this library has launched in this context (bench.py's gpu_launches) */

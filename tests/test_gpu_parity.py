@@ -407,6 +407,41 @@ def test_tile_store_rebuild_across_read_lengths():
     e.close()
 
 
+@pytest.mark.parametrize("cap", [None, "64"])
+@pytest.mark.parametrize("n,n_keys,seed,known", [(37, 5, 2, False), (200000, 5000, 4, False), (300000, 3, 5, False), (250000, 40000, 6, True)])
+def test_partitioned_distinct_counts_match_python(monkeypatch, n, n_keys, seed, known, cap):
+    """large inputs count distinct reads / names through partitions + shared-memory sets (agg.cu: distinct_parts_kernel)
+    instead of one global set: forced here at small sizes; cap=64 makes the partitions overflow, so the call has to find
+    its way back to the global set; `known`: half of the records carry the scan kernel's own verdict on their name"""
+    monkeypatch.setenv("FC_AGG_SETS", "part")
+    if cap:
+        monkeypatch.setenv("FC_AGG_PART_CAP", cap)
+    recs = _random_records(n, n_keys, seed, dens=(1, 1, 2, 4, 8))
+    if known:
+        # FC_SK_NAME_KNOWN: the emitter says whether the fragment is new to the junction (first record of a (junction, name))
+        # every second record settles its name itself, so its name must not meet the others': make the two kinds disjoint
+        recs["qname_hash"][0::2] |= np.uint64(1 << 63)
+        recs["qname_hash"][1::2] &= np.uint64((1 << 63) - 1)
+        first = set()
+        flags = np.zeros(n, dtype=np.uint32)
+        for i in range(0, n, 2):
+            k = (int(recs["chrom"][i]), int(recs["start"][i]), int(recs["end"][i]), int(recs["sk"][i]) & 3, int(recs["qname_hash"][i]))
+            flags[i] = 8 if k not in first else 8 | 16
+            first.add(k)
+        recs["sk"] |= flags
+    e = _engine()
+    for _ in range(2):  # twice: the partition buffers must come back clean
+        e.agg_reset()
+        e.agg_append_host(recs)
+        nj = e.agg_finalize()
+        got = _junction_rows(e.agg_fetch(nj))
+        want = _py_aggregate(recs)
+        assert len(got) == len(want)
+        for gr, wr in zip(got, want):
+            assert gr == wr, (gr, wr)
+    e.close()
+
+
 def test_sort_based_and_hash_based_aggregation_agree():
     """fc_agg_finalize has two implementations (sort-free default, sort-based fallback for weight denominators that are
     not powers of two): both must produce identical junction tables"""
