@@ -805,8 +805,7 @@ __global__ void __launch_bounds__(PART_THREADS) distinct_parts_kernel(PartView p
       bool fresh = false, placed = false;
 #pragma unroll 1
       for (int probe = 0; probe < PSET_ENTRIES; ++probe) {
-        unsigned long long cur = pset[h];
-        if (cur == 0ull) cur = atomicCAS(&pset[h], 0ull, k);
+        const unsigned long long cur = atomicCAS(&pset[h], 0ull, k);  // (no look first: most keys are new and most slots free)
         if (cur == 0ull) {
           fresh = placed = true;
           break;
