@@ -511,6 +511,120 @@ extern "C" int64_t fc_ingest_parse(fc_ingest* h, const char* text, int64_t nbyte
 // qualities of every spliced read in one compact blob per batch (fc_text_gather) and formats the FASTQ records in one
 // pass when the names are known (fc_fastq_format).
 
+// ---- the evidence rules of record_hits (find_circ.py:1276-1439) for a whole batch of the native ingest -------------
+// With at most two spans per fragment (back-splices first) every rule is a comparison between the fragment's columns and
+// the scan's answers for its rows: one pass over the m fragment records.  pipeline.Run._record_hits stays the reading of
+// the reference for everything else (three spans and more, --all-hits); the two are pinned to the same goldens.
+// Outputs (arrays sized by the caller): the four hit counters; per fragment the flag word, a class byte and the junction
+// keys (chrom id, start, end, minus, kind) of its spans and of its (last) back-splice; the compact list of per-junction
+// evidence events (<= 2 m); the compact list of reads to write (<= 2 m: one entry per mate of a fragment with a junction).
+extern "C" int fc_ingest_evidence(const fc_evidence_in* in, fc_evidence_out* o) {
+  if (!in || !o || in->n < 0 || in->m < 0) return FC_E_ARG;
+  const int64_t m = in->m;
+  const uint32_t* B = in->bit;
+  enum { UNRES_BACK = 0, CLOSURE, UNRES_LIN, OUT_SPLICE, IN_SPLICE, OTHER_CHROM, OUT_MATE, IN_MATE, BROKEN, MULTI };
+  int64_t cs_n = 0, cn_n = 0, ls_n = 0, ln_n = 0, n_ev = 0, n_reads = 0;
+  bool any_hit = false;
+  for (int64_t f = 0; f < m; ++f) {
+    const unsigned st = in->f_state[f], kd = in->f_kind[f], ff = in->f_flags[f];
+    const int64_t r0 = in->f_row0[f];
+    const bool two = in->f_nsp[f] == 2;
+    const bool q[2] = {(st & 1u) != 0, (st & 2u) != 0};
+    const int64_t row[2] = {q[0] ? r0 : 0, q[1] ? r0 + (int64_t)(st & 1u) : 0};
+    const bool c[2] = {(kd & 1u) != 0, (kd & 2u) != 0};
+    const bool l[2] = {!c[0], two && !c[1]};
+    bool h[2];
+    int64_t key[2][5];
+    for (int j = 0; j < 2; ++j) {
+      const fc_hit& hit = in->hits[row[j]];
+      h[j] = q[j] && (hit.w2 & 0xFFFFu) != 0u;
+      key[j][0] = in->chrom[row[j]];
+      key[j][1] = hit.start;
+      key[j][2] = hit.end;
+      key[j][3] = hit.w3 & 1u;
+      key[j][4] = l[j] ? 1 : 0;
+      cs_n += c[j] && h[j];
+      cn_n += c[j] && q[j] && !h[j];
+      ls_n += l[j] && h[j];
+      ln_n += l[j] && q[j] && !h[j];
+    }
+    any_hit = any_hit || h[0] || h[1];
+    const bool ch[2] = {c[0] && h[0], c[1] && h[1]};
+    const bool differ = memcmp(key[0], key[1], sizeof(key[0])) != 0;
+    const bool multi = ch[0] && ch[1] && differ;  // two different back-splices (find_circ.py:1319-1329)
+    const bool single = (ch[0] || ch[1]) && !multi;
+    const int64_t* ck = ch[1] ? key[1] : key[0];  // the (last) back-splice of the fragment
+    const int64_t cs = ck[1], ce = ck[2];
+    uint32_t W = 0;
+    uint8_t cls = 0;
+    if ((c[0] && q[0] && !h[0]) || (c[1] && q[1] && !h[1])) W |= B[UNRES_BACK];
+    if (single && c[0] && c[1]) W |= B[CLOSURE];
+    for (int j = 0; j < 2; ++j) {
+      if (l[j] && q[j] && !h[j]) W |= B[UNRES_LIN];
+      const bool ev = l[j] && h[j] && single;
+      const bool outside = key[j][1] <= cs || key[j][2] >= ce;
+      if (ev) W |= outside ? B[OUT_SPLICE] : B[IN_SPLICE];
+      if (ev) cls |= (uint8_t)(FC_EV_LIN0 << j);
+      if (ev && outside) cls |= (uint8_t)(FC_EV_LIN0_OUT << j);
+    }
+    const bool un = (ff & 1u) != 0 && single;  // FR_UNSPLICED
+    const bool un_other = un && (ff & 2u) != 0;  // FR_OTHER_CHROM
+    const bool un_outside = un && !un_other && ((int64_t)in->f_un_pos[f] + in->asize <= cs || (int64_t)in->f_un_aend[f] - in->asize >= ce);
+    if (un_other) W |= B[OTHER_CHROM];
+    if (un_outside) W |= B[OUT_MATE];
+    if (un && !un_other && !un_outside) W |= B[IN_MATE];
+    if (single && (ff & 4u) != 0) W |= B[BROKEN];  // FR_BROKEN
+    if (multi) W = B[MULTI];
+    if (un) cls |= FC_EV_UN;
+    if (un_other || un_outside) cls |= FC_EV_UN_OUT;
+    if (h[0]) cls |= FC_EV_HIT0;
+    if (h[1]) cls |= FC_EV_HIT1;
+    o->W[f] = W;
+    o->cls[f] = cls;
+    memcpy(o->key0 + 5 * f, key[0], sizeof(key[0]));
+    memcpy(o->key1 + 5 * f, key[1], sizeof(key[1]));
+    memcpy(o->ck + 5 * f, ck, sizeof(key[0]));
+    // per-junction flags (find_circ.py:1325-1327, 1433-1437)
+    const uint64_t name_hash = in->qname_hash[r0];
+    if (single && W != 0u) {
+      memcpy(o->ev_key + 5 * n_ev, ck, sizeof(key[0]));
+      o->ev_hash[n_ev] = name_hash;
+      o->ev_mask[n_ev++] = W;
+    } else if (multi) {
+      for (int j = 0; j < 2; ++j) {
+        memcpy(o->ev_key + 5 * n_ev, key[j], sizeof(key[0]));
+        o->ev_hash[n_ev] = name_hash;
+        o->ev_mask[n_ev++] = W;
+      }
+    }
+    // the reads of every fragment with a junction (find_circ.py:1439, 1442-1447)
+    if (h[0] || h[1]) {
+      const int64_t* first = h[0] ? key[0] : key[1];
+      const bool with2 = h[0] && h[1] && differ;
+      const int n_mates = 1 + ((ff & 8u) != 0);  // FR_TWO_MATES
+      for (int mate = 0; mate < n_mates; ++mate) {
+        o->r_seq[n_reads] = in->f_seq[f];
+        memcpy(o->r_k0 + 5 * n_reads, first, sizeof(key[0]));
+        for (int k = 0; k < 5; ++k) o->r_k1[5 * n_reads + k] = with2 ? key[1][k] : -1;
+        o->r_mask[n_reads] = (int64_t)W;
+        for (int k = 0; k < 3; ++k) {
+          o->r_off3[3 * n_reads + k] = in->f_txt_off[6 * f + 3 * mate + k] + in->text_off;
+          o->r_len3[3 * n_reads + k] = in->f_txt_len[6 * f + 3 * mate + k];
+        }
+        ++n_reads;
+      }
+    }
+  }
+  o->counters[0] = cs_n;
+  o->counters[1] = cn_n;
+  o->counters[2] = ls_n;
+  o->counters[3] = ln_n;
+  o->n_events = n_ev;
+  o->n_reads = n_reads;
+  o->any_hit = any_hit ? 1 : 0;
+  return FC_OK;
+}
+
 // copies n x 3 substrings of `buf` back to back into `out` (off/len are n x 3, row major; len < 0 = field absent);
 // returns the number of bytes written
 extern "C" int64_t fc_text_gather(const char* buf, int64_t n, const int64_t* off, const int32_t* len, char* out) {

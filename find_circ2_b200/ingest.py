@@ -44,6 +44,59 @@ COUNTER_NAMES = ("total_mates", "unmapped_reads", "unspliced_mates", "seg_too_sh
                  "lin_junc_not_unique")
 
 
+class EvidenceIn(C.Structure):
+    _fields_ = [("n", C.c_int64), ("m", C.c_int64), ("hits", _P), ("chrom", _P), ("qname_hash", _P), ("f_seq", _P), ("f_row0", _P),
+                ("f_nsp", _P), ("f_kind", _P), ("f_state", _P), ("f_flags", _P), ("f_un_pos", _P), ("f_un_aend", _P),
+                ("f_txt_off", _P), ("f_txt_len", _P), ("text_off", C.c_int64), ("asize", C.c_int32), ("bit", C.c_uint32 * 10)]
+
+
+class EvidenceOut(C.Structure):
+    _fields_ = [("counters", C.c_int64 * 4), ("n_events", C.c_int64), ("n_reads", C.c_int64), ("any_hit", C.c_int32), ("W", _P),
+                ("cls", _P), ("key0", _P), ("key1", _P), ("ck", _P), ("ev_key", _P), ("ev_hash", _P), ("ev_mask", _P),
+                ("r_seq", _P), ("r_k0", _P), ("r_k1", _P), ("r_mask", _P), ("r_off3", _P), ("r_len3", _P)]
+
+
+EV_HIT0, EV_HIT1, EV_LIN0, EV_LIN1, EV_LIN0_OUT, EV_LIN1_OUT, EV_UN, EV_UN_OUT = 1, 2, 4, 8, 16, 32, 64, 128  # fc_evidence_out.cls
+# the order fc_ingest_evidence expects the flag bits in
+EVIDENCE_FLAGS = ("WARN_UNRESOLVED_EXTRA_BACKSPLICE", "SUPPORT_CLOSURE", "WARN_UNRESOLVED_LINSPLICE", "WARN_OUTSIDE_SPLICE_JUNCTION",
+                  "SUPPORT_INSIDE_SPLICE_JUNCTION", "WARN_OTHER_CHROM_MATE", "WARN_OUTSIDE_MATE", "SUPPORT_INSIDE_MATE",
+                  "BROKEN_SEGMENTS", "WARN_MULTI_BACKSPLICE")
+
+
+def evidence(lib, a: dict, hits: np.ndarray, n: int, m: int, text_off: int, asize: int, flag_bit: dict) -> dict:
+    """fc_ingest_evidence on the arrays of one fc_ingest_parse call (`a`) and the scan's hits for its n rows: counters,
+    per-fragment flag words / classes / junction keys, the evidence events and the reads to write (see the header)"""
+    i = EvidenceIn()
+    i.n, i.m, i.text_off, i.asize = n, m, text_off, asize
+    hits = np.ascontiguousarray(hits)
+    i.hits = hits.ctypes.data
+    for k in ("chrom", "qname_hash", "f_seq", "f_row0", "f_nsp", "f_kind", "f_state", "f_flags", "f_un_pos", "f_un_aend", "f_txt_off",
+              "f_txt_len"):
+        setattr(i, k, a[k].ctypes.data)
+    for k, name in enumerate(EVIDENCE_FLAGS):
+        i.bit[k] = flag_bit[name]
+    r = {"W": np.empty(m, np.uint32), "cls": np.empty(m, np.uint8), "key0": np.empty((m, 5), np.int64), "key1": np.empty((m, 5), np.int64),
+         "ck": np.empty((m, 5), np.int64), "ev_key": np.empty((2 * m, 5), np.int64), "ev_hash": np.empty(2 * m, np.uint64),
+         "ev_mask": np.empty(2 * m, np.uint32), "r_seq": np.empty(2 * m, np.int64), "r_k0": np.empty((2 * m, 5), np.int64),
+         "r_k1": np.empty((2 * m, 5), np.int64), "r_mask": np.empty(2 * m, np.int64), "r_off3": np.empty((2 * m, 3), np.int64),
+         "r_len3": np.empty((2 * m, 3), np.int32)}
+    o = EvidenceOut()
+    for k, arr in r.items():
+        setattr(o, k, arr.ctypes.data)
+    rc = lib.fc_ingest_evidence(C.byref(i), C.byref(o))
+    if rc != 0:
+        raise RuntimeError("fc_ingest_evidence failed (%d)" % rc)
+    ne, nr = int(o.n_events), int(o.n_reads)
+    # (events are few: copies, so that the full-size buffers do not stay alive behind small views)
+    for k in ("ev_key", "ev_hash", "ev_mask"):
+        r[k] = r[k][:ne].copy()
+    for k in ("r_seq", "r_k0", "r_k1", "r_mask", "r_off3", "r_len3"):
+        r[k] = r[k][:nr] if 2 * nr >= len(r[k]) else r[k][:nr].copy()
+    r["counters"] = [int(o.counters[k]) for k in range(4)]
+    r["any_hit"] = bool(o.any_hit)
+    return r
+
+
 class NativeIngest(object):
     def __init__(self, asize, margin, min_uniq_qual, nolinear, names, tid2gid, cap=1 << 18, n_words=8, cap_complex=1 << 16,
                  first_fragment=0, at_stream_start=True):

@@ -682,7 +682,7 @@ class Run(object):
             self.add_fragment(mate1, mate2)
         self.flush()
 
-    def process_native(self, fh, chunk_bytes: int = 64 << 20, first_fragment: int = 0, at_stream_start: bool = True):
+    def process_native(self, fh, chunk_bytes: int = 32 << 20, first_fragment: int = 0, at_stream_start: bool = True):
         """SAM text (binary file object, header included) through the native ingest (csrc/ingest.cu); fragments it does
         not handle go through add_fragment().  Same results as process(), an order of magnitude less host time.
         first_fragment / at_stream_start: this stream is a part of a larger one (one rank of a multi-GPU run)."""
@@ -742,21 +742,37 @@ class Run(object):
                     break  # (a fragment has up to two rows) the rest is an incomplete fragment: wait for the next chunk
             return out, off
 
+        def consume_parsed(buf, jobs):
+            for job in jobs:
+                results, _ = job.result()
+                for (o0, n, m, max_l, n_frag, counters, cx, arrays) in results:
+                    consume(buf, o0, arrays, n, m, max_l, n_frag, counters, cx, n)
+
         try:
+            if threads > 1:
+                from concurrent.futures import ThreadPoolExecutor
+
+                pool = ThreadPoolExecutor(threads + 1)
+            # Three things overlap: the file read of chunk k+2 (one pool thread), the parse of chunk k+1 (parser threads, in
+            # C++ without the GIL) and, on this thread, the GPU call + evidence rules + python-path fragments of chunk k.
+            # The only dependency between chunks is the tail an earlier parse left over (an incomplete last fragment).
+            ahead = pool.submit(fh.read, chunk_bytes) if pool is not None else None
+            waiting = None  # (buf, jobs) of the chunk whose results the main thread has not consumed yet
             while not eof:
-                chunk = fh.read(chunk_bytes)
+                chunk = ahead.result() if ahead is not None else fh.read(chunk_bytes)
                 eof = len(chunk) == 0  # (a stream may return short chunks before its end: BAM text comes in whole lines)
+                if ahead is not None and not eof:
+                    ahead = pool.submit(fh.read, chunk_bytes)
                 buf = carry + chunk if carry else chunk
                 if not len(buf):
                     break
                 cuts = _piece_cuts(buf, threads) if threads > 1 and len(buf) > int(getattr(opt, "ingest_piece_bytes", 4 << 20)) else [0, len(buf)]
                 if len(cuts) == 2:
+                    if waiting is not None:
+                        consume_parsed(*waiting)
+                        waiting = None
                     _, off = parse_piece(ings[0], buf, 0, len(buf), eof, False)
                 else:
-                    if pool is None:
-                        from concurrent.futures import ThreadPoolExecutor
-
-                        pool = ThreadPoolExecutor(threads)
                     while len(ings) < len(cuts) - 1:
                         ings.append(mk(0, False))
                     # every piece numbers its fragments from its own base: more than it can hold apart (a SAM line is > 16 bytes)
@@ -768,16 +784,18 @@ class Run(object):
                             ings[k].set_position(next_ord + k * stride, False)
                         last = k == len(cuts) - 2
                         jobs.append(pool.submit(parse_piece, ings[k], buf, cuts[k], cuts[k + 1], eof if last else True, True))
-                    off = 0
-                    for k, job in enumerate(jobs):
-                        results, end_off = job.result()
-                        for (o0, n, m, max_l, n_frag, counters, cx, arrays) in results:
-                            consume(buf, o0, arrays, n, m, max_l, n_frag, counters, cx, n)
-                        off = end_off
+                    if waiting is not None:  # (while the pool parses this chunk)
+                        consume_parsed(*waiting)
+                    waiting = (buf, jobs)
+                    off = jobs[-1].result()[1]
+                    for job in jobs:
+                        job.result()  # (every handle is free again; a parser error surfaces here)
                     ings[0].set_position(next_ord + (len(cuts) - 1) * stride, False)
                 carry = buf[off:]
                 if eof and carry.strip():
                     raise ValueError("unparsable trailing SAM text")
+            if waiting is not None:
+                consume_parsed(*waiting)
             self.flush()
         finally:
             if pool is not None:
@@ -787,12 +805,12 @@ class Run(object):
 
     def _native_batch(self, buf, off, a, n, m, max_l, n_words, plane_stride, lib):
         """scan + record the n rows of m fragments the native ingest produced, then the evidence rules of record_hits
-        (find_circ.py:1276-1439) for all fragments at once: with at most two spans per fragment (back-splices first) every
-        rule is a comparison between the fragment's columns -- same outcome as _record_hits(), which stays the reading
-        of the reference for everything else"""
-        from .ingest import FR_BROKEN, FR_OTHER_CHROM, FR_TWO_MATES, FR_UNSPLICED
+        (find_circ.py:1276-1439) for all fragments at once in C++ (fc_ingest_evidence: with at most two spans per fragment,
+        back-splices first, every rule is a comparison between the fragment's columns) -- same outcome as _record_hits(),
+        which stays the reading of the reference for everything else"""
+        from .ingest import EV_LIN0, EV_LIN0_OUT, EV_LIN1, EV_LIN1_OUT, EV_UN, EV_UN_OUT, evidence
 
-        N, opt, B = self.N, self.opt, FLAG_BIT
+        N, opt = self.N, self.opt
         idx = a["frag_seq"][:n].astype(np.uint64) * np.uint64(64) + a["idx_k"][:n].astype(np.uint64)
         t0 = time.perf_counter()
         hits = self.eng.batch_host_planes(n, a["chrom"], a["a_start"], a["b_end"], a["l"], a["flags"], a["rlo"], a["rhi"], a["rn"],
@@ -800,70 +818,15 @@ class Run(object):
                                           a["qname_hash"], idx=idx, emit=True)
         self.t_scan += time.perf_counter() - t0
         self.n_pairs_scanned += n
-        has = (hits["w2"] & 0xFFFF) > 0
-        state, kind, ff = a["f_state"][:m], a["f_kind"][:m], a["f_flags"][:m]
-        row0 = a["f_row0"][:m].astype(np.int64)
-        two = a["f_nsp"][:m] == 2
-        queued = [(state & 1) > 0, (state & 2) > 0]
-        row = [np.where(queued[0], row0, 0), np.where(queued[1], row0 + (state & 1), 0)]
-        circ = [(kind & 1) > 0, (kind & 2) > 0]
-        lin = [~circ[0], two & ~circ[1]]
-        hit = [queued[j] & has[row[j]] for j in (0, 1)]
-        count = np.count_nonzero
-        for key, cnt in (("circ_spliced", sum(count(circ[j] & hit[j]) for j in (0, 1))),
-                         ("circ_no_bp", sum(count(circ[j] & queued[j] & ~hit[j]) for j in (0, 1))),
-                         ("lin_spliced", sum(count(lin[j] & hit[j]) for j in (0, 1))),
-                         ("lin_no_bp", sum(count(lin[j] & queued[j] & ~hit[j]) for j in (0, 1)))):
+        ev = evidence(lib, a, hits, n, m, off, opt.asize, FLAG_BIT)
+        for key, cnt in zip(("circ_spliced", "circ_no_bp", "lin_spliced", "lin_no_bp"), ev["counters"]):
             if cnt:  # the reference's counter dict only holds keys that were incremented (find_circ.py:1146)
                 N[key] += float(cnt)
-        if not (hit[0].any() or hit[1].any()):
+        if not ev["any_hit"]:
             return
-        # junction of every span: chrom id, start, end, minus, kind
-        chrom = a["chrom"][:n].astype(np.int64)
-        h_start, h_end, h_minus = hits["start"].astype(np.int64), hits["end"].astype(np.int64), (hits["w3"] & 1).astype(np.int64)
-        key = [np.stack([chrom[row[j]], h_start[row[j]], h_end[row[j]], h_minus[row[j]], lin[j].astype(np.int64)], axis=1) for j in (0, 1)]
-        ch = [circ[j] & hit[j] for j in (0, 1)]
-        both = ch[0] & ch[1]
-        multi = both & (key[0] != key[1]).any(axis=1)     # two different back-splices (find_circ.py:1319-1329)
-        circ_any = ch[0] | ch[1]
-        single = circ_any & ~multi
-        ck = np.where(ch[1][:, None], key[1], key[0])      # the (last) back-splice of the fragment
-        cs, ce = ck[:, 1], ck[:, 2]
-        W = np.zeros(m, dtype=np.uint32)
-
-        def flag(cond, name):
-            W[cond] |= np.uint32(B[name])
-
-        flag((circ[0] & queued[0] & ~hit[0]) | (circ[1] & queued[1] & ~hit[1]), "WARN_UNRESOLVED_EXTRA_BACKSPLICE")
-        flag(single & circ[0] & circ[1], "SUPPORT_CLOSURE")
-        lin_ev, lin_out = [], []
-        for j in (0, 1):
-            flag(lin[j] & queued[j] & ~hit[j], "WARN_UNRESOLVED_LINSPLICE")
-            ev = lin[j] & hit[j] & single
-            outside = (key[j][:, 1] <= cs) | (key[j][:, 2] >= ce)
-            flag(ev & outside, "WARN_OUTSIDE_SPLICE_JUNCTION")
-            flag(ev & ~outside, "SUPPORT_INSIDE_SPLICE_JUNCTION")
-            lin_ev.append(ev)
-            lin_out.append(outside)
-        un = ((ff & FR_UNSPLICED) > 0) & single
-        un_other = un & ((ff & FR_OTHER_CHROM) > 0)
-        un_pos, un_aend = a["f_un_pos"][:m].astype(np.int64), a["f_un_aend"][:m].astype(np.int64)
-        un_outside = un & ~un_other & ((un_pos + opt.asize <= cs) | (un_aend - opt.asize >= ce))
-        flag(un_other, "WARN_OTHER_CHROM_MATE")
-        flag(un_outside, "WARN_OUTSIDE_MATE")
-        flag(un & ~un_other & ~un_outside, "SUPPORT_INSIDE_MATE")
-        flag(single & ((ff & FR_BROKEN) > 0), "BROKEN_SEGMENTS")
-        W[multi] = B["WARN_MULTI_BACKSPLICE"]
-        name_hash = a["qname_hash"][:n][row0]
         # ---- per-junction flags (find_circ.py:1325-1327, 1433-1437)
-        ev1 = np.nonzero(single & (W != 0))[0]
-        evm = np.nonzero(multi)[0]
-        if len(ev1) or len(evm):
-            self.ev_native.append((np.concatenate([ck[ev1], key[0][evm], key[1][evm]]),
-                                   np.concatenate([name_hash[ev1], name_hash[evm], name_hash[evm]]),
-                                   np.concatenate([W[ev1], W[evm], W[evm]])))
-        txt_off = a["f_txt_off"][:6 * m].reshape(m, 2, 3)
-        txt_len = a["f_txt_len"][:6 * m].reshape(m, 2, 3)
+        if len(ev["ev_mask"]):
+            self.ev_native.append((ev["ev_key"], ev["ev_hash"], ev["ev_mask"]))
         base = C.cast(C.c_char_p(buf), C.c_void_p).value
 
         def gather(off3, len3):
@@ -875,28 +838,25 @@ class Run(object):
 
         # ---- multi-event rows (find_circ.py:1429-1431)
         if opt.multi_events:
-            me = np.nonzero(lin_ev[0] | lin_ev[1] | un)[0]
+            cls = ev["cls"]
+            me = np.nonzero(cls & (EV_LIN0 | EV_LIN1 | EV_UN))[0]
             if len(me):
+                txt_off = a["f_txt_off"][:6 * m].reshape(m, 2, 3)
+                txt_len = a["f_txt_len"][:6 * m].reshape(m, 2, 3)
                 off3 = np.ascontiguousarray(txt_off[me, 0] + off)
                 len3 = np.ascontiguousarray(txt_len[me, 0])
                 len3[:, 1:] = -1  # (the name only)
+                c = cls[me]
                 self.native_multi.append(dict(
-                    seqs=a["f_seq"][:m][me].copy(), names=gather(off3, len3), name_len=len3[:, 0].copy(), ck=ck[me],
-                    lin=[(lin_ev[j][me], lin_out[j][me], key[j][me]) for j in (0, 1)],
-                    un=(un[me], (un_other | un_outside)[me], a["f_un_tid"][:m][me].copy(), un_pos[me], un_aend[me])))
+                    seqs=a["f_seq"][:m][me].copy(), names=gather(off3, len3), name_len=len3[:, 0].copy(), ck=ev["ck"][me],
+                    lin=[((c & EV_LIN0) > 0, (c & EV_LIN0_OUT) > 0, ev["key0"][me]), ((c & EV_LIN1) > 0, (c & EV_LIN1_OUT) > 0, ev["key1"][me])],
+                    un=((c & EV_UN) > 0, (c & EV_UN_OUT) > 0, a["f_un_tid"][:m][me].copy(), a["f_un_pos"][:m][me].astype(np.int64),
+                        a["f_un_aend"][:m][me].astype(np.int64))))
         # ---- the reads of every fragment with a junction (find_circ.py:1439, 1442-1447): name, sequence and qualities of
         # both mates go into one compact blob (C++); the FASTQ records are formatted from it when the junction names are
         # known (reads_text)
-        fr = np.nonzero(hit[0] | hit[1])[0]
-        first = np.where(hit[0][fr, None], key[0][fr], key[1][fr])
-        second = np.where((hit[0] & hit[1])[fr, None] & (key[0][fr] != key[1][fr]).any(axis=1)[:, None], key[1][fr], -1)
-        n_mates = 1 + ((ff[fr] & FR_TWO_MATES) > 0)
-        who = np.repeat(np.arange(len(fr)), n_mates)
-        mate = np.arange(len(who)) - np.repeat(np.cumsum(n_mates) - n_mates, n_mates)
-        off3 = np.ascontiguousarray(txt_off[fr[who], mate] + off)
-        len3 = np.ascontiguousarray(txt_len[fr[who], mate])
-        self.native_reads.append(dict(seqs=a["f_seq"][:m][fr[who]].copy(), blob=gather(off3, len3), len3=len3,
-                                      k0=first[who], k1=second[who], mask=W[fr[who]].astype(np.int64)))
+        self.native_reads.append(dict(seqs=ev["r_seq"], blob=gather(ev["r_off3"], ev["r_len3"]), len3=ev["r_len3"], k0=ev["r_k0"],
+                                      k1=ev["r_k1"], mask=ev["r_mask"]))
 
     # ------------------------------------------------------------------ outputs
     def finalize(self, dist=None, torch_dev=None):

@@ -446,6 +446,53 @@ const char* fc_bam_ref_name(const fc_bam* b, int32_t i);
 int64_t fc_bam_ref_length(const fc_bam* b, int32_t i);
 int64_t fc_bam_read_text(fc_bam* b, char* out, int64_t cap);
 
+/* The evidence rules of record_hits (find_circ.py:1276-1439, flags of :1319-1344, :1369-1375, :1396-1437) for one batch of
+ * the native ingest: the n rows / m fragment records of an fc_ingest_parse call plus the scan's answers for the rows.
+ * Every fragment here has at most two spans, so each rule is a comparison between its columns: one host pass in C++.
+ * `bit`: the flag bits in this order -- WARN_UNRESOLVED_EXTRA_BACKSPLICE, SUPPORT_CLOSURE, WARN_UNRESOLVED_LINSPLICE,
+ * WARN_OUTSIDE_SPLICE_JUNCTION, SUPPORT_INSIDE_SPLICE_JUNCTION, WARN_OTHER_CHROM_MATE, WARN_OUTSIDE_MATE,
+ * SUPPORT_INSIDE_MATE, BROKEN_SEGMENTS, WARN_MULTI_BACKSPLICE.  Keys are (chrom id, start, end, minus, kind) rows. */
+#define FC_EV_HIT0 1u      /* fc_evidence_out.cls: the first / second span found a breakpoint */
+#define FC_EV_HIT1 2u
+#define FC_EV_LIN0 4u      /* the first / second span is a linear splice next to the fragment's one back-splice ... */
+#define FC_EV_LIN1 8u
+#define FC_EV_LIN0_OUT 16u /* ... and lies outside of it */
+#define FC_EV_LIN1_OUT 32u
+#define FC_EV_UN 64u       /* an unspliced mate next to the one back-splice ... */
+#define FC_EV_UN_OUT 128u  /* ... on another chromosome or outside of it */
+typedef struct fc_evidence_in {
+  int64_t n, m;
+  const fc_hit* hits;          /* n */
+  const int32_t* chrom;        /* n */
+  const uint64_t* qname_hash;  /* n */
+  const int64_t* f_seq;        /* m: fc_ingest_out columns of the same names */
+  const int32_t* f_row0;
+  const uint8_t *f_nsp, *f_kind, *f_state, *f_flags;
+  const int32_t *f_un_pos, *f_un_aend;
+  const int64_t* f_txt_off;    /* 6 m */
+  const int32_t* f_txt_len;    /* 6 m */
+  int64_t text_off;            /* added to every text offset (position of the parsed piece in the caller's buffer) */
+  int32_t asize;
+  uint32_t bit[10];
+} fc_evidence_in;
+typedef struct fc_evidence_out {
+  int64_t counters[4];         /* circ_spliced, circ_no_bp, lin_spliced, lin_no_bp (find_circ.py:1303-1317, 1350-1367) */
+  int64_t n_events, n_reads;
+  int32_t any_hit;
+  uint32_t* W;                 /* m: flag word of the fragment */
+  uint8_t* cls;                /* m: FC_EV_* */
+  int64_t *key0, *key1, *ck;   /* m x 5: junction of span 0 / span 1 / the (last) back-splice */
+  int64_t* ev_key;             /* 2 m x 5: per-junction evidence events (find_circ.py:1325-1327, 1433-1437) ... */
+  uint64_t* ev_hash;           /* ... the fragment's name hash ... */
+  uint32_t* ev_mask;           /* ... and its flags */
+  int64_t* r_seq;              /* 2 m: reads to write (find_circ.py:1439-1447), one per mate: stream position, ... */
+  int64_t *r_k0, *r_k1;        /* ... first and (or -1) second junction, */
+  int64_t* r_mask;             /* flags, */
+  int64_t* r_off3;             /* 2 m x 3: name / sequence / qualities in the text buffer (for fc_text_gather) */
+  int32_t* r_len3;
+} fc_evidence_out;
+int fc_ingest_evidence(const fc_evidence_in* in, fc_evidence_out* out);
+
 /* Spliced reads of the native ingest (write_read, find_circ.py:1442-1447): fc_text_gather copies n x 3 substrings
  * (name, sequence, qualities; off/len row major, len < 0 = absent) of a text buffer back to back into `out` and returns
  * the bytes written; fc_fastq_format turns such a blob into FASTQ records "@<name> <tail>\n<seq>\n+<name> <tail>\n<qual>\n"

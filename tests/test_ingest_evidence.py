@@ -1,0 +1,52 @@
+"""fc_ingest_evidence (C++, csrc/ingest.cu) against its numpy twin (tests/evidence_numpy.py) on random fragment records:
+every combination of queued / back-splice / hit / unspliced-mate / broken flags that a two-span fragment can show.
+The reference's own answers for these rules are pinned by the goldens (test_pipeline_host_logic.py, test_gpu_pipeline.py)."""
+import numpy as np
+import pytest
+
+from evidence_numpy import evidence_numpy
+from find_circ2_b200 import _lib
+from find_circ2_b200._lib import HIT_DTYPE
+from find_circ2_b200.ingest import evidence
+from find_circ2_b200.pipeline import FLAG_BIT
+
+
+def _random_batch(m, seed):
+    rng = np.random.default_rng(seed)
+    state = rng.choice(np.array([0, 1, 2, 3], dtype=np.uint8), m, p=[0.05, 0.45, 0.1, 0.4])
+    nrows = (state & 1) + ((state >> 1) & 1)
+    row0 = np.zeros(m, dtype=np.int32)
+    row0[1:] = np.cumsum(nrows[:-1])
+    n = int(nrows.sum())
+    a = {"f_state": state, "f_row0": row0, "f_nsp": rng.integers(1, 3, m).astype(np.uint8), "f_kind": rng.integers(0, 4, m).astype(np.uint8),
+         "f_flags": rng.integers(0, 16, m).astype(np.uint8), "f_un_tid": rng.integers(0, 3, m).astype(np.int32),
+         "f_un_pos": rng.integers(0, 3000, m).astype(np.int32), "f_seq": np.arange(m, dtype=np.int64) * 3 + 5,
+         "f_txt_off": rng.integers(0, 1 << 20, 6 * m).astype(np.int64), "f_txt_len": rng.integers(-1, 120, 6 * m).astype(np.int32),
+         "chrom": rng.integers(0, 3, max(n, 1)).astype(np.int32), "qname_hash": rng.integers(0, 1 << 62, max(n, 1)).astype(np.uint64)}
+    a["f_un_aend"] = (a["f_un_pos"] + rng.integers(20, 200, m)).astype(np.int32)
+    hits = np.zeros(max(n, 1), dtype=HIT_DTYPE)
+    # few distinct coordinates: the two spans of a fragment often name the same junction, nest or lie apart
+    hits["start"] = rng.integers(0, 8, len(hits)) * 400
+    hits["end"] = hits["start"] + rng.integers(1, 6, len(hits)) * 400
+    hits["w2"] = np.where(rng.random(len(hits)) < 0.8, rng.integers(1, 4, len(hits)), 0) | (rng.integers(0, 3, len(hits)) << 16)
+    hits["w3"] = rng.integers(0, 2, len(hits)) | (0x4D3 << 1)
+    return a, hits, n
+
+
+@pytest.mark.parametrize("m,seed", [(1, 1), (7, 2), (1000, 3), (50000, 4)])
+def test_evidence_pass_equals_numpy_twin(m, seed):
+    lib = _lib.load()
+    a, hits, n = _random_batch(m, seed)
+    got = evidence(lib, a, hits, n, m, 1000, 20, FLAG_BIT)
+    want = evidence_numpy(a, hits, n, m, 1000, 20, FLAG_BIT)
+    assert got["counters"] == want["counters"] and got["any_hit"] == want["any_hit"]
+    for k in ("W", "cls", "key0", "key1", "ck", "r_seq", "r_k0", "r_k1", "r_mask", "r_off3", "r_len3"):
+        assert np.array_equal(got[k], want[k]), k
+    # the events come in another order (the product sorts them per junction anyway)
+    def canon(r):
+        rows = np.concatenate([r["ev_key"], r["ev_hash"].astype(np.int64)[:, None], r["ev_mask"].astype(np.int64)[:, None]], axis=1)
+        return rows[np.lexsort(rows.T[::-1])]
+    assert np.array_equal(canon(got), canon(want))
+    if m >= 1000:
+        assert len(got["ev_mask"]) > 0 and len(got["r_seq"]) > m // 2
+        assert len(set(got["W"].tolist())) > 8  # the flags really vary
