@@ -61,6 +61,9 @@ struct Ingest {
   int last_tid = -1;
   int64_t frag_seq = 0;
   bool first_record = true;
+  int64_t planes_rows = -1;  // rows / words of the plane arrays that the last call has written (-1: unknown, clear everything)
+  int planes_words = 0;
+  const void* planes_of = nullptr;
 
   int lookup(sv name) {
     if (name.size() == last_name.size() && memcmp(name.data(), last_name.data(), name.size()) == 0) return last_tid;
@@ -158,17 +161,61 @@ struct Ingest {
   }
 };
 
-inline void pack_planes(sv s, int n_words, int64_t stride, int64_t row, uint32_t* rlo, uint32_t* rhi, uint32_t* rn, bool& any_n) {
-  for (int w = 0; w < n_words; ++w) {
+// 8 bases -> 8 bits of the low plane, the high plane and the N plane (bit j = base j).  Upper-cased ASCII: A 0x41, C 0x43,
+// G 0x47, T 0x54, so code bit 0 = bit 1 ^ bit 2 and code bit 1 = bit 2 of the letter; anything else is N (code 0), like
+// fc::pack32 (scan_core.cuh), which the device uses and tests/ compare with.
+inline uint64_t zero_bytes(uint64_t v) {  // 0x80 in every byte of v that is zero (exact)
+  const uint64_t k = 0x7F7F7F7F7F7F7F7FULL;
+  return ~(((v & k) + k) | v | k);
+}
+inline uint32_t gather_bit0(uint64_t v) {  // bit 0 of every byte -> 8 bits
+  return (uint32_t)(((v & 0x0101010101010101ULL) * 0x0102040810204080ULL) >> 56);
+}
+inline void pack8(uint64_t x, uint32_t& lo, uint32_t& hi, uint32_t& nn) {
+  x &= 0xDFDFDFDFDFDFDFDFULL;
+  const uint64_t acgt = zero_bytes(x ^ 0x4141414141414141ULL) | zero_bytes(x ^ 0x4343434343434343ULL) |
+                        zero_bytes(x ^ 0x4747474747474747ULL) | zero_bytes(x ^ 0x5454545454545454ULL);
+  uint64_t l = (x >> 1) ^ (x >> 2), h = x >> 2;
+  if (acgt != 0x8080808080808080ULL) {
+    const uint64_t keep = (acgt >> 7) * 0xFFULL;  // 0xFF in the bytes that hold A, C, G or T
+    l &= keep;
+    h &= keep;
+    nn = gather_bit0(~acgt >> 7);
+  } else {
+    nn = 0;
+  }
+  lo = gather_bit0(l);
+  hi = gather_bit0(h);
+}
+inline void pack32_host(const uint8_t* src, int count, uint32_t& lo, uint32_t& hi, uint32_t& nn) {
+  lo = hi = nn = 0;
+  for (int j = 0; j < count; j += 8) {
+    uint64_t x = 0x4141414141414141ULL;  // (bases beyond the end read as A = all planes 0)
+    const int take = count - j < 8 ? count - j : 8;
+    memcpy(&x, src + j, (size_t)take);
+    uint32_t a, b, c;
+    pack8(x, a, b, c);
+    lo |= a << j;
+    hi |= b << j;
+    nn |= c << j;
+  }
+}
+
+// the internal read part of row `row` as bit planes (column-major: word w of every row is contiguous).  Only the words the
+// part reaches are written: fc_ingest_parse clears what an earlier call left in the arrays, in bulk.
+inline int pack_planes(sv s, int n_words, int64_t stride, int64_t row, uint32_t* rlo, uint32_t* rhi, uint32_t* rn, bool& any_n) {
+  const int used = ((int)s.size() + 31) / 32 < n_words ? ((int)s.size() + 31) / 32 : n_words;
+  for (int w = 0; w < used; ++w) {
     uint32_t lo = 0, hi = 0, nn = 0;
     int count = (int)s.size() - 32 * w;
     if (count > 32) count = 32;
-    if (count > 0) fc::pack32(reinterpret_cast<const uint8_t*>(s.data()) + 32 * w, count, lo, hi, nn);
+    pack32_host(reinterpret_cast<const uint8_t*>(s.data()) + 32 * w, count, lo, hi, nn);
     rlo[(int64_t)w * stride + row] = lo;
     rhi[(int64_t)w * stride + row] = hi;
     rn[(int64_t)w * stride + row] = nn;
     if (nn) any_n = true;
   }
+  return used;
 }
 
 }  // namespace
@@ -214,6 +261,21 @@ extern "C" int64_t fc_ingest_parse(fc_ingest* h, const char* text, int64_t nbyte
   o->n_fragments = 0;
   o->max_l = 0;
   for (int k = 0; k < 8; ++k) o->counters[k] = 0;
+  {
+    // rows write only the plane words their read part reaches: whatever an earlier call left behind goes now, in bulk
+    // (the first call, or a call with other arrays, clears them whole)
+    const bool same = g.planes_of == (const void*)o->rlo && g.planes_rows >= 0;
+    const int words = same ? g.planes_words : o->n_words;
+    const int64_t rows = same ? g.planes_rows : o->cap;
+    for (int w = 0; w < words; ++w) {
+      memset(o->rlo + (int64_t)w * o->cap, 0, (size_t)rows * 4);
+      memset(o->rhi + (int64_t)w * o->cap, 0, (size_t)rows * 4);
+      memset(o->rn + (int64_t)w * o->cap, 0, (size_t)rows * 4);
+    }
+    g.planes_of = o->rlo;
+    g.planes_rows = 0;
+    g.planes_words = 0;
+  }
   enum { C_TOTAL_MATES, C_UNMAPPED, C_UNSPLICED, C_TOO_SHORT, C_CIRC_NOT_UNIQ, C_LIN_NOT_UNIQ };
 
   std::vector<Rec> frag;       // mapped records of the current fragment (first record regardless of its flag)
@@ -382,7 +444,8 @@ extern "C" int64_t fc_ingest_parse(fc_ingest* h, const char* text, int64_t nbyte
         o->b_end[i] = sp.B->aend - eff;
         o->l[i] = l;
         bool any_n = false;
-        pack_planes(internal, o->n_words, o->cap, i, o->rlo, o->rhi, o->rn, any_n);
+        const int used = pack_planes(internal, o->n_words, o->cap, i, o->rlo, o->rhi, o->rn, any_n);
+        if (used > g.planes_words) g.planes_words = used;
         o->flags[i] = (uint8_t)((sp.backsplice ? 1 : 0) | ((p.flag & 0x10) ? 2 : 0) | (any_n ? 4 : 0));
         o->wden[i] = (uint8_t)sp.den;
         const int qa = sp.A->AS - (sp.A->has_XS ? sp.A->XS : 0), qb = sp.B->AS - (sp.B->has_XS ? sp.B->XS : 0);
@@ -394,6 +457,7 @@ extern "C" int64_t fc_ingest_parse(fc_ingest* h, const char* text, int64_t nbyte
         o->idx_k[i] = (uint8_t)kq++;
         if (l > o->max_l) o->max_l = l;
         o->n_rows++;
+        g.planes_rows = o->n_rows;
       }
       o->f_kind[fi] = kind;
       o->f_state[fi] = state;

@@ -50,3 +50,54 @@ def test_evidence_pass_equals_numpy_twin(m, seed):
     if m >= 1000:
         assert len(got["ev_mask"]) > 0 and len(got["r_seq"]) > m // 2
         assert len(set(got["W"].tolist())) > 8  # the flags really vary
+
+
+def test_native_ingest_planes_for_every_kind_of_letter():
+    """the ingest's word-at-a-time packer (csrc/ingest.cu: pack8) against the plain definition of the planes: bit j of word w =
+    code of base 32 w + j of the internal read part (A 0, C 1, G 2, T 3, lower case alike; anything else: N plane, code 0)"""
+    from find_circ2_b200.ingest import NativeIngest
+
+    rng = np.random.default_rng(11)
+    letters = np.frombuffer(b"ACGTacgtNnRYKMSWBDHVXacgtACGTACGTACGTACGTACGT", dtype=np.uint8)
+    asize, margin, L = 20, 2, 150
+    eff = asize - margin
+    lines, reads = [], []
+    for k in range(300):
+        seq = bytes(rng.choice(letters, L)).decode()
+        cut = int(rng.integers(asize, L - asize))
+        pos_a, pos_b = 5000 + 3 * k, 1000 + 3 * k
+        lines.append("r%d\t0\tchr1\t%d\t60\t%dM%dS\t*\t0\t0\t%s\t*\tAS:i:%d\tXS:i:0\n" % (k, pos_a + 1, cut, L - cut, seq, cut))
+        lines.append("r%d\t2048\tchr1\t%d\t60\t%dH%dM\t*\t0\t0\t%s\t*\tAS:i:%d\tXS:i:0\n" % (k, pos_b + 1, cut, L - cut, seq[cut:], L - cut))
+        reads.append(seq)
+    text = ("@SQ\tSN:chr1\tLN:100000\n" + "".join(lines)).encode()
+    ing = NativeIngest(asize, margin, 2, False, ["chr1"], [0], cap=1024, n_words=8)
+    for rep in range(2):  # twice into the same arrays: what the first call wrote must not shine through
+        used = ing.parse(text, 0, True)
+        assert used == len(text)
+        n = int(ing.out.n_rows)
+        assert n == 300 and int(ing.out.n_complex) == 0
+        planes = {k: ing.a[k].reshape(8, ing.cap) for k in ("rlo", "rhi", "rn")}
+        for i, seq in enumerate(reads):
+            internal = seq[eff:L - eff]
+            assert int(ing.a["l"][i]) == len(internal)
+            for w in range(8):
+                lo = hi = nn = 0
+                for j, ch in enumerate(internal[32 * w:32 * w + 32]):
+                    code = "ACGT".find(ch.upper())
+                    if code < 0:
+                        nn |= 1 << j
+                        code = 0
+                    lo |= (code & 1) << j
+                    hi |= (code >> 1) << j
+                assert (int(planes["rlo"][w, i]), int(planes["rhi"][w, i]), int(planes["rn"][w, i])) == (lo, hi, nn), (i, w)
+        # second round: shorter reads in the same rows (fewer words per row)
+        reads = [s[:100] for s in reads]
+        L2 = 100
+        lines = []
+        for k, seq in enumerate(reads):
+            cut = 50
+            lines.append("r%d\t0\tchr1\t%d\t60\t%dM%dS\t*\t0\t0\t%s\t*\tAS:i:%d\tXS:i:0\n" % (k, 5001 + 3 * k, cut, L2 - cut, seq, cut))
+            lines.append("r%d\t2048\tchr1\t%d\t60\t%dH%dM\t*\t0\t0\t%s\t*\tAS:i:%d\tXS:i:0\n" % (k, 1001 + 3 * k, cut, L2 - cut, seq[cut:], L2 - cut))
+        text = ("@SQ\tSN:chr1\tLN:100000\n" + "".join(lines)).encode()
+        L = L2
+    ing.close()
