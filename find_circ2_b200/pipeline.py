@@ -988,20 +988,25 @@ class Run(object):
         lib = _lib.load()
         py_seqs = np.array([e[0] for e in self.reads_out], dtype=np.int64)
         pieces, done = [], 0
+        # the tail of a record's header ("<junction names> <flags>") is the same for every read of a (junctions, flags)
+        # combination: one table of tails for the whole run, one index per read
+        uniq, inverse = _unique_rows(np.concatenate([np.concatenate([b["k0"], b["k1"], b["mask"][:, None]], axis=1) for b in self.native_reads]))
+        jn = []
+        for u in uniq.tolist():
+            nm = names[(u[0], u[1], u[2], "-" if u[3] else "+", u[4])]
+            if u[5] >= 0:
+                nm = ",".join(sorted((nm, names[(u[5], u[6], u[7], "-" if u[8] else "+", u[9])])))
+            jn.append((nm + " " + flag_text(u[10])).encode("latin-1"))
+        name_len = np.array([len(x) for x in jn], dtype=np.int32)
+        name_off = np.zeros(len(jn), dtype=np.int64)
+        name_off[1:] = np.cumsum(name_len[:-1])
+        names_blob = b"".join(jn)
+        inverse = np.ascontiguousarray(inverse.reshape(-1), dtype=np.int32)
+        at = 0
         for b in self.native_reads:
-            uniq, inverse = _unique_rows(np.concatenate([b["k0"], b["k1"], b["mask"][:, None]], axis=1))
-            jn = []
-            for u in uniq.tolist():
-                nm = names[(u[0], u[1], u[2], "-" if u[3] else "+", u[4])]
-                if u[5] >= 0:
-                    nm = ",".join(sorted((nm, names[(u[5], u[6], u[7], "-" if u[8] else "+", u[9])])))
-                jn.append((nm + " " + flag_text(u[10])).encode("latin-1"))
-            name_len = np.array([len(x) for x in jn], dtype=np.int32)
-            name_off = np.zeros(len(jn), dtype=np.int64)
-            name_off[1:] = np.cumsum(name_len[:-1])
-            names_blob = b"".join(jn)
-            name_idx = np.ascontiguousarray(inverse.reshape(-1), dtype=np.int32)
-            m = len(name_idx)
+            m = len(b["seqs"])
+            name_idx = inverse[at:at + m]
+            at += m
             rec_off = np.zeros(m + 1, dtype=np.int64)
             args = (b["blob"].ctypes.data, m, b["len3"].ctypes.data, name_idx.ctypes.data, names_blob, name_off.ctypes.data,
                     name_len.ctypes.data)
