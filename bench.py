@@ -320,6 +320,7 @@ def dropin_parity(eng, spec, cfg, n_sample, large=True, error_rate=None):
         threads = opt.ingest_threads or max(1, min(16, os.cpu_count() or 1))
         res["native_large"] = {"pairs_per_s": n_sample * copies / host_s, "reads": n_sample * copies, "sam_bytes": os.path.getsize(big),
                                "parser_threads": threads, "seconds_host": host_s, "seconds_gpu_calls": out["seconds_gpu_calls"],
+                               "seconds_main_thread": out.get("seconds_ingest_stages"),
                                "seconds_writers": out["seconds_total"] - out["seconds_ingest_and_scan"],
                                "seconds_wall": out["seconds_total"], "junction_rows": out["circ"].count("\n") + out["lin"].count("\n") - 2}
     n_rows = len(want.circ_bed.splitlines()) + len(want.lin_bed.splitlines()) - 2

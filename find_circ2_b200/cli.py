@@ -366,6 +366,7 @@ def run_to_strings(opt: Options, path=None, engine=None, native=None):
             "n_pairs_scanned": run.n_pairs_scanned,
             "seconds_ingest_and_scan": t1 - t0,
             "seconds_gpu_calls": run.t_scan,
+            "seconds_ingest_stages": {k: round(v, 4) for k, v in getattr(run, "t_ingest", {}).items()},
             "seconds_total": time.perf_counter() - t0,
         }
     finally:

@@ -97,6 +97,13 @@ def evidence(lib, a: dict, hits: np.ndarray, n: int, m: int, text_off: int, asiz
     return r
 
 
+def text_address(buf) -> int:
+    """address of the first byte of a bytes / bytearray object (which the caller keeps alive and does not resize)"""
+    if isinstance(buf, bytearray):
+        return C.addressof(C.c_char.from_buffer(buf))
+    return C.cast(C.c_char_p(buf), C.c_void_p).value
+
+
 class NativeIngest(object):
     def __init__(self, asize, margin, min_uniq_qual, nolinear, names, tid2gid, cap=1 << 18, n_words=8, cap_complex=1 << 16,
                  first_fragment=0, at_stream_start=True):
@@ -148,7 +155,7 @@ class NativeIngest(object):
 
     def parse(self, buf: bytes, offset: int, final: bool, end: int = -1) -> int:
         """parse buf[offset:]; returns bytes consumed.  Results are in self.out / self.a until the next call."""
-        base = C.cast(C.c_char_p(buf), C.c_void_p).value
+        base = text_address(buf)
         n = self.lib.fc_ingest_parse(self.h, base + offset, (len(buf) if end < 0 else end) - offset, int(final), C.byref(self.out))
         if n < 0:
             raise RuntimeError("fc_ingest_parse failed (%d)" % n)

@@ -235,26 +235,26 @@ def _unique_rows(key: np.ndarray):
     return uniq, inverse
 
 
-def _piece_cuts(buf: bytes, pieces: int):
-    """offsets that cut a chunk of SAM text into `pieces` parts on fragment boundaries (a line whose read name differs from
-    the line before it, find_circ.py:1450-1486): the parts can be parsed independently"""
-    n = len(buf)
-    cuts = [0]
+def _piece_cuts(buf, pieces: int, start: int = 0, end: Optional[int] = None):
+    """offsets that cut the SAM text buf[start:end] into `pieces` parts on fragment boundaries (a line whose read name
+    differs from the line before it, find_circ.py:1450-1486): the parts can be parsed independently"""
+    n = len(buf) if end is None else end
+    cuts = [start]
     for k in range(1, pieces):
-        pos = buf.find(b"\n", max(n * k // pieces, cuts[-1]))
+        pos = buf.find(b"\n", max(start + (n - start) * k // pieces, cuts[-1]), n)
         if pos < 0:
             break
         ls = pos + 1  # start of a line; skip the rest of its fragment
         if ls >= n:
             break
-        name = buf[ls:buf.find(b"\t", ls)]
+        name = buf[ls:buf.find(b"\t", ls, n)]
         while True:
-            nl = buf.find(b"\n", ls)
+            nl = buf.find(b"\n", ls, n)
             if nl < 0:
                 ls = n
                 break
             ls = nl + 1
-            if ls >= n or buf[ls:buf.find(b"\t", ls)] != name:
+            if ls >= n or buf[ls:buf.find(b"\t", ls, n)] != name:
                 break
         if ls >= n:
             break
@@ -696,13 +696,28 @@ class Run(object):
         name2tid = {n: i for i, n in enumerate(self.sam_chroms)}
         threads = int(getattr(opt, "ingest_threads", 0) or 0) or max(1, min(16, os.cpu_count() or 1))
         cap = max(1024, opt.batch_pairs)
-        mk = lambda first, at_start: NativeIngest(opt.asize, opt.margin, opt.min_uniq_qual, opt.nolinear, self.sam_chroms, tid2gid,  # noqa: E731
-                                                  cap=cap, first_fragment=first, at_stream_start=at_start)
+        # the handles of the parser threads see one piece of a chunk each: arrays for the rows such a piece can hold (a row
+        # takes more than 64 bytes of SAM text; a piece that holds more just takes another call)
+        piece_cap = max(1024, min(cap, chunk_bytes // max(threads, 1) // 64 + 1024))
+        mk = lambda first, at_start, c=cap: NativeIngest(opt.asize, opt.margin, opt.min_uniq_qual, opt.nolinear, self.sam_chroms, tid2gid,  # noqa: E731
+                                                         cap=c, first_fragment=first, at_stream_start=at_start)
         ings = [mk(first_fragment, at_stream_start)]
         self.explicit_idx = True
-        carry = b""
         eof = False
         pool = None
+        pending = []  # evidence of the batches so far, in stream order (results or futures)
+        HEAD = 1 << 20  # room in front of every chunk for the tail the chunk before it left over (an unfinished fragment)
+
+        def read_chunk():
+            """the next chunk_bytes of the stream behind HEAD free bytes -> (bytearray, bytes read)"""
+            if hasattr(fh, "readinto"):
+                ba = bytearray(HEAD + chunk_bytes)
+                got = fh.readinto(memoryview(ba)[HEAD:])
+                return ba, int(got or 0)
+            data = fh.read(chunk_bytes)  # (BAM text, a prefixed stdin, a rank's byte range: objects with read() only)
+            ba = bytearray(HEAD + len(data))
+            ba[HEAD:] = data
+            return ba, len(data)
 
         def consume(buf, off, a, n, m, max_l, n_frag, counters, complex_ranges, plane_stride):
             """what one fc_ingest_parse call produced: rows and fragment records -> GPU + evidence rules, fragments it
@@ -712,7 +727,11 @@ class Run(object):
                 if counters[k]:
                     N[name] += counters[k]
             if n:
-                self._native_batch(buf, off, a, n, m, max_l, ings[0].n_words, plane_stride, ings[0].lib)
+                # (arrays that belong to a parser handle are overwritten by its next call: their evidence is taken right away)
+                later = pool if a is not ings[0].a else None
+                pending.append(self._native_batch(buf, off, a, n, m, max_l, ings[0].n_words, plane_stride, ings[0].lib, later))
+                while len(pending) > 64:  # (bounded: a future holds its batch's arrays)
+                    self._apply_native_evidence(pending.pop(0))
             for s0, s1, seq in complex_ranges:
                 self.cur_seq = seq
                 lines = buf[off + s0:off + s1].decode("latin-1").splitlines(True)
@@ -756,25 +775,42 @@ class Run(object):
             # Three things overlap: the file read of chunk k+2 (one pool thread), the parse of chunk k+1 (parser threads, in
             # C++ without the GIL) and, on this thread, the GPU call + evidence rules + python-path fragments of chunk k.
             # The only dependency between chunks is the tail an earlier parse left over (an incomplete last fragment).
-            ahead = pool.submit(fh.read, chunk_bytes) if pool is not None else None
+            ahead = pool.submit(read_chunk) if pool is not None else None
             waiting = None  # (buf, jobs) of the chunk whose results the main thread has not consumed yet
+            T = self.t_ingest = {"read_wait": 0.0, "cut": 0.0, "consume": 0.0, "parse_wait": 0.0}  # where this thread's time goes
+            clock = time.perf_counter
+            carry = b""
             while not eof:
-                chunk = ahead.result() if ahead is not None else fh.read(chunk_bytes)
-                eof = len(chunk) == 0  # (a stream may return short chunks before its end: BAM text comes in whole lines)
+                t0 = clock()
+                buf, got = ahead.result() if ahead is not None else read_chunk()
+                T["read_wait"] += clock() - t0
+                eof = got == 0  # (a stream may return short chunks before its end: BAM text comes in whole lines)
                 if ahead is not None and not eof:
-                    ahead = pool.submit(fh.read, chunk_bytes)
-                buf = carry + chunk if carry else chunk
-                if not len(buf):
+                    ahead = pool.submit(read_chunk)
+                t0 = clock()
+                if len(carry) <= HEAD:
+                    lo, hi = HEAD - len(carry), HEAD + got
+                    buf[lo:HEAD] = carry
+                else:  # (a fragment of more than a megabyte of text)
+                    buf = bytearray(carry) + buf[HEAD:HEAD + got]
+                    lo, hi = 0, len(buf)
+                if hi == lo:
                     break
-                cuts = _piece_cuts(buf, threads) if threads > 1 and len(buf) > int(getattr(opt, "ingest_piece_bytes", 4 << 20)) else [0, len(buf)]
+                cuts = (_piece_cuts(buf, threads, lo, hi) if threads > 1 and hi - lo > int(getattr(opt, "ingest_piece_bytes", 4 << 20))
+                        else [lo, hi])
+                T["cut"] += clock() - t0
                 if len(cuts) == 2:
+                    t0 = clock()
                     if waiting is not None:
                         consume_parsed(*waiting)
                         waiting = None
-                    _, off = parse_piece(ings[0], buf, 0, len(buf), eof, False)
+                    _, off = parse_piece(ings[0], buf, lo, hi, eof, False)
+                    T["consume"] += clock() - t0
                 else:
+                    t0 = clock()
                     while len(ings) < len(cuts) - 1:
-                        ings.append(mk(0, False))
+                        ings.append(mk(0, False, piece_cap))
+                    T["handles"] = T.get("handles", 0.0) + clock() - t0
                     # every piece numbers its fragments from its own base: more than it can hold apart (a SAM line is > 16 bytes)
                     stride = max(b - a0 for a0, b in zip(cuts, cuts[1:])) // 16 + 2
                     next_ord = ings[0].next_fragment()
@@ -784,33 +820,42 @@ class Run(object):
                             ings[k].set_position(next_ord + k * stride, False)
                         last = k == len(cuts) - 2
                         jobs.append(pool.submit(parse_piece, ings[k], buf, cuts[k], cuts[k + 1], eof if last else True, True))
+                    t0 = clock()
                     if waiting is not None:  # (while the pool parses this chunk)
                         consume_parsed(*waiting)
+                    T["consume"] += clock() - t0
                     waiting = (buf, jobs)
+                    t0 = clock()
                     off = jobs[-1].result()[1]
                     for job in jobs:
                         job.result()  # (every handle is free again; a parser error surfaces here)
+                    T["parse_wait"] += clock() - t0
                     ings[0].set_position(next_ord + (len(cuts) - 1) * stride, False)
-                carry = buf[off:]
+                carry = bytes(buf[off:hi])
                 if eof and carry.strip():
                     raise ValueError("unparsable trailing SAM text")
+            t0 = clock()
             if waiting is not None:
                 consume_parsed(*waiting)
+            for res in pending:
+                self._apply_native_evidence(res)
+            pending = []
+            T["consume"] += clock() - t0
             self.flush()
         finally:
+            t0 = time.perf_counter()
             if pool is not None:
                 pool.shutdown()
             for ing in ings:
                 ing.close()
+            if getattr(self, "t_ingest", None) is not None:
+                self.t_ingest["close"] = time.perf_counter() - t0
 
-    def _native_batch(self, buf, off, a, n, m, max_l, n_words, plane_stride, lib):
-        """scan + record the n rows of m fragments the native ingest produced, then the evidence rules of record_hits
-        (find_circ.py:1276-1439) for all fragments at once in C++ (fc_ingest_evidence: with at most two spans per fragment,
-        back-splices first, every rule is a comparison between the fragment's columns) -- same outcome as _record_hits(),
-        which stays the reading of the reference for everything else"""
-        from .ingest import EV_LIN0, EV_LIN0_OUT, EV_LIN1, EV_LIN1_OUT, EV_UN, EV_UN_OUT, evidence
-
-        N, opt = self.N, self.opt
+    def _native_batch(self, buf, off, a, n, m, max_l, n_words, plane_stride, lib, pool=None):
+        """scan + record the n rows of m fragments the native ingest produced (on this thread: the context's stream takes one
+        batch at a time), then their evidence (_native_evidence) -- on a pool thread when there is one and `a` is a snapshot:
+        the rules run in C++ without the interpreter lock, beside the next batch's GPU call.  Returns what
+        _apply_native_evidence takes (or a future of it); results are applied in stream order."""
         idx = a["frag_seq"][:n].astype(np.uint64) * np.uint64(64) + a["idx_k"][:n].astype(np.uint64)
         t0 = time.perf_counter()
         hits = self.eng.batch_host_planes(n, a["chrom"], a["a_start"], a["b_end"], a["l"], a["flags"], a["rlo"], a["rhi"], a["rn"],
@@ -818,16 +863,24 @@ class Run(object):
                                           a["qname_hash"], idx=idx, emit=True)
         self.t_scan += time.perf_counter() - t0
         self.n_pairs_scanned += n
+        if pool is not None:
+            return pool.submit(self._native_evidence, buf, off, a, n, m, hits, lib)
+        return self._native_evidence(buf, off, a, n, m, hits, lib)
+
+    def _native_evidence(self, buf, off, a, n, m, hits, lib):
+        """the evidence rules of record_hits (find_circ.py:1276-1439) for all fragments of a batch at once in C++
+        (fc_ingest_evidence: with at most two spans per fragment, back-splices first, every rule is a comparison between the
+        fragment's columns) -- same outcome as _record_hits(), which stays the reading of the reference for everything else.
+        Touches no state of the run: returns (counters, events | None, multi-event rows | None, reads | None)."""
+        from .ingest import EV_LIN0, EV_LIN0_OUT, EV_LIN1, EV_LIN1_OUT, EV_UN, EV_UN_OUT, evidence, text_address
+
+        opt = self.opt
         ev = evidence(lib, a, hits, n, m, off, opt.asize, FLAG_BIT)
-        for key, cnt in zip(("circ_spliced", "circ_no_bp", "lin_spliced", "lin_no_bp"), ev["counters"]):
-            if cnt:  # the reference's counter dict only holds keys that were incremented (find_circ.py:1146)
-                N[key] += float(cnt)
         if not ev["any_hit"]:
-            return
+            return ev["counters"], None, None, None
         # ---- per-junction flags (find_circ.py:1325-1327, 1433-1437)
-        if len(ev["ev_mask"]):
-            self.ev_native.append((ev["ev_key"], ev["ev_hash"], ev["ev_mask"]))
-        base = C.cast(C.c_char_p(buf), C.c_void_p).value
+        events = (ev["ev_key"], ev["ev_hash"], ev["ev_mask"]) if len(ev["ev_mask"]) else None
+        base = text_address(buf)
 
         def gather(off3, len3):
             blob = np.empty(int(np.maximum(len3, 0).sum()), dtype=np.uint8)
@@ -837,6 +890,7 @@ class Run(object):
             return blob
 
         # ---- multi-event rows (find_circ.py:1429-1431)
+        multi = None
         if opt.multi_events:
             cls = ev["cls"]
             me = np.nonzero(cls & (EV_LIN0 | EV_LIN1 | EV_UN))[0]
@@ -847,16 +901,30 @@ class Run(object):
                 len3 = np.ascontiguousarray(txt_len[me, 0])
                 len3[:, 1:] = -1  # (the name only)
                 c = cls[me]
-                self.native_multi.append(dict(
+                multi = dict(
                     seqs=a["f_seq"][:m][me].copy(), names=gather(off3, len3), name_len=len3[:, 0].copy(), ck=ev["ck"][me],
                     lin=[((c & EV_LIN0) > 0, (c & EV_LIN0_OUT) > 0, ev["key0"][me]), ((c & EV_LIN1) > 0, (c & EV_LIN1_OUT) > 0, ev["key1"][me])],
                     un=((c & EV_UN) > 0, (c & EV_UN_OUT) > 0, a["f_un_tid"][:m][me].copy(), a["f_un_pos"][:m][me].astype(np.int64),
-                        a["f_un_aend"][:m][me].astype(np.int64))))
+                        a["f_un_aend"][:m][me].astype(np.int64)))
         # ---- the reads of every fragment with a junction (find_circ.py:1439, 1442-1447): name, sequence and qualities of
         # both mates go into one compact blob (C++); the FASTQ records are formatted from it when the junction names are
         # known (reads_text)
-        self.native_reads.append(dict(seqs=ev["r_seq"], blob=gather(ev["r_off3"], ev["r_len3"]), len3=ev["r_len3"], k0=ev["r_k0"],
-                                      k1=ev["r_k1"], mask=ev["r_mask"]))
+        reads = dict(seqs=ev["r_seq"], blob=gather(ev["r_off3"], ev["r_len3"]), len3=ev["r_len3"], k0=ev["r_k0"], k1=ev["r_k1"],
+                     mask=ev["r_mask"])
+        return ev["counters"], events, multi, reads
+
+    def _apply_native_evidence(self, res):
+        """what _native_evidence returned for one batch (or a future of it) into the run's state; call in stream order"""
+        counters, events, multi, reads = res.result() if hasattr(res, "result") else res
+        for key, cnt in zip(("circ_spliced", "circ_no_bp", "lin_spliced", "lin_no_bp"), counters):
+            if cnt:  # the reference's counter dict only holds keys that were incremented (find_circ.py:1146)
+                self.N[key] += float(cnt)
+        if events is not None:
+            self.ev_native.append(events)
+        if multi is not None:
+            self.native_multi.append(multi)
+        if reads is not None:
+            self.native_reads.append(reads)
 
     # ------------------------------------------------------------------ outputs
     def finalize(self, dist=None, torch_dev=None):
