@@ -962,26 +962,32 @@ class Run(object):
         self._names_cache = (junc, names)
         return names
 
-    def categories(self, r, inf: Optional[JunctionInfo], min_dist, min_ov=None, min_nh=None) -> List[str]:
-        """Hit.categories (find_circ.py:601-654)"""
+    def categories(self, r, inf: Optional[JunctionInfo], min_dist, min_ov=None, min_nh=None, fields=None) -> List[str]:
+        """Hit.categories (find_circ.py:601-654).  r: the junction's row, or None with fields = (signal text, best_q_left,
+        best_q_right, n_uniq_bridges, end - start) and min_ov / min_nh given"""
         opt = self.opt
         cats = []
-        if decode_signal((int(r["sk"]) >> 16) & 0xFFF) != "GTAG":
+        if fields is None:
+            fields = (decode_signal((int(r["sk"]) >> 16) & 0xFFF), int(r["best_q_left"]), int(r["best_q_right"]),
+                      float(r["n_uniq_bridges"]), int(r["end"]) - int(r["start"]))
+            min_ov = int(r["min_ov"]) if min_ov is None else min_ov
+            min_nh = int(r["min_n_hits"]) if min_nh is None else min_nh
+        signal, ql, qr, bridges, span = fields
+        if signal != "GTAG":
             cats.append("NON_CANONICAL")
-        if int(r["best_q_left"]) == 0 or int(r["best_q_right"]) == 0:
+        if ql == 0 or qr == 0:
             cats.append("WARN_NON_UNIQUE_ANCHOR")
-        if float(r["n_uniq_bridges"]) == 0:
+        if bridges == 0:
             cats.append("WARN_NO_UNIQ_BRIDGES")
-        if (int(r["min_n_hits"]) if min_nh is None else min_nh) > 1:
+        if min_nh > 1:
             cats.append("WARN_AMBIGUOUS_BP")
-        ov, ed = (int(r["min_ov"]) if min_ov is None else min_ov), int(min_dist)
+        ov, ed = min_ov, int(min_dist)
         if ov == 0 and ed == 0:
             pass
         elif ov < 2 and ed < 2:
             cats.append("WARN_EXT_1MM")
         elif ov >= 2 or ed >= 2:
             cats.append("WARN_EXT_2MM+")
-        span = int(r["end"]) - int(r["start"])
         if span < opt.short_threshold:
             cats.append("SHORT")
         elif span > opt.huge_threshold:
@@ -996,45 +1002,49 @@ class Run(object):
     def bed_text(self, kind: int) -> str:
         """store_list (find_circ.py:695-730)"""
         opt = self.opt
-        names = self._names(self.junctions)
+        J = self.junctions
+        names = self._names(J)
         cn = self.eng.chrom_names
         info = self.junction_info()
         lines = ["#" + "\t".join(BED_HEADER) + "\n"]
-        for r in self.junctions:
-            sk = int(r["sk"])
-            if ((sk >> 1) & 1) != kind:
-                continue
-            ql, qr = int(r["best_q_left"]), int(r["best_q_right"])
-            if opt.halfunique:
-                if ql < opt.min_uniq_qual and qr < opt.min_uniq_qual:
-                    continue
-            elif ql < opt.min_uniq_qual or qr < opt.min_uniq_qual:
-                continue
-            bridges = float(r["n_uniq_bridges"])
-            if bridges == 0 and not opt.report_nobridges:
-                continue
-            start, end = int(r["start"]), int(r["end"])
+        if len(J) == 0:
+            return lines[0]
+        # the filters of :706-717 on whole columns, the surviving rows as python tuples (a numpy record costs a microsecond per field)
+        sk_all = J["sk"].astype(np.int64)
+        keep = ((sk_all >> 1) & 1) == kind
+        ql_all, qr_all = J["best_q_left"].astype(np.int64), J["best_q_right"].astype(np.int64)
+        if opt.halfunique:
+            keep &= ~((ql_all < opt.min_uniq_qual) & (qr_all < opt.min_uniq_qual))
+        else:
+            keep &= ~((ql_all < opt.min_uniq_qual) | (qr_all < opt.min_uniq_qual))
+        if not opt.report_nobridges:
+            keep &= J["n_uniq_bridges"] != 0
+        rows = J[keep]
+        cols = [rows[f].tolist() for f in ("chrom", "start", "end", "sk", "best_q_left", "best_q_right", "n_uniq_bridges", "n_weighted",
+                                           "min_dist", "min_ov", "min_n_hits", "n_frags", "n_spanned", "n_uniq")]
+        sig_text: Dict[int, str] = {}
+        for chrom, start, end, sk, ql, qr, bridges, w, min_dist, min_ov, min_nh, n_frags, n_spanned, n_uniq in zip(*cols):
             strand = "-" if sk & 1 else "+"
-            key = (int(r["chrom"]), start, end, strand, kind)
+            key = (chrom, start, end, strand, kind)
             inf = info.get(key)
             if inf is not None and inf.flags:
                 flags = sorted(inf.flags)
                 fcounts = [inf.flags[f] for f in flags]
             else:
                 flags, fcounts = ["N/A"], [0]
-            w = float(r["n_weighted"])
-            min_dist, min_ov, min_nh = int(r["min_dist"]), int(r["min_ov"]), int(r["min_n_hits"])
             if key in self.known:  # the placeholder splice of a known site (find_circ.py:676)
                 min_dist, min_ov, min_nh = min(min_dist, 10), min(min_ov, 10), 1
+            sig = (sk >> 16) & 0xFFF
+            if sig not in sig_text:
+                sig_text[sig] = decode_signal(sig)
+            cats = self.categories(None, inf, min_dist, min_ov, min_nh, (sig_text[sig], ql, qr, bridges, end - start))
             # with --max-mismatch 0 the reference's edit distance is a python bool (find_circ.py:868-870)
             edits = bool(min_dist) if opt.maxdist == 0 else min_dist
-            cols = [
-                cn[int(r["chrom"])], start, end, names[key], int(r["n_frags"]), strand, w, int(r["n_spanned"]), int(r["n_uniq"]),
-                bridges, ql, qr, opt.name, py2_str(w), edits, min_ov, min_nh,
-                decode_signal((sk >> 16) & 0xFFF), "N/A", ",".join(sorted(self.categories(r, inf, min_dist, min_ov, min_nh))),
-                ",".join(flags), ",".join(str(c) for c in fcounts),
-            ]
-            lines.append("\t".join(py2_str(c) for c in cols) + "\n")
+            ws = py2_str(w)
+            lines.append("\t".join((
+                cn[chrom], str(start), str(end), names[key], str(n_frags), strand, ws, str(n_spanned), str(n_uniq), py2_str(bridges),
+                str(ql), str(qr), opt.name, ws, py2_str(edits), str(min_ov), str(min_nh), sig_text[sig], "N/A", ",".join(sorted(cats)),
+                ",".join(flags), ",".join(str(c) for c in fcounts))) + "\n")
         return "".join(lines)
 
     def reads_text(self) -> str:
