@@ -432,6 +432,14 @@ constexpr int PSET_ENTRIES = 8192;    // shared-memory set of pass 2 (64 KB: thr
 constexpr int PSET_TARGET = 2600;     // elements per partition the host aims at (load 0.32; 0.64 when every name goes through it too)
 constexpr int PART_THREADS = 512;
 
+// 16 bytes of shared memory in one instruction, not cached in registers across calls
+__device__ __forceinline__ ulonglong2 lds128(const void* p) {
+  ulonglong2 v;
+  const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(a));
+  return v;
+}
+
 // key (never 0) and partition of the pair (value, tag).  The value is a 64-bit hash already, so x = v ^ t * odd is a
 // bijection of v for every tag and as uniform as v is; the partition mixes x with the tag once more, so two pairs with
 // equal keys and different tags (which need v' = v ^ const, 2^-64 for hashes) still part ways in all but 1/n_parts cases.
@@ -452,7 +460,8 @@ __device__ __forceinline__ unsigned long long part_key(unsigned long long v, uns
 // once.  Every value in the cache is a key that was sent, whatever the races between the lanes do to it.
 __device__ __forceinline__ bool part_claim(const PartView& pv, unsigned long long* recent, unsigned long long k, unsigned int part, unsigned int& pos) {
   volatile unsigned long long* rc = recent + 2u * ((unsigned int)(k >> 20) & (RECENT_SETS - 1));
-  const unsigned long long w0 = rc[0], w1 = rc[1];
+  const ulonglong2 ways = lds128(recent + 2u * ((unsigned int)(k >> 20) & (RECENT_SETS - 1)));  // (both ways in one 16-byte load)
+  const unsigned long long w0 = ways.x, w1 = ways.y;
   if (w0 == k) return false;
   if (w1 == k) {
     rc[0] = k;
@@ -494,13 +503,16 @@ constexpr int ACC_THREADS = 512;
 constexpr int ACC_MAX_TILES = 30;  // tiles of ACC_THREADS records per chunk (between two flushes of the shared-memory table)
 constexpr int HOT_ENTRIES = 512;
 constexpr int HOT_BITS = 9;
+struct alignas(32) HotEntry {  // one junction of the CTA's table: everything a record looks at or changes in two 16-byte halves
+  unsigned int tag;                // junction slot + 1, 0 = free
+  unsigned int c0;                 // n_spanned | 8 * weight << 14 (a chunk holds fewer than 16384 records of weight <= 1)
+  unsigned int c1;                 // names seen before | 8 * non-bridge weight << 14
+  unsigned int c2;
+  unsigned long long ext;          // packed extrema, as JSlot.ext
+  unsigned long long first_inv;    // identity | first position, as JSlot.kf
+};
 struct HotTable {
-  unsigned int tag[HOT_ENTRIES];    // junction slot + 1, 0 = free
-  unsigned int c0[HOT_ENTRIES];     // n_spanned | 8 * weight << 14 (a chunk holds fewer than 16384 records of weight <= 1)
-  unsigned int c1[HOT_ENTRIES];     // names seen before | 8 * non-bridge weight << 14
-  unsigned int c2[HOT_ENTRIES];
-  unsigned long long ext[HOT_ENTRIES];        // packed extrema, as JSlot.ext
-  unsigned long long first_inv[HOT_ENTRIES];  // identity | first position, as JSlot.kf
+  HotEntry e[HOT_ENTRIES];
 };
 static_assert(ACC_MAX_TILES * ACC_THREADS < (1 << 14) && ACC_MAX_TILES * ACC_THREADS * 8 < (1 << 18), "hot-table fields");
 
@@ -510,10 +522,10 @@ __device__ __forceinline__ int hot_find_or_insert(HotTable& t, unsigned int jid,
   unsigned int h = (jid * 2654435761u) >> (32 - HOT_BITS);
 #pragma unroll 1
   for (int probe = 0; probe < FC_HOT_PROBES; ++probe) {  // (2 probes: a miss is the common case and must stay cheap)
-    unsigned int cur = *reinterpret_cast<volatile unsigned int*>(&t.tag[h]);
+    unsigned int cur = *reinterpret_cast<volatile unsigned int*>(&t.e[h].tag);
     if (cur == 0u) {
       if (!insert) return -1;
-      cur = atomicCAS(&t.tag[h], 0u, jid + 1u);
+      cur = atomicCAS(&t.e[h].tag, 0u, jid + 1u);
       if (cur == 0u) return (int)h;
     }
     if (cur == jid + 1u) return (int)h;
@@ -582,9 +594,8 @@ __global__ void __launch_bounds__(ACC_THREADS, FC_ACC_MIN_CTAS) fused_accumulate
 #pragma unroll 1
   for (int64_t c0 = (int64_t)blockIdx.x * chunk_recs; c0 < n; c0 += (int64_t)gridDim.x * chunk_recs) {
     for (int e = threadIdx.x; e < HOT_ENTRIES; e += ACC_THREADS) {
-      hot.tag[e] = hot.c0[e] = hot.c1[e] = hot.c2[e] = 0u;
-      hot.ext[e] = 0ull;
-      hot.first_inv[e] = 0ull;
+      uint4* z = reinterpret_cast<uint4*>(&hot.e[e]);
+      z[0] = z[1] = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
     int64_t i = c0 + threadIdx.x;
@@ -692,11 +703,13 @@ __global__ void __launch_bounds__(ACC_THREADS, FC_ACC_MIN_CTAS) fused_accumulate
       const unsigned n_hits = r2.w & 0xFFFFu, dist = (r2.w >> 16) & 0xFFu, ov = r2.w >> 24;
       const unsigned long long x = ext_pack(q_left, q_right, dist, ov, n_hits);
       if (he >= 0) {
-        if (kf > hot.first_inv[he]) atomicMax(&hot.first_inv[he], kf);
-        unsigned long long cx = hot.ext[he], want = cx;
+        // (one 16-byte load shows both words; they only grow, so a stale view costs a needless attempt at worst)
+        const ulonglong2 seen = lds128(&hot.e[he].ext);
+        if (kf > seen.y) atomicMax(&hot.e[he].first_inv, kf);
+        unsigned long long cx = seen.x, want = cx;
         if (ext_improves(cx, x)) want = ext_max(cx, x);
         while (want != cx) {  // (rare once the entry has seen a few records)
-          const unsigned long long old = atomicCAS(&hot.ext[he], cx, want);
+          const unsigned long long old = atomicCAS(&hot.e[he].ext, cx, want);
           if (old == cx) break;
           cx = old;
           want = ext_max(cx, x);
@@ -728,9 +741,9 @@ __global__ void __launch_bounds__(ACC_THREADS, FC_ACC_MIN_CTAS) fused_accumulate
       if (__all_sync(amask, group == 1u)) {
         // no two lanes of the warp share a junction (the usual case)
         if (he >= 0) {
-          atomicAdd(&hot.c0[he], 1u | (fx << 14));
-          if (nb | (unsigned)dup_name) atomicAdd(&hot.c1[he], (unsigned)dup_name | (nb << 14));
-          if (c2) atomicAdd(&hot.c2[he], c2);
+          atomicAdd(&hot.e[he].c0, 1u | (fx << 14));
+          if (nb | (unsigned)dup_name) atomicAdd(&hot.e[he].c1, (unsigned)dup_name | (nb << 14));
+          if (c2) atomicAdd(&hot.e[he].c2, c2);
         } else {
           atomicAdd(&a->c0, 1ull | ((unsigned long long)fx << 32));
           if (nb | (unsigned)dup_name) atomicAdd(&a->c1, (unsigned long long)nb | ((unsigned long long)dup_name << 32));
@@ -747,9 +760,9 @@ __global__ void __launch_bounds__(ACC_THREADS, FC_ACC_MIN_CTAS) fused_accumulate
         const unsigned c2s = 2u * __popc(__ballot_sync(amask, c2 == 2u) & peers) + __popc(__ballot_sync(amask, c2 == 1u) & peers);
         if (lead) {
           if (he >= 0) {
-            atomicAdd(&hot.c0[he], group | (w << 14));
-            if (b | dups) atomicAdd(&hot.c1[he], dups | (b << 14));
-            if (c2s) atomicAdd(&hot.c2[he], c2s);
+            atomicAdd(&hot.e[he].c0, group | (w << 14));
+            if (b | dups) atomicAdd(&hot.e[he].c1, dups | (b << 14));
+            if (c2s) atomicAdd(&hot.e[he].c2, c2s);
           } else {
             atomicAdd(&a->c0, (unsigned long long)group | ((unsigned long long)w << 32));
             if (b | dups) atomicAdd(&a->c1, (unsigned long long)b | ((unsigned long long)dups << 32));
@@ -764,10 +777,11 @@ __global__ void __launch_bounds__(ACC_THREADS, FC_ACC_MIN_CTAS) fused_accumulate
     }
     __syncthreads();
     for (int e = threadIdx.x; e < HOT_ENTRIES; e += ACC_THREADS) {
-      if (hot.tag[e] == 0u) continue;
-      JSlot* a = slots + (hot.tag[e] - 1u);
-      extrema_to_global(a, hot.first_inv[e], hot.ext[e], __ldcg(&a->kf), __ldcg(&a->ext));
-      const unsigned c0v = hot.c0[e], c1v = hot.c1[e], c2v = hot.c2[e];
+      const HotEntry h = hot.e[e];
+      if (h.tag == 0u) continue;
+      JSlot* a = slots + (h.tag - 1u);
+      extrema_to_global(a, h.first_inv, h.ext, __ldcg(&a->kf), __ldcg(&a->ext));
+      const unsigned c0v = h.c0, c1v = h.c1, c2v = h.c2;
       if (c0v) atomicAdd(&a->c0, (unsigned long long)(c0v & 0x3FFFu) | ((unsigned long long)(c0v >> 14) << 32));
       if (c1v) atomicAdd(&a->c1, (unsigned long long)(c1v >> 14) | ((unsigned long long)(c1v & 0x3FFFu) << 32));
       if (c2v) atomicAdd(&a->c2, (unsigned long long)c2v);
