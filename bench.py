@@ -643,16 +643,23 @@ def bench_config(args, cfg, dist, dev, primary, error_rate=None):
     else:
         total_pairs, total_rec, total_junc = n, n_rec, int(nj)
     peak, peak_src = peaks()
+    # DRAM bytes per launch from the one `ncu --set full` capture of this workload (profiles/r02_kernels_ncu_summary_final.txt):
+    # only quoted for the launch that was captured (config 3 at full size on one GPU)
+    captured = primary and world == 1 and cfg.name == "3" and n == 49037197
+    traffic_scan = 3.600574e9 + 2.856026e9 if captured else None
+    traffic_acc = 2.282065e9 + 0.888959e9 if captured else None
     achieved = bpp * n / (scan_step * 1e-3) / 1e9
     merge_bytes = 48.0 * n_rec + 64.0 * int(nj)
     acc_achieved = merge_bytes / (max(acc_step_ms, 1e-9) * 1e-3) / 1e9
     fused = world == 1 or use_p2p
-    roof_scan = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    roof_scan = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic_scan,
                  "kernel": ("scan_emit%s_kernel (csrc/scan.cu): breakpoint scan; also writes a 48-byte record per accepted pair" % ("" if world == 1 else "_p2p")
                             if fused else "scan_kernel (csrc/scan.cu)"),
                  "bytes_per_pair": bpp, "pairs": n, "ms": scan_step, "peak_source": peak_src}
-    roof_acc = {"bound": "hbm", "achieved": acc_achieved, "peak": peak, "unit": "GB/s", "frac": acc_achieved / peak, "traffic": None,
-                "kernel": "fused_accumulate_kernel (csrc/agg.cu)", "ms": acc_step_ms,
+    distinct_ms = stages_us.get("distinct", 0.0) * 1e-3
+    roof_acc = {"bound": "hbm", "achieved": acc_achieved, "peak": peak, "unit": "GB/s", "frac": acc_achieved / peak, "traffic": traffic_acc,
+                "kernel": "fused_accumulate_kernel (csrc/agg.cu)" + ("; large inputs: the distinct counts follow in distinct_parts_kernel (%.3f ms, not in `ms`)" % distinct_ms if distinct_ms > 0.01 else ""),
+                "ms": acc_step_ms,
                 "bytes": "48 B x %d records + 64 B x %d junctions (rank 0)" % (n_rec, int(nj)), "peak_source": peak_src}
     dominant, other = (roof_acc, roof_scan) if acc_step_ms > scan_step else (roof_scan, roof_acc)
     res = {
