@@ -322,6 +322,7 @@ def dropin_parity(eng, spec, cfg, n_sample, large=True, error_rate=None):
                                "parser_threads": threads, "seconds_host": host_s, "seconds_gpu_calls": out["seconds_gpu_calls"],
                                "seconds_main_thread": out.get("seconds_ingest_stages"),
                                "seconds_writers": out["seconds_total"] - out["seconds_ingest_and_scan"],
+                               "seconds_writer_stages": out.get("seconds_writer_stages"),
                                "seconds_wall": out["seconds_total"], "junction_rows": out["circ"].count("\n") + out["lin"].count("\n") - 2}
     n_rows = len(want.circ_bed.splitlines()) + len(want.lin_bed.splitlines()) - 2
     parity = {"ok": ok and n_rows > 0, "against": "oracle (oracle/find_circ_oracle.py), all five outputs of the drop-in, native and python ingest",

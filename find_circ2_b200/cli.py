@@ -354,14 +354,23 @@ def run_to_strings(opt: Options, path=None, engine=None, native=None):
         else:
             run.process(records)
         t1 = time.perf_counter()
-        run.finalize()
+        stages = {}
+
+        def timed(name, fn, *a):
+            t = time.perf_counter()
+            r = fn(*a)
+            stages[name] = round(time.perf_counter() - t, 4)
+            return r
+
+        timed("aggregate", run.finalize)
         out = {
-            "circ": run.bed_text(0),
-            "lin": run.bed_text(1),
-            "reads": run.reads_text(),
-            "multi": run.multi_text(),
+            "circ": timed("circ_bed", run.bed_text, 0),
+            "lin": timed("lin_bed", run.bed_text, 1),
+            "reads": timed("reads", run.reads_text),
+            "multi": timed("multi_events", run.multi_text),
             "test": run.test_text(),
             "counters": run.counters_text(),
+            "seconds_writer_stages": stages,
             "n_fragments": run.n_fragments,
             "n_pairs_scanned": run.n_pairs_scanned,
             "seconds_ingest_and_scan": t1 - t0,

@@ -530,10 +530,13 @@ class Run(object):
         K, H, M = self.events()
         out: Dict[tuple, JunctionInfo] = {}
         if len(M):
-            order = np.lexsort((H, K[:, 4], K[:, 3], K[:, 2], K[:, 1], K[:, 0]))
-            K, H, M = K[order], H[order], M[order]
+            # group by junction, then by name: the junction of a row as one number first (two sort keys instead of six)
+            _, kid = _unique_rows(K)
+            kid = kid.reshape(-1)
+            order = np.lexsort((H, kid))
+            K, H, M, kid = K[order], H[order], M[order], kid[order]
             new_key = np.ones(len(M), dtype=bool)
-            new_key[1:] = (K[1:] != K[:-1]).any(axis=1)
+            new_key[1:] = kid[1:] != kid[:-1]
             new_name = new_key.copy()
             new_name[1:] |= H[1:] != H[:-1]
             key_start = np.nonzero(new_key)[0]
@@ -1093,7 +1096,7 @@ class Run(object):
             got = lib.fc_fastq_format(*args, text.ctypes.data, int(need), rec_off.ctypes.data)
             if got != need:
                 raise RuntimeError("fc_fastq_format failed (%d)" % got)
-            raw = text[:got].tobytes().decode("latin-1")
+            raw = str(memoryview(text[:got]), "latin-1")  # (one copy: the bytes are ASCII)
             # python-path reads whose stream position falls inside this batch split it
             lo = 0
             hi_py = int(np.searchsorted(py_seqs, b["seqs"][-1], side="right")) if m else done
@@ -1105,7 +1108,7 @@ class Run(object):
             pieces.append(raw[int(rec_off[lo]):])
             done = max(done, hi_py)
         pieces.extend(out[done:])
-        return "".join(pieces)
+        return pieces[0] if len(pieces) == 1 else "".join(pieces)
 
     def _multi_rows(self):
         """python-path and native rows together, in stream order"""
