@@ -1476,6 +1476,7 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st, const Re
     a.sets_clean = false;
     a.f_keys.release();
     a.f_sets.release();
+    a.f_pcur.release();  // (the partition cursors as well: a kernel that did not finish has left counts behind)
     a.f_dirty = false;
   }
   if ((rc = reserve_clean(ctx, a.f_keys, (size_t)kcap * sizeof(JSlot), st))) return rc;
@@ -2109,6 +2110,8 @@ void fc_agg_release(fc_ctx* ctx) {
   a.f_keys.release();
   a.f_sets.release();
   a.f_acc.release();
+  a.f_part.release();
+  a.f_pcur.release();
   if (a.h_pinned) cudaFreeHost(a.h_pinned);
   a.h_pinned = nullptr;
   if (a.side) {
