@@ -150,6 +150,7 @@ SYMBOLS = [
     ("fc_bam_ref_length", C.c_int64, [_P, C.c_int32]),
     ("fc_bam_read_text", C.c_int64, [_P, _P, C.c_int64]),
     ("fc_ingest_evidence", C.c_int, [_P, _P]),
+    ("fc_unique_rows", C.c_int64, [_P, C.c_int64, C.c_int32, _P, _P]),
     ("fc_text_gather", C.c_int64, [_P, C.c_int64, _P, _P, _P]),
     ("fc_fastq_format", C.c_int64, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, C.c_int64, _P]),
     ("fc_merge_tables", C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P, _P]),

@@ -689,6 +689,39 @@ extern "C" int fc_ingest_evidence(const fc_evidence_in* in, fc_evidence_out* o) 
   return FC_OK;
 }
 
+// distinct rows of an n x width matrix of 64-bit integers (np.unique(axis=0) without the sort): inverse[i] = number of
+// row i's value in order of first appearance, first[u] = the row where value u appears first; returns the number of
+// distinct rows.  Exact (rows are compared in full); one open-addressing table, host code.  Used by the text writers:
+// the (junctions, flags) combinations of the reads, the junctions of the evidence events.
+extern "C" int64_t fc_unique_rows(const int64_t* rows, int64_t n, int32_t width, int64_t* first, int32_t* inverse) {
+  if (!rows || !first || !inverse || n < 0 || width <= 0 || n >= (1ll << 31)) return FC_E_ARG;
+  uint64_t cap = 1024;
+  while (cap < 2ull * (uint64_t)n) cap <<= 1;
+  std::vector<int32_t> table(cap, -1);
+  int64_t nu = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const int64_t* r = rows + i * width;
+    uint64_t h = 0x9E3779B97F4A7C15ULL;
+    for (int32_t c = 0; c < width; ++c) h = fc_mix64(h ^ (uint64_t)r[c]) + 0x632BE59BD9B4E019ULL;
+    uint64_t s = h & (cap - 1);
+    for (;;) {
+      const int32_t u = table[s];
+      if (u < 0) {
+        table[s] = (int32_t)nu;
+        first[nu] = i;
+        inverse[i] = (int32_t)nu++;
+        break;
+      }
+      if (memcmp(rows + first[u] * width, r, sizeof(int64_t) * (size_t)width) == 0) {
+        inverse[i] = u;
+        break;
+      }
+      s = (s + 1) & (cap - 1);
+    }
+  }
+  return nu;
+}
+
 // copies n x 3 substrings of `buf` back to back into `out` (off/len are n x 3, row major; len < 0 = field absent);
 // returns the number of bytes written
 extern "C" int64_t fc_text_gather(const char* buf, int64_t n, const int64_t* off, const int32_t* len, char* out) {

@@ -220,19 +220,21 @@ def test_result_row(frag: str, lin_coords, circ_coords, unspliced_coords, broken
 
 
 def _unique_rows(key: np.ndarray):
-    """np.unique(key, axis=0, return_inverse=True) for an [n, 5] int64 matrix of junction identities, by way of one 64-bit
-    mix per row (a 1-D sort instead of a lexicographic one); rows that share a mix are verified, a clash falls back"""
+    """np.unique(key, axis=0, return_inverse=True) for an [n, w] int64 matrix (junction identities, combinations of them)
+    without the lexicographic sort: distinct rows in order of first appearance and the number of every row's value
+    (fc_unique_rows: one exact hash table in C++)"""
     if len(key) == 0:
         return key, np.zeros(0, dtype=np.int64)
-    k = key.astype(np.uint64)
-    h = k[:, 0] * np.uint64(0x9E3779B97F4A7C15)
-    for c in range(1, k.shape[1]):
-        h = (h ^ (h >> np.uint64(29))) * np.uint64(0xBF58476D1CE4E5B9) + k[:, c] * np.uint64(0x94D049BB133111EB)
-    uh, first, inverse = np.unique(h, return_index=True, return_inverse=True)
-    uniq = key[first]
-    if not np.array_equal(uniq[inverse], key):
-        return np.unique(key, axis=0, return_inverse=True)
-    return uniq, inverse
+    from . import _lib
+
+    key = np.ascontiguousarray(key, dtype=np.int64)
+    n, w = key.shape
+    first = np.empty(n, dtype=np.int64)
+    inverse = np.empty(n, dtype=np.int32)
+    nu = _lib.load().fc_unique_rows(key.ctypes.data, n, w, first.ctypes.data, inverse.ctypes.data)
+    if nu < 0:
+        raise RuntimeError("fc_unique_rows failed (%d)" % nu)
+    return key[first[:nu]], inverse
 
 
 def _piece_cuts(buf, pieces: int, start: int = 0, end: Optional[int] = None):

@@ -493,6 +493,12 @@ typedef struct fc_evidence_out {
 } fc_evidence_out;
 int fc_ingest_evidence(const fc_evidence_in* in, fc_evidence_out* out);
 
+/* Distinct rows of an n x width matrix of 64-bit integers in order of first appearance (host code, exact): first[u] = the
+ * row where value u appears first, inverse[i] = u for row i; returns the number of distinct rows.  What the writers group by:
+ * the (junction, junction, flags) combinations of the reads to print (find_circ.py:1442-1447) and the junctions of the
+ * evidence events (:1433-1437). */
+int64_t fc_unique_rows(const int64_t* rows, int64_t n, int32_t width, int64_t* first, int32_t* inverse);
+
 /* Spliced reads of the native ingest (write_read, find_circ.py:1442-1447): fc_text_gather copies n x 3 substrings
  * (name, sequence, qualities; off/len row major, len < 0 = absent) of a text buffer back to back into `out` and returns
  * the bytes written; fc_fastq_format turns such a blob into FASTQ records "@<name> <tail>\n<seq>\n+<name> <tail>\n<qual>\n"

@@ -101,3 +101,23 @@ def test_native_ingest_planes_for_every_kind_of_letter():
         text = ("@SQ\tSN:chr1\tLN:100000\n" + "".join(lines)).encode()
         L = L2
     ing.close()
+
+
+@pytest.mark.parametrize("n,w,vals", [(0, 5, 3), (1, 5, 3), (1000, 11, 2), (200000, 5, 40), (50000, 3, 1 << 40)])
+def test_unique_rows_equals_numpy(n, w, vals):
+    """fc_unique_rows (C++ hash table) against np.unique(axis=0): same distinct rows, consistent inverse, first-appearance order"""
+    from find_circ2_b200.pipeline import _unique_rows
+
+    rng = np.random.default_rng(n + w)
+    key = rng.integers(-2, vals, (n, w)).astype(np.int64)
+    uniq, inv = _unique_rows(key)
+    if n == 0:
+        assert len(uniq) == 0 and len(inv) == 0
+        return
+    want = np.unique(key, axis=0)
+    assert len(uniq) == len(want)
+    assert np.array_equal(uniq[np.lexsort(uniq.T[::-1])], want)
+    assert np.array_equal(uniq[inv], key)
+    # order of first appearance
+    firsts = [int(np.nonzero(inv == u)[0][0]) for u in range(min(len(uniq), 50))]
+    assert firsts == sorted(firsts)
