@@ -328,6 +328,11 @@ int64_t fc_agg_n_records(fc_ctx* ctx);
 const fc_jrec* fc_agg_records(fc_ctx* ctx); /* device pointer to the record buffer (for the all-to-all) */
 /* destination rank of every record: hash(key) % n_ranks (int32 per record) and per-rank counts (int64[n_ranks]) */
 int fc_agg_partition(fc_ctx* ctx, int32_t n_ranks, fc_jrec* d_out_sorted_by_rank, int64_t* h_counts, void* stream);
+/* Reduce the records per junction (find_circ.py:486-600, 657-690); returns the number of junctions (fc_agg_fetch copies
+ * the table to the host, fc_agg_junctions gives the device pointer).  Three implementations with identical results, chosen by
+ * the input: sort-free with one global set for the distinct counts (inputs whose set fits L2), sort-free with the distinct
+ * counts through partitions + shared-memory sets (larger inputs), sort-based (weight denominators other than 1, 2, 4, 8;
+ * positions beyond 2^41).  For tests the environment can force one: FC_AGG_MODE=sort|hash, FC_AGG_SETS=global|part. */
 int64_t fc_agg_finalize(fc_ctx* ctx, void* stream);
 int fc_agg_fetch(fc_ctx* ctx, int64_t n, fc_junction* h_out); /* sorted by first_idx */
 const fc_junction* fc_agg_junctions(fc_ctx* ctx);             /* device pointer, after finalize */
