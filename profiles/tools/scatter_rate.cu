@@ -40,6 +40,35 @@ __global__ void __launch_bounds__(512, 2) k(uint4* table, uint64_t mask, unsigne
         const unsigned pos = atomicAdd(cursors + cstride * p, 1u);
         out[((size_t)p * 2048u + (pos & 2047u)) & ((1ull << 28) - 1)] = make_uint4((unsigned)a[u], pos, p, 0u);
       }
+    } else if (KIND == 9) {  // the 16-byte store into the partition space alone (position from a private counter)
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const unsigned p = (unsigned)(a[u] % ncur);
+        out[((size_t)p * 2048u + ((unsigned)(tid + it + u) & 2047u)) & ((1ull << 28) - 1)] = make_uint4((unsigned)a[u], 1u, p, 0u);
+      }
+    } else if (KIND == 10) {  // returning atomic + dependent 16-byte store into an L2-resident space (32 MB)
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const unsigned p = (unsigned)(a[u] % ncur);
+        const unsigned pos = atomicAdd(cursors + cstride * p, 1u);
+        table[((size_t)p * 128u + (pos & 127u)) & mask] = make_uint4((unsigned)a[u], pos, p, 0u);
+      }
+    } else if (KIND == 11) {  // returning atomic + dependent store, partitions spread evenly over `mask + 1` slots of the partition space
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const unsigned p = (unsigned)(a[u] % ncur);
+        const unsigned pos = atomicAdd(cursors + cstride * p, 1u);
+        const uint64_t per = (mask + 1) / ncur;  // slots per partition (>= 2048 here)
+        out[(size_t)p * per + (pos % (unsigned)per)] = make_uint4((unsigned)a[u], pos, p, 0u);
+      }
+    } else if (KIND == 12) {  // the same with the partitions interleaved in chunks of 256 entries (4 KB): all partitions fill at the same
+      // pace, so the stores of any moment fall into one row of chunks (ncur x 4 KB) whatever the total size is
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const unsigned p = (unsigned)(a[u] % ncur);
+        const unsigned pos = atomicAdd(cursors + cstride * p, 1u);
+        out[(((size_t)(pos >> 8) * ncur + p) << 8) + (pos & 255u)] = make_uint4((unsigned)a[u], pos, p, 0u);
+      }
     } else if (KIND == 7) {  // the returning atomic alone
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) acc += atomicAdd(cursors + cstride * (unsigned)(a[u] % ncur), 1u);
@@ -116,6 +145,15 @@ int main() {
   run<7>("global: returning atomic alone, 2048 cursors 32 B apart", table, n16 - 1, cursors, out, sink, sms, mhz, 2048, 8);
   run<8>("global: reduction (no return), 16384 cursors 32 B apart", table, n16 - 1, cursors, out, sink, sms, mhz, 16384, 8);
   run<2>("global: returning atomic on 1 of 131072 cursors (32 B apart) + dependent 16-byte store", table, n16 - 1, cursors, out, sink, sms, mhz, 131072, 8);
+  run<11>("global: returning atomic + dependent store, 16384 partitions over  64 MB", table, (1ull << 22) - 1, cursors, out, sink, sms, mhz, 16384, 8);
+  run<11>("global: returning atomic + dependent store, 16384 partitions over 256 MB", table, (1ull << 24) - 1, cursors, out, sink, sms, mhz, 16384, 8);
+  run<11>("global: returning atomic + dependent store, 16384 partitions over 512 MB", table, (1ull << 25) - 1, cursors, out, sink, sms, mhz, 16384, 8);
+  run<11>("global: returning atomic + dependent store, 16384 partitions over   1 GB", table, (1ull << 26) - 1, cursors, out, sink, sms, mhz, 16384, 8);
+  run<11>("global: returning atomic + dependent store, 16384 partitions over   2 GB", table, (1ull << 27) - 1, cursors, out, sink, sms, mhz, 16384, 8);
+  run<11>("global: returning atomic + dependent store, 16384 partitions over   4 GB", table, (1ull << 28) - 1, cursors, out, sink, sms, mhz, 16384, 8);
+  run<12>("global: returning atomic + dependent store, 16384 partitions interleaved in 4-KB chunks", table, n16 - 1, cursors, out, sink, sms, mhz, 16384, 8);
+  run<9>("global: 16-byte store into 4 GB of partition space alone (16384 partitions)", table, n16 - 1, cursors, out, sink, sms, mhz, 16384, 8);
+  run<10>("global: returning atomic + dependent 16-byte store into 32 MB (16384 partitions)", table, n16 - 1, cursors, out, sink, sms, mhz, 16384, 8);
   run<3>("global: 16-byte store, random slot of a 32-MB table", table, n16 - 1, cursors, out, sink, sms, mhz);
   run<4>("shared: 64-bit load, random word of 32 KB", table, n16 - 1, cursors, out, sink, sms, mhz);
   run<5>("shared: 64-bit compare-and-swap, random word of 32 KB", table, n16 - 1, cursors, out, sink, sms, mhz);
