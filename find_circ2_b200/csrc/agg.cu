@@ -301,9 +301,12 @@ constexpr uint32_t SK_NAME_KNOWN = FC_SK_NAME_KNOWN, SK_NAME_DUP = FC_SK_NAME_DU
 
 // counters (32-bit words at counters + 8): [0] junctions listed, [1] records with another denominator,
 // [2] list overflow / records outside a declared idx range, [3] junctions, [4] set entries that found their partition
-// full, [5] partitions whose shared-memory set ran full (either: the call is repeated with the global set)
-enum { FC_N_ALLOC = 0, FC_N_OTHER = 1, FC_N_OVERFLOW = 2, FC_N_JUNC = 3, FC_N_PART_OVF = 4, FC_N_SET_FULL = 5 };
-constexpr int FC_N_CTR = 6;
+// full, [5] partitions whose shared-memory set ran full (either: the call is repeated with the global set),
+enum { FC_N_ALLOC = 0, FC_N_OTHER = 1, FC_N_OVERFLOW = 2, FC_N_JUNC = 3, FC_N_PART_OVF = 4, FC_N_SET_FULL = 5, FC_N_TABLE_FULL = 6 };
+constexpr int FC_N_CTR = 8;
+// [6] records that found no place for their junction within SLOT_MAX_PROBES slots of a junction table that was sized after
+// the last call's junction count: the call is repeated with the table sized after the record count
+constexpr int SLOT_MAX_PROBES = 64;
 
 __device__ __forceinline__ unsigned long long ext_pack(int q_left, int q_right, unsigned dist, unsigned ov, unsigned n_hits) {
   const unsigned lo = (unsigned)(q_left + 32768) | ((unsigned)(q_right + 32768) << 16);
@@ -449,19 +452,15 @@ __device__ __forceinline__ ulonglong2 lds128(const void* p) {
   return v;
 }
 
-// key (never 0) and partition of the pair (value, tag).  The value is a 64-bit hash already, so x = v ^ t * odd is a
-// bijection of v for every tag and as uniform as v is; the partition mixes x with the tag once more, so two pairs with
-// equal keys and different tags (which need v' = v ^ const, 2^-64 for hashes) still part ways in all but 1/n_parts cases.
+// key (never 0) and partition of the pair (value, tag): two independent 64-bit mixes of the pair.  (The values are hashes
+// already, but the caller's: a cheaper key such as v ^ t * odd makes (v, t) and (t, v) one element when somebody's hashes
+// are small multiples of that constant -- and the kernel's time does not depend on its instruction count, section 4.2.)
 __device__ __forceinline__ unsigned long long part_key(unsigned long long v, unsigned long long t, unsigned int n_parts, unsigned int& part) {
-  const unsigned long long x = v ^ (t * 0x9E3779B97F4A7C15ULL);
-  unsigned int m = (unsigned int)(x >> 32) * 0x85EBCA6Bu ^ (unsigned int)x * 0xC2B2AE35u ^ ((unsigned int)t + (unsigned int)(t >> 32)) * 0x27D4EB2Fu;
-  m ^= m >> 16;
-  m *= 0x85EBCA6Bu;
-  m ^= m >> 13;
-  m *= 0xC2B2AE35u;
-  m ^= m >> 16;
-  part = __umulhi(m, n_parts);
-  return x ? x : 1ull;
+  const unsigned long long tm = fc_mix64(t * 0x9E3779B97F4A7C15ULL + 0x632BE59BD9B4E019ULL);
+  const unsigned long long k = fc_mix64(v ^ tm);
+  const unsigned long long m2 = fc_mix64((v + 0xD1B54A32D192ED03ULL) * 0xA24BAED4963EE407ULL ^ (tm >> 29) ^ (tm << 35));
+  part = __umulhi((unsigned int)(m2 >> 32), n_parts);
+  return k ? k : 1ull;
 }
 // claim a place in the key's partition unless this CTA has sent the same key before and still remembers it (returns
 // false: a repeat).  The memory is a two-way cache with a protected way: a key enters way 1 and moves to way 0 when it comes
@@ -607,10 +606,12 @@ __global__ void __launch_bounds__(ACC_THREADS, FC_ACC_MIN_CTAS) fused_accumulate
       z[0] = z[1] = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
+    // (a junction table that turned out too small: the call is going to be repeated, the chunks left have nothing to do)
+    const bool give_up = *reinterpret_cast<volatile unsigned int*>(&ctr[FC_N_TABLE_FULL]) != 0u;
     int64_t i = c0 + threadIdx.x;
 #pragma unroll 1
     for (int t = 0; t < chunk_tiles; ++t, i += ACC_THREADS) {
-      const bool active = i < n;
+      const bool active = i < n && !give_up;
       const unsigned amask = __ballot_sync(0xffffffffu, active);
       if (!active) continue;  // (trailing lanes of the last tile; the masks below name the active lanes only)
       const uint4* rp = rec_ptr(src, i);
@@ -642,7 +643,13 @@ __global__ void __launch_bounds__(ACC_THREADS, FC_ACC_MIN_CTAS) fused_accumulate
       if ((rel >> FIRST_BITS) != 0ull || (r0.x >> CHROM_BITS) != 0u) atomicAdd(&ctr[FC_N_OTHER], 1u);
       kf = kid | (FIRST_MAX - (rel & FIRST_MAX));
       unsigned long long slot = slot_of(klo, kid, kmask);
-      for (;;) {
+      bool dead = false;  // no place found: the lane goes along (the warp-wide steps below need it) without touching any state
+      for (int probes = 0;; ++probes) {
+        if (probes == SLOT_MAX_PROBES) {
+          atomicAdd(&ctr[FC_N_TABLE_FULL], 1u);
+          dead = true;
+          break;
+        }
         // L1-cached look: the identity never changes once written and the maxima only grow, so a cached copy is as
         // good as the one in L2 (the slot of a popular junction is read by thousands of threads); a cached EMPTY may be
         // stale: the compare-and-swap below then returns the real owner
@@ -667,7 +674,7 @@ __global__ void __launch_bounds__(ACC_THREADS, FC_ACC_MIN_CTAS) fused_accumulate
         slot = (slot + 1ull) & kmask;
       }
       // ---- partitioned distinct counts: claim the places in the partitions now, the answers are used at the very end
-      if (SETS == 1) {
+      if (SETS == 1 && !dead) {
         const unsigned long long tag = (unsigned long long)(unsigned int)slot + 1ull;
         key_r = part_key(read_hash, tag, pv.n_parts, part_r);
         sent_r = part_claim(pv, recent, key_r, part_r, pos_r);
@@ -676,8 +683,9 @@ __global__ void __launch_bounds__(ACC_THREADS, FC_ACC_MIN_CTAS) fused_accumulate
           sent_n = part_claim(pv, recent, key_n, part_n, pos_n);
         }
       }
-      const unsigned int jid = (unsigned int)slot;  // slot number = the junction's id in this call
-      JSlot* a = slots + jid;
+      // slot number = the junction's id in this call (a lane without a slot: a number no slot has, its own in the warp)
+      const unsigned int jid = dead ? 0xFFFFFF00u | lane : (unsigned int)slot;
+      JSlot* a = slots + (dead ? 0u : jid);
       const unsigned long long tag = (unsigned long long)jid + 1ull;  // never 0: no set entry is all-zero
       {
         // new junctions of the warp: one atomic for all of them claims their places in the list
@@ -723,14 +731,14 @@ __global__ void __launch_bounds__(ACC_THREADS, FC_ACC_MIN_CTAS) fused_accumulate
           cx = old;
           want = ext_max(cx, x);
         }
-      } else {
+      } else if (!dead) {
         extrema_to_global(a, kf, x, cur_kf, cur_x);
       }
 
       // ---- distinct reads / fragment names of the junction
       bool new_read = false, new_name = false;
       if (SETS == 0) {
-        set_insert2(sets, smask, read_hash, tag, s_read, !name_known, qname_hash, tag | (1ull << 32), s_name, !prefetch, new_read, new_name);
+        if (!dead) set_insert2(sets, smask, read_hash, tag, s_read, !name_known, qname_hash, tag | (1ull << 32), s_name, !prefetch, new_read, new_name);
       } else {
         // pass 2 decides; a repeat of a key this CTA has sent before is counted as the duplicate it is right here
         new_read = sent_r;
@@ -753,7 +761,7 @@ __global__ void __launch_bounds__(ACC_THREADS, FC_ACC_MIN_CTAS) fused_accumulate
           atomicAdd(&hot.e[he].c0, 1u | (fx << 14));
           if (nb | (unsigned)dup_name) atomicAdd(&hot.e[he].c1, (unsigned)dup_name | (nb << 14));
           if (c2) atomicAdd(&hot.e[he].c2, c2);
-        } else {
+        } else if (!dead) {
           atomicAdd(&a->c0, 1ull | ((unsigned long long)fx << 32));
           if (nb | (unsigned)dup_name) atomicAdd(&a->c1, (unsigned long long)nb | ((unsigned long long)dup_name << 32));
           if (c2) atomicAdd(&a->c2, (unsigned long long)c2);
@@ -772,7 +780,7 @@ __global__ void __launch_bounds__(ACC_THREADS, FC_ACC_MIN_CTAS) fused_accumulate
             atomicAdd(&hot.e[he].c0, group | (w << 14));
             if (b | dups) atomicAdd(&hot.e[he].c1, dups | (b << 14));
             if (c2s) atomicAdd(&hot.e[he].c2, c2s);
-          } else {
+          } else if (!dead) {
             atomicAdd(&a->c0, (unsigned long long)group | ((unsigned long long)w << 32));
             if (b | dups) atomicAdd(&a->c1, (unsigned long long)b | ((unsigned long long)dups << 32));
             if (c2s) atomicAdd(&a->c2, (unsigned long long)c2s);
@@ -979,7 +987,7 @@ __global__ void __launch_bounds__(FINISH_THREADS) finish_dense_kernel(int64_t ra
     // everything the host wants to know, written straight into its (mapped, pinned) memory: no copy to wait for
     ctr[FC_N_JUNC] = s_base + mine;
     __threadfence();
-    for (int k = 0; k < 11; ++k) h_counters[k] = counters[k];
+    for (int k = 0; k < 12; ++k) h_counters[k] = counters[k];
     h_counters[9] = (counters[9] & 0xFFFFFFFFull) | ((unsigned long long)(s_base + mine) << 32);
   }
   if (mine == 0u) return;
@@ -1466,7 +1474,7 @@ struct StageTimer {
 
 // sort-free path over the `ub` (upper bound; the exact count is on the device) records of the context; returns -100
 // when the input needs the sort-based path (a weight denominator that is not 1, 2, 4 or 8; too many records)
-static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st, const RecSrc& src, bool global_set = false) {
+static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st, const RecSrc& src, bool global_set = false, bool full_table = false) {
   fc_agg& a = ctx->agg;
   if (ub >= FUSED_MAX_RECORDS) return -100;
   // junction table: one 64-byte slot per junction, at most one junction per record (load <= 0.8); distinct set: up to two
@@ -1474,6 +1482,17 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st, const Re
   unsigned long long kcap = 1024, scap = 2048;
   while (4ull * kcap < 5ull * (unsigned long long)ub) kcap <<= 1;
   while (scap < 3ull * (unsigned long long)ub) scap <<= 1;
+  // The slots of a call lie all over the table, and a table of gigabytes costs every access a TLB miss on top (measured at
+  // config 3, 426 k junctions: 2.32 ms with the 4-GB table the record count asks for, 1.68 ms with 128 MB).  So a context
+  // that has reduced a batch before sizes the table after that batch's junction count (four times it: load 0.25 when the
+  // next batch is alike); a batch with so many more junctions that records find no place (SLOT_MAX_PROBES) is detected and
+  // reduced again with the full table.
+  if (!full_table && a.nj_hint >= 0) {
+    unsigned long long want = 4ull * (unsigned long long)a.nj_hint + 32768ull, k = 1024;
+    if (const char* e = getenv("FC_AGG_TABLE_HINT")) want = (unsigned long long)atoll(e);  // (tests: a table that is too small)
+    while (k < want) k <<= 1;
+    if (k < kcap) kcap = k;
+  }
   const unsigned int lcap = (unsigned int)ub + 1024u;  // list of the occupied slots (one entry per junction)
   int rc;
   StageTimer tm(ctx, st);
@@ -1601,7 +1620,7 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st, const Re
   // one round trip: exact record count, junction count, fallback conditions, peer-to-peer overflow
   tm.mark("finish");
   unsigned long long* h = a.h_pinned;  // pinned + mapped; the dense finish kernel has already written it
-  if (!dense) FC_CUDA(ctx, cudaMemcpyAsync(h, counters, 11 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  if (!dense) FC_CUDA(ctx, cudaMemcpyAsync(h, counters, 12 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   tm.mark("copy");
   FC_CUDA(ctx, cudaStreamSynchronize(st));
   tm.report();
@@ -1617,8 +1636,15 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st, const Re
     return fc_fail(ctx, FC_E_ARG, "%llu records came without a read-name hash and without fragment fields in their descriptors", h[6]);
   const unsigned int n_other = (unsigned int)(h[8] >> 32), n_overflow = (unsigned int)h[9];
   const int64_t nj = (int64_t)(h[9] >> 32);
-  if (n_overflow) {  // ids ran out, or a record lies outside a declared idx range: its accumulator was not consumed
-    a.f_dirty = true;
+  if (n_overflow) a.f_dirty = true;  // ids ran out, or a record lies outside a declared idx range: its accumulator was not consumed
+  if ((unsigned int)h[11]) {
+    // the junction table was too small for this batch: everything is clean again (the lanes without a slot touched
+    // nothing, the finish pass has consumed what the others did): once more with the table the record count asks for
+    if (tm.print) fprintf(stderr, "[fc_agg_finalize] junction table of %llu slots too small (%u records without a slot): full table\n", kcap, (unsigned)h[11]);
+    a.nj_hint = -1;
+    return finalize_fused(ctx, ub, st, src, global_set, true);
+  }
+  if (n_overflow) {
     a.range_declared = false;
     a.max_idx = ~0ull;
   }
@@ -1629,7 +1655,7 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st, const Re
               (unsigned)h[10], (unsigned)(h[10] >> 32));
     // a partition or its shared-memory set ran full (copies of one element beyond what the caches absorb, or a hash that
     // does not spread): every table is clean again, the call is repeated with the global set
-    return finalize_fused(ctx, ub, st, src, true);
+    return finalize_fused(ctx, ub, st, src, true, full_table);
   }
   if (!dense && nj > 0) {
     uint32_t* vB = vA + ub;
@@ -1639,6 +1665,7 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st, const Re
     FC_LAUNCH_CHECK(ctx);
   }
   a.n_junc = nj;
+  a.nj_hint = nj;
   return nj;
 }
 

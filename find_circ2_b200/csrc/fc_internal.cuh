@@ -85,6 +85,7 @@ struct fc_agg {
   fc_dbuf f_keys, f_sets, f_acc;
   fc_dbuf f_part, f_pcur;       // partitioned distinct counts: entries, fill counts (kept all-zero between calls)
   bool f_dirty = false;
+  int64_t nj_hint = -1;         // junctions of the last batch this context reduced on the sort-free path (-1: none yet)
   cudaStream_t side = nullptr;  // early clear of the distinct set (see clear_sets_early)
   cudaEvent_t ev_side = nullptr, ev_main = nullptr;
   bool timing = false;          // keep the per-stage device times of fc_agg_finalize (fc_agg_set_timing)

@@ -670,3 +670,32 @@ def test_packed_batch_with_fragment_rows_equals_soa_path(torch_cuda, read_len):
     e.scan_batch(batch, out3, 0)
     assert torch.equal(out1, out3)
     e.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sets", ["global", "part"])
+def test_junction_table_sized_after_the_last_batch(monkeypatch, sets):
+    """a context that has reduced a batch sizes its junction table after that batch's junction count (agg.cu: nj_hint); a
+    batch with many more junctions than the table holds must be noticed and reduced again with the full table -- and the
+    calls after it must find clean tables"""
+    monkeypatch.setenv("FC_AGG_SETS", sets)
+    e = _engine()
+    small = _random_records(20000, 50, 21, dens=(1, 2, 4, 8))
+    big = _random_records(300000, 120000, 22, dens=(1, 2, 4, 8))
+    for recs in (small, small, big, big, small):
+        e.agg_reset()
+        e.agg_append_host(recs)
+        nj = e.agg_finalize()
+        got = _junction_rows(e.agg_fetch(nj))
+        want = _py_aggregate(recs)
+        assert len(got) == len(want)
+        for gr, wr in zip(got, want):
+            assert gr == wr, (gr, wr)
+    # a table far too small on purpose (every record runs out of probes at once)
+    monkeypatch.setenv("FC_AGG_TABLE_HINT", "1024")
+    for recs in (big, small):
+        e.agg_reset()
+        e.agg_append_host(recs)
+        nj = e.agg_finalize()
+        assert _junction_rows(e.agg_fetch(nj)) == _py_aggregate(recs)
+    e.close()
