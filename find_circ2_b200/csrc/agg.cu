@@ -812,7 +812,7 @@ __global__ void __launch_bounds__(ACC_THREADS, FC_ACC_MIN_CTAS) fused_accumulate
 // JSlot.c1 high word: fragment names seen before) is collected per junction in a small shared-memory table first -- the
 // repeats belong to the popular junctions -- and flushed once per partition.  The partition's fill count is zeroed on
 // the way out, so the buffers are clean for the next call.
-constexpr int PADD_ENTRIES = 1024;
+constexpr int PADD_ENTRIES = 512;   // (64 KB of set + 6 KB of this table: three CTAs per SM)
 __global__ void __launch_bounds__(PART_THREADS) distinct_parts_kernel(PartView pv, JSlot* __restrict__ slots, unsigned int* __restrict__ ctr) {
   extern __shared__ unsigned long long pset[];  // PSET_ENTRIES
   __shared__ unsigned int a_tag[PADD_ENTRIES], a_c2[PADD_ENTRIES], a_c1[PADD_ENTRIES];
@@ -855,7 +855,7 @@ __global__ void __launch_bounds__(PART_THREADS) distinct_parts_kernel(PartView p
       const unsigned int add1 = (is_name && !fresh) ? 1u : 0u;
       if ((add2 | add1) == 0u) continue;
       const unsigned int jid = e.z & PART_JID;
-      unsigned int s = (jid * 2654435761u) >> (32 - 10);
+      unsigned int s = (jid * 2654435761u) >> (32 - 9);
       bool done = false;
 #pragma unroll 1
       for (int probe = 0; probe < 4 && !done; ++probe) {
@@ -885,7 +885,7 @@ __global__ void __launch_bounds__(PART_THREADS) distinct_parts_kernel(PartView p
     __syncthreads();
   }
 }
-static_assert(PADD_ENTRIES == 1024, "distinct_parts_kernel hashes junctions to 10 bits");
+static_assert(PADD_ENTRIES == 512, "distinct_parts_kernel hashes junctions to 9 bits");
 
 __device__ __forceinline__ fc_junction junction_from_slot(const JSlot& a, unsigned long long first_idx) {
   fc_junction o;
