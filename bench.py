@@ -647,8 +647,8 @@ def bench_config(args, cfg, dist, dev, primary, error_rate=None):
     # DRAM bytes per launch from the one `ncu --set full` capture of this workload (profiles/r02_kernels_ncu_summary_final.txt):
     # only quoted for the launch that was captured (config 3 at full size on one GPU)
     captured = primary and world == 1 and cfg.name == "3" and n == 49037197
-    traffic_scan = 3.600574e9 + 2.856026e9 if captured else None
-    traffic_acc = 2.282065e9 + 0.888959e9 if captured else None
+    traffic_scan = 3.601469e9 + 2.857509e9 if captured else None
+    traffic_acc = 2.269204e9 + 0.883749e9 if captured else None
     achieved = bpp * n / (scan_step * 1e-3) / 1e9
     merge_bytes = 48.0 * n_rec + 64.0 * int(nj)
     acc_achieved = merge_bytes / (max(acc_step_ms, 1e-9) * 1e-3) / 1e9
