@@ -121,3 +121,34 @@ def test_unique_rows_equals_numpy(n, w, vals):
     # order of first appearance
     firsts = [int(np.nonzero(inv == u)[0][0]) for u in range(min(len(uniq), 50))]
     assert firsts == sorted(firsts)
+
+
+def test_read_hash_spreads_over_64_bits():
+    """n_uniq / n_frags compare 64-bit hashes of reads and names (DESIGN.md section 2 has the collision bound, which assumes a
+    hash that spreads): a million distinct reads -- random ones and runs of reads that differ in one base, the shape of real
+    duplicates-with-an-error -- must give a million distinct hashes, strand-invariant, with bit 0 reserved for palindromes and the
+    lower bits balanced"""
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    L, n = 100, 1000000
+    reads = rng.integers(0, 4, (n, L)).astype(np.uint8)
+    base = reads[0].copy()
+    for k in range(1, 300):  # one-base neighbours of one read
+        reads[k] = base
+        reads[k, k % L] = (base[k % L] + 1 + k // L) % 4
+    ascii_ = np.frombuffer(b"ACGT", dtype=np.uint8)[reads]
+    lens = np.full(n, L, dtype=np.int32)
+    h = np.zeros(n, dtype=np.uint64)
+    pal = np.zeros(n, dtype=np.uint8)
+    assert lib.fc_hash_reads_host(n, ascii_.ctypes.data, L, lens.ctypes.data, h.ctypes.data, pal.ctypes.data) == 0
+    assert pal.sum() == 0 and not (h & np.uint64(1)).any()
+    assert len(np.unique(h)) == len(np.unique(ascii_[:, :], axis=0)) == n
+    # the reverse complement of a read is the same element (find_circ.py:588-590)
+    comp = np.frombuffer(b"TGCA", dtype=np.uint8)[reads[:1000, ::-1]]
+    h2 = np.zeros(1000, dtype=np.uint64)
+    assert lib.fc_hash_reads_host(1000, np.ascontiguousarray(comp).ctypes.data, L, lens.ctypes.data, h2.ctypes.data, None) == 0
+    assert np.array_equal(h2, h[:1000])
+    # (the element's hash is the smaller of the hashes of its two strands, so the top bits lean towards 0 -- one bit of the 63
+    # is spent on strand invariance; the tables mix the value again before they use it)
+    bits = ((h[:, None] >> np.arange(1, 56, dtype=np.uint64)[None, :]) & np.uint64(1)).mean(axis=0)
+    assert np.all(np.abs(bits - 0.5) < 0.005), bits
