@@ -14,8 +14,9 @@ from conftest import GOLDEN, ROOT
 from oracle import find_circ_oracle as O
 
 
-def sam_to_bam(sam_path, bam_path):
-    """minimal BAM writer (test helper): one BGZF member per 64 KiB, python's gzip writes valid multi-member files"""
+def sam_to_bam(sam_path, bam_path, bgzf=0):
+    """minimal BAM writer (test helper).  bgzf=0: plain gzip members of 60 kB (valid for every gzip reader, but without the block
+    sizes of BGZF: the library reads it through one zlib stream); bgzf=n: real BGZF with blocks of n bytes"""
     names, lens, recs = [], [], []
     text = ""
     for line in open(sam_path):
@@ -57,8 +58,27 @@ def sam_to_bam(sam_path, bam_path):
         body += qname + b"".join(struct.pack("<I", (n << 4) | o) for n, o in cig) + bytes(sb) + qual + bytes(tags)
         out += struct.pack("<i", len(body)) + body
     with open(bam_path, "wb") as fh:
-        for i in range(0, len(out), 60000):
-            fh.write(gzip.compress(bytes(out[i : i + 60000])))
+        if bgzf:
+            fh.write(bgzf_compress(bytes(out), bgzf))
+        else:
+            for i in range(0, len(out), 60000):
+                fh.write(gzip.compress(bytes(out[i : i + 60000])))
+
+
+def bgzf_compress(data: bytes, block: int = 60000) -> bytes:
+    """BGZF as samtools / htslib write it: gzip members of at most 64 KiB whose extra field 'BC' holds the member's size, closed
+    by the empty end-of-file member"""
+    import zlib
+
+    out = bytearray()
+    for i in list(range(0, len(data), block)) + [None]:
+        chunk = b"" if i is None else data[i : i + block]
+        c = zlib.compressobj(6, zlib.DEFLATED, -15)
+        body = c.compress(chunk) + c.flush()
+        size = 18 + len(body) + 8
+        out += struct.pack("<BBBBIBBHBBHH", 31, 139, 8, 4, 0, 0, 255, 6, ord("B"), ord("C"), 2, size - 1)
+        out += body + struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk))
+    return bytes(out)
 
 
 def test_bam_reader_equals_sam_reader(tmp_path):
@@ -153,3 +173,53 @@ def test_find_circ_process_rare_switches(tmp_path, case_name, tag):
 
     tests = rd(out, "test_results.tsv") if "--test" in argv else None
     H.compare_outputs(got["circs"], got["lins"], got["reads"], got["multi"], counters, ref, argv, tests)
+
+
+@pytest.mark.parametrize("block,threads", [(60000, "1"), (60000, "4"), (700, "3"), (65280, "16")])
+def test_bgzf_on_several_threads_gives_the_same_text(tmp_path, monkeypatch, block, threads):
+    """BAM written as real BGZF is inflated and formatted on several threads (csrc/bam.cu): the SAM text must be the text the
+    one-stream reader gives for the same records, whatever the block size (records straddle members and batches of 512
+    members) and the thread count"""
+    from find_circ2_b200.ingest import BamText
+
+    sam = os.path.join(GOLDEN, "synth_a", "input.sam")
+    big = str(tmp_path / "big.sam")
+    lines = open(sam).read().splitlines(True)
+    head = [ln for ln in lines if ln.startswith("@")]
+    body = [ln for ln in lines if not ln.startswith("@")]
+    with open(big, "w") as fh:
+        fh.writelines(head)
+        for k in range(12):  # ~30 000 records: more than one batch of members at the small block size
+            fh.writelines(ln.replace("\t", "_%d\t" % k, 1) for ln in body)
+    plain, bg = str(tmp_path / "plain.bam"), str(tmp_path / "bgzf.bam")
+    sam_to_bam(big, plain)
+    sam_to_bam(big, bg, bgzf=block)
+    monkeypatch.setenv("FC_BAM_THREADS", threads)
+
+    def text(path, n):
+        t = BamText(path)
+        names = list(t.names)
+        out = []
+        while True:
+            piece = t.read(n)
+            if not piece:
+                break
+            assert piece.endswith(b"\n")
+            out.append(piece)
+        t.close()
+        return names, b"".join(out)
+
+    n1, t1 = text(plain, 1 << 20)
+    n2, t2 = text(bg, 1 << 20)
+    n3, t3 = text(bg, 1 << 16)  # small reads: pieces are cut on line boundaries
+    assert n1 == n2 == n3 and len(t1) > 3000000
+    assert t2 == t1 and t3 == t1
+    # a file that ends inside a member, and one whose member is damaged
+    raw = open(bg, "rb").read()
+    for bad in (raw[: len(raw) // 2], raw[:5000] + bytes([raw[5000] ^ 0x55]) + raw[5001:]):
+        p = str(tmp_path / "bad.bam")
+        open(p, "wb").write(bad)
+        with pytest.raises((IOError, OSError, RuntimeError)):
+            t = BamText(p)
+            while t.read(1 << 20):
+                pass
