@@ -572,7 +572,7 @@ __device__ __forceinline__ unsigned long long slot_of(unsigned long long klo, un
 
 // SETS: 0 = one global set (inputs whose set fits L2), 1 = partitioned (PartView; distinct_parts_kernel follows).
 template <int SETS>
-__global__ void __launch_bounds__(ACC_THREADS, FC_ACC_MIN_CTAS) fused_accumulate_kernel(RecSrc src, int chunk_tiles, int prefetch, unsigned long long idx_base, JSlot* __restrict__ slots,
+__global__ void __launch_bounds__(ACC_THREADS, FC_ACC_MIN_CTAS) fused_accumulate_kernel(RecSrc src, int chunk_tiles, int prefetch, int max_probes, unsigned long long idx_base, JSlot* __restrict__ slots,
                                                                   unsigned long long kmask, U128* __restrict__ sets,
                                                                   unsigned long long smask, PartView pv, unsigned int* __restrict__ list,
                                                                   unsigned int lcap, unsigned int* __restrict__ ctr,
@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(ACC_THREADS, FC_ACC_MIN_CTAS) fused_accumulate
       unsigned long long slot = slot_of(klo, kid, kmask);
       bool dead = false;  // no place found: the lane goes along (the warp-wide steps below need it) without touching any state
       for (int probes = 0;; ++probes) {
-        if (probes == SLOT_MAX_PROBES) {
+        if (probes == max_probes) {  // (only a table sized after the last batch has a limit: the full table always has room)
           atomicAdd(&ctr[FC_N_TABLE_FULL], 1u);
           dead = true;
           break;
@@ -1487,11 +1487,15 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st, const Re
   // that has reduced a batch before sizes the table after that batch's junction count (four times it: load 0.25 when the
   // next batch is alike); a batch with so many more junctions that records find no place (SLOT_MAX_PROBES) is detected and
   // reduced again with the full table.
+  int max_probes = 0x7fffffff;  // the table the record count asks for has room for every junction: probe until found
   if (!full_table && a.nj_hint >= 0) {
     unsigned long long want = 4ull * (unsigned long long)a.nj_hint + 32768ull, k = 1024;
     if (const char* e = getenv("FC_AGG_TABLE_HINT")) want = (unsigned long long)atoll(e);  // (tests: a table that is too small)
     while (k < want) k <<= 1;
-    if (k < kcap) kcap = k;
+    if (k < kcap) {
+      kcap = k;
+      max_probes = SLOT_MAX_PROBES;
+    }
   }
   const unsigned int lcap = (unsigned int)ub + 1024u;  // list of the occupied slots (one entry per junction)
   int rc;
@@ -1564,11 +1568,11 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st, const Re
     const int prefetch = (size_t)scap * 16 <= ((size_t)64 << 20) ? 1 : 0;
     if (part) FC_CUDA(ctx, cudaFuncSetAttribute(fused_accumulate_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * RECENT_SETS * 8));
     if (part)
-      fused_accumulate_kernel<1><<<grid, ACC_THREADS, 2 * RECENT_SETS * 8, st>>>(src, chunk_tiles, 0, idx_base, (JSlot*)a.f_keys.p, kcap - 1, nullptr, 0ull, pv,
+      fused_accumulate_kernel<1><<<grid, ACC_THREADS, 2 * RECENT_SETS * 8, st>>>(src, chunk_tiles, 0, max_probes, idx_base, (JSlot*)a.f_keys.p, kcap - 1, nullptr, 0ull, pv,
                                                                (unsigned int*)a.f_acc.p, lcap, ctr, (uint4*)flag, (range + 3) / 4,
                                                                tile_count, n_tiles);
     else
-      fused_accumulate_kernel<0><<<grid, ACC_THREADS, 0, st>>>(src, chunk_tiles, prefetch, idx_base, (JSlot*)a.f_keys.p, kcap - 1,
+      fused_accumulate_kernel<0><<<grid, ACC_THREADS, 0, st>>>(src, chunk_tiles, prefetch, max_probes, idx_base, (JSlot*)a.f_keys.p, kcap - 1,
                                                                (U128*)a.f_sets.p, scap - 1, pv, (unsigned int*)a.f_acc.p, lcap, ctr,
                                                                (uint4*)flag, (range + 3) / 4, tile_count, n_tiles);
   }
@@ -1637,6 +1641,8 @@ static int64_t finalize_fused(fc_ctx* ctx, int64_t ub, cudaStream_t st, const Re
   const unsigned int n_other = (unsigned int)(h[8] >> 32), n_overflow = (unsigned int)h[9];
   const int64_t nj = (int64_t)(h[9] >> 32);
   if (n_overflow) a.f_dirty = true;  // ids ran out, or a record lies outside a declared idx range: its accumulator was not consumed
+  if ((unsigned int)h[11] && max_probes == 0x7fffffff)
+    return fc_fail(ctx, FC_E_STATE, "junction table: no free slot in a table with room for every record (internal error)");
   if ((unsigned int)h[11]) {
     // the junction table was too small for this batch: everything is clean again (the lanes without a slot touched
     // nothing, the finish pass has consumed what the others did): once more with the table the record count asks for
