@@ -25,7 +25,6 @@ import random
 import sys
 from optparse import OptionParser
 
-import numpy as np
 
 from . import samio
 
@@ -84,9 +83,15 @@ class Anchors(object):
             raise ValueError("read %s has no sequence or no qualities" % qname)
         a = self.asize
         seq, qual = self.read_f(seq), self.read_f(qual)
-        nq = np.frombuffer(qual.encode("latin-1"), dtype=np.uint8) - np.uint8(35)  # wraps below '#', like the reference
-        if nq[:a].mean() < self.minqual or nq[-a:].mean() < self.minqual:
-            return
+        # mean of (quality byte - 35) as unsigned bytes over either anchor: the subtraction wraps below '#', like the reference's
+        # numpy arithmetic (unmapped2anchors.py:100-104); plain integer sums, no array per read
+        qb = qual.encode("latin-1")
+        head, tail = qb[:a], qb[-a:]
+        if head and tail:  # (an empty read: numpy's mean is nan there, which is not smaller than anything)
+            sh = sum(head) - 35 * len(head) + (256 * sum(1 for c in head if c < 35) if min(head) < 35 else 0)
+            st = sum(tail) - 35 * len(tail) + (256 * sum(1 for c in tail if c < 35) if min(tail) < 35 else 0)
+            if sh < self.minqual * len(head) or st < self.minqual * len(tail):
+                return
         if self.rev == "P":
             self.pool_a.append((seq[:a], qual[:a]))
             self.pool_b.append((seq[-a:], qual[-a:]))
@@ -134,9 +139,33 @@ def main(argv=None, out=None):
             for n, (name, seq) in enumerate(fasta_records(fh), 1):
                 anchors.handle("%s_%d" % (name.replace(" ", "_"), n), seq, "b" * len(seq))
     else:
-        _names, _lengths, records = samio.open_alignments(args[0])
-        for r in records:
-            anchors.handle(r.qname, r.seq, r.qual, r.is_unmapped)
+        bam_text = None
+        if not args[0].endswith("sam"):
+            # BAM through the C++ reader (csrc/bam.cu: BGZF inflated on several threads, records as SAM text lines); without the
+            # library (a machine that only cuts anchors) the python reader does the same
+            try:
+                from .ingest import BamText
+
+                bam_text = BamText(args[0])
+            except (OSError, ImportError, RuntimeError):
+                bam_text = None
+        if bam_text is not None:
+            try:
+                while True:
+                    chunk = bam_text.read(16 << 20)
+                    if not chunk:
+                        break
+                    for line in chunk.decode("latin-1").split("\n"):
+                        if not line:
+                            continue
+                        f = line.split("\t", 11)
+                        anchors.handle(f[0], None if f[9] == "*" else f[9], None if f[10] == "*" else f[10], (int(f[1]) & 4) != 0)
+            finally:
+                bam_text.close()
+        else:
+            _names, _lengths, records = samio.open_alignments(args[0])
+            for r in records:
+                anchors.handle(r.qname, r.seq, r.qual, r.is_unmapped)
     anchors.finish()
     return 0
 
