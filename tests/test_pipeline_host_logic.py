@@ -158,3 +158,46 @@ def test_bam_text_stream_errors_and_close(tmp_path):
     b.close()
     with pytest.raises(IOError):
         BamText(sam)  # not a BAM file
+
+
+@pytest.mark.parametrize("threads", [1, 3])
+def test_native_ingest_chunk_boundaries_and_a_fragment_larger_than_the_head_room(tmp_path, threads):
+    """process_native reads the stream in chunks behind 1 MB of head room for the unfinished fragment a chunk leaves over.
+    Small chunks put many fragments across boundaries; one fragment of 1.3 MB of text (thousands of unmapped records under
+    one name) does not fit the head room and takes the concatenating way.  Outputs must equal those of the
+    python ingest on the same file."""
+    from conftest import GOLDEN
+    from find_circ2_b200 import cli, pipeline, samio
+
+    case_dir = os.path.join(GOLDEN, "synth_a")
+    lines = open(os.path.join(case_dir, "input.sam")).read().splitlines(True)
+    head = [ln for ln in lines if ln.startswith("@")]
+    body = [ln for ln in lines if not ln.startswith("@")]
+    # (one mapped record, then thousands of unmapped ones under the same name: counted and skipped, find_circ.py:1466-1467)
+    first = [ln for ln in body if ln.split("\t")[2] != "*"][0]
+    unmapped = "giant\t4\t*\t0\t0\t*\t*\t0\t0\t" + "ACGT" * 25 + "\t" + "I" * 100 + "\n"
+    giant = ["giant\t" + first.split("\t", 1)[1]] + [unmapped] * (1300000 // len(unmapped))
+    sam = str(tmp_path / "with_giant.sam")
+    with open(sam, "w") as fh:
+        fh.writelines(head + body[:3000] + giant + body[3000:])
+    argv = ["-a", "15", "-n", "t", "-q"]
+    outs = []
+    for native in (False, True):
+        opt = cli.parse_args(["-G", os.path.join(case_dir, "genome.fa")] + argv)[0]
+        opt.batch_pairs, opt.ingest_threads, opt.ingest_piece_bytes = 211, threads, 1 << 15
+        eng = FakeEngine(0, opt.asize, opt.margin, opt.maxdist, opt.noncanonical, opt.strandpref)
+        eng.load_genome_fasta(opt.genome)
+        if not native:
+            outs.append(cli.run_to_strings(opt, sam, engine=eng, native=False))
+            continue
+        names = samio.sam_header_names(sam)
+        run = pipeline.Run(opt, names, eng)
+        with open(sam, "rb") as fh:
+            run.process_native(fh, chunk_bytes=200000)
+        run.finalize()
+        outs.append({"circ": run.bed_text(0), "lin": run.bed_text(1), "reads": run.reads_text(), "multi": run.multi_text(),
+                     "counters": run.counters_text()})
+        run.close()
+    for k in ("circ", "lin", "reads", "multi", "counters"):
+        assert outs[0][k] == outs[1][k], k
+    assert outs[1]["circ"].count("\n") > 5
